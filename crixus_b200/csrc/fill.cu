@@ -1,0 +1,745 @@
+// crixus_b200 -- fill_fluid (box) and fill_fluid_complex (geometry) on the dr lattice.
+// Reference: /root/reference/src/crixus_d.cu:680-744 (box), :753-963 (checkTriangleCollision, checkCollision),
+// :965-1058 (fill_fluid_complex, one full-grid sweep per launch, looped up to 10 000 times by crixus.cu:934-947).
+//
+// The fill result is the least fixed point of "s unset, a 6-neighbour e set, !checkCollision(s,e) => set s"
+// (SURVEY.md A.6), so any schedule reaches the same bits.  B200 mapping (DESIGN.md "fill"):
+//   * the packed reference bitfield is unpacked to a row-aligned layout (x-rows padded to 32-bit words);
+//   * a classification pass marks the cells whose test can be non-trivial ("hard": a non-empty 27-cell
+//     neighbourhood in the 3dr grid, or close to a free-surface triangle).  For every other cell
+//     checkCollision is provably false, so propagation is pure bit arithmetic on 32-cell words;
+//   * tiles of 1 word x 16 x 16 rows are iterated to local convergence in shared memory; hard candidates are
+//     compacted into a shared-memory queue and evaluated warp-cooperatively (lanes stride the cell-sorted
+//     segments of the 27 neighbour cells, all open directions of a cell share the distance computation);
+//     failed directed tests are memoised in 6 "blocked" bit planes so that no pair is tested twice;
+//   * a tile that changed activates its 6 face neighbours for the next round; rounds continue until no tile is
+//     active.  Only active tiles are touched: work ~ filled volume + wall area, not sweeps x grid.
+// Bound: HBM, 0.25 B/cell + 8 B/filled cell -- in practice latency/round bound.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+
+#define FT_Y 16
+#define FT_Z 16
+#define FT_THREADS (FT_Y * FT_Z)
+#define FT_QCAP 1024
+#define FS_MAX_DESC 512
+
+// ================================================================================================ box fill
+// crixus_d.cu:686-717.  One thread per packed 32-bit word; nfi counts every in-box cell (even if already set).
+struct BoxArgs {
+  int64_t dimg[3];
+  uint32_t mn[3], dim[3];
+};
+
+__global__ void __launch_bounds__(256) k_fill_box(uint32_t *__restrict__ fpos, BoxArgs b, int64_t nwords, unsigned long long *nfi)
+{
+  unsigned long long cnt = 0;
+  const int64_t G = b.dimg[0] * b.dimg[1] * b.dimg[2], plane = b.dimg[0] * b.dimg[1];
+  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < nwords; wi += (int64_t)gridDim.x * blockDim.x) {
+    int64_t bit0 = wi * 32;
+    int64_t k = bit0 / plane, rem = bit0 - k * plane;
+    int64_t j = rem / b.dimg[0], i = rem - j * b.dimg[0];
+    uint32_t m = 0;
+    for (int ii = 0; ii < 32 && bit0 + ii < G; ii++) {
+      const uint32_t ui = (uint32_t)i, uj = (uint32_t)j, uk = (uint32_t)k;
+      if (ui >= b.mn[0] && uj >= b.mn[1] && uk >= b.mn[2] && ui - b.mn[0] < b.dim[0] && uj - b.mn[1] < b.dim[1] &&
+          uk - b.mn[2] < b.dim[2]) {
+        m |= 1u << ii;
+        cnt++;
+      }
+      if (++i == b.dimg[0]) { i = 0; if (++j == b.dimg[1]) { j = 0; k++; } }
+    }
+    if (m) fpos[wi] |= m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nfi, cnt);
+}
+
+extern "C" int cx_fill_box(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float lo[3], const float hi[3], int64_t *nfi_host)
+{
+  if (!ctx || !p || !fpos_d || !lo || !hi) return CX_WRONG_INPUT;
+  BoxArgs b;
+  cx_fill_dims(p, b.dimg);
+  const float eps = p->eps, dr = p->dr;
+  for (int j = 0; j < 3; j++) {
+    b.dim[j] = (uint32_t)(floorf((hi[j] + eps - lo[j]) / dr) + 1);  // crixus_d.cu:686-688
+    const double r = round(((float)(uint32_t)b.dimg[j] - 1.) * (lo[j] - p->fcmin[j]) / (p->fcmax[j] - p->fcmin[j]));  // :694-696
+    b.mn[j] = r < 0 ? 0xffffffffu : (uint32_t)r;
+  }
+  const int64_t G = b.dimg[0] * b.dimg[1] * b.dimg[2], nwords = (G + 31) / 32;
+  unsigned long long *cnt = (unsigned long long *)(ctx->d_mail + 20);
+  CX_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int64_t), ctx->stream));
+  k_fill_box<<<cx_blocks(nwords, 256, ctx->num_sms * 16), 256, 0, ctx->stream>>>(fpos_d, b, nwords, cnt);
+  CX_LAUNCH_CHECK(ctx, "k_fill_box");
+  if (nfi_host) {
+    CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 20, cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *nfi_host = ctx->h_mail[20];
+  }
+  return CX_OK;
+}
+
+// ================================================================================================ geometry fill
+// conservative description of a free-surface (fshape) triangle, used only to decide which cells are "hard"
+struct FsDesc {
+  float lo[3], hi[3];  // bounding box grown by the margin outside of which checkTriangleCollision cannot be true
+  float n[3], v0[3];   // plane, for the "ray in plane => collision" rule (crixus_d.cu:766-769)
+  int quirk;           // some axis direction can be parallel to the plane within eps
+};
+
+struct FillArgs {
+  cx_params p;
+  const float4 *pos;
+  const float4 *norm;
+  const int4 *ep;
+  const int32_t *cell_idx;
+  int64_t nbe, cnbe;
+  int dimg[3];       // lattice size
+  int wr;            // words per x-row
+  int ty, tz;        // tile counts in y and z
+  int64_t ntiles;    // wr * ty * tz
+  int k_lo, k_hi;    // owned planes [k_lo, k_hi): only these are written (z-slab sharding)
+  uint32_t *F;       // row-aligned filled bits, wr*dimg[1]*dimg[2] words
+  uint32_t *H;       // hard mask, same shape
+  uint32_t *B;       // 6 blocked planes, same shape each (direction d at B + d*nw)
+  int64_t nw;        // words per plane set
+  const uint8_t *nbflag;  // per 3dr-cell: 27-neighbourhood contains a segment
+  const FsDesc *fs;       // fshape descriptors
+  int nfs, all_hard;
+  uint8_t *act_cur, *act_next;  // tile activation flags
+  int32_t *list;                // active tile list
+  int32_t *count;               // [0] = list length, [1] = cursor
+  unsigned long long *changed;  // newly set cells
+  int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
+  int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
+  float drw2;                   // dr_wall*dr_wall
+  double one_eps;               // 1.0 + eps (double, crixus_d.cu:774)
+};
+
+// ---- the reference's directed test, warp-cooperative -------------------------------------------------------------
+// checkTriangleCollision, crixus_d.cu:753-799
+__device__ __forceinline__ bool tri_collision(const FillArgs &A, f3 s, f3 dir, f3 n, f3 v0, f3 v1, f3 v2)
+{
+  const float eps = A.p.eps;
+  const f3 u = sub3(v1, v0), v = sub3(v2, v0), w0 = sub3(s, v0);
+  const float a = -dot3_r3(n, w0), b = dot3_r3(n, dir);
+  if (fabsf(b) < eps) return fabsf(a) < eps;
+  const float r = __fdiv_rn(a, b);
+  if (r < -eps || (double)r > A.one_eps) return false;
+  const f3 w = mk3(fsub(ffma(r, dir.x, s.x), v0.x), fsub(ffma(r, dir.y, s.y), v0.y), fsub(ffma(r, dir.z, s.z), v0.z));
+  const float uu = dot3_r3(u, u), uv = dot3_r3(u, v), vv = dot3_r3(v, v), wu = dot3_r3(w, u), wv = dot3_r3(w, v);
+  const float D = det_r2(uv, uv, uu, vv);
+  const float t1 = __fdiv_rn(det_r2(uv, wv, vv, wu), D);
+  if (t1 < -eps || (double)t1 > A.one_eps) return false;
+  const float t2 = __fdiv_rn(det_r2(uv, wu, uu, wv), D);
+  if (t2 < -eps || (double)fadd(t1, t2) > A.one_eps) return false;
+  return true;
+}
+
+// squared distance from s to triangle (v0,v1,v2) exactly as crixus_d.cu:859-939 computes it
+__device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0, f3 v1, f3 v2)
+{
+  const float eps = A.p.eps;
+  const f3 segpos = mk3(__fdiv_rn(fadd(fadd(v0.x, v1.x), v2.x), 3.0f), __fdiv_rn(fadd(fadd(v0.y, v1.y), v2.y), 3.0f),
+                        __fdiv_rn(fadd(fadd(v0.z, v1.z), v2.z), 3.0f));
+  f3 nr[3];
+  const f3 vv[3] = {v0, v1, v2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const f3 a = vv[k], b = vv[(k + 1) % 3];
+    f3 ed = sub3(b, a);
+    const float len = __fsqrt_rn(dot3_r3(ed, ed));
+    ed = mk3(__fdiv_rn(ed.x, len), __fdiv_rn(ed.y, len), __fdiv_rn(ed.z, len));
+    const f3 sv = sub3(segpos, a);
+    const float d = dot3_r3(ed, sv);
+    nr[k] = mk3(ffma(-ed.x, d, sv.x), ffma(-ed.y, d, sv.y), ffma(-ed.z, d, sv.z));
+  }
+  const f3 sm = sub3(s, segpos);
+  const float pd = dot3_r3(sm, n);
+  const f3 pp = mk3(ffma(-n.x, pd, sm.x), ffma(-n.y, pd, sm.y), ffma(-n.z, pd, sm.z));
+  float o[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) o[k] = dot3_r3(sub3(add3(pp, segpos), vv[k]), nr[k]);
+  f3 t;
+  if (o[0] > -eps && o[1] > -eps && o[2] > -eps) t = sub3(pp, sm);
+  else if (o[0] < eps && o[1] < eps) t = sub3(s, v2);
+  else if (o[1] < eps && o[2] < eps) t = sub3(s, v0);
+  else if (o[2] < eps && o[0] < eps) t = sub3(s, v1);
+  else {
+    f3 x1, x2;
+    if (o[0] < eps) { x1 = v0; x2 = v1; }
+    else if (o[1] < eps) { x1 = v1; x2 = v2; }
+    else { x1 = v2; x2 = v0; }
+    const f3 x21 = sub3(x2, x1), sx1 = sub3(s, x1);
+    const float td = dot3_r3(x21, sx1), l2 = dot3_r3(x21, x21);
+    t = mk3(ffma(-__fdiv_rn(x21.x, l2), td, sx1.x), ffma(-__fdiv_rn(x21.y, l2), td, sx1.y), ffma(-__fdiv_rn(x21.z, l2), td, sx1.z));
+  }
+  return dot3_r3(t, t);
+}
+
+// checkCollision (crixus_d.cu:801-963) for cell s=(si,sj,sk) and every direction in dmask at once (bit d: 0:-x 1:+x
+// 2:-y 3:+y 4:-z 5:+z, the reference's neighbour order).  Called by a full warp; returns the directions that collide.
+__device__ uint32_t warp_check_collision(const FillArgs &A, int si, int sj, int sk, uint32_t dmask, int lane)
+{
+  const cx_params &p = A.p;
+  const float dr = p.dr, eps = p.eps;
+  const int sidx[3] = {si, sj, sk};
+  float sc[3], ec[6], dirc[6], infl[6], midc[6], mids[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    sc[a] = ffma((float)sidx[a], dr, p.fcmin[a]);  // crixus_d.cu:805-807 (R5)
+    mids[a] = fadd(sc[a], sc[a]);
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    const int a = d >> 1;
+    ec[d] = ffma((float)(sidx[a] + ((d & 1) ? 1 : -1)), dr, p.fcmin[a]);
+    dirc[d] = fsub(ec[d], sc[a]);
+    const float hd = fmul(fsub(sc[a], ec[d]), 0.5f);  // (s-e)/2.0f; the two other components are exactly +0
+    const f3 hv = mk3(a == 0 ? hd : 0.f, a == 1 ? hd : 0.f, a == 2 ? hd : 0.f);
+    float l = dot3_r3(hv, hv);
+    l = __fsqrt_rn(l);
+    float r = fadd(ffma(dr, 3.0f, l), p.dr_wall);  // crixus_d.cu:815 (R6)
+    infl[d] = fmul(r, r);
+    midc[d] = fadd(sc[a], ec[d]);
+  }
+  const f3 s = mk3(sc[0], sc[1], sc[2]);
+  const int gx = cell_coord(sc[0], p.dmin[0], p.griddr[0], p.gridn[0]);
+  const int gy = cell_coord(sc[1], p.dmin[1], p.griddr[1], p.gridn[1]);
+  const int gz = cell_coord(sc[2], p.dmin[2], p.griddr[2], p.gridn[2]);
+  uint32_t coll = 0;
+  for (int c27 = 0; c27 < 27 && coll != dmask; c27++) {
+    const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
+    if (c < 0) continue;
+    const int b = __ldg(&A.cell_idx[c]), e = __ldg(&A.cell_idx[c + 1]);
+    for (int base = b; base < e && coll != dmask; base += 32) {
+      const int i = base + lane;
+      uint32_t mine = 0;
+      if (i < e) {
+        const f3 n = mk3(__ldg(&A.norm[i]));
+        const int4 E = __ldg(&A.ep[i]);
+        const f3 v0 = mk3(__ldg(&A.pos[E.x])), v1 = mk3(__ldg(&A.pos[E.y])), v2 = mk3(__ldg(&A.pos[E.z]));
+        uint32_t pass = 0;
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+          if (!((dmask & ~coll) >> d & 1)) continue;
+          const int a = d >> 1;
+          const f3 t = mk3(ffma(a == 0 ? midc[d] : mids[0], 0.5f, -v0.x), ffma(a == 1 ? midc[d] : mids[1], 0.5f, -v0.y),
+                           ffma(a == 2 ? midc[d] : mids[2], 0.5f, -v0.z));
+          if (!(dot3_r3(t, t) > infl[d])) pass |= 1u << d;  // crixus_d.cu:855-857
+        }
+        if (pass) {
+          const float dist = tri_dist2(A, s, n, v0, v1, v2);
+          if (fadd(dist, eps) < A.drw2) mine = pass;  // crixus_d.cu:940
+          else {
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+              if (!(pass >> d & 1)) continue;
+              const int a = d >> 1;
+              const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
+              if (tri_collision(A, s, dir, n, v0, v1, v2)) mine |= 1u << d;
+            }
+          }
+        }
+      }
+      coll |= __reduce_or_sync(0xffffffffu, mine);
+    }
+  }
+  // free-surface triangles: all of them, segment test only (crixus_d.cu:951-960)
+  for (int64_t base = A.nbe - A.cnbe; base < A.nbe && coll != dmask; base += 32) {
+    const int64_t i = base + lane;
+    uint32_t mine = 0;
+    if (i < A.nbe) {
+      const f3 n = mk3(__ldg(&A.norm[i]));
+      const int4 E = __ldg(&A.ep[i]);
+      const f3 v0 = mk3(__ldg(&A.pos[E.x])), v1 = mk3(__ldg(&A.pos[E.y])), v2 = mk3(__ldg(&A.pos[E.z]));
+#pragma unroll
+      for (int d = 0; d < 6; d++) {
+        if (!((dmask & ~coll) >> d & 1)) continue;
+        const int a = d >> 1;
+        const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
+        if (tri_collision(A, s, dir, n, v0, v1, v2)) mine |= 1u << d;
+      }
+    }
+    coll |= __reduce_or_sync(0xffffffffu, mine);
+  }
+  return coll & dmask;
+}
+
+// ---- preparation kernels ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell3_flags(cx_params p, const int32_t *__restrict__ cell_idx, uint8_t *__restrict__ flag)
+{
+  const int64_t n = p.gridn[3];
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((int64_t)p.gridn[2] * p.gridn[1]));
+    int any = 0;
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int64_t q = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
+      if (q >= 0 && cell_idx[q + 1] > cell_idx[q]) { any = 1; break; }
+    }
+    flag[c] = (uint8_t)any;
+  }
+}
+
+// packed (reference) layout -> row-aligned words; marks tiles that contain set bits as active
+__global__ void __launch_bounds__(256) k_unpack(FillArgs A, const uint32_t *__restrict__ fpos)
+{
+  const int64_t rows = (int64_t)A.dimg[1] * A.dimg[2];
+  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = wi / A.wr;
+    const int wx = (int)(wi - row * A.wr);
+    if (row >= rows) continue;
+    const int64_t b0 = row * A.dimg[0] + (int64_t)wx * 32;
+    const int nvalid = min(32, A.dimg[0] - wx * 32);
+    const int64_t w0 = b0 >> 5;
+    const int sh = (int)(b0 & 31);
+    uint32_t v = fpos[w0] >> sh;
+    if (sh && sh + nvalid > 32) v |= fpos[w0 + 1] << (32 - sh);
+    if (nvalid < 32) v &= (1u << nvalid) - 1u;
+    uint32_t fresh_bits = v;
+    if (A.merge) {
+      const uint32_t old = A.F[wi];
+      fresh_bits = v & ~old;
+      v |= old;
+    }
+    A.F[wi] = v;
+    if (fresh_bits) {
+      const int j = (int)(row % A.dimg[1]), k = (int)(row / A.dimg[1]);
+      A.act_cur[((int64_t)(k / FT_Z) * A.ty + j / FT_Y) * A.wr + wx] = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pack(FillArgs A, uint32_t *__restrict__ fpos)
+{
+  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = A.F[wi];
+    if (!v) continue;
+    const int64_t row = wi / A.wr;
+    const int wx = (int)(wi - row * A.wr);
+    const int k = (int)(row / A.dimg[1]);
+    if (k < A.k_lo || k >= A.k_hi) continue;
+    const int64_t b0 = row * A.dimg[0] + (int64_t)wx * 32;
+    const int64_t w0 = b0 >> 5;
+    const int sh = (int)(b0 & 31);
+    atomicOr(&fpos[w0], v << sh);
+    if (sh && (v >> (32 - sh))) atomicOr(&fpos[w0 + 1], v >> (32 - sh));
+  }
+}
+
+// hard mask: cell needs the real test (otherwise checkCollision(s, .) is false for every direction)
+__global__ void __launch_bounds__(256) k_classify(FillArgs A)
+{
+  const cx_params &p = A.p;
+  const int64_t rows = (int64_t)A.dimg[1] * A.dimg[2];
+  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = wi / A.wr;
+    const int wx = (int)(wi - row * A.wr);
+    if (row >= rows) continue;
+    const int j = (int)(row % A.dimg[1]), k = (int)(row / A.dimg[1]);
+    const int nvalid = min(32, A.dimg[0] - wx * 32);
+    uint32_t h = 0;
+    if (A.all_hard) h = 0xffffffffu;
+    else {
+      const float sy = ffma((float)j, p.dr, p.fcmin[1]), sz = ffma((float)k, p.dr, p.fcmin[2]);
+      const int gy = cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]), gz = cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]);
+      for (int b = 0; b < nvalid; b++) {
+        const float sx = ffma((float)(wx * 32 + b), p.dr, p.fcmin[0]);
+        const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
+        int hard = A.nbflag[((int64_t)gx * p.gridn[1] + gy) * p.gridn[2] + gz];
+        for (int t = 0; t < A.nfs && !hard; t++) {
+          const FsDesc &f = A.fs[t];
+          if (sx >= f.lo[0] && sx <= f.hi[0] && sy >= f.lo[1] && sy <= f.hi[1] && sz >= f.lo[2] && sz <= f.hi[2]) hard = 1;
+          else if (f.quirk) {
+            const float a = f.n[0] * (sx - f.v0[0]) + f.n[1] * (sy - f.v0[1]) + f.n[2] * (sz - f.v0[2]);
+            if (fabsf(a) < 4.f * p.eps) hard = 1;
+          }
+        }
+        h |= (uint32_t)hard << b;
+      }
+    }
+    if (nvalid < 32) h &= (1u << nvalid) - 1u;
+    A.H[wi] = h;
+  }
+}
+
+__global__ void k_seed(FillArgs A, int64_t seed)
+{
+  if (seed < 0) return;
+  const int64_t plane = (int64_t)A.dimg[0] * A.dimg[1];
+  const int k = (int)(seed / plane), j = (int)((seed % plane) / A.dimg[0]), i = (int)(seed % A.dimg[0]);
+  const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + (i >> 5);
+  const uint32_t bit = 1u << (i & 31);
+  if (k >= A.k_lo && k < A.k_hi && !(A.F[wi] & bit)) {  // crixus_d.cu:972-980: counted only if it was unset
+    A.F[wi] |= bit;
+    atomicAdd(A.changed, 1ull);
+  }
+  A.act_cur[((int64_t)(k / FT_Z) * A.ty + j / FT_Y) * A.wr + (i >> 5)] = 1;
+}
+
+// ---- one round -------------------------------------------------------------------------------------------------
+__global__ void k_round_prep(int32_t *count) { count[0] = 0; count[1] = 0; }
+
+__global__ void __launch_bounds__(256) k_build_list(FillArgs A)
+{
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < A.ntiles; t += (int64_t)gridDim.x * blockDim.x)
+    if (A.act_cur[t]) {
+      A.act_cur[t] = 0;
+      A.list[atomicAdd(&A.count[0], 1)] = (int32_t)t;
+    }
+}
+
+struct TileSM {
+  uint32_t F[FT_Z + 2][FT_Y + 2];  // filled, with y/z halo
+  uint32_t XL[FT_Z][FT_Y];         // word to the left (only bit 31 is used) / right (bit 0)
+  uint32_t XR[FT_Z][FT_Y];
+  uint32_t H[FT_Z][FT_Y];
+  uint32_t B[6][FT_Z][FT_Y];
+  uint32_t Q[FT_QCAP];             // hard candidates: (dmask << 16) | (bit << 8) | word
+  int qn, changed, anyhard, bdirty, overflow;
+  uint32_t newbits;
+};
+
+__global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
+{
+  __shared__ TileSM S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ly = tid % FT_Y, lz = tid / FT_Y;
+  for (;;) {
+    __shared__ int s_t;
+    if (tid == 0) {
+      const int q = atomicAdd(&A.count[1], 1);
+      s_t = q < A.count[0] ? A.list[q] : -1;
+    }
+    __syncthreads();
+    const int tile = s_t;
+    if (tile < 0) break;
+    const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
+    const int j0 = tyi * FT_Y, k0 = tzi * FT_Z;
+    const int nvalid = min(32, A.dimg[0] - wx * 32);
+    const uint32_t vmask = nvalid < 32 ? (1u << nvalid) - 1u : 0xffffffffu;
+    // ---- load (halo rows outside the lattice read as 0)
+    for (int h = tid; h < (FT_Z + 2) * (FT_Y + 2); h += FT_THREADS) {
+      const int hz = h / (FT_Y + 2), hy = h % (FT_Y + 2);
+      const int j = j0 + hy - 1, k = k0 + hz - 1;
+      uint32_t v = 0;
+      if (j >= 0 && j < A.dimg[1] && k >= 0 && k < A.dimg[2]) v = A.F[((int64_t)k * A.dimg[1] + j) * A.wr + wx];
+      S.F[hz][hy] = v;
+    }
+    const int j = j0 + ly, k = k0 + lz;
+    const bool inrow = j < A.dimg[1] && k < A.dimg[2];
+    const bool owned = inrow && k >= A.k_lo && k < A.k_hi;
+    const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
+    uint32_t hmask = 0;
+    {
+      uint32_t xl = 0, xr = 0;
+      if (inrow) {
+        if (wx > 0) xl = A.F[wi - 1];
+        if (wx + 1 < A.wr) xr = A.F[wi + 1];
+        hmask = A.H[wi];
+      }
+      S.XL[lz][ly] = xl; S.XR[lz][ly] = xr; S.H[lz][ly] = hmask;
+    }
+    if (tid == 0) { S.anyhard = 0; S.bdirty = 0; S.newbits = 0; }
+    __syncthreads();
+    if (hmask) S.anyhard = 1;
+    __syncthreads();
+    const bool anyhard = S.anyhard != 0;
+    if (anyhard) {
+#pragma unroll
+      for (int d = 0; d < 6; d++) S.B[d][lz][ly] = inrow ? A.B[d * A.nw + wi] : 0u;
+    }
+    const uint32_t f_start = S.F[lz + 1][ly + 1];
+    __syncthreads();
+
+    // ---- iterate to local convergence (bounded: every iteration sets a bit or resolves queued candidates)
+    for (int iter = 0; iter < 200000; iter++) {
+      if (tid == 0) { S.qn = 0; S.changed = 0; S.overflow = 0; }
+      __syncthreads();
+      if (owned) {
+        uint32_t f = S.F[lz + 1][ly + 1];
+        const uint32_t nb_xm = (f << 1) | (S.XL[lz][ly] >> 31);  // neighbour at i-1 is set
+        const uint32_t nb_xp = (f >> 1) | (S.XR[lz][ly] << 31);
+        const uint32_t nb_ym = S.F[lz + 1][ly], nb_yp = S.F[lz + 1][ly + 2];
+        const uint32_t nb_zm = S.F[lz][ly + 1], nb_zp = S.F[lz + 2][ly + 1];
+        const uint32_t open = vmask & ~hmask;
+        uint32_t nf = f | ((nb_xm | nb_xp | nb_ym | nb_yp | nb_zm | nb_zp) & open);
+        // free propagation along x inside the word through easy cells
+        for (;;) {
+          const uint32_t g = (((nf << 1) | (nf >> 1)) & open) & ~nf;
+          if (!g) break;
+          nf |= g;
+        }
+        if (nf != f) {
+          S.F[lz + 1][ly + 1] = nf;
+          S.changed = 1;
+        }
+        if (hmask) {
+          // hard candidates: unset hard cells with a set neighbour whose directed test is not known to fail
+          const uint32_t xm = (nf << 1) | (S.XL[lz][ly] >> 31), xp = (nf >> 1) | (S.XR[lz][ly] << 31);
+          const uint32_t c0 = xm & ~S.B[0][lz][ly], c1 = xp & ~S.B[1][lz][ly], c2 = nb_ym & ~S.B[2][lz][ly],
+                         c3 = nb_yp & ~S.B[3][lz][ly], c4 = nb_zm & ~S.B[4][lz][ly], c5 = nb_zp & ~S.B[5][lz][ly];
+          uint32_t cand = (c0 | c1 | c2 | c3 | c4 | c5) & hmask & ~nf & vmask;
+          while (cand) {
+            const int b = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint32_t dm = ((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3) |
+                                (((c4 >> b) & 1) << 4) | (((c5 >> b) & 1) << 5);
+            const int q = atomicAdd(&S.qn, 1);
+            if (q < FT_QCAP) S.Q[q] = (dm << 16) | ((uint32_t)b << 8) | (uint32_t)tid;
+            else S.overflow = 1;
+          }
+        }
+      }
+      __syncthreads();
+      const int qn = min(S.qn, FT_QCAP);
+      // ---- hard candidates, one warp per candidate cell
+      for (int q = warp; q < qn; q += FT_THREADS / 32) {
+        const uint32_t it = S.Q[q];
+        const int wtid = it & 0xff, b = (it >> 8) & 0xff;
+        const uint32_t dm = it >> 16;
+        const int qy = wtid % FT_Y, qz = wtid / FT_Y;
+        const uint32_t coll = warp_check_collision(A, wx * 32 + b, j0 + qy, k0 + qz, dm, lane);
+        if (lane == 0) {
+          if (coll != dm) {  // some direction is free -> fill
+            atomicOr(&S.F[qz + 1][qy + 1], 1u << b);
+            S.changed = 1;
+          } else {
+            for (int d = 0; d < 6; d++)
+              if (dm >> d & 1) atomicOr(&S.B[d][qz][qy], 1u << b);
+            S.bdirty = 1;
+          }
+        }
+      }
+      __syncthreads();
+      if (!S.changed && !S.overflow) break;
+      __syncthreads();
+    }
+
+    // ---- write back + activate neighbours
+    const uint32_t f_end = S.F[lz + 1][ly + 1];
+    if (owned && f_end != f_start) {
+      A.F[wi] = f_end;
+      atomicAdd(&S.newbits, (uint32_t)__popc(f_end & ~f_start));
+    }
+    if (anyhard && S.bdirty && owned) {
+#pragma unroll
+      for (int d = 0; d < 6; d++) A.B[d * A.nw + wi] = S.B[d][lz][ly];
+    }
+    __syncthreads();
+    if (tid == 0 && S.newbits) atomicAdd(A.changed, (unsigned long long)S.newbits);
+    if (tid == 0 && (S.newbits || A.force_activate)) {
+      if (wx > 0) A.act_next[tile - 1] = 1;
+      if (wx + 1 < A.wr) A.act_next[tile + 1] = 1;
+      if (tyi > 0) A.act_next[tile - A.wr] = 1;
+      if (tyi + 1 < A.ty) A.act_next[tile + A.wr] = 1;
+      if (tzi > 0) A.act_next[tile - A.wr * A.ty] = 1;
+      if (tzi + 1 < A.tz) A.act_next[tile + A.wr * A.ty] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+struct FillState {
+  const uint32_t *fpos_key = nullptr;
+  int64_t dimg[3] = {0, 0, 0};
+  int64_t nbe = 0, cnbe = 0;
+  uint32_t *F = nullptr, *H = nullptr, *B = nullptr;
+  uint8_t *nbflag = nullptr, *act = nullptr;
+  int32_t *list = nullptr, *count = nullptr;
+  FsDesc *fs = nullptr;
+  int nfs = 0, all_hard = 0;
+  int64_t nw = 0, ntiles = 0;
+};
+
+void cx_fill_state_free(cx_ctx *ctx)
+{
+  FillState *s = (FillState *)ctx->fill_state;
+  if (!s) return;
+  cudaFree(s->F); cudaFree(s->H); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
+  cudaFree(s->count); cudaFree(s->fs);
+  delete s;
+  ctx->fill_state = nullptr;
+}
+
+// conservative fshape descriptors (host): see DESIGN.md "fill / easy cells"
+static void make_fs_desc(const cx_params *p, const float *n, const float *a, const float *b, const float *c, FsDesc *d, int *cullable)
+{
+  float u[3], v[3];
+  double lu = 0, lv = 0, ln = 0, nu = 0, nv = 0, uv = 0;
+  for (int k = 0; k < 3; k++) {
+    u[k] = b[k] - a[k]; v[k] = c[k] - a[k];
+    lu += (double)u[k] * u[k]; lv += (double)v[k] * v[k]; ln += (double)n[k] * n[k];
+    nu += (double)n[k] * u[k]; nv += (double)n[k] * v[k]; uv += (double)u[k] * v[k];
+  }
+  lu = sqrt(lu); lv = sqrt(lv); ln = sqrt(ln);
+  // cullable: the stored normal is consistent with the triangle's plane and the triangle is well conditioned
+  *cullable = ln > 0 && lu > 0 && lv > 0 && fabs(nu) <= 1e-3 * ln * lu && fabs(nv) <= 1e-3 * ln * lv &&
+              (lu * lu * lv * lv - uv * uv) >= 1e-4 * lu * lu * lv * lv;
+  const double margin = 1.5 * p->dr + 0.01 * (lu + lv) + 10.0 * p->eps;
+  for (int k = 0; k < 3; k++) {
+    const float mn = std::min(a[k], std::min(b[k], c[k])), mx = std::max(a[k], std::max(b[k], c[k]));
+    d->lo[k] = (float)(mn - margin); d->hi[k] = (float)(mx + margin);
+    d->n[k] = n[k]; d->v0[k] = a[k];
+  }
+  d->quirk = 0;
+  for (int k = 0; k < 3; k++)
+    if (fabs((double)n[k]) * p->dr * 0.5 < p->eps) d->quirk = 1;
+}
+
+static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                        const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int first, FillArgs *A, FillState **out)
+{
+  cudaStream_t st = ctx->stream;
+  FillState *s = (FillState *)ctx->fill_state;
+  int64_t dimg[3];
+  cx_fill_dims(p, dimg);
+  for (int k = 0; k < 3; k++)
+    if (dimg[k] <= 0 || dimg[k] > 0x7fffffff) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad lattice dimensions");
+  const int wr = (int)((dimg[0] + 31) / 32);
+  const int64_t nw = (int64_t)wr * dimg[1] * dimg[2];
+  const int ty = (int)((dimg[1] + FT_Y - 1) / FT_Y), tz = (int)((dimg[2] + FT_Z - 1) / FT_Z);
+  const int64_t ntiles = (int64_t)wr * ty * tz;
+  if (ntiles > 0x7fffffff) return cx_fail(ctx, CX_WRONG_INPUT, "fill: too many tiles");
+  const bool fresh = first || !s || s->fpos_key != fpos_d || s->dimg[0] != dimg[0] || s->dimg[1] != dimg[1] || s->dimg[2] != dimg[2] ||
+                     s->nbe != nbe || s->cnbe != cnbe;
+  if (fresh) {
+    cx_fill_state_free(ctx);
+    s = new FillState();
+    ctx->fill_state = s;
+    s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
+    for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
+    CX_CUDA(ctx, cudaMalloc(&s->F, sizeof(uint32_t) * (size_t)nw));
+    CX_CUDA(ctx, cudaMalloc(&s->H, sizeof(uint32_t) * (size_t)nw));
+    CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 6));
+    CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
+    CX_CUDA(ctx, cudaMalloc(&s->act, (size_t)ntiles * 2));
+    CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
+    CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 2));
+    CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
+    CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)ntiles * 2, st));
+    // fshape descriptors
+    s->nfs = 0; s->all_hard = 0;
+    if (cnbe > 0) {
+      if (cnbe > FS_MAX_DESC) s->all_hard = 1;
+      else {
+        std::vector<float> hn(4 * cnbe);
+        std::vector<int32_t> he(4 * cnbe);
+        CX_CUDA(ctx, cudaMemcpyAsync(hn.data(), norm_d + 4 * (nbe - cnbe), sizeof(float) * 4 * cnbe, cudaMemcpyDeviceToHost, st));
+        CX_CUDA(ctx, cudaMemcpyAsync(he.data(), ep_d + 4 * (nbe - cnbe), sizeof(int32_t) * 4 * cnbe, cudaMemcpyDeviceToHost, st));
+        CX_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<FsDesc> desc(cnbe);
+        for (int64_t t = 0; t < cnbe && !s->all_hard; t++) {
+          float v[3][4];
+          for (int c = 0; c < 3; c++)
+            CX_CUDA(ctx, cudaMemcpy(v[c], pos_d + 4 * (int64_t)he[4 * t + c], sizeof(float) * 4, cudaMemcpyDeviceToHost));
+          int cullable = 0;
+          make_fs_desc(p, &hn[4 * t], v[0], v[1], v[2], &desc[t], &cullable);
+          if (!cullable) s->all_hard = 1;
+        }
+        if (!s->all_hard) {
+          CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * (size_t)cnbe));
+          CX_CUDA(ctx, cudaMemcpy(s->fs, desc.data(), sizeof(FsDesc) * (size_t)cnbe, cudaMemcpyHostToDevice));
+          s->nfs = (int)cnbe;
+        }
+      }
+    }
+  }
+  memset(A, 0, sizeof(*A));
+  A->p = *p;
+  A->pos = (const float4 *)pos_d; A->norm = (const float4 *)norm_d; A->ep = (const int4 *)ep_d; A->cell_idx = cell_idx_d;
+  A->nbe = nbe; A->cnbe = cnbe;
+  for (int k = 0; k < 3; k++) A->dimg[k] = (int)dimg[k];
+  A->wr = wr; A->ty = ty; A->tz = tz; A->ntiles = ntiles; A->nw = nw;
+  A->k_lo = 0; A->k_hi = (int)dimg[2];
+  A->F = s->F; A->H = s->H; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
+  A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
+  A->changed = (unsigned long long *)(ctx->d_mail + 24);
+  A->drw2 = p->dr_wall * p->dr_wall;
+  A->one_eps = 1.0 + (double)p->eps;
+  if (fresh) {
+    k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
+    CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
+    k_classify<<<cx_blocks(nw, 256, ctx->num_sms * 16), 256, 0, st>>>(*A);
+    CX_LAUNCH_CHECK(ctx, "k_classify");
+  }
+  *out = s;
+  return CX_OK;
+}
+
+// runs rounds until no tile is active; returns the number of rounds
+static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_out)
+{
+  cudaStream_t st = ctx->stream;
+  int rounds = 0;
+  const int grid_tiles = ctx->num_sms * 4;
+  int32_t *hcount = (int32_t *)(ctx->h_mail + 28);
+  for (;;) {
+    // a batch of rounds without host synchronisation; empty rounds are cheap
+    const int batch = 4;
+    for (int r = 0; r < batch; r++) {
+      k_round_prep<<<1, 1, 0, st>>>(A->count);
+      CX_LAUNCH_CHECK(ctx, "k_round_prep");
+      k_build_list<<<cx_blocks(A->ntiles, 256, ctx->num_sms * 8), 256, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_build_list");
+      A->force_activate = (rounds == 0);
+      k_fill_tiles<<<grid_tiles, FT_THREADS, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_fill_tiles");
+      std::swap(A->act_cur, A->act_next);
+      rounds++;
+    }
+    CX_CUDA(ctx, cudaMemcpyAsync(hcount, A->count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hcount[0] == 0) break;  // the last round of the batch found no active tile
+    if (rounds > 4000000) return cx_fail(ctx, CX_INTERNAL_ERROR, "fill: round limit");
+  }
+  (void)s;
+  if (rounds_out) *rounds_out = rounds;
+  return CX_OK;
+}
+
+extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                     const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                                     int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host)
+{
+  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
+  FillArgs A;
+  FillState *s = nullptr;
+  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, first_call, &A, &s);
+  if (rc != CX_OK) return rc;
+  if (k_begin < 0 || k_end > A.dimg[2] || k_begin >= k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
+  A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
+  cudaStream_t st = ctx->stream;
+  CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
+  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  A.merge = first_call ? 0 : 1;
+  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_unpack");
+  if (first_call) {
+    k_seed<<<1, 1, 0, st>>>(A, seed);
+    CX_LAUNCH_CHECK(ctx, "k_seed");
+  }
+  rc = fill_rounds(ctx, &A, s, rounds_host);
+  if (rc != CX_OK) return rc;
+  k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_pack");
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CX_CUDA(ctx, cudaStreamSynchronize(st));
+  if (changed_host) *changed_host = ctx->h_mail[24];
+  return CX_OK;
+}
+
+extern "C" int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed, int64_t *nfi_host,
+                                int32_t *rounds_host)
+{
+  if (!p) return CX_WRONG_INPUT;
+  int64_t dimg[3];
+  cx_fill_dims(p, dimg);
+  if (seed >= dimg[0] * dimg[1] * dimg[2]) return cx_fail(ctx, CX_SEED_OUTSIDE, "fill: seed outside the lattice");
+  return cx_fill_geometry_slab(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, seed, 0, dimg[2], 1, nfi_host, rounds_host);
+}

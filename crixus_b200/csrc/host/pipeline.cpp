@@ -1,0 +1,186 @@
+// crixus_b200 -- the whole hot path on host buffers: the sequence of crixus_main, /root/reference/src/crixus.cpp /
+// src/crixus.cu:184-962, expressed through the C-ABI stage entry points.  This is what the CLI calls and what
+// bench.py times end to end (host->device and device->host copies included).
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../../include/crixus_b200.h"
+
+namespace {
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess ? 0 : -1; }
+  template <class T> T *as() { return (T *)p; }
+};
+#define RC(call) do { int rc__ = (call); if (rc__ != CX_OK) return rc__; } while (0)
+#define CU(call) do { if ((call) != cudaSuccess) return CX_CUDA_ERROR; } while (0)
+}  // namespace
+
+extern "C" void cx_job_free(cx_job *job)
+{
+  if (!job) return;
+  free(job->pos); free(job->norm); free(job->ep); free(job->surf); free(job->vol); free(job->cell_idx); free(job->fpos);
+  job->pos = job->norm = job->surf = job->vol = nullptr;
+  job->ep = job->cell_idx = nullptr;
+  job->fpos = nullptr;
+}
+
+extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
+{
+  if (!ctx || !job || !job->corners || !job->normals || job->nbe <= 0 || !(job->dr > 0)) return CX_WRONG_INPUT;
+  const int64_t nbe = job->nbe;
+  const float dr = job->dr;
+  double t0 = now_s();
+  // bounding box over all raw corners (crixus.cu:185-208)
+  float bbmin[3] = {1e10f, 1e10f, 1e10f}, bbmax[3] = {-1e10f, -1e10f, -1e10f};
+  for (int64_t c = 0; c < 3 * nbe; c++)
+    for (int k = 0; k < 3; k++) {
+      const float x = job->corners[3 * c + k];
+      bbmin[k] = bbmin[k] > x ? x : bbmin[k];
+      bbmax[k] = bbmax[k] < x ? x : bbmax[k];
+    }
+  // weld (crixus.cu:214)
+  std::vector<float> verts((size_t)9 * nbe);
+  std::vector<int32_t> ids((size_t)3 * nbe);
+  const int64_t nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
+  job->nvert = nvert;
+  std::vector<float> h_pos((size_t)4 * nvert), h_norm((size_t)4 * nbe);
+  std::vector<int32_t> h_ep((size_t)4 * nbe);
+  for (int64_t v = 0; v < nvert; v++) {
+    h_pos[4 * v] = verts[3 * v]; h_pos[4 * v + 1] = verts[3 * v + 1]; h_pos[4 * v + 2] = verts[3 * v + 2]; h_pos[4 * v + 3] = 0.f;
+  }
+  for (int64_t i = 0; i < nbe; i++) {
+    for (int k = 0; k < 3; k++) { h_norm[4 * i + k] = job->normals[3 * i + k]; h_ep[4 * i + k] = ids[3 * i + k]; }
+    h_norm[4 * i + 3] = 0.f; h_ep[4 * i + 3] = 0;
+  }
+  job->t_weld_s = now_s() - t0;
+
+  cx_params p;
+  cx_params_domain(&p, dr, bbmin, bbmax);  // crixus.cu:262-283
+  const int64_t ncell = p.gridn[3];
+
+  t0 = now_s();
+  DevBuf pre_pos, pos, pre_norm, norm, pre_ep, ep, pre_surf, surf, cell_idx, trisize, vol, newlink;
+  if (pre_pos.alloc(16 * (size_t)(nvert + nbe)) || pos.alloc(16 * (size_t)(nvert + nbe)) || pre_norm.alloc(16 * (size_t)nbe) ||
+      norm.alloc(16 * (size_t)nbe) || pre_ep.alloc(16 * (size_t)nbe) || ep.alloc(16 * (size_t)nbe) || pre_surf.alloc(4 * (size_t)nbe) ||
+      surf.alloc(4 * (size_t)nbe) || cell_idx.alloc(4 * (size_t)(ncell + 1)) || trisize.alloc(4 * (size_t)nvert) ||
+      vol.alloc(4 * (size_t)nvert) || newlink.alloc(4 * (size_t)nvert))
+    return CX_CUDA_ERROR;
+  CU(cudaMemcpy(pre_pos.p, h_pos.data(), 16 * (size_t)nvert, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pre_norm.p, h_norm.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pre_ep.p, h_ep.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
+  CU(cudaMemset(trisize.p, 0, 4 * (size_t)nvert));
+  CU(cudaMemset(vol.p, 0, 4 * (size_t)nvert));
+  job->t_h2d_s = now_s() - t0;
+
+  t0 = now_s();
+  if (job->swap_normals) RC(cx_swap_normals(ctx, pre_norm.as<float>(), nbe));  // crixus.cu:310-317
+  RC(cx_set_bound_elem(ctx, pre_pos.as<float>(), pre_norm.as<float>(), pre_surf.as<float>(), pre_ep.as<int32_t>(), nbe, nvert, job->zstat));
+  RC(cx_bin_segments(ctx, &p, pre_pos.as<float>(), pos.as<float>(), pre_norm.as<float>(), norm.as<float>(), pre_ep.as<int32_t>(),
+                     ep.as<int32_t>(), pre_surf.as<float>(), surf.as<float>(), cell_idx.as<int32_t>(), nbe, nvert));
+  for (int idim = 0; idim < 3; idim++) {  // crixus.cu:391-412
+    if (!job->periodic[idim]) continue;
+    RC(cx_synchronize(ctx));
+    CU(cudaMemset(newlink.p, 0xff, 4 * (size_t)nvert));
+    RC(cx_find_links(ctx, &p, pos.as<float>(), nvert, newlink.as<int32_t>(), idim));
+    RC(cx_periodicity_links(ctx, ep.as<int32_t>(), nbe, newlink.as<int32_t>()));
+  }
+  for (int k = 0; k < 3; k++) p.per[k] = job->periodic[k] ? 1 : 0;  // crixus.cu:428
+  RC(cx_calc_trisize(ctx, ep.as<int32_t>(), trisize.as<int32_t>(), nbe));
+  RC(cx_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
+                         cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
+
+  // ---- fluid (crixus.cu:463-467, 698-961)
+  cx_params_fill_eps(&p);
+  cx_params_container(&p, job->use_container, job->cmin, job->cmax);
+  cx_fill_dims(&p, job->dimg);
+  const int64_t G = job->dimg[0] * job->dimg[1] * job->dimg[2];
+  const int64_t nwords = (G + 31) / 32;
+  DevBuf fpos, fnorm, fep, fposv;
+  if (fpos.alloc(4 * (size_t)nwords)) return CX_CUDA_ERROR;
+  CU(cudaMemset(fpos.p, 0, 4 * (size_t)nwords));
+  job->nfluid_counted = 0;
+  bool have_fs = false;
+  int64_t fnbe = nbe, cnbe = 0;
+  const float *g_norm = norm.as<float>(), *g_pos = pos.as<float>();
+  const int32_t *g_ep = ep.as<int32_t>();
+  for (int f = 0; f < job->nfills; f++) {
+    const cx_fill_spec &fs = job->fills[f];
+    if (fs.option == 2) {
+      if (!have_fs && job->fs_nbe > 0 && job->fs_corners && job->fs_normals) {  // crixus.cu:809-930
+        have_fs = true;
+        const int64_t fsn = job->fs_nbe;
+        std::vector<float> fv((size_t)9 * fsn);
+        std::vector<int32_t> fid((size_t)3 * fsn);
+        const int64_t fsnvert = cx_weld_host(job->fs_corners, 3 * fsn, dr, fv.data(), fid.data());
+        std::vector<float> hp((size_t)4 * fsnvert), hn((size_t)4 * fsn);
+        std::vector<int32_t> he((size_t)4 * fsn);
+        for (int64_t v = 0; v < fsnvert; v++) { hp[4 * v] = fv[3 * v]; hp[4 * v + 1] = fv[3 * v + 1]; hp[4 * v + 2] = fv[3 * v + 2]; hp[4 * v + 3] = 0.f; }
+        for (int64_t i = 0; i < fsn; i++) {
+          for (int k = 0; k < 3; k++) { hn[4 * i + k] = job->fs_normals[3 * i + k]; he[4 * i + k] = fid[3 * i + k] + (int32_t)nvert; }
+          hn[4 * i + 3] = 0.f; he[4 * i + 3] = 0;
+        }
+        if (fnorm.alloc(16 * (size_t)(nbe + fsn)) || fep.alloc(16 * (size_t)(nbe + fsn)) || fposv.alloc(16 * (size_t)(nvert + fsnvert)))
+          return CX_CUDA_ERROR;
+        RC(cx_synchronize(ctx));
+        CU(cudaMemcpy(fnorm.p, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(fep.p, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(fposv.p, pos.p, 16 * (size_t)nvert, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(fnorm.as<float>() + 4 * nbe, hn.data(), 16 * (size_t)fsn, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(fep.as<int32_t>() + 4 * nbe, he.data(), 16 * (size_t)fsn, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(fposv.as<float>() + 4 * nvert, hp.data(), 16 * (size_t)fsnvert, cudaMemcpyHostToDevice));
+        g_norm = fnorm.as<float>(); g_ep = fep.as<int32_t>(); g_pos = fposv.as<float>();
+        fnbe = nbe + fsn; cnbe = fsn;
+      }
+      p.dr_wall = fs.dr_wall > 0 ? fs.dr_wall : dr;  // crixus.cu:795
+      const int64_t seed = cx_seed_index(&p, fs.seed);
+      if (seed < 0) return CX_SEED_OUTSIDE;
+      int64_t nfi = 0;
+      int32_t rounds = 0;
+      RC(cx_fill_geometry(ctx, &p, fpos.as<uint32_t>(), g_norm, g_ep, g_pos, fnbe, cnbe, cell_idx.as<int32_t>(), seed, &nfi, &rounds));
+      job->nfluid_counted += nfi;
+    } else {
+      const float *lo = fs.lo, *hi = fs.hi;  // crixus.cu:759-773
+      if (hi[0] - lo[0] < 1e-5 * dr || hi[1] - lo[1] < 1e-5 * dr || hi[2] - lo[2] < 1e-5 * dr) return CX_FLUID_NDEF;
+      for (int k = 0; k < 3; k++)
+        if (lo[k] + p.eps < p.fcmin[k] || hi[k] - p.eps > p.fcmax[k]) return CX_FLUID_BBOX_TOO_SMALL;
+      int64_t nfi = 0;
+      RC(cx_fill_box(ctx, &p, fpos.as<uint32_t>(), lo, hi, &nfi));
+      job->nfluid_counted += nfi;
+    }
+  }
+  RC(cx_synchronize(ctx));
+  job->t_gpu_s = now_s() - t0;
+  job->params_fill = p;
+
+  // ---- results to the host (crixus.cu:363-365, 413, 456, 962)
+  t0 = now_s();
+  job->pos = (float *)malloc(16 * (size_t)(nvert + nbe));
+  job->norm = (float *)malloc(16 * (size_t)nbe);
+  job->ep = (int32_t *)malloc(16 * (size_t)nbe);
+  job->surf = (float *)malloc(4 * (size_t)nbe);
+  job->vol = (float *)malloc(4 * (size_t)nvert);
+  job->cell_idx = (int32_t *)malloc(4 * (size_t)(ncell + 1));
+  job->fpos = (uint32_t *)malloc(4 * (size_t)nwords);
+  if (!job->pos || !job->norm || !job->ep || !job->surf || !job->vol || !job->cell_idx || !job->fpos) return CX_INTERNAL_ERROR;
+  CU(cudaMemcpy(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->vol, vol.p, 4 * (size_t)nvert, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(job->fpos, fpos.p, 4 * (size_t)nwords, cudaMemcpyDeviceToHost));
+  int64_t pop = 0;
+  for (int64_t w = 0; w < nwords; w++) pop += __builtin_popcount(job->fpos[w]);
+  job->nfluid = pop;
+  job->t_d2h_s = now_s() - t0;
+  return CX_OK;
+}

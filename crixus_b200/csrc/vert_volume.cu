@@ -1,0 +1,411 @@
+// crixus_b200 -- calc_vert_volume: vertex-particle volume by the reference's 41^3-voxel quadrature.
+// Reference: /root/reference/src/crixus_d.cu:271-678 (one thread per vertex, 8.6 KB of local memory per thread).
+//
+// B200 mapping (DESIGN.md "calc_vert_volume"):
+//   * one WARP per vertex, vertices handed out by an atomic work counter (persistent CTAs, 4 warps each);
+//   * phase A (warp-cooperative, once per vertex): fan gather over the 27 neighbouring 3dr-cells with lanes striding
+//     the cell-sorted segments (ballot/scan compaction keeps the reference's discovery order), chain ordering,
+//     edge-normal pairing, and the 12 plane vectors per fan triangle -> 160 B per triangle in shared memory;
+//   * phase B: the 41x41 z-lines of the voxel cube are dealt to the lanes.  Along a line only gp.z changes, and in
+//     the reference's left-to-right dot product gp.z enters LAST (R1: fma(gz,cz, fma(gy,cy, fma(gx,cx,0)))), so the
+//     (x,y) partial is shared by the 41 voxels of the line bit-exactly: 1 FFMA per plane per voxel instead of 3.
+//     Per-voxel state lives in bit masks (hit / alive / bit-sliced halving counters); the z loop is fully
+//     unrolled so gp.z comes straight from the kernel-parameter constant bank.
+//   * the result is summed in integers (weights are 2^-k) so it is independent of the order of summation.
+// Bound: FP32 ALU (non-tensor).  Algorithmic flops F = 68921 * T * 56 per vertex.
+#include "common.cuh"
+
+#define VV_WARPS 4
+#define VV_GS 41      // gres*2+1 voxels per axis (crixus_d.cu:280)
+#define VV_LINES (VV_GS * VV_GS)
+#define VV_PLANE_F4 10
+
+#define VVE_TRIMAX 1
+#define VVE_FAN 2
+#define VVE_NONMANIFOLD 4
+
+struct VVArgs {
+  cx_params p;
+  const float4 *pos;
+  const float4 *norm;
+  const int4 *ep;
+  float *vol;
+  const int32_t *trisize;
+  const int32_t *cell_idx;
+  int64_t v_begin, v_end;
+  int zero_open;
+  float thr_cube;  // largest float <= dr/2.+eps (double), so |sp| <= thr_cube  <=>  (double)|sp| <= dr/2.+eps
+  float eps;
+  float two_dr;    // 2*dr (crixus_d.cu:513)
+  double gd3;      // pow(dr/2.0/(float)gres, 3) (crixus_d.cu:674)
+  int cmax;        // largest k with 2^-k >= eps (vgrid < eps -> voxel dropped, crixus_d.cu:551,662)
+  unsigned long long *work;  // work counter
+  int *err;                  // error bits
+  float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
+};
+
+struct VVWarp {
+  float4 plane[CX_TRIMAX][VV_PLANE_F4];
+  int tri[CX_TRIMAX][3];
+  int ecount[CX_TRIMAX];
+  int eseg[CX_TRIMAX][2];
+  int closed;
+};
+
+__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+// periodic unwrap of a vertex-to-vertex offset component (crixus_d.cu:513): c += sgn(c)*(-dmax+dmin)
+__device__ __forceinline__ float unwrap1(const cx_params &p, float c, int n, float two_dr)
+{
+  if (p.per[n] && fabsf(c) > two_dr) c = ffma(sgnf(c), fadd(-p.dmax[n], p.dmin[n]), c);
+  return c;
+}
+__device__ __forceinline__ f3 unwrap3(const cx_params &p, f3 c, float two_dr)
+{
+  return mk3(unwrap1(p, c.x, 0, two_dr), unwrap1(p, c.y, 1, two_dr), unwrap1(p, c.z, 2, two_dr));
+}
+// normalise like crixus_d.cu:510-517: vnorm accumulated in double from float squares, narrowed every step
+__device__ __forceinline__ f3 normalise_ref(f3 c)
+{
+  float vn = (float)(0.0 + (double)c.x * (double)c.x);
+  vn = (float)((double)vn + (double)c.y * (double)c.y);
+  vn = (float)((double)vn + (double)c.z * (double)c.z);
+  vn = __fsqrt_rn(vn);
+  return mk3(__fdiv_rn(c.x, vn), __fdiv_rn(c.y, vn), __fdiv_rn(c.z, vn));
+}
+__device__ __forceinline__ float halfway(float pi, float c) { return (float)((double)pi + (double)c / 2.); }  // :558
+
+__device__ __forceinline__ int warp_incl_scan_i(int v, int lane)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// bit-sliced +1 on the 5-bit per-voxel halving counters (saturating at 31)
+__device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t bit)
+{
+  uint32_t c = bit;
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    uint32_t t = h[b] & c;
+    h[b] ^= c;
+    c = t;
+  }
+#pragma unroll
+  for (int b = 0; b < 5; b++) h[b] |= c;  // overflow -> stay at 31
+}
+
+template <bool OPEN>
+__device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1,
+                                          uint32_t &hit_lo, uint32_t &hit_hi, uint32_t &alive_lo, uint32_t &alive_hi,
+                                          uint32_t (&hlo)[5], uint32_t (&hhi)[5])
+{
+  const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
+  const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
+  for (int j = 0; j < tris; j++) {
+    // ---------------- cubes (crixus_d.cu:531-543): voxel is sampled if it lies in one of the two dr-cubes of j
+    if (__any_sync(0xffffffffu, (hit_lo != 0xffffffffu) | (hit_hi != 0x1ffu))) {
+      const float4 P0 = w.plane[j][0], P1 = w.plane[j][1], P2 = w.plane[j][2], P3 = w.plane[j][3];
+      const float t0 = ffma(gp1, P0.y, ffma(gp0, P0.x, 0.f));  // c0
+      const float t1 = ffma(gp1, P1.x, ffma(gp0, P0.w, 0.f));  // c1
+      const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
+      const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
+      const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
+#pragma unroll
+      for (int m = 0; m < VV_GS; m++) {
+        const float g = a.gz[m];
+        const bool i0 = fabsf(ffma(g, P0.z, t0)) <= thr;
+        const bool i1 = fabsf(ffma(g, P1.y, t1)) <= thr;
+        const bool i2 = fabsf(ffma(g, P2.x, t2)) <= thr;
+        const bool i3 = fabsf(ffma(g, P2.w, t3)) <= thr;
+        const bool i4 = fabsf(ffma(g, P3.z, t4)) <= thr;
+        const bool in = (i0 && i1 && i2) || (i2 && i3 && i4);
+        if (m < 32) hit_lo |= in ? (1u << (m & 31)) : 0u;
+        else hit_hi |= in ? (1u << (m & 31)) : 0u;
+      }
+    }
+    // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
+    if (!__any_sync(0xffffffffu, (alive_lo | alive_hi) != 0u)) break;
+    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
+                 P9 = w.plane[j][9];
+    // c5 = (P4.x,P4.y,P4.z) c6 = (P4.w,P5.x,P5.y) c7 = (P5.z,P5.w,P6.x) c8 = (P6.y,P6.z,P6.w)
+    // c9 = (P7.x,P7.y,P7.z) c10 = (P7.w,P8.x,P8.y) c11 = (P8.z,P8.w,P9.x) en = (P9.y,P9.z,P9.w)
+    const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
+    float tV2 = 0.f;
+    if (OPEN) tV2 = ffma(fsub(q1, P6.z), P5.w, ffma(fsub(q0, P6.y), P5.z, 0.f));
+    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
+    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
+    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
+    const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
+#pragma unroll
+    for (int m = 0; m < VV_GS; m++) {
+      const float g = a.gz[m];
+      const uint32_t bit = 1u << (m & 31);
+      const float q2 = fadd(g, pi.z);
+      const float sV = ffma(fsub(q2, P5.y), P4.z, tV);
+      bool kill = sV > eps;
+      int nh = (fabsf(sV) < eps) ? 1 : 0;
+      if (OPEN) {
+        const float sV2 = ffma(fsub(q2, P6.w), P6.x, tV2);
+        kill |= sV2 > eps;
+        nh += (fabsf(sV2) < eps) ? 1 : 0;
+      }
+      const float w0 = ffma(g, P7.z, tW0), w1 = ffma(g, P8.y, tW1), w2 = ffma(g, P9.x, tW2);
+      const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
+      const bool hw = fabsf(w0) < eps;
+      kill |= inside && !hw;
+      nh += (inside && hw) ? 1 : 0;
+      const float sE = ffma(fsub(g, P4.z), P9.w, tE);
+      kill |= sE > eps;
+      nh += (fabsf(sE) < eps) ? 1 : 0;
+      if (m < 32) alive_lo &= kill ? ~bit : 0xffffffffu;
+      else alive_hi &= kill ? ~bit : 0xffffffffu;
+      if (nh) {  // rare: the voxel lies within eps of a clipping plane
+        for (int r = 0; r < nh; r++) {
+          if (m < 32) half_inc(hlo, bit);
+          else half_inc(hhi, bit);
+        }
+      }
+    }
+  }
+}
+
+// contribution of one 32-bit group of voxels, in units of 2^-31
+__device__ __forceinline__ long long group_weight(uint32_t va, const uint32_t (&h)[5], int cmax)
+{
+  const uint32_t anyh = (h[0] | h[1] | h[2] | h[3] | h[4]) & va;
+  long long s = (long long)__popc(va & ~anyh) << 31;
+  uint32_t r = anyh;
+  while (r) {
+    const int b = __ffs(r) - 1;
+    r &= r - 1;
+    const int c = ((h[0] >> b) & 1) | (((h[1] >> b) & 1) << 1) | (((h[2] >> b) & 1) << 2) | (((h[3] >> b) & 1) << 3) |
+                  (((h[4] >> b) & 1) << 4);
+    if (c <= cmax) s += 1ll << (31 - c);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_constant__ VVArgs a)
+{
+  __shared__ VVWarp sm[VV_WARPS];
+  const int lane = threadIdx.x & 31;
+  VVWarp &w = sm[threadIdx.x >> 5];
+  const cx_params &p = a.p;
+
+  for (;;) {
+    unsigned long long widx = 0;
+    if (lane == 0) widx = atomicAdd(a.work, 1ull);
+    widx = __shfl_sync(0xffffffffu, widx, 0);
+    const int64_t i = a.v_begin + (int64_t)widx;
+    if (i >= a.v_end) break;
+    __syncwarp();
+
+    const float4 pi4 = __ldg(&a.pos[i]);
+    if (pi4.x < -1e9f) continue;  // vertex deleted by the periodic pairing (crixus_d.cu:297)
+    const f3 pi = mk3(pi4);
+    const int tris = __ldg(&a.trisize[i]);
+    if (tris > CX_TRIMAX) {  // crixus_d.cu:306: the reference thread gives up; here: flag + zero
+      if (lane == 0) { atomicOr(a.err, VVE_TRIMAX); a.vol[i] = 0.f; }
+      continue;
+    }
+    if (tris <= 0) { if (lane == 0) a.vol[i] = 0.f; continue; }
+
+    const int gx = cell_coord(pi.x, p.dmin[0], p.griddr[0], p.gridn[0]);
+    const int gy = cell_coord(pi.y, p.dmin[1], p.griddr[1], p.gridn[1]);
+    const int gz = cell_coord(pi.z, p.dmin[2], p.griddr[2], p.gridn[2]);
+
+    // ---------------- fan gather (crixus_d.cu:316-369): discovery order = cell order, segment order, corner order
+    int itris = 0;
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
+      if (c < 0) continue;
+      const int b = __ldg(&a.cell_idx[c]), e = __ldg(&a.cell_idx[c + 1]);
+      for (int base = b; base < e; base += 32) {
+        const int j = base + lane;
+        int4 E = make_int4(-1, -1, -1, -1);
+        if (j < e) E = __ldg(&a.ep[j]);
+        const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
+        const int cnt = m0 + m1 + m2;
+        const int incl = warp_incl_scan_i(cnt, lane);
+        int off = itris + incl - cnt;
+        if (m0 && off < CX_TRIMAX) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
+        if (m1 && off < CX_TRIMAX) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
+        if (m2 && off < CX_TRIMAX) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
+        itris += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    if (itris != tris) {  // triangles outside the 27-cell neighbourhood: the reference reads garbage here
+      if (lane == 0) { atomicOr(a.err, VVE_FAN); a.vol[i] = 0.f; }
+      continue;
+    }
+    __syncwarp();
+
+    // ---------------- chain ordering + closedness (crixus_d.cu:371-399), serial on lane 0 (T <= 50)
+    if (lane == 0) {
+      int closed = 1;
+      for (int j = 0; j < tris; j++) {
+        for (int k = j + 1; k < tris; k++) {
+          if (w.tri[j][1] == w.tri[k][0]) {
+            if (k != j + 1)
+              for (int l = 0; l < 3; l++) { int t = w.tri[j + 1][l]; w.tri[j + 1][l] = w.tri[k][l]; w.tri[k][l] = t; }
+            break;
+          }
+          if (w.tri[j][1] == w.tri[k][1]) {
+            const int d0 = w.tri[k][1], d1 = w.tri[k][0], d2 = w.tri[k][2];
+            for (int l = 0; l < 3; l++) w.tri[k][l] = w.tri[j + 1][l];
+            w.tri[j + 1][0] = d0; w.tri[j + 1][1] = d1; w.tri[j + 1][2] = d2;
+            break;
+          }
+          if (k == tris - 1) closed = 0;
+        }
+      }
+      if (w.tri[0][0] != w.tri[tris - 1][1]) closed = 0;
+      w.closed = closed;
+    }
+    for (int k = lane; k < tris; k += 32) w.ecount[k] = 0;
+    __syncwarp();
+    const int closed = w.closed;
+    if (a.zero_open && !closed) {  // crixus_d.cu:403-407
+      if (lane == 0) a.vol[i] = 0.f;
+      continue;
+    }
+
+    // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
+      if (c < 0) continue;
+      const int b = __ldg(&a.cell_idx[c]), e = __ldg(&a.cell_idx[c + 1]);
+      for (int j = b + lane; j < e; j += 32) {
+        const int4 E = __ldg(&a.ep[j]);
+        for (int k = 0; k < tris; k++) {
+          const int t0 = w.tri[k][0], t1 = w.tri[k][1];
+          const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
+          if (vf == 2) {
+            const int slot = atomicAdd(&w.ecount[k], 1);
+            if (slot < 2) w.eseg[k][slot] = j;
+            else atomicOr(a.err, VVE_NONMANIFOLD);
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---------------- avnorm (crixus_d.cu:524): float sum in fan order, every lane computes the same value
+    f3 av = mk3(0.f, 0.f, 0.f);
+    for (int j = 0; j < tris; j++) {
+      const float4 n = __ldg(&a.norm[w.tri[j][2]]);
+      av = mk3(fsub(av.x, n.x), fsub(av.y, n.y), fsub(av.z, n.z));
+    }
+
+    // ---------------- per-triangle plane vectors (crixus_d.cu:507-529 and :552-596), one lane per fan triangle
+    for (int j = lane; j < tris; j += 32) {
+      const f3 n = mk3(__ldg(&a.norm[w.tri[j][2]]));
+      const f3 va = mk3(__ldg(&a.pos[w.tri[j][0]])), vb = mk3(__ldg(&a.pos[w.tri[j][1]]));
+      const f3 e1 = unwrap3(p, sub3(va, pi), a.two_dr);  // cvec[5] (and cvec[0] before normalisation)
+      const f3 e2 = unwrap3(p, sub3(vb, pi), a.two_dr);  // tvec[1] / cvec[7] (and cvec[3] before normalisation)
+      const f3 c0 = normalise_ref(e1), c3 = normalise_ref(e2);
+      const f3 c1 = cross_r2(c0, n), c4 = cross_r2(c3, n);
+      const f3 c6 = mk3(halfway(pi.x, e1.x), halfway(pi.y, e1.y), halfway(pi.z, e1.z));
+      const f3 c8 = mk3(halfway(pi.x, e2.x), halfway(pi.y, e2.y), halfway(pi.z, e2.z));
+      f3 c9 = cross_r2(e1, e2), c10 = cross_r2(e2, av), c11 = cross_r2(av, e1);  // crixus_d.cu:570
+      if (dot3_r1(n, c9) > 0.f) { c9 = neg3(c9); c10 = neg3(c10); c11 = neg3(c11); }
+      // edge normal: sum of the (<=2) adjacent segment normals x edge (crixus_d.cu:447-473)
+      f3 en = mk3(0.f, 0.f, 0.f);
+      const int cnt = min(w.ecount[j], 2);
+      if (cnt >= 1) {
+        const f3 na = mk3(__ldg(&a.norm[w.eseg[j][0]]));
+        en = add3(en, na);
+        if (cnt == 2) en = add3(en, mk3(__ldg(&a.norm[w.eseg[j][1]])));
+        f3 edge = sub3(va, vb);
+        if (cnt == 2) edge = unwrap3(p, edge, a.two_dr);  // single-segment edges are not unwrapped (:465-473)
+        en = cross_r2(en, edge);
+      }
+      if (dot3_r1(en, e1) < 0.f) en = neg3(en);  // crixus_d.cu:581-585
+      float4 *P = w.plane[j];
+      P[0] = make_float4(c0.x, c0.y, c0.z, c1.x);
+      P[1] = make_float4(c1.y, c1.z, n.x, n.y);
+      P[2] = make_float4(n.z, c3.x, c3.y, c3.z);
+      P[3] = make_float4(c4.x, c4.y, c4.z, 0.f);
+      P[4] = make_float4(e1.x, e1.y, e1.z, c6.x);
+      P[5] = make_float4(c6.y, c6.z, e2.x, e2.y);
+      P[6] = make_float4(e2.z, c8.x, c8.y, c8.z);
+      P[7] = make_float4(c9.x, c9.y, c9.z, c10.x);
+      P[8] = make_float4(c10.y, c10.z, c11.x, c11.y);
+      P[9] = make_float4(c11.z, en.x, en.y, en.z);
+    }
+    __syncwarp();
+
+    // ---------------- the voxel cube: lanes take z-lines (k = x index, l = y index), crixus_d.cu:488-670
+    long long acc = 0;
+    for (int line = lane; line < VV_LINES; line += 32) {
+      const int k = line / VV_GS, l = line - k * VV_GS;
+      uint32_t hit_lo = 0u, hit_hi = 0u, alive_lo = 0xffffffffu, alive_hi = 0x1ffu;
+      uint32_t hlo[5] = {0u, 0u, 0u, 0u, 0u}, hhi[5] = {0u, 0u, 0u, 0u, 0u};
+      // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
+      const float g0 = a.gz[k], g1 = a.gz[l];
+      if (closed) line_loop<false>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
+      else line_loop<true>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
+      acc += group_weight(hit_lo & alive_lo, hlo, a.cmax) + group_weight(hit_hi & alive_hi & 0x1ffu, hhi, a.cmax);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float volf = (float)((double)acc * (1.0 / 2147483648.0));  // exact sum of 2^-k weights, rounded once
+      a.vol[i] = (float)((double)volf * a.gd3);                          // crixus_d.cu:674
+    }
+  }
+}
+
+__global__ void k_vv_init(unsigned long long *work, int *err) { *work = 0ull; *err = 0; }
+
+extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                                   float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                                   int zero_open, int64_t v_begin, int64_t v_end)
+{
+  if (!ctx || !p || !pos_d || !norm_d || !ep_d || !vol_d || !trisize_d || !cell_idx_d) return CX_WRONG_INPUT;
+  if (v_begin < 0 || v_end > nvert || v_begin > v_end) return CX_WRONG_INPUT;
+  if (v_begin == v_end) return CX_OK;
+  (void)nbe;
+  VVArgs a;
+  a.p = *p;
+  a.pos = (const float4 *)pos_d; a.norm = (const float4 *)norm_d; a.ep = (const int4 *)ep_d;
+  a.vol = vol_d; a.trisize = trisize_d; a.cell_idx = cell_idx_d;
+  a.v_begin = v_begin; a.v_end = v_end; a.zero_open = zero_open;
+  const float dr = p->dr, eps = p->eps;
+  const float gdr = (float)(dr / 2.0 / (float)CX_GRES);               // crixus_d.cu:281
+  for (int m = 0; m < VV_GS; m++) a.gz[m] = ((float)m - (float)(VV_GS - 1) / 2) * gdr;  // :493-495
+  const double thr_d = dr / 2. + eps;                                  // :535 (double)
+  float thr = (float)thr_d;
+  if ((double)thr > thr_d) thr = nextafterf(thr, -INFINITY);
+  a.thr_cube = thr;
+  a.eps = eps;
+  a.two_dr = 2 * dr;
+  const double gd = dr / 2.0 / (float)CX_GRES;
+  a.gd3 = pow(gd, 3);
+  int cmax = 0;
+  while (cmax < 31 && !(ldexpf(1.0f, -(cmax + 1)) < eps)) cmax++;
+  a.cmax = cmax;
+  a.work = (unsigned long long *)(ctx->d_mail + 16);
+  a.err = (int *)(ctx->d_mail + 17);
+  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err);
+  CX_LAUNCH_CHECK(ctx, "k_vv_init");
+  int bps = 0;
+  CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume, VV_WARPS * 32, 0));
+  if (bps < 1) bps = 1;
+  int64_t want = (v_end - v_begin + VV_WARPS - 1) / VV_WARPS;
+  int64_t grid = (int64_t)ctx->num_sms * bps;
+  if (grid > want) grid = want;
+  k_vert_volume<<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  CX_LAUNCH_CHECK(ctx, "k_vert_volume");
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 17, ctx->d_mail + 17, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int err = *(int *)(ctx->h_mail + 17);
+  if (err & VVE_TRIMAX) return cx_fail(ctx, CX_TRIMAX_EXCEEDED, "calc_vert_volume: a vertex has more than trimax triangles");
+  if (err & VVE_FAN) return cx_fail(ctx, CX_FAN_INCOMPLETE, "calc_vert_volume: fan triangles missing from the 27-cell neighbourhood");
+  if (err & VVE_NONMANIFOLD) ctx->last_error = "calc_vert_volume: warning: an edge is shared by more than two segments";
+  return CX_OK;
+}

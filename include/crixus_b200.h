@@ -1,0 +1,159 @@
+/* crixus_b200 -- C-ABI of the B200-native Crixus preprocessing hot path.
+ *
+ * The reference (Azrael3000/Crixus) has no plugin/FFI surface: its hot path is the set of __global__ kernels in
+ * src/crixus_d.cu, launched only from crixus_main (src/crixus.cu:31-1237), parameterised through __constant__
+ * symbols (src/crixus_d.cu:13-32).  This header is the drop-in boundary for that path: one entry point per
+ * reference kernel (same argument meaning, device pointers + sizes), the __constant__ symbols replaced by a
+ * cx_params struct passed by pointer, silent device-side `return`s replaced by error codes in the style of
+ * src/return.h:4-21.  No torch / C++ types cross this boundary.
+ *
+ * Array layouts are the reference's (src/crixus_d.cuh:8-16, src/crixus.cu:225-245):
+ *   pos   float4[nvert+nbe]  vertices then segment barycentres (.w unused)
+ *   norm  float4[nbe]        STL facet normals (.w unused)
+ *   ep    int4[nbe]          the 3 vertex ids of a segment (.w unused)
+ *   surf  float[nbe]         segment areas
+ *   cell_idx int[ncell3+1]   exclusive prefix of segments per 3dr-cell, cell = gx*ny*nz + gy*nz + gz
+ *   fpos  uint32[ceil(G/32)] fluid bitfield, LSB first, cell = i + j*idimg + k*idimg*jdimg
+ * All pointers named *_d are DEVICE pointers on the context's device.  Calls are asynchronous on the context's
+ * stream unless they return a host value (those synchronise the stream).
+ */
+#ifndef CRIXUS_B200_H
+#define CRIXUS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CX_GRES 20   /* src/crixus.h:26  voxels per dr/2 */
+#define CX_TRIMAX 50 /* src/crixus.h:27  max triangles per vertex */
+
+/* error codes: src/return.h:4-21 where one exists, own codes below -100 */
+enum {
+  CX_OK = 0,
+  CX_STL_NOT_BINARY = -1, CX_NO_FILE = -2, CX_FILE_NOT_OPEN = -3, CX_CANT_READ_CONFIG = -4, CX_READ_ERROR = -5,
+  CX_FLUID_NDEF = -6, CX_WRITE_FAIL = -7, CX_NO_PER_VERT = -9, CX_WRONG_INPUT = -11, CX_NO_WRITE_FILE = -16,
+  CX_FLUID_BBOX_TOO_SMALL = -17, CX_INTERNAL_ERROR = -18,
+  CX_CUDA_ERROR = -101,      /* a CUDA runtime call failed; see cx_last_error */
+  CX_TRIMAX_EXCEEDED = -102, /* a vertex has more than CX_TRIMAX triangles (reference: thread returns, crixus_d.cu:306) */
+  CX_FAN_INCOMPLETE = -103,  /* a vertex' triangles were not all found in its 27 cells (mesh precondition violated) */
+  CX_SEED_OUTSIDE = -104,    /* geometry-fill seed outside the fluid lattice (reference: out-of-bounds write) */
+  CX_NO_DEVICE = -105
+};
+
+/* the __constant__ symbols of src/crixus_d.cu:13-32 */
+typedef struct cx_params {
+  float dr;       /* particle spacing */
+  float dr_wall;  /* min distance fluid particle <-> segment (fill_N.dr_wall) */
+  float eps;      /* NOTE: dr/gres*1e-4 up to calc_vert_volume, max(extent)*1e-5 for the fill (crixus.cu:265 vs :464-467) */
+  float dmin[4], dmax[4]; /* domain bounding box (all raw STL corners) */
+  float griddr[4];        /* 3dr-cell edge lengths */
+  int32_t gridn[4];       /* 3dr-cell counts, [3] = product */
+  float fcmin[4], fcmax[4]; /* fluid container */
+  int32_t per[3];           /* periodicity flags */
+} cx_params;
+
+typedef struct cx_ctx cx_ctx;
+
+/* ---- host-side glue of crixus_main, exact restatements (no device work) */
+void cx_params_domain(cx_params *p, float dr, const float bbmin[3], const float bbmax[3]); /* crixus.cu:262-283 */
+void cx_params_fill_eps(cx_params *p);                                                      /* crixus.cu:464-467 */
+void cx_params_container(cx_params *p, int use, const float cmin[3], const float cmax[3]);  /* crixus.cu:698-722 */
+void cx_fill_dims(const cx_params *p, int64_t dimg[3]);                 /* crixus_d.cu:985-987 / crixus.cu:802-803 */
+int64_t cx_seed_index(const cx_params *p, const float spos[3]);         /* crixus.cu:799-804; -1 if outside */
+
+/* ---- context */
+int cx_create(int device, cx_ctx **ctx);   /* selects the device, creates a stream */
+void cx_destroy(cx_ctx *ctx);
+int cx_set_stream(cx_ctx *ctx, void *cuda_stream); /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int cx_synchronize(cx_ctx *ctx);
+const char *cx_last_error(cx_ctx *ctx);
+const char *cx_version(void);
+int64_t cx_kernel_launches(cx_ctx *ctx);   /* number of kernels launched through this context so far */
+
+/* ---- stage entry points, one per reference kernel */
+
+/* swap_normals, crixus_d.cu:203-211 */
+int cx_swap_normals(cx_ctx *ctx, float *norm_d, int64_t nbe);
+
+/* set_bound_elem, crixus_d.cu:105-201.  zstat_host[4] = {xminp, xminn, nminp, nminn} (may be NULL). */
+int cx_set_bound_elem(cx_ctx *ctx, float *pos_d, const float *norm_d, float *surf_d, int32_t *ep_d, int64_t nbe,
+                      int64_t nvert, float *zstat_host);
+
+/* init_cell_idx + count_cell_bes + add_up_indices + sort_bes, crixus_d.cu:37-103, with a STABLE scatter
+ * (original segment order inside a cell; the reference's order is run-dependent, crixus_d.cu:94). */
+int cx_bin_segments(cx_ctx *ctx, const cx_params *p, const float *pre_pos_d, float *pos_d, const float *pre_norm_d,
+                    float *norm_d, const int32_t *pre_ep_d, int32_t *ep_d, const float *pre_surf_d, float *surf_d,
+                    int32_t *cell_idx_d, int64_t nbe, int64_t nvert);
+
+/* find_links, crixus_d.cu:213-237: pairs max-face vertices with min-face vertices in dimension idim, writes newlink
+ * (must be pre-set to -1), deletes paired vertices (pos = -1e10).  Returns CX_NO_PER_VERT if a partner is missing. */
+int cx_find_links(cx_ctx *ctx, const cx_params *p, float *pos_d, int64_t nvert, int32_t *newlink_d, int idim);
+
+/* periodicity_links, crixus_d.cu:240-256 */
+int cx_periodicity_links(cx_ctx *ctx, int32_t *ep_d, int64_t nbe, const int32_t *newlink_d);
+
+/* calc_trisize, crixus_d.cu:258-267 (trisize_d must be zeroed by the caller, as in crixus.cu:423-427) */
+int cx_calc_trisize(cx_ctx *ctx, const int32_t *ep_d, int32_t *trisize_d, int64_t nbe);
+
+/* calc_vert_volume, crixus_d.cu:271-678, for vertices [v_begin, v_end) (index-range sharding; whole mesh: 0, nvert) */
+int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                        float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                        int zero_open, int64_t v_begin, int64_t v_end);
+
+/* fill_fluid, crixus_d.cu:680-744 (box).  *nfi_host = cells in the box (counted even when already set). */
+int cx_fill_box(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float lo[3], const float hi[3],
+                int64_t *nfi_host);
+
+/* fill_fluid_complex driven to its fixed point (crixus_d.cu:965-1058 + loop crixus.cu:934-947) by a frontier/tile
+ * flood fill.  nbe counts wall + fshape segments, the last cnbe of them are the fshape ones (crixus_d.cu:951).
+ * seed = cell index from cx_seed_index (or -1 for none).  *nfi_host = newly set cells, *rounds_host = global rounds. */
+int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                     const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                     int64_t *nfi_host, int32_t *rounds_host);
+
+/* z-slab variant for multi-GPU runs: this rank owns lattice planes [k_begin, k_end); fpos_d is still the full packed
+ * bitfield on every rank (<= 1.25 GB at 1e10 cells) but only owned planes are written.  One call = propagate inside
+ * the slab until locally converged, given the current state of the two halo planes (k_begin-1, k_end) in fpos_d.
+ * *changed_host = number of cells newly set in the slab.  The caller exchanges boundary planes between calls. */
+int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                          int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host);
+
+/* ---- whole hot path on HOST buffers (the call the CLI / a reference maintainer would make; includes H2D/D2H) */
+typedef struct cx_fill_spec {
+  int32_t option;      /* 1 = box, 2 = geometry (crixus.cu:737-741) */
+  float lo[3], hi[3];  /* box */
+  float seed[3];       /* geometry */
+  float dr_wall;       /* geometry; <=0 -> dr */
+} cx_fill_spec;
+
+typedef struct cx_job {
+  /* inputs */
+  const float *corners;     /* nbe*9 floats: raw STL corner coordinates */
+  const float *normals;     /* nbe*3 floats: raw STL facet normals */
+  int64_t nbe;
+  float dr;
+  int32_t swap_normals, zero_open, periodic[3];
+  int32_t use_container; float cmin[3], cmax[3];
+  const float *fs_corners; const float *fs_normals; int64_t fs_nbe; /* optional fshape STL */
+  const cx_fill_spec *fills; int32_t nfills;
+  /* outputs (malloc'd by the library, released by cx_job_free) */
+  int64_t nvert, nfluid, nfluid_counted; /* popcount vs. the reference's running count (App. B-2 of SURVEY.md) */
+  float *pos;  float *norm;  int32_t *ep;  float *surf;  float *vol;  int32_t *cell_idx; uint32_t *fpos;
+  int64_t dimg[3];
+  float zstat[4];
+  cx_params params_fill;
+  double t_weld_s, t_gpu_s, t_h2d_s, t_d2h_s; /* wall-clock breakdown */
+} cx_job;
+
+int cx_preprocess_host(cx_ctx *ctx, cx_job *job);
+void cx_job_free(cx_job *job);
+
+/* host weld, src/crixus.cpp:343-455 (outcome-exact restatement).  out_verts: room for 3*ncorner floats,
+ * out_ids: ncorner ints.  Returns the number of welded vertices. */
+int64_t cx_weld_host(const float *corners, int64_t ncorner, float dr, float *out_verts, int32_t *out_ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+"""The parity cases shared by the oracle tests, the GPU tests and tests/golden/make_golden.py.  Each case is a small
+version of one BASELINE.json config, sized so that the CPU oracle finishes in seconds."""
+import numpy as np
+
+from crixus_b200 import meshgen as mg
+
+
+def _lcg_jitter(verts, tris, normals, amp, amp_n=0.0):
+    rng = np.random.default_rng(mg.RNG_SEED)
+    v = mg.jitter_interior(verts, tris, normals, amp, rng)
+    if amp_n:
+        # out-of-plane jitter of interior vertices (the D.4 sensitivity mesh of SURVEY.md): z only, plate case
+        inner = ~np.isclose(v, verts).all(1)
+        v[inner, 2] += rng.uniform(-amp_n, amp_n, size=int(inner.sum())).astype(np.float32)
+    return v
+
+
+def case(name):
+    """-> dict(tris, normals, dr, swap_normals, periodic, zero_open, container, fills, fshape)"""
+    c = dict(swap_normals=False, periodic=(False, False, False), zero_open=False, container=None, fills=[], fshape=None)
+    if name == "plate":            # KAT-plate, SURVEY.md App. D.3
+        v, t, n = mg.plate(10, 0.1)
+        c.update(dr=0.08)
+    elif name == "plate_jitter":   # D.4: lifted, jittered plate -> generic (non axis-aligned) plane tests
+        v, t, n = mg.plate(24, 0.1)
+        v = v.copy()
+        v[:, 2] += np.float32(0.013)
+        v = _lcg_jitter(v, t, n, 0.01, 0.0025)
+        n = mg.geometric_normals(v, t)
+        c.update(dr=0.08)
+    elif name == "plate_zero_open":
+        v, t, n = mg.plate(6, 0.1)
+        c.update(dr=0.08, zero_open=True)
+    elif name == "cube":           # KAT-cube, SURVEY.md App. D.3
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+        c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)])
+    elif name == "cube_jitter":    # D.5
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+        rng = np.random.default_rng(mg.RNG_SEED)
+        interior = ((v > 1e-6) & (v < 1 - 1e-6)).sum(1) == 2   # face-interior vertices
+        v = v.copy()
+        v[interior] += rng.uniform(-0.003, 0.003, size=(int(interior.sum()), 3)).astype(np.float32)
+        n = mg.geometric_normals(v, t)
+        ctr = v[t].mean(1) - 0.5
+        flip = (n * ctr).sum(1) > 0   # make normals point inward
+        n[flip] *= -1
+        c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)])
+    elif name == "spheric2_mini":  # config 1 at a coarser dr: swap_normals, container, box + geometry fill, fshape
+        dr = 0.06
+        v, t, n = mg.spheric2(dr=dr)
+        fv, ft, fn = mg.spheric2_fshape()
+        c.update(dr=dr, swap_normals=True, container=((0, 0, 0), (1.5, 1.0, 0.6)),
+                 fills=[("box", (0.2, 0.2, 0.2), (0.4, 0.4, 0.4)), ("geometry", (0.5, 0.5, 0.5), dr)], fshape=(fv[ft], fn))
+    elif name == "channel":        # config 3 in small: x/y periodic floor+lid
+        dr = 0.05
+        v, t, n = mg.channel(n=16, dr=dr, height=10 * 1.25 * dr)
+        L = 16 * 1.25 * dr
+        c.update(dr=dr, swap_normals=True, periodic=(True, True, False),
+                 fills=[("geometry", (L / 2, L / 2, 5 * 1.25 * dr), dr)])
+    elif name == "sphere_tank":    # config 4 in small: curved, non axis-aligned triangles
+        dr = 0.05
+        v, t, n = mg.sphere_in_tank(side_cells=20, dr=dr, hfac=1.0, sphere_levels=2)
+        c.update(dr=dr, swap_normals=True, fills=[("geometry", (0.1, 0.1, 0.1), dr)])
+    else:
+        raise KeyError(name)
+    c.update(name=name, tris=np.ascontiguousarray(v[t], dtype=np.float32), normals=np.ascontiguousarray(n, dtype=np.float32),
+             dr=np.float32(c["dr"]))
+    return c
+
+
+ALL = ["plate", "plate_jitter", "plate_zero_open", "cube", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"]
+
+
+def run(B, c, stages=("volume", "fill")):
+    from oracle import orc
+    return orc.run_pipeline(B, c["tris"], c["normals"], c["dr"], swap_normals=c["swap_normals"], periodic=c["periodic"],
+                            zero_open=c["zero_open"], container=c["container"], fills=c["fills"], fshape=c["fshape"], stages=stages)
