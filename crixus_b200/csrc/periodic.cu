@@ -74,9 +74,10 @@ extern "C" int cx_find_links(cx_ctx *ctx, const cx_params *p, float *pos_d, int6
   cudaStream_t st = ctx->stream;
   const double thr = 1e-4 * p->dr;  // double product of a double literal and float dr (crixus_d.cu:217)
   int32_t *fmax, *fmin, *omax, *omin, *lmax, *lmin;
-  CX_CUDA(ctx, cudaMallocAsync(&fmax, sizeof(int32_t) * (size_t)(nvert + 1) * 6, st));
-  fmin = fmax + (nvert + 1); omax = fmin + (nvert + 1); omin = omax + (nvert + 1); lmax = omin + (nvert + 1); lmin = lmax + (nvert + 1);
-  CX_CUDA(ctx, cudaMemsetAsync(fmax, 0, sizeof(int32_t) * (size_t)(nvert + 1) * 2, st));
+  const int64_t stride = (nvert + 1 + 63) & ~(int64_t)63;  // keep every sub-array 16-byte aligned (vectorised scan)
+  CX_CUDA(ctx, cudaMallocAsync(&fmax, sizeof(int32_t) * (size_t)stride * 6, st));
+  fmin = fmax + stride; omax = fmin + stride; omin = omax + stride; lmax = omin + stride; lmin = lmax + stride;
+  CX_CUDA(ctx, cudaMemsetAsync(fmax, 0, sizeof(int32_t) * (size_t)stride * 2, st));
   const int grid = cx_blocks(nvert, 256, ctx->num_sms * 16);
   k_face_flags<<<grid, 256, 0, st>>>((const float4 *)pos_d, nvert, idim, p->dmin[idim], p->dmax[idim], thr, fmax, fmin);
   CX_LAUNCH_CHECK(ctx, "k_face_flags");

@@ -341,15 +341,19 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
 
     // ---------------- the voxel cube: lanes take z-lines (k = x index, l = y index), crixus_d.cu:488-670
     long long acc = 0;
-    for (int line = lane; line < VV_LINES; line += 32) {
-      const int k = line / VV_GS, l = line - k * VV_GS;
-      uint32_t hit_lo = 0u, hit_hi = 0u, alive_lo = 0xffffffffu, alive_hi = 0x1ffu;
+    // all 32 lanes run the same number of iterations (line_loop uses full-warp votes); surplus lanes carry a dead line
+    for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
+      const int line = it * 32 + lane;
+      const bool valid = line < VV_LINES;
+      const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
+      uint32_t hit_lo = valid ? 0u : 0xffffffffu, hit_hi = valid ? 0u : 0x1ffu;
+      uint32_t alive_lo = valid ? 0xffffffffu : 0u, alive_hi = valid ? 0x1ffu : 0u;
       uint32_t hlo[5] = {0u, 0u, 0u, 0u, 0u}, hhi[5] = {0u, 0u, 0u, 0u, 0u};
       // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
       const float g0 = a.gz[k], g1 = a.gz[l];
       if (closed) line_loop<false>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
       else line_loop<true>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
-      acc += group_weight(hit_lo & alive_lo, hlo, a.cmax) + group_weight(hit_hi & alive_hi & 0x1ffu, hhi, a.cmax);
+      if (valid) acc += group_weight(hit_lo & alive_lo, hlo, a.cmax) + group_weight(hit_hi & alive_hi & 0x1ffu, hhi, a.cmax);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -15,22 +15,27 @@ def _lcg_jitter(verts, tris, normals, amp, amp_n=0.0):
     return v
 
 
+# the reference program refuses to run without a fill_0 section (crixus.cu:737,759-763): give the open plates a
+# container above the plate and a small box fill (which also exercises fill_fluid)
+_PLATE_FILL = dict(container=((0, 0, 0), (1.0, 1.0, 0.2)), fills=[("box", (0.4, 0.4, 0.08), (0.6, 0.6, 0.12))])
+
+
 def case(name):
     """-> dict(tris, normals, dr, swap_normals, periodic, zero_open, container, fills, fshape)"""
     c = dict(swap_normals=False, periodic=(False, False, False), zero_open=False, container=None, fills=[], fshape=None)
     if name == "plate":            # KAT-plate, SURVEY.md App. D.3
         v, t, n = mg.plate(10, 0.1)
-        c.update(dr=0.08)
+        c.update(dr=0.08, **_PLATE_FILL)
     elif name == "plate_jitter":   # D.4: lifted, jittered plate -> generic (non axis-aligned) plane tests
         v, t, n = mg.plate(24, 0.1)
         v = v.copy()
         v[:, 2] += np.float32(0.013)
         v = _lcg_jitter(v, t, n, 0.01, 0.0025)
         n = mg.geometric_normals(v, t)
-        c.update(dr=0.08)
+        c.update(dr=0.08, **_PLATE_FILL)
     elif name == "plate_zero_open":
         v, t, n = mg.plate(6, 0.1)
-        c.update(dr=0.08, zero_open=True)
+        c.update(dr=0.08, zero_open=True, container=((0, 0, 0), (0.6, 0.6, 0.2)), fills=[("box", (0.2, 0.2, 0.08), (0.4, 0.4, 0.12))])
     elif name == "cube":           # KAT-cube, SURVEY.md App. D.3
         v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
         c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)])

@@ -75,8 +75,7 @@ def main(outdir):
                             vert_pos=d["vertex"]["Points"].astype(np.float32), vert_vol=d["vertex"]["Volume"],
                             seg_pos=seg["Points"].astype(np.float32), seg_norm=seg["Normal"], seg_surf=seg["Surface"],
                             seg_ep=seg["VertexParticle"].astype(np.int64), fluid_pos=d["fluid"]["Points"].astype(np.float32),
-                            fluid_vol=d["fluid"]["Volume"][:1], n_total=np.int64(d["vertex"]["Points"].shape[0] + seg["Points"].shape[0] +
-                                                                                  d["fluid"]["Points"].shape[0]),
+                            fluid_vol=d["fluid"]["Volume"][:1], n_file=np.int64(read_vtu(os.path.join(work, name + ".vtu"))["n"]),
                             log=np.array(log.stdout))
         print(name, "verts", d["vertex"]["Points"].shape[0], "segs", seg["Points"].shape[0], "fluid", d["fluid"]["Points"].shape[0], flush=True)
 

@@ -44,7 +44,17 @@ def compare_with_golden(g, gold, c, vol_exact=True):
     assert a["vert_pos"].shape == gold["vert_pos"].shape
     np.testing.assert_array_equal(a["vert_pos"], gold["vert_pos"])
     np.testing.assert_array_equal(a["fluid_pos"], gold["fluid_pos"])
-    np.testing.assert_array_equal(a["seg_ep"], gold["seg_ep"])
+    # The reference's running particle count `nfluid` (crixus.cu:944) can exceed the number of fluid particles it
+    # writes by one: fill_fluid_complex keeps its bitfield word in a register (SASS: one LDG before the bit loop, STG
+    # after a fill), so the thread that owns the seed's word can overwrite the seed set by thread 0 and then fill
+    # and count the seed cell a second time (a data race; it shows on the GPU whenever the seed's word is not owned
+    # by warp 0 of block 0, never in the host build).  The extra count shifts every VertexParticle index by one and
+    # leaves one uninitialised record at the end of the file.  We compare modulo that shift and require it to be 0/1.
+    import re
+    counted = int(re.search(r"Creation of (\d+) fluid particles", str(gold["log"])).group(1))   # crixus.cu:963
+    shift = counted - gold["fluid_pos"].shape[0]
+    assert shift in (0, 1), shift
+    np.testing.assert_array_equal(a["seg_ep"] + shift, gold["seg_ep"])
     np.testing.assert_array_equal(a["seg_pos"], gold["seg_pos"])
     np.testing.assert_array_equal(a["seg_norm"], gold["seg_norm"])
     np.testing.assert_array_equal(a["seg_surf"], gold["seg_surf"])
