@@ -32,7 +32,9 @@ class CxFillSpec(C.Structure):
 
 
 class CxJob(C.Structure):
-    _fields_ = [("corners", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("nbe", C.c_int64), ("dr", C.c_float),
+    _fields_ = [("corners", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("nbe", C.c_int64),
+                ("welded_pos", C.POINTER(C.c_float)), ("welded_ep", C.POINTER(C.c_int32)), ("welded_nvert", C.c_int64),
+                ("bbmin", C.c_float * 3), ("bbmax", C.c_float * 3), ("dr", C.c_float),
                 ("swap_normals", C.c_int32), ("zero_open", C.c_int32), ("periodic", C.c_int32 * 3),
                 ("use_container", C.c_int32), ("cmin", C.c_float * 3), ("cmax", C.c_float * 3),
                 ("fs_corners", C.POINTER(C.c_float)), ("fs_normals", C.POINTER(C.c_float)), ("fs_nbe", C.c_int64),
@@ -42,7 +44,8 @@ class CxJob(C.Structure):
                 ("surf", C.POINTER(C.c_float)), ("vol", C.POINTER(C.c_float)), ("cell_idx", C.POINTER(C.c_int32)),
                 ("fpos", C.POINTER(C.c_uint32)), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
                 ("params_fill", CxParams),
-                ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double)]
+                ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double),
+                ("stage_ms", C.c_float * 8)]
 
 
 ERRORS = {0: "CX_OK", -1: "STL_NOT_BINARY", -2: "NO_FILE", -3: "FILE_NOT_OPEN", -4: "CANT_READ_CONFIG", -5: "READ_ERROR",
@@ -82,9 +85,11 @@ def lib():
         "cx_destroy": (None, [VP]),
         "cx_set_stream": (C.c_int, [VP, VP]),
         "cx_synchronize": (C.c_int, [VP]),
+        "cx_get_stream": (VP, [VP]),
         "cx_last_error": (C.c_char_p, [VP]),
         "cx_version": (C.c_char_p, []),
         "cx_kernel_launches": (I64, [VP]),
+        "cx_measure_fp32_peak": (C.c_int, [VP, C.c_int, C.POINTER(C.c_double)]),
         "cx_swap_normals": (C.c_int, [VP, VP, I64]),
         "cx_set_bound_elem": (C.c_int, [VP, VP, VP, VP, VP, I64, I64, C.POINTER(C.c_float)]),
         "cx_bin_segments": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, VP, VP, VP, I64, I64]),
@@ -186,6 +191,11 @@ class Context:
 
     def launches(self):
         return int(self.L.cx_kernel_launches(self.h))
+
+    def measure_fp32_peak(self, reps=5):
+        t = C.c_double(0)
+        self._ck(self.L.cx_measure_fp32_peak(self.h, reps, C.byref(t)))
+        return float(t.value)
 
     def synchronize(self):
         self._ck(self.L.cx_synchronize(self.h))

@@ -92,6 +92,7 @@ int cx_synchronize(cx_ctx *ctx)
   return CX_OK;
 }
 
+void *cx_get_stream(cx_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 const char *cx_last_error(cx_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 int64_t cx_kernel_launches(cx_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

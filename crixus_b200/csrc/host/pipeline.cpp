@@ -35,31 +35,50 @@ extern "C" void cx_job_free(cx_job *job)
 
 extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
 {
-  if (!ctx || !job || !job->corners || !job->normals || job->nbe <= 0 || !(job->dr > 0)) return CX_WRONG_INPUT;
+  if (!ctx || !job || !job->normals || job->nbe <= 0 || !(job->dr > 0)) return CX_WRONG_INPUT;
+  if (!job->corners && !(job->welded_pos && job->welded_ep && job->welded_nvert > 0)) return CX_WRONG_INPUT;
   const int64_t nbe = job->nbe;
   const float dr = job->dr;
   double t0 = now_s();
-  // bounding box over all raw corners (crixus.cu:185-208)
   float bbmin[3] = {1e10f, 1e10f, 1e10f}, bbmax[3] = {-1e10f, -1e10f, -1e10f};
-  for (int64_t c = 0; c < 3 * nbe; c++)
-    for (int k = 0; k < 3; k++) {
-      const float x = job->corners[3 * c + k];
-      bbmin[k] = bbmin[k] > x ? x : bbmin[k];
-      bbmax[k] = bbmax[k] < x ? x : bbmax[k];
+  std::vector<float> h_pos_own, h_norm((size_t)4 * nbe);
+  std::vector<int32_t> h_ep_own;
+  const float *h_pos_p;
+  const int32_t *h_ep_p;
+  int64_t nvert;
+  if (job->welded_pos) {  // the mesh as crixus_main holds it right before the upload (crixus.cu:225-245)
+    nvert = job->welded_nvert;
+    h_pos_p = job->welded_pos;
+    h_ep_p = job->welded_ep;
+    for (int k = 0; k < 3; k++) { bbmin[k] = job->bbmin[k]; bbmax[k] = job->bbmax[k]; }
+  } else {
+    // bounding box over all raw corners (crixus.cu:185-208)
+    for (int64_t c = 0; c < 3 * nbe; c++)
+      for (int k = 0; k < 3; k++) {
+        const float x = job->corners[3 * c + k];
+        bbmin[k] = bbmin[k] > x ? x : bbmin[k];
+        bbmax[k] = bbmax[k] < x ? x : bbmax[k];
+      }
+    // weld (crixus.cu:214)
+    std::vector<float> verts((size_t)9 * nbe);
+    std::vector<int32_t> ids((size_t)3 * nbe);
+    nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
+    h_pos_own.resize((size_t)4 * nvert);
+    h_ep_own.resize((size_t)4 * nbe);
+    for (int64_t v = 0; v < nvert; v++) {
+      h_pos_own[4 * v] = verts[3 * v]; h_pos_own[4 * v + 1] = verts[3 * v + 1]; h_pos_own[4 * v + 2] = verts[3 * v + 2]; h_pos_own[4 * v + 3] = 0.f;
     }
-  // weld (crixus.cu:214)
-  std::vector<float> verts((size_t)9 * nbe);
-  std::vector<int32_t> ids((size_t)3 * nbe);
-  const int64_t nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
-  job->nvert = nvert;
-  std::vector<float> h_pos((size_t)4 * nvert), h_norm((size_t)4 * nbe);
-  std::vector<int32_t> h_ep((size_t)4 * nbe);
-  for (int64_t v = 0; v < nvert; v++) {
-    h_pos[4 * v] = verts[3 * v]; h_pos[4 * v + 1] = verts[3 * v + 1]; h_pos[4 * v + 2] = verts[3 * v + 2]; h_pos[4 * v + 3] = 0.f;
+    for (int64_t i = 0; i < nbe; i++) {
+      for (int k = 0; k < 3; k++) h_ep_own[4 * i + k] = ids[3 * i + k];
+      h_ep_own[4 * i + 3] = 0;
+    }
+    h_pos_p = h_pos_own.data();
+    h_ep_p = h_ep_own.data();
   }
+  job->nvert = nvert;
   for (int64_t i = 0; i < nbe; i++) {
-    for (int k = 0; k < 3; k++) { h_norm[4 * i + k] = job->normals[3 * i + k]; h_ep[4 * i + k] = ids[3 * i + k]; }
-    h_norm[4 * i + 3] = 0.f; h_ep[4 * i + 3] = 0;
+    for (int k = 0; k < 3; k++) h_norm[4 * i + k] = job->normals[3 * i + k];
+    h_norm[4 * i + 3] = 0.f;
   }
   job->t_weld_s = now_s() - t0;
 
@@ -74,18 +93,24 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
       surf.alloc(4 * (size_t)nbe) || cell_idx.alloc(4 * (size_t)(ncell + 1)) || trisize.alloc(4 * (size_t)nvert) ||
       vol.alloc(4 * (size_t)nvert) || newlink.alloc(4 * (size_t)nvert))
     return CX_CUDA_ERROR;
-  CU(cudaMemcpy(pre_pos.p, h_pos.data(), 16 * (size_t)nvert, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pre_pos.p, h_pos_p, 16 * (size_t)nvert, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(pre_norm.p, h_norm.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(pre_ep.p, h_ep.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pre_ep.p, h_ep_p, 16 * (size_t)nbe, cudaMemcpyHostToDevice));
   CU(cudaMemset(trisize.p, 0, 4 * (size_t)nvert));
   CU(cudaMemset(vol.p, 0, 4 * (size_t)nvert));
   job->t_h2d_s = now_s() - t0;
 
   t0 = now_s();
+  cudaEvent_t ev[8];
+  for (int k = 0; k < 8; k++) CU(cudaEventCreate(&ev[k]));
+  cudaStream_t st = (cudaStream_t)cx_get_stream(ctx);
+  CU(cudaEventRecord(ev[0], st));
   if (job->swap_normals) RC(cx_swap_normals(ctx, pre_norm.as<float>(), nbe));  // crixus.cu:310-317
   RC(cx_set_bound_elem(ctx, pre_pos.as<float>(), pre_norm.as<float>(), pre_surf.as<float>(), pre_ep.as<int32_t>(), nbe, nvert, job->zstat));
+  CU(cudaEventRecord(ev[1], st));
   RC(cx_bin_segments(ctx, &p, pre_pos.as<float>(), pos.as<float>(), pre_norm.as<float>(), norm.as<float>(), pre_ep.as<int32_t>(),
                      ep.as<int32_t>(), pre_surf.as<float>(), surf.as<float>(), cell_idx.as<int32_t>(), nbe, nvert));
+  CU(cudaEventRecord(ev[2], st));
   for (int idim = 0; idim < 3; idim++) {  // crixus.cu:391-412
     if (!job->periodic[idim]) continue;
     RC(cx_synchronize(ctx));
@@ -94,10 +119,13 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     RC(cx_periodicity_links(ctx, ep.as<int32_t>(), nbe, newlink.as<int32_t>()));
   }
   for (int k = 0; k < 3; k++) p.per[k] = job->periodic[k] ? 1 : 0;  // crixus.cu:428
+  CU(cudaEventRecord(ev[3], st));
   RC(cx_calc_trisize(ctx, ep.as<int32_t>(), trisize.as<int32_t>(), nbe));
+  CU(cudaEventRecord(ev[4], st));
   RC(cx_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
                          cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
 
+  CU(cudaEventRecord(ev[5], st));
   // ---- fluid (crixus.cu:463-467, 698-961)
   cx_params_fill_eps(&p);
   cx_params_container(&p, job->use_container, job->cmin, job->cmax);
@@ -157,8 +185,11 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
       job->nfluid_counted += nfi;
     }
   }
+  CU(cudaEventRecord(ev[6], st));
   RC(cx_synchronize(ctx));
   job->t_gpu_s = now_s() - t0;
+  for (int k = 0; k < 6; k++) { CU(cudaEventElapsedTime(&job->stage_ms[k], ev[k], ev[k + 1])); }
+  for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
   job->params_fill = p;
 
   // ---- results to the host (crixus.cu:363-365, 413, 456, 962)

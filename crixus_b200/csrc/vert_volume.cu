@@ -41,16 +41,23 @@ struct VVArgs {
   int cmax;        // largest k with 2^-k >= eps (vgrid < eps -> voxel dropped, crixus_d.cu:551,662)
   unsigned long long *work;  // work counter
   int *err;                  // error bits
+  int *big_list;             // vertices deferred to the TCAP=50 launch
+  int *big_count;
   float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
 };
 
-struct VVWarp {
-  float4 plane[CX_TRIMAX][VV_PLANE_F4];
-  int tri[CX_TRIMAX][3];
-  int ecount[CX_TRIMAX];
-  int eseg[CX_TRIMAX][2];
+// per-warp shared-memory working set; TCAP = max fan size it can hold.  Almost every vertex has <= 16 triangles, so the
+// main launch uses TCAP=16 (3 KB per warp, occupancy limited by registers only); the few larger fans are deferred to
+// a second launch with TCAP = trimax = 50.
+template <int TCAP>
+struct VVWarpT {
+  float4 plane[TCAP][VV_PLANE_F4];
+  int tri[TCAP][3];
+  int ecount[TCAP];
+  int eseg[TCAP][2];
   int closed;
 };
+#define VV_TCAP_SMALL 16
 
 __device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 // periodic unwrap of a vertex-to-vertex offset component (crixus_d.cu:513): c += sgn(c)*(-dmax+dmin)
@@ -84,10 +91,10 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane)
   return v;
 }
 
-// bit-sliced +1 on the 5-bit per-voxel halving counters (saturating at 31)
-__device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t bit)
+// bit-sliced +1 on the 5-bit per-voxel halving counters (saturating at 31) for every voxel whose bit is set in `m`
+__device__ __noinline__ void half_inc(uint32_t (&h)[5], uint32_t m)
 {
-  uint32_t c = bit;
+  uint32_t c = m;
 #pragma unroll
   for (int b = 0; b < 5; b++) {
     uint32_t t = h[b] & c;
@@ -98,7 +105,32 @@ __device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t bit)
   for (int b = 0; b < 5; b++) h[b] |= c;  // overflow -> stay at 31
 }
 
-template <bool OPEN>
+// Rare path: some voxel of the line lies within eps of a voronoi or edge plane of triangle j (the wall-plane event,
+// which is COMMON -- every voxel in the plane of a flat wall -- is handled in the fast loop).  Recomputes the line with the
+// same arithmetic and bumps the halving counter once per event (crixus_d.cu:610-612, 622-624, 632/640-642, 659-661).
+struct HalfCtx {
+  float4 P4, P5, P6, P7, P8, P9;
+  float tV, tV2, tW0, tW1, tW2, tE, piz, eps;
+  int open;
+};
+__device__ __noinline__ void half_events(const VVArgs &a, const HalfCtx &c, uint32_t (&hlo)[5], uint32_t (&hhi)[5])
+{
+  const float eps = c.eps;
+  for (int m = 0; m < VV_GS; m++) {
+    const float g = a.gz[m];
+    const float q2 = fadd(g, c.piz);
+    int nh = 0;
+    nh += fabsf(ffma(fsub(q2, c.P5.y), c.P4.z, c.tV)) < eps;
+    if (c.open) nh += fabsf(ffma(fsub(q2, c.P6.w), c.P6.x, c.tV2)) < eps;
+    nh += fabsf(ffma(fsub(g, c.P4.z), c.P9.w, c.tE)) < eps;
+    for (int r = 0; r < nh; r++) {
+      if (m < 32) half_inc(hlo, 1u << m);
+      else half_inc(hhi, 1u << (m - 32));
+    }
+  }
+}
+
+template <bool OPEN, class VVWarp>
 __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1,
                                           uint32_t &hit_lo, uint32_t &hit_hi, uint32_t &alive_lo, uint32_t &alive_hi,
                                           uint32_t (&hlo)[5], uint32_t (&hhi)[5])
@@ -114,6 +146,7 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
       const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
       const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
       const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
+      uint32_t in_lo = 0u, in_hi = 0u;
 #pragma unroll
       for (int m = 0; m < VV_GS; m++) {
         const float g = a.gz[m];
@@ -122,10 +155,13 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
         const bool i2 = fabsf(ffma(g, P2.x, t2)) <= thr;
         const bool i3 = fabsf(ffma(g, P2.w, t3)) <= thr;
         const bool i4 = fabsf(ffma(g, P3.z, t4)) <= thr;
-        const bool in = (i0 && i1 && i2) || (i2 && i3 && i4);
-        if (m < 32) hit_lo |= in ? (1u << (m & 31)) : 0u;
-        else hit_hi |= in ? (1u << (m & 31)) : 0u;
+        if ((i0 && i1 && i2) || (i2 && i3 && i4)) {
+          if (m < 32) in_lo |= 1u << (m & 31);
+          else in_hi |= 1u << (m & 31);
+        }
       }
+      hit_lo |= in_lo;
+      hit_hi |= in_hi;
     }
     // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
     if (!__any_sync(0xffffffffu, (alive_lo | alive_hi) != 0u)) break;
@@ -140,35 +176,46 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
     const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
     const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
     const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
+    // kill mask of this triangle; the (rare) "within eps of a plane" events are only DETECTED here, through the
+    // running minimum of |s| over the line, and handled exactly in half_events()
+    uint32_t k_lo = 0u, k_hi = 0u, hw_lo = 0u, hw_hi = 0u;
+    float mn = 3.0e38f;
 #pragma unroll
     for (int m = 0; m < VV_GS; m++) {
       const float g = a.gz[m];
-      const uint32_t bit = 1u << (m & 31);
       const float q2 = fadd(g, pi.z);
       const float sV = ffma(fsub(q2, P5.y), P4.z, tV);
       bool kill = sV > eps;
-      int nh = (fabsf(sV) < eps) ? 1 : 0;
+      float av = fabsf(sV);
       if (OPEN) {
         const float sV2 = ffma(fsub(q2, P6.w), P6.x, tV2);
         kill |= sV2 > eps;
-        nh += (fabsf(sV2) < eps) ? 1 : 0;
+        av = fminf(av, fabsf(sV2));
       }
       const float w0 = ffma(g, P7.z, tW0), w1 = ffma(g, P8.y, tW1), w2 = ffma(g, P9.x, tW2);
       const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
       const bool hw = fabsf(w0) < eps;
       kill |= inside && !hw;
-      nh += (inside && hw) ? 1 : 0;
       const float sE = ffma(fsub(g, P4.z), P9.w, tE);
       kill |= sE > eps;
-      nh += (fabsf(sE) < eps) ? 1 : 0;
-      if (m < 32) alive_lo &= kill ? ~bit : 0xffffffffu;
-      else alive_hi &= kill ? ~bit : 0xffffffffu;
-      if (nh) {  // rare: the voxel lies within eps of a clipping plane
-        for (int r = 0; r < nh; r++) {
-          if (m < 32) half_inc(hlo, bit);
-          else half_inc(hhi, bit);
-        }
+      mn = fminf(mn, fminf(av, fabsf(sE)));
+      if (m < 32) {
+        if (kill) k_lo |= 1u << (m & 31);
+        if (inside && hw) hw_lo |= 1u << (m & 31);
+      } else {
+        if (kill) k_hi |= 1u << (m & 31);
+        if (inside && hw) hw_hi |= 1u << (m & 31);
       }
+    }
+    alive_lo &= ~k_lo;
+    alive_hi &= ~k_hi;
+    if (hw_lo) half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
+    if (hw_hi) half_inc(hhi, hw_hi);
+    if (mn < eps) {
+      HalfCtx c;
+      c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
+      c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
+      half_events(a, c, hlo, hhi);
     }
   }
 }
@@ -189,8 +236,10 @@ __device__ __forceinline__ long long group_weight(uint32_t va, const uint32_t (&
   return s;
 }
 
-__global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_constant__ VVArgs a)
+template <int TCAP, bool LIST>
+__global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volume(const __grid_constant__ VVArgs a)
 {
+  typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
@@ -200,8 +249,14 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
     unsigned long long widx = 0;
     if (lane == 0) widx = atomicAdd(a.work, 1ull);
     widx = __shfl_sync(0xffffffffu, widx, 0);
-    const int64_t i = a.v_begin + (int64_t)widx;
-    if (i >= a.v_end) break;
+    int64_t i;
+    if (LIST) {
+      if ((int64_t)widx >= (int64_t)*a.big_count) break;
+      i = a.big_list[widx];
+    } else {
+      i = a.v_begin + (int64_t)widx;
+      if (i >= a.v_end) break;
+    }
     __syncwarp();
 
     const float4 pi4 = __ldg(&a.pos[i]);
@@ -213,6 +268,10 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
       continue;
     }
     if (tris <= 0) { if (lane == 0) a.vol[i] = 0.f; continue; }
+    if (tris > TCAP) {  // fan too large for this launch's shared-memory slot: defer
+      if (lane == 0) a.big_list[atomicAdd(a.big_count, 1)] = (int)i;
+      continue;
+    }
 
     const int gx = cell_coord(pi.x, p.dmin[0], p.griddr[0], p.gridn[0]);
     const int gy = cell_coord(pi.y, p.dmin[1], p.griddr[1], p.gridn[1]);
@@ -232,9 +291,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
         const int cnt = m0 + m1 + m2;
         const int incl = warp_incl_scan_i(cnt, lane);
         int off = itris + incl - cnt;
-        if (m0 && off < CX_TRIMAX) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
-        if (m1 && off < CX_TRIMAX) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
-        if (m2 && off < CX_TRIMAX) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
+        if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
+        if (m1 && off < TCAP) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
+        if (m2 && off < TCAP) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
         itris += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
@@ -351,8 +410,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
       uint32_t hlo[5] = {0u, 0u, 0u, 0u, 0u}, hhi[5] = {0u, 0u, 0u, 0u, 0u};
       // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
       const float g0 = a.gz[k], g1 = a.gz[l];
-      if (closed) line_loop<false>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
-      else line_loop<true>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
+      if (closed) line_loop<false, VVWarp>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
+      else line_loop<true, VVWarp>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
       if (valid) acc += group_weight(hit_lo & alive_lo, hlo, a.cmax) + group_weight(hit_hi & alive_hi & 0x1ffu, hhi, a.cmax);
     }
 #pragma unroll
@@ -364,7 +423,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32) k_vert_volume(const __grid_cons
   }
 }
 
-__global__ void k_vv_init(unsigned long long *work, int *err) { *work = 0ull; *err = 0; }
+__global__ void k_vv_init(unsigned long long *work, int *err, int *big_count) { *work = 0ull; *err = 0; if (big_count) *big_count = 0; }
 
 extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
                                    float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
@@ -395,16 +454,24 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   a.cmax = cmax;
   a.work = (unsigned long long *)(ctx->d_mail + 16);
   a.err = (int *)(ctx->d_mail + 17);
-  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err);
+  a.big_count = (int *)(ctx->d_mail + 18);
+  CX_CUDA(ctx, cudaMallocAsync(&a.big_list, sizeof(int) * (size_t)(v_end - v_begin), ctx->stream));
+  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err, a.big_count);
   CX_LAUNCH_CHECK(ctx, "k_vv_init");
   int bps = 0;
-  CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume, VV_WARPS * 32, 0));
+  CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false>, VV_WARPS * 32, 0));
   if (bps < 1) bps = 1;
   int64_t want = (v_end - v_begin + VV_WARPS - 1) / VV_WARPS;
   int64_t grid = (int64_t)ctx->num_sms * bps;
   if (grid > want) grid = want;
-  k_vert_volume<<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  k_vert_volume<VV_TCAP_SMALL, false><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
   CX_LAUNCH_CHECK(ctx, "k_vert_volume");
+  // second launch: the (rare) vertices with more than 16 triangles, work list built by the first launch
+  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, (int *)(ctx->d_mail + 19), nullptr);
+  CX_LAUNCH_CHECK(ctx, "k_vv_init");
+  k_vert_volume<CX_TRIMAX, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  CX_LAUNCH_CHECK(ctx, "k_vert_volume_big");
+  CX_CUDA(ctx, cudaFreeAsync(a.big_list, ctx->stream));
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 17, ctx->d_mail + 17, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const int err = *(int *)(ctx->h_mail + 17);

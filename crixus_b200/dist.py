@@ -1,0 +1,366 @@
+"""Multi-GPU orchestration of the hot path above the C-ABI: one process per GPU, torch.distributed for the plumbing.
+
+What shards and what does not (DESIGN.md "multi-GPU"):
+  * swap_normals / set_bound_elem / cell binning / calc_trisize are HBM-bound passes of ~100-150 B per segment; an
+    all-gather of their outputs over NVLink would move more bytes than recomputing them, so every rank runs them on
+    the full (replicated) mesh -- identical results on every rank because the binning order is stable.
+  * calc_vert_volume (FP32-ALU bound, >99 % of the time) shards by contiguous vertex-index ranges; the volumes
+    (4 B/vertex) are all-gathered.
+  * the geometry fill shards the dr lattice into z-slabs.  Each rank propagates inside its slab to local convergence
+    (cx_fill_geometry_slab), then the two boundary planes are exchanged with the z-neighbours (the packed words covering
+    the plane are OR-ed in) and the global count of new cells is all-reduced; repeat until no rank changed anything.
+    Bit-exactness across rank counts follows from the fixed-point property of the fill.
+
+The partition helpers are pure functions (tested on CPU with gloo, world_size 2, with the CPU oracle as the compute
+backend in tests/test_dist.py)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def split_range(n, world, rank):
+    """contiguous index range [lo, hi) of rank; sizes differ by at most one"""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def split_weighted(weights, world, rank):
+    """contiguous range [lo, hi) with ~equal sum of weights (vertex ranges balanced by trisize)"""
+    c = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
+    tot = c[-1]
+    lo = int(np.searchsorted(c, tot * rank / world, side="left"))
+    hi = int(np.searchsorted(c, tot * (rank + 1) / world, side="left")) if rank + 1 < world else len(weights)
+    return min(lo, len(weights)), min(max(hi, lo), len(weights))
+
+
+def plane_words(dimg, k):
+    """word range [w0, w1) of the packed reference bitfield that covers lattice plane k"""
+    P = int(dimg[0]) * int(dimg[1])
+    return (k * P) // 32, ((k + 1) * P + 31) // 32
+
+
+def exchange_halos(fpos, dimg, k0, k1, rank, world, dist, device_ops):
+    """Sends this rank's two boundary planes to its z-neighbours and ORs the received planes into fpos.
+    fpos: int32 torch tensor holding the packed bitfield (CPU for gloo, CUDA for nccl)."""
+    import torch
+    kd = int(dimg[2])
+    ops, recv = [], []
+    if rank + 1 < world and k1 < kd:          # upper neighbour: send my top plane, receive its bottom plane (k1)
+        a, b = plane_words(dimg, k1 - 1)
+        ops.append(dist.P2POp(dist.isend, fpos[a:b].contiguous(), rank + 1))
+        a, b = plane_words(dimg, k1)
+        buf = torch.empty(b - a, dtype=fpos.dtype, device=fpos.device)
+        ops.append(dist.P2POp(dist.irecv, buf, rank + 1))
+        recv.append((a, b, buf))
+    if rank > 0 and k0 > 0:                   # lower neighbour
+        a, b = plane_words(dimg, k0)
+        ops.append(dist.P2POp(dist.isend, fpos[a:b].contiguous(), rank - 1))
+        a, b = plane_words(dimg, k0 - 1)
+        buf = torch.empty(b - a, dtype=fpos.dtype, device=fpos.device)
+        ops.append(dist.P2POp(dist.irecv, buf, rank - 1))
+        recv.append((a, b, buf))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    for a, b, buf in recv:
+        fpos[a:b] |= buf
+    del device_ops
+
+
+def distributed_fill(slab_fill, fpos, dimg, seed, rank, world, dist):
+    """z-slab sharded geometry fill.  slab_fill(fpos, seed, k0, k1, first_call) -> newly set cells in the slab.
+    Returns (total new cells over all ranks, outer iterations).  Afterwards every rank holds its own slab; call
+    gather_slabs to assemble the full bitfield."""
+    import torch
+    k0, k1 = split_range(int(dimg[2]), world, rank)
+    total, it = 0, 0
+    while True:
+        n = slab_fill(fpos, seed, k0, k1, it == 0) if k1 > k0 else 0
+        t = torch.tensor([n], dtype=torch.int64, device=fpos.device)
+        if world > 1:
+            dist.all_reduce(t)
+        it += 1
+        total += int(t.item())
+        if int(t.item()) == 0 or world == 1:
+            break
+        exchange_halos(fpos, dimg, k0, k1, rank, world, dist, None)
+    return total, it
+
+
+def gather_slabs(fpos, dimg, rank, world, dist):
+    """OR-reduces the per-rank bitfields (each rank only ever sets bits of its own planes + received halos)."""
+    if world > 1:
+        dist.all_reduce(fpos, op=dist.ReduceOp.BOR)
+    return fpos
+
+
+# ---------------------------------------------------------------------------------------------------- GPU hot path
+class ShardedHotPath:
+    """Device-resident hot path for bench.py: holds the welded mesh in HBM and runs one pass per step()."""
+    STAGES = ["restore", "set_bound_elem", "binning", "trisize", "vert_volume", "fill"]
+
+    def __init__(self, ctx, w, rank=0, world=1):
+        import torch
+        from . import api
+        self.ctx, self.w, self.rank, self.world = ctx, w, rank, world
+        self.torch = torch
+        dev = ctx.device
+        nv, nbe = w["nvert"], w["nbe"]
+        self.nv, self.nbe = nv, nbe
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+        self.pos0, self.norm0, self.ep0 = f(w["pos"]), f(w["norm"]), f(w["ep"])
+        self.p = api.params_domain(w["dr"], w["bbmin"], w["bbmax"])
+        self.ncell3 = int(self.p.gridn[3])
+        z4 = lambda n, dt=torch.float32: torch.zeros((n, 4), dtype=dt, device=dev)   # noqa: E731
+        self.pre_pos, self.pos = z4(nv + nbe), z4(nv + nbe)
+        self.pre_norm, self.norm = z4(nbe), z4(nbe)
+        self.pre_ep, self.ep = z4(nbe, torch.int32), z4(nbe, torch.int32)
+        self.pre_surf = torch.zeros(nbe, dtype=torch.float32, device=dev)
+        self.surf = torch.zeros(nbe, dtype=torch.float32, device=dev)
+        self.cell_idx = torch.zeros(self.ncell3 + 1, dtype=torch.int32, device=dev)
+        self.trisize = torch.zeros(nv, dtype=torch.int32, device=dev)
+        self.vol = torch.zeros(nv, dtype=torch.float32, device=dev)
+        self.newlink = torch.zeros(nv, dtype=torch.int32, device=dev)
+        # fill parameters (crixus.cu:464-467, 698-722)
+        self.pf = self.p.copy()
+        for j in range(3):
+            self.pf.per[j] = int(w["periodic"][j])
+        api.params_fill_eps(self.pf)
+        if w["container"] is not None:
+            api.params_container(self.pf, True, *w["container"])
+        else:
+            api.params_container(self.pf, False)
+        self.dimg = api.fill_dims(self.pf)
+        G = int(np.prod(self.dimg))
+        self.fpos = torch.zeros((G + 31) // 32, dtype=torch.int32, device=dev)
+        self.cnbe = 0
+        if w["fshape"] is not None:
+            fs_t, fs_n = w["fshape"]
+            fv, fe = api.weld_host(np.ascontiguousarray(fs_t, dtype=np.float32).reshape(-1, 3), w["dr"])
+            self.cnbe = fe.shape[0]
+            fv4 = np.zeros((fv.shape[0], 4), dtype=np.float32); fv4[:, :3] = fv
+            fn4 = np.zeros((self.cnbe, 4), dtype=np.float32); fn4[:, :3] = fs_n
+            fe4 = np.zeros((self.cnbe, 4), dtype=np.int32); fe4[:, :3] = fe + nv
+            self.fs_pos, self.fs_norm, self.fs_ep = f(fv4), f(fn4), f(fe4)
+            self.fposv = z4(nv + fv.shape[0])
+            self.fnorm, self.fep = z4(nbe + self.cnbe), z4(nbe + self.cnbe, torch.int32)
+        self.v0, self.v1 = 0, nv
+        self.k0, self.k1 = split_range(int(self.dimg[2]), world, rank)
+        self.parallelism = "1 GPU" if world == 1 else "vert-volume: %d vertex ranges + all-gather; fill: %d z-slabs + halo exchange; cheap stages replicated" % (world, world)
+        self.events, self.nfluid, self.fill_rounds = [], 0, 0
+        self._sizes = None
+        # one untimed pass to learn trisize (vertex-range balancing) and the S27 statistic for the byte count
+        self.step()
+        ts = self.trisize.cpu().numpy()
+        alive = self.pos[:nv, 0].cpu().numpy() > -1e9
+        self.nalive = int(alive.sum())
+        self.mean_trisize = float(ts[alive].mean())
+        if world > 1:
+            self._sizes = [split_weighted(ts, world, r) for r in range(world)]
+            self.v0, self.v1 = self._sizes[rank]
+        self.local_verts = int(alive[self.v0:self.v1].sum())
+        cnt = np.diff(self.cell_idx.cpu().numpy()).reshape(self.p.gridn[0], self.p.gridn[1], self.p.gridn[2]).astype(np.int64)
+        pad = np.pad(cnt, 1)
+        s27 = sum(pad[1 + a:pad.shape[0] - 1 + a, 1 + b:pad.shape[1] - 1 + b, 1 + c:pad.shape[2] - 1 + c]
+                  for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1))
+        vpos = w["pos"][self.v0:self.v1, :3]
+        g = [np.clip(((vpos[:, j] - np.float32(self.p.dmin[j])) / np.float32(self.p.griddr[j])).astype(np.int64), 0, self.p.gridn[j] - 1)
+             for j in range(3)]
+        S27 = s27[g[0], g[1], g[2]].astype(np.float64)
+        self.vv_bytes = float((240.0 + 32.0 * S27 + 48.0 * ts[self.v0:self.v1]).sum())   # SURVEY.md §8d bytes / vertex
+        self.vv_kernel_ms = 1.0
+
+    # ---- one pass
+    def step(self, timed=False):
+        torch, ctx, w = self.torch, self.ctx, self.w
+        nv, nbe = self.nv, self.nbe
+        ev = []
+
+        def mark():
+            if timed:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append(e)
+        mark()
+        self.pre_pos[:nv].copy_(self.pos0)          # the welded mesh as uploaded by crixus.cu:295-297
+        self.pre_norm.copy_(self.norm0)
+        self.pre_ep.copy_(self.ep0)
+        mark()
+        if w["swap_normals"]:
+            ctx.swap_normals(self.pre_norm)
+        ctx.set_bound_elem(self.pre_pos, self.pre_norm, self.pre_surf, self.pre_ep, nbe, nv, want_zstat=False)
+        mark()
+        ctx.bin_segments(self.p, self.pre_pos, self.pos, self.pre_norm, self.norm, self.pre_ep, self.ep, self.pre_surf, self.surf,
+                         self.cell_idx, nbe, nv)
+        pv = self.p.copy()
+        for idim in range(3):
+            if w["periodic"][idim]:
+                self.newlink.fill_(-1)
+                ctx.find_links(self.p, self.pos, nv, self.newlink, idim)
+                ctx.periodicity_links(self.ep, nbe, self.newlink)
+            pv.per[idim] = int(w["periodic"][idim])
+        mark()
+        self.trisize.zero_()
+        ctx.calc_trisize(self.ep, self.trisize, nbe)
+        mark()
+        ctx.calc_vert_volume(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"],
+                             self.v0, self.v1)
+        if self.world > 1 and self._sizes is not None:
+            self._allgather_vol()
+        mark()
+        self._fill()
+        mark()
+        if timed:
+            self.events.append(ev)
+        return np.zeros(len(self.STAGES))
+
+    def _allgather_vol(self):
+        import torch.distributed as dist
+        torch = self.torch
+        sizes = self._sizes
+        mx = max(b - a for a, b in sizes)
+        buf = torch.zeros(mx, dtype=torch.float32, device=self.vol.device)
+        buf[: self.v1 - self.v0] = self.vol[self.v0:self.v1]
+        out = torch.empty(mx * self.world, dtype=torch.float32, device=self.vol.device)
+        dist.all_gather_into_tensor(out, buf)
+        for r, (a, b) in enumerate(sizes):
+            self.vol[a:b] = out[r * mx: r * mx + (b - a)]
+
+    def _fill(self):
+        ctx, w, nv, nbe = self.ctx, self.w, self.nv, self.nbe
+        from . import api
+        self.fpos.zero_()
+        if self.cnbe:
+            self.fposv[:nv].copy_(self.pos[:nv]); self.fposv[nv:].copy_(self.fs_pos)
+            self.fnorm[:nbe].copy_(self.norm); self.fnorm[nbe:].copy_(self.fs_norm)
+            self.fep[:nbe].copy_(self.ep); self.fep[nbe:].copy_(self.fs_ep)
+            gn, ge, gp, fnbe = self.fnorm, self.fep, self.fposv, nbe + self.cnbe
+        else:
+            gn, ge, gp, fnbe = self.norm, self.ep, self.pos, nbe
+        nfl, rounds = 0, 0
+        for f in w["fills"]:
+            if f[0] == "box":
+                nfl += ctx.fill_box(self.pf, self.fpos, f[1], f[2])
+                continue
+            p = self.pf.copy()
+            p.dr_wall = np.float32(f[2] if f[2] is not None else w["dr"])
+            seed = api.seed_index(p, f[1])
+            if self.world == 1:
+                nfl += ctx.fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
+                rounds += ctx.last_rounds
+            else:
+                import torch.distributed as dist
+
+                def slab(fpos, seed_, k0, k1, first):
+                    n = ctx.fill_geometry_slab(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed_, k0, k1, first)
+                    self._rounds += ctx.last_rounds
+                    return n
+                self._rounds = 0
+                n, its = distributed_fill(slab, self.fpos, self.dimg, seed, self.rank, self.world, dist)
+                gather_slabs(self.fpos, self.dimg, self.rank, self.world, dist)
+                nfl += n
+                rounds += self._rounds
+        self.nfluid, self.fill_rounds = int(nfl), int(rounds)
+
+    def collect_stage_ms(self):
+        torch = self.torch
+        acc = np.zeros(len(self.STAGES))
+        for ev in self.events:
+            for s in range(len(self.STAGES)):
+                acc[s] += ev[s].elapsed_time(ev[s + 1])
+        self.events = []
+        t = torch.tensor(acc, dtype=torch.float64, device=self.ctx.device)
+        rank0 = acc.copy()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self._stage_rank_local = rank0
+        return t.cpu().numpy()
+
+    # ---- end to end with host buffers
+    def e2e(self, steps, barrier):
+        import time
+        torch, w = self.torch, self.w
+        nv, nbe = self.nv, self.nbe
+        if self.world == 1:
+            from . import api
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+            hpos, hep, hnorm3 = pin(w["pos"]), pin(w["ep"]), pin(np.ascontiguousarray(w["normals"], dtype=np.float32))
+            job = api.CxJob()
+            job.normals = C.cast(hnorm3.data_ptr(), C.POINTER(C.c_float))
+            job.nbe = nbe
+            job.welded_pos = C.cast(hpos.data_ptr(), C.POINTER(C.c_float))
+            job.welded_ep = C.cast(hep.data_ptr(), C.POINTER(C.c_int32))
+            job.welded_nvert = nv
+            for j in range(3):
+                job.bbmin[j], job.bbmax[j] = float(w["bbmin"][j]), float(w["bbmax"][j])
+                job.periodic[j] = int(w["periodic"][j])
+            job.dr = float(w["dr"])
+            job.swap_normals, job.zero_open = int(w["swap_normals"]), int(w["zero_open"])
+            if w["container"] is not None:
+                job.use_container = 1
+                for j in range(3):
+                    job.cmin[j], job.cmax[j] = w["container"][0][j], w["container"][1][j]
+            keep = []
+            if w["fshape"] is not None:
+                fc = np.ascontiguousarray(w["fshape"][0], dtype=np.float32).reshape(-1)
+                fn = np.ascontiguousarray(w["fshape"][1], dtype=np.float32).reshape(-1)
+                keep += [fc, fn]
+                job.fs_corners = fc.ctypes.data_as(C.POINTER(C.c_float))
+                job.fs_normals = fn.ctypes.data_as(C.POINTER(C.c_float))
+                job.fs_nbe = w["fshape"][0].shape[0]
+            specs = (api.CxFillSpec * len(w["fills"]))()
+            for i, f in enumerate(w["fills"]):
+                if f[0] == "box":
+                    specs[i].option = 1
+                    for j in range(3):
+                        specs[i].lo[j], specs[i].hi[j] = f[1][j], f[2][j]
+                else:
+                    specs[i].option = 2
+                    for j in range(3):
+                        specs[i].seed[j] = f[1][j]
+                    specs[i].dr_wall = float(f[2]) if f[2] is not None else 0.0
+            job.fills, job.nfills = specs, len(w["fills"])
+            self.ctx.preprocess_host(job)           # warm-up
+            self.ctx.L.cx_job_free(C.byref(job))
+            barrier()
+            t0 = time.perf_counter()
+            br = {"h2d_s": 0.0, "gpu_s": 0.0, "d2h_s": 0.0}
+            for _ in range(steps):
+                self.ctx.preprocess_host(job)
+                br["h2d_s"] += job.t_h2d_s; br["gpu_s"] += job.t_gpu_s; br["d2h_s"] += job.t_d2h_s
+                nfl = int(job.nfluid)
+                self.ctx.L.cx_job_free(C.byref(job))
+            barrier()
+            dt = time.perf_counter() - t0
+            G = int(np.prod(self.dimg))
+            h2d = 16 * nv + 16 * nbe + 12 * nbe + (w["fshape"][0].shape[0] * 48 if w["fshape"] is not None else 0)
+            d2h = 16 * (nv + nbe) + 16 * nbe * 2 + 4 * nbe + 4 * nv + 4 * (self.ncell3 + 1) + 4 * ((G + 31) // 32)
+            return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * dt / steps, "api": "cx_preprocess_host (welded mesh in pinned host memory)",
+                    "breakdown_ms": {k: 1e3 * v / steps for k, v in br.items()}, "nfluid": nfl}
+        # N > 1: the sharded driver with the input upload and the result download inside the timed region
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        hpos, hep, hnorm = pin(w["pos"]), pin(w["ep"]), pin(w["norm"])
+        out = [torch.empty_like(t, device="cpu").pin_memory() for t in (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.pos0.copy_(hpos, non_blocking=True); self.ep0.copy_(hep, non_blocking=True); self.norm0.copy_(hnorm, non_blocking=True)
+            self.step()
+            for o, t in zip(out, (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)):
+                o.copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=self.ctx.device)
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(t.numel() * t.element_size() for t in (hpos, hep, hnorm))
+        d2h = sum(t.numel() * t.element_size() for t in out)
+        return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * dt / steps, "api": "stage-level C-ABI on every rank, pinned host buffers (per rank)"}

@@ -53,52 +53,54 @@ def _axis(breaks, h):
 
 
 class _Builder:
-    """Accumulates an indexed triangle mesh; vertices are keyed by their float32 bit pattern."""
+    """Accumulates axis-aligned faces as right-triangle grids (vectorised); shared vertices are merged at the end by
+    their float32 bit pattern, so faces built from the same coordinate arrays are conforming and watertight."""
 
     def __init__(self):
         self.verts = []
-        self.index = {}
         self.tris = []
         self.normals = []
-
-    def vid(self, p):
-        p = np.asarray(p, dtype=np.float32)
-        k = p.tobytes()
-        i = self.index.get(k)
-        if i is None:
-            i = len(self.verts)
-            self.index[k] = i
-            self.verts.append(p)
-        return i
+        self.nv = 0
 
     def quad_face(self, axis, const, U, V, normal_sign, keep=None):
         """Axis-aligned face at coordinate ``const`` on ``axis``; U, V are the coordinate arrays of the two other
         axes in cyclic order (axis+1, axis+2).  Each quad gets two right triangles wound to match the normal
-        ``normal_sign`` * e_axis.  keep(iu, iv) -> bool drops quads (holes)."""
+        ``normal_sign`` * e_axis, emitted quad by quad with iu outer and iv inner.  keep(iu, iv) -> bool array drops
+        quads (holes)."""
         a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+        U = np.asarray(U, dtype=np.float32)
+        V = np.asarray(V, dtype=np.float32)
+        nu, nv = len(U), len(V)
+        if nu < 2 or nv < 2:
+            return
+        P = np.zeros((nu, nv, 3), dtype=np.float32)
+        P[..., axis] = np.float32(const)
+        P[..., a1] = U[:, None]
+        P[..., a2] = V[None, :]
+        idx = (np.arange(nu)[:, None] * nv + np.arange(nv)[None, :]) + self.nv
+        a, b, c, d = idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]
+        if normal_sign > 0:   # (a,b,c),(a,c,d) is counter-clockwise seen from +axis
+            t = np.stack([np.stack([a, b, c], -1), np.stack([a, c, d], -1)], 2)
+        else:
+            t = np.stack([np.stack([a, c, b], -1), np.stack([a, d, c], -1)], 2)
+        if keep is not None:
+            iu, iv = np.meshgrid(np.arange(nu - 1), np.arange(nv - 1), indexing="ij")
+            t = t[np.asarray(keep(iu, iv), dtype=bool)]
+        t = t.reshape(-1, 3)
         nrm = np.zeros(3, dtype=np.float32)
         nrm[axis] = normal_sign
-
-        def P(iu, iv):
-            p = np.zeros(3, dtype=np.float32)
-            p[axis] = const
-            p[a1] = U[iu]
-            p[a2] = V[iv]
-            return self.vid(p)
-
-        for iu in range(len(U) - 1):
-            for iv in range(len(V) - 1):
-                if keep is not None and not keep(iu, iv):
-                    continue
-                a, b, c, d = P(iu, iv), P(iu + 1, iv), P(iu + 1, iv + 1), P(iu, iv + 1)
-                # (a,b,c),(a,c,d) is counter-clockwise seen from +axis
-                t1, t2 = ((a, b, c), (a, c, d)) if normal_sign > 0 else ((a, c, b), (a, d, c))
-                self.tris += [t1, t2]
-                self.normals += [nrm, nrm]
+        self.verts.append(P.reshape(-1, 3))
+        self.tris.append(t)
+        self.normals.append(np.tile(nrm, (t.shape[0], 1)))
+        self.nv += nu * nv
 
     def finish(self):
-        return (np.asarray(self.verts, dtype=np.float32).reshape(-1, 3), np.asarray(self.tris, dtype=np.int32).reshape(-1, 3),
-                np.asarray(self.normals, dtype=np.float32).reshape(-1, 3))
+        v = np.concatenate(self.verts)
+        t = np.concatenate(self.tris)
+        n = np.concatenate(self.normals)
+        key = np.ascontiguousarray(v).view(np.dtype((np.void, 12))).ravel()
+        _, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        return v[first].astype(np.float32), inv[t].astype(np.int32), n.astype(np.float32)
 
 
 def soup(verts, tris):
@@ -197,7 +199,7 @@ def box_tank(lo, hi, h, open_top=False, inward=False, obstacle=None):
     hole = None
     if obstacle is not None:
         ix0, ix1, iy0, iy1 = idx(0, olo[0]), idx(0, ohi[0]), idx(1, olo[1]), idx(1, ohi[1])
-        hole = lambda iu, iv: not (ix0 <= iu < ix1 and iy0 <= iv < iy1)  # noqa: E731
+        hole = lambda iu, iv: ~((ix0 <= iu) & (iu < ix1) & (iy0 <= iv) & (iv < iy1))  # noqa: E731
     # z faces: axis 2 -> (U,V) = (x,y)
     b.quad_face(2, ax[2][0], ax[0], ax[1], -s, keep=hole)
     if not open_top:

@@ -66,9 +66,11 @@ int cx_create(int device, cx_ctx **ctx);   /* selects the device, creates a stre
 void cx_destroy(cx_ctx *ctx);
 int cx_set_stream(cx_ctx *ctx, void *cuda_stream); /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
 int cx_synchronize(cx_ctx *ctx);
+void *cx_get_stream(cx_ctx *ctx);            /* the cudaStream_t the context launches on */
 const char *cx_last_error(cx_ctx *ctx);
 const char *cx_version(void);
 int64_t cx_kernel_launches(cx_ctx *ctx);   /* number of kernels launched through this context so far */
+int cx_measure_fp32_peak(cx_ctx *ctx, int reps, double *tflops); /* FFMA micro-benchmark: roofline denominator */
 
 /* ---- stage entry points, one per reference kernel */
 
@@ -129,9 +131,15 @@ typedef struct cx_fill_spec {
 
 typedef struct cx_job {
   /* inputs */
-  const float *corners;     /* nbe*9 floats: raw STL corner coordinates */
+  const float *corners;     /* nbe*9 floats: raw STL corner coordinates (may be NULL when the welded mesh is given) */
   const float *normals;     /* nbe*3 floats: raw STL facet normals */
   int64_t nbe;
+  /* optional: the already welded mesh, i.e. exactly what crixus_main uploads at crixus.cu:295-297.  When welded_pos is
+   * non-NULL the host weld is skipped; bbmin/bbmax (bounding box of the raw corners, crixus.cu:185-208) must be set. */
+  const float *welded_pos;  /* welded_nvert*4 floats (float4) */
+  const int32_t *welded_ep; /* nbe*4 ints (int4) */
+  int64_t welded_nvert;
+  float bbmin[3], bbmax[3];
   float dr;
   int32_t swap_normals, zero_open, periodic[3];
   int32_t use_container; float cmin[3], cmax[3];
@@ -144,6 +152,7 @@ typedef struct cx_job {
   float zstat[4];
   cx_params params_fill;
   double t_weld_s, t_gpu_s, t_h2d_s, t_d2h_s; /* wall-clock breakdown */
+  float stage_ms[8]; /* CUDA-event times: 0 swap+set_bound_elem, 1 binning, 2 periodic links, 3 trisize, 4 vert volume, 5 fills */
 } cx_job;
 
 int cx_preprocess_host(cx_ctx *ctx, cx_job *job);

@@ -680,30 +680,35 @@ static int check_collision(const orc_params *p, int64_t si, int64_t sj, int64_t 
 static inline int getbit(const uint32_t *f, int64_t b) { return (f[b >> 5] >> (b & 31)) & 1u; }
 
 /* fill_fluid_complex driven to its fixed point (src/crixus_d.cu:965-1058, loop src/crixus.cu:934-947).
- * Sweeps in cell-index order on one thread (a legal schedule of the reference: its result is the unique least
+ * The _slab variant sweeps only the lattice planes [k0,k1) (cells outside are read-only): the unit of the z-slab
+ * sharded multi-GPU fill.  Sweeps in cell-index order on one thread (a legal schedule of the reference: its result is the unique least
  * fixed point).  seed < 0: no seed.  Returns the number of newly set cells; *sweeps_out = sweeps. */
-int64_t orc_fill_geometry(const orc_params *p, uint32_t *fpos, const float *norm, const int32_t *ep, const float *pos,
-                          int64_t nbe, int64_t cnbe, const int32_t *cell_idx, int64_t seed, int *sweeps_out)
+int64_t orc_fill_geometry_slab(const orc_params *p, uint32_t *fpos, const float *norm, const int32_t *ep, const float *pos,
+                               int64_t nbe, int64_t cnbe, const int32_t *cell_idx, int64_t seed, int64_t k0, int64_t k1,
+                               int *sweeps_out)
 {
   int64_t dimg[3], total = 0;
   orc_fill_dims(p, dimg);
-  const int64_t G = dimg[0] * dimg[1] * dimg[2];
+  const int64_t plane = dimg[0] * dimg[1];
   int it = 0;
   int64_t nfi;
   do {
     it++;
     nfi = 0;
-    if (it == 1 && seed >= 0 && !getbit(fpos, seed)) { fpos[seed >> 5] |= 1u << (seed & 31); nfi++; } /* :972-980 */
-    for (int64_t b = 0; b < G; b++) {
+    if (it == 1 && seed >= 0 && seed / plane >= k0 && seed / plane < k1 && !getbit(fpos, seed)) { /* :972-980 */
+      fpos[seed >> 5] |= 1u << (seed & 31);
+      nfi++;
+    }
+    for (int64_t b = k0 * plane; b < k1 * plane; b++) {
       if (getbit(fpos, b)) continue;
-      const int64_t k = b / (dimg[0] * dimg[1]), tmp = b % (dimg[0] * dimg[1]), j = tmp / dimg[0], i = tmp % dimg[0];
+      const int64_t k = b / plane, tmp = b % plane, j = tmp / dimg[0], i = tmp % dimg[0];
       for (int ij = 0; ij < 6; ij++) { /* :1005-1028, order -x +x -y +y -z +z */
         int64_t io = i, jo = j, ko = k;
         if (ij <= 1) io += (ij == 0) ? -1 : 1;
         else if (ij <= 3) jo += (ij == 2) ? -1 : 1;
         else ko += (ij == 4) ? -1 : 1;
         if (io < 0 || io >= dimg[0] || jo < 0 || jo >= dimg[1] || ko < 0 || ko >= dimg[2]) continue;
-        const int64_t o = io + jo * dimg[0] + ko * dimg[0] * dimg[1];
+        const int64_t o = io + jo * dimg[0] + ko * plane;
         if (getbit(fpos, o) && !check_collision(p, i, j, k, io, jo, ko, norm, ep, pos, nbe, cnbe, cell_idx)) {
           fpos[b >> 5] |= 1u << (b & 31);
           nfi++;
@@ -715,6 +720,15 @@ int64_t orc_fill_geometry(const orc_params *p, uint32_t *fpos, const float *norm
   } while (nfi > 0 && it < MAX_ITERATIONS);
   if (sweeps_out) *sweeps_out = it;
   return total;
+}
+
+/* whole lattice: the slab [0, kdim) */
+int64_t orc_fill_geometry(const orc_params *p, uint32_t *fpos, const float *norm, const int32_t *ep, const float *pos,
+                          int64_t nbe, int64_t cnbe, const int32_t *cell_idx, int64_t seed, int *sweeps_out)
+{
+  int64_t dimg[3];
+  orc_fill_dims(p, dimg);
+  return orc_fill_geometry_slab(p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed, 0, dimg[2], sweeps_out);
 }
 
 /* one directed test, exported so tests can probe single (s,e) pairs against the shim build */

@@ -71,6 +71,9 @@ class Oracle:
         L.orc_fill_box.restype = C.c_int64
         L.orc_fill_geometry.argtypes = [P, u32p, f32p, i32p, f32p, C.c_int64, C.c_int64, i32p, C.c_int64, C.POINTER(C.c_int)]
         L.orc_fill_geometry.restype = C.c_int64
+        L.orc_fill_geometry_slab.argtypes = [P, u32p, f32p, i32p, f32p, C.c_int64, C.c_int64, i32p, C.c_int64, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_int)]
+        L.orc_fill_geometry_slab.restype = C.c_int64
         L.orc_check_collision.argtypes = [P, i64p, i64p, f32p, i32p, f32p, C.c_int64, C.c_int64, i32p]
         L.orc_num_threads.restype = C.c_int
         self.L = L
@@ -147,6 +150,11 @@ class Oracle:
         n = int(self.L.orc_fill_geometry(C.byref(p), fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed, C.byref(sw)))
         self.last_sweeps = sw.value
         return n
+
+    def fill_geometry_slab(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed, k0, k1, first_call=True):
+        sw = C.c_int(0)
+        return int(self.L.orc_fill_geometry_slab(C.byref(p), fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed if first_call else -1,
+                                                 k0, k1, C.byref(sw)))
 
     def check_collision(self, p, s, e, norm, ep, pos, nbe, cnbe, cell_idx):
         return int(self.L.orc_check_collision(C.byref(p), np.asarray(s, dtype=np.int64), np.asarray(e, dtype=np.int64),

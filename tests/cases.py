@@ -36,6 +36,13 @@ def case(name):
     elif name == "plate_zero_open":
         v, t, n = mg.plate(6, 0.1)
         c.update(dr=0.08, zero_open=True, container=((0, 0, 0), (0.6, 0.6, 0.2)), fills=[("box", (0.2, 0.2, 0.08), (0.4, 0.4, 0.12))])
+    elif name == "fan20":          # one vertex with 20 triangles (> the 16-triangle fast path, < trimax = 50)
+        k = 20
+        ang = 2 * np.pi * np.arange(k) / k
+        v = np.concatenate([[[0.5, 0.5, 0.0]], np.stack([0.5 + 0.07 * np.cos(ang), 0.5 + 0.07 * np.sin(ang), np.zeros(k)], 1)]).astype(np.float32)
+        t = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+        n = np.tile(np.array([0, 0, 1], dtype=np.float32), (k, 1))
+        c.update(dr=0.08, **_PLATE_FILL)
     elif name == "cube":           # KAT-cube, SURVEY.md App. D.3
         v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
         c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)])
@@ -44,7 +51,9 @@ def case(name):
         rng = np.random.default_rng(mg.RNG_SEED)
         interior = ((v > 1e-6) & (v < 1 - 1e-6)).sum(1) == 2   # face-interior vertices
         v = v.copy()
-        v[interior] += rng.uniform(-0.003, 0.003, size=(int(interior.sum()), 3)).astype(np.float32)
+        ids = np.nonzero(interior)[0]
+        ids = ids[np.lexsort((v[ids, 2], v[ids, 1], v[ids, 0]))]   # independent of the generator's vertex numbering
+        v[ids] += rng.uniform(-0.003, 0.003, size=(ids.size, 3)).astype(np.float32)
         n = mg.geometric_normals(v, t)
         ctr = v[t].mean(1) - 0.5
         flip = (n * ctr).sum(1) > 0   # make normals point inward
@@ -73,7 +82,7 @@ def case(name):
     return c
 
 
-ALL = ["plate", "plate_jitter", "plate_zero_open", "cube", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"]
+ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"]
 
 
 def run(B, c, stages=("volume", "fill")):
