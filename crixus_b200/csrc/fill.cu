@@ -8,12 +8,14 @@
 //   * a classification pass marks the cells whose test can be non-trivial ("hard": a non-empty 27-cell
 //     neighbourhood in the 3dr grid, or close to a free-surface triangle).  For every other cell
 //     checkCollision is provably false, so propagation is pure bit arithmetic on 32-cell words;
-//   * tiles of 1 word x 16 x 16 rows are iterated to local convergence in shared memory; hard candidates are
-//     compacted into a shared-memory queue and evaluated warp-cooperatively (lanes stride the cell-sorted
-//     segments of the 27 neighbour cells, all open directions of a cell share the distance computation);
-//     failed directed tests are memoised in 6 "blocked" bit planes so that no pair is tested twice;
-//   * a tile that changed activates its 6 face neighbours for the next round; rounds continue until no tile is
-//     active.  Only active tiles are touched: work ~ filled volume + wall area, not sweeps x grid.
+//   * the lattice is cut into tiles of 1 word x 16 x 16 rows.  The first time the flood reaches a tile, ALL hard cells
+//     of the tile are resolved in one bulk, perfectly parallel pass (k_resolve_tiles): one warp per cell, lanes
+//     stride the cell-sorted segments of the 27 neighbour cells, the 6 directions of a cell share the distance
+//     computation; the results are 6 "blocked" bit planes.  The directed tests are pure functions of (s,e), so
+//     evaluating them before they are needed changes nothing but the schedule;
+//   * propagation is then bit arithmetic for every cell: tiles are iterated to local convergence in shared memory
+//     (k_fill_tiles); a tile that changed activates its 6 face neighbours for the next round; rounds continue
+//     until no tile is active.  Only reached tiles are touched: work ~ filled volume + wall area.
 // Bound: HBM, 0.25 B/cell + 8 B/filled cell -- in practice latency/round bound.
 #include <math.h>
 #include <string.h>
@@ -23,7 +25,6 @@
 #define FT_Y 16
 #define FT_Z 16
 #define FT_THREADS (FT_Y * FT_Z)
-#define FT_QCAP 1024
 #define FS_MAX_DESC 512
 
 // ================================================================================================ box fill
@@ -111,7 +112,9 @@ struct FillArgs {
   int nfs, all_hard;
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
-  int32_t *count;               // [0] = list length, [1] = cursor
+  int32_t *count;               // [0] = list length, [1] = cursor, [2] = resolve-list length, [3] = resolve cursor
+  uint8_t *tile_res;            // tile already resolved (blocked planes valid)
+  int32_t *rlist;               // tiles to resolve this round
   unsigned long long *changed;  // newly set cells
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
@@ -381,7 +384,7 @@ __global__ void k_seed(FillArgs A, int64_t seed)
 }
 
 // ---- one round -------------------------------------------------------------------------------------------------
-__global__ void k_round_prep(int32_t *count) { count[0] = 0; count[1] = 0; }
+__global__ void k_round_prep(int32_t *count) { count[0] = 0; count[1] = 0; count[2] = 0; count[3] = 0; }
 
 __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
 {
@@ -389,30 +392,70 @@ __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
     if (A.act_cur[t]) {
       A.act_cur[t] = 0;
       A.list[atomicAdd(&A.count[0], 1)] = (int32_t)t;
+      if (!A.tile_res[t]) {   // first visit: its hard cells are resolved before k_fill_tiles runs
+        A.tile_res[t] = 1;
+        A.rlist[atomicAdd(&A.count[2], 1)] = (int32_t)t;
+      }
     }
+}
+
+// bulk resolution of the hard cells of newly reached tiles: one warp per 32-cell word, one warp-cooperative
+// checkCollision per hard cell for all of its in-lattice directions at once
+__global__ void __launch_bounds__(256) k_resolve_tiles(FillArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&A.count[3], 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= A.count[2] * FT_THREADS) break;
+    const int tile = A.rlist[item / FT_THREADS], wt = item % FT_THREADS;
+    const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
+    const int j = tyi * FT_Y + wt % FT_Y, k = tzi * FT_Z + wt / FT_Y;
+    if (j >= A.dimg[1] || k >= A.dimg[2] || k < A.k_lo || k >= A.k_hi) continue;
+    const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
+    uint32_t todo = A.H[wi] & ~A.F[wi];
+    if (!todo) continue;
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int i = wx * 32 + b;
+      const uint32_t dm = (i > 0 ? 1u : 0u) | (i + 1 < A.dimg[0] ? 2u : 0u) | (j > 0 ? 4u : 0u) | (j + 1 < A.dimg[1] ? 8u : 0u) |
+                          (k > 0 ? 16u : 0u) | (k + 1 < A.dimg[2] ? 32u : 0u);
+      const uint32_t coll = warp_check_collision(A, i, j, k, dm, lane);
+      const uint32_t bit = 1u << b;
+      if (coll & 1u) b0 |= bit;
+      if (coll & 2u) b1 |= bit;
+      if (coll & 4u) b2 |= bit;
+      if (coll & 8u) b3 |= bit;
+      if (coll & 16u) b4 |= bit;
+      if (coll & 32u) b5 |= bit;
+    }
+    if (lane == 0) {
+      A.B[0 * A.nw + wi] = b0; A.B[1 * A.nw + wi] = b1; A.B[2 * A.nw + wi] = b2;
+      A.B[3 * A.nw + wi] = b3; A.B[4 * A.nw + wi] = b4; A.B[5 * A.nw + wi] = b5;
+    }
+  }
 }
 
 struct TileSM {
   uint32_t F[FT_Z + 2][FT_Y + 2];  // filled, with y/z halo
-  uint32_t XL[FT_Z][FT_Y];         // word to the left (only bit 31 is used) / right (bit 0)
-  uint32_t XR[FT_Z][FT_Y];
-  uint32_t H[FT_Z][FT_Y];
-  uint32_t B[6][FT_Z][FT_Y];
-  uint32_t Q[FT_QCAP];             // hard candidates: (dmask << 16) | (bit << 8) | word
-  int qn, changed, anyhard, bdirty, overflow;
-  uint32_t newbits;
+  int changed, newbits;
 };
 
+// propagation inside active tiles: pure bit arithmetic (all directed tests of the tile are already in the B planes)
 __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
 {
   __shared__ TileSM S;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_t;
+  const int tid = threadIdx.x;
   const int ly = tid % FT_Y, lz = tid / FT_Y;
   for (;;) {
-    __shared__ int s_t;
     if (tid == 0) {
       const int q = atomicAdd(&A.count[1], 1);
       s_t = q < A.count[0] ? A.list[q] : -1;
+      S.newbits = 0;
     }
     __syncthreads();
     const int tile = s_t;
@@ -433,43 +476,29 @@ __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
     const bool inrow = j < A.dimg[1] && k < A.dimg[2];
     const bool owned = inrow && k >= A.k_lo && k < A.k_hi;
     const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
-    uint32_t hmask = 0;
-    {
-      uint32_t xl = 0, xr = 0;
-      if (inrow) {
-        if (wx > 0) xl = A.F[wi - 1];
-        if (wx + 1 < A.wr) xr = A.F[wi + 1];
-        hmask = A.H[wi];
+    uint32_t xl = 0, xr = 0, hmask = 0;
+    // per direction: cells that may be entered from that neighbour (easy cells always, hard cells unless blocked)
+    uint32_t o0 = vmask, o1 = vmask, o2 = vmask, o3 = vmask, o4 = vmask, o5 = vmask;
+    if (inrow) {
+      if (wx > 0) xl = A.F[wi - 1] >> 31;
+      if (wx + 1 < A.wr) xr = A.F[wi + 1] << 31;
+      hmask = A.H[wi];
+      if (hmask) {
+        o0 &= ~(hmask & A.B[0 * A.nw + wi]); o1 &= ~(hmask & A.B[1 * A.nw + wi]); o2 &= ~(hmask & A.B[2 * A.nw + wi]);
+        o3 &= ~(hmask & A.B[3 * A.nw + wi]); o4 &= ~(hmask & A.B[4 * A.nw + wi]); o5 &= ~(hmask & A.B[5 * A.nw + wi]);
       }
-      S.XL[lz][ly] = xl; S.XR[lz][ly] = xr; S.H[lz][ly] = hmask;
     }
-    if (tid == 0) { S.anyhard = 0; S.bdirty = 0; S.newbits = 0; }
     __syncthreads();
-    if (hmask) S.anyhard = 1;
-    __syncthreads();
-    const bool anyhard = S.anyhard != 0;
-    if (anyhard) {
-#pragma unroll
-      for (int d = 0; d < 6; d++) S.B[d][lz][ly] = inrow ? A.B[d * A.nw + wi] : 0u;
-    }
     const uint32_t f_start = S.F[lz + 1][ly + 1];
-    __syncthreads();
-
-    // ---- iterate to local convergence (bounded: every iteration sets a bit or resolves queued candidates)
+    // ---- iterate to local convergence (every productive iteration sets at least one bit)
     for (int iter = 0; iter < 200000; iter++) {
-      if (tid == 0) { S.qn = 0; S.changed = 0; S.overflow = 0; }
+      if (tid == 0) S.changed = 0;
       __syncthreads();
       if (owned) {
-        uint32_t f = S.F[lz + 1][ly + 1];
-        const uint32_t nb_xm = (f << 1) | (S.XL[lz][ly] >> 31);  // neighbour at i-1 is set
-        const uint32_t nb_xp = (f >> 1) | (S.XR[lz][ly] << 31);
-        const uint32_t nb_ym = S.F[lz + 1][ly], nb_yp = S.F[lz + 1][ly + 2];
-        const uint32_t nb_zm = S.F[lz][ly + 1], nb_zp = S.F[lz + 2][ly + 1];
-        const uint32_t open = vmask & ~hmask;
-        uint32_t nf = f | ((nb_xm | nb_xp | nb_ym | nb_yp | nb_zm | nb_zp) & open);
-        // free propagation along x inside the word through easy cells
-        for (;;) {
-          const uint32_t g = (((nf << 1) | (nf >> 1)) & open) & ~nf;
+        const uint32_t f = S.F[lz + 1][ly + 1];
+        uint32_t nf = f | (S.F[lz + 1][ly] & o2) | (S.F[lz + 1][ly + 2] & o3) | (S.F[lz][ly + 1] & o4) | (S.F[lz + 2][ly + 1] & o5);
+        for (;;) {   // x direction inside the word (and from the two neighbouring words)
+          const uint32_t g = ((((nf << 1) | xl) & o0) | (((nf >> 1) | xr) & o1)) & ~nf;
           if (!g) break;
           nf |= g;
         }
@@ -477,57 +506,16 @@ __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
           S.F[lz + 1][ly + 1] = nf;
           S.changed = 1;
         }
-        if (hmask) {
-          // hard candidates: unset hard cells with a set neighbour whose directed test is not known to fail
-          const uint32_t xm = (nf << 1) | (S.XL[lz][ly] >> 31), xp = (nf >> 1) | (S.XR[lz][ly] << 31);
-          const uint32_t c0 = xm & ~S.B[0][lz][ly], c1 = xp & ~S.B[1][lz][ly], c2 = nb_ym & ~S.B[2][lz][ly],
-                         c3 = nb_yp & ~S.B[3][lz][ly], c4 = nb_zm & ~S.B[4][lz][ly], c5 = nb_zp & ~S.B[5][lz][ly];
-          uint32_t cand = (c0 | c1 | c2 | c3 | c4 | c5) & hmask & ~nf & vmask;
-          while (cand) {
-            const int b = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const uint32_t dm = ((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3) |
-                                (((c4 >> b) & 1) << 4) | (((c5 >> b) & 1) << 5);
-            const int q = atomicAdd(&S.qn, 1);
-            if (q < FT_QCAP) S.Q[q] = (dm << 16) | ((uint32_t)b << 8) | (uint32_t)tid;
-            else S.overflow = 1;
-          }
-        }
       }
       __syncthreads();
-      const int qn = min(S.qn, FT_QCAP);
-      // ---- hard candidates, one warp per candidate cell
-      for (int q = warp; q < qn; q += FT_THREADS / 32) {
-        const uint32_t it = S.Q[q];
-        const int wtid = it & 0xff, b = (it >> 8) & 0xff;
-        const uint32_t dm = it >> 16;
-        const int qy = wtid % FT_Y, qz = wtid / FT_Y;
-        const uint32_t coll = warp_check_collision(A, wx * 32 + b, j0 + qy, k0 + qz, dm, lane);
-        if (lane == 0) {
-          if (coll != dm) {  // some direction is free -> fill
-            atomicOr(&S.F[qz + 1][qy + 1], 1u << b);
-            S.changed = 1;
-          } else {
-            for (int d = 0; d < 6; d++)
-              if (dm >> d & 1) atomicOr(&S.B[d][qz][qy], 1u << b);
-            S.bdirty = 1;
-          }
-        }
-      }
-      __syncthreads();
-      if (!S.changed && !S.overflow) break;
+      if (!S.changed) break;
       __syncthreads();
     }
-
     // ---- write back + activate neighbours
     const uint32_t f_end = S.F[lz + 1][ly + 1];
     if (owned && f_end != f_start) {
       A.F[wi] = f_end;
-      atomicAdd(&S.newbits, (uint32_t)__popc(f_end & ~f_start));
-    }
-    if (anyhard && S.bdirty && owned) {
-#pragma unroll
-      for (int d = 0; d < 6; d++) A.B[d * A.nw + wi] = S.B[d][lz][ly];
+      atomicAdd(&S.newbits, __popc(f_end & ~f_start));
     }
     __syncthreads();
     if (tid == 0 && S.newbits) atomicAdd(A.changed, (unsigned long long)S.newbits);
@@ -549,8 +537,8 @@ struct FillState {
   int64_t dimg[3] = {0, 0, 0};
   int64_t nbe = 0, cnbe = 0;
   uint32_t *F = nullptr, *H = nullptr, *B = nullptr;
-  uint8_t *nbflag = nullptr, *act = nullptr;
-  int32_t *list = nullptr, *count = nullptr;
+  uint8_t *nbflag = nullptr, *act = nullptr, *tile_res = nullptr;
+  int32_t *list = nullptr, *count = nullptr, *rlist = nullptr;
   FsDesc *fs = nullptr;
   int nfs = 0, all_hard = 0;
   int64_t nw = 0, ntiles = 0;
@@ -561,7 +549,7 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->H); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->tile_res); cudaFree(s->rlist);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -619,7 +607,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
     CX_CUDA(ctx, cudaMalloc(&s->act, (size_t)ntiles * 2));
     CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
-    CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 2));
+    CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 4));
+    CX_CUDA(ctx, cudaMalloc(&s->tile_res, (size_t)ntiles));
+    CX_CUDA(ctx, cudaMalloc(&s->rlist, sizeof(int32_t) * (size_t)ntiles));
+    CX_CUDA(ctx, cudaMemsetAsync(s->tile_res, 0, (size_t)ntiles, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)ntiles * 2, st));
     // fshape descriptors
@@ -658,6 +649,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->k_lo = 0; A->k_hi = (int)dimg[2];
   A->F = s->F; A->H = s->H; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
   A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
+  A->tile_res = s->tile_res; A->rlist = s->rlist;
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
   A->drw2 = p->dr_wall * p->dr_wall;
   A->one_eps = 1.0 + (double)p->eps;
@@ -686,6 +678,8 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_o
       CX_LAUNCH_CHECK(ctx, "k_round_prep");
       k_build_list<<<cx_blocks(A->ntiles, 256, ctx->num_sms * 8), 256, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_build_list");
+      k_resolve_tiles<<<ctx->num_sms * 4, 256, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_resolve_tiles");
       A->force_activate = (rounds == 0);
       k_fill_tiles<<<grid_tiles, FT_THREADS, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_fill_tiles");

@@ -130,6 +130,13 @@ __device__ __noinline__ void half_events(const VVArgs &a, const HalfCtx &c, uint
   }
 }
 
+// One z-line of 41 voxels against every fan triangle.
+//
+// Exact line-level culling: along a line only gz changes, gz[m] is non-decreasing in m, and every plane expression is
+// a composition of correctly rounded (hence monotone) operations of gz, so each expression is (weakly) monotone in m
+// and its values on the line lie between its values at the two ends m=0 and m=40.  Evaluating the ends with the very
+// same arithmetic therefore decides, exactly, whether a test can have any effect on the line ("none"), or kills the
+// whole line ("all"); only lines that are genuinely cut by a plane run the per-voxel loop, and only for that plane.
 template <bool OPEN, class VVWarp>
 __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1,
                                           uint32_t &hit_lo, uint32_t &hit_hi, uint32_t &alive_lo, uint32_t &alive_hi,
@@ -137,31 +144,44 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
 {
   const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
   const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
+  const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
+  const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
   for (int j = 0; j < tris; j++) {
     // ---------------- cubes (crixus_d.cu:531-543): voxel is sampled if it lies in one of the two dr-cubes of j
-    if (__any_sync(0xffffffffu, (hit_lo != 0xffffffffu) | (hit_hi != 0x1ffu))) {
+    const bool need_hit = (hit_lo != 0xffffffffu) | (hit_hi != 0x1ffu);
+    if (__any_sync(0xffffffffu, need_hit)) {
       const float4 P0 = w.plane[j][0], P1 = w.plane[j][1], P2 = w.plane[j][2], P3 = w.plane[j][3];
       const float t0 = ffma(gp1, P0.y, ffma(gp0, P0.x, 0.f));  // c0
       const float t1 = ffma(gp1, P1.x, ffma(gp0, P0.w, 0.f));  // c1
       const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
       const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
       const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
-      uint32_t in_lo = 0u, in_hi = 0u;
+      // both ends inside a cube => the whole line is inside it
+      const float e0 = fmaxf(fabsf(ffma(gA, P0.z, t0)), fabsf(ffma(gB, P0.z, t0)));
+      const float e1 = fmaxf(fabsf(ffma(gA, P1.y, t1)), fabsf(ffma(gB, P1.y, t1)));
+      const float e2 = fmaxf(fabsf(ffma(gA, P2.x, t2)), fabsf(ffma(gB, P2.x, t2)));
+      const float e3 = fmaxf(fabsf(ffma(gA, P2.w, t3)), fabsf(ffma(gB, P2.w, t3)));
+      const float e4 = fmaxf(fabsf(ffma(gA, P3.z, t4)), fabsf(ffma(gB, P3.z, t4)));
+      const bool full = (e0 <= thr && e1 <= thr && e2 <= thr) || (e2 <= thr && e3 <= thr && e4 <= thr);
+      if (full) { hit_lo = 0xffffffffu; hit_hi = 0x1ffu; }
+      if (__any_sync(0xffffffffu, need_hit && !full)) {
+        uint32_t in_lo = 0u, in_hi = 0u;
 #pragma unroll
-      for (int m = 0; m < VV_GS; m++) {
-        const float g = a.gz[m];
-        const bool i0 = fabsf(ffma(g, P0.z, t0)) <= thr;
-        const bool i1 = fabsf(ffma(g, P1.y, t1)) <= thr;
-        const bool i2 = fabsf(ffma(g, P2.x, t2)) <= thr;
-        const bool i3 = fabsf(ffma(g, P2.w, t3)) <= thr;
-        const bool i4 = fabsf(ffma(g, P3.z, t4)) <= thr;
-        if ((i0 && i1 && i2) || (i2 && i3 && i4)) {
-          if (m < 32) in_lo |= 1u << (m & 31);
-          else in_hi |= 1u << (m & 31);
+        for (int m = 0; m < VV_GS; m++) {
+          const float g = a.gz[m];
+          const bool i0 = fabsf(ffma(g, P0.z, t0)) <= thr;
+          const bool i1 = fabsf(ffma(g, P1.y, t1)) <= thr;
+          const bool i2 = fabsf(ffma(g, P2.x, t2)) <= thr;
+          const bool i3 = fabsf(ffma(g, P2.w, t3)) <= thr;
+          const bool i4 = fabsf(ffma(g, P3.z, t4)) <= thr;
+          if ((i0 && i1 && i2) || (i2 && i3 && i4)) {
+            if (m < 32) in_lo |= 1u << (m & 31);
+            else in_hi |= 1u << (m & 31);
+          }
         }
+        hit_lo |= in_lo;
+        hit_hi |= in_hi;
       }
-      hit_lo |= in_lo;
-      hit_hi |= in_hi;
     }
     // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
     if (!__any_sync(0xffffffffu, (alive_lo | alive_hi) != 0u)) break;
@@ -176,42 +196,81 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
     const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
     const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
     const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
-    // kill mask of this triangle; the (rare) "within eps of a plane" events are only DETECTED here, through the
-    // running minimum of |s| over the line, and handled exactly in half_events()
-    uint32_t k_lo = 0u, k_hi = 0u, hw_lo = 0u, hw_hi = 0u;
+    // values at the two ends of the line
+    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
+    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
+    const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
+    const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
+    const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
+    // "none": the test cannot touch any voxel of the line; "all": it removes every voxel of the line
+    bool noneV = (sVa <= neps) && (sVb <= neps), allV = (sVa > eps) && (sVb > eps);
+    if (OPEN) {
+      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
+      noneV = noneV && (s2a <= neps) && (s2b <= neps);
+      allV = allV || ((s2a > eps) && (s2b > eps));
+    }
+    const bool noneE = (sEa <= neps) && (sEb <= neps), allE = (sEa > eps) && (sEb > eps);
+    const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
+    const bool allW = (w0a >= eps) && (w0b >= eps) && (w1a >= neps) && (w1b >= neps) && (w2a >= neps) && (w2b >= neps);
+    if (allV || allE || allW) { alive_lo = 0u; alive_hi = 0u; }
+    const bool live = (alive_lo | alive_hi) != 0u;
+    uint32_t k_lo = 0u, k_hi = 0u;
     float mn = 3.0e38f;
+    // ---- voronoi plane(s), per voxel, only if some line of the warp is cut by it
+    if (__any_sync(0xffffffffu, live && !noneV)) {
 #pragma unroll
-    for (int m = 0; m < VV_GS; m++) {
-      const float g = a.gz[m];
-      const float q2 = fadd(g, pi.z);
-      const float sV = ffma(fsub(q2, P5.y), P4.z, tV);
-      bool kill = sV > eps;
-      float av = fabsf(sV);
-      if (OPEN) {
-        const float sV2 = ffma(fsub(q2, P6.w), P6.x, tV2);
-        kill |= sV2 > eps;
-        av = fminf(av, fabsf(sV2));
+      for (int m = 0; m < VV_GS; m++) {
+        const float q2 = fadd(a.gz[m], pi.z);
+        const float sV = ffma(fsub(q2, P5.y), P4.z, tV);
+        bool kill = sV > eps;
+        float av = fabsf(sV);
+        if (OPEN) {
+          const float sV2 = ffma(fsub(q2, P6.w), P6.x, tV2);
+          kill |= sV2 > eps;
+          av = fminf(av, fabsf(sV2));
+        }
+        mn = fminf(mn, av);
+        if (kill) {
+          if (m < 32) k_lo |= 1u << (m & 31);
+          else k_hi |= 1u << (m & 31);
+        }
       }
-      const float w0 = ffma(g, P7.z, tW0), w1 = ffma(g, P8.y, tW1), w2 = ffma(g, P9.x, tW2);
-      const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
-      const bool hw = fabsf(w0) < eps;
-      kill |= inside && !hw;
-      const float sE = ffma(fsub(g, P4.z), P9.w, tE);
-      kill |= sE > eps;
-      mn = fminf(mn, fminf(av, fabsf(sE)));
-      if (m < 32) {
-        if (kill) k_lo |= 1u << (m & 31);
-        if (inside && hw) hw_lo |= 1u << (m & 31);
-      } else {
-        if (kill) k_hi |= 1u << (m & 31);
-        if (inside && hw) hw_hi |= 1u << (m & 31);
+    }
+    // ---- edge plane
+    if (__any_sync(0xffffffffu, live && !noneE)) {
+#pragma unroll
+      for (int m = 0; m < VV_GS; m++) {
+        const float sE = ffma(fsub(a.gz[m], P4.z), P9.w, tE);
+        mn = fminf(mn, fabsf(sE));
+        if (sE > eps) {
+          if (m < 32) k_lo |= 1u << (m & 31);
+          else k_hi |= 1u << (m & 31);
+        }
       }
+    }
+    // ---- wall tetrahedron
+    if (__any_sync(0xffffffffu, live && !noneW)) {
+      uint32_t hw_lo = 0u, hw_hi = 0u;
+#pragma unroll
+      for (int m = 0; m < VV_GS; m++) {
+        const float g = a.gz[m];
+        const float w0 = ffma(g, P7.z, tW0), w1 = ffma(g, P8.y, tW1), w2 = ffma(g, P9.x, tW2);
+        const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
+        const bool hw = fabsf(w0) < eps;
+        if (m < 32) {
+          if (inside && !hw) k_lo |= 1u << (m & 31);
+          if (inside && hw) hw_lo |= 1u << (m & 31);
+        } else {
+          if (inside && !hw) k_hi |= 1u << (m & 31);
+          if (inside && hw) hw_hi |= 1u << (m & 31);
+        }
+      }
+      if (hw_lo) half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
+      if (hw_hi) half_inc(hhi, hw_hi);
     }
     alive_lo &= ~k_lo;
     alive_hi &= ~k_hi;
-    if (hw_lo) half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
-    if (hw_hi) half_inc(hhi, hw_hi);
-    if (mn < eps) {
+    if (mn < eps && live) {
       HalfCtx c;
       c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
       c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
