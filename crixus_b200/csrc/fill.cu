@@ -18,7 +18,9 @@
 //     until no tile is active.  Only reached tiles are touched: work ~ filled volume + wall area.
 // Bound: HBM, 0.25 B/cell + 8 B/filled cell -- in practice latency/round bound.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include "common.cuh"
 
@@ -110,6 +112,7 @@ struct FillArgs {
   const uint8_t *nbflag;  // per 3dr-cell: 27-neighbourhood contains a segment
   const FsDesc *fs;       // fshape descriptors
   int nfs, all_hard;
+  const int *all_hard_d;       // set by k_fs_desc when a free-surface triangle cannot be culled
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
   int32_t *count;               // [0] = list length, [1] = cursor, [2] = resolve-list length, [3] = resolve cursor
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256) k_classify(FillArgs A)
     const int j = (int)(row % A.dimg[1]), k = (int)(row / A.dimg[1]);
     const int nvalid = min(32, A.dimg[0] - wx * 32);
     uint32_t h = 0;
-    if (A.all_hard) h = 0xffffffffu;
+    if (A.all_hard || *A.all_hard_d) h = 0xffffffffu;
     else {
       const float sy = ffma((float)j, p.dr, p.fcmin[1]), sz = ffma((float)k, p.dr, p.fcmin[2]);
       const int gy = cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]), gz = cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]);
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
 
 // bulk resolution of the hard cells of newly reached tiles: one warp per 32-cell word, one warp-cooperative
 // checkCollision per hard cell for all of its in-lattice directions at once
-__global__ void __launch_bounds__(256) k_resolve_tiles(FillArgs A)
+__global__ void __launch_bounds__(256, 3) k_resolve_tiles(FillArgs A)
 {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -537,6 +540,7 @@ struct FillState {
   int64_t dimg[3] = {0, 0, 0};
   int64_t nbe = 0, cnbe = 0;
   uint32_t *F = nullptr, *H = nullptr, *B = nullptr;
+  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0;
   uint8_t *nbflag = nullptr, *act = nullptr, *tile_res = nullptr;
   int32_t *list = nullptr, *count = nullptr, *rlist = nullptr;
   FsDesc *fs = nullptr;
@@ -554,29 +558,40 @@ void cx_fill_state_free(cx_ctx *ctx)
   ctx->fill_state = nullptr;
 }
 
-// conservative fshape descriptors (host): see DESIGN.md "fill / easy cells"
-static void make_fs_desc(const cx_params *p, const float *n, const float *a, const float *b, const float *c, FsDesc *d, int *cullable)
+// conservative fshape descriptors, one thread per free-surface triangle (DESIGN.md "fill / easy cells").
+// A triangle is "cullable" when its stored normal is consistent with its plane and it is well conditioned; then
+// checkTriangleCollision(s, dir, .) can only be true for s inside the triangle's bounding box grown by
+// 1.5 dr + 1 % of its edge lengths + 10 eps, or (ray-in-plane rule, crixus_d.cu:766-769) within 4 eps of its plane
+// when some axis direction is parallel to the plane within eps.  One non-cullable triangle makes every cell hard.
+__global__ void k_fs_desc(FillArgs A, FsDesc *out, int *all_hard)
 {
-  float u[3], v[3];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.cnbe) return;
+  const int64_t i = A.nbe - A.cnbe + t;
+  const float4 n4 = A.norm[i];
+  const int4 E = A.ep[i];
+  const float4 a4 = A.pos[E.x], b4 = A.pos[E.y], c4 = A.pos[E.z];
+  const float n[3] = {n4.x, n4.y, n4.z}, a[3] = {a4.x, a4.y, a4.z}, b[3] = {b4.x, b4.y, b4.z}, c[3] = {c4.x, c4.y, c4.z};
   double lu = 0, lv = 0, ln = 0, nu = 0, nv = 0, uv = 0;
   for (int k = 0; k < 3; k++) {
-    u[k] = b[k] - a[k]; v[k] = c[k] - a[k];
-    lu += (double)u[k] * u[k]; lv += (double)v[k] * v[k]; ln += (double)n[k] * n[k];
-    nu += (double)n[k] * u[k]; nv += (double)n[k] * v[k]; uv += (double)u[k] * v[k];
+    const double u = (double)b[k] - a[k], v = (double)c[k] - a[k];
+    lu += u * u; lv += v * v; ln += (double)n[k] * n[k];
+    nu += (double)n[k] * u; nv += (double)n[k] * v; uv += u * v;
   }
   lu = sqrt(lu); lv = sqrt(lv); ln = sqrt(ln);
-  // cullable: the stored normal is consistent with the triangle's plane and the triangle is well conditioned
-  *cullable = ln > 0 && lu > 0 && lv > 0 && fabs(nu) <= 1e-3 * ln * lu && fabs(nv) <= 1e-3 * ln * lv &&
-              (lu * lu * lv * lv - uv * uv) >= 1e-4 * lu * lu * lv * lv;
-  const double margin = 1.5 * p->dr + 0.01 * (lu + lv) + 10.0 * p->eps;
+  const bool cullable = ln > 0 && lu > 0 && lv > 0 && fabs(nu) <= 1e-3 * ln * lu && fabs(nv) <= 1e-3 * ln * lv &&
+                        (lu * lu * lv * lv - uv * uv) >= 1e-4 * lu * lu * lv * lv;
+  if (!cullable) atomicExch(all_hard, 1);
+  const double margin = 1.5 * A.p.dr + 0.01 * (lu + lv) + 10.0 * A.p.eps;
+  FsDesc d;
+  d.quirk = 0;
   for (int k = 0; k < 3; k++) {
-    const float mn = std::min(a[k], std::min(b[k], c[k])), mx = std::max(a[k], std::max(b[k], c[k]));
-    d->lo[k] = (float)(mn - margin); d->hi[k] = (float)(mx + margin);
-    d->n[k] = n[k]; d->v0[k] = a[k];
+    const float mn = fminf(a[k], fminf(b[k], c[k])), mx = fmaxf(a[k], fmaxf(b[k], c[k]));
+    d.lo[k] = (float)(mn - margin); d.hi[k] = (float)(mx + margin);
+    d.n[k] = n[k]; d.v0[k] = a[k];
+    if (fabs((double)n[k]) * A.p.dr * 0.5 < A.p.eps) d.quirk = 1;
   }
-  d->quirk = 0;
-  for (int k = 0; k < 3; k++)
-    if (fabs((double)n[k]) * p->dr * 0.5 < p->eps) d->quirk = 1;
+  out[t] = d;
 }
 
 static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
@@ -596,49 +611,43 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   const bool fresh = first || !s || s->fpos_key != fpos_d || s->dimg[0] != dimg[0] || s->dimg[1] != dimg[1] || s->dimg[2] != dimg[2] ||
                      s->nbe != nbe || s->cnbe != cnbe;
   if (fresh) {
-    cx_fill_state_free(ctx);
-    s = new FillState();
-    ctx->fill_state = s;
+    if (!s) {
+      s = new FillState();
+      ctx->fill_state = s;
+    }
+    // buffers are kept between calls and only grow (cudaMalloc/cudaFree cost milliseconds and synchronise)
+    if (nw > s->cap_nw) {
+      cudaFree(s->F); cudaFree(s->H); cudaFree(s->B);
+      s->F = s->H = s->B = nullptr; s->cap_nw = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->F, sizeof(uint32_t) * (size_t)nw));
+      CX_CUDA(ctx, cudaMalloc(&s->H, sizeof(uint32_t) * (size_t)nw));
+      CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 6));
+      s->cap_nw = nw;
+    }
+    if (ntiles > s->cap_ntiles) {
+      cudaFree(s->act); cudaFree(s->list); cudaFree(s->tile_res); cudaFree(s->rlist);
+      s->act = s->tile_res = nullptr; s->list = s->rlist = nullptr; s->cap_ntiles = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->act, (size_t)ntiles * 2));
+      CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
+      CX_CUDA(ctx, cudaMalloc(&s->tile_res, (size_t)ntiles));
+      CX_CUDA(ctx, cudaMalloc(&s->rlist, sizeof(int32_t) * (size_t)ntiles));
+      s->cap_ntiles = ntiles;
+    }
+    if (p->gridn[3] > s->cap_ncell) {
+      cudaFree(s->nbflag); s->nbflag = nullptr; s->cap_ncell = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
+      s->cap_ncell = p->gridn[3];
+    }
+    if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 4));
+    if (!s->fs) CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * FS_MAX_DESC + 16));
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
     for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
-    CX_CUDA(ctx, cudaMalloc(&s->F, sizeof(uint32_t) * (size_t)nw));
-    CX_CUDA(ctx, cudaMalloc(&s->H, sizeof(uint32_t) * (size_t)nw));
-    CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 6));
-    CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
-    CX_CUDA(ctx, cudaMalloc(&s->act, (size_t)ntiles * 2));
-    CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
-    CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 4));
-    CX_CUDA(ctx, cudaMalloc(&s->tile_res, (size_t)ntiles));
-    CX_CUDA(ctx, cudaMalloc(&s->rlist, sizeof(int32_t) * (size_t)ntiles));
     CX_CUDA(ctx, cudaMemsetAsync(s->tile_res, 0, (size_t)ntiles, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)ntiles * 2, st));
-    // fshape descriptors
-    s->nfs = 0; s->all_hard = 0;
-    if (cnbe > 0) {
-      if (cnbe > FS_MAX_DESC) s->all_hard = 1;
-      else {
-        std::vector<float> hn(4 * cnbe);
-        std::vector<int32_t> he(4 * cnbe);
-        CX_CUDA(ctx, cudaMemcpyAsync(hn.data(), norm_d + 4 * (nbe - cnbe), sizeof(float) * 4 * cnbe, cudaMemcpyDeviceToHost, st));
-        CX_CUDA(ctx, cudaMemcpyAsync(he.data(), ep_d + 4 * (nbe - cnbe), sizeof(int32_t) * 4 * cnbe, cudaMemcpyDeviceToHost, st));
-        CX_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<FsDesc> desc(cnbe);
-        for (int64_t t = 0; t < cnbe && !s->all_hard; t++) {
-          float v[3][4];
-          for (int c = 0; c < 3; c++)
-            CX_CUDA(ctx, cudaMemcpy(v[c], pos_d + 4 * (int64_t)he[4 * t + c], sizeof(float) * 4, cudaMemcpyDeviceToHost));
-          int cullable = 0;
-          make_fs_desc(p, &hn[4 * t], v[0], v[1], v[2], &desc[t], &cullable);
-          if (!cullable) s->all_hard = 1;
-        }
-        if (!s->all_hard) {
-          CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * (size_t)cnbe));
-          CX_CUDA(ctx, cudaMemcpy(s->fs, desc.data(), sizeof(FsDesc) * (size_t)cnbe, cudaMemcpyHostToDevice));
-          s->nfs = (int)cnbe;
-        }
-      }
-    }
+    // fshape descriptors are built on the device (k_fs_desc): no host round trip
+    s->nfs = (cnbe > 0 && cnbe <= FS_MAX_DESC) ? (int)cnbe : 0;
+    s->all_hard = (cnbe > FS_MAX_DESC) ? 1 : 0;
   }
   memset(A, 0, sizeof(*A));
   A->p = *p;
@@ -653,7 +662,13 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
   A->drw2 = p->dr_wall * p->dr_wall;
   A->one_eps = 1.0 + (double)p->eps;
+  A->all_hard_d = (const int *)((const char *)s->fs + sizeof(FsDesc) * FS_MAX_DESC);
   if (fresh) {
+    CX_CUDA(ctx, cudaMemsetAsync((void *)A->all_hard_d, 0, sizeof(int), st));
+    if (s->nfs > 0) {
+      k_fs_desc<<<cx_blocks(s->nfs, 128), 128, 0, st>>>(*A, s->fs, (int *)A->all_hard_d);
+      CX_LAUNCH_CHECK(ctx, "k_fs_desc");
+    }
     k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
     CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
     k_classify<<<cx_blocks(nw, 256, ctx->num_sms * 16), 256, 0, st>>>(*A);
@@ -696,6 +711,13 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_o
   return CX_OK;
 }
 
+static double dbg_now()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                                      const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                                      int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host)
@@ -703,8 +725,12 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
   FillArgs A;
   FillState *s = nullptr;
+  const bool dbg = getenv("CX_DEBUG_TIMING") != nullptr;
+  double t0 = 0, t1 = 0, t2 = 0;
+  if (dbg) { cudaStreamSynchronize(ctx->stream); t0 = dbg_now(); }
   int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, first_call, &A, &s);
   if (rc != CX_OK) return rc;
+  if (dbg) { cudaStreamSynchronize(ctx->stream); t1 = dbg_now(); }
   if (k_begin < 0 || k_end > A.dimg[2] || k_begin >= k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
   cudaStream_t st = ctx->stream;
@@ -719,6 +745,11 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   }
   rc = fill_rounds(ctx, &A, s, rounds_host);
   if (rc != CX_OK) return rc;
+  if (dbg) {
+    cudaStreamSynchronize(ctx->stream);
+    t2 = dbg_now();
+    fprintf(stderr, "[cx fill] prepare %.3f ms, rounds %.3f ms (%d rounds)\n", 1e3 * (t1 - t0), 1e3 * (t2 - t1), rounds_host ? *rounds_host : -1);
+  }
   k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_pack");
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
