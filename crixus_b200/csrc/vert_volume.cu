@@ -92,7 +92,7 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane)
 }
 
 // bit-sliced +1 on the 5-bit per-voxel halving counters (saturating at 31) for every voxel whose bit is set in `m`
-__device__ __noinline__ void half_inc(uint32_t (&h)[5], uint32_t m)
+__device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t m)
 {
   uint32_t c = m;
 #pragma unroll
@@ -113,9 +113,10 @@ struct HalfCtx {
   float tV, tV2, tW0, tW1, tW2, tE, piz, eps;
   int open;
 };
-__device__ __noinline__ void half_events(const VVArgs &a, const HalfCtx &c, uint32_t (&hlo)[5], uint32_t (&hhi)[5])
+__device__ __noinline__ void half_events(const VVArgs &a, const HalfCtx &c, uint32_t (&hlo)[5], uint32_t (&hhi)[5], bool mine)
 {
   const float eps = c.eps;
+  if (!mine) return;   // called by the whole warp (keeps it converged); only lanes with an event do the work
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
     const float q2 = fadd(g, c.piz);
@@ -265,16 +266,17 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
           if (inside && hw) hw_hi |= 1u << (m & 31);
         }
       }
-      if (hw_lo) half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
-      if (hw_hi) half_inc(hhi, hw_hi);
+      half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
+      half_inc(hhi, hw_hi);
     }
     alive_lo &= ~k_lo;
     alive_hi &= ~k_hi;
-    if (mn < eps && live) {
+    const bool ev = mn < eps && live;
+    if (__any_sync(0xffffffffu, ev)) {
       HalfCtx c;
       c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
       c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
-      half_events(a, c, hlo, hhi);
+      half_events(a, c, hlo, hhi, ev);
     }
   }
 }
@@ -397,8 +399,10 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
       if (c < 0) continue;
       const int b = __ldg(&a.cell_idx[c]), e = __ldg(&a.cell_idx[c + 1]);
-      for (int j = b + lane; j < e; j += 32) {
-        const int4 E = __ldg(&a.ep[j]);
+      for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
+        const int j = base + lane;
+        int4 E = make_int4(-1, -1, -1, -1);
+        if (j < e) E = __ldg(&a.ep[j]);
         for (int k = 0; k < tris; k++) {
           const int t0 = w.tri[k][0], t1 = w.tri[k][1];
           const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
@@ -420,7 +424,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     }
 
     // ---------------- per-triangle plane vectors (crixus_d.cu:507-529 and :552-596), one lane per fan triangle
-    for (int j = lane; j < tris; j += 32) {
+    for (int jb = 0; jb < tris; jb += 32) {
+      const int j = jb + lane;
+      if (j >= tris) continue;
       const f3 n = mk3(__ldg(&a.norm[w.tri[j][2]]));
       const f3 va = mk3(__ldg(&a.pos[w.tri[j][0]])), vb = mk3(__ldg(&a.pos[w.tri[j][1]]));
       const f3 e1 = unwrap3(p, sub3(va, pi), a.two_dr);  // cvec[5] (and cvec[0] before normalisation)
