@@ -1,0 +1,292 @@
+#include "output.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+// ---------------------------------------------------------------------------------------------- STL
+int cx_read_stl(const std::string &filename, std::vector<float> &corners, std::vector<float> &normals)
+{
+  std::ifstream f(filename.c_str(), std::ios::in | std::ios::binary);
+  if (!f.is_open()) return CX_FILE_NOT_OPEN;
+  char head[80];
+  f.read(head, 80);
+  if (f.gcount() >= 5 && memcmp(head, "solid", 5) == 0) return CX_STL_NOT_BINARY;  // crixus.cu:137-153
+  uint32_t n = 0;
+  f.read((char *)&n, 4);
+  corners.resize((size_t)9 * n);
+  normals.resize((size_t)3 * n);
+  uint32_t through = 0;
+  while (through < n && !f.eof()) {  // crixus.cu:188-213
+    float rec[12];
+    uint16_t attr;
+    f.read((char *)rec, 48);
+    f.read((char *)&attr, 2);
+    if (f.gcount() != 2) break;
+    memcpy(&normals[3 * (size_t)through], rec, 12);
+    memcpy(&corners[9 * (size_t)through], rec + 3, 36);
+    through++;
+  }
+  if (through != n) return CX_READ_ERROR;  // crixus.cu:218-221
+  return CX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- assembly
+std::vector<CxOutBuf> cx_assemble(const cx_job &job, int64_t nfluid)
+{
+  const int64_t nvert = job.nvert, nbe = job.nbe;
+  const cx_params &p = job.params_fill;
+  const float dr = job.dr;
+  std::vector<CxOutBuf> buf;
+  buf.reserve((size_t)(nvert + nbe + job.nfluid));
+  const float fluid_vol = (float)pow(dr, 3);  // crixus.cu:986
+  const int64_t d0 = job.dimg[0], d1 = job.dimg[1], G = job.dimg[0] * job.dimg[1] * job.dimg[2];
+  CxOutBuf z;
+  memset(&z, 0, sizeof(z));
+  for (int64_t j = 0; j < G; j++) {  // crixus.cu:991-1019
+    if (!(job.fpos[j >> 5] >> (j & 31) & 1u)) continue;
+    CxOutBuf b = z;
+    const int64_t k = j / (d1 * d0), n = j % (d1 * d0);
+    b.z = p.fcmin[2] + dr * (float)k;
+    b.y = p.fcmin[1] + dr * (float)(n / d0);
+    b.x = p.fcmin[0] + dr * (float)(n % d0);
+    b.vol = fluid_vol;
+    b.kpar = 1; b.kfluid = 1;
+    b.iref = (int32_t)buf.size();
+    buf.push_back(b);
+  }
+  std::vector<int32_t> nvshift((size_t)nvert, 0);
+  int32_t ishift = 0;
+  for (int64_t i = 0; i < nvert; i++) {  // crixus.cu:1026-1053
+    if (job.pos[4 * i] < -1e9f) { ishift++; continue; }
+    nvshift[i] = ishift;
+    CxOutBuf b = z;
+    b.x = job.pos[4 * i]; b.y = job.pos[4 * i + 1]; b.z = job.pos[4 * i + 2];
+    b.vol = job.vol[i];
+    b.kpar = 2; b.kfluid = 1;
+    b.iref = (int32_t)buf.size();
+    buf.push_back(b);
+  }
+  for (int64_t i = 0; i < nbe; i++) {  // crixus.cu:1063-1097 (KENT = 0 everywhere: no reordering)
+    CxOutBuf b = z;
+    const float *q = job.pos + 4 * (nvert + i);
+    b.x = q[0]; b.y = q[1]; b.z = q[2];
+    b.nx = job.norm[4 * i]; b.ny = job.norm[4 * i + 1]; b.nz = job.norm[4 * i + 2];
+    b.surf = job.surf[i];
+    b.kpar = 3; b.kfluid = 1;
+    b.iref = (int32_t)buf.size();
+    const int32_t *e = job.ep + 4 * i;
+    b.ep1 = (int32_t)nfluid + e[0] - nvshift[e[0]];
+    b.ep2 = (int32_t)nfluid + e[1] - nvshift[e[1]];
+    b.ep3 = (int32_t)nfluid + e[2] - nvshift[e[2]];
+    buf.push_back(b);
+  }
+  return buf;
+}
+
+// ---------------------------------------------------------------------------------------------- VTU
+static void scalar_array(FILE *f, const char *type, const char *name, size_t off)
+{
+  fprintf(f, "  <DataArray type='%s' Name='%s' format='appended' offset='%zu'/>\n", type, name, off);
+}
+static void vector_array(FILE *f, const char *type, const char *name, unsigned dim, size_t off)
+{
+  if (name) fprintf(f, "  <DataArray type='%s' Name='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, name, dim, off);
+  else fprintf(f, "  <DataArray type='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, dim, off);
+}
+
+int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
+{
+  FILE *fid = fopen(filename.c_str(), "w");
+  if (!fid) return CX_NO_WRITE_FILE;
+  const int len = (int)buf.size();
+  fprintf(fid, "<?xml version='1.0'?>\n");
+  fprintf(fid, "<VTKFile type= 'UnstructuredGrid'  version= '0.1'  byte_order= '%s'>\n", "LittleEndian");
+  fprintf(fid, " <UnstructuredGrid>\n");
+  fprintf(fid, "  <Piece NumberOfPoints='%d' NumberOfCells='%d'>\n", len, len);
+  fprintf(fid, "   <PointData Scalars='Volume'>\n");
+  size_t off = 0;
+  scalar_array(fid, "Float32", "Volume", off); off += sizeof(float) * len + sizeof(int);
+  scalar_array(fid, "Float32", "Surface", off); off += sizeof(float) * len + sizeof(int);
+  scalar_array(fid, "UInt32", "ParticleType", off); off += 4 * (size_t)len + sizeof(int);
+  scalar_array(fid, "UInt32", "FluidType", off); off += 4 * (size_t)len + sizeof(int);
+  scalar_array(fid, "UInt32", "KENT", off); off += 4 * (size_t)len + sizeof(int);
+  scalar_array(fid, "UInt32", "MovingBoundary", off); off += 4 * (size_t)len + sizeof(int);
+  scalar_array(fid, "UInt32", "AbsoluteIndex", off); off += 4 * (size_t)len + sizeof(int);
+  vector_array(fid, "Float32", "Normal", 3, off); off += 12 * (size_t)len + sizeof(int);
+  vector_array(fid, "UInt32", "VertexParticle", 3, off); off += 12 * (size_t)len + sizeof(int);
+  fprintf(fid, "   </PointData>\n");
+  fprintf(fid, "   <Points>\n");
+  vector_array(fid, "Float64", nullptr, 3, off); off += 24 * (size_t)len + sizeof(int);
+  fprintf(fid, "   </Points>\n");
+  fprintf(fid, "   <Cells>\n");
+  scalar_array(fid, "Int32", "connectivity", off); off += 4 * (size_t)len + sizeof(int);
+  scalar_array(fid, "Int32", "offsets", off); off += 4 * (size_t)len + sizeof(int);
+  fprintf(fid, "  <DataArray type='Int32' Name='types' format='ascii'>\n");
+  for (int i = 0; i < len; i++) fprintf(fid, "%d\t", 1);
+  fprintf(fid, "\n");
+  fprintf(fid, "  </DataArray>\n");
+  fprintf(fid, "   </Cells>\n");
+  fprintf(fid, "  </Piece>\n");
+  fprintf(fid, " </UnstructuredGrid>\n");
+  fprintf(fid, " <AppendedData encoding='raw'>\n_");
+  std::vector<char> tmp;
+  auto emit = [&](size_t elem, auto getter) {
+    int nbytes = (int)(elem * (size_t)len);
+    fwrite(&nbytes, sizeof(nbytes), 1, fid);
+    tmp.resize((size_t)nbytes);
+    for (int i = 0; i < len; i++) getter(buf[i], tmp.data() + elem * (size_t)i);
+    fwrite(tmp.data(), 1, tmp.size(), fid);
+  };
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.vol, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.surf, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.kpar, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.kfluid, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.kent, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.kparmob, 4); });
+  emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.iref, 4); });
+  emit(12, [](const CxOutBuf &b, char *o) { memcpy(o, &b.nx, 12); });
+  emit(12, [](const CxOutBuf &b, char *o) { memcpy(o, &b.ep1, 12); });
+  emit(24, [](const CxOutBuf &b, char *o) { double v[3] = {(double)b.x, (double)b.y, (double)b.z}; memcpy(o, v, 24); });
+  {
+    int nbytes = 4 * len;
+    std::vector<uint32_t> idx((size_t)len);
+    fwrite(&nbytes, sizeof(nbytes), 1, fid);
+    for (int i = 0; i < len; i++) idx[i] = (uint32_t)i;
+    fwrite(idx.data(), 4, idx.size(), fid);
+    fwrite(&nbytes, sizeof(nbytes), 1, fid);
+    for (int i = 0; i < len; i++) idx[i] = (uint32_t)i + 1;
+    fwrite(idx.data(), 4, idx.size(), fid);
+  }
+  fprintf(fid, " </AppendedData>\n");
+  fprintf(fid, "</VTKFile>");
+  fclose(fid);
+  return CX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- minimal HDF5
+// What the reference asks libhdf5 for (crixus.cpp:12-60): one contiguous 1-D dataset "Compound" of `len` 64-byte
+// compound records (16 members, names/offsets below) in the root group.  libhdf5 is absent from this image, so the
+// file is produced here following the HDF5 File Format Specification (superblock v0, v1 object headers, v1 group
+// B-tree + local heap + symbol-table node, dataspace v1, compound datatype v1, layout v3 contiguous).  A matching
+// independent parser lives in tests/h5mini.py.
+namespace {
+struct Bytes {
+  std::vector<uint8_t> b;
+  void u8(uint8_t v) { b.push_back(v); }
+  void u16(uint16_t v) { for (int i = 0; i < 2; i++) b.push_back((uint8_t)(v >> (8 * i))); }
+  void u32(uint32_t v) { for (int i = 0; i < 4; i++) b.push_back((uint8_t)(v >> (8 * i))); }
+  void u64(uint64_t v) { for (int i = 0; i < 8; i++) b.push_back((uint8_t)(v >> (8 * i))); }
+  void raw(const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; b.insert(b.end(), q, q + n); }
+  void pad_to(size_t n) { while (b.size() < n) b.push_back(0); }
+  void align8() { while (b.size() % 8) b.push_back(0); }
+  size_t size() const { return b.size(); }
+};
+const uint64_t UNDEF = 0xffffffffffffffffull;
+
+void datatype_f32(Bytes &o)
+{
+  o.u8(0x11); o.u8(0x20); o.u8(0x1f); o.u8(0x00);  // class 1 (float) v1; LE, implied-1 mantissa, sign bit 31
+  o.u32(4);
+  o.u16(0); o.u16(32); o.u8(23); o.u8(8); o.u8(0); o.u8(23); o.u32(127);
+}
+void datatype_i32(Bytes &o)
+{
+  o.u8(0x10); o.u8(0x08); o.u8(0x00); o.u8(0x00);  // class 0 (fixed point) v1; LE, two's complement
+  o.u32(4);
+  o.u16(0); o.u16(32);
+}
+void message(Bytes &o, uint16_t type, const Bytes &data)
+{
+  size_t n = (data.size() + 7) & ~(size_t)7;
+  o.u16(type); o.u16((uint16_t)n); o.u8(0); o.u8(0); o.u8(0); o.u8(0);
+  o.raw(data.b.data(), data.size());
+  for (size_t i = data.size(); i < n; i++) o.u8(0);
+}
+}  // namespace
+
+int cx_write_h5sph(const std::vector<CxOutBuf> &buf, const std::string &filename)
+{
+  static const char *names[16] = {"Coords_0", "Coords_1", "Coords_2", "Normal_0", "Normal_1", "Normal_2", "Volume", "Surface",
+                                  "ParticleType", "FluidType", "KENT", "MovingBoundary", "AbsoluteIndex", "VertexParticle1",
+                                  "VertexParticle2", "VertexParticle3"};  // crixus.cpp:23-38
+  const uint64_t len = buf.size();
+  // ---- layout of the metadata blocks
+  const uint64_t a_super = 0, a_root_hdr = 96;
+  // root object header: 16-byte prefix + one symbol-table message (8 + 16)
+  const uint64_t a_heap = a_root_hdr + 16 + 24;                  // 136
+  const uint64_t heap_data_size = 40;
+  const uint64_t a_heap_data = a_heap + 32;                      // 168
+  const uint64_t a_btree = a_heap_data + heap_data_size;         // 208
+  const uint64_t btree_size = 24 + (2 * 16 + 1) * 8 + (2 * 16) * 8;  // 544
+  const uint64_t a_snod = a_btree + btree_size;                  // 752
+  const uint64_t snod_size = 8 + 8 * 40;                         // 328
+  const uint64_t a_dset_hdr = a_snod + snod_size;                // 1080
+  // dataset messages
+  Bytes m_space, m_type, m_fill, m_layout, msgs;
+  m_space.u8(1); m_space.u8(1); m_space.u8(0); m_space.u8(0); m_space.u32(0); m_space.u64(len);
+  m_type.u8(0x16); m_type.u8(16); m_type.u8(0); m_type.u8(0); m_type.u32(64);  // class 6 (compound) v1, 16 members, size 64
+  for (int i = 0; i < 16; i++) {
+    const size_t nl = strlen(names[i]) + 1, npad = (nl + 7) & ~(size_t)7;
+    m_type.raw(names[i], nl);
+    for (size_t k = nl; k < npad; k++) m_type.u8(0);
+    m_type.u32((uint32_t)(4 * i));                     // byte offset of member
+    m_type.u8(0); m_type.u8(0); m_type.u8(0); m_type.u8(0);  // dimensionality + reserved
+    m_type.u32(0); m_type.u32(0);                      // permutation, reserved
+    for (int d = 0; d < 4; d++) m_type.u32(0);         // dimension sizes
+    if (i < 8) datatype_f32(m_type); else datatype_i32(m_type);
+  }
+  m_fill.u8(2); m_fill.u8(2); m_fill.u8(2); m_fill.u8(0);   // fill value v2: alloc late, write if set, undefined
+  const uint64_t dset_msgs_size = (8 + ((m_space.size() + 7) & ~7ull)) + (8 + ((m_type.size() + 7) & ~7ull)) + (8 + 8) + (8 + 24);
+  const uint64_t a_data = (a_dset_hdr + 16 + dset_msgs_size + 7) & ~7ull;
+  m_layout.u8(3); m_layout.u8(1); m_layout.u64(a_data); m_layout.u64(len * 64);
+  message(msgs, 0x0001, m_space);
+  message(msgs, 0x0003, m_type);
+  message(msgs, 0x0005, m_fill);
+  message(msgs, 0x0008, m_layout);
+  if (msgs.size() != dset_msgs_size) return CX_INTERNAL_ERROR;
+  const uint64_t a_eof = a_data + len * 64;
+
+  Bytes o;
+  // ---- superblock v0
+  const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+  o.raw(sig, 8);
+  o.u8(0); o.u8(0); o.u8(0); o.u8(0); o.u8(0); o.u8(8); o.u8(8); o.u8(0);
+  o.u16(4); o.u16(16); o.u32(0);
+  o.u64(0); o.u64(UNDEF); o.u64(a_eof); o.u64(UNDEF);
+  // root group symbol table entry
+  o.u64(0); o.u64(a_root_hdr); o.u32(1); o.u32(0); o.u64(a_btree); o.u64(a_heap);
+  o.pad_to(a_root_hdr);
+  (void)a_super;
+  // ---- root group object header (v1): symbol table message
+  o.u8(1); o.u8(0); o.u16(1); o.u32(1); o.u32(24); o.u32(0);
+  { Bytes st; st.u64(a_btree); st.u64(a_heap); message(o, 0x0011, st); }
+  o.pad_to(a_heap);
+  // ---- local heap
+  o.raw("HEAP", 4); o.u8(0); o.u8(0); o.u8(0); o.u8(0);
+  o.u64(heap_data_size); o.u64(24); o.u64(a_heap_data);
+  o.pad_to(a_heap_data);
+  o.u64(0);                                   // offset 0: "" (root)
+  o.raw("Compound\0\0\0\0\0\0\0", 16);        // offset 8
+  o.u64(1); o.u64(16);                        // free block at 24: next = H5HL_FREE_NULL, size 16
+  o.pad_to(a_btree);
+  // ---- B-tree node (group, leaf level)
+  o.raw("TREE", 4); o.u8(0); o.u8(0); o.u16(1); o.u64(UNDEF); o.u64(UNDEF);
+  o.u64(0); o.u64(a_snod); o.u64(8);          // key0 = "", child0, key1 = "Compound"
+  o.pad_to(a_snod);
+  // ---- symbol table node
+  o.raw("SNOD", 4); o.u8(1); o.u8(0); o.u16(1);
+  o.u64(8); o.u64(a_dset_hdr); o.u32(0); o.u32(0); o.u64(0); o.u64(0);
+  o.pad_to(a_dset_hdr);
+  // ---- dataset object header (v1)
+  o.u8(1); o.u8(0); o.u16(4); o.u32(1); o.u32((uint32_t)dset_msgs_size); o.u32(0);
+  o.raw(msgs.b.data(), msgs.size());
+  o.pad_to(a_data);
+
+  FILE *f = fopen(filename.c_str(), "wb");
+  if (!f) return CX_NO_WRITE_FILE;
+  bool ok = fwrite(o.b.data(), 1, o.size(), f) == o.size();
+  if (len) ok = ok && fwrite(buf.data(), 64, (size_t)len, f) == (size_t)len;
+  fclose(f);
+  return ok ? CX_OK : CX_WRITE_FAIL;
+}
