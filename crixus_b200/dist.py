@@ -90,10 +90,32 @@ def distributed_fill(slab_fill, fpos, dimg, seed, rank, world, dist):
     return total, it
 
 
+def own_bits_only(fpos, dimg, k0, k1):
+    """Clears every bit outside this rank's planes [k0, k1) (the received halo planes and everything it never owned)."""
+    P = int(dimg[0]) * int(dimg[1])
+    lo, hi = k0 * P, k1 * P
+    w0, w1 = lo // 32, (hi + 31) // 32
+    if hi <= lo:
+        fpos.zero_()
+        return fpos
+    fpos[:w0] = 0
+    fpos[w1:] = 0
+    if lo % 32:
+        m = (0xFFFFFFFF << (lo % 32)) & 0xFFFFFFFF
+        fpos[w0] &= m - (1 << 32) if m >= (1 << 31) else m          # as a signed 32-bit value
+    if hi % 32:
+        m = (1 << (hi % 32)) - 1
+        fpos[w1 - 1] &= m - (1 << 32) if m >= (1 << 31) else m
+    return fpos
+
+
 def gather_slabs(fpos, dimg, rank, world, dist):
-    """OR-reduces the per-rank bitfields (each rank only ever sets bits of its own planes + received halos)."""
+    """Assembles the full bitfield on every rank.  NCCL has no bitwise-OR reduction, so each rank first clears the bits
+    it does not own; the owned bit ranges are disjoint, hence the (wrapping) int32 SUM equals the OR."""
     if world > 1:
-        dist.all_reduce(fpos, op=dist.ReduceOp.BOR)
+        k0, k1 = split_range(int(dimg[2]), world, rank)
+        own_bits_only(fpos, dimg, k0, k1)
+        dist.all_reduce(fpos, op=dist.ReduceOp.SUM)
     return fpos
 
 
