@@ -91,13 +91,18 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane)
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Phase B building blocks.  A z-line has 41 voxels; all per-voxel state is a 41-bit mask in a uint64_t.
+#define VV_ALL 0x1FFFFFFFFFFull
+#define VV_FULLWARP 0xffffffffu
+
 // bit-sliced +1 on the 5-bit per-voxel halving counters (saturating at 31) for every voxel whose bit is set in `m`
-__device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t m)
+__device__ __forceinline__ void half_inc(uint64_t (&h)[5], uint64_t m)
 {
-  uint32_t c = m;
+  uint64_t c = m;
 #pragma unroll
   for (int b = 0; b < 5; b++) {
-    uint32_t t = h[b] & c;
+    const uint64_t t = h[b] & c;
     h[b] ^= c;
     c = t;
   }
@@ -105,87 +110,170 @@ __device__ __forceinline__ void half_inc(uint32_t (&h)[5], uint32_t m)
   for (int b = 0; b < 5; b++) h[b] |= c;  // overflow -> stay at 31
 }
 
-// Rare path: some voxel of the line lies within eps of a voronoi or edge plane of triangle j (the wall-plane event,
-// which is COMMON -- every voxel in the plane of a flat wall -- is handled in the fast loop).  Recomputes the line with the
-// same arithmetic and bumps the halving counter once per event (crixus_d.cu:610-612, 622-624, 632/640-642, 659-661).
-struct HalfCtx {
+__device__ __forceinline__ uint64_t lowmask(int b) { return (1ull << b) - 1ull; }   // b in [0, 63]
+
+// Every plane expression of the reference is, along a z-line, a composition of correctly rounded (hence monotone)
+// operations of gz, and gz[m] is non-decreasing in m.  A threshold predicate of such an expression is therefore a
+// monotone step function of m: its truth values are pa..pa pb..pb with ONE flip.  mono_search finds the flip with six
+// evaluations of the very same arithmetic (exact, no approximation): the largest s in [0,39] with pred(gz[s]) == pa,
+// given pred(gz[0]) == pa and pred(gz[40]) != pa.  Lanes whose ends agree run along (the warp stays converged) and
+// ignore the result.
+template <class Pred>
+__device__ __forceinline__ int mono_search(const float *gzt, bool pa, Pred pred)
+{
+  int s = (pred(gzt[32]) == pa) ? 32 : 0;
+  {
+    const int i = min(s + 16, VV_GS - 1);
+    if (pred(gzt[i]) == pa) s = i;
+  }
+#pragma unroll
+  for (int st = 8; st >= 1; st >>= 1)
+    if (pred(gzt[s + st]) == pa) s += st;   // never beyond 39 for a lane that is really cut; the table has 64 entries
+  return s;
+}
+
+// mask of the voxels where pv(f(gz[m])) holds.  fa, fb = f at the two ends.  lo = last index that agrees with end A
+// (40 if the line is not cut by the predicate), pa = the predicate at end A.
+template <class F, class PV>
+__device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float fb, F f, PV pv, int &lo, bool &pa)
+{
+  pa = pv(fa);
+  const bool pb = pv(fb);
+  lo = VV_GS - 1;
+  if (__any_sync(VV_FULLWARP, pa != pb)) {
+    const bool pa_ = pa;
+    const int s = mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
+    if (pa != pb) lo = s;
+  }
+  const uint64_t lm = lowmask(lo + 1);
+  return pa ? lm : (VV_ALL & ~lm);
+}
+
+struct TriCtx {
   float4 P4, P5, P6, P7, P8, P9;
   float tV, tV2, tW0, tW1, tW2, tE, piz, eps;
   int open;
 };
-__device__ __noinline__ void half_events(const VVArgs &a, const HalfCtx &c, uint32_t (&hlo)[5], uint32_t (&hhi)[5], bool mine)
+// Exact per-voxel evaluation of triangle j on one line (the reference's loop body, crixus_d.cu:598-662): kill mask and
+// halving events.  Used for the lanes where the threshold shortcut cannot prove its result (a voxel within eps of a
+// voronoi/edge plane on a line that is cut by it, or an expression exactly equal to a threshold).
+__device__ __noinline__ void exact_tri(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
 {
-  const float eps = c.eps;
-  if (!mine) return;   // called by the whole warp (keeps it converged); only lanes with an event do the work
+  if (!mine) return;   // called by the whole warp (keeps it converged); only the flagged lanes do the work
+  const float eps = c.eps, neps = -c.eps;
+  uint64_t k = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
     const float q2 = fadd(g, c.piz);
-    int nh = 0;
-    nh += fabsf(ffma(fsub(q2, c.P5.y), c.P4.z, c.tV)) < eps;
-    if (c.open) nh += fabsf(ffma(fsub(q2, c.P6.w), c.P6.x, c.tV2)) < eps;
-    nh += fabsf(ffma(fsub(g, c.P4.z), c.P9.w, c.tE)) < eps;
-    for (int r = 0; r < nh; r++) {
-      if (m < 32) half_inc(hlo, 1u << m);
-      else half_inc(hhi, 1u << (m - 32));
+    const float sV = ffma(fsub(q2, c.P5.y), c.P4.z, c.tV);
+    bool kill = sV > eps;
+    int nh = fabsf(sV) < eps;
+    if (c.open) {
+      const float sV2 = ffma(fsub(q2, c.P6.w), c.P6.x, c.tV2);
+      kill |= sV2 > eps;
+      nh += fabsf(sV2) < eps;
     }
+    const float sE = ffma(fsub(g, c.P4.z), c.P9.w, c.tE);
+    kill |= sE > eps;
+    nh += fabsf(sE) < eps;
+    const float w0 = ffma(g, c.P7.z, c.tW0), w1 = ffma(g, c.P8.y, c.tW1), w2 = ffma(g, c.P9.x, c.tW2);
+    const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
+    const bool hw = fabsf(w0) < eps;
+    kill |= inside && !hw;
+    nh += inside && hw;
+    if (kill) k |= 1ull << m;
+    for (int r = 0; r < nh; r++) half_inc(h, 1ull << m);
+  }
+  K = k;
+}
+
+// kill mask {f > eps} and halving mask {|f| < eps} of a voronoi / edge plane on one line.  trig is raised when the
+// halving mask cannot be decided from the ends and the element next to the flip.
+template <class F>
+__device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig)
+{
+  const float neps = -eps;
+  int lo;
+  bool pa;
+  K |= mono_mask(gzt, fa, fb, f, [&](float v) { return v > eps; }, lo, pa);
+  const bool pb = fb > eps;
+  // the largest value among the voxels that survive: next to the flip (cut lines) / the larger end (uncut lines)
+  const float fnext = f(gzt[pa ? lo + 1 : lo]);
+  if (pa != pb) {
+    trig |= fnext > neps;          // a surviving voxel may lie within eps of the plane: let exact_tri decide
+  } else {
+    const bool Aa = fa > neps, Ab = fb > neps, Ba = fa < eps, Bb = fb < eps;
+    if (Aa != Ab || Ba != Bb) trig = true;
+    else if (Aa && Ba) H = VV_ALL;  // the whole line lies within eps of the plane (line parallel to it)
   }
 }
 
-// One z-line of 41 voxels against every fan triangle.
-//
-// Exact line-level culling: along a line only gz changes, gz[m] is non-decreasing in m, and every plane expression is
-// a composition of correctly rounded (hence monotone) operations of gz, so each expression is (weakly) monotone in m
-// and its values on the line lie between its values at the two ends m=0 and m=40.  Evaluating the ends with the very
-// same arithmetic therefore decides, exactly, whether a test can have any effect on the line ("none"), or kills the
-// whole line ("all"); only lines that are genuinely cut by a plane run the per-voxel loop, and only for that plane.
+// First pass: is the whole line removed by a single triangle?  (both ends beyond a voronoi/edge plane, or both ends
+// strictly inside a wall sector; exact by monotonicity).  Cheap: no per-voxel work, no searches.
 template <bool OPEN, class VVWarp>
-__device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1,
-                                          uint32_t &hit_lo, uint32_t &hit_hi, uint32_t &alive_lo, uint32_t &alive_hi,
-                                          uint32_t (&hlo)[5], uint32_t (&hhi)[5])
+__device__ __forceinline__ bool line_dead(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1, bool dead)
 {
-  const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
+  const float eps = a.eps, neps = -a.eps;
   const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
   const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
   for (int j = 0; j < tris; j++) {
-    // ---------------- cubes (crixus_d.cu:531-543): voxel is sampled if it lies in one of the two dr-cubes of j
-    const bool need_hit = (hit_lo != 0xffffffffu) | (hit_hi != 0x1ffu);
-    if (__any_sync(0xffffffffu, need_hit)) {
-      const float4 P0 = w.plane[j][0], P1 = w.plane[j][1], P2 = w.plane[j][2], P3 = w.plane[j][3];
-      const float t0 = ffma(gp1, P0.y, ffma(gp0, P0.x, 0.f));  // c0
-      const float t1 = ffma(gp1, P1.x, ffma(gp0, P0.w, 0.f));  // c1
-      const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
-      const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
-      const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
-      // both ends inside a cube => the whole line is inside it
-      const float e0 = fmaxf(fabsf(ffma(gA, P0.z, t0)), fabsf(ffma(gB, P0.z, t0)));
-      const float e1 = fmaxf(fabsf(ffma(gA, P1.y, t1)), fabsf(ffma(gB, P1.y, t1)));
-      const float e2 = fmaxf(fabsf(ffma(gA, P2.x, t2)), fabsf(ffma(gB, P2.x, t2)));
-      const float e3 = fmaxf(fabsf(ffma(gA, P2.w, t3)), fabsf(ffma(gB, P2.w, t3)));
-      const float e4 = fmaxf(fabsf(ffma(gA, P3.z, t4)), fabsf(ffma(gB, P3.z, t4)));
-      const bool full = (e0 <= thr && e1 <= thr && e2 <= thr) || (e2 <= thr && e3 <= thr && e4 <= thr);
-      if (full) { hit_lo = 0xffffffffu; hit_hi = 0x1ffu; }
-      if (__any_sync(0xffffffffu, need_hit && !full)) {
-        uint32_t in_lo = 0u, in_hi = 0u;
-#pragma unroll
-        for (int m = 0; m < VV_GS; m++) {
-          const float g = a.gz[m];
-          const bool i0 = fabsf(ffma(g, P0.z, t0)) <= thr;
-          const bool i1 = fabsf(ffma(g, P1.y, t1)) <= thr;
-          const bool i2 = fabsf(ffma(g, P2.x, t2)) <= thr;
-          const bool i3 = fabsf(ffma(g, P2.w, t3)) <= thr;
-          const bool i4 = fabsf(ffma(g, P3.z, t4)) <= thr;
-          if ((i0 && i1 && i2) || (i2 && i3 && i4)) {
-            if (m < 32) in_lo |= 1u << (m & 31);
-            else in_hi |= 1u << (m & 31);
-          }
-        }
-        hit_lo |= in_lo;
-        hit_hi |= in_hi;
-      }
+    if (!__any_sync(VV_FULLWARP, !dead)) break;
+    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
+                 P9 = w.plane[j][9];
+    const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
+    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
+    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
+    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
+    const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
+    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
+    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
+    const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
+    const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
+    const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
+    bool all = ((sVa > eps) && (sVb > eps)) || ((sEa > eps) && (sEb > eps));
+    if (OPEN) {
+      const float tV2 = ffma(fsub(q1, P6.z), P5.w, ffma(fsub(q0, P6.y), P5.z, 0.f));
+      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
+      all = all || ((s2a > eps) && (s2b > eps));
     }
-    // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
-    if (!__any_sync(0xffffffffu, (alive_lo | alive_hi) != 0u)) break;
+    all = all || ((w0a >= eps) && (w0b >= eps) && (w1a >= neps) && (w1b >= neps) && (w2a >= neps) && (w2b >= neps));
+    dead = dead || all;
+  }
+  return dead;
+}
+
+// contribution of the voxels in `va`, in units of 2^-31
+__device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&h)[5], int cmax)
+{
+  const uint64_t anyh = (h[0] | h[1] | h[2] | h[3] | h[4]) & va;
+  long long s = (long long)__popcll(va & ~anyh) << 31;
+  uint64_t r = anyh;
+  while (r) {
+    const int b = __ffsll((long long)r) - 1;
+    r &= r - 1;
+    const int c = (int)((h[0] >> b) & 1) | ((int)((h[1] >> b) & 1) << 1) | ((int)((h[2] >> b) & 1) << 2) |
+                  ((int)((h[3] >> b) & 1) << 3) | ((int)((h[4] >> b) & 1) << 4);
+    if (c <= cmax) s += 1ll << (31 - c);
+  }
+  return s;
+}
+
+// Second pass: the weight of one surviving z-line (in units of 2^-31), every lane of the warp on a line of its own.
+// Lanes without a line (valid == false) run along with an empty line.
+template <bool OPEN, class VVWarp>
+__device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
+                                                 float gp1, bool valid)
+{
+  const float thr = a.thr_cube, nthr = -a.thr_cube, eps = a.eps, neps = -a.eps;
+  const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
+  const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
+  const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
+  uint64_t alive = valid ? VV_ALL : 0ull;
+  uint64_t h[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+  // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
+  for (int j = 0; j < tris; j++) {
+    if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
     const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
                  P9 = w.plane[j][9];
     // c5 = (P4.x,P4.y,P4.z) c6 = (P4.w,P5.x,P5.y) c7 = (P5.z,P5.w,P6.x) c8 = (P6.y,P6.z,P6.w)
@@ -197,104 +285,108 @@ __device__ __forceinline__ void line_loop(const VVArgs &a, const VVWarp &w, int 
     const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
     const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
     const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
-    // values at the two ends of the line
-    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
+    auto fV = [&](float g) { return ffma(fsub(fadd(g, pi.z), P5.y), P4.z, tV); };
+    auto fV2 = [&](float g) { return ffma(fsub(fadd(g, pi.z), P6.w), P6.x, tV2); };
+    auto fE = [&](float g) { return ffma(fsub(g, P4.z), P9.w, tE); };
+    auto fW0 = [&](float g) { return ffma(g, P7.z, tW0); };
+    auto fW1 = [&](float g) { return ffma(g, P8.y, tW1); };
+    auto fW2 = [&](float g) { return ffma(g, P9.x, tW2); };
+    uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull;
+    bool trig = false;
+    plane_kill(gzt, ffma(fsub(q2A, P5.y), P4.z, tV), ffma(fsub(q2B, P5.y), P4.z, tV), fV, eps, K, HV, trig);
+    if (OPEN) plane_kill(gzt, ffma(fsub(q2A, P6.w), P6.x, tV2), ffma(fsub(q2B, P6.w), P6.x, tV2), fV2, eps, K, HV2, trig);
+    plane_kill(gzt, ffma(fsub(gA, P4.z), P9.w, tE), ffma(fsub(gB, P4.z), P9.w, tE), fE, eps, K, HE, trig);
+    // ---- wall tetrahedron: inside = all three w >= -eps; inside and |w0| < eps -> halved, inside otherwise -> removed
     const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
     const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
     const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
-    // "none": the test cannot touch any voxel of the line; "all": it removes every voxel of the line
-    bool noneV = (sVa <= neps) && (sVb <= neps), allV = (sVa > eps) && (sVb > eps);
-    if (OPEN) {
-      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
-      noneV = noneV && (s2a <= neps) && (s2b <= neps);
-      allV = allV || ((s2a > eps) && (s2b > eps));
-    }
-    const bool noneE = (sEa <= neps) && (sEb <= neps), allE = (sEa > eps) && (sEb > eps);
-    const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
-    const bool allW = (w0a >= eps) && (w0b >= eps) && (w1a >= neps) && (w1b >= neps) && (w2a >= neps) && (w2b >= neps);
-    if (allV || allE || allW) { alive_lo = 0u; alive_hi = 0u; }
-    const bool live = (alive_lo | alive_hi) != 0u;
-    uint32_t k_lo = 0u, k_hi = 0u;
-    float mn = 3.0e38f;
-    // ---- voronoi plane(s), per voxel, only if some line of the warp is cut by it
-    if (__any_sync(0xffffffffu, live && !noneV)) {
-#pragma unroll
-      for (int m = 0; m < VV_GS; m++) {
-        const float q2 = fadd(a.gz[m], pi.z);
-        const float sV = ffma(fsub(q2, P5.y), P4.z, tV);
-        bool kill = sV > eps;
-        float av = fabsf(sV);
-        if (OPEN) {
-          const float sV2 = ffma(fsub(q2, P6.w), P6.x, tV2);
-          kill |= sV2 > eps;
-          av = fminf(av, fabsf(sV2));
-        }
-        mn = fminf(mn, av);
-        if (kill) {
-          if (m < 32) k_lo |= 1u << (m & 31);
-          else k_hi |= 1u << (m & 31);
-        }
+    auto ge = [&](float v) { return !(v < neps); };
+    int lo0, lo1, lo2;
+    bool pa0, pa1, pa2;
+    const uint64_t IN0 = mono_mask(gzt, w0a, w0b, fW0, ge, lo0, pa0);
+    const uint64_t IN1 = mono_mask(gzt, w1a, w1b, fW1, ge, lo1, pa1);
+    const uint64_t IN2 = mono_mask(gzt, w2a, w2b, fW2, ge, lo2, pa2);
+    const uint64_t inside = IN0 & IN1 & IN2;
+    // LT = {w0 < eps}.  On a line cut by IN0 it is the complement of IN0 plus the n voxels of IN0 next to the flip that
+    // lie in the wall plane (n = 0 or 1 in all but degenerate cases).
+    const bool cut0 = pa0 != !(w0b < neps);
+    uint64_t LT;
+    bool needLT;
+    {
+      const int d = pa0 ? -1 : 1, t1 = pa0 ? lo0 : lo0 + 1;
+      const int t2 = min(max(t1 + d, 0), VV_GS - 1);
+      const float v1 = fW0(gzt[t1]), v2 = fW0(gzt[t2]);
+      const bool b1 = v1 < eps, b2 = v2 < eps;
+      const bool Ba = w0a < eps, Bb = w0b < eps;
+      if (cut0) {
+        trig |= (v1 == neps);                     // |w0| == eps exactly: IN0 true but not "in the wall plane"
+        needLT = b1 && b2 && (t2 != t1);          // two or more voxels in the plane band: search
+        LT = (VV_ALL & ~IN0) | (b1 ? (1ull << t1) : 0ull);
+      } else {
+        trig |= pa0 && (fminf(w0a, w0b) == neps);
+        needLT = Ba != Bb;
+        LT = Ba ? VV_ALL : 0ull;
       }
     }
-    // ---- edge plane
-    if (__any_sync(0xffffffffu, live && !noneE)) {
-#pragma unroll
-      for (int m = 0; m < VV_GS; m++) {
-        const float sE = ffma(fsub(a.gz[m], P4.z), P9.w, tE);
-        mn = fminf(mn, fabsf(sE));
-        if (sE > eps) {
-          if (m < 32) k_lo |= 1u << (m & 31);
-          else k_hi |= 1u << (m & 31);
-        }
-      }
+    if (__any_sync(VV_FULLWARP, needLT)) {
+      int lo_;
+      bool pa_;
+      const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
+      if (needLT) LT = m;
     }
-    // ---- wall tetrahedron
-    if (__any_sync(0xffffffffu, live && !noneW)) {
-      uint32_t hw_lo = 0u, hw_hi = 0u;
-#pragma unroll
-      for (int m = 0; m < VV_GS; m++) {
-        const float g = a.gz[m];
-        const float w0 = ffma(g, P7.z, tW0), w1 = ffma(g, P8.y, tW1), w2 = ffma(g, P9.x, tW2);
-        const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
-        const bool hw = fabsf(w0) < eps;
-        if (m < 32) {
-          if (inside && !hw) k_lo |= 1u << (m & 31);
-          if (inside && hw) hw_lo |= 1u << (m & 31);
-        } else {
-          if (inside && !hw) k_hi |= 1u << (m & 31);
-          if (inside && hw) hw_hi |= 1u << (m & 31);
-        }
-      }
-      half_inc(hlo, hw_lo);   // voxels in the wall plane of j's sector: weight halved (crixus_d.cu:632,640-642)
-      half_inc(hhi, hw_hi);
-    }
-    alive_lo &= ~k_lo;
-    alive_hi &= ~k_hi;
-    const bool ev = mn < eps && live;
-    if (__any_sync(0xffffffffu, ev)) {
-      HalfCtx c;
+    K |= inside & ~LT;
+    uint64_t HW = inside & LT;
+    trig = trig && (alive != 0ull);
+    if (__any_sync(VV_FULLWARP, trig)) {
+      TriCtx c;
       c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
       c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
-      half_events(a, c, hlo, hhi, ev);
+      exact_tri(a, c, trig, K, h);
+      if (trig) { HV = 0ull; HV2 = 0ull; HE = 0ull; HW = 0ull; }
+    }
+    if (__any_sync(VV_FULLWARP, HW != 0ull)) half_inc(h, HW);
+    if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { half_inc(h, HV); half_inc(h, HE); }
+    if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc(h, HV2);
+    alive &= ~K;
+  }
+  // ---------------- cubes (crixus_d.cu:531-543): a voxel is sampled if it lies in one of the two dr-cubes of some j
+  uint64_t hit = 0ull;
+  for (int j = 0; j < tris; j++) {
+    if (!__any_sync(VV_FULLWARP, (alive & ~hit) != 0ull)) break;
+    const float4 P0 = w.plane[j][0], P1 = w.plane[j][1], P2 = w.plane[j][2], P3 = w.plane[j][3];
+    const float t0 = ffma(gp1, P0.y, ffma(gp0, P0.x, 0.f));  // c0
+    const float t1 = ffma(gp1, P1.x, ffma(gp0, P0.w, 0.f));  // c1
+    const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
+    const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
+    const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
+    const float a0 = ffma(gA, P0.z, t0), b0 = ffma(gB, P0.z, t0);
+    const float a1 = ffma(gA, P1.y, t1), b1 = ffma(gB, P1.y, t1);
+    const float a2 = ffma(gA, P2.x, t2), b2 = ffma(gB, P2.x, t2);
+    const float a3 = ffma(gA, P2.w, t3), b3 = ffma(gB, P2.w, t3);
+    const float a4 = ffma(gA, P3.z, t4), b4 = ffma(gB, P3.z, t4);
+    // both ends inside a cube => the whole line is inside it
+    const bool i0 = fmaxf(fabsf(a0), fabsf(b0)) <= thr, i1 = fmaxf(fabsf(a1), fabsf(b1)) <= thr, i2 = fmaxf(fabsf(a2), fabsf(b2)) <= thr,
+               i3 = fmaxf(fabsf(a3), fabsf(b3)) <= thr, i4 = fmaxf(fabsf(a4), fabsf(b4)) <= thr;
+    const bool full = (i0 && i1 && i2) || (i2 && i3 && i4);
+    if (full) hit = VV_ALL;
+    if (__any_sync(VV_FULLWARP, !full && (alive & ~hit) != 0ull)) {
+      auto le = [&](float v) { return v <= thr; };
+      auto ge = [&](float v) { return v >= nthr; };
+      int lo_;
+      bool pa_;
+#define VV_SLAB(fa, fb, C, T)                                                                       \
+  (mono_mask(gzt, fa, fb, [&](float g) { return ffma(g, C, T); }, le, lo_, pa_) &                    \
+   mono_mask(gzt, fa, fb, [&](float g) { return ffma(g, C, T); }, ge, lo_, pa_))
+      const uint64_t s0 = VV_SLAB(a0, b0, P0.z, t0);
+      const uint64_t s1 = VV_SLAB(a1, b1, P1.y, t1);
+      const uint64_t s2 = VV_SLAB(a2, b2, P2.x, t2);
+      const uint64_t s3 = VV_SLAB(a3, b3, P2.w, t3);
+      const uint64_t s4 = VV_SLAB(a4, b4, P3.z, t4);
+#undef VV_SLAB
+      hit |= (s0 & s1 & s2) | (s2 & s3 & s4);
     }
   }
-}
-
-// contribution of one 32-bit group of voxels, in units of 2^-31
-__device__ __forceinline__ long long group_weight(uint32_t va, const uint32_t (&h)[5], int cmax)
-{
-  const uint32_t anyh = (h[0] | h[1] | h[2] | h[3] | h[4]) & va;
-  long long s = (long long)__popc(va & ~anyh) << 31;
-  uint32_t r = anyh;
-  while (r) {
-    const int b = __ffs(r) - 1;
-    r &= r - 1;
-    const int c = ((h[0] >> b) & 1) | (((h[1] >> b) & 1) << 1) | (((h[2] >> b) & 1) << 2) | (((h[3] >> b) & 1) << 3) |
-                  (((h[4] >> b) & 1) << 4);
-    if (c <= cmax) s += 1ll << (31 - c);
-  }
-  return s;
+  return valid ? group_weight(hit & alive, h, a.cmax) : 0ll;
 }
 
 template <int TCAP, bool LIST>
@@ -302,8 +394,13 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
 {
   typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
+  __shared__ float gzt[64];                       // gz[0..40] for lane-dependent lookups (the rest is padding)
+  __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
+  unsigned short *wq = wqs[threadIdx.x >> 5];
+  if (threadIdx.x < 64) gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
+  __syncthreads();
   const cx_params &p = a.p;
 
   for (;;) {
@@ -464,20 +561,33 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     __syncwarp();
 
     // ---------------- the voxel cube: lanes take z-lines (k = x index, l = y index), crixus_d.cu:488-670
+    // pass 1 drops the lines that a single triangle removes entirely (typically 60-70 % of them); the survivors are
+    // compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
     long long acc = 0;
-    // all 32 lanes run the same number of iterations (line_loop uses full-warp votes); surplus lanes carry a dead line
+    int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
     for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
       const int line = it * 32 + lane;
       const bool valid = line < VV_LINES;
       const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
-      uint32_t hit_lo = valid ? 0u : 0xffffffffu, hit_hi = valid ? 0u : 0x1ffu;
-      uint32_t alive_lo = valid ? 0xffffffffu : 0u, alive_hi = valid ? 0x1ffu : 0u;
-      uint32_t hlo[5] = {0u, 0u, 0u, 0u, 0u}, hhi[5] = {0u, 0u, 0u, 0u, 0u};
       // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
-      const float g0 = a.gz[k], g1 = a.gz[l];
-      if (closed) line_loop<false, VVWarp>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
-      else line_loop<true, VVWarp>(a, w, tris, pi, g0, g1, hit_lo, hit_hi, alive_lo, alive_hi, hlo, hhi);
-      if (valid) acc += group_weight(hit_lo & alive_lo, hlo, a.cmax) + group_weight(hit_hi & alive_hi & 0x1ffu, hhi, a.cmax);
+      const float g0 = gzt[k], g1 = gzt[l];
+      const bool dead = closed ? line_dead<false, VVWarp>(a, w, tris, pi, g0, g1, !valid) : line_dead<true, VVWarp>(a, w, tris, pi, g0, g1, !valid);
+      const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
+      if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
+      qn += __popc(live);
+      __syncwarp();
+      const bool last = it == (VV_LINES + 31) / 32 - 1;
+      while (qn >= 32 || (last && qn > 0)) {
+        const bool have = lane < qn;
+        const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
+        const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
+        const float h0 = gzt[kk], h1 = gzt[ll];
+        acc += closed ? line_weight<false, VVWarp>(a, w, gzt, tris, pi, h0, h1, have) : line_weight<true, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
+        const int took = min(qn, 32);
+        qh = (qh + took) & 63;
+        qn -= took;
+        __syncwarp();
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
