@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     deps = cu + host + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "host", "*.h")) + \
         [os.path.join(HERE, "..", "include", "crixus_b200.h")]
     if force or _newer(LIB, deps):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB] + cu + lib_host + ["-lcudart"]
+        cmd = ["nvcc"] + NVCC_FLAGS + os.environ.get("CX_NVCC_EXTRA", "").split() + ["-shared", "-o", LIB] + cu + lib_host + ["-lcudart"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -110,7 +110,32 @@ __device__ __forceinline__ void half_inc(uint64_t (&h)[5], uint64_t m)
   for (int b = 0; b < 5; b++) h[b] |= c;  // overflow -> stay at 31
 }
 
+// same, called by the converged warp: almost every voxel is halved at most once, so the carry out of bit 0 is empty
+__device__ __forceinline__ void half_inc_warp(uint64_t (&h)[5], uint64_t m)
+{
+  uint64_t c = h[0] & m;
+  h[0] ^= m;
+  if (__any_sync(VV_FULLWARP, c != 0ull)) {
+#pragma unroll
+    for (int b = 1; b < 5; b++) {
+      const uint64_t t = h[b] & c;
+      h[b] ^= c;
+      c = t;
+    }
+#pragma unroll
+    for (int b = 0; b < 5; b++) h[b] |= c;
+  }
+}
+
 __device__ __forceinline__ uint64_t lowmask(int b) { return (1ull << b) - 1ull; }   // b in [0, 63]
+__device__ __forceinline__ uint64_t bit64(int b) { return 1ull << b; }
+
+#ifdef VV_STATS
+__device__ unsigned long long vv_stats[16];
+#define VV_STAT(i, n) do { if ((threadIdx.x & 31) == 0) atomicAdd(&vv_stats[i], (unsigned long long)(n)); } while (0)
+#else
+#define VV_STAT(i, n) do { } while (0)
+#endif
 
 // Every plane expression of the reference is, along a z-line, a composition of correctly rounded (hence monotone)
 // operations of gz, and gz[m] is non-decreasing in m.  A threshold predicate of such an expression is therefore a
@@ -140,13 +165,16 @@ __device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float 
   pa = pv(fa);
   const bool pb = pv(fb);
   lo = VV_GS - 1;
-  if (__any_sync(VV_FULLWARP, pa != pb)) {
+  const unsigned cutm = __ballot_sync(VV_FULLWARP, pa != pb);
+  if (cutm) {
+    VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
     const bool pa_ = pa;
     const int s = mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
     if (pa != pb) lo = s;
   }
-  const uint64_t lm = lowmask(lo + 1);
-  return pa ? lm : (VV_ALL & ~lm);
+  // lmt[1][b] = the b lowest voxels, lmt[0][b] = the others (gzt + 64 floats = two tables of 64 x uint64)
+  const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
+  return lmt[(pa ? 64 : 0) + lo + 1];
 }
 
 struct TriCtx {
@@ -197,10 +225,15 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   bool pa;
   K |= mono_mask(gzt, fa, fb, f, [&](float v) { return v > eps; }, lo, pa);
   const bool pb = fb > eps;
-  // the largest value among the voxels that survive: next to the flip (cut lines) / the larger end (uncut lines)
-  const float fnext = f(gzt[pa ? lo + 1 : lo]);
   if (pa != pb) {
-    trig |= fnext > neps;          // a surviving voxel may lie within eps of the plane: let exact_tri decide
+    // the surviving voxels next to the flip carry the largest values: the first one may lie within eps of the plane
+    const int d = pa ? 1 : -1, t1 = pa ? lo + 1 : lo;
+    const int t2 = min(max(t1 + d, 0), VV_GS - 1);
+    const float v1 = f(gzt[t1]), v2 = f(gzt[t2]);
+    if (v1 > neps) {
+      if (v1 == eps || (t2 != t1 && v2 > neps)) trig = true;   // exactly on the threshold / two voxels in the band
+      else H = bit64(t1);
+    }
   } else {
     const bool Aa = fa > neps, Ab = fb > neps, Ba = fa < eps, Bb = fb < eps;
     if (Aa != Ab || Ba != Bb) trig = true;
@@ -219,6 +252,7 @@ __device__ __forceinline__ bool line_dead(const VVArgs &a, const VVWarp &w, int 
   const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
   for (int j = 0; j < tris; j++) {
     if (!__any_sync(VV_FULLWARP, !dead)) break;
+    VV_STAT(0, 1);
     const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
                  P9 = w.plane[j][9];
     const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
@@ -248,13 +282,20 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
 {
   const uint64_t anyh = (h[0] | h[1] | h[2] | h[3] | h[4]) & va;
   long long s = (long long)__popcll(va & ~anyh) << 31;
-  uint64_t r = anyh;
-  while (r) {
-    const int b = __ffsll((long long)r) - 1;
-    r &= r - 1;
-    const int c = (int)((h[0] >> b) & 1) | ((int)((h[1] >> b) & 1) << 1) | ((int)((h[2] >> b) & 1) << 2) |
-                  ((int)((h[3] >> b) & 1) << 3) | ((int)((h[4] >> b) & 1) << 4);
-    if (c <= cmax) s += 1ll << (31 - c);
+  if (anyh) {
+    const uint64_t big = (h[2] | h[3] | h[4]) & va;          // halved four times or more: rare, one by one
+    const uint64_t sm = va & ~big;
+    if (cmax >= 1) s += (long long)__popcll(sm & h[0] & ~h[1]) << 30;
+    if (cmax >= 2) s += (long long)__popcll(sm & ~h[0] & h[1]) << 29;
+    if (cmax >= 3) s += (long long)__popcll(sm & h[0] & h[1]) << 28;
+    uint64_t r = big;
+    while (r) {
+      const int b = __ffsll((long long)r) - 1;
+      r &= r - 1;
+      const int c = (int)((h[0] >> b) & 1) | ((int)((h[1] >> b) & 1) << 1) | ((int)((h[2] >> b) & 1) << 2) |
+                    ((int)((h[3] >> b) & 1) << 3) | ((int)((h[4] >> b) & 1) << 4);
+      if (c <= cmax) s += 1ll << (31 - c);
+    }
   }
   return s;
 }
@@ -321,7 +362,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       if (cut0) {
         trig |= (v1 == neps);                     // |w0| == eps exactly: IN0 true but not "in the wall plane"
         needLT = b1 && b2 && (t2 != t1);          // two or more voxels in the plane band: search
-        LT = (VV_ALL & ~IN0) | (b1 ? (1ull << t1) : 0ull);
+        LT = (VV_ALL & ~IN0) | (b1 ? bit64(t1) : 0ull);
       } else {
         trig |= pa0 && (fminf(w0a, w0b) == neps);
         needLT = Ba != Bb;
@@ -329,6 +370,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       }
     }
     if (__any_sync(VV_FULLWARP, needLT)) {
+      VV_STAT(9, 1);
       int lo_;
       bool pa_;
       const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
@@ -337,16 +379,18 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     K |= inside & ~LT;
     uint64_t HW = inside & LT;
     trig = trig && (alive != 0ull);
+    VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
+      VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
       TriCtx c;
       c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
       c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
       exact_tri(a, c, trig, K, h);
       if (trig) { HV = 0ull; HV2 = 0ull; HE = 0ull; HW = 0ull; }
     }
-    if (__any_sync(VV_FULLWARP, HW != 0ull)) half_inc(h, HW);
-    if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { half_inc(h, HV); half_inc(h, HE); }
-    if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc(h, HV2);
+    if (__any_sync(VV_FULLWARP, HW != 0ull)) { VV_STAT(7, 1); half_inc_warp(h, HW); }
+    if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { VV_STAT(8, 1); half_inc_warp(h, HV); half_inc_warp(h, HE); }
+    if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc_warp(h, HV2);
     alive &= ~K;
   }
   // ---------------- cubes (crixus_d.cu:531-543): a voxel is sampled if it lies in one of the two dr-cubes of some j
@@ -369,7 +413,9 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
                i3 = fmaxf(fabsf(a3), fabsf(b3)) <= thr, i4 = fmaxf(fabsf(a4), fabsf(b4)) <= thr;
     const bool full = (i0 && i1 && i2) || (i2 && i3 && i4);
     if (full) hit = VV_ALL;
+    VV_STAT(10, 1);
     if (__any_sync(VV_FULLWARP, !full && (alive & ~hit) != 0ull)) {
+      VV_STAT(11, 1);
       auto le = [&](float v) { return v <= thr; };
       auto ge = [&](float v) { return v >= nthr; };
       int lo_;
@@ -394,12 +440,19 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
 {
   typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
-  __shared__ float gzt[64];                       // gz[0..40] for lane-dependent lookups (the rest is padding)
+  __shared__ __align__(16) float gzt[64 + 256];   // gz[0..40] for lane-dependent lookups (padded to 64), then the two
+                                                  // 64-entry uint64 mask tables used by mono_mask
   __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
   unsigned short *wq = wqs[threadIdx.x >> 5];
-  if (threadIdx.x < 64) gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
+  if (threadIdx.x < 64) {
+    gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
+    uint64_t *lmt = reinterpret_cast<uint64_t *>(gzt + 64);
+    const uint64_t lm = threadIdx.x <= VV_GS ? lowmask(threadIdx.x) : VV_ALL;
+    lmt[threadIdx.x] = VV_ALL & ~lm;
+    lmt[64 + threadIdx.x] = lm;
+  }
   __syncthreads();
   const cx_params &p = a.p;
 
@@ -579,6 +632,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       const bool last = it == (VV_LINES + 31) / 32 - 1;
       while (qn >= 32 || (last && qn > 0)) {
         const bool have = lane < qn;
+        VV_STAT(6, min(qn, 32)); VV_STAT(12, 1);
         const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
         const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
         const float h0 = gzt[kk], h1 = gzt[ll];
@@ -649,6 +703,17 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   CX_CUDA(ctx, cudaFreeAsync(a.big_list, ctx->stream));
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 17, ctx->d_mail + 17, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef VV_STATS
+  {
+    unsigned long long st[16];
+    cudaMemcpyFromSymbol(st, vv_stats, sizeof(st));
+    fprintf(stderr, "VV_STATS verts=%lld pass1=%llu pass2=%llu searches=%llu cut_lanes=%llu exact=%llu exact_lanes=%llu alive_lines=%llu "
+            "hw_inc=%llu hve_inc=%llu lt_search=%llu cube_it=%llu cube_search=%llu batches=%llu\n", (long long)(v_end - v_begin), st[0], st[1],
+            st[2], st[3], st[4], st[5], st[6], st[7], st[8], st[9], st[10], st[11], st[12]);
+    memset(st, 0, sizeof(st));
+    cudaMemcpyToSymbol(vv_stats, st, sizeof(st));
+  }
+#endif
   const int err = *(int *)(ctx->h_mail + 17);
   if (err & VVE_TRIMAX) return cx_fail(ctx, CX_TRIMAX_EXCEEDED, "calc_vert_volume: a vertex has more than trimax triangles");
   if (err & VVE_FAN) return cx_fail(ctx, CX_FAN_INCOMPLETE, "calc_vert_volume: fan triangles missing from the 27-cell neighbourhood");
