@@ -332,15 +332,25 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     auto fW0 = [&](float g) { return ffma(g, P7.z, tW0); };
     auto fW1 = [&](float g) { return ffma(g, P8.y, tW1); };
     auto fW2 = [&](float g) { return ffma(g, P9.x, tW2); };
-    uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull;
+    uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull, HW = 0ull;
     bool trig = false;
-    plane_kill(gzt, ffma(fsub(q2A, P5.y), P4.z, tV), ffma(fsub(q2B, P5.y), P4.z, tV), fV, eps, K, HV, trig);
-    if (OPEN) plane_kill(gzt, ffma(fsub(q2A, P6.w), P6.x, tV2), ffma(fsub(q2B, P6.w), P6.x, tV2), fV2, eps, K, HV2, trig);
-    plane_kill(gzt, ffma(fsub(gA, P4.z), P9.w, tE), ffma(fsub(gB, P4.z), P9.w, tE), fE, eps, K, HE, trig);
+    const bool live = alive != 0ull;
+    // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
+    // line is (by monotonicity) on the near side of the plane and further than eps from it.
+    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
+    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    if (OPEN) {
+      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
+      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
+    }
+    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
+    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
     // ---- wall tetrahedron: inside = all three w >= -eps; inside and |w0| < eps -> halved, inside otherwise -> removed
     const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
     const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
     const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
+    const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
+    if (__any_sync(VV_FULLWARP, live && !noneW)) {
     auto ge = [&](float v) { return !(v < neps); };
     int lo0, lo1, lo2;
     bool pa0, pa1, pa2;
@@ -377,8 +387,9 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       if (needLT) LT = m;
     }
     K |= inside & ~LT;
-    uint64_t HW = inside & LT;
-    trig = trig && (alive != 0ull);
+    HW = inside & LT;
+    }
+    trig = trig && live;
     VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
       VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
@@ -488,18 +499,23 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     const int gy = cell_coord(pi.y, p.dmin[1], p.griddr[1], p.gridn[1]);
     const int gz = cell_coord(pi.z, p.dmin[2], p.griddr[2], p.gridn[2]);
 
+    // the 27 neighbouring 3dr-cells (crixus_d.cu:327-347): lane c holds the segment range of cell c (empty if skipped)
+    int cb = 0, ce = 0;
+    if (lane < 27) {
+      const int64_t c = nb_cell(p, gx + lane / 9 - 1, gy + (lane / 3) % 3 - 1, gz + lane % 3 - 1);
+      if (c >= 0) { cb = __ldg(&a.cell_idx[c]); ce = __ldg(&a.cell_idx[c + 1]); }
+    }
     // ---------------- fan gather (crixus_d.cu:316-369): discovery order = cell order, segment order, corner order
     int itris = 0;
     for (int c27 = 0; c27 < 27; c27++) {
-      const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
-      if (c < 0) continue;
-      const int b = __ldg(&a.cell_idx[c]), e = __ldg(&a.cell_idx[c + 1]);
+      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
       for (int base = b; base < e; base += 32) {
         const int j = base + lane;
         int4 E = make_int4(-1, -1, -1, -1);
         if (j < e) E = __ldg(&a.ep[j]);
         const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
         const int cnt = m0 + m1 + m2;
+        if (!__any_sync(0xffffffffu, cnt != 0)) continue;
         const int incl = warp_incl_scan_i(cnt, lane);
         int off = itris + incl - cnt;
         if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
@@ -544,15 +560,21 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       continue;
     }
 
-    // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k
+    // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k.
+    // A 64-bit filter of the rim vertices (id mod 64) rejects almost every segment batch without entering the k loop.
+    uint64_t rim = 0ull;
+    for (int k = 0; k < tris; k++) rim |= (1ull << (w.tri[k][0] & 63)) | (1ull << (w.tri[k][1] & 63));
     for (int c27 = 0; c27 < 27; c27++) {
-      const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
-      if (c < 0) continue;
-      const int b = __ldg(&a.cell_idx[c]), e = __ldg(&a.cell_idx[c + 1]);
+      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
       for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
         const int j = base + lane;
         int4 E = make_int4(-1, -1, -1, -1);
-        if (j < e) E = __ldg(&a.ep[j]);
+        bool cand = false;
+        if (j < e) {
+          E = __ldg(&a.ep[j]);
+          cand = (int)((rim >> (E.x & 63)) & 1ull) + (int)((rim >> (E.y & 63)) & 1ull) + (int)((rim >> (E.z & 63)) & 1ull) >= 2;
+        }
+        if (!__any_sync(0xffffffffu, cand)) continue;
         for (int k = 0; k < tris; k++) {
           const int t0 = w.tri[k][0], t1 = w.tri[k][1];
           const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
