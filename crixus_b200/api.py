@@ -104,6 +104,18 @@ def lib():
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+        "cx_ini_open": (C.c_int, [C.c_char_p, C.POINTER(VP)]),
+        "cx_ini_close": (None, [VP]),
+        "cx_ini_get": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+        "cx_ini_get_integer": (C.c_long, [VP, C.c_char_p, C.c_char_p, C.c_long]),
+        "cx_ini_get_real": (C.c_double, [VP, C.c_char_p, C.c_char_p, C.c_double]),
+        "cx_ini_get_boolean": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_int]),
+        "cx_stl_read": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)), C.POINTER(I64)]),
+        "cx_free": (None, [VP]),
+        "cx_assemble_records": (I64, [C.POINTER(CxJob), I64, VP, I64]),
+        "cx_write_vtu_records": (C.c_int, [VP, I64, C.c_char_p]),
+        "cx_write_h5sph_records": (C.c_int, [VP, I64, C.c_char_p]),
+        "cx_run_ini": (C.c_int, [C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError if the library lacks a declared symbol

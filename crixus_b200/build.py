@@ -26,7 +26,7 @@ def _newer(target, sources):
 def build(force=False, verbose=False):
     cu = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     host = sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
-    lib_host = [h for h in host if os.path.basename(h) in ("weld.cpp", "pipeline.cpp")]
+    lib_host = [h for h in host if os.path.basename(h) != "main.cpp"]
     deps = cu + host + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "host", "*.h")) + \
         [os.path.join(HERE, "..", "include", "crixus_b200.h")]
     if force or _newer(LIB, deps):
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     main = os.path.join(CSRC, "host", "main.cpp")
     if os.path.exists(main) and (force or _newer(CLI, deps)):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
-        cli_src = [main] + [os.path.join(CSRC, "host", f) for f in ("ini.cpp", "output.cpp")]
+        cli_src = [main]
         cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(HERE, "..", "include")] + cli_src + ["-o", CLI,
                "-L" + HERE, "-lcrixus_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..",
                "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"]

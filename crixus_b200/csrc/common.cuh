@@ -24,6 +24,10 @@ struct cx_ctx {
   int64_t *d_mail = nullptr;  // 64 x int64 device
   // persistent fill state for the slab variant
   void *fill_state = nullptr;
+  // grow-only arenas of cx_preprocess_host: device working set and pinned host result buffers (cudaMalloc and
+  // page-locking cost milliseconds per call; the arenas make repeated calls allocation-free)
+  void *dev_arena = nullptr, *host_arena = nullptr;
+  size_t dev_arena_bytes = 0, host_arena_bytes = 0;
 };
 
 int cx_fail(cx_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);

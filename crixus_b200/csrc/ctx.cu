@@ -71,10 +71,52 @@ void cx_destroy(cx_ctx *ctx)
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cx_fill_state_free(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->dev_arena) cudaFree(ctx->dev_arena);
+  if (ctx->host_arena) cudaFreeHost(ctx->host_arena);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   if (ctx->d_mail) cudaFree(ctx->d_mail);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+void *cx_internal_dev_arena(cx_ctx *ctx, size_t bytes)
+{
+  if (bytes > ctx->dev_arena_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->dev_arena) cudaFree(ctx->dev_arena);
+    ctx->dev_arena = nullptr; ctx->dev_arena_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    if (cudaMalloc(&ctx->dev_arena, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->dev_arena_bytes = want;
+  }
+  return ctx->dev_arena;
+}
+
+void *cx_internal_host_arena(cx_ctx *ctx, size_t bytes)
+{
+  if (bytes > ctx->host_arena_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->host_arena) cudaFreeHost(ctx->host_arena);
+    ctx->host_arena = nullptr; ctx->host_arena_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    if (cudaMallocHost(&ctx->host_arena, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->host_arena_bytes = want;
+  }
+  return ctx->host_arena;
+}
+
+__global__ void __launch_bounds__(256) k_expand3(const float *__restrict__ s, float4 *__restrict__ d, int64_t n)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = make_float4(s[3 * i], s[3 * i + 1], s[3 * i + 2], 0.f);
+}
+
+int cx_internal_expand3(cx_ctx *ctx, const float *src3_d, float *dst4_d, int64_t n)
+{
+  if (n <= 0) return CX_OK;
+  k_expand3<<<cx_blocks(n, 256, ctx->num_sms * 16), 256, 0, ctx->stream>>>(src3_d, (float4 *)dst4_d, n);
+  CX_LAUNCH_CHECK(ctx, "k_expand3");
+  return CX_OK;
 }
 
 int cx_set_stream(cx_ctx *ctx, void *s)

@@ -1,0 +1,171 @@
+// crixus_b200 -- the reference's process surface behind the C-ABI: .ini reader, binary STL reader, particle-record
+// assembly, VTU / h5sph writers, and cx_run_ini = what `Crixus file.ini` does
+// (/root/reference/src/crixus.cu:57-73,126-221,310,394,433,647-649,698-707,737-795,973-1135; src/crixus.cpp:12-289).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "ini.h"
+#include "output.h"
+
+struct cx_ini {
+  CxIni ini;
+  explicit cx_ini(const char *fn) : ini(fn) {}
+};
+
+extern "C" {
+
+int cx_ini_open(const char *filename, cx_ini **out)
+{
+  if (!filename || !out) return CX_WRONG_INPUT;
+  *out = new cx_ini(filename);
+  return (*out)->ini.ParseError();
+}
+void cx_ini_close(cx_ini *ini) { delete ini; }
+int cx_ini_get(const cx_ini *ini, const char *section, const char *name, const char *def, char *buf, int buflen)
+{
+  if (!ini || !section || !name || !buf || buflen <= 0) return CX_WRONG_INPUT;
+  const std::string v = ini->ini.Get(section, name, def ? def : "");
+  snprintf(buf, (size_t)buflen, "%s", v.c_str());
+  return (int)v.size();
+}
+long cx_ini_get_integer(const cx_ini *ini, const char *section, const char *name, long def) { return ini->ini.GetInteger(section, name, def); }
+double cx_ini_get_real(const cx_ini *ini, const char *section, const char *name, double def) { return ini->ini.GetReal(section, name, def); }
+int cx_ini_get_boolean(const cx_ini *ini, const char *section, const char *name, int def) { return ini->ini.GetBoolean(section, name, def != 0) ? 1 : 0; }
+
+void cx_free(void *p) { free(p); }
+
+int cx_stl_read(const char *filename, float **corners, float **normals, int64_t *nbe)
+{
+  if (!filename || !corners || !normals || !nbe) return CX_WRONG_INPUT;
+  *corners = *normals = nullptr;
+  *nbe = 0;
+  std::vector<float> c, n;
+  const int rc = cx_read_stl(filename, c, n);
+  if (rc != CX_OK) return rc;
+  *nbe = (int64_t)(n.size() / 3);
+  *corners = (float *)malloc(std::max<size_t>(c.size() * 4, 4));
+  *normals = (float *)malloc(std::max<size_t>(n.size() * 4, 4));
+  if (!*corners || !*normals) return CX_INTERNAL_ERROR;
+  memcpy(*corners, c.data(), c.size() * 4);
+  memcpy(*normals, n.data(), n.size() * 4);
+  return CX_OK;
+}
+
+int64_t cx_assemble_records(const cx_job *job, int64_t nfluid_for_indices, void *records, int64_t capacity)
+{
+  if (!job || !job->pos || !job->fpos) return CX_WRONG_INPUT;
+  const std::vector<CxOutBuf> buf = cx_assemble(*job, nfluid_for_indices);
+  if (records) {
+    if ((int64_t)buf.size() > capacity) return CX_WRONG_INPUT;
+    memcpy(records, buf.data(), buf.size() * sizeof(CxOutBuf));
+  }
+  return (int64_t)buf.size();
+}
+
+static std::vector<CxOutBuf> as_vector(const void *records, int64_t n)
+{
+  std::vector<CxOutBuf> v((size_t)(n > 0 ? n : 0));
+  if (n > 0) memcpy(v.data(), records, (size_t)n * sizeof(CxOutBuf));
+  return v;
+}
+int cx_write_vtu_records(const void *records, int64_t n, const char *filename)
+{
+  if ((!records && n > 0) || !filename) return CX_WRONG_INPUT;
+  return cx_write_vtu(as_vector(records, n), filename);
+}
+int cx_write_h5sph_records(const void *records, int64_t n, const char *filename)
+{
+  if ((!records && n > 0) || !filename) return CX_WRONG_INPUT;
+  return cx_write_h5sph(as_vector(records, n), filename);
+}
+
+int cx_run_ini(const char *ini_path)
+{
+  printf("\n\tcrixus_b200 -- B200-native Crixus hot path (%s)\n\n", cx_version());
+  if (!ini_path) {
+    printf("No configuration file specified.\nCorrect use: crixus filename\nExample use: crixus box.ini\n");
+    return CX_NO_FILE;
+  }
+  const std::string cfg = ini_path;
+  CxIni ini(cfg);
+  if (ini.ParseError() < 0) { printf("Can't load configuration file %s\n", cfg.c_str()); return CX_CANT_READ_CONFIG; }
+  const std::string stl = ini.Get("mesh", "stlfile", "UNKNOWN");
+  const float dr = (float)ini.GetReal("mesh", "dr", -1);
+  printf("Opening file %s ...", stl.c_str());
+  std::vector<float> corners, normals, fs_corners, fs_normals;
+  int rc = cx_read_stl(stl, corners, normals);
+  if (rc != CX_OK) { printf(" [FAILED]\n"); return rc; }
+  printf(" [OK]\nMesh size: %g\nRead %zu facets\n", dr, normals.size() / 3);
+  if (!(dr > 0) || normals.empty()) return CX_WRONG_INPUT;
+
+  cx_job job;
+  memset(&job, 0, sizeof(job));
+  job.corners = corners.data(); job.normals = normals.data(); job.nbe = (int64_t)(normals.size() / 3); job.dr = dr;
+  job.swap_normals = ini.GetBoolean("mesh", "swap_normals", false);
+  job.zero_open = ini.GetBoolean("mesh", "zeroOpen", false);
+  const char *ax[3] = {"x", "y", "z"};
+  for (int d = 0; d < 3; d++) job.periodic[d] = ini.GetBoolean("periodicity", ax[d], false);
+  job.use_container = ini.GetBoolean("fluid_container", "use", false);
+  if (job.use_container)
+    for (int d = 0; d < 3; d++) {
+      job.cmin[d] = (float)ini.GetReal("fluid_container", std::string(ax[d]) + "min", 1e9);
+      job.cmax[d] = (float)ini.GetReal("fluid_container", std::string(ax[d]) + "max", -1e9);
+    }
+  // free-surface shape: default <ini minus 4 chars>_fshape.stl, absent file is fine (crixus.cu:647-659)
+  std::string fsname = cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0) + "_fshape.stl";
+  fsname = ini.Get("mesh", "fshape", fsname);
+  const int frc = cx_read_stl(fsname, fs_corners, fs_normals);
+  printf("Checking whether fluid geometry (%s) is available ... %s\n", fsname.c_str(), frc == CX_OK ? "[YES]" : "[NO]");
+  if (frc == CX_OK) { job.fs_corners = fs_corners.data(); job.fs_normals = fs_normals.data(); job.fs_nbe = (int64_t)(fs_normals.size() / 3); }
+  std::vector<cx_fill_spec> fills;
+  for (int n = 0;; n++) {  // crixus.cu:734-961: fill_0 is always attempted, then while fill_(n+1).option exists
+    std::ostringstream sec;
+    sec << "fill_" << n;
+    if (n > 0 && ini.Get(sec.str(), "option", "UNKNOWN") == "UNKNOWN") break;
+    cx_fill_spec f;
+    memset(&f, 0, sizeof(f));
+    const std::string opt = ini.Get(sec.str(), "option", "box");
+    f.option = opt == "geometry" ? 2 : 1;
+    printf("Option for fill #%d: %s\n", n, opt.c_str());
+    for (int d = 0; d < 3; d++) {
+      if (f.option == 1) {
+        f.lo[d] = (float)ini.GetReal(sec.str(), std::string(ax[d]) + "min", 1e9);
+        f.hi[d] = (float)ini.GetReal(sec.str(), std::string(ax[d]) + "max", -1e9);
+      } else f.seed[d] = (float)ini.GetReal(sec.str(), std::string(ax[d]) + "seed", 1e9);
+    }
+    f.dr_wall = (float)ini.GetReal(sec.str(), "dr_wall", dr);
+    fills.push_back(f);
+  }
+  job.fills = fills.data(); job.nfills = (int32_t)fills.size();
+
+  cx_ctx *ctx = nullptr;
+  rc = cx_create((int)std::max(0L, ini.GetInteger("system", "gpu-id", 0)), &ctx);
+  if (rc != CX_OK) { printf("No usable CUDA device (crixus_b200 has no CPU path)\n"); return rc; }
+  rc = cx_preprocess_host(ctx, &job);
+  if (rc != CX_OK) { printf("Preprocessing failed: %d %s\n", rc, cx_last_error(ctx)); cx_destroy(ctx); return rc; }
+  printf("\n\tInformation:\n\tNumber of vertices:         \t%lld\n\tNumber of boundary elements:\t%lld\n\n", (long long)job.nvert, (long long)job.nbe);
+  printf("\tNormals information:\n\tPositive (n.(0,0,1)) minimum z: %g (%g)\n\tNegative (n.(0,0,1)) minimum z: %g (%g)\n\n", job.zstat[0],
+         job.zstat[2], job.zstat[1], job.zstat[3]);
+  printf("Creation of %lld fluid particles completed. [OK]\n", (long long)job.nfluid);
+  printf("Timing: weld %.3f s, upload %.3f s, GPU %.3f s, download %.3f s\n", job.t_weld_s, job.t_h2d_s, job.t_gpu_s, job.t_d2h_s);
+  const std::vector<CxOutBuf> buf = cx_assemble(job, job.nfluid);
+  const std::string fmt = ini.Get("output", "format", "vtu");
+  std::string outname = ini.Get("output", "name", cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0));
+  if (fmt == "h5sph") {
+    outname = "0." + outname + ".h5sph";
+    rc = cx_write_h5sph(buf, outname);
+  } else {
+    outname += ".vtu";
+    rc = cx_write_vtu(buf, outname);
+  }
+  printf("Writing output to file %s ... %s\n", outname.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
+  cx_job_free(&job);
+  cx_destroy(ctx);
+  return rc;
+}
+
+}  // extern "C"

@@ -7,27 +7,32 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "../../../include/crixus_b200.h"
+#include "internal.h"
 
 namespace {
 double now_s()
 {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-struct DevBuf {
+// bump allocation out of one arena block (256-byte aligned sub-buffers)
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
+};
+struct Buf {
+  size_t off = 0;
   void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess ? 0 : -1; }
   template <class T> T *as() { return (T *)p; }
 };
 #define RC(call) do { int rc__ = (call); if (rc__ != CX_OK) return rc__; } while (0)
 #define CU(call) do { if ((call) != cudaSuccess) return CX_CUDA_ERROR; } while (0)
 }  // namespace
 
+// The result arrays live in a pinned arena owned by the context (valid until the next cx_preprocess_host on the same
+// context or cx_destroy), so there is nothing to release here; the pointers are cleared.
 extern "C" void cx_job_free(cx_job *job)
 {
   if (!job) return;
-  free(job->pos); free(job->norm); free(job->ep); free(job->surf); free(job->vol); free(job->cell_idx); free(job->fpos);
   job->pos = job->norm = job->surf = job->vol = nullptr;
   job->ep = job->cell_idx = nullptr;
   job->fpos = nullptr;
@@ -39,17 +44,14 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   if (!job->corners && !(job->welded_pos && job->welded_ep && job->welded_nvert > 0)) return CX_WRONG_INPUT;
   const int64_t nbe = job->nbe;
   const float dr = job->dr;
+  cudaStream_t st = (cudaStream_t)cx_get_stream(ctx);
   double t0 = now_s();
   float bbmin[3] = {1e10f, 1e10f, 1e10f}, bbmax[3] = {-1e10f, -1e10f, -1e10f};
-  std::vector<float> h_pos_own, h_norm((size_t)4 * nbe);
-  std::vector<int32_t> h_ep_own;
-  const float *h_pos_p;
-  const int32_t *h_ep_p;
+  std::vector<float> verts;
+  std::vector<int32_t> ids;
   int64_t nvert;
   if (job->welded_pos) {  // the mesh as crixus_main holds it right before the upload (crixus.cu:225-245)
     nvert = job->welded_nvert;
-    h_pos_p = job->welded_pos;
-    h_ep_p = job->welded_ep;
     for (int k = 0; k < 3; k++) { bbmin[k] = job->bbmin[k]; bbmax[k] = job->bbmax[k]; }
   } else {
     // bounding box over all raw corners (crixus.cu:185-208)
@@ -60,50 +62,78 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
         bbmax[k] = bbmax[k] < x ? x : bbmax[k];
       }
     // weld (crixus.cu:214)
-    std::vector<float> verts((size_t)9 * nbe);
-    std::vector<int32_t> ids((size_t)3 * nbe);
+    verts.resize((size_t)9 * nbe);
+    ids.resize((size_t)3 * nbe);
     nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
-    h_pos_own.resize((size_t)4 * nvert);
-    h_ep_own.resize((size_t)4 * nbe);
-    for (int64_t v = 0; v < nvert; v++) {
-      h_pos_own[4 * v] = verts[3 * v]; h_pos_own[4 * v + 1] = verts[3 * v + 1]; h_pos_own[4 * v + 2] = verts[3 * v + 2]; h_pos_own[4 * v + 3] = 0.f;
-    }
-    for (int64_t i = 0; i < nbe; i++) {
-      for (int k = 0; k < 3; k++) h_ep_own[4 * i + k] = ids[3 * i + k];
-      h_ep_own[4 * i + 3] = 0;
-    }
-    h_pos_p = h_pos_own.data();
-    h_ep_p = h_ep_own.data();
   }
   job->nvert = nvert;
-  for (int64_t i = 0; i < nbe; i++) {
-    for (int k = 0; k < 3; k++) h_norm[4 * i + k] = job->normals[3 * i + k];
-    h_norm[4 * i + 3] = 0.f;
-  }
   job->t_weld_s = now_s() - t0;
 
   cx_params p;
   cx_params_domain(&p, dr, bbmin, bbmax);  // crixus.cu:262-283
   const int64_t ncell = p.gridn[3];
+  // the lattice of the fills is known up front (crixus.cu:463-467, 698-722 depend on the bounding box only)
+  cx_params pf = p;
+  for (int k = 0; k < 3; k++) pf.per[k] = job->periodic[k] ? 1 : 0;
+  cx_params_fill_eps(&pf);
+  cx_params_container(&pf, job->use_container, job->cmin, job->cmax);
+  cx_fill_dims(&pf, job->dimg);
+  const int64_t G = job->dimg[0] * job->dimg[1] * job->dimg[2];
+  const int64_t nwords = (G + 31) / 32;
+  const int64_t fsn = (job->fs_nbe > 0 && job->fs_corners && job->fs_normals) ? job->fs_nbe : 0;
 
+  // ---- one device block and one pinned host block, carved into the working set (no per-call cudaMalloc)
   t0 = now_s();
-  DevBuf pre_pos, pos, pre_norm, norm, pre_ep, ep, pre_surf, surf, cell_idx, trisize, vol, newlink;
-  if (pre_pos.alloc(16 * (size_t)(nvert + nbe)) || pos.alloc(16 * (size_t)(nvert + nbe)) || pre_norm.alloc(16 * (size_t)nbe) ||
-      norm.alloc(16 * (size_t)nbe) || pre_ep.alloc(16 * (size_t)nbe) || ep.alloc(16 * (size_t)nbe) || pre_surf.alloc(4 * (size_t)nbe) ||
-      surf.alloc(4 * (size_t)nbe) || cell_idx.alloc(4 * (size_t)(ncell + 1)) || trisize.alloc(4 * (size_t)nvert) ||
-      vol.alloc(4 * (size_t)nvert) || newlink.alloc(4 * (size_t)nvert))
-    return CX_CUDA_ERROR;
-  CU(cudaMemcpy(pre_pos.p, h_pos_p, 16 * (size_t)nvert, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(pre_norm.p, h_norm.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(pre_ep.p, h_ep_p, 16 * (size_t)nbe, cudaMemcpyHostToDevice));
-  CU(cudaMemset(trisize.p, 0, 4 * (size_t)nvert));
-  CU(cudaMemset(vol.p, 0, 4 * (size_t)nvert));
+  Bump db, hb;
+  Buf pre_pos, pos, pre_norm, norm, pre_ep, ep, pre_surf, surf, cell_idx, trisize, vol, newlink, norm3, fpos, fnorm, fep, fposv;
+  pre_pos.off = db.take(16 * (size_t)(nvert + nbe)); pos.off = db.take(16 * (size_t)(nvert + nbe));
+  pre_norm.off = db.take(16 * (size_t)nbe); norm.off = db.take(16 * (size_t)nbe);
+  pre_ep.off = db.take(16 * (size_t)nbe); ep.off = db.take(16 * (size_t)nbe);
+  pre_surf.off = db.take(4 * (size_t)nbe); surf.off = db.take(4 * (size_t)nbe);
+  cell_idx.off = db.take(4 * (size_t)(ncell + 1)); trisize.off = db.take(4 * (size_t)nvert);
+  vol.off = db.take(4 * (size_t)nvert); newlink.off = db.take(4 * (size_t)nvert);
+  norm3.off = db.take(12 * (size_t)nbe); fpos.off = db.take(4 * (size_t)nwords);
+  if (fsn) {
+    fnorm.off = db.take(16 * (size_t)(nbe + fsn)); fep.off = db.take(16 * (size_t)(nbe + fsn));
+    fposv.off = db.take(16 * (size_t)(nvert + 3 * fsn));
+  }
+  char *dbase = (char *)cx_internal_dev_arena(ctx, db.off + 256);
+  if (!dbase) return CX_CUDA_ERROR;
+  for (Buf *b : {&pre_pos, &pos, &pre_norm, &norm, &pre_ep, &ep, &pre_surf, &surf, &cell_idx, &trisize, &vol, &newlink, &norm3, &fpos,
+                 &fnorm, &fep, &fposv})
+    b->p = dbase + b->off;
+  const size_t o_pos = hb.take(16 * (size_t)(nvert + nbe)), o_norm = hb.take(16 * (size_t)nbe), o_ep = hb.take(16 * (size_t)nbe),
+               o_surf = hb.take(4 * (size_t)nbe), o_vol = hb.take(4 * (size_t)nvert), o_cell = hb.take(4 * (size_t)(ncell + 1)),
+               o_fpos = hb.take(4 * (size_t)nwords), o_stage_pos = hb.take(job->welded_pos ? 0 : 16 * (size_t)nvert),
+               o_stage_ep = hb.take(job->welded_pos ? 0 : 16 * (size_t)nbe), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0);
+  char *hbase = (char *)cx_internal_host_arena(ctx, hb.off + 256);
+  if (!hbase) return CX_CUDA_ERROR;
+  const float *h_pos_p = job->welded_pos;
+  const int32_t *h_ep_p = job->welded_ep;
+  if (!job->welded_pos) {  // float3 / int3 -> the float4 / int4 records of crixus.cu:225-245, staged in pinned memory
+    float *sp = (float *)(hbase + o_stage_pos);
+    int32_t *se = (int32_t *)(hbase + o_stage_ep);
+    for (int64_t v = 0; v < nvert; v++) { sp[4 * v] = verts[3 * v]; sp[4 * v + 1] = verts[3 * v + 1]; sp[4 * v + 2] = verts[3 * v + 2]; sp[4 * v + 3] = 0.f; }
+    for (int64_t i = 0; i < nbe; i++) {
+      for (int k = 0; k < 3; k++) se[4 * i + k] = ids[3 * i + k];
+      se[4 * i + 3] = 0;
+    }
+    h_pos_p = sp;
+    h_ep_p = se;
+  }
+  CU(cudaMemcpyAsync(pre_pos.p, h_pos_p, 16 * (size_t)nvert, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(norm3.p, job->normals, 12 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(pre_ep.p, h_ep_p, 16 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+  RC(cx_internal_expand3(ctx, norm3.as<float>(), pre_norm.as<float>(), nbe));
+  CU(cudaMemsetAsync(trisize.p, 0, 4 * (size_t)nvert, st));
+  CU(cudaMemsetAsync(vol.p, 0, 4 * (size_t)nvert, st));
+  CU(cudaMemsetAsync(fpos.p, 0, 4 * (size_t)nwords, st));
+  RC(cx_synchronize(ctx));
   job->t_h2d_s = now_s() - t0;
 
   t0 = now_s();
   cudaEvent_t ev[8];
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&ev[k]));
-  cudaStream_t st = (cudaStream_t)cx_get_stream(ctx);
   CU(cudaEventRecord(ev[0], st));
   if (job->swap_normals) RC(cx_swap_normals(ctx, pre_norm.as<float>(), nbe));  // crixus.cu:310-317
   RC(cx_set_bound_elem(ctx, pre_pos.as<float>(), pre_norm.as<float>(), pre_surf.as<float>(), pre_ep.as<int32_t>(), nbe, nvert, job->zstat));
@@ -113,8 +143,7 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   CU(cudaEventRecord(ev[2], st));
   for (int idim = 0; idim < 3; idim++) {  // crixus.cu:391-412
     if (!job->periodic[idim]) continue;
-    RC(cx_synchronize(ctx));
-    CU(cudaMemset(newlink.p, 0xff, 4 * (size_t)nvert));
+    CU(cudaMemsetAsync(newlink.p, 0xff, 4 * (size_t)nvert, st));
     RC(cx_find_links(ctx, &p, pos.as<float>(), nvert, newlink.as<int32_t>(), idim));
     RC(cx_periodicity_links(ctx, ep.as<int32_t>(), nbe, newlink.as<int32_t>()));
   }
@@ -129,12 +158,6 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   // ---- fluid (crixus.cu:463-467, 698-961)
   cx_params_fill_eps(&p);
   cx_params_container(&p, job->use_container, job->cmin, job->cmax);
-  cx_fill_dims(&p, job->dimg);
-  const int64_t G = job->dimg[0] * job->dimg[1] * job->dimg[2];
-  const int64_t nwords = (G + 31) / 32;
-  DevBuf fpos, fnorm, fep, fposv;
-  if (fpos.alloc(4 * (size_t)nwords)) return CX_CUDA_ERROR;
-  CU(cudaMemset(fpos.p, 0, 4 * (size_t)nwords));
   job->nfluid_counted = 0;
   bool have_fs = false;
   int64_t fnbe = nbe, cnbe = 0;
@@ -143,28 +166,24 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   for (int f = 0; f < job->nfills; f++) {
     const cx_fill_spec &fs = job->fills[f];
     if (fs.option == 2) {
-      if (!have_fs && job->fs_nbe > 0 && job->fs_corners && job->fs_normals) {  // crixus.cu:809-930
+      if (!have_fs && fsn > 0) {  // crixus.cu:809-930
         have_fs = true;
-        const int64_t fsn = job->fs_nbe;
         std::vector<float> fv((size_t)9 * fsn);
         std::vector<int32_t> fid((size_t)3 * fsn);
         const int64_t fsnvert = cx_weld_host(job->fs_corners, 3 * fsn, dr, fv.data(), fid.data());
-        std::vector<float> hp((size_t)4 * fsnvert), hn((size_t)4 * fsn);
-        std::vector<int32_t> he((size_t)4 * fsn);
+        float *hp = (float *)(hbase + o_fs), *hn = hp + 4 * (3 * fsn);
+        int32_t *he = (int32_t *)(hn + 4 * fsn);
         for (int64_t v = 0; v < fsnvert; v++) { hp[4 * v] = fv[3 * v]; hp[4 * v + 1] = fv[3 * v + 1]; hp[4 * v + 2] = fv[3 * v + 2]; hp[4 * v + 3] = 0.f; }
         for (int64_t i = 0; i < fsn; i++) {
           for (int k = 0; k < 3; k++) { hn[4 * i + k] = job->fs_normals[3 * i + k]; he[4 * i + k] = fid[3 * i + k] + (int32_t)nvert; }
           hn[4 * i + 3] = 0.f; he[4 * i + 3] = 0;
         }
-        if (fnorm.alloc(16 * (size_t)(nbe + fsn)) || fep.alloc(16 * (size_t)(nbe + fsn)) || fposv.alloc(16 * (size_t)(nvert + fsnvert)))
-          return CX_CUDA_ERROR;
-        RC(cx_synchronize(ctx));
-        CU(cudaMemcpy(fnorm.p, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice));
-        CU(cudaMemcpy(fep.p, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice));
-        CU(cudaMemcpy(fposv.p, pos.p, 16 * (size_t)nvert, cudaMemcpyDeviceToDevice));
-        CU(cudaMemcpy(fnorm.as<float>() + 4 * nbe, hn.data(), 16 * (size_t)fsn, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(fep.as<int32_t>() + 4 * nbe, he.data(), 16 * (size_t)fsn, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(fposv.as<float>() + 4 * nvert, hp.data(), 16 * (size_t)fsnvert, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(fnorm.p, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fep.p, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fposv.p, pos.p, 16 * (size_t)nvert, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(fnorm.as<float>() + 4 * nbe, hn, 16 * (size_t)fsn, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fep.as<int32_t>() + 4 * nbe, he, 16 * (size_t)fsn, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(fposv.as<float>() + 4 * nvert, hp, 16 * (size_t)fsnvert, cudaMemcpyHostToDevice, st));
         g_norm = fnorm.as<float>(); g_ep = fep.as<int32_t>(); g_pos = fposv.as<float>();
         fnbe = nbe + fsn; cnbe = fsn;
       }
@@ -192,23 +211,19 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
   job->params_fill = p;
 
-  // ---- results to the host (crixus.cu:363-365, 413, 456, 962)
+  // ---- results to the host (crixus.cu:363-365, 413, 456, 962): pinned arena, asynchronous copies, one synchronise
   t0 = now_s();
-  job->pos = (float *)malloc(16 * (size_t)(nvert + nbe));
-  job->norm = (float *)malloc(16 * (size_t)nbe);
-  job->ep = (int32_t *)malloc(16 * (size_t)nbe);
-  job->surf = (float *)malloc(4 * (size_t)nbe);
-  job->vol = (float *)malloc(4 * (size_t)nvert);
-  job->cell_idx = (int32_t *)malloc(4 * (size_t)(ncell + 1));
-  job->fpos = (uint32_t *)malloc(4 * (size_t)nwords);
-  if (!job->pos || !job->norm || !job->ep || !job->surf || !job->vol || !job->cell_idx || !job->fpos) return CX_INTERNAL_ERROR;
-  CU(cudaMemcpy(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->vol, vol.p, 4 * (size_t)nvert, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(job->fpos, fpos.p, 4 * (size_t)nwords, cudaMemcpyDeviceToHost));
+  job->pos = (float *)(hbase + o_pos); job->norm = (float *)(hbase + o_norm); job->ep = (int32_t *)(hbase + o_ep);
+  job->surf = (float *)(hbase + o_surf); job->vol = (float *)(hbase + o_vol); job->cell_idx = (int32_t *)(hbase + o_cell);
+  job->fpos = (uint32_t *)(hbase + o_fpos);
+  CU(cudaMemcpyAsync(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->vol, vol.p, 4 * (size_t)nvert, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(job->fpos, fpos.p, 4 * (size_t)nwords, cudaMemcpyDeviceToHost, st));
+  RC(cx_synchronize(ctx));
   int64_t pop = 0;
   for (int64_t w = 0; w < nwords; w++) pop += __builtin_popcount(job->fpos[w]);
   job->nfluid = pop;

@@ -145,7 +145,8 @@ typedef struct cx_job {
   int32_t use_container; float cmin[3], cmax[3];
   const float *fs_corners; const float *fs_normals; int64_t fs_nbe; /* optional fshape STL */
   const cx_fill_spec *fills; int32_t nfills;
-  /* outputs (malloc'd by the library, released by cx_job_free) */
+  /* outputs: they live in a pinned host arena owned by the context and stay valid until the next cx_preprocess_host on
+   * the same context (or cx_destroy); cx_job_free only clears the pointers */
   int64_t nvert, nfluid, nfluid_counted; /* popcount vs. the reference's running count (App. B-2 of SURVEY.md) */
   float *pos;  float *norm;  int32_t *ep;  float *surf;  float *vol;  int32_t *cell_idx; uint32_t *fpos;
   int64_t dimg[3];
@@ -161,6 +162,31 @@ void cx_job_free(cx_job *job);
 /* host weld, src/crixus.cpp:343-455 (outcome-exact restatement).  out_verts: room for 3*ncorner floats,
  * out_ids: ncorner ints.  Returns the number of welded vertices. */
 int64_t cx_weld_host(const float *corners, int64_t ncorner, float dr, float *out_verts, int32_t *out_ids);
+
+/* ---- the reference's process surface (front end), usable without a GPU except cx_run_ini -------------------- */
+/* .ini reader with the rules of the reference's vendored inih (src/ini/ini.c:60-167, src/ini/cpp/INIReader.cpp:15-75).
+ * cx_ini_open returns INIReader::ParseError(): 0 ok, -1 cannot open, >0 first bad line; *out is valid in every case. */
+typedef struct cx_ini cx_ini;
+int cx_ini_open(const char *filename, cx_ini **out);
+void cx_ini_close(cx_ini *ini);
+int cx_ini_get(const cx_ini *ini, const char *section, const char *name, const char *def, char *buf, int buflen); /* -> length */
+long cx_ini_get_integer(const cx_ini *ini, const char *section, const char *name, long def);
+double cx_ini_get_real(const cx_ini *ini, const char *section, const char *name, double def);
+int cx_ini_get_boolean(const cx_ini *ini, const char *section, const char *name, int def);
+
+/* binary STL reader, src/crixus.cu:126-221: CX_OK / CX_FILE_NOT_OPEN / CX_STL_NOT_BINARY / CX_READ_ERROR.
+ * corners: nbe*9 floats, normals: nbe*3 floats, both malloc'ed (release with cx_free). */
+int cx_stl_read(const char *filename, float **corners, float **normals, int64_t *nbe);
+void cx_free(void *p);
+
+/* particle records, src/crixus.cu:973-1097: 64-byte OutBuf records (src/crixus.h:33-36) -- fluid particles in bit order,
+ * alive vertices in index order, segments in sorted order.  Returns the record count (records may be NULL to size). */
+int64_t cx_assemble_records(const cx_job *job, int64_t nfluid_for_indices, void *records, int64_t capacity);
+int cx_write_vtu_records(const void *records, int64_t n, const char *filename);   /* vtk_output, src/crixus.cpp:62-259 */
+int cx_write_h5sph_records(const void *records, int64_t n, const char *filename); /* hdf5_output, src/crixus.cpp:12-60 */
+
+/* what `Crixus file.ini` does (crixus_main, src/crixus.cu:31-1237, hot path only): ini -> STL -> GPU -> output file */
+int cx_run_ini(const char *ini_path);
 
 #ifdef __cplusplus
 }

@@ -149,4 +149,25 @@ int refshim_weld(const float *corners, int ntri, float dr, float *out_verts, uns
   return (int)new_verts.size();
 }
 
+// the reference's own VTU writer (src/crixus.cpp:62-259) on an array of 64-byte OutBuf records
+int refshim_vtk_output(void *records, int len, const char *filename) { return vtk_output((OutBuf *)records, len, filename); }
+
+// the reference's own .ini reader (vendored inih + INIReader, src/ini/)
+void *refshim_ini_open(const char *filename, int *parse_error)
+{
+  INIReader *r = new INIReader(filename);
+  *parse_error = r->ParseError();
+  return r;
+}
+void refshim_ini_close(void *r) { delete (INIReader *)r; }
+int refshim_ini_get(void *r, const char *section, const char *name, const char *def, char *buf, int buflen)
+{
+  const std::string v = ((INIReader *)r)->Get(section, name, def);
+  snprintf(buf, (size_t)buflen, "%s", v.c_str());
+  return (int)v.size();
+}
+long refshim_ini_get_integer(void *r, const char *section, const char *name, long def) { return ((INIReader *)r)->GetInteger(section, name, def); }
+double refshim_ini_get_real(void *r, const char *section, const char *name, double def) { return ((INIReader *)r)->GetReal(section, name, def); }
+int refshim_ini_get_boolean(void *r, const char *section, const char *name, int def) { return ((INIReader *)r)->GetBoolean(section, name, def != 0) ? 1 : 0; }
+
 }  // extern "C"

@@ -1,0 +1,215 @@
+"""The reference's process surface, CPU only: .ini reader against the reference's own INIReader (vendored inih, linked
+into oracle/_ref/libcrixus_refshim.so), VTU writer byte-for-byte against the reference's own vtk_output
+(src/crixus.cpp:62-259), the hand-written HDF5 writer against an independent parser (tests/h5mini.py; there is no
+libhdf5 in this image), binary-STL reader edge cases (src/crixus.cu:126-221)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from crixus_b200 import api, meshgen as mg
+
+REC = np.dtype([(n, "<f4") for n in ("x", "y", "z", "nx", "ny", "nz", "vol", "surf")] +
+               [(n, "<i4") for n in ("kpar", "kfluid", "kent", "kparmob", "iref", "ep1", "ep2", "ep3")])
+H5_NAMES = ["Coords_0", "Coords_1", "Coords_2", "Normal_0", "Normal_1", "Normal_2", "Volume", "Surface", "ParticleType",
+            "FluidType", "KENT", "MovingBoundary", "AbsoluteIndex", "VertexParticle1", "VertexParticle2", "VertexParticle3"]
+
+
+def _records(n, seed=1):
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, dtype=REC)
+    for k in ("x", "y", "z", "nx", "ny", "nz", "vol", "surf"):
+        r[k] = rng.standard_normal(n).astype(np.float32)
+    r["kpar"] = rng.integers(1, 4, n)
+    r["kfluid"] = 1
+    r["iref"] = np.arange(n)
+    for k in ("ep1", "ep2", "ep3"):
+        r[k] = rng.integers(0, max(n, 1), n)
+    return r
+
+
+INI_TRICKY = """; comment line
+# another comment
+[mesh]
+stlfile = tank.stl   ; inline comment after whitespace
+dr=0.018333
+swap_normals : yes
+zeroOpen=OFF
+name with spaces = a;b ;c
+long = first
+  second line
+  third ; x
+[Periodicity]
+X=TRUE
+y = 0
+z = maybe
+[fill_0]
+option=geometry
+xseed = 1e-1
+yseed = .5abc
+zseed = abc
+[output]
+format=h5sph
+name = run 7
+[system]
+gpu-id = 0x1
+bad line without separator
+[unterminated
+k=v
+"""
+
+
+def _write(tmp_path, text, name="c.ini"):
+    p = tmp_path / name
+    p.write_bytes(text.encode())
+    return str(p)
+
+
+def test_ini_reader_equals_reference(tmp_path, cxlib, refshim):
+    R = refshim.R
+    R.refshim_ini_open.restype = C.c_void_p
+    R.refshim_ini_open.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    R.refshim_ini_close.argtypes = [C.c_void_p]
+    R.refshim_ini_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    R.refshim_ini_get_integer.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_long]
+    R.refshim_ini_get_integer.restype = C.c_long
+    R.refshim_ini_get_real.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]
+    R.refshim_ini_get_real.restype = C.c_double
+    R.refshim_ini_get_boolean.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    long_line = "[s]\nk=" + "x" * 300 + "\nafter=1\n"
+    bom = "﻿[mesh]\ndr=1\n"
+    shipped = open("/root/reference/resources/spheric2.ini").read() if os.path.exists("/root/reference/resources/spheric2.ini") else ""
+    for idx, text in enumerate([INI_TRICKY, long_line, bom, "", "[a]\nb=1\nb=2\n", shipped]):
+        path = _write(tmp_path, text, "c%d.ini" % idx).encode()
+        err = C.c_int(0)
+        r = R.refshim_ini_open(path, C.byref(err))
+        h = api.VP()
+        mine = cxlib.cx_ini_open(path, C.byref(h))
+        assert mine == err.value, (idx, mine, err.value)
+        keys = [("mesh", "stlfile"), ("MESH", "DR"), ("mesh", "swap_normals"), ("mesh", "zeroopen"), ("mesh", "name with spaces"),
+                ("mesh", "long"), ("periodicity", "x"), ("periodicity", "y"), ("periodicity", "z"), ("fill_0", "option"),
+                ("fill_0", "xseed"), ("fill_0", "yseed"), ("fill_0", "zseed"), ("output", "format"), ("output", "name"),
+                ("system", "gpu-id"), ("unterminated", "k"), ("system", "k"), ("s", "k"), ("s", "after"), ("a", "b"), ("nope", "nope"),
+                ("fluid_container", "use"), ("fluid_container", "xmax"), ("fill_1", "dr_wall"), ("fill_1", "option")]
+        for sec, key in keys:
+            a, b = C.create_string_buffer(1024), C.create_string_buffer(1024)
+            la = R.refshim_ini_get(r, sec.encode(), key.encode(), b"DEF", a, 1024)
+            lb = cxlib.cx_ini_get(h, sec.encode(), key.encode(), b"DEF", b, 1024)
+            assert (la, a.value) == (lb, b.value), (idx, sec, key, a.value, b.value)
+            assert R.refshim_ini_get_integer(r, sec.encode(), key.encode(), -7) == cxlib.cx_ini_get_integer(h, sec.encode(), key.encode(), -7)
+            ra, rb = R.refshim_ini_get_real(r, sec.encode(), key.encode(), -7.5), cxlib.cx_ini_get_real(h, sec.encode(), key.encode(), -7.5)
+            assert ra == rb, (sec, key, ra, rb)
+            for d in (0, 1):
+                assert R.refshim_ini_get_boolean(r, sec.encode(), key.encode(), d) == cxlib.cx_ini_get_boolean(h, sec.encode(), key.encode(), d)
+        R.refshim_ini_close(r)
+        cxlib.cx_ini_close(h)
+    # a file that does not exist: ParseError -1 on both sides
+    err = C.c_int(0)
+    r = R.refshim_ini_open(b"/nonexistent.ini", C.byref(err))
+    h = api.VP()
+    assert cxlib.cx_ini_open(b"/nonexistent.ini", C.byref(h)) == err.value == -1
+    R.refshim_ini_close(r)
+    cxlib.cx_ini_close(h)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 1000])
+def test_vtu_writer_is_byte_identical_to_reference(n, tmp_path, cxlib, refshim):
+    rec = _records(n)
+    a, b = str(tmp_path / "a.vtu"), str(tmp_path / "b.vtu")
+    refshim.R.refshim_vtk_output.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    assert refshim.R.refshim_vtk_output(rec.ctypes.data, n, a.encode()) == 0
+    assert cxlib.cx_write_vtu_records(rec.ctypes.data, n, b.encode()) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+    if n:
+        from vtu import read_vtu
+        d = read_vtu(b)
+        assert d["n"] == n
+        np.testing.assert_array_equal(d["Volume"], rec["vol"])
+        np.testing.assert_array_equal(d["Points"], np.stack([rec["x"], rec["y"], rec["z"]], 1).astype(np.float64))
+        np.testing.assert_array_equal(d["VertexParticle"], np.stack([rec["ep1"], rec["ep2"], rec["ep3"]], 1).astype(np.uint32))
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 4096])
+def test_h5sph_writer_against_independent_parser(n, tmp_path, cxlib):
+    import h5mini
+    rec = _records(n, seed=3)
+    path = str(tmp_path / "0.case.h5sph")
+    assert cxlib.cx_write_h5sph_records(rec.ctypes.data, n, path.encode()) == 0
+    arr, info = h5mini.read_compound_dataset(path, "Compound")       # dataset name: src/crixus.h:21
+    assert info["dims"] == [n] and info["record"] == 64
+    # member names, order, offsets and types of src/crixus.cpp:21-38
+    assert [m[0] for m in info["members"]] == H5_NAMES
+    assert [m[1] for m in info["members"]] == [4 * i for i in range(16)]
+    assert [m[2] for m in info["members"]] == [np.dtype("<f4")] * 8 + [np.dtype("<i4")] * 8
+    assert arr.tobytes() == rec.tobytes()
+    assert info["data_address"] % 8 == 0
+
+
+def test_h5mini_rejects_corruption(tmp_path, cxlib):
+    import h5mini
+    rec = _records(3)
+    path = str(tmp_path / "x.h5sph")
+    cxlib.cx_write_h5sph_records(rec.ctypes.data, 3, path.encode())
+    raw = bytearray(open(path, "rb").read())
+    raw[0] ^= 0xff
+    open(path, "wb").write(raw)
+    with pytest.raises(h5mini.H5Error):
+        h5mini.read_compound_dataset(path)
+    raw[0] ^= 0xff
+    open(path, "wb").write(raw[:-10])          # truncated data: end-of-file address no longer matches
+    with pytest.raises(h5mini.H5Error):
+        h5mini.read_compound_dataset(path)
+
+
+def _stl_read(cxlib, path):
+    c, n, nbe = C.POINTER(C.c_float)(), C.POINTER(C.c_float)(), api.I64(0)
+    rc = cxlib.cx_stl_read(path.encode(), C.byref(c), C.byref(n), C.byref(nbe))
+    out = None
+    if rc == 0:
+        k = int(nbe.value)
+        out = (np.ctypeslib.as_array(c, shape=(k, 3, 3)).copy() if k else np.zeros((0, 3, 3), np.float32),
+               np.ctypeslib.as_array(n, shape=(k, 3)).copy() if k else np.zeros((0, 3), np.float32))
+    cxlib.cx_free(c)
+    cxlib.cx_free(n)
+    return rc, out
+
+
+def test_stl_reader_edge_cases(tmp_path, cxlib):
+    v, t, n = mg.plate(3, 0.1)
+    good = str(tmp_path / "good.stl")
+    mg.write_stl(good, v[t], n)
+    rc, out = _stl_read(cxlib, good)
+    assert rc == 0
+    np.testing.assert_array_equal(out[0], v[t])
+    np.testing.assert_array_equal(out[1], n)
+    # the shipped free-surface fixture of the reference (4 triangles, VTK header)
+    shipped = "/root/reference/resources/spheric2_fshape.stl"
+    if os.path.exists(shipped):
+        rc, out = _stl_read(cxlib, shipped)
+        assert rc == 0 and out[0].shape == (4, 3, 3)
+        assert abs(float(out[0][..., 2].max()) - 0.551) < 1e-6
+    raw = open(good, "rb").read()
+    # ASCII STL ("solid" in the first five bytes) is refused: crixus.cu:137-153 -> STL_NOT_BINARY
+    asc = str(tmp_path / "ascii.stl")
+    open(asc, "wb").write(b"solid x" + raw[7:])
+    assert _stl_read(cxlib, asc)[0] == -1
+    # record count larger than the file content: crixus.cu:218-221 -> READ_ERROR
+    trunc = str(tmp_path / "trunc.stl")
+    open(trunc, "wb").write(raw[:-30])
+    assert _stl_read(cxlib, trunc)[0] == -5
+    # missing file -> FILE_NOT_OPEN; empty mesh (0 facets) reads fine
+    assert _stl_read(cxlib, str(tmp_path / "missing.stl"))[0] == -3
+    empty = str(tmp_path / "empty.stl")
+    open(empty, "wb").write(b"\0" * 80 + struct.pack("<I", 0))
+    rc, out = _stl_read(cxlib, empty)
+    assert rc == 0 and out[0].shape[0] == 0
+
+
+def test_run_ini_without_config_or_gpu(cxlib, tmp_path, capfd):
+    assert cxlib.cx_run_ini(None) == -2                               # NO_FILE, crixus.cu:57-65
+    assert cxlib.cx_run_ini(str(tmp_path / "nope.ini").encode()) == -4  # CANT_READ_CONFIG, crixus.cu:67-71
+    ini = _write(tmp_path, "[mesh]\nstlfile=%s\ndr=0.1\n" % (tmp_path / "missing.stl"))
+    assert cxlib.cx_run_ini(ini.encode()) == -3                        # FILE_NOT_OPEN
+    capfd.readouterr()
