@@ -101,7 +101,8 @@ def _run_cli(tmp_path, name, fmt):
     ini = str(tmp_path / (name + ".ini"))
     write_ini(ini, c, stl, fsp)
     if fmt != "vtu":
-        open(ini, "w").write(open(ini).read().replace("format=vtu", "format=" + fmt))
+        text = open(ini).read().replace("format=vtu", "format=" + fmt)
+        open(ini, "w").write(text)
     exe = os.path.join(ROOT, "crixus_b200", "bin", "crixus")
     r = subprocess.run([exe, ini], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
