@@ -121,23 +121,30 @@ struct FillArgs {
   unsigned long long *changed;  // newly set cells
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
+  const float4 *rec;            // per-segment invariants of checkCollision (k_seg_prep), 8 x float4 per segment
+  float rrej;                   // plane distance beyond which a well-formed triangle cannot matter
   float drw2;                   // dr_wall*dr_wall
   double one_eps;               // 1.0 + eps (double, crixus_d.cu:774)
 };
 
 // ---- the reference's directed test, warp-cooperative -------------------------------------------------------------
-// checkTriangleCollision, crixus_d.cu:753-799
-__device__ __forceinline__ bool tri_collision(const FillArgs &A, f3 s, f3 dir, f3 n, f3 v0, f3 v1, f3 v2)
+// Everything in checkCollision that depends on the triangle alone is hoisted into a per-segment record (k_seg_prep):
+// the same operations in the same order, so the results are bit-identical to evaluating them per (cell, segment) pair.
+//   R0 = (n, wf)   R1 = (v0, uu)   R2 = (v1, uv)   R3 = (v2, vv)   R4 = (segpos, D)   R5..R7 = (nr[0..2], -)
+#define FREC 8
+
+// checkTriangleCollision, crixus_d.cu:753-799 (u, v, uu, uv, vv, D from the record)
+__device__ __forceinline__ bool tri_collision(const FillArgs &A, f3 s, f3 dir, f3 n, f3 v0, f3 u, f3 v, float uu, float uv, float vv,
+                                              float D)
 {
   const float eps = A.p.eps;
-  const f3 u = sub3(v1, v0), v = sub3(v2, v0), w0 = sub3(s, v0);
+  const f3 w0 = sub3(s, v0);
   const float a = -dot3_r3(n, w0), b = dot3_r3(n, dir);
   if (fabsf(b) < eps) return fabsf(a) < eps;
   const float r = __fdiv_rn(a, b);
   if (r < -eps || (double)r > A.one_eps) return false;
   const f3 w = mk3(fsub(ffma(r, dir.x, s.x), v0.x), fsub(ffma(r, dir.y, s.y), v0.y), fsub(ffma(r, dir.z, s.z), v0.z));
-  const float uu = dot3_r3(u, u), uv = dot3_r3(u, v), vv = dot3_r3(v, v), wu = dot3_r3(w, u), wv = dot3_r3(w, v);
-  const float D = det_r2(uv, uv, uu, vv);
+  const float wu = dot3_r3(w, u), wv = dot3_r3(w, v);
   const float t1 = __fdiv_rn(det_r2(uv, wv, vv, wu), D);
   if (t1 < -eps || (double)t1 > A.one_eps) return false;
   const float t2 = __fdiv_rn(det_r2(uv, wu, uu, wv), D);
@@ -145,39 +152,24 @@ __device__ __forceinline__ bool tri_collision(const FillArgs &A, f3 s, f3 dir, f
   return true;
 }
 
-// squared distance from s to triangle (v0,v1,v2) exactly as crixus_d.cu:859-939 computes it
-__device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0, f3 v1, f3 v2)
+// squared distance from s to triangle (v0,v1,v2) exactly as crixus_d.cu:859-939 computes it (segpos, nr from the record)
+__device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0, f3 v1, f3 v2, f3 segpos, f3 nr0, f3 nr1, f3 nr2)
 {
   const float eps = A.p.eps;
-  const f3 segpos = mk3(__fdiv_rn(fadd(fadd(v0.x, v1.x), v2.x), 3.0f), __fdiv_rn(fadd(fadd(v0.y, v1.y), v2.y), 3.0f),
-                        __fdiv_rn(fadd(fadd(v0.z, v1.z), v2.z), 3.0f));
-  f3 nr[3];
-  const f3 vv[3] = {v0, v1, v2};
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const f3 a = vv[k], b = vv[(k + 1) % 3];
-    f3 ed = sub3(b, a);
-    const float len = __fsqrt_rn(dot3_r3(ed, ed));
-    ed = mk3(__fdiv_rn(ed.x, len), __fdiv_rn(ed.y, len), __fdiv_rn(ed.z, len));
-    const f3 sv = sub3(segpos, a);
-    const float d = dot3_r3(ed, sv);
-    nr[k] = mk3(ffma(-ed.x, d, sv.x), ffma(-ed.y, d, sv.y), ffma(-ed.z, d, sv.z));
-  }
   const f3 sm = sub3(s, segpos);
   const float pd = dot3_r3(sm, n);
   const f3 pp = mk3(ffma(-n.x, pd, sm.x), ffma(-n.y, pd, sm.y), ffma(-n.z, pd, sm.z));
-  float o[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) o[k] = dot3_r3(sub3(add3(pp, segpos), vv[k]), nr[k]);
+  const f3 q = add3(pp, segpos);
+  const float o0 = dot3_r3(sub3(q, v0), nr0), o1 = dot3_r3(sub3(q, v1), nr1), o2 = dot3_r3(sub3(q, v2), nr2);
   f3 t;
-  if (o[0] > -eps && o[1] > -eps && o[2] > -eps) t = sub3(pp, sm);
-  else if (o[0] < eps && o[1] < eps) t = sub3(s, v2);
-  else if (o[1] < eps && o[2] < eps) t = sub3(s, v0);
-  else if (o[2] < eps && o[0] < eps) t = sub3(s, v1);
+  if (o0 > -eps && o1 > -eps && o2 > -eps) t = sub3(pp, sm);
+  else if (o0 < eps && o1 < eps) t = sub3(s, v2);
+  else if (o1 < eps && o2 < eps) t = sub3(s, v0);
+  else if (o2 < eps && o0 < eps) t = sub3(s, v1);
   else {
     f3 x1, x2;
-    if (o[0] < eps) { x1 = v0; x2 = v1; }
-    else if (o[1] < eps) { x1 = v1; x2 = v2; }
+    if (o0 < eps) { x1 = v0; x2 = v1; }
+    else if (o1 < eps) { x1 = v1; x2 = v2; }
     else { x1 = v2; x2 = v0; }
     const f3 x21 = sub3(x2, x1), sx1 = sub3(s, x1);
     const float td = dot3_r3(x21, sx1), l2 = dot3_r3(x21, x21);
@@ -186,8 +178,59 @@ __device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0,
   return dot3_r3(t, t);
 }
 
+// one thread per segment: the triangle-only parts of crixus_d.cu:859-896 (segpos, edge normals nr) and :755-783 (uu, uv,
+// vv, D), plus the "well-formed" flag that licenses the plane-distance reject in warp_check_collision.
+__global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict__ rec)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < A.nbe; i += (int64_t)gridDim.x * blockDim.x) {
+    const f3 n = mk3(__ldg(&A.norm[i]));
+    const int4 E = __ldg(&A.ep[i]);
+    const f3 v0 = mk3(__ldg(&A.pos[E.x])), v1 = mk3(__ldg(&A.pos[E.y])), v2 = mk3(__ldg(&A.pos[E.z]));
+    const f3 segpos = mk3(__fdiv_rn(fadd(fadd(v0.x, v1.x), v2.x), 3.0f), __fdiv_rn(fadd(fadd(v0.y, v1.y), v2.y), 3.0f),
+                          __fdiv_rn(fadd(fadd(v0.z, v1.z), v2.z), 3.0f));
+    f3 nr[3];
+    const f3 vv3[3] = {v0, v1, v2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const f3 a = vv3[k], b = vv3[(k + 1) % 3];
+      f3 ed = sub3(b, a);
+      const float len = __fsqrt_rn(dot3_r3(ed, ed));
+      ed = mk3(__fdiv_rn(ed.x, len), __fdiv_rn(ed.y, len), __fdiv_rn(ed.z, len));
+      const f3 sv = sub3(segpos, a);
+      const float d = dot3_r3(ed, sv);
+      nr[k] = mk3(ffma(-ed.x, d, sv.x), ffma(-ed.y, d, sv.y), ffma(-ed.z, d, sv.z));
+    }
+    const f3 u = sub3(v1, v0), v = sub3(v2, v0);
+    const float uu = dot3_r3(u, u), uv = dot3_r3(u, v), vv = dot3_r3(v, v);
+    const float D = det_r2(uv, uv, uu, vv);
+    // well-formed: |n| = 1 within 1 %, n perpendicular to both edges within 2e-3 rad (evaluated in double).  Then for
+    // every point within the influence radius, |n.(s - v0)| is the distance to the triangle's plane within a few
+    // per cent, and no distance the reference can compute (plane, vertex or edge-line distance) is smaller.
+    const double nn = (double)n.x * n.x + (double)n.y * n.y + (double)n.z * n.z;
+    const double lu = sqrt((double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z);
+    const double lv = sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z);
+    const double nu = (double)n.x * u.x + (double)n.y * u.y + (double)n.z * u.z;
+    const double nv = (double)n.x * v.x + (double)n.y * v.y + (double)n.z * v.z;
+    const bool wf = nn > 0.98 && nn < 1.02 && lu > 0 && lv > 0 && fabs(nu) <= 2e-3 * lu && fabs(nv) <= 2e-3 * lv;
+    float4 *r = rec + i * FREC;
+    r[0] = make_float4(n.x, n.y, n.z, wf ? 1.f : 0.f);
+    r[1] = make_float4(v0.x, v0.y, v0.z, uu);
+    r[2] = make_float4(v1.x, v1.y, v1.z, uv);
+    r[3] = make_float4(v2.x, v2.y, v2.z, vv);
+    r[4] = make_float4(segpos.x, segpos.y, segpos.z, D);
+    r[5] = make_float4(nr[0].x, nr[0].y, nr[0].z, 0.f);
+    r[6] = make_float4(nr[1].x, nr[1].y, nr[1].z, 0.f);
+    r[7] = make_float4(nr[2].x, nr[2].y, nr[2].z, 0.f);
+  }
+}
+
 // checkCollision (crixus_d.cu:801-963) for cell s=(si,sj,sk) and every direction in dmask at once (bit d: 0:-x 1:+x
 // 2:-y 3:+y 4:-z 5:+z, the reference's neighbour order).  Called by a full warp; returns the directions that collide.
+//
+// Plane-distance reject (exact): for a well-formed triangle, a cell further than rrej = 1.2 max(dr_wall, dr) from the
+// triangle's plane can neither pass the distance test (every distance the reference computes is >= the plane
+// distance up to a few per cent) nor be hit by a lattice step of length dr, and the "ray in plane" rule needs
+// |n.(s-v0)| < eps.  Such pairs are skipped after two loads; everything else runs the reference's arithmetic.
 __device__ uint32_t warp_check_collision(const FillArgs &A, int si, int sj, int sk, uint32_t dmask, int lane)
 {
   const cx_params &p = A.p;
@@ -217,41 +260,62 @@ __device__ uint32_t warp_check_collision(const FillArgs &A, int si, int sj, int 
   const int gy = cell_coord(sc[1], p.dmin[1], p.griddr[1], p.gridn[1]);
   const int gz = cell_coord(sc[2], p.dmin[2], p.griddr[2], p.gridn[2]);
   uint32_t coll = 0;
-  for (int c27 = 0; c27 < 27 && coll != dmask; c27++) {
-    const int64_t c = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
-    if (c < 0) continue;
-    const int b = __ldg(&A.cell_idx[c]), e = __ldg(&A.cell_idx[c + 1]);
-    for (int base = b; base < e && coll != dmask; base += 32) {
-      const int i = base + lane;
-      uint32_t mine = 0;
-      if (i < e) {
-        const f3 n = mk3(__ldg(&A.norm[i]));
-        const int4 E = __ldg(&A.ep[i]);
-        const f3 v0 = mk3(__ldg(&A.pos[E.x])), v1 = mk3(__ldg(&A.pos[E.y])), v2 = mk3(__ldg(&A.pos[E.z]));
-        uint32_t pass = 0;
-#pragma unroll
-        for (int d = 0; d < 6; d++) {
-          if (!((dmask & ~coll) >> d & 1)) continue;
-          const int a = d >> 1;
-          const f3 t = mk3(ffma(a == 0 ? midc[d] : mids[0], 0.5f, -v0.x), ffma(a == 1 ? midc[d] : mids[1], 0.5f, -v0.y),
-                           ffma(a == 2 ? midc[d] : mids[2], 0.5f, -v0.z));
-          if (!(dot3_r3(t, t) > infl[d])) pass |= 1u << d;  // crixus_d.cu:855-857
-        }
-        if (pass) {
-          const float dist = tri_dist2(A, s, n, v0, v1, v2);
-          if (fadd(dist, eps) < A.drw2) mine = pass;  // crixus_d.cu:940
-          else {
+  // the 27 cells as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run
+  // of segments (plus, at a periodic z border, the wrapped cell as a run of its own)
+  for (int c9 = 0; c9 < 9 && coll != dmask; c9++) {
+    const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
+    for (int part = 0; part < 3 && coll != dmask; part++) {
+      int b, e;
+      if (part == 0) {
+        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
+        const int64_t c0 = nb_cell(p, cx, cy, z0);
+        if (c0 < 0) break;   // column outside the grid (not periodic): nothing in the other parts either
+        b = __ldg(&A.cell_idx[c0]); e = __ldg(&A.cell_idx[c0 + (z1 - z0) + 1]);
+      } else {
+        const int zz = part == 1 ? gz - 1 : gz + 1;
+        if (zz >= 0 && zz < p.gridn[2]) continue;   // in range: part of the run above
+        const int64_t c0 = nb_cell(p, cx, cy, zz);  // wrapped (periodic z) or -1
+        if (c0 < 0) continue;
+        b = __ldg(&A.cell_idx[c0]); e = __ldg(&A.cell_idx[c0 + 1]);
+      }
+      for (int base = b; base < e && coll != dmask; base += 32) {
+        const int i = base + lane;
+        uint32_t mine = 0;
+        if (i < e) {
+          const float4 *r = A.rec + (int64_t)i * FREC;
+          const float4 R0 = __ldg(r), R1 = __ldg(r + 1);
+          const f3 n = mk3(R0), v0 = mk3(R1);
+          const float t = (s.x - v0.x) * n.x + (s.y - v0.y) * n.y + (s.z - v0.z) * n.z;
+          if (!(R0.w != 0.f && fabsf(t) > A.rrej)) {
+            uint32_t pass = 0;
 #pragma unroll
             for (int d = 0; d < 6; d++) {
-              if (!(pass >> d & 1)) continue;
+              if (!((dmask & ~coll) >> d & 1)) continue;
               const int a = d >> 1;
-              const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
-              if (tri_collision(A, s, dir, n, v0, v1, v2)) mine |= 1u << d;
+              const f3 tt = mk3(ffma(a == 0 ? midc[d] : mids[0], 0.5f, -v0.x), ffma(a == 1 ? midc[d] : mids[1], 0.5f, -v0.y),
+                                ffma(a == 2 ? midc[d] : mids[2], 0.5f, -v0.z));
+              if (!(dot3_r3(tt, tt) > infl[d])) pass |= 1u << d;  // crixus_d.cu:855-857
+            }
+            if (pass) {
+              const float4 R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4), R5 = __ldg(r + 5), R6 = __ldg(r + 6), R7 = __ldg(r + 7);
+              const f3 v1 = mk3(R2), v2 = mk3(R3);
+              const float dist = tri_dist2(A, s, n, v0, v1, v2, mk3(R4), mk3(R5), mk3(R6), mk3(R7));
+              if (fadd(dist, eps) < A.drw2) mine = pass;  // crixus_d.cu:940
+              else {
+                const f3 u = sub3(v1, v0), v = sub3(v2, v0);
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                  if (!(pass >> d & 1)) continue;
+                  const int a = d >> 1;
+                  const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
+                  if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) mine |= 1u << d;
+                }
+              }
             }
           }
         }
+        coll |= __reduce_or_sync(0xffffffffu, mine);
       }
-      coll |= __reduce_or_sync(0xffffffffu, mine);
     }
   }
   // free-surface triangles: all of them, segment test only (crixus_d.cu:951-960)
@@ -259,15 +323,15 @@ __device__ uint32_t warp_check_collision(const FillArgs &A, int si, int sj, int 
     const int64_t i = base + lane;
     uint32_t mine = 0;
     if (i < A.nbe) {
-      const f3 n = mk3(__ldg(&A.norm[i]));
-      const int4 E = __ldg(&A.ep[i]);
-      const f3 v0 = mk3(__ldg(&A.pos[E.x])), v1 = mk3(__ldg(&A.pos[E.y])), v2 = mk3(__ldg(&A.pos[E.z]));
+      const float4 *r = A.rec + i * FREC;
+      const float4 R0 = __ldg(r), R1 = __ldg(r + 1), R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4);
+      const f3 n = mk3(R0), v0 = mk3(R1), u = sub3(mk3(R2), v0), v = sub3(mk3(R3), v0);
 #pragma unroll
       for (int d = 0; d < 6; d++) {
         if (!((dmask & ~coll) >> d & 1)) continue;
         const int a = d >> 1;
         const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
-        if (tri_collision(A, s, dir, n, v0, v1, v2)) mine |= 1u << d;
+        if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) mine |= 1u << d;
       }
     }
     coll |= __reduce_or_sync(0xffffffffu, mine);
@@ -540,7 +604,8 @@ struct FillState {
   int64_t dimg[3] = {0, 0, 0};
   int64_t nbe = 0, cnbe = 0;
   uint32_t *F = nullptr, *H = nullptr, *B = nullptr;
-  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0;
+  float4 *rec = nullptr;
+  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0;
   uint8_t *nbflag = nullptr, *act = nullptr, *tile_res = nullptr;
   int32_t *list = nullptr, *count = nullptr, *rlist = nullptr;
   FsDesc *fs = nullptr;
@@ -553,7 +618,7 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->H); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->tile_res); cudaFree(s->rlist);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->tile_res); cudaFree(s->rlist); cudaFree(s->rec);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -638,6 +703,11 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
       s->cap_ncell = p->gridn[3];
     }
+    if (nbe > s->cap_rec) {
+      cudaFree(s->rec); s->rec = nullptr; s->cap_rec = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->rec, sizeof(float4) * FREC * (size_t)nbe));
+      s->cap_rec = nbe;
+    }
     if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 4));
     if (!s->fs) CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * FS_MAX_DESC + 16));
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
@@ -660,10 +730,14 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
   A->tile_res = s->tile_res; A->rlist = s->rlist;
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
+  A->rec = s->rec;
+  A->rrej = 1.2f * fmaxf(p->dr_wall, p->dr);
   A->drw2 = p->dr_wall * p->dr_wall;
   A->one_eps = 1.0 + (double)p->eps;
   A->all_hard_d = (const int *)((const char *)s->fs + sizeof(FsDesc) * FS_MAX_DESC);
   if (fresh) {
+    k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec);
+    CX_LAUNCH_CHECK(ctx, "k_seg_prep");
     CX_CUDA(ctx, cudaMemsetAsync((void *)A->all_hard_d, 0, sizeof(int), st));
     if (s->nfs > 0) {
       k_fs_desc<<<cx_blocks(s->nfs, 128), 128, 0, st>>>(*A, s->fs, (int *)A->all_hard_d);
