@@ -116,9 +116,11 @@ struct FillArgs {
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
   int32_t *count;               // [0] = list length, [1] = cursor, [2] = resolve-list length, [3] = resolve cursor
+  unsigned long long *count64;  // work counter of the up-front resolve (one item per 32-cell word of the lattice)
   uint8_t *tile_res;            // tile already resolved (blocked planes valid)
   int32_t *rlist;               // tiles to resolve this round
   unsigned long long *changed;  // newly set cells
+  int resolved_all;             // every hard cell of the owned planes was resolved up front (no per-round resolve)
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
   const float4 *rec;            // per-segment invariants of checkCollision (k_seg_prep), 8 x float4 per segment
@@ -468,15 +470,16 @@ __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
 
 // bulk resolution of the hard cells of newly reached tiles: one warp per 32-cell word, one warp-cooperative
 // checkCollision per hard cell for all of its in-lattice directions at once
+template <bool ALL>
 __global__ void __launch_bounds__(256, 3) k_resolve_tiles(FillArgs A)
 {
   const int lane = threadIdx.x & 31;
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&A.count[3], 1);
+    long long item = 0;
+    if (lane == 0) item = ALL ? (long long)atomicAdd((unsigned long long *)A.count64, 1ull) : (long long)atomicAdd(&A.count[3], 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= A.count[2] * FT_THREADS) break;
-    const int tile = A.rlist[item / FT_THREADS], wt = item % FT_THREADS;
+    if (item >= (ALL ? A.ntiles : (long long)A.count[2]) * FT_THREADS) break;
+    const int tile = ALL ? (int)(item / FT_THREADS) : A.rlist[item / FT_THREADS], wt = (int)(item % FT_THREADS);
     const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
     const int j = tyi * FT_Y + wt % FT_Y, k = tzi * FT_Z + wt / FT_Y;
     if (j >= A.dimg[1] || k >= A.dimg[2] || k < A.k_lo || k >= A.k_hi) continue;
@@ -611,6 +614,7 @@ struct FillState {
   FsDesc *fs = nullptr;
   int nfs = 0, all_hard = 0;
   int64_t nw = 0, ntiles = 0;
+  int resolved_lo = 0, resolved_hi = 0;   // planes whose hard cells were resolved up front
 };
 
 void cx_fill_state_free(cx_ctx *ctx)
@@ -708,7 +712,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       CX_CUDA(ctx, cudaMalloc(&s->rec, sizeof(float4) * FREC * (size_t)nbe));
       s->cap_rec = nbe;
     }
-    if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 4));
+    if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 8));
     if (!s->fs) CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * FS_MAX_DESC + 16));
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
     for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
@@ -729,6 +733,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->F = s->F; A->H = s->H; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
   A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
   A->tile_res = s->tile_res; A->rlist = s->rlist;
+  A->count64 = (unsigned long long *)(s->count + 4);
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
   A->rec = s->rec;
   A->rrej = 1.2f * fmaxf(p->dr_wall, p->dr);
@@ -767,8 +772,10 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_o
       CX_LAUNCH_CHECK(ctx, "k_round_prep");
       k_build_list<<<cx_blocks(A->ntiles, 256, ctx->num_sms * 8), 256, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_build_list");
-      k_resolve_tiles<<<ctx->num_sms * 4, 256, 0, st>>>(*A);
-      CX_LAUNCH_CHECK(ctx, "k_resolve_tiles");
+      if (!A->resolved_all) {
+        k_resolve_tiles<false><<<ctx->num_sms * 4, 256, 0, st>>>(*A);
+        CX_LAUNCH_CHECK(ctx, "k_resolve_tiles");
+      }
       A->force_activate = (rounds == 0);
       k_fill_tiles<<<grid_tiles, FT_THREADS, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_fill_tiles");
@@ -816,6 +823,20 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   if (first_call) {
     k_seed<<<1, 1, 0, st>>>(A, seed);
     CX_LAUNCH_CHECK(ctx, "k_seed");
+  }
+  // Resolve every hard cell of the owned planes up front, in one balanced launch: the directed tests are pure functions
+  // of the geometry, so nothing is gained by waiting for the flood to arrive (24 small launches with tails before).
+  // CX_FILL_LAZY=1 restores the per-round resolution of newly reached tiles.
+  static const bool lazy = getenv("CX_FILL_LAZY") != nullptr;
+  if (!lazy) {
+    if (first_call) { s->resolved_lo = s->resolved_hi = 0; }
+    if (s->resolved_lo != A.k_lo || s->resolved_hi != A.k_hi) {
+      CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
+      k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
+      CX_LAUNCH_CHECK(ctx, "k_resolve_all");
+      s->resolved_lo = A.k_lo; s->resolved_hi = A.k_hi;
+    }
+    A.resolved_all = 1;
   }
   rc = fill_rounds(ctx, &A, s, rounds_host);
   if (rc != CX_OK) return rc;
