@@ -241,40 +241,58 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   }
 }
 
-// First pass: is the whole line removed by a single triangle?  (both ends beyond a voronoi/edge plane, or both ends
-// strictly inside a wall sector; exact by monotonicity).  Cheap: no per-voxel work, no searches.
+// First pass, a whole x-row of 41 z-lines at a time: which lines are removed entirely by a single triangle?
+// A line dies if both of its ends lie beyond a voronoi/edge plane or strictly inside a wall sector (exact, by
+// monotonicity along z).  Along z each plane expression takes its smaller value at a FIXED end (A if its z coefficient
+// is >= 0, else B), so "both ends pass" is one predicate of the y index l -- again a monotone step function, found by
+// the same six-evaluation search over gz[l].  One lane per (row, triangle): ~6 searches instead of 41 line tests.
 template <bool OPEN, class VVWarp>
-__device__ __forceinline__ bool line_dead(const VVArgs &a, const VVWarp &w, int tris, f3 pi, float gp0, float gp1, bool dead)
+__device__ __forceinline__ void rows_dead(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, int lane,
+                                          unsigned long long *rd)
 {
   const float eps = a.eps, neps = -a.eps;
-  const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
   const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
-  for (int j = 0; j < tris; j++) {
-    if (!__any_sync(VV_FULLWARP, !dead)) break;
-    VV_STAT(0, 1);
+  const int nitems = VV_GS * tris;
+  for (int base = 0; base < nitems; base += 32) {   // warp-uniform trip count
+    const int item = base + lane;
+    const bool act = item < nitems;
+    const int j = act ? item / VV_GS : 0, k = act ? item - j * VV_GS : 0;   // consecutive lanes: same triangle (broadcast loads)
+    const float gp0 = gzt[k];
+    const float q0 = fadd(gp0, pi.x);
     const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
                  P9 = w.plane[j][9];
-    const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
-    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
-    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
-    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
-    const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
-    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
-    const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
-    const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
-    bool all = ((sVa > eps) && (sVb > eps)) || ((sEa > eps) && (sEb > eps));
-    if (OPEN) {
-      const float tV2 = ffma(fsub(q1, P6.z), P5.w, ffma(fsub(q0, P6.y), P5.z, 0.f));
-      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
-      all = all || ((s2a > eps) && (s2b > eps));
+    int lo;
+    bool pa;
+    uint64_t dead;
+    {  // voronoi plane: s = ffma(fsub(q2, P5.y), P4.z, ffma(fsub(fadd(gy, pi.y), P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0)))
+      const float X = ffma(fsub(q0, P4.w), P4.x, 0.f), c = fsub(P4.z >= 0.f ? q2A : q2B, P5.y);
+      auto f = [&](float g) { return ffma(c, P4.z, ffma(fsub(fadd(g, pi.y), P5.x), P4.y, X)); };
+      dead = mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
     }
-    all = all || ((w0a >= eps) && (w0b >= eps) && (w1a >= neps) && (w1b >= neps) && (w2a >= neps) && (w2b >= neps));
-    dead = dead || all;
+    if (OPEN) {
+      const float X = ffma(fsub(q0, P6.y), P5.z, 0.f), c = fsub(P6.x >= 0.f ? q2A : q2B, P6.w);
+      auto f = [&](float g) { return ffma(c, P6.x, ffma(fsub(fadd(g, pi.y), P6.z), P5.w, X)); };
+      dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
+    }
+    {  // edge plane
+      const float X = ffma(fsub(gp0, P4.x), P9.y, 0.f), c = fsub(P9.w >= 0.f ? gA : gB, P4.z);
+      auto f = [&](float g) { return ffma(c, P9.w, ffma(fsub(g, P4.y), P9.z, X)); };
+      dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
+    }
+    {  // wall sector: w0 >= eps, w1 >= -eps, w2 >= -eps at both ends
+      const float X0 = ffma(gp0, P7.x, 0.f), X1 = ffma(gp0, P7.w, 0.f), X2 = ffma(gp0, P8.z, 0.f);
+      const float e0 = P7.z >= 0.f ? gA : gB, e1 = P8.y >= 0.f ? gA : gB, e2 = P9.x >= 0.f ? gA : gB;
+      auto f0 = [&](float g) { return ffma(e0, P7.z, ffma(g, P7.y, X0)); };
+      auto f1 = [&](float g) { return ffma(e1, P8.y, ffma(g, P8.x, X1)); };
+      auto f2 = [&](float g) { return ffma(e2, P9.x, ffma(g, P8.w, X2)); };
+      uint64_t m = mono_mask(gzt, f0(gA), f0(gB), f0, [&](float v) { return v >= eps; }, lo, pa);
+      m &= mono_mask(gzt, f1(gA), f1(gB), f1, [&](float v) { return v >= neps; }, lo, pa);
+      m &= mono_mask(gzt, f2(gA), f2(gB), f2, [&](float v) { return v >= neps; }, lo, pa);
+      dead |= m;
+    }
+    if (act && dead) atomicOr(&rd[k], (unsigned long long)dead);
   }
-  return dead;
 }
 
 // contribution of the voxels in `va`, in units of 2^-31
@@ -454,9 +472,11 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
   __shared__ __align__(16) float gzt[64 + 256];   // gz[0..40] for lane-dependent lookups (padded to 64), then the two
                                                   // 64-entry uint64 mask tables used by mono_mask
   __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
+  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = z-line (k, l) is dead
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
   unsigned short *wq = wqs[threadIdx.x >> 5];
+  unsigned long long *rd = rds[threadIdx.x >> 5];
   if (threadIdx.x < 64) {
     gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
     uint64_t *lmt = reinterpret_cast<uint64_t *>(gzt + 64);
@@ -636,8 +656,13 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     __syncwarp();
 
     // ---------------- the voxel cube: lanes take z-lines (k = x index, l = y index), crixus_d.cu:488-670
-    // pass 1 drops the lines that a single triangle removes entirely (typically 60-70 % of them); the survivors are
-    // compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
+    // pass 1 (rows_dead) drops the lines that a single triangle removes entirely (about half of them); the survivors
+    // are compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
+    for (int r = lane; r < 48; r += 32) rd[r] = 0ull;
+    __syncwarp();
+    if (closed) rows_dead<false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+    else rows_dead<true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+    __syncwarp();
     long long acc = 0;
     int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
     for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
@@ -645,8 +670,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       const bool valid = line < VV_LINES;
       const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
       // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
-      const float g0 = gzt[k], g1 = gzt[l];
-      const bool dead = closed ? line_dead<false, VVWarp>(a, w, tris, pi, g0, g1, !valid) : line_dead<true, VVWarp>(a, w, tris, pi, g0, g1, !valid);
+      const bool dead = !valid || ((rd[k] >> l) & 1ull);
       const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
       if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
       qn += __popc(live);

@@ -25,8 +25,7 @@ for l in lines[start + 1:]:
             cur = int(m.group(2))
         elif m.group(3) and m.group(3).endswith(cu):
             cur = int(m.group(4))
-        else:
-            cur = -1
+        # else: a helper header (common.cuh): keep the last line of the kernel's own file (nearest-preceding attribution)
         continue
     m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(.*?);", l)
     if m:
