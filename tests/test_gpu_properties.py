@@ -1,0 +1,198 @@
+"""Full-size GPU tests (BASELINE.json configs[1] = the bench workload, plus larger members of the channel and
+sphere-in-tank families) through size-independent properties, and against the CPU oracle on samples:
+
+  * calc_vert_volume: sampled vertex ranges bit-exact vs the oracle; index-range sharding invariance;
+  * geometry fill: z-slab sharding invariance (bit-exact flags and counts), idempotence (a second fill adds nothing),
+    closure (every unset cell next to a set cell is separated from it by the reference's checkCollision -- evaluated
+    by the oracle on a sample -- i.e. the result is the fixed point), popcount == running count;
+  * binning: cell_idx is an exclusive prefix ending at nbe and every segment sits in the cell of its barycentre;
+  * periodic links: every vertex of the max face is deleted and linked, no dangling index survives in ep.
+"""
+import numpy as np
+import pytest
+import torch
+
+from crixus_b200 import api, workloads as wl
+from crixus_b200.dist import ShardedHotPath, split_range
+
+pytestmark = pytest.mark.gpu
+
+
+def _op(p):
+    """the product's cx_params -> the oracle's params struct (same layout, tests/test_host.py checks it)"""
+    import ctypes as C
+    from oracle import orc
+    q = orc.Params()
+    assert C.sizeof(q) == C.sizeof(p)
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+    return q
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return api.Context(0)
+
+
+def _run(ctx, w):
+    hp = ShardedHotPath(ctx, w, 0, 1)      # one untimed pass happens in the constructor
+    torch.cuda.synchronize()
+    return hp
+
+
+def _fill_inputs(hp):
+    if hp.cnbe:
+        return hp.fnorm, hp.fep, hp.fposv, hp.nbe + hp.cnbe
+    return hp.norm, hp.ep, hp.pos, hp.nbe
+
+
+def _geometry_fill(hp):
+    f = [x for x in hp.w["fills"] if x[0] == "geometry"][0]
+    p = hp.pf.copy()
+    p.dr_wall = np.float32(f[2] if f[2] is not None else hp.w["dr"])
+    return p, api.seed_index(p, f[1])
+
+
+def _check_common(hp, oracle, nsample_ranges=4, range_len=150):
+    ctx, w, nv, nbe = hp.ctx, hp.w, hp.nv, hp.nbe
+    pos, norm, ep, surf = (t.cpu().numpy() for t in (hp.pos, hp.norm, hp.ep, hp.surf))
+    cell_idx, trisize, vol = hp.cell_idx.cpu().numpy(), hp.trisize.cpu().numpy(), hp.vol.cpu().numpy()
+    p = hp.p
+    # ---- binning
+    assert cell_idx[0] == 0 and cell_idx[-1] == nbe and np.all(np.diff(cell_idx) >= 0)
+    bary = pos[nv:, :3]
+    g = [np.clip(((bary[:, j] - np.float32(p.dmin[j])) / np.float32(p.griddr[j])).astype(np.int64), 0, p.gridn[j] - 1) for j in range(3)]
+    cell = (g[0] * p.gridn[1] + g[1]) * p.gridn[2] + g[2]
+    assert np.all(np.diff(cell) >= 0), "segments are not sorted by 3dr-cell"
+    np.testing.assert_array_equal(np.searchsorted(cell, np.arange(p.gridn[3] + 1), side="left"), cell_idx)
+    assert np.all(surf > 0) and np.isfinite(surf).all()
+    # ---- connectivity
+    alive = pos[:nv, 0] > -1e9
+    np.testing.assert_array_equal(np.bincount(ep[:, :3].ravel(), minlength=nv), trisize)
+    assert alive[ep[:, :3]].all(), "a segment refers to a deleted vertex"
+    # ---- volumes: sampled ranges vs the oracle (bit-exact), sharding invariance, sanity
+    pv = hp.p.copy()
+    for j in range(3):
+        pv.per[j] = int(w["periodic"][j])
+    rng = np.random.default_rng(7)
+    for s in sorted(rng.integers(0, max(nv - range_len, 1), nsample_ranges)):
+        a, b = int(s), int(min(s + range_len, nv))
+        ref = oracle.calc_vert_volume(_op(pv), pos, norm, ep, trisize, cell_idx, nv, nbe, w["zero_open"], a, b)
+        m = alive[a:b]
+        np.testing.assert_array_equal(vol[a:b][m].view(np.uint32), ref[a:b][m].view(np.uint32))
+    vol2 = torch.zeros_like(hp.vol)
+    for r in range(3):
+        a, b = split_range(nv, 3, r)
+        ctx.calc_vert_volume(pv, hp.pos, hp.norm, hp.ep, vol2, hp.trisize, hp.cell_idx, nv, nbe, w["zero_open"], a, b)
+    assert torch.equal(vol2[torch.from_numpy(alive).to(vol2.device)], hp.vol[torch.from_numpy(alive).to(vol2.device)])
+    dr3 = float(w["dr"]) ** 3
+    assert np.all(vol[alive] > 0) and np.all(vol[alive] <= 1.0001 * dr3)
+
+
+def _check_fill(hp, oracle, nsample=1500):
+    ctx, w = hp.ctx, hp.w
+    gn, ge, gp, fnbe = _fill_inputs(hp)
+    p, seed = _geometry_fill(hp)
+    dimg = [int(x) for x in hp.dimg]
+    G = dimg[0] * dimg[1] * dimg[2]
+    f0 = hp.fpos.clone()
+    bits = np.unpackbits(f0.cpu().numpy().view(np.uint8), bitorder="little")[:G].reshape(dimg[2], dimg[1], dimg[0]).astype(bool)
+    assert int(bits.sum()) == hp.nfluid
+    assert 0 < hp.nfluid < G
+    # ---- idempotence: filling again from the same seed adds nothing
+    f1 = f0.clone()
+    assert ctx.fill_geometry(p, f1, gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed) == 0
+    assert torch.equal(f1, f0)
+    # ---- z-slab sharding on one GPU: 3 slabs, each with its own context and bitfield copy, halo planes exchanged by hand
+    n = 3
+    ctxs = [api.Context(0) for _ in range(n)]
+    fs = [torch.zeros_like(f0) for _ in range(n)]
+    if any(x[0] == "box" for x in w["fills"]):
+        for x in w["fills"]:
+            if x[0] == "box":
+                for r in range(n):
+                    ctxs[r].fill_box(hp.pf, fs[r], x[1], x[2])
+    ks = [split_range(dimg[2], n, r) for r in range(n)]
+    total, first = sum(1 for _ in ()), True
+    P = dimg[0] * dimg[1]
+    for outer in range(10000):
+        changed = 0
+        for r in range(n):
+            changed += ctxs[r].fill_geometry_slab(p, fs[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed, ks[r][0], ks[r][1], first)
+        first = False
+        total += changed
+        if changed == 0:
+            break
+        for r in range(n - 1):          # exchange the boundary planes between slab r and r+1 (packed words, OR)
+            for src, dst, k in ((r, r + 1, ks[r][1] - 1), (r + 1, r, ks[r + 1][0])):
+                a, b = (k * P) // 32, ((k + 1) * P + 31) // 32
+                fs[dst][a:b] |= fs[src][a:b]
+    merged = torch.zeros_like(f0)
+    for r in range(n):
+        part = fs[r].cpu().numpy().view(np.uint32).copy()
+        pb = np.unpackbits(part.view(np.uint8), bitorder="little")
+        keep = np.zeros_like(pb)
+        keep[ks[r][0] * P: ks[r][1] * P] = 1
+        merged |= torch.from_numpy(np.packbits(pb & keep, bitorder="little").view(np.int32).copy()).to(merged.device)
+    assert torch.equal(merged, f0), "z-slab sharded fill differs from the unsharded fill"
+    for c in ctxs:
+        c.close()
+    # ---- closure: unset cells next to set cells must be blocked by the reference's predicate (oracle on a sample)
+    pos, norm, ep = (t.cpu().numpy() for t in (gp, gn, ge))
+    cell_idx = hp.cell_idx.cpu().numpy()
+    rng = np.random.default_rng(11)
+    pairs = []
+    for axis, (dz, dy, dx) in enumerate(((0, 0, 1), (0, 1, 0), (1, 0, 0))):
+        a = bits[: dimg[2] - dz, : dimg[1] - dy, : dimg[0] - dx]
+        b = bits[dz:, dy:, dx:]
+        for s_is_low, m in ((True, ~a & b), (False, a & ~b)):
+            idx = np.argwhere(m)
+            if idx.shape[0] == 0:
+                continue
+            for k, j, i in idx[rng.choice(idx.shape[0], min(nsample // 6, idx.shape[0]), replace=False)]:
+                lo, hi = (i, j, k), (i + dx, j + dy, k + dz)
+                pairs.append((lo, hi) if s_is_low else (hi, lo))
+    assert len(pairs) > 50
+    for s, e in pairs:
+        assert oracle.check_collision(_op(p), s, e, norm, ep, pos, fnbe, hp.cnbe, cell_idx), "cell %r should have been filled from %r" % (s, e)
+
+
+def test_config2_full_size(ctx, oracle):
+    """BASELINE.json configs[1]: 3.06e6 triangles, 328 x 219 x 131 lattice, free-surface fill."""
+    w = wl.config2(3)
+    assert w["nbe"] > 3_000_000
+    hp = _run(ctx, w)
+    _check_common(hp, oracle)
+    _check_fill(hp, oracle)
+
+
+def test_config1(ctx, oracle):
+    """BASELINE.json configs[0]: resources/spheric2.ini verbatim (box fill + geometry fill)."""
+    hp = _run(ctx, wl.config1())
+    _check_common(hp, oracle, nsample_ranges=6)
+    _check_fill(hp, oracle)
+
+
+def test_channel_family(ctx, oracle):
+    """configs[2] family (x/y periodic channel) at 6.4e5 triangles: periodic pairing at scale."""
+    w = wl.channel(n=400, dr=0.01)
+    hp = _run(ctx, w)
+    pos = hp.pos.cpu().numpy()
+    nv = hp.nv
+    deleted = pos[:nv, 0] < -1e9
+    n = 400
+    assert int(deleted.sum()) == 2 * (2 * (n + 1) - 1), "every vertex of the two max faces (floor and lid) must be linked and deleted"
+    _check_common(hp, oracle)
+    _check_fill(hp, oracle)
+
+
+def test_sphere_tank_family(ctx, oracle):
+    """configs[3] family (sphere in a closed tank): curved, non axis-aligned triangles, 100^3 lattice."""
+    w = wl.sphere_tank(side_cells=100, dr=0.01, sphere_levels=5)
+    hp = _run(ctx, w)
+    _check_common(hp, oracle)
+    _check_fill(hp, oracle)
+    # the sphere's interior is never reached
+    dimg = [int(x) for x in hp.dimg]
+    bits = np.unpackbits(hp.fpos.cpu().numpy().view(np.uint8), bitorder="little")[: dimg[0] * dimg[1] * dimg[2]].reshape(dimg[2], dimg[1], dimg[0])
+    c = [d // 2 for d in dimg]
+    assert bits[c[2], c[1], c[0]] == 0
