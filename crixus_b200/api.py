@@ -104,6 +104,8 @@ def lib():
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+        "cx_bbox_device": (C.c_int, [VP, VP, I64, F3, F3]),
+        "cx_weld_device": (C.c_int, [VP, VP, I64, C.c_float, F3, F3, VP, VP, C.POINTER(I64)]),
         "cx_ini_open": (C.c_int, [C.c_char_p, C.POINTER(VP)]),
         "cx_ini_close": (None, [VP]),
         "cx_ini_get": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
@@ -124,6 +126,10 @@ def lib():
     L._declared = sorted(sig)
     _lib = L
     return L
+
+
+def F3c():
+    return (C.c_float * 3)()
 
 
 def f3(a):
@@ -257,6 +263,18 @@ class Context:
                                               self._p(cell_idx), seed, k_begin, k_end, int(first_call), C.byref(n), C.byref(r)))
         self.last_rounds = int(r.value)
         return int(n.value)
+
+    def weld_device(self, corners, dr):
+        """corners: torch float32 (ncorner, 3) on the device -> (pos float4 (nvert,4), ep int4 (nbe,4), bbmin, bbmax)"""
+        import torch
+        n = corners.shape[0]
+        lo, hi = F3c(), F3c()
+        self._ck(self.L.cx_bbox_device(self.h, self._p(corners), n, lo, hi))
+        pos4 = torch.zeros((n, 4), dtype=torch.float32, device=corners.device)
+        ep4 = torch.zeros((n // 3, 4), dtype=torch.int32, device=corners.device)
+        nv = I64(0)
+        self._ck(self.L.cx_weld_device(self.h, self._p(corners), n, float(dr), lo, hi, self._p(pos4), self._p(ep4), C.byref(nv)))
+        return pos4[: int(nv.value)], ep4, np.array(list(lo), dtype=np.float32), np.array(list(hi), dtype=np.float32)
 
     def preprocess_host(self, job):
         self._ck(self.L.cx_preprocess_host(self.h, C.byref(job)))

@@ -2,6 +2,7 @@
 // assembly, VTU / h5sph writers, and cx_run_ini = what `Crixus file.ini` does
 // (/root/reference/src/crixus.cu:57-73,126-221,310,394,433,647-649,698-707,737-795,973-1135; src/crixus.cpp:12-289).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +11,11 @@
 #include <vector>
 #include "ini.h"
 #include "output.h"
+
+static double wall_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct cx_ini {
   CxIni ini;
@@ -97,7 +103,9 @@ int cx_run_ini(const char *ini_path)
   const float dr = (float)ini.GetReal("mesh", "dr", -1);
   printf("Opening file %s ...", stl.c_str());
   std::vector<float> corners, normals, fs_corners, fs_normals;
+  const double t_start = wall_s();
   int rc = cx_read_stl(stl, corners, normals);
+  const double t_read = wall_s() - t_start;
   if (rc != CX_OK) { printf(" [FAILED]\n"); return rc; }
   printf(" [OK]\nMesh size: %g\nRead %zu facets\n", dr, normals.size() / 3);
   if (!(dr > 0) || normals.empty()) return CX_WRONG_INPUT;
@@ -143,8 +151,10 @@ int cx_run_ini(const char *ini_path)
   job.fills = fills.data(); job.nfills = (int32_t)fills.size();
 
   cx_ctx *ctx = nullptr;
+  const double t_c0 = wall_s();
   rc = cx_create((int)std::max(0L, ini.GetInteger("system", "gpu-id", 0)), &ctx);
   if (rc != CX_OK) { printf("No usable CUDA device (crixus_b200 has no CPU path)\n"); return rc; }
+  const double t_create = wall_s() - t_c0;
   rc = cx_preprocess_host(ctx, &job);
   if (rc != CX_OK) { printf("Preprocessing failed: %d %s\n", rc, cx_last_error(ctx)); cx_destroy(ctx); return rc; }
   printf("\n\tInformation:\n\tNumber of vertices:         \t%lld\n\tNumber of boundary elements:\t%lld\n\n", (long long)job.nvert, (long long)job.nbe);
@@ -152,7 +162,9 @@ int cx_run_ini(const char *ini_path)
          job.zstat[2], job.zstat[1], job.zstat[3]);
   printf("Creation of %lld fluid particles completed. [OK]\n", (long long)job.nfluid);
   printf("Timing: weld %.3f s, upload %.3f s, GPU %.3f s, download %.3f s\n", job.t_weld_s, job.t_h2d_s, job.t_gpu_s, job.t_d2h_s);
+  const double t_a0 = wall_s();
   const std::vector<CxOutBuf> buf = cx_assemble(job, job.nfluid);
+  const double t_asm = wall_s() - t_a0;
   const std::string fmt = ini.Get("output", "format", "vtu");
   std::string outname = ini.Get("output", "name", cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0));
   if (fmt == "h5sph") {
@@ -163,6 +175,8 @@ int cx_run_ini(const char *ini_path)
     rc = cx_write_vtu(buf, outname);
   }
   printf("Writing output to file %s ... %s\n", outname.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
+  printf("Timing: read STL %.3f s, CUDA context %.3f s, assemble %.3f s, write %.3f s, total %.3f s\n", t_read, t_create, t_asm,
+         wall_s() - t_a0 - t_asm, wall_s() - t_start);
   cx_job_free(&job);
   cx_destroy(ctx);
   return rc;

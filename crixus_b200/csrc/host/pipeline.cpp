@@ -47,24 +47,21 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   cudaStream_t st = (cudaStream_t)cx_get_stream(ctx);
   double t0 = now_s();
   float bbmin[3] = {1e10f, 1e10f, 1e10f}, bbmax[3] = {-1e10f, -1e10f, -1e10f};
-  std::vector<float> verts;
-  std::vector<int32_t> ids;
   int64_t nvert;
+  float *w_corners = nullptr, *w_pos4 = nullptr;   // device temporaries of the weld (stream-ordered pool)
+  int32_t *w_ep4 = nullptr;
   if (job->welded_pos) {  // the mesh as crixus_main holds it right before the upload (crixus.cu:225-245)
     nvert = job->welded_nvert;
     for (int k = 0; k < 3; k++) { bbmin[k] = job->bbmin[k]; bbmax[k] = job->bbmax[k]; }
   } else {
-    // bounding box over all raw corners (crixus.cu:185-208)
-    for (int64_t c = 0; c < 3 * nbe; c++)
-      for (int k = 0; k < 3; k++) {
-        const float x = job->corners[3 * c + k];
-        bbmin[k] = bbmin[k] > x ? x : bbmin[k];
-        bbmax[k] = bbmax[k] < x ? x : bbmax[k];
-      }
-    // weld (crixus.cu:214)
-    verts.resize((size_t)9 * nbe);
-    ids.resize((size_t)3 * nbe);
-    nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
+    // raw corners -> device; bounding box (crixus.cu:185-208) and vertex weld (crixus.cu:214) run there
+    CU(cudaMallocAsync((void **)&w_corners, 36 * (size_t)nbe, st));
+    CU(cudaMallocAsync((void **)&w_pos4, 48 * (size_t)nbe, st));
+    CU(cudaMallocAsync((void **)&w_ep4, 16 * (size_t)nbe, st));
+    CU(cudaMemcpyAsync(w_corners, job->corners, 36 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+    RC(cx_bbox_device(ctx, w_corners, 3 * nbe, bbmin, bbmax));
+    RC(cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert));
+    CU(cudaFreeAsync(w_corners, st));
   }
   job->nvert = nvert;
   job->t_weld_s = now_s() - t0;
@@ -104,26 +101,19 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     b->p = dbase + b->off;
   const size_t o_pos = hb.take(16 * (size_t)(nvert + nbe)), o_norm = hb.take(16 * (size_t)nbe), o_ep = hb.take(16 * (size_t)nbe),
                o_surf = hb.take(4 * (size_t)nbe), o_vol = hb.take(4 * (size_t)nvert), o_cell = hb.take(4 * (size_t)(ncell + 1)),
-               o_fpos = hb.take(4 * (size_t)nwords), o_stage_pos = hb.take(job->welded_pos ? 0 : 16 * (size_t)nvert),
-               o_stage_ep = hb.take(job->welded_pos ? 0 : 16 * (size_t)nbe), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0);
+               o_fpos = hb.take(4 * (size_t)nwords), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0);
   char *hbase = (char *)cx_internal_host_arena(ctx, hb.off + 256);
   if (!hbase) return CX_CUDA_ERROR;
-  const float *h_pos_p = job->welded_pos;
-  const int32_t *h_ep_p = job->welded_ep;
-  if (!job->welded_pos) {  // float3 / int3 -> the float4 / int4 records of crixus.cu:225-245, staged in pinned memory
-    float *sp = (float *)(hbase + o_stage_pos);
-    int32_t *se = (int32_t *)(hbase + o_stage_ep);
-    for (int64_t v = 0; v < nvert; v++) { sp[4 * v] = verts[3 * v]; sp[4 * v + 1] = verts[3 * v + 1]; sp[4 * v + 2] = verts[3 * v + 2]; sp[4 * v + 3] = 0.f; }
-    for (int64_t i = 0; i < nbe; i++) {
-      for (int k = 0; k < 3; k++) se[4 * i + k] = ids[3 * i + k];
-      se[4 * i + 3] = 0;
-    }
-    h_pos_p = sp;
-    h_ep_p = se;
+  if (job->welded_pos) {
+    CU(cudaMemcpyAsync(pre_pos.p, job->welded_pos, 16 * (size_t)nvert, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pre_ep.p, job->welded_ep, 16 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+  } else {
+    CU(cudaMemcpyAsync(pre_pos.p, w_pos4, 16 * (size_t)nvert, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(pre_ep.p, w_ep4, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice, st));
+    CU(cudaFreeAsync(w_pos4, st));
+    CU(cudaFreeAsync(w_ep4, st));
   }
-  CU(cudaMemcpyAsync(pre_pos.p, h_pos_p, 16 * (size_t)nvert, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(norm3.p, job->normals, 12 * (size_t)nbe, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(pre_ep.p, h_ep_p, 16 * (size_t)nbe, cudaMemcpyHostToDevice, st));
   RC(cx_internal_expand3(ctx, norm3.as<float>(), pre_norm.as<float>(), nbe));
   CU(cudaMemsetAsync(trisize.p, 0, 4 * (size_t)nvert, st));
   CU(cudaMemsetAsync(vol.p, 0, 4 * (size_t)nvert, st));

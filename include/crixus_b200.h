@@ -159,6 +159,14 @@ typedef struct cx_job {
 int cx_preprocess_host(cx_ctx *ctx, cx_job *job);
 void cx_job_free(cx_job *job);
 
+/* bounding box of the raw STL corners (src/crixus.cu:185-208) and vertex weld (remove_duplicate_vertices,
+ * src/crixus.cpp:343-455) on the device: cell keys -> stable radix sort -> one thread per cell replays the claim loop ->
+ * prefix sum = the reference's vertex numbering.  corners_d: ncorner*3 floats in STL order (ncorner = 3*nbe);
+ * pos4_d: room for ncorner float4 (nvert are written); ep4_d: nbe int4.  Same outcome as cx_weld_host. */
+int cx_bbox_device(cx_ctx *ctx, const float *corners_d, int64_t ncorner, float bbmin[3], float bbmax[3]);
+int cx_weld_device(cx_ctx *ctx, const float *corners_d, int64_t ncorner, float dr, const float bbmin[3], const float bbmax[3],
+                   float *pos4_d, int32_t *ep4_d, int64_t *nvert_host);
+
 /* host weld, src/crixus.cpp:343-455 (outcome-exact restatement).  out_verts: room for 3*ncorner floats,
  * out_ids: ncorner ints.  Returns the number of welded vertices. */
 int64_t cx_weld_host(const float *corners, int64_t ncorner, float dr, float *out_verts, int32_t *out_ids);

@@ -154,3 +154,34 @@ def test_cli_h5sph_equals_vtu(tmp_path):
     np.testing.assert_array_equal(np.stack([h["VertexParticle1"], h["VertexParticle2"], h["VertexParticle3"]], 1).astype(np.uint32),
                                   v["VertexParticle"])
     np.testing.assert_array_equal(np.stack([h["Normal_0"], h["Normal_1"], h["Normal_2"]], 1), v["Normal"])
+
+
+@pytest.mark.parametrize("name", cases.ALL + ["weld_quirks", "config2_l2"])
+def test_device_weld_equals_host_weld(name, cuda_backend):
+    """cx_weld_device / cx_bbox_device against cx_weld_host (itself pinned to the reference's remove_duplicate_vertices in
+    tests/test_oracle.py): same vertices, same numbering, same ids."""
+    import torch
+    if name == "weld_quirks":        # near-duplicates inside a cell, across a cell border, negative coordinates (SURVEY App. B-1)
+        dr = np.float32(0.1)
+        rng = np.random.default_rng(5)
+        base = rng.uniform(-0.35, 0.35, size=(400, 3)).astype(np.float32)
+        pts = np.concatenate([base, base + np.float32(3e-7), base[:50] + np.float32(2e-6),
+                              np.array([[0.19999999, 0.05, 0.05], [0.2, 0.05, 0.05], [-0.05, 0.0, 0.0], [0.05, 0.0, 0.0]], dtype=np.float32)])
+        pts = np.concatenate([pts, pts[::-1]])[: (2 * pts.shape[0]) // 3 * 3]
+        corners = np.ascontiguousarray(pts, dtype=np.float32)
+    elif name == "config2_l2":
+        from crixus_b200 import workloads as wl
+        w = wl.spheric2_family(wl.SPHERIC2_DR / 2, 1.25, levels=2, base_dr=wl.SPHERIC2_DR)
+        corners, dr = np.ascontiguousarray(w["tris"], dtype=np.float32).reshape(-1, 3), np.float32(w["dr"])
+    else:
+        c = cases.case(name)
+        corners, dr = np.ascontiguousarray(c["tris"], dtype=np.float32).reshape(-1, 3), np.float32(c["dr"])
+    hv, hid = api.weld_host(corners, dr)
+    ctx = cuda_backend.ctx
+    pos4, ep4, lo, hi = ctx.weld_device(torch.from_numpy(corners).to(ctx.device), dr)
+    np.testing.assert_array_equal(lo, corners.min(0))
+    np.testing.assert_array_equal(hi, corners.max(0))
+    assert pos4.shape[0] == hv.shape[0]
+    np.testing.assert_array_equal(pos4.cpu().numpy()[:, :3], hv)
+    np.testing.assert_array_equal(ep4.cpu().numpy()[:, :3], hid)
+    assert not ep4[:, 3].any() and not pos4[:, 3].any()
