@@ -2,7 +2,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
+#include <string>
 
 // ---------------------------------------------------------------------------------------------- STL
 int cx_read_stl(const std::string &filename, std::vector<float> &corners, std::vector<float> &normals)
@@ -99,6 +101,7 @@ int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
 {
   FILE *fid = fopen(filename.c_str(), "w");
   if (!fid) return CX_NO_WRITE_FILE;
+  setvbuf(fid, nullptr, _IOFBF, 8 << 20);
   const int len = (int)buf.size();
   fprintf(fid, "<?xml version='1.0'?>\n");
   fprintf(fid, "<VTKFile type= 'UnstructuredGrid'  version= '0.1'  byte_order= '%s'>\n", "LittleEndian");
@@ -123,20 +126,29 @@ int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
   scalar_array(fid, "Int32", "connectivity", off); off += 4 * (size_t)len + sizeof(int);
   scalar_array(fid, "Int32", "offsets", off); off += 4 * (size_t)len + sizeof(int);
   fprintf(fid, "  <DataArray type='Int32' Name='types' format='ascii'>\n");
-  for (int i = 0; i < len; i++) fprintf(fid, "%d\t", 1);
+  {  // len times "1\t" (crixus.cpp:133-137), written in large pieces
+    std::string ones;
+    ones.reserve(2 << 16);
+    for (int i = 0; i < (1 << 16); i++) ones += "1\t";
+    for (int i = 0; i < len; i += 1 << 16) fwrite(ones.data(), 2, (size_t)std::min(1 << 16, len - i), fid);
+  }
   fprintf(fid, "\n");
   fprintf(fid, "  </DataArray>\n");
   fprintf(fid, "   </Cells>\n");
   fprintf(fid, "  </Piece>\n");
   fprintf(fid, " </UnstructuredGrid>\n");
   fprintf(fid, " <AppendedData encoding='raw'>\n_");
-  std::vector<char> tmp;
+  // appended arrays: int32 byte count, then the values; converted AoS -> SoA through a fixed 4 MB staging buffer
+  const int CH = 1 << 16;
+  std::vector<char> tmp((size_t)CH * 24);
   auto emit = [&](size_t elem, auto getter) {
     int nbytes = (int)(elem * (size_t)len);
     fwrite(&nbytes, sizeof(nbytes), 1, fid);
-    tmp.resize((size_t)nbytes);
-    for (int i = 0; i < len; i++) getter(buf[i], tmp.data() + elem * (size_t)i);
-    fwrite(tmp.data(), 1, tmp.size(), fid);
+    for (int i0 = 0; i0 < len; i0 += CH) {
+      const int m = std::min(CH, len - i0);
+      for (int i = 0; i < m; i++) getter(buf[(size_t)i0 + i], tmp.data() + elem * (size_t)i);
+      fwrite(tmp.data(), elem, (size_t)m, fid);
+    }
   };
   emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.vol, 4); });
   emit(4, [](const CxOutBuf &b, char *o) { memcpy(o, &b.surf, 4); });
@@ -148,15 +160,15 @@ int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
   emit(12, [](const CxOutBuf &b, char *o) { memcpy(o, &b.nx, 12); });
   emit(12, [](const CxOutBuf &b, char *o) { memcpy(o, &b.ep1, 12); });
   emit(24, [](const CxOutBuf &b, char *o) { double v[3] = {(double)b.x, (double)b.y, (double)b.z}; memcpy(o, v, 24); });
-  {
+  for (int pass = 0; pass < 2; pass++) {   // connectivity 0..len-1, offsets 1..len
     int nbytes = 4 * len;
-    std::vector<uint32_t> idx((size_t)len);
     fwrite(&nbytes, sizeof(nbytes), 1, fid);
-    for (int i = 0; i < len; i++) idx[i] = (uint32_t)i;
-    fwrite(idx.data(), 4, idx.size(), fid);
-    fwrite(&nbytes, sizeof(nbytes), 1, fid);
-    for (int i = 0; i < len; i++) idx[i] = (uint32_t)i + 1;
-    fwrite(idx.data(), 4, idx.size(), fid);
+    uint32_t *idx = (uint32_t *)tmp.data();
+    for (int i0 = 0; i0 < len; i0 += CH) {
+      const int m = std::min(CH, len - i0);
+      for (int i = 0; i < m; i++) idx[i] = (uint32_t)(i0 + i + pass);
+      fwrite(idx, 4, (size_t)m, fid);
+    }
   }
   fprintf(fid, " </AppendedData>\n");
   fprintf(fid, "</VTKFile>");
