@@ -101,6 +101,8 @@ def lib():
         "cx_fill_geometry": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_fill_geometry_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, I64, C.c_int, C.POINTER(I64),
                                             C.POINTER(C.c_int32)]),
+        "cx_fill_resolve_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, C.POINTER(VP), C.POINTER(I64)]),
+        "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
@@ -261,6 +263,24 @@ class Context:
         n, r = I64(0), C.c_int32(0)
         self._ck(self.L.cx_fill_geometry_slab(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
                                               self._p(cell_idx), seed, k_begin, k_end, int(first_call), C.byref(n), C.byref(r)))
+        self.last_rounds = int(r.value)
+        return int(n.value)
+
+    def fill_resolve_slab(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, k_begin, k_end):
+        """-> torch int32 view (zero-copy) of the 6 blocked bit planes owned by the context"""
+        import torch
+        ptr, n = VP(), I64(0)
+        self._ck(self.L.cx_fill_resolve_slab(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
+                                             self._p(cell_idx), k_begin, k_end, C.byref(ptr), C.byref(n)))
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i4", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def fill_propagate(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed):
+        n, r = I64(0), C.c_int32(0)
+        self._ck(self.L.cx_fill_propagate(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
+                                          self._p(cell_idx), seed, C.byref(n), C.byref(r)))
         self.last_rounds = int(r.value)
         return int(n.value)
 

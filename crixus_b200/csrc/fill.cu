@@ -863,3 +863,64 @@ extern "C" int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_
   if (seed >= dimg[0] * dimg[1] * dimg[2]) return cx_fail(ctx, CX_SEED_OUTSIDE, "fill: seed outside the lattice");
   return cx_fill_geometry_slab(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, seed, 0, dimg[2], 1, nfi_host, rounds_host);
 }
+
+// ---- multi-GPU helpers: resolve a slab, merge the blocked planes across ranks, propagate everywhere ---------------
+// The directed tests are pure functions of the geometry: each rank resolves the hard cells of its own planes
+// (the expensive part, shards perfectly), the six blocked bit planes are merged by the caller (disjoint rows: a SUM
+// all-reduce is an OR), and the cheap propagation then runs on the whole lattice on every rank -- no halo exchange and
+// no per-sweep collective.  Meant for lattices whose bit planes are small; large lattices use cx_fill_geometry_slab.
+extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                    const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
+                                    int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words)
+{
+  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
+  FillArgs A;
+  FillState *s = nullptr;
+  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 1, &A, &s);
+  if (rc != CX_OK) return rc;
+  if (k_begin < 0 || k_end > A.dimg[2] || k_begin > k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
+  cudaStream_t st = ctx->stream;
+  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  A.merge = 0;
+  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);   // cells that are already set need no test
+  CX_LAUNCH_CHECK(ctx, "k_unpack");
+  A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
+  if (k_end > k_begin) {
+    CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
+    k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
+    CX_LAUNCH_CHECK(ctx, "k_resolve_all");
+  }
+  s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
+  if (blocked_d) *blocked_d = s->B;
+  if (blocked_words) *blocked_words = 6 * A.nw;
+  return CX_OK;
+}
+
+extern "C" int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                 const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                                 int64_t *nfi_host, int32_t *rounds_host)
+{
+  if (!ctx || !p || !fpos_d) return CX_WRONG_INPUT;
+  FillArgs A;
+  FillState *s = nullptr;
+  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, &A, &s);
+  if (rc != CX_OK) return rc;
+  if (s->resolved_hi != A.dimg[2] || s->resolved_lo != 0) return cx_fail(ctx, CX_WRONG_INPUT, "fill: cx_fill_propagate without cx_fill_resolve_slab");
+  cudaStream_t st = ctx->stream;
+  CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
+  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  A.merge = 0;
+  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_unpack");
+  k_seed<<<1, 1, 0, st>>>(A, seed);
+  CX_LAUNCH_CHECK(ctx, "k_seed");
+  A.resolved_all = 1;
+  rc = fill_rounds(ctx, &A, s, rounds_host);
+  if (rc != CX_OK) return rc;
+  k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_pack");
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CX_CUDA(ctx, cudaStreamSynchronize(st));
+  if (nfi_host) *nfi_host = ctx->h_mail[24];
+  return CX_OK;
+}

@@ -20,6 +20,10 @@ import ctypes as C
 import numpy as np
 
 
+# lattices whose six blocked bit planes stay below this size use "sharded tests + replicated flood" on multi-GPU runs
+SMALL_LATTICE_BYTES = 64 << 20
+
+
 def split_range(n, world, rank):
     """contiguous index range [lo, hi) of rank; sizes differ by at most one"""
     base, rem = divmod(int(n), int(world))
@@ -272,6 +276,13 @@ class ShardedHotPath:
             seed = api.seed_index(p, f[1])
             if self.world == 1:
                 nfl += ctx.fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
+                rounds += ctx.last_rounds
+            elif 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES:
+                # small lattice: shard the directed tests by z-slab, merge the blocked planes, flood everywhere
+                import torch.distributed as dist
+                B = ctx.fill_resolve_slab(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.k0, self.k1)
+                dist.all_reduce(B)                       # rows are disjoint and zero elsewhere: SUM == OR
+                nfl += ctx.fill_propagate(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
                 rounds += ctx.last_rounds
             else:
                 import torch.distributed as dist

@@ -121,6 +121,17 @@ int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, con
                           const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                           int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host);
 
+/* Multi-GPU variant for lattices whose bit planes are small: the directed tests (pure functions of the geometry) are
+ * resolved for planes [k_begin, k_end) only; *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32,
+ * zero outside the slab) which the caller merges across ranks (rows are disjoint: SUM == OR); cx_fill_propagate then
+ * runs the flood on the whole lattice on every rank.  No halo exchange, no per-sweep collective. */
+int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                         const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
+                         int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words);
+int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                      const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                      int64_t *nfi_host, int32_t *rounds_host);
+
 /* ---- whole hot path on HOST buffers (the call the CLI / a reference maintainer would make; includes H2D/D2H) */
 typedef struct cx_fill_spec {
   int32_t option;      /* 1 = box, 2 = geometry (crixus.cu:737-741) */

@@ -134,6 +134,24 @@ def _check_fill(hp, oracle, nsample=1500):
         keep[ks[r][0] * P: ks[r][1] * P] = 1
         merged |= torch.from_numpy(np.packbits(pb & keep, bitorder="little").view(np.int32).copy()).to(merged.device)
     assert torch.equal(merged, f0), "z-slab sharded fill differs from the unsharded fill"
+    # ---- "sharded tests + replicated flood" (small-lattice multi-GPU path): every emulated rank resolves its slab, the
+    #      blocked planes are summed, each rank floods the whole lattice
+    fr = [torch.zeros_like(f0) for _ in range(n)]
+    for r in range(n):
+        for x in w["fills"]:
+            if x[0] == "box":
+                ctxs[r].fill_box(hp.pf, fr[r], x[1], x[2])
+    Bs = [ctxs[r].fill_resolve_slab(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, ks[r][0], ks[r][1]) for r in range(n)]
+    tot = Bs[0].clone()
+    for r in range(1, n):
+        tot += Bs[r]
+    for r in range(n):
+        Bs[r].copy_(tot)
+    for r in range(n):
+        before = int(np.unpackbits(fr[r].cpu().numpy().view(np.uint8)).sum())
+        got = ctxs[r].fill_propagate(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed)
+        assert torch.equal(fr[r], f0), "sharded-tests/replicated-flood result differs from the unsharded fill"
+        assert got == int(bits.sum()) - before
     for c in ctxs:
         c.close()
     # ---- closure: unset cells next to set cells must be blocked by the reference's predicate (oracle on a sample)
