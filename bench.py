@@ -10,8 +10,9 @@ triangles) at dr/4, fluid filled through the shipped free-surface shape.  Metric
 triangles/s (whole job); stage rates (vert-volume verts/s, fill cells/s, seconds) are reported beside it.
 
 `value`  : inputs (the welded mesh) already resident in HBM when the timed region starts, CUDA-event timed.
-`e2e`    : the same pass through the C-ABI call cx_preprocess_host on pinned HOST buffers: H2D of the welded mesh and
-           D2H of every result array inside the timed region.
+`e2e`    : the same pass through the C-ABI call cx_preprocess_host on pinned HOST buffers: H2D of the raw STL content
+           (corners + facet normals), bounding box + vertex weld on the device, D2H of every result array -- all
+           inside the timed region.
 `roofline`: calc_vert_volume is FP32-ALU bound: achieved = 68921*T*56 flop/vertex * verts/s against the
            FFMA peak measured in this run; the fill is reported against the measured HBM copy bandwidth.
 `cpu_baseline`: the CPU oracle (oracle/liboracle.so, all host threads) on a bounded sample of the same workload.
@@ -218,7 +219,7 @@ def main():
                          "peak_source": "FFMA micro-kernel measured in this run (cx_measure_fp32_peak); nominal 148*128*2*1.965 GHz = 74.4",
                          "flops_per_vertex": VOXELS * T * FLOP_PER_VOXEL_TRI, "mean_trisize": T,
                          "hbm_frac": (hp.vv_bytes / (hp.vv_kernel_ms * 1e-3) / 1e9) / hbm_peak},
-            "roofline_fill": {"kernel": "k_fill_tiles (+rounds)", "bound": "hbm", "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
+            "roofline_fill": {"kernel": "k_resolve_tiles + k_fill_tiles rounds (whole geometry fill)", "bound": "hbm", "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s", "frac": fill_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak,
                               "traffic": None, "peak_source": hbm_src, "bytes": fill_bytes},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
