@@ -356,19 +356,23 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
     const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    const bool gV = __any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)));
+    if (gV) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
     if (OPEN) {
       const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
       if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
     }
     const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    const bool gE = __any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)));
+    if (gE) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
     // ---- wall tetrahedron: inside = all three w >= -eps; inside and |w0| < eps -> halved, inside otherwise -> removed
     const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
     const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
     const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
     const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
-    if (__any_sync(VV_FULLWARP, live && !noneW)) {
+    const bool gW = __any_sync(VV_FULLWARP, live && !noneW);
+    VV_STAT(13, gV); VV_STAT(14, gE); VV_STAT(15, gW); VV_STAT(9, !(gV || gE || gW));
+    if (gW) {
     auto ge = [&](float v) { return !(v < neps); };
     int lo0, lo1, lo2;
     bool pa0, pa1, pa2;
@@ -398,7 +402,6 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       }
     }
     if (__any_sync(VV_FULLWARP, needLT)) {
-      VV_STAT(9, 1);
       int lo_;
       bool pa_;
       const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
@@ -754,8 +757,8 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
     unsigned long long st[16];
     cudaMemcpyFromSymbol(st, vv_stats, sizeof(st));
     fprintf(stderr, "VV_STATS verts=%lld pass1=%llu pass2=%llu searches=%llu cut_lanes=%llu exact=%llu exact_lanes=%llu alive_lines=%llu "
-            "hw_inc=%llu hve_inc=%llu lt_search=%llu cube_it=%llu cube_search=%llu batches=%llu\n", (long long)(v_end - v_begin), st[0], st[1],
-            st[2], st[3], st[4], st[5], st[6], st[7], st[8], st[9], st[10], st[11], st[12]);
+            "hw_inc=%llu hve_inc=%llu idle_it=%llu cube_it=%llu cube_search=%llu batches=%llu gV=%llu gE=%llu gW=%llu\n", (long long)(v_end - v_begin), st[0], st[1],
+            st[2], st[3], st[4], st[5], st[6], st[7], st[8], st[9], st[10], st[11], st[12], st[13], st[14], st[15]);
     memset(st, 0, sizeof(st));
     cudaMemcpyToSymbol(vv_stats, st, sizeof(st));
   }
