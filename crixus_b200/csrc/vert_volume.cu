@@ -183,12 +183,13 @@ struct TriCtx {
   int open;
 };
 // Exact per-voxel evaluation of triangle j on one line (the reference's loop body, crixus_d.cu:598-662): kill mask and
-// halving events.  Used for the lanes where the threshold shortcut cannot prove its result (a voxel within eps of a
-// voronoi/edge plane on a line that is cut by it, or an expression exactly equal to a threshold).
-__device__ __noinline__ void exact_tri(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
+// halving events.  Used for the lanes where the threshold shortcut cannot prove its result (two voxels within eps of a
+// plane on a line that is cut by it, or an expression exactly equal to a threshold).  One function per plane family,
+// because pass 2 visits the families in two separate triangle loops.
+__device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
 {
   if (!mine) return;   // called by the whole warp (keeps it converged); only the flagged lanes do the work
-  const float eps = c.eps, neps = -c.eps;
+  const float eps = c.eps;
   uint64_t k = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
@@ -204,28 +205,52 @@ __device__ __noinline__ void exact_tri(const VVArgs &a, const TriCtx &c, bool mi
     const float sE = ffma(fsub(g, c.P4.z), c.P9.w, c.tE);
     kill |= sE > eps;
     nh += fabsf(sE) < eps;
+    if (kill) k |= 1ull << m;
+    for (int r = 0; r < nh; r++) half_inc(h, 1ull << m);
+  }
+  K = k;
+}
+__device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
+{
+  if (!mine) return;
+  const float eps = c.eps, neps = -c.eps;
+  uint64_t k = 0ull;
+  for (int m = 0; m < VV_GS; m++) {
+    const float g = a.gz[m];
     const float w0 = ffma(g, c.P7.z, c.tW0), w1 = ffma(g, c.P8.y, c.tW1), w2 = ffma(g, c.P9.x, c.tW2);
     const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
     const bool hw = fabsf(w0) < eps;
-    kill |= inside && !hw;
-    nh += inside && hw;
-    if (kill) k |= 1ull << m;
-    for (int r = 0; r < nh; r++) half_inc(h, 1ull << m);
+    if (inside && !hw) k |= 1ull << m;
+    if (inside && hw) half_inc(h, 1ull << m);
   }
   K = k;
 }
 
 // kill mask {f > eps} and halving mask {|f| < eps} of a voronoi / edge plane on one line.  trig is raised when the
 // halving mask cannot be decided from the ends and the element next to the flip.
+// One search serves both questions: a lane whose line is cut by the plane looks for the flip of {f > eps}; a lane whose
+// line is not cut but whose ends disagree on {f > -eps} (e.g. the last voxel lies exactly in a plane through the face of
+// the sampling cube -- common when h is commensurate with dr/40) looks for the flip of that predicate instead.
 template <class F>
 __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig)
 {
   const float neps = -eps;
-  int lo;
-  bool pa;
-  K |= mono_mask(gzt, fa, fb, f, [&](float v) { return v > eps; }, lo, pa);
-  const bool pb = fb > eps;
-  if (pa != pb) {
+  const bool pa = fa > eps, pb = fb > eps, Aa = fa > neps, Ab = fb > neps;
+  const bool cutK = pa != pb;
+  const bool cutA = !cutK && !pa && (Aa != Ab);
+  const float th = cutK ? eps : neps;
+  const bool qa = cutK ? pa : Aa;
+  int lo = VV_GS - 1;
+  const unsigned cutm = __ballot_sync(VV_FULLWARP, cutK || cutA);
+  if (cutm) {
+    VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
+    const int s = mono_search(gzt, qa, [&](float g) { return f(g) > th; });
+    if (cutK || cutA) lo = s;
+  }
+  const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
+  const uint64_t mask = lmt[(qa ? 64 : 0) + lo + 1];     // {f > th}
+  if (cutK) {
+    K |= mask;
     // the surviving voxels next to the flip carry the largest values: the first one may lie within eps of the plane
     const int d = pa ? 1 : -1, t1 = pa ? lo + 1 : lo;
     const int t2 = min(max(t1 + d, 0), VV_GS - 1);
@@ -234,10 +259,15 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
       if (v1 == eps || (t2 != t1 && v2 > neps)) trig = true;   // exactly on the threshold / two voxels in the band
       else H = bit64(t1);
     }
+  } else if (pa) {
+    K = VV_ALL;                   // both ends beyond the plane: the whole line is removed
   } else {
-    const bool Aa = fa > neps, Ab = fb > neps, Ba = fa < eps, Bb = fb < eps;
-    if (Aa != Ab || Ba != Bb) trig = true;
-    else if (Aa && Ba) H = VV_ALL;  // the whole line lies within eps of the plane (line parallel to it)
+    // no voxel is removed (all f <= eps).  If both ends are < eps so is every voxel (monotone) and the halved voxels
+    // are {f > -eps}: the searched mask, or all / none when the ends agree.  An end exactly equal to eps: exact_tri.
+    if (fa < eps && fb < eps) {
+      if (cutA) H = mask;
+      else if (Aa) H = VV_ALL;    // the whole line lies within eps of the plane (line parallel to it)
+    } else trig = true;
   }
 }
 
@@ -301,11 +331,17 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
   const uint64_t anyh = (h[0] | h[1] | h[2] | h[3] | h[4]) & va;
   long long s = (long long)__popcll(va & ~anyh) << 31;
   if (anyh) {
-    const uint64_t big = (h[2] | h[3] | h[4]) & va;          // halved four times or more: rare, one by one
-    const uint64_t sm = va & ~big;
-    if (cmax >= 1) s += (long long)__popcll(sm & h[0] & ~h[1]) << 30;
-    if (cmax >= 2) s += (long long)__popcll(sm & ~h[0] & h[1]) << 29;
-    if (cmax >= 3) s += (long long)__popcll(sm & h[0] & h[1]) << 28;
+    const uint64_t big = (h[3] | h[4]) & va;                  // halved eight times or more: rare, one by one
+    const uint64_t lo4 = va & ~big & ~h[2], hi4 = va & ~big & h[2];
+    if (cmax >= 1) s += (long long)__popcll(lo4 & h[0] & ~h[1]) << 30;
+    if (cmax >= 2) s += (long long)__popcll(lo4 & ~h[0] & h[1]) << 29;
+    if (cmax >= 3) s += (long long)__popcll(lo4 & h[0] & h[1]) << 28;
+    if (hi4) {                                                // four to seven halvings (voxels on several planes at once)
+      if (cmax >= 4) s += (long long)__popcll(hi4 & ~h[0] & ~h[1]) << 27;
+      if (cmax >= 5) s += (long long)__popcll(hi4 & h[0] & ~h[1]) << 26;
+      if (cmax >= 6) s += (long long)__popcll(hi4 & ~h[0] & h[1]) << 25;
+      if (cmax >= 7) s += (long long)__popcll(hi4 & h[0] & h[1]) << 24;
+    }
     uint64_t r = big;
     while (r) {
       const int b = __ffsll((long long)r) - 1;
@@ -324,55 +360,73 @@ template <bool OPEN, class VVWarp>
 __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
                                                  float gp1, bool valid)
 {
-  const float thr = a.thr_cube, nthr = -a.thr_cube, eps = a.eps, neps = -a.eps;
+  const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
   const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
   const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
   uint64_t alive = valid ? VV_ALL : 0ull;
   uint64_t h[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
-  // ---------------- planes (crixus_d.cu:598-662): voronoi, (voronoi 2), wall tetrahedron, edge plane
+  // ---------------- planes (crixus_d.cu:598-662) in two triangle loops -- voronoi (+ second voronoi) and edge planes first,
+  // wall tetrahedra second.  The per-voxel result is a product over triangles and families, so the order is free; two
+  // small loop bodies instead of one large one keep the hot code inside the instruction cache (ncu: instruction-fetch
+  // stalls were a quarter of the issue interval), and lines that the voronoi planes remove never reach the wall tests.
+  // c5 = (P4.x,P4.y,P4.z) c6 = (P4.w,P5.x,P5.y) c7 = (P5.z,P5.w,P6.x) c8 = (P6.y,P6.z,P6.w)
+  // c9 = (P7.x,P7.y,P7.z) c10 = (P7.w,P8.x,P8.y) c11 = (P8.z,P8.w,P9.x) en = (P9.y,P9.z,P9.w)
   for (int j = 0; j < tris; j++) {
     if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
-    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
-                 P9 = w.plane[j][9];
-    // c5 = (P4.x,P4.y,P4.z) c6 = (P4.w,P5.x,P5.y) c7 = (P5.z,P5.w,P6.x) c8 = (P6.y,P6.z,P6.w)
-    // c9 = (P7.x,P7.y,P7.z) c10 = (P7.w,P8.x,P8.y) c11 = (P8.z,P8.w,P9.x) en = (P9.y,P9.z,P9.w)
+    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P9 = w.plane[j][9];
     const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
     float tV2 = 0.f;
     if (OPEN) tV2 = ffma(fsub(q1, P6.z), P5.w, ffma(fsub(q0, P6.y), P5.z, 0.f));
-    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
-    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
-    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
     const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
     auto fV = [&](float g) { return ffma(fsub(fadd(g, pi.z), P5.y), P4.z, tV); };
     auto fV2 = [&](float g) { return ffma(fsub(fadd(g, pi.z), P6.w), P6.x, tV2); };
     auto fE = [&](float g) { return ffma(fsub(g, P4.z), P9.w, tE); };
-    auto fW0 = [&](float g) { return ffma(g, P7.z, tW0); };
-    auto fW1 = [&](float g) { return ffma(g, P8.y, tW1); };
-    auto fW2 = [&](float g) { return ffma(g, P9.x, tW2); };
-    uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull, HW = 0ull;
+    uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull;
     bool trig = false;
     const bool live = alive != 0ull;
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
     const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    const bool gV = __any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)));
-    if (gV) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
     if (OPEN) {
       const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
       if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
     }
     const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    const bool gE = __any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)));
-    if (gE) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    trig = trig && live;
+    VV_STAT(1, 1);
+    if (__any_sync(VV_FULLWARP, trig)) {
+      VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
+      TriCtx c;
+      c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P4; c.P8 = P4; c.P9 = P9;
+      c.tV = tV; c.tV2 = tV2; c.tW0 = 0.f; c.tW1 = 0.f; c.tW2 = 0.f; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
+      exact_tri_ve(a, c, trig, K, h);
+      if (trig) { HV = 0ull; HV2 = 0ull; HE = 0ull; }
+    }
+    if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { VV_STAT(8, 1); half_inc_warp(h, HV); half_inc_warp(h, HE); }
+    if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc_warp(h, HV2);
+    alive &= ~K;
+  }
+  for (int j = 0; j < tris; j++) {
+    if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
+    const float4 P7 = w.plane[j][7], P8 = w.plane[j][8], P9 = w.plane[j][9];
+    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
+    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
+    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
+    auto fW0 = [&](float g) { return ffma(g, P7.z, tW0); };
+    auto fW1 = [&](float g) { return ffma(g, P8.y, tW1); };
+    auto fW2 = [&](float g) { return ffma(g, P9.x, tW2); };
+    const bool live = alive != 0ull;
     // ---- wall tetrahedron: inside = all three w >= -eps; inside and |w0| < eps -> halved, inside otherwise -> removed
     const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
     const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
     const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
     const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
-    const bool gW = __any_sync(VV_FULLWARP, live && !noneW);
-    VV_STAT(13, gV); VV_STAT(14, gE); VV_STAT(15, gW); VV_STAT(9, !(gV || gE || gW));
-    if (gW) {
+    if (!__any_sync(VV_FULLWARP, live && !noneW)) continue;
+    uint64_t K, HW;
+    bool trig = false;
     auto ge = [&](float v) { return !(v < neps); };
     int lo0, lo1, lo2;
     bool pa0, pa1, pa2;
@@ -407,22 +461,17 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
       if (needLT) LT = m;
     }
-    K |= inside & ~LT;
+    K = inside & ~LT;
     HW = inside & LT;
-    }
     trig = trig && live;
-    VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
-      VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
       TriCtx c;
-      c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P7; c.P8 = P8; c.P9 = P9;
-      c.tV = tV; c.tV2 = tV2; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
-      exact_tri(a, c, trig, K, h);
-      if (trig) { HV = 0ull; HV2 = 0ull; HE = 0ull; HW = 0ull; }
+      c.P4 = P7; c.P5 = P7; c.P6 = P7; c.P7 = P7; c.P8 = P8; c.P9 = P9;
+      c.tV = 0.f; c.tV2 = 0.f; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = 0.f; c.piz = pi.z; c.eps = eps; c.open = 0;
+      exact_tri_w(a, c, trig, K, h);
+      if (trig) HW = 0ull;
     }
     if (__any_sync(VV_FULLWARP, HW != 0ull)) { VV_STAT(7, 1); half_inc_warp(h, HW); }
-    if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { VV_STAT(8, 1); half_inc_warp(h, HV); half_inc_warp(h, HE); }
-    if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc_warp(h, HV2);
     alive &= ~K;
   }
   // ---------------- cubes (crixus_d.cu:531-543): a voxel is sampled if it lies in one of the two dr-cubes of some j
@@ -448,6 +497,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     VV_STAT(10, 1);
     if (__any_sync(VV_FULLWARP, !full && (alive & ~hit) != 0ull)) {
       VV_STAT(11, 1);
+      const float nthr = -thr;
       auto le = [&](float v) { return v <= thr; };
       auto ge = [&](float v) { return v >= nthr; };
       int lo_;

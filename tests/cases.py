@@ -59,6 +59,9 @@ def case(name):
         flip = (n * ctr).sum(1) > 0   # make normals point inward
         n[flip] *= -1
         c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)])
+    elif name == "cube_h05":       # h = dr/2: voronoi planes on voxel planes, edge planes through the faces of the sampling cube
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.05, inward=True)
+        c.update(dr=0.1, fills=[("geometry", (0.5, 0.5, 0.5), 0.1)])
     elif name == "spheric2_mini":  # config 1 at a coarser dr: swap_normals, container, box + geometry fill, fshape
         dr = 0.06
         v, t, n = mg.spheric2(dr=dr)
@@ -82,7 +85,7 @@ def case(name):
     return c
 
 
-ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"]
+ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "spheric2_mini", "channel", "sphere_tank"]
 
 
 def run(B, c, stages=("volume", "fill")):
