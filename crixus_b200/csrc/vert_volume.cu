@@ -13,6 +13,7 @@
 //     unrolled so gp.z comes straight from the kernel-parameter constant bank.
 //   * the result is summed in integers (weights are 2^-k) so it is independent of the order of summation.
 // Bound: FP32 ALU (non-tensor).  Algorithmic flops F = 68921 * T * 56 per vertex.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define VV_WARPS 4
@@ -231,7 +232,12 @@ __device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool 
 // One search serves both questions: a lane whose line is cut by the plane looks for the flip of {f > eps}; a lane whose
 // line is not cut but whose ends disagree on {f > -eps} (e.g. the last voxel lies exactly in a plane through the face of
 // the sampling cube -- common when h is commensurate with dr/40) looks for the flip of that predicate instead.
-template <class F>
+// WIDE (kernel-level template flag, chosen by the host from dr): the plane expressions are not normalised -- c is an
+// edge vector of length ~h -- while eps = dr/20*1e-4 and the voxel step is dr/40, so a voxel step changes f by ~h*dr/40
+// against a band of 2*eps: for dr below ~2e-3 (length units of the mesh) a cut line has two or more voxels within eps
+// of a plane as a rule, and those lanes also need the flip of {f > -eps}.  The non-WIDE kernel leaves that (then
+// rare) case to exact_tri; the extra gated search costs ~8 % when it is never needed, hence two kernels.
+template <bool WIDE, class F>
 __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig)
 {
   const float neps = -eps;
@@ -249,14 +255,16 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   }
   const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
   const uint64_t mask = lmt[(qa ? 64 : 0) + lo + 1];     // {f > th}
+  bool need2 = false;
   if (cutK) {
     K |= mask;
-    // the surviving voxels next to the flip carry the largest values: the first one may lie within eps of the plane
+    // the surviving voxels next to the flip carry the largest values: the first one(s) may lie within eps of the plane
     const int d = pa ? 1 : -1, t1 = pa ? lo + 1 : lo;
     const int t2 = min(max(t1 + d, 0), VV_GS - 1);
     const float v1 = f(gzt[t1]), v2 = f(gzt[t2]);
-    if (v1 > neps) {
-      if (v1 == eps || (t2 != t1 && v2 > neps)) trig = true;   // exactly on the threshold / two voxels in the band
+    if (v1 == eps) trig = true;                       // exactly on the threshold: exact_tri decides
+    else if (v1 > neps) {
+      if (t2 != t1 && v2 > neps) { if (WIDE) need2 = true; else trig = true; }   // two or more voxels in the band
       else H = bit64(t1);
     }
   } else if (pa) {
@@ -268,6 +276,14 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
       if (cutA) H = mask;
       else if (Aa) H = VV_ALL;    // the whole line lies within eps of the plane (line parallel to it)
     } else trig = true;
+  }
+  if (WIDE) {
+    if (__any_sync(VV_FULLWARP, need2)) {   // wide band on a cut line: the band is {f > -eps} minus the removed voxels
+      int l2;
+      bool p2;
+      const uint64_t mA = mono_mask(gzt, fa, fb, f, [&](float v) { return v > neps; }, l2, p2);
+      if (need2) H = mA & ~mask;
+    }
   }
 }
 
@@ -356,7 +372,7 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
 
 // Second pass: the weight of one surviving z-line (in units of 2^-31), every lane of the warp on a line of its own.
 // Lanes without a line (valid == false) run along with an empty line.
-template <bool OPEN, class VVWarp>
+template <bool OPEN, bool WIDE, class VVWarp>
 __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
                                                  float gp1, bool valid)
 {
@@ -388,13 +404,13 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
     const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill<WIDE>(gzt, sVa, sVb, fV, eps, K, HV, trig);
     if (OPEN) {
       const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
-      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
+      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill<WIDE>(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
     }
     const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill<WIDE>(gzt, sEa, sEb, fE, eps, K, HE, trig);
     trig = trig && live;
     VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
@@ -517,7 +533,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   return valid ? group_weight(hit & alive, h, a.cmax) : 0ll;
 }
 
-template <int TCAP, bool LIST>
+template <int TCAP, bool LIST, bool WIDE>
 __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volume(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<TCAP> VVWarp;
@@ -735,7 +751,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
         const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
         const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
         const float h0 = gzt[kk], h1 = gzt[ll];
-        acc += closed ? line_weight<false, VVWarp>(a, w, gzt, tris, pi, h0, h1, have) : line_weight<true, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
+        acc += closed ? line_weight<false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have) : line_weight<true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
         const int took = min(qn, 32);
         qh = (qh + took) & 63;
         qn -= took;
@@ -787,17 +803,23 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err, a.big_count);
   CX_LAUNCH_CHECK(ctx, "k_vv_init");
   int bps = 0;
-  CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false>, VV_WARPS * 32, 0));
+  // see plane_kill<WIDE>: below this dr several voxels of a cut line lie within eps of a plane as a rule
+  static const char *force_wide = getenv("CX_VV_WIDE");
+  const bool wide = force_wide ? (force_wide[0] == '1') : (dr < 3.0e-3f);
+  if (wide) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, true>, VV_WARPS * 32, 0));
+  else CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false>, VV_WARPS * 32, 0));
   if (bps < 1) bps = 1;
   int64_t want = (v_end - v_begin + VV_WARPS - 1) / VV_WARPS;
   int64_t grid = (int64_t)ctx->num_sms * bps;
   if (grid > want) grid = want;
-  k_vert_volume<VV_TCAP_SMALL, false><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  if (wide) k_vert_volume<VV_TCAP_SMALL, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else k_vert_volume<VV_TCAP_SMALL, false, false><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
   CX_LAUNCH_CHECK(ctx, "k_vert_volume");
   // second launch: the (rare) vertices with more than 16 triangles, work list built by the first launch
   k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, (int *)(ctx->d_mail + 19), nullptr);
   CX_LAUNCH_CHECK(ctx, "k_vv_init");
-  k_vert_volume<CX_TRIMAX, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  if (wide) k_vert_volume<CX_TRIMAX, true, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else k_vert_volume<CX_TRIMAX, true, false><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
   CX_LAUNCH_CHECK(ctx, "k_vert_volume_big");
   CX_CUDA(ctx, cudaFreeAsync(a.big_list, ctx->stream));
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 17, ctx->d_mail + 17, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -62,6 +62,19 @@ def case(name):
     elif name == "cube_h05":       # h = dr/2: voronoi planes on voxel planes, edge planes through the faces of the sampling cube
         v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.05, inward=True)
         c.update(dr=0.1, fills=[("geometry", (0.5, 0.5, 0.5), 0.1)])
+    elif name == "cube_tiny":      # dr = 2e-4: eps/(|c| dr/40) > 1, several voxels of a line lie within eps of a voronoi plane
+        dr = 2e-4
+        v, t, n = mg.box_tank((0, 0, 0), (20 * dr, 20 * dr, 20 * dr), 0.625 * dr, inward=True)
+        rng = np.random.default_rng(mg.RNG_SEED)
+        interior = ((v > 1e-9) & (v < 20 * dr - 1e-9)).sum(1) == 2
+        v = v.copy()
+        ids = np.nonzero(interior)[0]
+        ids = ids[np.lexsort((v[ids, 2], v[ids, 1], v[ids, 0]))]
+        v[ids] += rng.uniform(-0.03 * dr, 0.03 * dr, size=(ids.size, 3)).astype(np.float32)
+        n = mg.geometric_normals(v, t)
+        ctr = v[t].mean(1) - 10 * dr
+        n[(n * ctr).sum(1) > 0] *= -1
+        c.update(dr=dr, fills=[("geometry", (10 * dr, 10 * dr, 10 * dr), dr)])
     elif name == "spheric2_mini":  # config 1 at a coarser dr: swap_normals, container, box + geometry fill, fshape
         dr = 0.06
         v, t, n = mg.spheric2(dr=dr)
@@ -85,7 +98,7 @@ def case(name):
     return c
 
 
-ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "spheric2_mini", "channel", "sphere_tank"]
+ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "sphere_tank"]
 
 
 def run(B, c, stages=("volume", "fill")):

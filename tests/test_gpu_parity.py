@@ -68,3 +68,17 @@ def test_case_vs_reference_golden(name, cuda_backend):
     g = cases.run(cuda_backend, c)
     from golden_compare import compare_with_golden
     compare_with_golden(g, gold, c)
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_both_vert_volume_kernels(wide):
+    """calc_vert_volume has two kernels (plane_kill<WIDE>, chosen from dr); both must be bit-exact on every kind of mesh:
+    the fine-dr case (several voxels within eps of a plane), the commensurate case and an ordinary one."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CX_VV_WIDE=wide)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_case.py"), "cube_tiny", "cube_h05", "spheric2_mini", "plate_jitter"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
