@@ -56,7 +56,7 @@ def test_case_vs_oracle(name, oracle, cuda_backend):
     _cmp_pipeline(o, g, c)
 
 
-@pytest.mark.parametrize("name", ["plate", "cube", "spheric2_mini", "channel", "sphere_tank", "plate_jitter", "cube_jitter"])
+@pytest.mark.parametrize("name", cases.ALL)
 def test_case_vs_reference_golden(name, cuda_backend):
     """CUDA path against outputs of the reference CUDA binary itself (tests/golden/, made by make_golden.py)."""
     import os
