@@ -97,10 +97,13 @@ def lib():
         "cx_periodicity_links": (C.c_int, [VP, VP, I64, VP]),
         "cx_calc_trisize": (C.c_int, [VP, VP, VP, I64]),
         "cx_calc_vert_volume": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, I64, I64, C.c_int, I64, I64]),
+        "cx_calc_vert_volume_part": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, I64, I64, C.c_int, I64, C.c_int, C.c_int]),
         "cx_fill_box": (C.c_int, [VP, P, VP, F3, F3, C.POINTER(I64)]),
         "cx_fill_geometry": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_fill_geometry_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, I64, C.c_int, C.POINTER(I64),
                                             C.POINTER(C.c_int32)]),
+        "cx_fill_set_max_rounds": (C.c_int, [VP, C.c_int]),
+        "cx_fill_unfinished": (C.c_int, [VP]),
         "cx_fill_resolve_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, C.POINTER(VP), C.POINTER(I64)]),
         "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
@@ -247,6 +250,10 @@ class Context:
                                             self._p(trisize), self._p(cell_idx), nvert, nbe, int(zero_open), v_begin,
                                             nvert if v_end is None else v_end))
 
+    def calc_vert_volume_part(self, p, pos, norm, ep, vol, trisize, cell_idx, nvert, nbe, zero_open, chunk, nparts, part):
+        self._ck(self.L.cx_calc_vert_volume_part(self.h, C.byref(p), self._p(pos), self._p(norm), self._p(ep), self._p(vol),
+                                                 self._p(trisize), self._p(cell_idx), nvert, nbe, int(zero_open), int(chunk), int(nparts), int(part)))
+
     def fill_box(self, p, fpos, lo, hi):
         n = I64(0)
         self._ck(self.L.cx_fill_box(self.h, C.byref(p), self._p(fpos), f3(lo), f3(hi), C.byref(n)))
@@ -265,6 +272,12 @@ class Context:
                                               self._p(cell_idx), seed, k_begin, k_end, int(first_call), C.byref(n), C.byref(r)))
         self.last_rounds = int(r.value)
         return int(n.value)
+
+    def fill_set_max_rounds(self, n):
+        self._ck(self.L.cx_fill_set_max_rounds(self.h, int(n)))
+
+    def fill_unfinished(self):
+        return int(self.L.cx_fill_unfinished(self.h))
 
     def fill_resolve_slab(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, k_begin, k_end):
         """-> torch int32 view (zero-copy) of the 6 blocked bit planes owned by the context"""

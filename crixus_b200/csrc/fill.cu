@@ -784,7 +784,9 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_o
     }
     CX_CUDA(ctx, cudaMemcpyAsync(hcount, A->count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CX_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->fill_unfinished = 0;
     if (hcount[0] == 0) break;  // the last round of the batch found no active tile
+    if (ctx->fill_max_rounds > 0 && rounds >= ctx->fill_max_rounds) { ctx->fill_unfinished = 1; break; }   // caller exchanges halos first
     if (rounds > 4000000) return cx_fail(ctx, CX_INTERNAL_ERROR, "fill: round limit");
   }
   (void)s;
@@ -816,7 +818,8 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
   cudaStream_t st = ctx->stream;
   CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
-  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  // a previous call that stopped at the round limit left its pending tile activations in the first half of s->act
+  if (first_call || !ctx->fill_unfinished) CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
   A.merge = first_call ? 0 : 1;
   k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_unpack");
@@ -924,3 +927,13 @@ extern "C" int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos
   if (nfi_host) *nfi_host = ctx->h_mail[24];
   return CX_OK;
 }
+
+// multi-GPU pipelining: bound the number of propagation rounds of one cx_fill_geometry_slab call (0 = until converged),
+// and ask whether the last call stopped at that bound with active tiles left
+extern "C" int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds)
+{
+  if (!ctx || max_rounds < 0) return CX_WRONG_INPUT;
+  ctx->fill_max_rounds = max_rounds;
+  return CX_OK;
+}
+extern "C" int cx_fill_unfinished(cx_ctx *ctx) { return ctx ? ctx->fill_unfinished : 0; }

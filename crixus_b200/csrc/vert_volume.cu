@@ -34,6 +34,8 @@ struct VVArgs {
   const int32_t *trisize;
   const int32_t *cell_idx;
   int64_t v_begin, v_end;
+  int64_t chunk, nown;       // interleaved sharding: this call owns chunks part, part+nparts, ... of `chunk` vertices;
+  int nparts, part;          // nown = number of owned vertices in [v_begin, v_end)
   int zero_open;
   float thr_cube;  // largest float <= dr/2.+eps (double), so |sp| <= thr_cube  <=>  (double)|sp| <= dr/2.+eps
   float eps;
@@ -565,8 +567,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       if ((int64_t)widx >= (int64_t)*a.big_count) break;
       i = a.big_list[widx];
     } else {
-      i = a.v_begin + (int64_t)widx;
-      if (i >= a.v_end) break;
+      if ((int64_t)widx >= a.nown) break;
+      const int64_t q = (int64_t)widx / a.chunk;
+      i = a.v_begin + (q * a.nparts + a.part) * a.chunk + ((int64_t)widx - q * a.chunk);
     }
     __syncwarp();
 
@@ -769,9 +772,32 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
 
 __global__ void k_vv_init(unsigned long long *work, int *err, int *big_count) { *work = 0ull; *err = 0; if (big_count) *big_count = 0; }
 
+static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                            float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                            int zero_open, int64_t v_begin, int64_t v_end, int64_t chunk, int nparts, int part);
+
 extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
                                    float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
                                    int zero_open, int64_t v_begin, int64_t v_end)
+{
+  return vert_volume_impl(ctx, p, pos_d, norm_d, ep_d, vol_d, trisize_d, cell_idx_d, nvert, nbe, zero_open, v_begin, v_end,
+                          v_end > v_begin ? v_end - v_begin : 1, 1, 0);
+}
+
+// Interleaved sharding for multi-GPU runs: the vertices are cut into chunks of `chunk`; this call computes chunks
+// part, part + nparts, part + 2 nparts, ...  (the cost per vertex varies along the mesh, contiguous ranges balance badly).
+// Only the owned entries of vol_d are written.
+extern "C" int cx_calc_vert_volume_part(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                                        float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                                        int zero_open, int64_t chunk, int nparts, int part)
+{
+  if (chunk <= 0 || nparts <= 0 || part < 0 || part >= nparts) return CX_WRONG_INPUT;
+  return vert_volume_impl(ctx, p, pos_d, norm_d, ep_d, vol_d, trisize_d, cell_idx_d, nvert, nbe, zero_open, 0, nvert, chunk, nparts, part);
+}
+
+static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                            float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                            int zero_open, int64_t v_begin, int64_t v_end, int64_t chunk, int nparts, int part)
 {
   if (!ctx || !p || !pos_d || !norm_d || !ep_d || !vol_d || !trisize_d || !cell_idx_d) return CX_WRONG_INPUT;
   if (v_begin < 0 || v_end > nvert || v_begin > v_end) return CX_WRONG_INPUT;
@@ -782,6 +808,15 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   a.pos = (const float4 *)pos_d; a.norm = (const float4 *)norm_d; a.ep = (const int4 *)ep_d;
   a.vol = vol_d; a.trisize = trisize_d; a.cell_idx = cell_idx_d;
   a.v_begin = v_begin; a.v_end = v_end; a.zero_open = zero_open;
+  a.chunk = chunk; a.nparts = nparts; a.part = part;
+  {
+    const int64_t n = v_end - v_begin, period = chunk * nparts;
+    const int64_t full = n / period, rem = n - full * period;
+    int64_t tail = rem - (int64_t)part * chunk;
+    tail = tail < 0 ? 0 : (tail > chunk ? chunk : tail);
+    a.nown = full * chunk + tail;
+  }
+  if (a.nown == 0) return CX_OK;
   const float dr = p->dr, eps = p->eps;
   const float gdr = (float)(dr / 2.0 / (float)CX_GRES);               // crixus_d.cu:281
   for (int m = 0; m < VV_GS; m++) a.gz[m] = ((float)m - (float)(VV_GS - 1) / 2) * gdr;  // :493-495
@@ -799,7 +834,7 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   a.work = (unsigned long long *)(ctx->d_mail + 16);
   a.err = (int *)(ctx->d_mail + 17);
   a.big_count = (int *)(ctx->d_mail + 18);
-  CX_CUDA(ctx, cudaMallocAsync(&a.big_list, sizeof(int) * (size_t)(v_end - v_begin), ctx->stream));
+  CX_CUDA(ctx, cudaMallocAsync(&a.big_list, sizeof(int) * (size_t)a.nown, ctx->stream));
   k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err, a.big_count);
   CX_LAUNCH_CHECK(ctx, "k_vv_init");
   int bps = 0;
@@ -809,7 +844,7 @@ extern "C" int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float 
   if (wide) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, true>, VV_WARPS * 32, 0));
   else CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false>, VV_WARPS * 32, 0));
   if (bps < 1) bps = 1;
-  int64_t want = (v_end - v_begin + VV_WARPS - 1) / VV_WARPS;
+  int64_t want = (a.nown + VV_WARPS - 1) / VV_WARPS;
   int64_t grid = (int64_t)ctx->num_sms * bps;
   if (grid > want) grid = want;
   if (wide) k_vert_volume<VV_TCAP_SMALL, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);

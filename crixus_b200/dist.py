@@ -20,6 +20,9 @@ import ctypes as C
 import numpy as np
 
 
+FILL_ROUNDS_PER_EXCHANGE = 8   # z-slab fill: propagation rounds between two halo exchanges (one tile layer per round)
+VV_CHUNK = 1024     # vertices per chunk of the interleaved calc_vert_volume sharding
+
 # lattices whose six blocked bit planes stay below this size use "sharded tests + replicated flood" on multi-GPU runs
 SMALL_LATTICE_BYTES = 64 << 20
 
@@ -82,13 +85,15 @@ def distributed_fill(slab_fill, fpos, dimg, seed, rank, world, dist):
     k0, k1 = split_range(int(dimg[2]), world, rank)
     total, it = 0, 0
     while True:
-        n = slab_fill(fpos, seed, k0, k1, it == 0) if k1 > k0 else 0
-        t = torch.tensor([n], dtype=torch.int64, device=fpos.device)
+        r = slab_fill(fpos, seed, k0, k1, it == 0) if k1 > k0 else 0
+        n, unfinished = r if isinstance(r, tuple) else (r, 0)     # unfinished: stopped at its round limit with work left
+        t = torch.tensor([n, unfinished], dtype=torch.int64, device=fpos.device)
         if world > 1:
             dist.all_reduce(t)
         it += 1
-        total += int(t.item())
-        if int(t.item()) == 0 or world == 1:
+        tn, tu = (int(x) for x in t.tolist())
+        total += tn
+        if (tn == 0 and tu == 0) or world == 1:
             break
         exchange_halos(fpos, dimg, k0, k1, rank, world, dist, None)
     return total, it
@@ -175,7 +180,11 @@ class ShardedHotPath:
             self.fnorm, self.fep = z4(nbe + self.cnbe), z4(nbe + self.cnbe, torch.int32)
         self.v0, self.v1 = 0, nv
         self.k0, self.k1 = split_range(int(self.dimg[2]), world, rank)
-        self.parallelism = "1 GPU" if world == 1 else "vert-volume: %d vertex ranges + all-gather; fill: %d z-slabs + halo exchange; cheap stages replicated" % (world, world)
+        small = 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES
+        self.parallelism = "1 GPU" if world == 1 else (
+            "vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; fill: %s; cheap stages and device weld replicated"
+            % (VV_CHUNK, world, ("directed tests sharded in %d z-slabs, blocked planes all-reduced, flood replicated" % world) if small else
+               ("%d z-slabs, halo exchange every %d rounds" % (world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
         # one untimed pass to learn trisize (vertex-range balancing) and the S27 statistic for the byte count
@@ -184,19 +193,17 @@ class ShardedHotPath:
         alive = self.pos[:nv, 0].cpu().numpy() > -1e9
         self.nalive = int(alive.sum())
         self.mean_trisize = float(ts[alive].mean())
-        if world > 1:
-            self._sizes = [split_weighted(ts, world, r) for r in range(world)]
-            self.v0, self.v1 = self._sizes[rank]
-        self.local_verts = int(alive[self.v0:self.v1].sum())
+        own = ((np.arange(nv) // VV_CHUNK) % world) == rank
+        self.local_verts = int((alive & own).sum())
         cnt = np.diff(self.cell_idx.cpu().numpy()).reshape(self.p.gridn[0], self.p.gridn[1], self.p.gridn[2]).astype(np.int64)
         pad = np.pad(cnt, 1)
         s27 = sum(pad[1 + a:pad.shape[0] - 1 + a, 1 + b:pad.shape[1] - 1 + b, 1 + c:pad.shape[2] - 1 + c]
                   for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1))
-        vpos = w["pos"][self.v0:self.v1, :3]
+        vpos = w["pos"][own, :3]
         g = [np.clip(((vpos[:, j] - np.float32(self.p.dmin[j])) / np.float32(self.p.griddr[j])).astype(np.int64), 0, self.p.gridn[j] - 1)
              for j in range(3)]
         S27 = s27[g[0], g[1], g[2]].astype(np.float64)
-        self.vv_bytes = float((240.0 + 32.0 * S27 + 48.0 * ts[self.v0:self.v1]).sum())   # SURVEY.md §8d bytes / vertex
+        self.vv_bytes = float((240.0 + 32.0 * S27 + 48.0 * ts[own]).sum())   # SURVEY.md §8d bytes / vertex
         self.vv_kernel_ms = 1.0
 
     # ---- one pass
@@ -232,28 +239,22 @@ class ShardedHotPath:
         self.trisize.zero_()
         ctx.calc_trisize(self.ep, self.trisize, nbe)
         mark()
-        ctx.calc_vert_volume(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"],
-                             self.v0, self.v1)
-        if self.world > 1 and self._sizes is not None:
-            self._allgather_vol()
+        if self.world == 1:
+            ctx.calc_vert_volume(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"], 0, nv)
+        else:
+            # interleaved chunks: the cost per vertex varies along the mesh (walls, corners, curved parts), contiguous
+            # ranges balance badly.  Every rank fills its own chunks of a zeroed array; SUM all-reduce = gather.
+            import torch.distributed as dist
+            self.vol.zero_()
+            ctx.calc_vert_volume_part(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"],
+                                      VV_CHUNK, self.world, self.rank)
+            dist.all_reduce(self.vol)
         mark()
         self._fill()
         mark()
         if timed:
             self.events.append(ev)
         return np.zeros(len(self.STAGES))
-
-    def _allgather_vol(self):
-        import torch.distributed as dist
-        torch = self.torch
-        sizes = self._sizes
-        mx = max(b - a for a, b in sizes)
-        buf = torch.zeros(mx, dtype=torch.float32, device=self.vol.device)
-        buf[: self.v1 - self.v0] = self.vol[self.v0:self.v1]
-        out = torch.empty(mx * self.world, dtype=torch.float32, device=self.vol.device)
-        dist.all_gather_into_tensor(out, buf)
-        for r, (a, b) in enumerate(sizes):
-            self.vol[a:b] = out[r * mx: r * mx + (b - a)]
 
     def _fill(self):
         ctx, w, nv, nbe = self.ctx, self.w, self.nv, self.nbe
@@ -290,9 +291,13 @@ class ShardedHotPath:
                 def slab(fpos, seed_, k0, k1, first):
                     n = ctx.fill_geometry_slab(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed_, k0, k1, first)
                     self._rounds += ctx.last_rounds
-                    return n
+                    return n, ctx.fill_unfinished()
                 self._rounds = 0
+                # exchange boundary planes every FILL_ROUNDS_PER_EXCHANGE rounds: the flood front crosses the slabs while
+                # it is moving, instead of one slab converging after the other
+                ctx.fill_set_max_rounds(FILL_ROUNDS_PER_EXCHANGE)
                 n, its = distributed_fill(slab, self.fpos, self.dimg, seed, self.rank, self.world, dist)
+                ctx.fill_set_max_rounds(0)
                 gather_slabs(self.fpos, self.dimg, self.rank, self.world, dist)
                 nfl += n
                 rounds += self._rounds

@@ -102,6 +102,12 @@ int cx_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, con
                         float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
                         int zero_open, int64_t v_begin, int64_t v_end);
 
+/* interleaved sharding of calc_vert_volume for multi-GPU runs: vertices are cut into chunks of `chunk`, this call
+ * computes chunks part, part+nparts, ... and writes only those entries of vol_d (the others are left untouched) */
+int cx_calc_vert_volume_part(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                             float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                             int zero_open, int64_t chunk, int nparts, int part);
+
 /* fill_fluid, crixus_d.cu:680-744 (box).  *nfi_host = cells in the box (counted even when already set). */
 int cx_fill_box(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float lo[3], const float hi[3],
                 int64_t *nfi_host);
@@ -120,6 +126,12 @@ int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const fl
 int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                           const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                           int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host);
+
+/* Pipelining of the z-slab fill: bound the propagation rounds of one cx_fill_geometry_slab call (0 = run until the slab
+ * is converged) so that boundary planes are exchanged while the flood front is still moving; cx_fill_unfinished tells
+ * whether the last call stopped at the bound with active tiles left (the caller must then call again). */
+int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds);
+int cx_fill_unfinished(cx_ctx *ctx);
 
 /* Multi-GPU variant for lattices whose bit planes are small: the directed tests (pure functions of the geometry) are
  * resolved for planes [k_begin, k_end) only; *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32,

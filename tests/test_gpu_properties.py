@@ -83,7 +83,17 @@ def _check_common(hp, oracle, nsample_ranges=4, range_len=150):
     for r in range(3):
         a, b = split_range(nv, 3, r)
         ctx.calc_vert_volume(pv, hp.pos, hp.norm, hp.ep, vol2, hp.trisize, hp.cell_idx, nv, nbe, w["zero_open"], a, b)
-    assert torch.equal(vol2[torch.from_numpy(alive).to(vol2.device)], hp.vol[torch.from_numpy(alive).to(vol2.device)])
+    al = torch.from_numpy(alive).to(vol2.device)
+    assert torch.equal(vol2[al], hp.vol[al])
+    # interleaved chunks (the multi-GPU sharding): 3 parts into zeroed arrays, summed
+    tot = torch.zeros_like(hp.vol)
+    for r in range(3):
+        part = torch.zeros_like(hp.vol)
+        ctx.calc_vert_volume_part(pv, hp.pos, hp.norm, hp.ep, part, hp.trisize, hp.cell_idx, nv, nbe, w["zero_open"], 1000, 3, r)
+        own = ((torch.arange(nv, device=part.device) // 1000) % 3) == r
+        assert not part[~own].any(), "a part wrote outside its chunks"
+        tot += part
+    assert torch.equal(tot[al], hp.vol[al])
     dr3 = float(w["dr"]) ** 3
     assert np.all(vol[alive] > 0) and np.all(vol[alive] <= 1.0001 * dr3)
 
@@ -114,18 +124,23 @@ def _check_fill(hp, oracle, nsample=1500):
     ks = [split_range(dimg[2], n, r) for r in range(n)]
     total, first = sum(1 for _ in ()), True
     P = dimg[0] * dimg[1]
-    for outer in range(10000):
-        changed = 0
+    for c in ctxs:
+        c.fill_set_max_rounds(4)        # the pipelined form: at most 4 rounds per call, halo exchange in between
+    for outer in range(100000):
+        changed, unfinished = 0, 0
         for r in range(n):
             changed += ctxs[r].fill_geometry_slab(p, fs[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed, ks[r][0], ks[r][1], first)
+            unfinished += ctxs[r].fill_unfinished()
         first = False
         total += changed
-        if changed == 0:
+        if changed == 0 and unfinished == 0:
             break
         for r in range(n - 1):          # exchange the boundary planes between slab r and r+1 (packed words, OR)
             for src, dst, k in ((r, r + 1, ks[r][1] - 1), (r + 1, r, ks[r + 1][0])):
                 a, b = (k * P) // 32, ((k + 1) * P + 31) // 32
                 fs[dst][a:b] |= fs[src][a:b]
+    for c in ctxs:
+        c.fill_set_max_rounds(0)
     merged = torch.zeros_like(f0)
     for r in range(n):
         part = fs[r].cpu().numpy().view(np.uint32).copy()

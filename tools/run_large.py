@@ -55,13 +55,18 @@ def build(kind, size):
 
 def main():
     kind, size = sys.argv[1], int(sys.argv[2])
-    out = {"config": kind, "size": size}
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:      # launched by torch.distributed.run: one process per GPU, every rank holds the (replicated) mesh
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = {"config": kind, "size": size, "n_gpus": world}
     t0 = time.time()
     v, t, n, w = build(kind, size)
     out["mesh_gen_s"] = time.time() - t0
     nbe = t.shape[0]
     corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
-    ctx = api.Context(0)
+    ctx = api.Context(local)
     dev = ctx.device
     # ---- device weld (timed twice: first call grows the scratch arena)
     dc = torch.from_numpy(corners).to(dev)
@@ -80,20 +85,28 @@ def main():
     del dc, pos4, ep4, corners
     torch.cuda.empty_cache()
     # ---- hot path, device resident
-    hp = ShardedHotPath(ctx, w, 0, 1)
+    hp = ShardedHotPath(ctx, w, rank, world)
     torch.cuda.synchronize()
     steps = 2
+    if world > 1:
+        dist.barrier()
     for _ in range(steps):
         hp.step(timed=True)
     torch.cuda.synchronize()
-    ms = hp.collect_stage_ms() / steps
+    ms = hp.collect_stage_ms() / steps          # max over ranks
     dimg = [int(x) for x in hp.dimg]
     G = dimg[0] * dimg[1] * dimg[2]
     out.update(stage_ms={k: float(x) for k, x in zip(hp.STAGES, ms)}, lattice=dimg, lattice_cells=G, nfluid=int(hp.nfluid),
                fill_rounds=int(hp.fill_rounds), alive_vertices=int(hp.nalive), pass_ms=float(ms.sum()),
                triangles_per_s=nbe / (ms.sum() * 1e-3), verts_per_s=hp.nalive / (ms[hp.STAGES.index("vert_volume")] * 1e-3),
                fill_cells_per_s=G / (ms[hp.STAGES.index("fill")] * 1e-3), hbm_gb_in_use=torch.cuda.memory_allocated() / 1e9)
-    print(json.dumps(out), flush=True)
+    out["parallelism"] = hp.parallelism
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if rank != 0:       # the checks below run on rank 0 (every rank holds the gathered volumes and the merged bitfield)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # ---- properties
     O = orc.Oracle()
     pos, norm, ep = hp.pos.cpu().numpy(), hp.norm.cpu().numpy(), hp.ep.cpu().numpy()
@@ -126,7 +139,7 @@ def main():
     seed = api.seed_index(p, f[1])
     f1 = hp.fpos.clone()
     assert ctx.fill_geometry(p, f1, hp.norm, hp.ep, hp.pos, nbe, 0, hp.cell_idx, seed) == 0 and torch.equal(f1, hp.fpos)
-    out["fill_idempotent"] = True
+    out["fill_idempotent"] = True      # at N > 1 this is also "the sharded fill equals the single-GPU fixed point"
 
     def bit(i, j, k):
         idx = i + dimg[0] * (j + dimg[1] * k)
@@ -152,7 +165,10 @@ def main():
     out["closure_pairs_checked"] = len(pairs)
     print(json.dumps(out), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "large_%s_%d.json" % (kind, size)), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "large_%s_%d%s.json" % (kind, size, "" if world == 1 else "_n%d" % world)), "w"), indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
