@@ -396,8 +396,9 @@ class ShardedHotPath:
             self.pos0.copy_(pos4)
             self.ep0.copy_(ep4)
             self.step()
-            for o, t in zip(out, (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)):
-                o.copy_(t, non_blocking=True)
+            if self.rank == 0:      # every rank holds the complete result; the host needs it once
+                for o, t in zip(out, (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)):
+                    o.copy_(t, non_blocking=True)
             torch.cuda.synchronize()
         barrier()
         dt = time.perf_counter() - t0
@@ -408,4 +409,4 @@ class ShardedHotPath:
         h2d = sum(t.numel() * t.element_size() for t in (hcorn, hnorm))
         d2h = sum(t.numel() * t.element_size() for t in out)
         return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dt / steps, "api": "stage-level C-ABI on every rank (device weld + sharded hot path), pinned host buffers (per rank)"}
+                "ms_per_step": 1e3 * dt / steps, "api": "stage-level C-ABI on every rank (upload + device weld replicated, sharded hot path), results downloaded by rank 0, pinned host buffers"}
