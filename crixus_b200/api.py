@@ -105,6 +105,7 @@ def lib():
         "cx_fill_set_max_rounds": (C.c_int, [VP, C.c_int]),
         "cx_fill_unfinished": (C.c_int, [VP]),
         "cx_fill_resolve_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, C.POINTER(VP), C.POINTER(I64)]),
+        "cx_fill_resolve_part": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, C.c_int, C.c_int, C.POINTER(VP), C.POINTER(I64)]),
         "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
@@ -285,6 +286,16 @@ class Context:
         ptr, n = VP(), I64(0)
         self._ck(self.L.cx_fill_resolve_slab(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
                                              self._p(cell_idx), k_begin, k_end, C.byref(ptr), C.byref(n)))
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i4", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def fill_resolve_part(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, nparts, part):
+        import torch
+        ptr, n = VP(), I64(0)
+        self._ck(self.L.cx_fill_resolve_part(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
+                                             self._p(cell_idx), int(nparts), int(part), C.byref(ptr), C.byref(n)))
 
         class _Raw:
             __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i4", "data": (int(ptr.value), False), "version": 2}

@@ -120,6 +120,7 @@ struct FillArgs {
   uint8_t *tile_res;            // tile already resolved (blocked planes valid)
   int32_t *rlist;               // tiles to resolve this round
   unsigned long long *changed;  // newly set cells
+  int res_nparts, res_part;     // up-front resolve of items part, part+nparts, ... in chunks of 64 (0/1: everything)
   int resolved_all;             // every hard cell of the owned planes was resolved up front (no per-round resolve)
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(256, 3) k_resolve_tiles(FillArgs A)
     long long item = 0;
     if (lane == 0) item = ALL ? (long long)atomicAdd((unsigned long long *)A.count64, 1ull) : (long long)atomicAdd(&A.count[3], 1);
     item = __shfl_sync(0xffffffffu, item, 0);
+    if (ALL && A.res_nparts > 1) item = ((item >> 6) * A.res_nparts + A.res_part) * 64 + (item & 63);   // interleaved sharding
     if (item >= (ALL ? A.ntiles : (long long)A.count[2]) * FT_THREADS) break;
     const int tile = ALL ? (int)(item / FT_THREADS) : A.rlist[item / FT_THREADS], wt = (int)(item % FT_THREADS);
     const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
@@ -894,6 +896,33 @@ extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *f
     CX_LAUNCH_CHECK(ctx, "k_resolve_all");
   }
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
+  if (blocked_d) *blocked_d = s->B;
+  if (blocked_words) *blocked_words = 6 * A.nw;
+  return CX_OK;
+}
+
+// interleaved variant: the 32-cell words of the lattice are dealt to the ranks in chunks of 64 (z-slabs balance badly:
+// the floor slab holds most of the hard cells); same contract otherwise
+extern "C" int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                    const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
+                                    uint32_t **blocked_d, int64_t *blocked_words)
+{
+  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe || nparts < 1 || part < 0 || part >= nparts)
+    return CX_WRONG_INPUT;
+  FillArgs A;
+  FillState *s = nullptr;
+  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 1, &A, &s);
+  if (rc != CX_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  A.merge = 0;
+  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_unpack");
+  A.res_nparts = nparts; A.res_part = part;
+  CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
+  k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
+  CX_LAUNCH_CHECK(ctx, "k_resolve_all");
+  s->resolved_lo = 0; s->resolved_hi = A.dimg[2];
   if (blocked_d) *blocked_d = s->B;
   if (blocked_words) *blocked_words = 6 * A.nw;
   return CX_OK;

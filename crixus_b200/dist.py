@@ -183,7 +183,7 @@ class ShardedHotPath:
         small = 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES
         self.parallelism = "1 GPU" if world == 1 else (
             "vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; fill: %s; cheap stages and device weld replicated"
-            % (VV_CHUNK, world, ("directed tests sharded in %d z-slabs, blocked planes all-reduced, flood replicated" % world) if small else
+            % (VV_CHUNK, world, ("directed tests dealt to %d ranks in interleaved chunks, blocked planes all-reduced, flood replicated" % world) if small else
                ("%d z-slabs, halo exchange every %d rounds" % (world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
@@ -281,7 +281,7 @@ class ShardedHotPath:
             elif 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES:
                 # small lattice: shard the directed tests by z-slab, merge the blocked planes, flood everywhere
                 import torch.distributed as dist
-                B = ctx.fill_resolve_slab(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.k0, self.k1)
+                B = ctx.fill_resolve_part(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.world, self.rank)
                 dist.all_reduce(B)                       # rows are disjoint and zero elsewhere: SUM == OR
                 nfl += ctx.fill_propagate(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
                 rounds += ctx.last_rounds

@@ -140,6 +140,10 @@ int cx_fill_unfinished(cx_ctx *ctx);
 int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
                          int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words);
+/* same, but the lattice words are dealt to the ranks in interleaved chunks (balanced; z-slabs are not) */
+int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                         const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
+                         uint32_t **blocked_d, int64_t *blocked_words);
 int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                       const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                       int64_t *nfi_host, int32_t *rounds_host);

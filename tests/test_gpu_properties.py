@@ -156,10 +156,16 @@ def _check_fill(hp, oracle, nsample=1500):
         for x in w["fills"]:
             if x[0] == "box":
                 ctxs[r].fill_box(hp.pf, fr[r], x[1], x[2])
-    Bs = [ctxs[r].fill_resolve_slab(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, ks[r][0], ks[r][1]) for r in range(n)]
+    # the blocked planes are zero-copy views of context-owned memory: clone before the context is used again
+    Bp = [ctxs[r].fill_resolve_part(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, n, r).clone() for r in range(n)]   # interleaved
+    Bs = [ctxs[r].fill_resolve_slab(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, ks[r][0], ks[r][1]) for r in range(n)]  # z-slabs
     tot = Bs[0].clone()
     for r in range(1, n):
         tot += Bs[r]
+    totp = Bp[0].clone()
+    for r in range(1, n):
+        totp += Bp[r]
+    assert torch.equal(tot, totp), "interleaved and z-slab sharding of the directed tests disagree"
     for r in range(n):
         Bs[r].copy_(tot)
     for r in range(n):
