@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""calc_vert_volume rate on meshes that stress different regimes of the kernel (gpurun -- python tools/bench_vert_volume_meshes.py):
+closed cube tanks with h/dr = 1.25, 0.625, 0.5 (commensurate with the voxel grid: planes on voxel planes and through the
+faces of the sampling cube), 0.53 (generic), a shifted copy, a sphere in a tank, and the SPHERIC-2 tank of the bench."""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from crixus_b200 import api, meshgen as mg, workloads as wl
