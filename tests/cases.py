@@ -87,6 +87,18 @@ def case(name):
         L = 16 * 1.25 * dr
         c.update(dr=dr, swap_normals=True, periodic=(True, True, False),
                  fills=[("geometry", (L / 2, L / 2, 5 * 1.25 * dr), dr)])
+    elif name == "channel_yz":     # the channel with its axes permuted: periodic in y and z (wrap of the z-columns in the fill,
+        dr = 0.05                  # periodic unwrap along z in calc_vert_volume, find_links for idim = 1, 2)
+        v, t, n = mg.channel(n=16, dr=dr, height=10 * 1.25 * dr)
+        v, n = np.ascontiguousarray(v[:, [2, 0, 1]]), np.ascontiguousarray(n[:, [2, 0, 1]])
+        L = 16 * 1.25 * dr
+        c.update(dr=dr, swap_normals=True, periodic=(False, True, True),
+                 fills=[("geometry", (5 * 1.25 * dr, L / 2, L / 2), dr)])
+    elif name == "cube_fs_bad":    # free-surface triangles whose stored normal disagrees with their plane: nothing can be culled,
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)      # every lattice cell takes the full test
+        fs_t = np.array([[[0, 0, 0.5], [1, 0, 0.5], [1, 1, 0.5]], [[0, 0, 0.5], [1, 1, 0.5], [0, 1, 0.5]]], dtype=np.float32)
+        fs_n = np.array([[0, 0.6, 0.8], [0, 0, 0.5]], dtype=np.float32)
+        c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.25), 0.08)], fshape=(fs_t, fs_n))
     elif name == "sphere_tank":    # config 4 in small: curved, non axis-aligned triangles
         dr = 0.05
         v, t, n = mg.sphere_in_tank(side_cells=20, dr=dr, hfac=1.0, sphere_levels=2)
@@ -98,7 +110,7 @@ def case(name):
     return c
 
 
-ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "sphere_tank"]
+ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "channel_yz", "cube_fs_bad", "sphere_tank"]
 
 
 def run(B, c, stages=("volume", "fill")):
