@@ -51,7 +51,7 @@ class CxJob(C.Structure):
 ERRORS = {0: "CX_OK", -1: "STL_NOT_BINARY", -2: "NO_FILE", -3: "FILE_NOT_OPEN", -4: "CANT_READ_CONFIG", -5: "READ_ERROR",
           -6: "FLUID_NDEF", -7: "WRITE_FAIL", -9: "NO_PER_VERT", -11: "WRONG_INPUT", -16: "NO_WRITE_FILE",
           -17: "FLUID_BBOX_TOO_SMALL", -18: "INTERNAL_ERROR", -101: "CUDA_ERROR", -102: "TRIMAX_EXCEEDED",
-          -103: "FAN_INCOMPLETE", -104: "SEED_OUTSIDE", -105: "NO_DEVICE"}
+          -103: "FAN_INCOMPLETE", -104: "SEED_OUTSIDE", -105: "NO_DEVICE", -106: "WELD_CELL_TOO_FULL"}
 
 
 class CxError(RuntimeError):

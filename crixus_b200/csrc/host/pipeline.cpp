@@ -60,7 +60,20 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     CU(cudaMallocAsync((void **)&w_ep4, 16 * (size_t)nbe, st));
     CU(cudaMemcpyAsync(w_corners, job->corners, 36 * (size_t)nbe, cudaMemcpyHostToDevice, st));
     RC(cx_bbox_device(ctx, w_corners, 3 * nbe, bbmin, bbmax));
-    RC(cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert));
+    int wrc = cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert);
+    if (wrc == CX_WELD_CELL_TOO_FULL) {
+      // degenerate input (dr far larger than the mesh spacing): the host restatement of the weld, same outcome
+      std::vector<float> verts((size_t)9 * nbe), hp;
+      std::vector<int32_t> ids((size_t)3 * nbe), he((size_t)4 * nbe);
+      nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
+      hp.resize((size_t)4 * nvert);
+      for (int64_t v = 0; v < nvert; v++) { hp[4 * v] = verts[3 * v]; hp[4 * v + 1] = verts[3 * v + 1]; hp[4 * v + 2] = verts[3 * v + 2]; hp[4 * v + 3] = 0.f; }
+      for (int64_t i = 0; i < nbe; i++) { for (int k = 0; k < 3; k++) he[4 * i + k] = ids[3 * i + k]; he[4 * i + 3] = 0; }
+      CU(cudaMemcpy(w_pos4, hp.data(), 16 * (size_t)nvert, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(w_ep4, he.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
+      wrc = CX_OK;
+    }
+    RC(wrc);
     CU(cudaFreeAsync(w_corners, st));
   }
   job->nvert = nvert;

@@ -166,6 +166,8 @@ static int radix_sort_pairs(cx_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ weld
+#define CX_WELD_MAX_RUN 20000
+
 struct WeldGrid {
   int32_t cmin[3];
   int64_t ny, nz;
@@ -194,6 +196,19 @@ __global__ void __launch_bounds__(256) k_weld_starts(const uint64_t *__restrict_
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     if (i == 0 || keys[i] != keys[i - 1]) start[headscan[i]] = (int32_t)i;
+}
+
+// longest run (corners per cell): the claim loop is quadratic in it
+__global__ void __launch_bounds__(256) k_weld_maxrun(const int32_t *__restrict__ start, int64_t nruns, int64_t n, int32_t *__restrict__ mx)
+{
+  int m = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nruns; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = (r + 1 < nruns) ? (int64_t)start[r + 1] : n;
+    m = max(m, (int)(e - start[r]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(mx, m);
 }
 
 // one thread per cell: the claim loop of crixus.cpp:363-380 + find_in_cell (:317-329)
@@ -288,6 +303,16 @@ extern "C" int cx_weld_device(cx_ctx *ctx, const float *corners_d, int64_t ncorn
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 44, head + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CX_CUDA(ctx, cudaStreamSynchronize(st));
   const int64_t nruns = *(int32_t *)(ctx->h_mail + 44);
+  {  // a cell with tens of thousands of corners (dr far larger than the mesh spacing) would make one thread loop for minutes
+    int32_t *mx = (int32_t *)(ctx->d_mail + 45);
+    CX_CUDA(ctx, cudaMemsetAsync(mx, 0, sizeof(int32_t), st));
+    k_weld_maxrun<<<cx_blocks(nruns, 256, ctx->num_sms * 8), 256, 0, st>>>(start, nruns, n, mx);
+    CX_LAUNCH_CHECK(ctx, "k_weld_maxrun");
+    CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 45, mx, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*(int32_t *)(ctx->h_mail + 45) > CX_WELD_MAX_RUN)
+      return cx_fail(ctx, CX_WELD_CELL_TOO_FULL, "weld: more than 20000 corners in one dr-cell (dr far larger than the mesh spacing?)");
+  }
   const double thr = 1e-10 * dr * dr;                   // crixus.cpp:324 (double)
   k_weld_cells<<<cx_blocks(nruns, 128, ctx->num_sms * 32), 128, 0, st>>>(corners_d, vs, start, nruns, n, thr, rep, isrep);
   CX_LAUNCH_CHECK(ctx, "k_weld_cells");

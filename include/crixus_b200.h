@@ -37,7 +37,8 @@ enum {
   CX_TRIMAX_EXCEEDED = -102, /* a vertex has more than CX_TRIMAX triangles (reference: thread returns, crixus_d.cu:306) */
   CX_FAN_INCOMPLETE = -103,  /* a vertex' triangles were not all found in its 27 cells (mesh precondition violated) */
   CX_SEED_OUTSIDE = -104,    /* geometry-fill seed outside the fluid lattice (reference: out-of-bounds write) */
-  CX_NO_DEVICE = -105
+  CX_NO_DEVICE = -105,
+  CX_WELD_CELL_TOO_FULL = -106 /* cx_weld_device: > 20000 corners in one dr-cell; cx_preprocess_host falls back to cx_weld_host */
 };
 
 /* the __constant__ symbols of src/crixus_d.cu:13-32 */

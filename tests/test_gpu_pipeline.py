@@ -185,3 +185,15 @@ def test_device_weld_equals_host_weld(name, cuda_backend):
     np.testing.assert_array_equal(pos4.cpu().numpy()[:, :3], hv)
     np.testing.assert_array_equal(ep4.cpu().numpy()[:, :3], hid)
     assert not ep4[:, 3].any() and not pos4[:, 3].any()
+
+
+def test_device_weld_refuses_overfull_cells(cuda_backend):
+    """dr far larger than the mesh spacing puts every corner into one cell; the per-cell claim loop is quadratic, so the
+    device weld refuses (CX_WELD_CELL_TOO_FULL) and cx_preprocess_host takes the host weld instead."""
+    import torch
+    v, t, n = mg.plate(60, 0.01)
+    corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
+    assert corners.shape[0] > 20000
+    with pytest.raises(api.CxError) as e:
+        cuda_backend.ctx.weld_device(torch.from_numpy(corners).to(cuda_backend.ctx.device), np.float32(5.0))
+    assert e.value.code == -106
