@@ -33,9 +33,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01g_*.txt),
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01h_*.txt),
 # valid for the default workload (config 2) on one GPU only
-NCU_TRAFFIC = {"k_vert_volume": 135.710976e6 + 15.543296e6, "k_resolve_tiles": 141.216e6 + 9.152e6}
+NCU_TRAFFIC = {"k_vert_volume": 135.112960e6 + 9.579264e6, "k_resolve_tiles": 140.846592e6 + 7.789312e6}
 
 VOXELS = 41 ** 3
 FLOP_PER_VOXEL_TRI = 56      # 25 cube + 8 voronoi + 15 wall + 8 edge
@@ -222,7 +222,7 @@ def main():
                          "frac": achieved / fp32_peak, "traffic": NCU_TRAFFIC["k_vert_volume"] if (world == 1 and args.levels == 3) else None,
                          "frac_note": "ALGORITHMIC flops of the reference's brute-force 41^3 quadrature over the measured FFMA peak; the kernel "
                                       "removes > 90 % of them by exact culling (monotone threshold search), hence frac > 1.  Executed view (ncu, "
-                                      "profiles/r01g_vv.txt): 64.6e3 warp instructions per vertex, 67 % of issue slots busy, DRAM traffic 0.15 GB "
+                                      "profiles/r01h_vv.txt): 70e3 warp instructions per vertex, 2.7 instructions per cycle and SM, DRAM traffic 0.15 GB "
                                       "per launch against 23 GB algorithmic bytes (L2 hit 99.9 %)",
                          "peak_source": "FFMA micro-kernel measured in this run (cx_measure_fp32_peak); nominal 148*128*2*1.965 GHz = 74.4",
                          "flops_per_vertex": VOXELS * T * FLOP_PER_VOXEL_TRI, "mean_trisize": T,
@@ -232,7 +232,7 @@ def main():
                               "traffic": NCU_TRAFFIC["k_resolve_tiles"] if (world == 1 and args.levels == 3) else None,
                               "peak_source": hbm_src, "bytes": fill_bytes,
                               "frac_note": "the fill is bound by the directed tests of the cells near walls (k_resolve_tiles, ALU/latency), "
-                                           "not by HBM; profiles/r01g_resolve.txt"},
+                                           "not by HBM; profiles/r01h_resolve.txt"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
