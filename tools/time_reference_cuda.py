@@ -41,6 +41,37 @@ def run(cmd, cwd, limit):
         return None, None, "timeout after %d s" % limit
 
 
+def compare_outputs(d, c, ini):
+    """runs both programs once more into separate directories and compares the particle files (segments in canonical
+    order: the reference's intra-cell segment order is run-dependent, crixus_d.cu:94)"""
+    import re
+    import shutil
+    from make_golden import canonical_segments
+    from vtu import read_vtu, split_particles
+    outs = {}
+    for name, exe in (("ours", os.path.join(ROOT, "crixus_b200", "bin", "crixus")), ("ref", os.path.join(ROOT, "oracle", "_ref", "Crixus_ref"))):
+        wd = os.path.join(d, name)
+        os.makedirs(wd, exist_ok=True)
+        r = subprocess.run([exe, ini], cwd=wd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, name + " failed"
+        p = split_particles(read_vtu(os.path.join(wd, c["name"] + ".vtu")))
+        p["segment"] = canonical_segments(p["segment"])
+        p["counted"] = int(re.search(r"Creation of (\d+) fluid particles", r.stdout).group(1))
+        outs[name] = p
+        shutil.rmtree(wd)
+    a, b = outs["ours"], outs["ref"]
+    nf = b["fluid"]["Points"].shape[0]
+    shift = b["counted"] - nf              # the reference's racy extra count (DESIGN.md section 5): 0 or 1
+    assert shift in (0, 1), "reference count shift %d" % shift
+    assert a["counted"] == nf, "fluid count %d vs %d" % (a["counted"], nf)
+    for grp, keys in (("fluid", ("Points", "Volume")), ("vertex", ("Points", "Volume")), ("segment", ("Points", "Normal", "Surface"))):
+        for k in keys:
+            assert np.array_equal(a[grp][k], b[grp][k]), "%s.%s differs" % (grp, k)
+    assert np.array_equal(a["segment"]["VertexParticle"].astype(np.int64) + shift, b["segment"]["VertexParticle"].astype(np.int64)), "segment links differ"
+    return {"bit_exact": True, "fluid": int(nf), "vertices": int(a["vertex"]["Points"].shape[0]), "segments": int(a["segment"]["Points"].shape[0]),
+            "reference_count_shift": int(shift)}
+
+
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "ref_timing.json")
     levels = [int(x) for x in sys.argv[2:]] or [0, 1, 2]
@@ -48,6 +79,7 @@ def main():
     res = []
     for lv in levels:
         c = case_for(lv)
+        c["name"] = "m"
         with tempfile.TemporaryDirectory() as d:
             stl, fsp, ini = os.path.join(d, "m.stl"), os.path.join(d, "m_fs.stl"), os.path.join(d, "m.ini")
             mg.write_stl(stl, c["tris"], c["normals"])
@@ -65,6 +97,13 @@ def main():
                 for line in tail.splitlines():
                     if "Timing:" in line or "fluid particles completed" in line:
                         row.setdefault(name + "_log", []).append(line.strip())
+            # ---- full-size parity: our .vtu against the reference's, particle by particle
+            ours_vtu, ref_vtu = os.path.join(d, c["name"] + ".vtu"), None
+            if row.get("reference_cuda_rc") == 0 and row.get("ours_rc") == 0:
+                try:
+                    row["parity"] = compare_outputs(d, c, ini)
+                except AssertionError as e:
+                    row["parity"] = "MISMATCH: " + str(e)[:300]
             res.append(row)
             print(json.dumps(row), flush=True)
     json.dump(res, open(out, "w"), indent=1)
