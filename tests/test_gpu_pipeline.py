@@ -197,3 +197,24 @@ def test_device_weld_refuses_overfull_cells(cuda_backend):
     with pytest.raises(api.CxError) as e:
         cuda_backend.ctx.weld_device(torch.from_numpy(corners).to(cuda_backend.ctx.device), np.float32(5.0))
     assert e.value.code == -106
+
+
+def test_cli_equals_reference_binary_on_config1(tmp_path):
+    """BASELINE configs[0] at full size, live: resources/spheric2.ini's options on the regenerated SPHERIC-2 mesh (47 736
+    triangles) through both command lines -- ours and the reference's own CUDA build (oracle/_ref/Crixus_ref, made by
+    oracle/build_ref.sh) -- and the two .vtu files compared particle by particle."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "Crixus_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/Crixus_ref not built")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import time_reference_cuda as trc
+    from make_golden import write_ini
+    c = trc.case_for(0)
+    c["name"] = "m"
+    stl, fsp, ini = str(tmp_path / "m.stl"), str(tmp_path / "m_fs.stl"), str(tmp_path / "m.ini")
+    mg.write_stl(stl, c["tris"], c["normals"])
+    mg.write_stl(fsp, c["fshape"][0], c["fshape"][1])
+    write_ini(ini, c, stl, fsp)
+    res = trc.compare_outputs(str(tmp_path), c, ini)
+    assert res["bit_exact"] and res["fluid"] == 104940 and res["segments"] == 47736
