@@ -44,6 +44,7 @@ class CxJob(C.Structure):
                 ("surf", C.POINTER(C.c_float)), ("vol", C.POINTER(C.c_float)), ("cell_idx", C.POINTER(C.c_int32)),
                 ("fpos", C.POINTER(C.c_uint32)), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
                 ("params_fill", CxParams),
+                ("tri_failed", C.c_int64), ("tri_mind", C.c_float), ("tri_maxd", C.c_float),
                 ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double),
                 ("stage_ms", C.c_float * 8)]
 
@@ -111,6 +112,7 @@ def lib():
         "cx_job_free": (None, [C.POINTER(CxJob)]),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
         "cx_bbox_device": (C.c_int, [VP, VP, I64, F3, F3]),
+        "cx_check_triangle_size": (C.c_int, [VP, VP, I64, C.c_float, C.POINTER(I64), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "cx_weld_device": (C.c_int, [VP, VP, I64, C.c_float, F3, F3, VP, VP, C.POINTER(I64)]),
         "cx_ini_open": (C.c_int, [C.c_char_p, C.POINTER(VP)]),
         "cx_ini_close": (None, [VP]),
@@ -307,6 +309,12 @@ class Context:
                                           self._p(cell_idx), seed, C.byref(n), C.byref(r)))
         self.last_rounds = int(r.value)
         return int(n.value)
+
+    def check_triangle_size(self, corners, dr):
+        """corners: torch float32 (3*ntri, 3) on the device -> (failures, min distance, max distance)"""
+        n, lo, hi = I64(0), C.c_float(0), C.c_float(0)
+        self._ck(self.L.cx_check_triangle_size(self.h, self._p(corners), corners.shape[0] // 3, float(dr), C.byref(n), C.byref(lo), C.byref(hi)))
+        return int(n.value), float(lo.value), float(hi.value)
 
     def weld_device(self, corners, dr):
         """corners: torch float32 (ncorner, 3) on the device -> (pos float4 (nvert,4), ep int4 (nbe,4), bbmin, bbmax)"""

@@ -157,6 +157,9 @@ int cx_run_ini(const char *ini_path)
   const double t_create = wall_s() - t_c0;
   rc = cx_preprocess_host(ctx, &job);
   if (rc != CX_OK) { printf("Preprocessing failed: %d %s\n", rc, cx_last_error(ctx)); cx_destroy(ctx); return rc; }
+  if (job.tri_failed > 0)   // the reference leaves this check to its stand-alone tool resources/test-triangle-size.c
+    printf("WARNING: %lld vertex-barycentre distances exceed dr - 1e-4*dr (max %g): triangles too large for dr, results are unreliable\n",
+           (long long)job.tri_failed, job.tri_maxd);
   printf("\n\tInformation:\n\tNumber of vertices:         \t%lld\n\tNumber of boundary elements:\t%lld\n\n", (long long)job.nvert, (long long)job.nbe);
   printf("\tNormals information:\n\tPositive (n.(0,0,1)) minimum z: %g (%g)\n\tNegative (n.(0,0,1)) minimum z: %g (%g)\n\n", job.zstat[0],
          job.zstat[2], job.zstat[1], job.zstat[3]);

@@ -60,6 +60,7 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     CU(cudaMallocAsync((void **)&w_ep4, 16 * (size_t)nbe, st));
     CU(cudaMemcpyAsync(w_corners, job->corners, 36 * (size_t)nbe, cudaMemcpyHostToDevice, st));
     RC(cx_bbox_device(ctx, w_corners, 3 * nbe, bbmin, bbmax));
+    RC(cx_check_triangle_size(ctx, w_corners, nbe, dr, &job->tri_failed, &job->tri_mind, &job->tri_maxd));
     int wrc = cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert);
     if (wrc == CX_WELD_CELL_TOO_FULL) {
       // degenerate input (dr far larger than the mesh spacing): the host restatement of the weld, same outcome

@@ -78,6 +78,70 @@ extern "C" int cx_bbox_device(cx_ctx *ctx, const float *corners_d, int64_t ncorn
   return CX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ mesh precondition
+// resources/test-triangle-size.c: every vertex-barycentre distance must be <= dr - 1e-4*dr (README.md: triangles larger
+// than that break the 27-cell neighbourhood assumption of calc_vert_volume and checkCollision).  Same arithmetic:
+// barycentre accumulated in float from double quotients (:43-46), distance in double, narrowed to float (:48).
+__global__ void __launch_bounds__(256) k_triangle_size(const float *__restrict__ c, int64_t ntri, float dr, float eps, unsigned *mm,
+                                                       unsigned long long *failed)
+{
+  float mind = 1e10f, maxd = 0.f;
+  unsigned long long nf = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ntri; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[9], s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 9; q++) v[q] = c[9 * i + q];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] = (float)((double)s[k] + (double)v[3 * j + k] / 3.0);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double dx = (double)fsub(s[0], v[3 * j]), dy = (double)fsub(s[1], v[3 * j + 1]), dz = (double)fsub(s[2], v[3 * j + 2]);
+      const float dist = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      maxd = fmaxf(maxd, dist);
+      mind = fminf(mind, dist);
+      if (dist > fsub(dr, eps)) nf++;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mind = fminf(mind, __shfl_xor_sync(0xffffffffu, mind, o));
+    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], f2ord(mind));
+    atomicMax(&mm[3], f2ord(maxd));
+    if (nf) atomicAdd(failed, nf);
+  }
+}
+
+extern "C" int cx_check_triangle_size(cx_ctx *ctx, const float *corners_d, int64_t ntri, float dr, int64_t *failed_host, float *mind_host,
+                                      float *maxd_host)
+{
+  if (!ctx || !corners_d || ntri <= 0 || !(dr > 0)) return CX_WRONG_INPUT;
+  unsigned *mm = (unsigned *)(ctx->d_mail + 32);
+  float *out = (float *)(ctx->d_mail + 36);
+  unsigned long long *failed = (unsigned long long *)(ctx->d_mail + 46);
+  k_bbox_init<<<1, 32, 0, ctx->stream>>>(mm);
+  CX_LAUNCH_CHECK(ctx, "k_bbox_init");
+  CX_CUDA(ctx, cudaMemsetAsync(failed, 0, sizeof(unsigned long long), ctx->stream));
+  const float eps = (float)(dr * 1e-4);     // test-triangle-size.c:24
+  k_triangle_size<<<cx_blocks(ntri, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(corners_d, ntri, dr, eps, mm, failed);
+  CX_LAUNCH_CHECK(ctx, "k_triangle_size");
+  k_bbox_finish<<<1, 32, 0, ctx->stream>>>(mm, out);
+  CX_LAUNCH_CHECK(ctx, "k_bbox_finish");
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 36, out, 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 46, failed, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const float *h = (const float *)(ctx->h_mail + 36);
+  if (failed_host) *failed_host = ctx->h_mail[46];
+  if (mind_host) *mind_host = h[0];
+  if (maxd_host) *maxd_host = h[3];
+  return CX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ radix sort
 // Stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass.  Per pass: per-block digit histograms
 // (bin-major) -> exclusive scan -> stable scatter (rank inside the block = warp match + per-warp digit counts).

@@ -180,6 +180,7 @@ typedef struct cx_job {
   int64_t dimg[3];
   float zstat[4];
   cx_params params_fill;
+  int64_t tri_failed; float tri_mind, tri_maxd; /* mesh precondition (cx_check_triangle_size), filled when raw corners are given */
   double t_weld_s, t_gpu_s, t_h2d_s, t_d2h_s; /* wall-clock breakdown */
   float stage_ms[8]; /* CUDA-event times: 0 swap+set_bound_elem, 1 binning, 2 periodic links, 3 trisize, 4 vert volume, 5 fills */
 } cx_job;
@@ -194,6 +195,11 @@ void cx_job_free(cx_job *job);
 int cx_bbox_device(cx_ctx *ctx, const float *corners_d, int64_t ncorner, float bbmin[3], float bbmax[3]);
 int cx_weld_device(cx_ctx *ctx, const float *corners_d, int64_t ncorner, float dr, const float bbmin[3], const float bbmax[3],
                    float *pos4_d, int32_t *ep4_d, int64_t *nvert_host);
+
+/* the mesh precondition of resources/test-triangle-size.c on the device: every vertex-barycentre distance must be
+ * <= dr - 1e-4*dr.  *failed_host = number of (triangle, corner) pairs that violate it, *mind / *maxd = extreme distances */
+int cx_check_triangle_size(cx_ctx *ctx, const float *corners_d, int64_t ntri, float dr, int64_t *failed_host, float *mind_host,
+                           float *maxd_host);
 
 /* host weld, src/crixus.cpp:343-455 (outcome-exact restatement).  out_verts: room for 3*ncorner floats,
  * out_ids: ncorner ints.  Returns the number of welded vertices. */

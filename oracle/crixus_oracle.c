@@ -289,6 +289,30 @@ void orc_periodicity_links(int32_t *ep, int64_t nbe, const int32_t *newlink)
       if (newlink[ep[4 * i + j]] != -1) ep[4 * i + j] = newlink[ep[4 * i + j]];
 }
 
+/* ------------------------------------------------------------------------------------------------ mesh precondition
+ * resources/test-triangle-size.c:24,38-58: every vertex-barycentre distance must be <= dr - 1e-4*dr.
+ * corners: ntri*9 floats (STL order).  out[0] = min distance, out[1] = max distance; returns the number of failures. */
+int64_t orc_triangle_size(const float *corners, int64_t ntri, float dr, float *out)
+{
+  const float eps = dr * 1e-4;                    /* :24  (double product narrowed to float) */
+  float mind = 1e10, maxd = 0e10;                 /* :33-34 */
+  int64_t failed = 0;
+  for (int64_t i = 0; i < ntri; i++) {
+    const float *v = corners + 9 * i;
+    float s[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < 3; k++) s[k] += v[3 * j + k] / 3.0;      /* :43-46 double division, float accumulator */
+    for (int j = 0; j < 3; j++) {
+      const float dist = sqrt(pow(s[0] - v[3 * j + 0], 2) + pow(s[1] - v[3 * j + 1], 2) + pow(s[2] - v[3 * j + 2], 2.0));  /* :48 */
+      if (dist > maxd) maxd = dist;
+      if (dist < mind) mind = dist;
+      if (dist > dr - eps) failed++;              /* :53 */
+    }
+  }
+  out[0] = mind; out[1] = maxd;
+  return failed;
+}
+
 /* ------------------------------------------------------------------------------------------------ trisize
  * src/crixus_d.cu:258-267 */
 void orc_calc_trisize(const int32_t *ep, int32_t *trisize, int64_t nbe)

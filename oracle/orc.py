@@ -65,6 +65,8 @@ class Oracle:
         L.orc_find_links.restype = C.c_int64
         L.orc_periodicity_links.argtypes = [i32p, C.c_int64, i32p]
         L.orc_calc_trisize.argtypes = [i32p, i32p, C.c_int64]
+        L.orc_triangle_size.argtypes = [f32p, C.c_int64, C.c_float, f32p]
+        L.orc_triangle_size.restype = C.c_int64
         L.orc_calc_vert_volume.argtypes = [P, f32p, f32p, i32p, f32p, i32p, i32p, C.c_int64, C.c_int64, C.c_int]
         L.orc_calc_vert_volume.restype = C.c_int64
         L.orc_fill_box.argtypes = [P, u32p] + [C.c_float] * 6
@@ -128,6 +130,13 @@ class Oracle:
 
     def periodicity_links(self, p, pos, ep, nvert, nbe, newlink, idim):
         self.L.orc_periodicity_links(ep, nbe, newlink)
+
+    def triangle_size(self, corners, dr):
+        """resources/test-triangle-size.c -> (failures, min distance, max distance)"""
+        corners = np.ascontiguousarray(corners, dtype=np.float32).reshape(-1)
+        out = np.zeros(2, dtype=np.float32)
+        n = int(self.L.orc_triangle_size(corners, corners.size // 9, np.float32(dr), out))
+        return n, float(out[0]), float(out[1])
 
     def calc_trisize(self, p, ep, nvert, nbe):
         t = np.zeros(nvert, dtype=np.int32)

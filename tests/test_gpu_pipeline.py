@@ -218,3 +218,15 @@ def test_cli_equals_reference_binary_on_config1(tmp_path):
     write_ini(ini, c, stl, fsp)
     res = trc.compare_outputs(str(tmp_path), c, ini)
     assert res["bit_exact"] and res["fluid"] == 104940 and res["segments"] == 47736
+
+
+def test_triangle_size_check(oracle, cuda_backend):
+    """cx_check_triangle_size (the criterion of resources/test-triangle-size.c) against the oracle, exactly."""
+    import torch
+    v, t, n = mg.spheric2(dr=0.06)
+    corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
+    d = torch.from_numpy(corners).to(cuda_backend.ctx.device)
+    for dr in (0.06, 0.05, 0.03):
+        got = cuda_backend.ctx.check_triangle_size(d, np.float32(dr))
+        ref = oracle.triangle_size(corners, np.float32(dr))
+        assert got[0] == ref[0] and np.float32(got[1]) == np.float32(ref[1]) and np.float32(got[2]) == np.float32(ref[2]), (dr, got, ref)

@@ -99,3 +99,28 @@ def test_empty_fill_and_box_overcount(oracle):
     c["fills"] = c["fills"] * 2
     o = cases.run(oracle, c, stages=("fill",))
     assert o["fill_counts"] == [9, 9] and int(np.unpackbits(o["fpos"].view(np.uint8)).sum()) == 9
+
+
+def test_triangle_size_vs_reference_tool(oracle, tmp_path):
+    """oracle.triangle_size against the reference's own stand-alone checker (resources/test-triangle-size.c, compiled
+    unmodified by oracle/build_ref.sh) on a mesh that passes and on one that is too coarse for dr."""
+    import re
+    import subprocess
+    from crixus_b200 import meshgen as mg
+    tool = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "test-triangle-size")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/test-triangle-size not built")
+    v, t, n = mg.spheric2(dr=0.06)
+    stl = str(tmp_path / "m.stl")
+    mg.write_stl(stl, v[t], n)
+    for dr in (0.06, 0.05, 0.03):
+        out = subprocess.run([tool, stl, repr(dr)], capture_output=True, text=True).stdout
+        m = re.search(r"(\d+) triangles failed", out)
+        ref_failed = int(m.group(1)) if m else 0
+        assert ("All triangles passed" in out) == (ref_failed == 0)
+        ref_min = float(re.search(r"Minimum distance: ([\d.eE+-]+)", out).group(1))
+        ref_max = float(re.search(r"Maximum distance: ([\d.eE+-]+)", out).group(1))
+        failed, mind, maxd = oracle.triangle_size(v[t], np.float32(dr))
+        assert failed == ref_failed, (dr, failed, ref_failed)
+        assert abs(mind - ref_min) < 1e-6 and abs(maxd - ref_max) < 1e-6
+    assert oracle.triangle_size(v[t], np.float32(0.06))[0] == 0 and oracle.triangle_size(v[t], np.float32(0.03))[0] > 0
