@@ -24,6 +24,11 @@ struct Buf {
   void *p = nullptr;
   template <class T> T *as() { return (T *)p; }
 };
+struct CopyStream {   // second stream + event for the overlapped download; released on every exit path
+  cudaStream_t s = nullptr;
+  cudaEvent_t e = nullptr;
+  ~CopyStream() { if (s) cudaStreamDestroy(s); if (e) cudaEventDestroy(e); }
+};
 #define RC(call) do { int rc__ = (call); if (rc__ != CX_OK) return rc__; } while (0)
 #define CU(call) do { if ((call) != cudaSuccess) return CX_CUDA_ERROR; } while (0)
 }  // namespace
@@ -153,6 +158,21 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   }
   for (int k = 0; k < 3; k++) p.per[k] = job->periodic[k] ? 1 : 0;  // crixus.cu:428
   CU(cudaEventRecord(ev[3], st));
+  // pos / norm / ep / surf / cell_idx are final from here on (crixus.cu:363-365, 413): download them on a second stream
+  // while calc_vert_volume and the fills run
+  job->pos = (float *)(hbase + o_pos); job->norm = (float *)(hbase + o_norm); job->ep = (int32_t *)(hbase + o_ep);
+  job->surf = (float *)(hbase + o_surf); job->cell_idx = (int32_t *)(hbase + o_cell);
+  CopyStream cs;
+  CU(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&cs.e, cudaEventDisableTiming));
+  CU(cudaEventRecord(cs.e, st));
+  CU(cudaStreamWaitEvent(cs.s, cs.e, 0));
+  cudaStream_t cst = cs.s;
+  CU(cudaMemcpyAsync(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
+  CU(cudaMemcpyAsync(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
+  CU(cudaMemcpyAsync(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
+  CU(cudaMemcpyAsync(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
+  CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, cst));
   RC(cx_calc_trisize(ctx, ep.as<int32_t>(), trisize.as<int32_t>(), nbe));
   CU(cudaEventRecord(ev[4], st));
   RC(cx_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
@@ -217,16 +237,11 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
 
   // ---- results to the host (crixus.cu:363-365, 413, 456, 962): pinned arena, asynchronous copies, one synchronise
   t0 = now_s();
-  job->pos = (float *)(hbase + o_pos); job->norm = (float *)(hbase + o_norm); job->ep = (int32_t *)(hbase + o_ep);
-  job->surf = (float *)(hbase + o_surf); job->vol = (float *)(hbase + o_vol); job->cell_idx = (int32_t *)(hbase + o_cell);
+  job->vol = (float *)(hbase + o_vol);
   job->fpos = (uint32_t *)(hbase + o_fpos);
-  CU(cudaMemcpyAsync(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(job->vol, vol.p, 4 * (size_t)nvert, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(job->fpos, fpos.p, 4 * (size_t)nwords, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(cst));
   RC(cx_synchronize(ctx));
   int64_t pop = 0;
   for (int64_t w = 0; w < nwords; w++) pop += __builtin_popcount(job->fpos[w]);
