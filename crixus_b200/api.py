@@ -39,10 +39,11 @@ class CxJob(C.Structure):
                 ("use_container", C.c_int32), ("cmin", C.c_float * 3), ("cmax", C.c_float * 3),
                 ("fs_corners", C.POINTER(C.c_float)), ("fs_normals", C.POINTER(C.c_float)), ("fs_nbe", C.c_int64),
                 ("fills", C.POINTER(CxFillSpec)), ("nfills", C.c_int32),
+                ("sb_corners", C.POINTER(C.POINTER(C.c_float))), ("sb_nbe", C.POINTER(C.c_int64)), ("nsb", C.c_int32),
                 ("nvert", C.c_int64), ("nfluid", C.c_int64), ("nfluid_counted", C.c_int64),
                 ("pos", C.POINTER(C.c_float)), ("norm", C.POINTER(C.c_float)), ("ep", C.POINTER(C.c_int32)),
                 ("surf", C.POINTER(C.c_float)), ("vol", C.POINTER(C.c_float)), ("cell_idx", C.POINTER(C.c_int32)),
-                ("fpos", C.POINTER(C.c_uint32)), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
+                ("fpos", C.POINTER(C.c_uint32)), ("sbid", C.POINTER(C.c_int32)), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
                 ("params_fill", CxParams),
                 ("tri_failed", C.c_int64), ("tri_mind", C.c_float), ("tri_maxd", C.c_float),
                 ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double),
@@ -99,6 +100,7 @@ def lib():
         "cx_calc_trisize": (C.c_int, [VP, VP, VP, I64]),
         "cx_calc_vert_volume": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, I64, I64, C.c_int, I64, I64]),
         "cx_calc_vert_volume_part": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, I64, I64, C.c_int, I64, C.c_int, C.c_int]),
+        "cx_identify_special_boundary": (C.c_int, [VP, P, VP, VP, VP, I64, I64, VP, VP, I64, VP, C.c_int32]),
         "cx_fill_box": (C.c_int, [VP, P, VP, F3, F3, C.POINTER(I64)]),
         "cx_fill_geometry": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_fill_geometry_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, I64, C.c_int, C.POINTER(I64),
@@ -110,6 +112,7 @@ def lib():
         "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
+        "cx_job_sizeof": (I64, []),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
         "cx_bbox_device": (C.c_int, [VP, VP, I64, F3, F3]),
         "cx_check_triangle_size": (C.c_int, [VP, VP, I64, C.c_float, C.POINTER(I64), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -125,6 +128,7 @@ def lib():
         "cx_assemble_records": (I64, [C.POINTER(CxJob), I64, VP, I64]),
         "cx_write_vtu_records": (C.c_int, [VP, I64, C.c_char_p]),
         "cx_write_h5sph_records": (C.c_int, [VP, I64, C.c_char_p]),
+        "cx_write_split_records": (C.c_int, [VP, I64, I64, C.c_int32, C.c_char_p, C.c_int]),
         "cx_run_ini": (C.c_int, [C.c_char_p]),
     }
     for name, (res, args) in sig.items():
@@ -132,6 +136,8 @@ def lib():
         fn.restype = res
         fn.argtypes = args
     L._declared = sorted(sig)
+    if L.cx_job_sizeof() != C.sizeof(CxJob):
+        raise ImportError("crixus_b200.api.CxJob (%d bytes) does not mirror the library's cx_job (%d bytes)" % (C.sizeof(CxJob), L.cx_job_sizeof()))
     _lib = L
     return L
 
@@ -247,6 +253,10 @@ class Context:
 
     def calc_trisize(self, ep, trisize, nbe):
         self._ck(self.L.cx_calc_trisize(self.h, self._p(ep), self._p(trisize), nbe))
+
+    def identify_special_boundary(self, p, pos, ep, cell_idx, nvert, nbe, sbpos, sbep, sbnbe, sbid, sbi):
+        self._ck(self.L.cx_identify_special_boundary(self.h, C.byref(p), self._p(pos), self._p(ep), self._p(cell_idx), nvert, nbe,
+                                                     self._p(sbpos), self._p(sbep), sbnbe, self._p(sbid), int(sbi)))
 
     def calc_vert_volume(self, p, pos, norm, ep, vol, trisize, cell_idx, nvert, nbe, zero_open=False, v_begin=0, v_end=None):
         self._ck(self.L.cx_calc_vert_volume(self.h, C.byref(p), self._p(pos), self._p(norm), self._p(ep), self._p(vol),

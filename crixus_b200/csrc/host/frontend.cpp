@@ -89,6 +89,39 @@ int cx_write_h5sph_records(const void *records, int64_t n, const char *filename)
   return cx_write_h5sph(as_vector(records, n), filename);
 }
 
+// [output] split=true, crixus.cu:1137-1216: the fluid records, then one file per special-boundary id holding the vertex
+// and segment records with that KENT (record content unchanged, AbsoluteIndex stays the index in the unsplit list)
+int cx_write_split_records(const void *records, int64_t n, int64_t nfluid_particles, int32_t num_kents, const char *outname, int format)
+{
+  if ((!records && n > 0) || !outname || nfluid_particles < 0 || nfluid_particles > n || num_kents < 1 || (format != 1 && format != 2))
+    return CX_WRONG_INPUT;
+  const CxOutBuf *buf = (const CxOutBuf *)records;
+  auto write = [&](const std::vector<CxOutBuf> &v, const std::string &name) {   // generic_output, crixus.cpp:261-289
+    const std::string fn = format == 2 ? "0." + name + ".h5sph" : name + ".vtu";
+    const int rc = format == 2 ? cx_write_h5sph(v, fn) : cx_write_vtu(v, fn);
+    printf("Writing output to file %s ... %s\n", fn.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
+    return rc == CX_OK ? CX_OK : CX_WRITE_FAIL;
+  };
+  std::vector<std::vector<CxOutBuf>> per((size_t)num_kents);
+  for (int64_t i = nfluid_particles; i < n; i++) {
+    if (buf[i].kent < 0 || buf[i].kent >= num_kents) return CX_INTERNAL_ERROR;
+    per[(size_t)buf[i].kent].push_back(buf[i]);
+  }
+  printf("Counted:\n - Fluid particles: %lld\n", (long long)nfluid_particles);
+  for (int32_t k = 0; k < num_kents; k++)   // the reference's kent-0 count includes the fluid particles (crixus.cu:1155-1156)
+    printf(" - Boundary particles, kent %d: %lld\n", k, (long long)(per[(size_t)k].size() + (k == 0 ? nfluid_particles : 0)));
+  int rc = write(std::vector<CxOutBuf>(buf, buf + nfluid_particles), std::string(outname) + ".fluid");
+  if (rc != CX_OK) return rc;
+  for (int32_t k = 0; k < num_kents; k++) {
+    if (per[(size_t)k].empty()) continue;
+    std::ostringstream nm;
+    nm << outname << ".boundary.kent" << k;
+    rc = write(per[(size_t)k], nm.str());
+    if (rc != CX_OK) return rc;
+  }
+  return CX_OK;
+}
+
 int cx_run_ini(const char *ini_path)
 {
   printf("\n\tcrixus_b200 -- B200-native Crixus hot path (%s)\n\n", cx_version());
@@ -129,6 +162,27 @@ int cx_run_ini(const char *ini_path)
   const int frc = cx_read_stl(fsname, fs_corners, fs_normals);
   printf("Checking whether fluid geometry (%s) is available ... %s\n", fsname.c_str(), frc == CX_OK ? "[YES]" : "[NO]");
   if (frc == CX_OK) { job.fs_corners = fs_corners.data(); job.fs_normals = fs_normals.data(); job.fs_nbe = (int64_t)(fs_normals.size() / 3); }
+  // special-boundary grids: <ini minus 4 chars>_sbgrid_<i>.stl or [special_boundary_grids] mesh<i>, i = 1, 2, ... until a
+  // file is missing or not binary (crixus.cu:477-510); a short file is a read error (:564-567)
+  std::vector<std::vector<float>> sb_corners;
+  for (int sbi = 1;; sbi++) {
+    std::ostringstream ss;
+    ss << sbi;
+    std::string name = cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0) + "_sbgrid_" + ss.str() + ".stl";
+    name = ini.Get("special_boundary_grids", "mesh" + ss.str(), name);
+    std::vector<float> c, nrm;
+    const int src = cx_read_stl(name, c, nrm);
+    printf("Checking whether special boundary grid #%d (%s) is available ... %s\n", sbi, name.c_str(),
+           src == CX_FILE_NOT_OPEN ? "[NO]" : (src == CX_STL_NOT_BINARY ? "[YES] but not binary" : "[YES]"));
+    if (src == CX_FILE_NOT_OPEN || src == CX_STL_NOT_BINARY) break;
+    if (src != CX_OK) return src;
+    printf("Read %zu facets of special boundary geometry #%d\n", nrm.size() / 3, sbi);
+    sb_corners.push_back(std::move(c));
+  }
+  std::vector<const float *> sb_ptr;
+  std::vector<int64_t> sb_n;
+  for (const auto &c : sb_corners) { sb_ptr.push_back(c.data()); sb_n.push_back((int64_t)(c.size() / 9)); }
+  job.sb_corners = sb_ptr.data(); job.sb_nbe = sb_n.data(); job.nsb = (int32_t)sb_ptr.size();
   std::vector<cx_fill_spec> fills;
   for (int n = 0;; n++) {  // crixus.cu:734-961: fill_0 is always attempted, then while fill_(n+1).option exists
     std::ostringstream sec;
@@ -170,14 +224,18 @@ int cx_run_ini(const char *ini_path)
   const double t_asm = wall_s() - t_a0;
   const std::string fmt = ini.Get("output", "format", "vtu");
   std::string outname = ini.Get("output", "name", cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0));
-  if (fmt == "h5sph") {
-    outname = "0." + outname + ".h5sph";
-    rc = cx_write_h5sph(buf, outname);
+  if (ini.GetBoolean("output", "split", false)) {   // crixus.cu:1135-1207
+    rc = cx_write_split_records(buf.data(), (int64_t)buf.size(), job.nfluid, job.nsb + 1, outname.c_str(), fmt == "h5sph" ? 2 : 1);
   } else {
-    outname += ".vtu";
-    rc = cx_write_vtu(buf, outname);
+    if (fmt == "h5sph") {
+      outname = "0." + outname + ".h5sph";
+      rc = cx_write_h5sph(buf, outname);
+    } else {
+      outname += ".vtu";
+      rc = cx_write_vtu(buf, outname);
+    }
+    printf("Writing output to file %s ... %s\n", outname.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
   }
-  printf("Writing output to file %s ... %s\n", outname.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
   printf("Timing: read STL %.3f s, CUDA context %.3f s, assemble %.3f s, write %.3f s, total %.3f s\n", t_read, t_create, t_asm,
          wall_s() - t_a0 - t_asm, wall_s() - t_start);
   cx_job_free(&job);

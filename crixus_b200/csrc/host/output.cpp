@@ -66,22 +66,33 @@ std::vector<CxOutBuf> cx_assemble(const cx_job &job, int64_t nfluid)
     b.x = job.pos[4 * i]; b.y = job.pos[4 * i + 1]; b.z = job.pos[4 * i + 2];
     b.vol = job.vol[i];
     b.kpar = 2; b.kfluid = 1;
+    b.kent = job.sbid ? job.sbid[i] : 0;   // crixus.cu:1042-1045
     b.iref = (int32_t)buf.size();
     buf.push_back(b);
   }
-  for (int64_t i = 0; i < nbe; i++) {  // crixus.cu:1063-1097 (KENT = 0 everywhere: no reordering)
-    CxOutBuf b = z;
+  // segments: crixus.cu:1056-1097.  With special boundaries they are stably grouped by KENT (counting sort over the ids).
+  const int32_t *sbid = job.sbid;
+  int32_t nk = 1;
+  if (sbid) for (int64_t i = 0; i < nbe; i++) nk = std::max(nk, sbid[nvert + i] + 1);
+  std::vector<int64_t> isbe((size_t)nk + 1, 0);
+  if (sbid) for (int64_t i = 0; i < nbe; i++) isbe[(size_t)sbid[nvert + i] + 1]++;
+  for (int32_t k = 0; k < nk; k++) isbe[(size_t)k + 1] += isbe[(size_t)k];
+  const int64_t ncur = (int64_t)buf.size();
+  buf.resize((size_t)(ncur + nbe), z);
+  for (int64_t i = 0; i < nbe; i++) {
+    const int32_t kent = sbid ? sbid[nvert + i] : 0;
+    const int64_t l = ncur + isbe[(size_t)kent]++;
+    CxOutBuf &b = buf[(size_t)l];
     const float *q = job.pos + 4 * (nvert + i);
     b.x = q[0]; b.y = q[1]; b.z = q[2];
     b.nx = job.norm[4 * i]; b.ny = job.norm[4 * i + 1]; b.nz = job.norm[4 * i + 2];
     b.surf = job.surf[i];
-    b.kpar = 3; b.kfluid = 1;
-    b.iref = (int32_t)buf.size();
+    b.kpar = 3; b.kfluid = 1; b.kent = kent;
+    b.iref = (int32_t)l;
     const int32_t *e = job.ep + 4 * i;
     b.ep1 = (int32_t)nfluid + e[0] - nvshift[e[0]];
     b.ep2 = (int32_t)nfluid + e[1] - nvshift[e[1]];
     b.ep3 = (int32_t)nfluid + e[2] - nvshift[e[2]];
-    buf.push_back(b);
   }
   return buf;
 }

@@ -41,6 +41,36 @@ extern "C" void cx_job_free(cx_job *job)
   job->pos = job->norm = job->surf = job->vol = nullptr;
   job->ep = job->cell_idx = nullptr;
   job->fpos = nullptr;
+  job->sbid = nullptr;
+}
+
+extern "C" int64_t cx_job_sizeof(void) { return (int64_t)sizeof(cx_job); }
+
+// bounding box + weld of a small auxiliary grid (special-boundary STL) on the device; host weld when a cell is over-full
+static int weld_grid(cx_ctx *ctx, cudaStream_t st, const float *corners, int64_t n, float dr, float **pos4_d, int32_t **ep4_d,
+                     int64_t *nvert)
+{
+  float *c_d = nullptr;
+  CU(cudaMallocAsync((void **)&c_d, 36 * (size_t)n, st));
+  CU(cudaMallocAsync((void **)pos4_d, 48 * (size_t)n, st));
+  CU(cudaMallocAsync((void **)ep4_d, 16 * (size_t)n, st));
+  CU(cudaMemcpyAsync(c_d, corners, 36 * (size_t)n, cudaMemcpyHostToDevice, st));
+  float lo[3], hi[3];
+  RC(cx_bbox_device(ctx, c_d, 3 * n, lo, hi));
+  int rc = cx_weld_device(ctx, c_d, 3 * n, dr, lo, hi, *pos4_d, *ep4_d, nvert);
+  if (rc == CX_WELD_CELL_TOO_FULL) {
+    std::vector<float> verts((size_t)9 * n), hp;
+    std::vector<int32_t> ids((size_t)3 * n), he((size_t)4 * n, 0);
+    *nvert = cx_weld_host(corners, 3 * n, dr, verts.data(), ids.data());
+    hp.assign((size_t)4 * *nvert, 0.f);
+    for (int64_t v = 0; v < *nvert; v++) for (int k = 0; k < 3; k++) hp[4 * v + k] = verts[3 * v + k];
+    for (int64_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) he[4 * i + k] = ids[3 * i + k];
+    CU(cudaMemcpy(*pos4_d, hp.data(), 16 * (size_t)*nvert, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*ep4_d, he.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
+    rc = CX_OK;
+  }
+  CU(cudaFreeAsync(c_d, st));
+  return rc;
 }
 
 extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
@@ -97,11 +127,12 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   const int64_t G = job->dimg[0] * job->dimg[1] * job->dimg[2];
   const int64_t nwords = (G + 31) / 32;
   const int64_t fsn = (job->fs_nbe > 0 && job->fs_corners && job->fs_normals) ? job->fs_nbe : 0;
+  const int nsb = (job->nsb > 0 && job->sb_corners && job->sb_nbe) ? job->nsb : 0;
 
   // ---- one device block and one pinned host block, carved into the working set (no per-call cudaMalloc)
   t0 = now_s();
   Bump db, hb;
-  Buf pre_pos, pos, pre_norm, norm, pre_ep, ep, pre_surf, surf, cell_idx, trisize, vol, newlink, norm3, fpos, fnorm, fep, fposv;
+  Buf pre_pos, pos, pre_norm, norm, pre_ep, ep, pre_surf, surf, cell_idx, trisize, vol, newlink, norm3, fpos, fnorm, fep, fposv, sbid;
   pre_pos.off = db.take(16 * (size_t)(nvert + nbe)); pos.off = db.take(16 * (size_t)(nvert + nbe));
   pre_norm.off = db.take(16 * (size_t)nbe); norm.off = db.take(16 * (size_t)nbe);
   pre_ep.off = db.take(16 * (size_t)nbe); ep.off = db.take(16 * (size_t)nbe);
@@ -113,14 +144,16 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     fnorm.off = db.take(16 * (size_t)(nbe + fsn)); fep.off = db.take(16 * (size_t)(nbe + fsn));
     fposv.off = db.take(16 * (size_t)(nvert + 3 * fsn));
   }
+  if (nsb) sbid.off = db.take(4 * (size_t)(nvert + nbe));
   char *dbase = (char *)cx_internal_dev_arena(ctx, db.off + 256);
   if (!dbase) return CX_CUDA_ERROR;
   for (Buf *b : {&pre_pos, &pos, &pre_norm, &norm, &pre_ep, &ep, &pre_surf, &surf, &cell_idx, &trisize, &vol, &newlink, &norm3, &fpos,
-                 &fnorm, &fep, &fposv})
+                 &fnorm, &fep, &fposv, &sbid})
     b->p = dbase + b->off;
   const size_t o_pos = hb.take(16 * (size_t)(nvert + nbe)), o_norm = hb.take(16 * (size_t)nbe), o_ep = hb.take(16 * (size_t)nbe),
                o_surf = hb.take(4 * (size_t)nbe), o_vol = hb.take(4 * (size_t)nvert), o_cell = hb.take(4 * (size_t)(ncell + 1)),
-               o_fpos = hb.take(4 * (size_t)nwords), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0);
+               o_fpos = hb.take(4 * (size_t)nwords), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0),
+               o_sbid = hb.take(nsb ? 4 * (size_t)(nvert + nbe) : 0);
   char *hbase = (char *)cx_internal_host_arena(ctx, hb.off + 256);
   if (!hbase) return CX_CUDA_ERROR;
   if (job->welded_pos) {
@@ -179,8 +212,29 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
                          cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
 
   CU(cudaEventRecord(ev[5], st));
-  // ---- fluid (crixus.cu:463-467, 698-961)
-  cx_params_fill_eps(&p);
+  cx_params_fill_eps(&p);   // crixus.cu:463-467
+  // ---- special-boundary grids #1..nsb (crixus.cu:469-617); a later grid overwrites the ids of an earlier one
+  job->sbid = nullptr;
+  if (nsb) {
+    CU(cudaMemsetAsync(sbid.p, 0, 4 * (size_t)(nvert + nbe), st));
+    for (int k = 0; k < nsb; k++) {
+      if (job->sb_nbe[k] <= 0 || !job->sb_corners[k]) continue;
+      float *sp = nullptr;
+      int32_t *se = nullptr;
+      int64_t snv = 0;
+      RC(weld_grid(ctx, st, job->sb_corners[k], job->sb_nbe[k], dr, &sp, &se, &snv));
+      RC(cx_identify_special_boundary(ctx, &p, pos.as<float>(), ep.as<int32_t>(), cell_idx.as<int32_t>(), nvert, nbe, sp, se,
+                                      job->sb_nbe[k], sbid.as<int32_t>(), k + 1));
+      CU(cudaFreeAsync(sp, st));
+      CU(cudaFreeAsync(se, st));
+    }
+    job->sbid = (int32_t *)(hbase + o_sbid);
+    CU(cudaEventRecord(cs.e, st));
+    CU(cudaStreamWaitEvent(cst, cs.e, 0));
+    CU(cudaMemcpyAsync(job->sbid, sbid.p, 4 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
+  }
+  CU(cudaEventRecord(ev[6], st));
+  // ---- fluid (crixus.cu:698-961)
   cx_params_container(&p, job->use_container, job->cmin, job->cmax);
   job->nfluid_counted = 0;
   bool have_fs = false;
@@ -228,10 +282,12 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
       job->nfluid_counted += nfi;
     }
   }
-  CU(cudaEventRecord(ev[6], st));
+  CU(cudaEventRecord(ev[7], st));
   RC(cx_synchronize(ctx));
   job->t_gpu_s = now_s() - t0;
-  for (int k = 0; k < 6; k++) { CU(cudaEventElapsedTime(&job->stage_ms[k], ev[k], ev[k + 1])); }
+  for (int k = 0; k < 5; k++) { CU(cudaEventElapsedTime(&job->stage_ms[k], ev[k], ev[k + 1])); }
+  CU(cudaEventElapsedTime(&job->stage_ms[5], ev[6], ev[7]));
+  CU(cudaEventElapsedTime(&job->stage_ms[6], ev[5], ev[6]));
   for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
   job->params_fill = p;
 

@@ -149,6 +149,16 @@ int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const f
                       const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                       int64_t *nfi_host, int32_t *rounds_host);
 
+/* identifySpecialBoundarySegments, crixus_d.cu:1085-1112 (+ segInTri :1060-1083): segments whose barycentre lies in a
+ * triangle of the special-boundary grid (sbpos float4[sbnvert], sbep int4[sbnbe], welded like the main mesh,
+ * crixus.cu:560) get sbid[nvert+seg] = sbi, and so do their three vertices.  sbid_d: int[nvert+nbe], zeroed by the caller
+ * before the first grid (crixus.cu:590-597).  p->eps must be the fill eps (cx_params_fill_eps; crixus.cu:464-467 runs
+ * first).  pos/ep/cell_idx are the cell-sorted arrays of cx_bin_segments: each grid triangle is only tested against the
+ * 3dr-cells its grown bounding box touches instead of all nbe segments. */
+int cx_identify_special_boundary(cx_ctx *ctx, const cx_params *p, const float *pos_d, const int32_t *ep_d,
+                                 const int32_t *cell_idx_d, int64_t nvert, int64_t nbe, const float *sbpos_d,
+                                 const int32_t *sbep_d, int64_t sbnbe, int32_t *sbid_d, int32_t sbi);
+
 /* ---- whole hot path on HOST buffers (the call the CLI / a reference maintainer would make; includes H2D/D2H) */
 typedef struct cx_fill_spec {
   int32_t option;      /* 1 = box, 2 = geometry (crixus.cu:737-741) */
@@ -173,20 +183,24 @@ typedef struct cx_job {
   int32_t use_container; float cmin[3], cmax[3];
   const float *fs_corners; const float *fs_normals; int64_t fs_nbe; /* optional fshape STL */
   const cx_fill_spec *fills; int32_t nfills;
+  /* optional special-boundary grids #1..nsb (crixus.cu:469-617): sb_corners[k] = sb_nbe[k]*9 floats, raw STL corners */
+  const float *const *sb_corners; const int64_t *sb_nbe; int32_t nsb;
   /* outputs: they live in a pinned host arena owned by the context and stay valid until the next cx_preprocess_host on
    * the same context (or cx_destroy); cx_job_free only clears the pointers */
   int64_t nvert, nfluid, nfluid_counted; /* popcount vs. the reference's running count (App. B-2 of SURVEY.md) */
   float *pos;  float *norm;  int32_t *ep;  float *surf;  float *vol;  int32_t *cell_idx; uint32_t *fpos;
+  int32_t *sbid; /* int[nvert+nbe]: special-boundary id (KENT) of vertices, then segments; NULL when nsb == 0 */
   int64_t dimg[3];
   float zstat[4];
   cx_params params_fill;
   int64_t tri_failed; float tri_mind, tri_maxd; /* mesh precondition (cx_check_triangle_size), filled when raw corners are given */
   double t_weld_s, t_gpu_s, t_h2d_s, t_d2h_s; /* wall-clock breakdown */
-  float stage_ms[8]; /* CUDA-event times: 0 swap+set_bound_elem, 1 binning, 2 periodic links, 3 trisize, 4 vert volume, 5 fills */
+  float stage_ms[8]; /* CUDA-event times: 0 swap+set_bound_elem, 1 binning, 2 periodic links, 3 trisize, 4 vert volume, 5 fills, 6 special-boundary tagging */
 } cx_job;
 
 int cx_preprocess_host(cx_ctx *ctx, cx_job *job);
 void cx_job_free(cx_job *job);
+int64_t cx_job_sizeof(void); /* sizeof(cx_job) of the library, for bindings to check their mirror of the struct */
 
 /* bounding box of the raw STL corners (src/crixus.cu:185-208) and vertex weld (remove_duplicate_vertices,
  * src/crixus.cpp:343-455) on the device: cell keys -> stable radix sort -> one thread per cell replays the claim loop ->
@@ -222,10 +236,15 @@ int cx_stl_read(const char *filename, float **corners, float **normals, int64_t 
 void cx_free(void *p);
 
 /* particle records, src/crixus.cu:973-1097: 64-byte OutBuf records (src/crixus.h:33-36) -- fluid particles in bit order,
- * alive vertices in index order, segments in sorted order.  Returns the record count (records may be NULL to size). */
+ * alive vertices in index order, segments in sorted order, stably grouped by KENT when special boundaries are present
+ * (crixus.cu:1088-1097).  Returns the record count (records may be NULL to size). */
 int64_t cx_assemble_records(const cx_job *job, int64_t nfluid_for_indices, void *records, int64_t capacity);
 int cx_write_vtu_records(const void *records, int64_t n, const char *filename);   /* vtk_output, src/crixus.cpp:62-259 */
 int cx_write_h5sph_records(const void *records, int64_t n, const char *filename); /* hdf5_output, src/crixus.cpp:12-60 */
+/* [output] split=true, src/crixus.cu:1137-1216: <outname>.fluid.<ext> holds the fluid particles, <outname>.boundary.kent<k>.<ext>
+ * the vertex and segment records of special-boundary id k (k < num_kents, files without particles are skipped);
+ * format 1 = vtu, 2 = h5sph (generic_output, src/crixus.cpp:261-289: "0." prefix and ".h5sph" suffix for h5sph). */
+int cx_write_split_records(const void *records, int64_t n, int64_t nfluid_particles, int32_t num_kents, const char *outname, int format);
 
 /* what `Crixus file.ini` does (crixus_main, src/crixus.cu:31-1237, hot path only): ini -> STL -> GPU -> output file */
 int cx_run_ini(const char *ini_path);

@@ -289,6 +289,61 @@ void orc_periodicity_links(int32_t *ep, int64_t nbe, const int32_t *newlink)
       if (newlink[ep[4 * i + j]] != -1) ep[4 * i + j] = newlink[ep[4 * i + j]];
 }
 
+/* ------------------------------------------------------------------------------------------------ special boundaries
+ * identifySpecialBoundarySegments + segInTri, src/crixus_d.cu:1060-1112, with the multiply-add fusion of the reference's
+ * sm_100 SASS: cross products a*b-c*d -> fma(a,b,-(c*d)); every "dot += x*y" chain -> fma chain from 0;
+ * 1.0/det -> correctly rounded float reciprocal; eps = the fill eps (crixus.cu:464-467 runs before the loop :469-642).
+ * sbid: int[nvert+nbe] (vertices, then segments); a segment whose barycentre lies in a special-boundary triangle gets sbi,
+ * and so do its three vertices. */
+static int orc_seg_in_tri(const float vb[3][3], const float spos[3], const float norm[4], float eps)
+{
+  float pa[3], ba[3], ca[3];
+  for (int i = 0; i < 3; i++) { ba[i] = vb[1][i] - vb[0][i]; ca[i] = vb[2][i] - vb[0][i]; pa[i] = spos[i] - vb[0][i]; }
+  float d = fmaf(norm[2], pa[2], fmaf(norm[1], pa[1], fmaf(norm[0], pa[0], 0.0f)));
+  if (fabsf(d) > eps * norm[3]) return 0;                                     /* :1065 */
+  const float dot00 = fmaf(ba[2], ba[2], fmaf(ba[1], ba[1], fmaf(ba[0], ba[0], 0.0f)));
+  const float dot01 = fmaf(ca[2], ba[2], fmaf(ba[1], ca[1], fmaf(ca[0], ba[0], 0.0f)));
+  const float dot02 = fmaf(ba[2], pa[2], fmaf(ba[1], pa[1], fmaf(ba[0], pa[0], 0.0f)));
+  const float dot11 = fmaf(ca[2], ca[2], fmaf(ca[1], ca[1], fmaf(ca[0], ca[0], 0.0f)));
+  const float dot12 = fmaf(ca[2], pa[2], fmaf(ca[1], pa[1], fmaf(ca[0], pa[0], 0.0f)));
+  const float det = fmaf(dot00, dot11, -(dot01 * dot01));
+  const float invdet = 1.0f / det;                                            /* :1078 */
+  const float u = fmaf(dot02, dot11, -(dot01 * dot12)) * invdet;
+  const float v = fmaf(dot00, dot12, -(dot01 * dot02)) * invdet;
+  if (u < -eps || v < -eps || u + v > 1 + eps) return 0;                      /* :1081 */
+  return 1;
+}
+
+void orc_identify_special_boundary(const orc_params *p, const float *pos, const int32_t *ep, int64_t nvert, int64_t nbe,
+                                   const float *sbpos, const int32_t *sbep, int64_t sbnbe, int32_t *sbid, int32_t sbi)
+{
+  const float eps = p->eps;
+#pragma omp parallel for schedule(static)
+  for (int64_t id = 0; id < nbe; id++) {
+    const float *spos = pos + 4 * (nvert + id);
+    for (int64_t i = 0; i < sbnbe; i++) {
+      float vb[3][3], norm[4];
+      for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) vb[j][k] = sbpos[4 * (int64_t)sbep[4 * i + j] + k];
+      norm[3] = 0.0f;
+      for (int j = 0; j < 3; j++) {                                           /* :1096-1100 */
+        const int a = (j + 1) % 3, b = (j + 2) % 3;
+        norm[j] = fmaf(vb[1][a] - vb[0][a], vb[2][b] - vb[0][b], -((vb[1][b] - vb[0][b]) * (vb[2][a] - vb[0][a])));
+        norm[3] += norm[j];
+      }
+      norm[3] = fabsf(norm[3]);
+      if (orc_seg_in_tri(vb, spos, norm, eps)) {
+        sbid[nvert + id] = sbi;
+        for (int j = 0; j < 3; j++) {
+#pragma omp atomic write
+          sbid[ep[4 * id + j]] = sbi;
+        }
+        break;
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------ mesh precondition
  * resources/test-triangle-size.c:24,38-58: every vertex-barycentre distance must be <= dr - 1e-4*dr.
  * corners: ntri*9 floats (STL order).  out[0] = min distance, out[1] = max distance; returns the number of failures. */

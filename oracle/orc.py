@@ -65,6 +65,7 @@ class Oracle:
         L.orc_find_links.restype = C.c_int64
         L.orc_periodicity_links.argtypes = [i32p, C.c_int64, i32p]
         L.orc_calc_trisize.argtypes = [i32p, i32p, C.c_int64]
+        L.orc_identify_special_boundary.argtypes = [P, f32p, i32p, C.c_int64, C.c_int64, f32p, i32p, C.c_int64, i32p, C.c_int32]
         L.orc_triangle_size.argtypes = [f32p, C.c_int64, C.c_float, f32p]
         L.orc_triangle_size.restype = C.c_int64
         L.orc_calc_vert_volume.argtypes = [P, f32p, f32p, i32p, f32p, i32p, i32p, C.c_int64, C.c_int64, C.c_int]
@@ -131,6 +132,10 @@ class Oracle:
     def periodicity_links(self, p, pos, ep, nvert, nbe, newlink, idim):
         self.L.orc_periodicity_links(ep, nbe, newlink)
 
+    def identify_special_boundary(self, p, pos, ep, nvert, nbe, sbpos, sbep, sbid, sbi, cell_idx=None):
+        """identifySpecialBoundarySegments (crixus_d.cu:1085-1112); sbid int32[nvert+nbe] is updated in place"""
+        self.L.orc_identify_special_boundary(C.byref(p), pos, ep, nvert, nbe, sbpos, sbep, sbep.shape[0], sbid, sbi)
+
     def triangle_size(self, corners, dr):
         """resources/test-triangle-size.c -> (failures, min distance, max distance)"""
         corners = np.ascontiguousarray(corners, dtype=np.float32).reshape(-1)
@@ -193,6 +198,7 @@ class RefShim(Oracle):
         R.refshim_find_links.argtypes = [f32p, C.c_int, i32p, C.c_int]
         R.refshim_periodicity_links.argtypes = [f32p, i32p, C.c_int, C.c_int, i32p, C.c_int]
         R.refshim_calc_trisize.argtypes = [i32p, i32p, C.c_int]
+        R.refshim_identify_sb.argtypes = [f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, i32p, C.c_int]
         R.refshim_calc_vert_volume.argtypes = [f32p, f32p, i32p, f32p, i32p, i32p, C.c_int, C.c_int, C.c_int]
         R.refshim_fill_fluid.argtypes = [u32p] + [C.c_float] * 6
         R.refshim_fill_fluid.restype = C.c_uint
@@ -241,6 +247,10 @@ class RefShim(Oracle):
     def periodicity_links(self, p, pos, ep, nvert, nbe, newlink, idim):
         self.R.refshim_periodicity_links(pos, ep, nvert, nbe, newlink, idim)
 
+    def identify_special_boundary(self, p, pos, ep, nvert, nbe, sbpos, sbep, sbid, sbi, cell_idx=None):
+        self._consts(p)
+        self.R.refshim_identify_sb(pos, ep, nvert, nbe, sbpos, sbep, sbep.shape[0], sbid, sbi)
+
     def calc_trisize(self, p, ep, nvert, nbe):
         t = np.zeros(nvert, dtype=np.int32)
         self.R.refshim_calc_trisize(ep, t, nbe)
@@ -279,11 +289,12 @@ def f4(a3, n=None):
 
 
 def run_pipeline(B, tris, normals, dr, swap_normals=False, periodic=(False, False, False), zero_open=False,
-                 container=None, fills=(), fshape=None, stages=("volume", "fill")):
+                 container=None, fills=(), fshape=None, stages=("volume", "fill"), special=()):
     """The hot path of crixus_main (/root/reference/src/crixus.cu:184-961) on backend B (Oracle or RefShim).
 
     tris (n,3,3) / normals (n,3): the STL content.  fills: list of ("box", lo, hi) or ("geometry", seed, dr_wall).
-    fshape: optional (tris, normals) of the free-surface STL.  Returns a dict of all stage outputs."""
+    fshape: optional (tris, normals) of the free-surface STL.  special: list of (n,3,3) corner arrays, the special-boundary
+    grids #1, #2, ... (crixus.cu:469-617).  Returns a dict of all stage outputs."""
     tris = np.ascontiguousarray(tris, dtype=np.float32)
     nbe = tris.shape[0]
     corners = tris.reshape(-1, 3)
@@ -317,9 +328,20 @@ def run_pipeline(B, tris, normals, dr, swap_normals=False, periodic=(False, Fals
     if "volume" in stages:
         out["vol"] = B.calc_vert_volume(p, pos, norm, ep, trisize, cell_idx, nvert, nbe, zero_open)  # :437
     out["params_volume"] = p.copy()
-    if "fill" not in stages:
+    if "fill" not in stages and not len(special):
         return out
     B.params_fill_eps(p)                                           # :464-467
+    if len(special):                                               # :469-617
+        sbid = np.zeros(nvert + nbe, dtype=np.int32)
+        for k, sb_t in enumerate(special):
+            sb_v, sb_e = B.weld(np.ascontiguousarray(sb_t, dtype=np.float32).reshape(-1, 3), np.float32(dr))   # :560
+            sb_ep = np.zeros((sb_e.shape[0], 4), dtype=np.int32)
+            sb_ep[:, :3] = sb_e
+            B.identify_special_boundary(p, pos, ep, nvert, nbe, f4(sb_v), sb_ep, sbid, k + 1, cell_idx=cell_idx)   # :606
+        out["sbid"] = sbid
+    if "fill" not in stages:
+        out["params_fill"] = p.copy()
+        return out
     if container is not None:                                      # :698-722
         B.params_container(p, True, container[0], container[1])
     else:

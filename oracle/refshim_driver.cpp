@@ -97,6 +97,12 @@ void refshim_periodicity_links(float *pos, int *ep, int nvert, int nbe, int *new
   launch(0, [&] { crixus_d::periodicity_links((uf4 *)pos, (ui4 *)ep, nvert, nbe, newlink, idim); });
 }
 
+// identifySpecialBoundarySegments (crixus_d.cu:1085-1112); eps must have been set through refshim_set_consts
+void refshim_identify_sb(float *pos, int *ep, int nvert, int nbe, float *sbpos, int *sbep, int sbnbe, int *sbid, int sbi)
+{
+  launch(0, [&] { crixus_d::identifySpecialBoundarySegments((uf4 *)pos, (ui4 *)ep, nvert, nbe, (uf4 *)sbpos, (ui4 *)sbep, sbnbe, sbid, sbi); });
+}
+
 void refshim_calc_trisize(int *ep, int *trisize, int nbe)
 {
   launch(0, [&] { crixus_d::calc_trisize((ui4 *)ep, trisize, nbe); });

@@ -86,6 +86,12 @@ class CudaBackend:
                                   zero_open, v0, v1)
         return vol.cpu().numpy()
 
+    def identify_special_boundary(self, p, pos, ep, nvert, nbe, sbpos, sbep, sbid, sbi, cell_idx=None):
+        d = self._d(sbid)
+        self.ctx.identify_special_boundary(p, self._d(pos), self._d(ep), self._d(cell_idx), nvert, nbe, self._d(sbpos), self._d(sbep),
+                                           sbep.shape[0], d, sbi)
+        sbid[...] = d.cpu().numpy()
+
     def fill_box(self, p, fpos, lo, hi):
         d = self._d(fpos.view(np.int32))
         n = self.ctx.fill_box(p, d, lo, hi)

@@ -22,7 +22,7 @@ _PLATE_FILL = dict(container=((0, 0, 0), (1.0, 1.0, 0.2)), fills=[("box", (0.4, 
 
 def case(name):
     """-> dict(tris, normals, dr, swap_normals, periodic, zero_open, container, fills, fshape)"""
-    c = dict(swap_normals=False, periodic=(False, False, False), zero_open=False, container=None, fills=[], fshape=None)
+    c = dict(swap_normals=False, periodic=(False, False, False), zero_open=False, container=None, fills=[], fshape=None, special=[])
     if name == "plate":            # KAT-plate, SURVEY.md App. D.3
         v, t, n = mg.plate(10, 0.1)
         c.update(dr=0.08, **_PLATE_FILL)
@@ -103,6 +103,30 @@ def case(name):
         dr = 0.05
         v, t, n = mg.sphere_in_tank(side_cells=20, dr=dr, hfac=1.0, sphere_levels=2)
         c.update(dr=dr, swap_normals=True, fills=[("geometry", (0.1, 0.1, 0.1), dr)])
+    elif name == "cube_sb":        # special-boundary grids (crixus.cu:469-617): inlet patch on x=0, slanted fan on the lid, and a
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)   # third grid overlapping the first (later ids overwrite)
+        def rect_x0(y0, y1, z0, z1):
+            return np.array([[[0, y0, z0], [0, y1, z0], [0, y1, z1]], [[0, y0, z0], [0, y1, z1], [0, y0, z1]]], dtype=np.float32)
+        ring = np.array([[0.3, 0.3, 1], [0.8, 0.35, 1], [0.7, 0.8, 1], [0.25, 0.7, 1]], dtype=np.float32)
+        ctr = np.array([0.5, 0.5, 1], dtype=np.float32)
+        fan = np.array([[ctr, ring[i], ring[(i + 1) % 4]] for i in range(4)], dtype=np.float32)
+        c.update(dr=0.08, fills=[("geometry", (0.5, 0.5, 0.5), 0.08)], special=[rect_x0(0.2, 0.6, 0.2, 0.5), fan, rect_x0(0.5, 0.8, 0.2, 0.5)])
+    elif name == "sphere_sb":      # special-boundary grid coincident with curved mesh triangles (the upper half of the sphere):
+        dr = 0.05                  # plane test |n.(b-v0)| <= eps*|nx+ny+nz| on un-normalised normals, marginal near nx+ny+nz = 0
+        v, t, n = mg.sphere_in_tank(side_cells=20, dr=dr, hfac=1.0, sphere_levels=2)
+        tr = v[t]
+        mid = 0.5 * (v.min(0) + v.max(0))
+        on_sphere = (np.abs(tr - mid).max(axis=(1, 2)) < 0.45 * float((v.max(0) - v.min(0)).max()))
+        upper = on_sphere & (tr[:, :, 2].mean(1) > mid[2])
+        c.update(dr=dr, swap_normals=True, fills=[("geometry", (0.1, 0.1, 0.1), dr)], special=[np.ascontiguousarray(tr[upper])])
+    elif name == "plate_sb_stress":   # adversarial special-boundary grids (special_stress below), incl. the rounding-sensitive kinds
+        v, t, n = mg.plate(24, 0.1)
+        v = v.copy()
+        v[:, 2] += np.float32(0.013)
+        v = _lcg_jitter(v, t, n, 0.01, 0.0025)
+        n = mg.geometric_normals(v, t)
+        sb = special_stress(v[t], 7, n=240)
+        c.update(dr=0.08, special=[sb[:120], sb[120:]], **_PLATE_FILL)
     else:
         raise KeyError(name)
     c.update(name=name, tris=np.ascontiguousarray(v[t], dtype=np.float32), normals=np.ascontiguousarray(n, dtype=np.float32),
@@ -110,10 +134,50 @@ def case(name):
     return c
 
 
-ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "channel_yz", "cube_fs_bad", "sphere_tank"]
+ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "channel_yz", "cube_fs_bad", "sphere_tank", "cube_sb", "sphere_sb", "plate_sb_stress"]
 
 
 def run(B, c, stages=("volume", "fill")):
     from oracle import orc
     return orc.run_pipeline(B, c["tris"], c["normals"], c["dr"], swap_normals=c["swap_normals"], periodic=c["periodic"],
-                            zero_open=c["zero_open"], container=c["container"], fills=c["fills"], fshape=c["fshape"], stages=stages)
+                            zero_open=c["zero_open"], container=c["container"], fills=c["fills"], fshape=c["fshape"], stages=stages,
+                            special=c.get("special", ()))
+
+
+def special_stress(tris, seed, n=160, skip=()):
+    """Adversarial special-boundary grid for a mesh: triangles built around segment barycentres so
+    that the barycentre sits at chosen barycentric coordinates (corner, edge, just inside / outside the eps bands of
+    segInTri, crixus_d.cu:1065,1081), lifted out of the plane by multiples of eps, with edge lengths from 0.02 to 3 domain
+    sizes; plus slivers (kind 3), zero-area triangles (4) and normals whose components sum to zero (5: norm.a[3] = 0,
+    crixus_d.cu:1099-1101).  Kinds 1, 6 (u+v = 1+eps can be hit exactly) and 3 are rounding-sensitive: their outcome depends on
+    the compiler's multiply-add fusion, so only the reference CUDA binary (golden fixture) pins them."""
+    rng = np.random.default_rng(1000 + seed)
+    tris = np.asarray(tris, dtype=np.float64)
+    bary = tris.mean(1)
+    nbe = bary.shape[0]
+    ext = float((tris.reshape(-1, 3).max(0) - tris.reshape(-1, 3).min(0)).max())
+    eps = 1e-5 * ext
+    out = []
+    for k in range(n):
+        b = bary[rng.integers(nbe)]
+        kind = k % 8
+        size = ext * 10 ** rng.uniform(-1.7, 0.5)
+        e1 = rng.normal(size=3)
+        e1 /= np.linalg.norm(e1)
+        e2 = rng.normal(size=3)
+        e2 -= e2.dot(e1) * e1
+        e2 /= np.linalg.norm(e2)
+        if kind == 5:                      # normal (1,-1,0)/sqrt2: components sum to zero
+            e1, e2 = np.array([1.0, 1.0, 0.0]) / np.sqrt(2), np.array([0.0, 0.0, 1.0])
+        if kind == 6:                      # axis-aligned, in the plane of a wall
+            e1, e2 = np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0])
+        ba, ca = size * e1, size * rng.uniform(0.3, 1.5) * (0.3 * e1 + e2) if kind != 3 else size * (e1 + 1e-4 * e2)   # 3: sliver
+        if kind == 4:
+            ca = 2.0 * ba                  # zero area
+        u, v = [(0.0, 0.0), (0.5, 0.5), (0.3, 0.0), (1 / 3, 1 / 3), (0.2, 0.2), (0.25, 0.25), (0.0, 1.0), (0.6, 0.1)][kind]
+        du, dv = rng.choice([-1.5, -0.5, 0.0, 0.5, 1.5], size=2) * eps
+        lift = rng.choice([0.0, 0.0, 0.3, 0.9, 1.1, 3.0]) * eps * np.cross(e1, e2)
+        v0 = b - (u + du) * ba - (v + dv) * ca - lift
+        if kind not in skip:
+            out.append([v0, v0 + ba, v0 + ca])
+    return np.ascontiguousarray(np.array(out), dtype=np.float32)

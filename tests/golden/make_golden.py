@@ -24,7 +24,7 @@ from crixus_b200 import meshgen as mg  # noqa: E402
 from vtu import read_vtu, split_particles  # noqa: E402
 
 
-def write_ini(path, c, stl, fshape_path):
+def write_ini(path, c, stl, fshape_path, sb_paths=(), split=False):
     L = ["[mesh]", "stlfile=%s" % stl, "dr=%.9g" % float(c["dr"]), "swap_normals=%s" % ("true" if c["swap_normals"] else "false"),
          "zeroOpen=%s" % ("true" if c["zero_open"] else "false")]
     if fshape_path:
@@ -41,8 +41,20 @@ def write_ini(path, c, stl, fshape_path):
                  ["%smax=%.9g" % (a, f[2][i]) for i, a in enumerate("xyz")]
         else:
             L += ["option=geometry"] + ["%sseed=%.9g" % (a, f[1][i]) for i, a in enumerate("xyz")] + ["dr_wall=%.9g" % float(f[2])]
-    L += ["[output]", "format=vtu", "name=%s" % c["name"]]
+    if sb_paths:
+        L += ["[special_boundary_grids]"] + ["mesh%d=%s" % (k + 1, sp) for k, sp in enumerate(sb_paths)]
+    L += ["[output]", "format=vtu", "name=%s" % c["name"]] + (["split=true"] if split else [])
     open(path, "w").write("\n".join(L) + "\n")
+
+
+def write_special(work, c):
+    """the special-boundary grids of a case as binary STL files (facet normals are not read, crixus.cu:538-556)"""
+    paths = []
+    for k, sb in enumerate(c.get("special", ())):
+        sp = os.path.join(work, "%s_sbgrid_%d.stl" % (c["name"], k + 1))
+        mg.write_stl(sp, sb, np.zeros((sb.shape[0], 3), dtype=np.float32))
+        paths.append(sp)
+    return paths
 
 
 def canonical_segments(seg):
@@ -65,8 +77,9 @@ def main(outdir):
         if c["fshape"] is not None:
             fsp = os.path.join(work, name + "_fs.stl")
             mg.write_stl(fsp, c["fshape"][0], c["fshape"][1])
+        sbp = write_special(work, c)
         ini = os.path.join(work, name + ".ini")
-        write_ini(ini, c, stl, fsp)
+        write_ini(ini, c, stl, fsp, sbp)
         log = subprocess.run([exe, ini], cwd=work, capture_output=True, text=True, timeout=1200)
         open(os.path.join(work, name + ".log"), "w").write(log.stdout + log.stderr)
         d = split_particles(read_vtu(os.path.join(work, name + ".vtu")))
@@ -75,6 +88,8 @@ def main(outdir):
                             vert_pos=d["vertex"]["Points"].astype(np.float32), vert_vol=d["vertex"]["Volume"],
                             seg_pos=seg["Points"].astype(np.float32), seg_norm=seg["Normal"], seg_surf=seg["Surface"],
                             seg_ep=seg["VertexParticle"].astype(np.int64), fluid_pos=d["fluid"]["Points"].astype(np.float32),
+                            vert_kent=d["vertex"]["KENT"].astype(np.int32), seg_kent=seg["KENT"].astype(np.int32),
+                            seg_kent_file_order=d["segment"]["KENT"].astype(np.int32),
                             fluid_vol=d["fluid"]["Volume"][:1], n_file=np.int64(read_vtu(os.path.join(work, name + ".vtu"))["n"]),
                             log=np.array(log.stdout))
         print(name, "verts", d["vertex"]["Points"].shape[0], "segs", seg["Points"].shape[0], "fluid", d["fluid"]["Points"].shape[0], flush=True)

@@ -18,6 +18,9 @@ def assemble(g):
     out["seg_pos"] = g["pos"][nv:, :3]
     out["seg_norm"] = g["norm"][:, :3]
     out["seg_surf"] = g["surf"]
+    sbid = g["sbid"] if "sbid" in g else np.zeros(nv + nbe, dtype=np.int32)
+    out["vert_kent"] = sbid[:nv][alive]           # crixus.cu:1042-1045
+    out["seg_kent"] = sbid[nv:]                   # crixus.cu:1072-1077
     if p is not None:
         d = g["dimg"]
         bits = np.unpackbits(g["fpos"].view(np.uint8), bitorder="little")[: int(d[0] * d[1] * d[2])]
@@ -58,6 +61,13 @@ def compare_with_golden(g, gold, c, vol_exact=True):
     np.testing.assert_array_equal(a["seg_pos"], gold["seg_pos"])
     np.testing.assert_array_equal(a["seg_norm"], gold["seg_norm"])
     np.testing.assert_array_equal(a["seg_surf"], gold["seg_surf"])
+    if "seg_kent" in gold.files:                  # special-boundary ids (fixtures made before that stage existed have none)
+        np.testing.assert_array_equal(a["vert_kent"], gold["vert_kent"])
+        np.testing.assert_array_equal(a["seg_kent"], gold["seg_kent"])
+        fo = gold["seg_kent_file_order"]          # the file holds the segments grouped by id (crixus.cu:1088-1097)
+        assert (np.diff(fo) >= 0).all()
+    else:
+        assert not a["seg_kent"].any() and not a["vert_kent"].any()
     gv, ov = a["vert_vol"], gold["vert_vol"]
     q = float(np.float32(c["dr"]) / 40) ** 3
     nbad = int((gv != ov).sum())

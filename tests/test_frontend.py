@@ -213,3 +213,109 @@ def test_run_ini_without_config_or_gpu(cxlib, tmp_path, capfd):
     ini = _write(tmp_path, "[mesh]\nstlfile=%s\ndr=0.1\n" % (tmp_path / "missing.stl"))
     assert cxlib.cx_run_ini(ini.encode()) == -3                        # FILE_NOT_OPEN
     capfd.readouterr()
+
+
+def _host_job(nv, nbe, dimg, seed=0, sb=True):
+    """A cx_job holding synthetic RESULT arrays (as cx_preprocess_host leaves them) for the CPU-only assembly tests."""
+    rng = np.random.default_rng(seed)
+    keep = {}
+    keep["pos"] = rng.standard_normal((nv + nbe, 4)).astype(np.float32)
+    keep["pos"][rng.integers(0, nv, max(nv // 10, 1)), 0] = np.float32(-1e10)        # periodic-deleted vertices
+    alive = np.nonzero(keep["pos"][:nv, 0] > -1e9)[0]
+    keep["norm"] = rng.standard_normal((nbe, 4)).astype(np.float32)
+    ep = np.zeros((nbe, 4), dtype=np.int32)
+    ep[:, :3] = alive[rng.integers(0, alive.size, (nbe, 3))]
+    keep["ep"] = ep
+    keep["surf"] = rng.random(nbe).astype(np.float32)
+    keep["vol"] = rng.random(nv).astype(np.float32)
+    G = int(np.prod(dimg))
+    bits = rng.random(G) < 0.3
+    keep["fpos"] = np.packbits(np.concatenate([bits, np.zeros((-G) % 32, dtype=bool)]), bitorder="little").view(np.uint32).copy()
+    keep["sbid"] = rng.integers(0, 4, nv + nbe).astype(np.int32)
+    job = api.CxJob()
+    job.nbe, job.nvert, job.dr, job.nfluid = nbe, nv, 0.05, int(bits.sum())
+    for k, t in (("pos", C.c_float), ("norm", C.c_float), ("ep", C.c_int32), ("surf", C.c_float), ("vol", C.c_float), ("fpos", C.c_uint32)):
+        setattr(job, k, keep[k].ctypes.data_as(C.POINTER(t)))
+    if sb:
+        job.sbid = keep["sbid"].ctypes.data_as(C.POINTER(C.c_int32))
+    for j in range(3):
+        job.dimg[j] = dimg[j]
+        job.params_fill.fcmin[j] = 0.1 * (j + 1)
+    job.params_fill.dr = 0.05
+    return job, keep, bits
+
+
+@pytest.mark.parametrize("sb", [False, True])
+def test_assemble_records_kent_grouping(sb, cxlib):
+    """cx_assemble_records against a numpy restatement of crixus.cu:973-1097: fluid particles in bit order, alive vertices with
+    KENT = sbid, segments stably grouped by KENT (counting sort :1088-1097), AbsoluteIndex = final position,
+    VertexParticle = nfluid + v - (deleted vertices before v)."""
+    nv, nbe, dimg = 120, 300, (7, 5, 4)
+    job, keep, bits = _host_job(nv, nbe, dimg, seed=4, sb=sb)
+    nfl = int(bits.sum())
+    n = cxlib.cx_assemble_records(C.byref(job), nfl, None, 0)
+    rec = np.zeros(n, dtype=REC)
+    assert cxlib.cx_assemble_records(C.byref(job), nfl, rec.ctypes.data, n) == n
+    alive = keep["pos"][:nv, 0] > -1e9
+    assert n == nfl + int(alive.sum()) + nbe
+    np.testing.assert_array_equal(rec["iref"], np.arange(n))
+    np.testing.assert_array_equal(rec["kpar"], np.concatenate([np.full(nfl, 1), np.full(int(alive.sum()), 2), np.full(nbe, 3)]))
+    idx = np.nonzero(bits)[0]
+    dr = np.float32(0.05)
+    fx = np.float32(0.1) + dr * (idx % dimg[0]).astype(np.float32)
+    fz = np.float32(0.1 * 3) + dr * (idx // (dimg[0] * dimg[1])).astype(np.float32)
+    np.testing.assert_array_equal(rec["x"][:nfl], fx)
+    np.testing.assert_array_equal(rec["z"][:nfl], fz)
+    assert (rec["vol"][:nfl] == np.float32(float(np.float32(0.05)) ** 3)).all() and not rec["kent"][:nfl].any()
+    sbid = keep["sbid"] if sb else np.zeros(nv + nbe, dtype=np.int32)
+    v = rec[nfl:nfl + int(alive.sum())]
+    np.testing.assert_array_equal(v["kent"], sbid[:nv][alive])
+    np.testing.assert_array_equal(v["vol"], keep["vol"][alive])
+    order = np.argsort(sbid[nv:], kind="stable")
+    s = rec[nfl + int(alive.sum()):]
+    np.testing.assert_array_equal(s["kent"], sbid[nv:][order])
+    np.testing.assert_array_equal(s["surf"], keep["surf"][order])
+    np.testing.assert_array_equal(s["x"], keep["pos"][nv:, 0][order])
+    nvs = np.cumsum(~alive)
+    e = keep["ep"][order, :3]
+    np.testing.assert_array_equal(np.stack([s["ep1"], s["ep2"], s["ep3"]], 1), nfl + e - nvs[e])
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_split_output(fmt, tmp_path, cxlib, capfd, monkeypatch):
+    """[output] split=true (crixus.cu:1137-1216): <name>.fluid + one file per special-boundary id holding the non-fluid
+    records of that id, in order, unchanged; ids without particles are skipped."""
+    from vtu import read_vtu
+    import h5mini
+    job, keep, bits = _host_job(90, 200, (6, 5, 3), seed=9)
+    keep["sbid"][keep["sbid"] == 2] = 0           # id 2 is empty: no file
+    nfl = int(bits.sum())
+    n = cxlib.cx_assemble_records(C.byref(job), nfl, None, 0)
+    rec = np.zeros(n, dtype=REC)
+    cxlib.cx_assemble_records(C.byref(job), nfl, rec.ctypes.data, n)
+    monkeypatch.chdir(tmp_path)                    # like the reference, "0." is prepended to the whole name (crixus.cpp:268)
+    base = "run"
+    assert cxlib.cx_write_split_records(rec.ctypes.data, n, nfl, 5, base.encode(), fmt) == 0
+    out = capfd.readouterr().out
+    assert " - Fluid particles: %d" % nfl in out and " - Boundary particles, kent 0: %d" % (nfl + int((rec["kent"][nfl:] == 0).sum())) in out
+
+    def load(name):
+        if fmt == 1:
+            d = read_vtu(str(tmp_path / (name + ".vtu")))
+            return d["AbsoluteIndex"].astype(np.int64), d["KENT"].astype(np.int64), d["Volume"], d["Surface"]
+        h, info = h5mini.read_compound_dataset(str(tmp_path / ("0." + name + ".h5sph")))
+        return h["AbsoluteIndex"].astype(np.int64), h["KENT"].astype(np.int64), h["Volume"], h["Surface"]
+    iref, kent, vol, surf = load("run.fluid")
+    np.testing.assert_array_equal(iref, np.arange(nfl))
+    for k in range(5):
+        want = np.nonzero(rec["kent"][nfl:] == k)[0] + nfl
+        exists = os.path.exists(str(tmp_path / ("run.boundary.kent%d.vtu" % k if fmt == 1 else "0.run.boundary.kent%d.h5sph" % k)))
+        assert exists == (want.size > 0), k
+        if want.size:
+            iref, kent, vol, surf = load("run.boundary.kent%d" % k)
+            np.testing.assert_array_equal(iref, want)
+            assert (kent == k).all()
+            np.testing.assert_array_equal(vol, rec["vol"][want])
+            np.testing.assert_array_equal(surf, rec["surf"][want])
+    assert cxlib.cx_write_split_records(rec.ctypes.data, n, nfl, 2, base.encode(), fmt) == -18   # a KENT >= num_kents: INTERNAL_ERROR
+    assert cxlib.cx_write_split_records(rec.ctypes.data, n, n + 1, 5, base.encode(), fmt) == -11

@@ -40,6 +40,8 @@ def _cmp_pipeline(o, g, c):
             bad = np.nonzero(gv != ov)[0]
             pytest.fail("%d of %d vertex volumes differ; max |diff| = %.3f voxel quanta; first: %s" %
                         (bad.size, gv.size, np.abs(gv - ov).max() / q, [(int(b), float(gv[b]), float(ov[b])) for b in bad[:5]]))
+    if "sbid" in o:
+        np.testing.assert_array_equal(g["sbid"], o["sbid"])
     if "fpos" in o:
         assert bytes(g["params_fill"]) == bytes(o["params_fill"])
         np.testing.assert_array_equal(g["dimg"], o["dimg"])
@@ -68,6 +70,20 @@ def test_case_vs_reference_golden(name, cuda_backend):
     g = cases.run(cuda_backend, c)
     from golden_compare import compare_with_golden
     compare_with_golden(g, gold, c)
+
+
+@pytest.mark.parametrize("name", ["plate_jitter", "sphere_tank", "channel"])
+def test_special_boundary_stress_vs_oracle(name, oracle, cuda_backend):
+    """cx_identify_special_boundary (cell-binned candidate lookup, hoisted per-triangle records) against the oracle's
+    all-pairs loop on adversarial grids -- every kind, including slivers / zero-area triangles (whole-domain fallback of the
+    candidate range) and the rounding-sensitive edge cases: bit-exact."""
+    c = cases.case(name)
+    for seed in range(4):
+        sb = cases.special_stress(c["tris"], seed, n=240)
+        c2 = dict(c, special=[sb[:80], sb[80:160], sb[160:]])
+        o, g = cases.run(oracle, c2, stages=()), cases.run(cuda_backend, c2, stages=())
+        np.testing.assert_array_equal(g["sbid"], o["sbid"])
+        assert 0 < (o["sbid"] > 0).sum() < o["sbid"].size
 
 
 @pytest.mark.parametrize("wide", ["0", "1"])

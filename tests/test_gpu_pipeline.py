@@ -54,6 +54,12 @@ def _job_for(c):
             specs[i].dr_wall = float(f[2]) if f[2] is not None else 0.0
     job.fills, job.nfills = specs, len(c["fills"])
     keep.append(specs)
+    sb = [np.ascontiguousarray(x, dtype=np.float32).reshape(-1) for x in c.get("special", ())]
+    if sb:
+        ptrs = (C.POINTER(C.c_float) * len(sb))(*[x.ctypes.data_as(C.POINTER(C.c_float)) for x in sb])
+        cnt = (C.c_int64 * len(sb))(*[x.size // 9 for x in sb])
+        job.sb_corners, job.sb_nbe, job.nsb = ptrs, cnt, len(sb)
+        keep += sb + [ptrs, cnt]
     return job, keep
 
 
@@ -62,7 +68,7 @@ def _arr(ptr, shape, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(shape).copy() if n else np.zeros(shape, dtype)
 
 
-@pytest.mark.parametrize("name", ["plate", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"])
+@pytest.mark.parametrize("name", ["plate", "cube_jitter", "spheric2_mini", "channel", "sphere_tank", "cube_sb", "plate_sb_stress"])
 def test_preprocess_host_vs_oracle(name, oracle, cuda_backend):
     c = cases.case(name)
     o = cases.run(oracle, c)
@@ -84,13 +90,17 @@ def test_preprocess_host_vs_oracle(name, oracle, cuda_backend):
         assert int(job.nfluid_counted) == o["nfluid"]
         assert int(job.nfluid) == int(np.unpackbits(o["fpos"].view(np.uint8)).sum())
         np.testing.assert_array_equal(np.array(list(job.zstat), dtype=np.float32)[:2], np.asarray(o["zstat"], dtype=np.float32)[:2])
+        if c["special"]:
+            np.testing.assert_array_equal(_arr(job.sbid, (nv + nbe,), np.int32), o["sbid"])
+        else:
+            assert not job.sbid
         ctx.L.cx_job_free(C.byref(job))
         assert not job.pos
 
 
-def _run_cli(tmp_path, name, fmt):
+def _run_cli(tmp_path, name, fmt, split=False):
     sys.path.insert(0, os.path.join(HERE, "golden"))
-    from make_golden import write_ini
+    from make_golden import write_ini, write_special
     c = cases.case(name)
     stl = str(tmp_path / (name + ".stl"))
     mg.write_stl(stl, c["tris"], c["normals"])
@@ -99,7 +109,7 @@ def _run_cli(tmp_path, name, fmt):
         fsp = str(tmp_path / (name + "_fs.stl"))
         mg.write_stl(fsp, c["fshape"][0], c["fshape"][1])
     ini = str(tmp_path / (name + ".ini"))
-    write_ini(ini, c, stl, fsp)
+    write_ini(ini, c, stl, fsp, write_special(str(tmp_path), c), split)
     if fmt != "vtu":
         text = open(ini).read().replace("format=vtu", "format=" + fmt)
         open(ini, "w").write(text)
@@ -119,9 +129,13 @@ def _cmp_particles_with_golden(d, gold, shift):
     np.testing.assert_array_equal(seg["Normal"], gold["seg_norm"])
     np.testing.assert_array_equal(seg["Surface"], gold["seg_surf"])
     np.testing.assert_array_equal(seg["VertexParticle"].astype(np.int64) + shift, gold["seg_ep"])
+    if "seg_kent" in gold.files:
+        np.testing.assert_array_equal(d["vertex"]["KENT"].astype(np.int32), gold["vert_kent"])
+        np.testing.assert_array_equal(seg["KENT"].astype(np.int32), gold["seg_kent"])
+        assert (np.diff(d["segment"]["KENT"].astype(np.int64)) >= 0).all()     # grouped by id in the file (crixus.cu:1088-1097)
 
 
-@pytest.mark.parametrize("name", ["spheric2_mini", "channel", "cube"])
+@pytest.mark.parametrize("name", ["spheric2_mini", "channel", "cube", "cube_sb", "sphere_sb"])
 def test_cli_vtu_vs_reference_golden(name, tmp_path):
     """`crixus case.ini` -> case.vtu, compared particle by particle with the file the reference binary wrote."""
     import re
@@ -134,6 +148,30 @@ def test_cli_vtu_vs_reference_golden(name, tmp_path):
     assert shift in (0, 1)
     _cmp_particles_with_golden(d, gold, shift)
     assert "Creation of %d fluid particles" % gold["fluid_pos"].shape[0] in out
+
+
+def test_cli_split_output(tmp_path):
+    """[output] split=true with special-boundary grids: the .fluid file and the per-id boundary files together hold exactly
+    the records of the unsplit file (crixus.cu:1137-1216)."""
+    from vtu import read_vtu
+    name = "cube_sb"
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    _run_cli(tmp_path / "a", name, "vtu")
+    _, out = _run_cli(tmp_path / "b", name, "vtu", split=True)
+    whole = read_vtu(str(tmp_path / "a" / (name + ".vtu")))
+    nfl = int((whole["ParticleType"] == 1).sum())
+    parts = [read_vtu(str(tmp_path / "b" / (name + ".fluid.vtu")))]
+    assert parts[0]["n"] == nfl and " - Fluid particles: %d" % nfl in out
+    for k in range(4):
+        d = read_vtu(str(tmp_path / "b" / ("%s.boundary.kent%d.vtu" % (name, k))))
+        assert (d["KENT"] == k).all() and d["n"] == int(((whole["KENT"] == k) & (whole["ParticleType"] > 1)).sum())
+        parts.append(d)
+    assert not os.path.exists(str(tmp_path / "b" / (name + ".vtu")))
+    for key in ("Volume", "Surface", "KENT", "AbsoluteIndex", "Points", "Normal", "VertexParticle", "ParticleType"):
+        cat = np.concatenate([p[key] for p in parts])
+        order = np.argsort(np.concatenate([p["AbsoluteIndex"] for p in parts]), kind="stable")
+        np.testing.assert_array_equal(cat[order], whole[key])
 
 
 def test_cli_h5sph_equals_vtu(tmp_path):

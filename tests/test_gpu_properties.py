@@ -6,7 +6,8 @@ sphere-in-tank families) through size-independent properties, and against the CP
     closure (every unset cell next to a set cell is separated from it by the reference's checkCollision -- evaluated
     by the oracle on a sample -- i.e. the result is the fixed point), popcount == running count;
   * binning: cell_idx is an exclusive prefix ending at nbe and every segment sits in the cell of its barycentre;
-  * periodic links: every vertex of the max face is deleted and linked, no dangling index survives in ep.
+  * periodic links: every vertex of the max face is deleted and linked, no dangling index survives in ep;
+  * special-boundary tagging: cell-binned lookup == the oracle's all-pairs loop on wall-sized and adversarial grids.
 """
 import numpy as np
 import pytest
@@ -195,6 +196,32 @@ def _check_fill(hp, oracle, nsample=1500):
         assert oracle.check_collision(_op(p), s, e, norm, ep, pos, fnbe, hp.cnbe, cell_idx), "cell %r should have been filled from %r" % (s, e)
 
 
+def _check_special(hp, oracle, n=96):
+    """special-boundary tagging at full size: two large inlet/outlet rectangles on the x-min / x-max walls plus an adversarial
+    grid (cases.special_stress), cell-binned CUDA lookup against the oracle's all-pairs loop, bit-exact."""
+    import cases
+    from oracle.orc import f4
+    ctx, w, nv, nbe = hp.ctx, hp.w, hp.nv, hp.nbe
+    tris = np.asarray(w["tris"], dtype=np.float32)
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    y0, y1, z0, z1 = lo[1] + 0.2 * (hi[1] - lo[1]), lo[1] + 0.7 * (hi[1] - lo[1]), lo[2] + 0.1 * (hi[2] - lo[2]), lo[2] + 0.5 * (hi[2] - lo[2])
+    walls = np.array([[[x, y0, z0], [x, y1, z0], [x, y1, z1]] for x in (lo[0], hi[0])] +
+                     [[[x, y0, z0], [x, y1, z1], [x, y0, z1]] for x in (lo[0], hi[0])], dtype=np.float32)
+    grids = [walls, cases.special_stress(tris, 3, n=n)]
+    pos, ep, cell_idx = hp.pos.cpu().numpy(), hp.ep.cpu().numpy(), hp.cell_idx.cpu().numpy()
+    got = torch.zeros(nv + nbe, dtype=torch.int32, device=hp.pos.device)
+    ref = np.zeros(nv + nbe, dtype=np.int32)
+    for k, g in enumerate(grids):
+        sv, se = api.weld_host(g.reshape(-1, 3), np.float32(w["dr"]))
+        sbpos, sbep = f4(sv), np.zeros((se.shape[0], 4), dtype=np.int32)
+        sbep[:, :3] = se
+        ctx.identify_special_boundary(hp.pf, hp.pos, hp.ep, hp.cell_idx, nv, nbe, torch.from_numpy(sbpos).to(got.device),
+                                      torch.from_numpy(sbep).to(got.device), sbep.shape[0], got, k + 1)
+        oracle.identify_special_boundary(_op(hp.pf), pos, ep, nv, nbe, sbpos, sbep, ref, k + 1)
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    assert (ref[nv:] == 1).sum() > 10 and (ref[nv:] == 2).sum() > 0
+
+
 def test_config2_full_size(ctx, oracle):
     """BASELINE.json configs[1]: 3.06e6 triangles, 328 x 219 x 131 lattice, free-surface fill."""
     w = wl.config2(3)
@@ -202,6 +229,7 @@ def test_config2_full_size(ctx, oracle):
     hp = _run(ctx, w)
     _check_common(hp, oracle)
     _check_fill(hp, oracle)
+    _check_special(hp, oracle)
 
 
 def test_config1(ctx, oracle):
@@ -209,6 +237,7 @@ def test_config1(ctx, oracle):
     hp = _run(ctx, wl.config1())
     _check_common(hp, oracle, nsample_ranges=6)
     _check_fill(hp, oracle)
+    _check_special(hp, oracle, n=240)
 
 
 def test_channel_family(ctx, oracle):

@@ -66,7 +66,7 @@ def test_host_glue_equals_oracle(name, oracle, cxlib):
 
 def test_meshes_satisfy_triangle_size_precondition():
     for name in cases.ALL:
-        if name == "plate_jitter":   # deliberately generic: the SURVEY D.4 sensitivity mesh (h=1.25dr plus 10 % jitter)
+        if name in ("plate_jitter", "plate_sb_stress"):   # deliberately generic: the SURVEY D.4 sensitivity mesh (h=1.25dr plus 10 % jitter)
             continue
         c = cases.case(name)
         t = c["tris"].astype(np.float64)

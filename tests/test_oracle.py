@@ -46,7 +46,7 @@ def test_oracle_vs_reference_cuda_golden(name, oracle):
     assert nbad == 0
 
 
-@pytest.mark.parametrize("name", ["plate_jitter", "cube_jitter", "spheric2_mini", "channel", "sphere_tank"])
+@pytest.mark.parametrize("name", ["plate_jitter", "cube_jitter", "spheric2_mini", "channel", "sphere_tank", "cube_sb", "sphere_sb"])
 def test_oracle_vs_reference_host_shim(name, oracle, refshim):
     """Stage by stage against the reference's own src/crixus_d.cu compiled for the host (g++ contraction)."""
     c = cases.case(name)
@@ -54,6 +54,9 @@ def test_oracle_vs_reference_host_shim(name, oracle, refshim):
     for k in ("verts", "epv", "pre_ep", "pre_surf", "pre_bary", "cell_idx", "ep", "pos", "norm", "surf", "trisize", "fpos", "dimg"):
         np.testing.assert_array_equal(o[k], r[k], err_msg=k)
     np.testing.assert_array_equal(o["zstat"][:2], r["zstat"][:2])
+    if c["special"]:
+        np.testing.assert_array_equal(o["sbid"], r["sbid"])
+        assert o["sbid"].any()
     assert o["nfluid"] == r["nfluid"] and o["fill_counts"] == r["fill_counts"]
     nv = o["nvert"]
     alive = o["pos"][:nv, 0] > -1e9
@@ -61,6 +64,21 @@ def test_oracle_vs_reference_host_shim(name, oracle, refshim):
     diff = np.abs(o["vol"] - r["vol"])[alive] / q
     # g++ may fuse multiply-adds differently from nvcc: allow <= 1 voxel quantum on <= 1 % of the vertices
     assert (diff > 0).mean() <= 0.01 and diff.max() <= 1.0 + 1e-6
+
+
+def test_special_boundary_stress_vs_reference_host_shim(oracle, refshim):
+    """identifySpecialBoundarySegments on adversarial grids (cases.special_stress: barycentres on edges and corners of the
+    grid triangles, just inside / outside the eps bands, normals with nx+ny+nz = 0, slivers, zero-area triangles, triangles
+    spanning the whole domain): restatement == the reference's own kernel compiled for the host.  (The rounding-sensitive
+    kinds are pinned by the golden fixture plate_sb_stress, made by the reference CUDA binary.)"""
+    for name in ("plate_jitter", "sphere_tank"):
+        c = cases.case(name)
+        for seed in range(3):
+            sb = cases.special_stress(c["tris"], seed, skip=(1, 3, 6))   # those kinds (sliver; u+v = 1+eps hit exactly) hinge on the compiler's FMA fusion: golden only
+            c2 = dict(c, special=[sb[: sb.shape[0] // 2], sb[sb.shape[0] // 2:]])
+            o, r = cases.run(oracle, c2, stages=()), cases.run(refshim, c2, stages=())
+            np.testing.assert_array_equal(o["sbid"], r["sbid"])
+            assert 0 < (o["sbid"] > 0).sum() < o["sbid"].size
 
 
 def test_fill_fixed_point_is_schedule_independent(oracle, refshim):
