@@ -43,7 +43,9 @@ class CxJob(C.Structure):
                 ("nvert", C.c_int64), ("nfluid", C.c_int64), ("nfluid_counted", C.c_int64),
                 ("pos", C.POINTER(C.c_float)), ("norm", C.POINTER(C.c_float)), ("ep", C.POINTER(C.c_int32)),
                 ("surf", C.POINTER(C.c_float)), ("vol", C.POINTER(C.c_float)), ("cell_idx", C.POINTER(C.c_int32)),
-                ("fpos", C.POINTER(C.c_uint32)), ("sbid", C.POINTER(C.c_int32)), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
+                ("fpos", C.POINTER(C.c_uint32)), ("sbid", C.POINTER(C.c_int32)),
+                ("d_pos", C.c_void_p), ("d_norm", C.c_void_p), ("d_ep", C.c_void_p), ("d_surf", C.c_void_p), ("d_vol", C.c_void_p),
+                ("d_fpos", C.c_void_p), ("d_sbid", C.c_void_p), ("dimg", C.c_int64 * 3), ("zstat", C.c_float * 4),
                 ("params_fill", CxParams),
                 ("tri_failed", C.c_int64), ("tri_mind", C.c_float), ("tri_maxd", C.c_float),
                 ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double),
@@ -129,6 +131,9 @@ def lib():
         "cx_write_vtu_records": (C.c_int, [VP, I64, C.c_char_p]),
         "cx_write_h5sph_records": (C.c_int, [VP, I64, C.c_char_p]),
         "cx_write_split_records": (C.c_int, [VP, I64, I64, C.c_int32, C.c_char_p, C.c_int]),
+        "cx_assemble_records_device": (C.c_int, [VP, P, C.POINTER(I64), VP, VP, VP, VP, VP, VP, VP, I64, I64, I64, VP, I64, C.POINTER(I64)]),
+        "cx_write_vtu_records_device": (C.c_int, [VP, VP, I64, C.c_char_p]),
+        "cx_write_h5sph_records_device": (C.c_int, [VP, VP, I64, C.c_char_p]),
         "cx_run_ini": (C.c_int, [C.c_char_p]),
     }
     for name, (res, args) in sig.items():
@@ -340,3 +345,20 @@ class Context:
 
     def preprocess_host(self, job):
         self._ck(self.L.cx_preprocess_host(self.h, C.byref(job)))
+
+    def assemble_records_device(self, job, nfluid_for_indices=None):
+        """cx_assemble_records_device on the device arrays a cx_preprocess_host call left behind -> torch uint8 (n, 64)"""
+        import torch
+        cap = int(job.nfluid) + int(job.nvert) + int(job.nbe)
+        rec = torch.empty((max(cap, 1), 64), dtype=torch.uint8, device=self.device)
+        n = I64(0)
+        self._ck(self.L.cx_assemble_records_device(self.h, C.byref(job.params_fill), job.dimg, VP(job.d_fpos), VP(job.d_pos), VP(job.d_norm),
+                                                   VP(job.d_ep), VP(job.d_surf), VP(job.d_vol), VP(job.d_sbid), int(job.nvert), int(job.nbe),
+                                                   int(job.nfluid if nfluid_for_indices is None else nfluid_for_indices), VP(rec.data_ptr()),
+                                                   cap, C.byref(n)))
+        self.synchronize()
+        return rec[: int(n.value)]
+
+    def write_records_device(self, rec, filename, fmt="vtu"):
+        fn = self.L.cx_write_h5sph_records_device if fmt == "h5sph" else self.L.cx_write_vtu_records_device
+        self._ck(fn(self.h, VP(rec.data_ptr()), int(rec.shape[0]), str(filename).encode()))

@@ -30,11 +30,15 @@ struct cx_ctx {
   // page-locking cost milliseconds per call; the arenas make repeated calls allocation-free)
   void *dev_arena = nullptr, *host_arena = nullptr;
   size_t dev_arena_bytes = 0, host_arena_bytes = 0;
+  // pinned staging of the streamed file writers (records.cu)
+  void *pin_stage = nullptr;
+  size_t pin_stage_bytes = 0;
 };
 
 int cx_fail(cx_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
 // returns a device pointer to >= bytes of scratch (contents undefined); nullptr on failure
 void *cx_scratch(cx_ctx *ctx, size_t bytes);
+void *cx_scratch_pinned(cx_ctx *ctx, size_t bytes);  // grow-only pinned host staging; nullptr on failure
 void cx_fill_state_free(cx_ctx *ctx);  // fill.cu
 
 #define CX_CUDA(ctx, call)                                              \

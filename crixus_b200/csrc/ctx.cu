@@ -12,6 +12,18 @@ int cx_fail(cx_ctx *ctx, int code, const char *what, cudaError_t e)
   return code;
 }
 
+void *cx_scratch_pinned(cx_ctx *ctx, size_t bytes)
+{
+  if (bytes > ctx->pin_stage_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pin_stage) cudaFreeHost(ctx->pin_stage);
+    ctx->pin_stage = nullptr; ctx->pin_stage_bytes = 0;
+    if (cudaMallocHost(&ctx->pin_stage, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->pin_stage_bytes = bytes;
+  }
+  return ctx->pin_stage;
+}
+
 void *cx_scratch(cx_ctx *ctx, size_t bytes)
 {
   if (bytes <= ctx->scratch_bytes) return ctx->scratch;
@@ -75,6 +87,7 @@ void cx_destroy(cx_ctx *ctx)
   if (ctx->host_arena) cudaFreeHost(ctx->host_arena);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   if (ctx->d_mail) cudaFree(ctx->d_mail);
+  if (ctx->pin_stage) cudaFreeHost(ctx->pin_stage);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

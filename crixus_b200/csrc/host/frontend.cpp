@@ -1,6 +1,7 @@
 // crixus_b200 -- the reference's process surface behind the C-ABI: .ini reader, binary STL reader, particle-record
 // assembly, VTU / h5sph writers, and cx_run_ini = what `Crixus file.ini` does
 // (/root/reference/src/crixus.cu:57-73,126-221,310,394,433,647-649,698-707,737-795,973-1135; src/crixus.cpp:12-289).
+#include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -219,25 +220,45 @@ int cx_run_ini(const char *ini_path)
          job.zstat[2], job.zstat[1], job.zstat[3]);
   printf("Creation of %lld fluid particles completed. [OK]\n", (long long)job.nfluid);
   printf("Timing: weld %.3f s, upload %.3f s, GPU %.3f s, download %.3f s\n", job.t_weld_s, job.t_h2d_s, job.t_gpu_s, job.t_d2h_s);
+  // particle records (crixus.cu:973-1097) and the output file: assembled and laid out on the device, streamed to the file
+  // through pinned staging (CX_HOST_ASSEMBLY=1 selects the host restatement of the same steps, kept as its checker)
   const double t_a0 = wall_s();
-  const std::vector<CxOutBuf> buf = cx_assemble(job, job.nfluid);
-  const double t_asm = wall_s() - t_a0;
   const std::string fmt = ini.Get("output", "format", "vtu");
   std::string outname = ini.Get("output", "name", cfg.substr(0, cfg.size() >= 4 ? cfg.size() - 4 : 0));
-  if (ini.GetBoolean("output", "split", false)) {   // crixus.cu:1135-1207
-    rc = cx_write_split_records(buf.data(), (int64_t)buf.size(), job.nfluid, job.nsb + 1, outname.c_str(), fmt == "h5sph" ? 2 : 1);
+  const bool split = ini.GetBoolean("output", "split", false);   // crixus.cu:1135
+  const char *hostenv = getenv("CX_HOST_ASSEMBLY");
+  const bool on_host = hostenv && hostenv[0] == '1';
+  std::vector<CxOutBuf> buf;
+  void *rec_d = nullptr;
+  int64_t nrec = 0;
+  if (on_host) {
+    buf = cx_assemble(job, job.nfluid);
+    nrec = (int64_t)buf.size();
   } else {
-    if (fmt == "h5sph") {
-      outname = "0." + outname + ".h5sph";
-      rc = cx_write_h5sph(buf, outname);
-    } else {
-      outname += ".vtu";
-      rc = cx_write_vtu(buf, outname);
+    const int64_t cap = job.nfluid + job.nvert + job.nbe;
+    if (cudaMalloc(&rec_d, 64 * (size_t)std::max<int64_t>(cap, 1)) != cudaSuccess) { cx_destroy(ctx); return CX_CUDA_ERROR; }
+    rc = cx_assemble_records_device(ctx, &job.params_fill, job.dimg, job.d_fpos, job.d_pos, job.d_norm, job.d_ep, job.d_surf, job.d_vol,
+                                    job.d_sbid, job.nvert, job.nbe, job.nfluid, rec_d, cap, &nrec);
+    if (rc == CX_OK) rc = cx_synchronize(ctx);
+    if (rc != CX_OK) { printf("Record assembly failed: %d %s\n", rc, cx_last_error(ctx)); cudaFree(rec_d); cx_destroy(ctx); return rc; }
+    if (split) {   // the per-id files are cut on the host
+      buf.resize((size_t)nrec);
+      if (cudaMemcpy(buf.data(), rec_d, 64 * (size_t)nrec, cudaMemcpyDeviceToHost) != cudaSuccess) rc = CX_CUDA_ERROR;
     }
+  }
+  const double t_asm = wall_s() - t_a0;
+  if (rc == CX_OK && split) {   // crixus.cu:1137-1207
+    rc = cx_write_split_records(buf.data(), nrec, job.nfluid, job.nsb + 1, outname.c_str(), fmt == "h5sph" ? 2 : 1);
+  } else if (rc == CX_OK) {
+    outname = fmt == "h5sph" ? "0." + outname + ".h5sph" : outname + ".vtu";   // generic_output, crixus.cpp:261-289
+    if (on_host) rc = fmt == "h5sph" ? cx_write_h5sph(buf, outname) : cx_write_vtu(buf, outname);
+    else rc = fmt == "h5sph" ? cx_write_h5sph_records_device(ctx, rec_d, nrec, outname.c_str())
+                             : cx_write_vtu_records_device(ctx, rec_d, nrec, outname.c_str());
     printf("Writing output to file %s ... %s\n", outname.c_str(), rc == CX_OK ? "[OK]" : "[FAILED]");
   }
-  printf("Timing: read STL %.3f s, CUDA context %.3f s, assemble %.3f s, write %.3f s, total %.3f s\n", t_read, t_create, t_asm,
-         wall_s() - t_a0 - t_asm, wall_s() - t_start);
+  if (rec_d) cudaFree(rec_d);
+  printf("Timing: read STL %.3f s, CUDA context %.3f s, assemble %.3f s (%s), write %.3f s, total %.3f s\n", t_read, t_create, t_asm,
+         on_host ? "host" : "device", wall_s() - t_a0 - t_asm, wall_s() - t_start);
   cx_job_free(&job);
   cx_destroy(ctx);
   return rc;

@@ -98,15 +98,53 @@ std::vector<CxOutBuf> cx_assemble(const cx_job &job, int64_t nfluid)
 }
 
 // ---------------------------------------------------------------------------------------------- VTU
-static void scalar_array(FILE *f, const char *type, const char *name, size_t off)
+// XML part of the file up to and including the '_' that starts the appended data (crixus.cpp:70-147)
+std::string cx_vtu_header(int len)
 {
-  fprintf(f, "  <DataArray type='%s' Name='%s' format='appended' offset='%zu'/>\n", type, name, off);
+  std::string h;
+  char line[256];
+  auto add = [&](const char *fmt, auto... a) { snprintf(line, sizeof(line), fmt, a...); h += line; };
+  auto scalar = [&](const char *type, const char *name, size_t off) {
+    add("  <DataArray type='%s' Name='%s' format='appended' offset='%zu'/>\n", type, name, off);
+  };
+  auto vec = [&](const char *type, const char *name, unsigned dim, size_t off) {
+    if (name) add("  <DataArray type='%s' Name='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, name, dim, off);
+    else add("  <DataArray type='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, dim, off);
+  };
+  h += "<?xml version='1.0'?>\n";
+  add("<VTKFile type= 'UnstructuredGrid'  version= '0.1'  byte_order= '%s'>\n", "LittleEndian");
+  h += " <UnstructuredGrid>\n";
+  add("  <Piece NumberOfPoints='%d' NumberOfCells='%d'>\n", len, len);
+  h += "   <PointData Scalars='Volume'>\n";
+  size_t off = 0;
+  scalar("Float32", "Volume", off); off += sizeof(float) * len + sizeof(int);
+  scalar("Float32", "Surface", off); off += sizeof(float) * len + sizeof(int);
+  scalar("UInt32", "ParticleType", off); off += 4 * (size_t)len + sizeof(int);
+  scalar("UInt32", "FluidType", off); off += 4 * (size_t)len + sizeof(int);
+  scalar("UInt32", "KENT", off); off += 4 * (size_t)len + sizeof(int);
+  scalar("UInt32", "MovingBoundary", off); off += 4 * (size_t)len + sizeof(int);
+  scalar("UInt32", "AbsoluteIndex", off); off += 4 * (size_t)len + sizeof(int);
+  vec("Float32", "Normal", 3, off); off += 12 * (size_t)len + sizeof(int);
+  vec("UInt32", "VertexParticle", 3, off); off += 12 * (size_t)len + sizeof(int);
+  h += "   </PointData>\n";
+  h += "   <Points>\n";
+  vec("Float64", nullptr, 3, off); off += 24 * (size_t)len + sizeof(int);
+  h += "   </Points>\n";
+  h += "   <Cells>\n";
+  scalar("Int32", "connectivity", off); off += 4 * (size_t)len + sizeof(int);
+  scalar("Int32", "offsets", off); off += 4 * (size_t)len + sizeof(int);
+  h += "  <DataArray type='Int32' Name='types' format='ascii'>\n";
+  h.reserve(h.size() + 2 * (size_t)len + 256);
+  for (int i = 0; i < len; i++) h += "1\t";   // crixus.cpp:133-137
+  h += "\n";
+  h += "  </DataArray>\n";
+  h += "   </Cells>\n";
+  h += "  </Piece>\n";
+  h += " </UnstructuredGrid>\n";
+  h += " <AppendedData encoding='raw'>\n_";
+  return h;
 }
-static void vector_array(FILE *f, const char *type, const char *name, unsigned dim, size_t off)
-{
-  if (name) fprintf(f, "  <DataArray type='%s' Name='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, name, dim, off);
-  else fprintf(f, "  <DataArray type='%s' NumberOfComponents='%u' format='appended' offset='%zu'/>\n", type, dim, off);
-}
+const char *cx_vtu_trailer() { return " </AppendedData>\n</VTKFile>"; }
 
 int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
 {
@@ -114,41 +152,10 @@ int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
   if (!fid) return CX_NO_WRITE_FILE;
   setvbuf(fid, nullptr, _IOFBF, 8 << 20);
   const int len = (int)buf.size();
-  fprintf(fid, "<?xml version='1.0'?>\n");
-  fprintf(fid, "<VTKFile type= 'UnstructuredGrid'  version= '0.1'  byte_order= '%s'>\n", "LittleEndian");
-  fprintf(fid, " <UnstructuredGrid>\n");
-  fprintf(fid, "  <Piece NumberOfPoints='%d' NumberOfCells='%d'>\n", len, len);
-  fprintf(fid, "   <PointData Scalars='Volume'>\n");
-  size_t off = 0;
-  scalar_array(fid, "Float32", "Volume", off); off += sizeof(float) * len + sizeof(int);
-  scalar_array(fid, "Float32", "Surface", off); off += sizeof(float) * len + sizeof(int);
-  scalar_array(fid, "UInt32", "ParticleType", off); off += 4 * (size_t)len + sizeof(int);
-  scalar_array(fid, "UInt32", "FluidType", off); off += 4 * (size_t)len + sizeof(int);
-  scalar_array(fid, "UInt32", "KENT", off); off += 4 * (size_t)len + sizeof(int);
-  scalar_array(fid, "UInt32", "MovingBoundary", off); off += 4 * (size_t)len + sizeof(int);
-  scalar_array(fid, "UInt32", "AbsoluteIndex", off); off += 4 * (size_t)len + sizeof(int);
-  vector_array(fid, "Float32", "Normal", 3, off); off += 12 * (size_t)len + sizeof(int);
-  vector_array(fid, "UInt32", "VertexParticle", 3, off); off += 12 * (size_t)len + sizeof(int);
-  fprintf(fid, "   </PointData>\n");
-  fprintf(fid, "   <Points>\n");
-  vector_array(fid, "Float64", nullptr, 3, off); off += 24 * (size_t)len + sizeof(int);
-  fprintf(fid, "   </Points>\n");
-  fprintf(fid, "   <Cells>\n");
-  scalar_array(fid, "Int32", "connectivity", off); off += 4 * (size_t)len + sizeof(int);
-  scalar_array(fid, "Int32", "offsets", off); off += 4 * (size_t)len + sizeof(int);
-  fprintf(fid, "  <DataArray type='Int32' Name='types' format='ascii'>\n");
-  {  // len times "1\t" (crixus.cpp:133-137), written in large pieces
-    std::string ones;
-    ones.reserve(2 << 16);
-    for (int i = 0; i < (1 << 16); i++) ones += "1\t";
-    for (int i = 0; i < len; i += 1 << 16) fwrite(ones.data(), 2, (size_t)std::min(1 << 16, len - i), fid);
+  {
+    const std::string h = cx_vtu_header(len);
+    fwrite(h.data(), 1, h.size(), fid);
   }
-  fprintf(fid, "\n");
-  fprintf(fid, "  </DataArray>\n");
-  fprintf(fid, "   </Cells>\n");
-  fprintf(fid, "  </Piece>\n");
-  fprintf(fid, " </UnstructuredGrid>\n");
-  fprintf(fid, " <AppendedData encoding='raw'>\n_");
   // appended arrays: int32 byte count, then the values; converted AoS -> SoA through a fixed 4 MB staging buffer
   const int CH = 1 << 16;
   std::vector<char> tmp((size_t)CH * 24);
@@ -181,8 +188,7 @@ int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename)
       fwrite(idx, 4, (size_t)m, fid);
     }
   }
-  fprintf(fid, " </AppendedData>\n");
-  fprintf(fid, "</VTKFile>");
+  fputs(cx_vtu_trailer(), fid);
   fclose(fid);
   return CX_OK;
 }
@@ -228,12 +234,12 @@ void message(Bytes &o, uint16_t type, const Bytes &data)
 }
 }  // namespace
 
-int cx_write_h5sph(const std::vector<CxOutBuf> &buf, const std::string &filename)
+// everything of the file that precedes the raw records (they start at byte .size() of the result)
+int cx_h5sph_header(uint64_t len, std::vector<uint8_t> &out)
 {
   static const char *names[16] = {"Coords_0", "Coords_1", "Coords_2", "Normal_0", "Normal_1", "Normal_2", "Volume", "Surface",
                                   "ParticleType", "FluidType", "KENT", "MovingBoundary", "AbsoluteIndex", "VertexParticle1",
                                   "VertexParticle2", "VertexParticle3"};  // crixus.cpp:23-38
-  const uint64_t len = buf.size();
   // ---- layout of the metadata blocks
   const uint64_t a_super = 0, a_root_hdr = 96;
   // root object header: 16-byte prefix + one symbol-table message (8 + 16)
@@ -305,10 +311,19 @@ int cx_write_h5sph(const std::vector<CxOutBuf> &buf, const std::string &filename
   o.u8(1); o.u8(0); o.u16(4); o.u32(1); o.u32((uint32_t)dset_msgs_size); o.u32(0);
   o.raw(msgs.b.data(), msgs.size());
   o.pad_to(a_data);
+  out.swap(o.b);
+  return CX_OK;
+}
 
+int cx_write_h5sph(const std::vector<CxOutBuf> &buf, const std::string &filename)
+{
+  const uint64_t len = buf.size();
+  std::vector<uint8_t> head;
+  const int rc = cx_h5sph_header(len, head);
+  if (rc != CX_OK) return rc;
   FILE *f = fopen(filename.c_str(), "wb");
   if (!f) return CX_NO_WRITE_FILE;
-  bool ok = fwrite(o.b.data(), 1, o.size(), f) == o.size();
+  bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
   if (len) ok = ok && fwrite(buf.data(), 64, (size_t)len, f) == (size_t)len;
   fclose(f);
   return ok ? CX_OK : CX_WRITE_FAIL;

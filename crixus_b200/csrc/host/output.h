@@ -14,5 +14,9 @@ struct CxOutBuf {  // 64 bytes: 8 float + 8 int, member order of src/crixus.h:33
 std::vector<CxOutBuf> cx_assemble(const cx_job &job, int64_t nfluid_for_indices);
 int cx_write_vtu(const std::vector<CxOutBuf> &buf, const std::string &filename);     // crixus.cpp:62-259
 int cx_write_h5sph(const std::vector<CxOutBuf> &buf, const std::string &filename);   // crixus.cpp:12-60 (own HDF5 writer)
+// the parts of the two file formats that do not depend on the particle data (shared with the device-side writers)
+std::string cx_vtu_header(int len);
+const char *cx_vtu_trailer();
+int cx_h5sph_header(uint64_t len, std::vector<uint8_t> &out);
 // binary STL, crixus.cu:126-221.  Returns CX_OK / CX_FILE_NOT_OPEN / CX_STL_NOT_BINARY / CX_READ_ERROR
 int cx_read_stl(const std::string &filename, std::vector<float> &corners, std::vector<float> &normals);

@@ -42,6 +42,9 @@ extern "C" void cx_job_free(cx_job *job)
   job->ep = job->cell_idx = nullptr;
   job->fpos = nullptr;
   job->sbid = nullptr;
+  job->d_pos = job->d_norm = job->d_surf = job->d_vol = nullptr;
+  job->d_ep = job->d_sbid = nullptr;
+  job->d_fpos = nullptr;
 }
 
 extern "C" int64_t cx_job_sizeof(void) { return (int64_t)sizeof(cx_job); }
@@ -290,6 +293,8 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   CU(cudaEventElapsedTime(&job->stage_ms[6], ev[5], ev[6]));
   for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
   job->params_fill = p;
+  job->d_pos = pos.as<float>(); job->d_norm = norm.as<float>(); job->d_ep = ep.as<int32_t>(); job->d_surf = surf.as<float>();
+  job->d_vol = vol.as<float>(); job->d_fpos = fpos.as<uint32_t>(); job->d_sbid = nsb ? sbid.as<int32_t>() : nullptr;
 
   // ---- results to the host (crixus.cu:363-365, 413, 456, 962): pinned arena, asynchronous copies, one synchronise
   t0 = now_s();

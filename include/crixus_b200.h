@@ -190,6 +190,9 @@ typedef struct cx_job {
   int64_t nvert, nfluid, nfluid_counted; /* popcount vs. the reference's running count (App. B-2 of SURVEY.md) */
   float *pos;  float *norm;  int32_t *ep;  float *surf;  float *vol;  int32_t *cell_idx; uint32_t *fpos;
   int32_t *sbid; /* int[nvert+nbe]: special-boundary id (KENT) of vertices, then segments; NULL when nsb == 0 */
+  /* the same result arrays in HBM (context-owned, valid until the next cx_preprocess_host on this context): inputs of
+   * cx_assemble_records_device, so that the particle file can be produced without a host round trip */
+  float *d_pos; float *d_norm; int32_t *d_ep; float *d_surf; float *d_vol; uint32_t *d_fpos; int32_t *d_sbid;
   int64_t dimg[3];
   float zstat[4];
   cx_params params_fill;
@@ -245,6 +248,19 @@ int cx_write_h5sph_records(const void *records, int64_t n, const char *filename)
  * the vertex and segment records of special-boundary id k (k < num_kents, files without particles are skipped);
  * format 1 = vtu, 2 = h5sph (generic_output, src/crixus.cpp:261-289: "0." prefix and ".h5sph" suffix for h5sph). */
 int cx_write_split_records(const void *records, int64_t n, int64_t nfluid_particles, int32_t num_kents, const char *outname, int format);
+
+/* cx_assemble_records on the device (src/crixus.cu:973-1097): prefix sums over the bitfield popcounts / alive flags give every
+ * particle its final index, one thread per bitfield word / vertex / segment writes the 64-byte records into records_d.
+ * capacity: room in records_d (nfluid + nvert + nbe always suffices); records_d == NULL only counts.  *n_host = record count. */
+int cx_assemble_records_device(cx_ctx *ctx, const cx_params *pfill, const int64_t dimg[3], const uint32_t *fpos_d,
+                               const float *pos_d, const float *norm_d, const int32_t *ep_d, const float *surf_d,
+                               const float *vol_d, const int32_t *sbid_d /* may be NULL */, int64_t nvert, int64_t nbe,
+                               int64_t nfluid_for_indices, void *records_d, int64_t capacity, int64_t *n_host);
+/* vtk_output / hdf5_output (src/crixus.cpp:62-259 / 12-60) from DEVICE records: the file body is laid out by a kernel and
+ * streamed to the file through pinned staging buffers (copy of chunk c+1 overlaps the write of chunk c).  Same bytes as
+ * cx_write_vtu_records / cx_write_h5sph_records. */
+int cx_write_vtu_records_device(cx_ctx *ctx, const void *records_d, int64_t n, const char *filename);
+int cx_write_h5sph_records_device(cx_ctx *ctx, const void *records_d, int64_t n, const char *filename);
 
 /* what `Crixus file.ini` does (crixus_main, src/crixus.cu:31-1237, hot path only): ini -> STL -> GPU -> output file */
 int cx_run_ini(const char *ini_path);

@@ -98,6 +98,72 @@ def test_preprocess_host_vs_oracle(name, oracle, cuda_backend):
         assert not job.pos
 
 
+REC = np.dtype([(n, "<f4") for n in ("x", "y", "z", "nx", "ny", "nz", "vol", "surf")] +
+               [(n, "<i4") for n in ("kpar", "kfluid", "kent", "kparmob", "iref", "ep1", "ep2", "ep3")])
+
+
+@pytest.mark.parametrize("name", ["plate", "spheric2_mini", "channel", "channel_yz", "cube_sb", "plate_sb_stress", "config2_l1"])
+def test_device_records_equal_host_records(name, cuda_backend, tmp_path):
+    """cx_assemble_records_device + the streamed device writers against the host restatement of crixus.cu:973-1097 /
+    crixus.cpp:12-259 (cx_assemble_records, itself checked against numpy in tests/test_frontend.py and, through the CLI, against
+    the reference binary's files): same records, byte-identical .vtu and .h5sph files."""
+    if name == "config2_l1":      # 1.9e5 triangles, ~1e6 particles: several scan blocks and staging chunks
+        from crixus_b200 import workloads as wl
+        w = wl.spheric2_family(wl.SPHERIC2_DR / 2, 1.25, levels=1, base_dr=wl.SPHERIC2_DR)
+        c = dict(cases.case("spheric2_mini"), tris=np.ascontiguousarray(w["tris"], dtype=np.float32),
+                 normals=np.ascontiguousarray(w["normals"], dtype=np.float32), dr=np.float32(w["dr"]),
+                 fills=[("geometry", (0.5, 0.5, 0.5), float(w["dr"]))])
+    else:
+        c = cases.case(name)
+    ctx = cuda_backend.ctx
+    job, keep = _job_for(c)
+    ctx.preprocess_host(job)
+    for nfl_idx in (int(job.nfluid), int(job.nfluid) + 1):   # the reference's racy count shifts the vertex indices (DESIGN.md §5)
+        n = ctx.L.cx_assemble_records(C.byref(job), nfl_idx, None, 0)
+        host = np.zeros(n, dtype=REC)
+        assert ctx.L.cx_assemble_records(C.byref(job), nfl_idx, host.ctypes.data, n) == n
+        dev = ctx.assemble_records_device(job, nfl_idx)
+        assert dev.shape[0] == n
+        assert dev.cpu().numpy().tobytes() == host.tobytes()
+    if c["special"]:
+        assert host["kent"].max() > 0
+    dev = ctx.assemble_records_device(job)
+    n = dev.shape[0]
+    host = np.frombuffer(dev.cpu().numpy().tobytes(), dtype=REC)
+    for fmt, hostfn in (("vtu", ctx.L.cx_write_vtu_records), ("h5sph", ctx.L.cx_write_h5sph_records)):
+        a, b = str(tmp_path / ("host." + fmt)), str(tmp_path / ("dev." + fmt))
+        assert hostfn(host.ctypes.data, n, a.encode()) == 0
+        ctx.write_records_device(dev, b, fmt)
+        assert open(a, "rb").read() == open(b, "rb").read(), fmt
+    ctx.L.cx_job_free(C.byref(job))
+    assert not job.d_pos
+
+
+def test_cli_device_and_host_assembly_write_identical_files(tmp_path):
+    """`crixus case.ini` with the default device-side assembly / streamed writers and with CX_HOST_ASSEMBLY=1: identical files,
+    unsplit and split, vtu and h5sph."""
+    import glob
+    name = "cube_sb"
+    outs = {}
+    for mode in ("device", "host"):
+        for fmt in ("vtu", "h5sph"):
+            for split in (False, True):
+                d = tmp_path / ("%s_%s_%d" % (mode, fmt, split))
+                d.mkdir()
+                os.environ["CX_HOST_ASSEMBLY"] = "1" if mode == "host" else "0"
+                try:
+                    _, out = _run_cli(d, name, fmt, split=split)
+                finally:
+                    os.environ.pop("CX_HOST_ASSEMBLY", None)
+                assert ("(%s)" % mode) in out
+                files = sorted(glob.glob(str(d / "*.vtu")) + glob.glob(str(d / "*.h5sph")))
+                assert len(files) == (5 if split else 1)
+                outs[(mode, fmt, split)] = {os.path.basename(f): open(f, "rb").read() for f in files}
+    for fmt in ("vtu", "h5sph"):
+        for split in (False, True):
+            assert outs[("device", fmt, split)] == outs[("host", fmt, split)], (fmt, split)
+
+
 def _run_cli(tmp_path, name, fmt, split=False):
     sys.path.insert(0, os.path.join(HERE, "golden"))
     from make_golden import write_ini, write_special
