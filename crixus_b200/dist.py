@@ -133,7 +133,7 @@ class ShardedHotPath:
     """Device-resident hot path for bench.py: holds the welded mesh in HBM and runs one pass per step()."""
     STAGES = ["restore", "set_bound_elem", "binning", "trisize", "vert_volume", "fill"]
 
-    def __init__(self, ctx, w, rank=0, world=1):
+    def __init__(self, ctx, w, rank=0, world=1, byte_stats=True):
         import torch
         from . import api
         self.ctx, self.w, self.rank, self.world = ctx, w, rank, world
@@ -195,6 +195,9 @@ class ShardedHotPath:
         self.mean_trisize = float(ts[alive].mean())
         own = ((np.arange(nv) // VV_CHUNK) % world) == rank
         self.local_verts = int((alive & own).sum())
+        self.vv_bytes, self.vv_kernel_ms = 0.0, 1.0
+        if not byte_stats:      # the S27 statistic below costs 27 passes over the 3dr-cell grid on the host (minutes at 1e10 cells)
+            return
         cnt = np.diff(self.cell_idx.cpu().numpy()).reshape(self.p.gridn[0], self.p.gridn[1], self.p.gridn[2]).astype(np.int64)
         pad = np.pad(cnt, 1)
         s27 = sum(pad[1 + a:pad.shape[0] - 1 + a, 1 + b:pad.shape[1] - 1 + b, 1 + c:pad.shape[2] - 1 + c]

@@ -33,24 +33,30 @@ def _op(p):
     return q
 
 
-def build(kind, size):
+def build(kind, size, mesh=True):
+    v = t = n = None
     if kind == "channel":
         dr = 0.01
-        v, t, n = mg.channel(n=size, dr=dr)
-        L, H = size * 1.25 * dr, float(v[:, 2].max())
+        H = max(6, size // 4) * 1.25 * dr
+        if mesh:
+            v, t, n = mg.channel(n=size, dr=dr)
+            H = float(v[:, 2].max())
+        L = size * 1.25 * dr
         w = dict(dr=np.float32(dr), swap_normals=True, periodic=(True, True, False), fills=[("geometry", (L / 2, L / 2, H / 2), np.float32(dr))])
     elif kind == "sphere":
         dr = 1.0 / size
-        v, t, n = mg.sphere_in_tank(side_cells=size, dr=dr, hfac=0.5, sphere_levels=7 if size >= 400 else 5)
+        if mesh:
+            v, t, n = mg.sphere_in_tank(side_cells=size, dr=dr, hfac=0.5, sphere_levels=7 if size >= 400 else 5)
         w = dict(dr=np.float32(dr), swap_normals=True, periodic=(False, False, False), fills=[("geometry", (4 * dr, 4 * dr, 4 * dr), np.float32(dr))])
     elif kind == "tank":
         dr = 1.0 / size
-        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.53 * dr, inward=False)
+        if mesh:
+            v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.53 * dr, inward=False)
         w = dict(dr=np.float32(dr), swap_normals=True, periodic=(False, False, False), fills=[("geometry", (0.5, 0.5, 0.5), np.float32(dr))])
     else:
         raise SystemExit("unknown configuration " + kind)
     w.update(zero_open=False, container=None, fshape=None, name="%s %d" % (kind, size))
-    return v, t, n, w
+    return (v, t, n, w) if mesh else w
 
 
 def main():
@@ -61,31 +67,53 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {"config": kind, "size": size, "n_gpus": world}
-    t0 = time.time()
-    v, t, n, w = build(kind, size)
-    out["mesh_gen_s"] = time.time() - t0
-    nbe = t.shape[0]
-    corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
     ctx = api.Context(local)
     dev = ctx.device
-    # ---- device weld (timed twice: first call grows the scratch arena)
-    dc = torch.from_numpy(corners).to(dev)
-    for rep in range(2):
-        torch.cuda.synchronize()
+    if rank == 0:      # rank 0 generates and welds the mesh; the other ranks receive the welded arrays over NCCL
         t0 = time.time()
-        pos4, ep4, lo, hi = ctx.weld_device(dc, w["dr"])
-        torch.cuda.synchronize()
-        out["weld_device_s"] = time.time() - t0
-    nv = int(pos4.shape[0])
-    out.update(triangles=int(nbe), vertices=nv, generator_vertices=int(v.shape[0]))
-    assert nv == v.shape[0], "device weld found %d vertices, the indexed generator mesh has %d" % (nv, v.shape[0])
-    norm4 = np.zeros((nbe, 4), dtype=np.float32)
-    norm4[:, :3] = n
+        v, t, n, w = build(kind, size)
+        out["mesh_gen_s"] = time.time() - t0
+        nbe = t.shape[0]
+        corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
+        # ---- device weld (timed twice: first call grows the scratch arena)
+        dc = torch.from_numpy(corners).to(dev)
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            pos4, ep4, lo, hi = ctx.weld_device(dc, w["dr"])
+            torch.cuda.synchronize()
+            out["weld_device_s"] = time.time() - t0
+        nv = int(pos4.shape[0])
+        out.update(triangles=int(nbe), vertices=nv, generator_vertices=int(v.shape[0]))
+        assert nv == v.shape[0], "device weld found %d vertices, the indexed generator mesh has %d" % (nv, v.shape[0])
+        norm4 = np.zeros((nbe, 4), dtype=np.float32)
+        norm4[:, :3] = n
+        del dc, corners, v, t, n
+        norm4_d = torch.from_numpy(norm4).to(dev) if world > 1 else None
+    else:
+        w = build(kind, size, mesh=False)
+    if world > 1:
+        hdr = torch.zeros(8, dtype=torch.float64, device=dev)
+        if rank == 0:
+            hdr[:] = torch.tensor([nbe, nv] + [float(x) for x in lo] + [float(x) for x in hi], dtype=torch.float64)
+        dist.broadcast(hdr, 0)
+        h = hdr.cpu().numpy()
+        nbe, nv = int(h[0]), int(h[1])
+        lo, hi = h[2:5].astype(np.float32), h[5:8].astype(np.float32)
+        if rank != 0:
+            pos4 = torch.empty((nv, 4), dtype=torch.float32, device=dev)
+            ep4 = torch.empty((nbe, 4), dtype=torch.int32, device=dev)
+            norm4_d = torch.empty((nbe, 4), dtype=torch.float32, device=dev)
+        for x in (pos4, ep4, norm4_d):
+            dist.broadcast(x, 0)
+        if rank != 0:
+            norm4 = norm4_d.cpu().numpy()
+        del norm4_d
     w.update(nvert=nv, nbe=nbe, pos=pos4.cpu().numpy(), ep=ep4.cpu().numpy(), norm=norm4, bbmin=lo, bbmax=hi)
-    del dc, pos4, ep4, corners
+    del pos4, ep4
     torch.cuda.empty_cache()
     # ---- hot path, device resident
-    hp = ShardedHotPath(ctx, w, rank, world)
+    hp = ShardedHotPath(ctx, w, rank, world, byte_stats=False)
     torch.cuda.synchronize()
     steps = 2
     if world > 1:
@@ -147,7 +175,8 @@ def main():
     # cells near the walls are the interesting ones: sample in the boundary layers of the lattice and around the seed
     pairs = []
     tries = 0
-    while len(pairs) < 600 and tries < 4_000_000:
+    want_pairs = int(os.environ.get("CX_LARGE_CLOSURE_PAIRS", "600"))
+    while len(pairs) < want_pairs and tries < 4_000_000:
         tries += 1
         ax = int(rng.integers(0, 3))
         c = [int(rng.integers(0, dimg[a])) for a in range(3)]
