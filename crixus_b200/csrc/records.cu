@@ -36,28 +36,27 @@ __global__ void __launch_bounds__(256) k_rec_flags(const uint32_t *__restrict__ 
   }
 }
 
-// fluid particles, crixus.cu:991-1019: one thread per bitfield word
+// fluid particles, crixus.cu:991-1019: one warp per bitfield word, one lane per bit -- the set lanes of a warp write a contiguous
+// run of records (rank inside the word = popcount of the lower set bits)
 __global__ void __launch_bounds__(256) k_rec_fluid(const uint32_t *__restrict__ fpos, const int32_t *__restrict__ wbase, int64_t nwords,
                                                    int64_t d0, int64_t d1, float3 fcmin, float dr, float fluid_vol, Rec *__restrict__ rec)
 {
-  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t bits = fpos[w];
-    int32_t k = wbase[w];
-    while (bits) {
-      const int l = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int64_t j = w * 32 + l;
-      const int64_t m = j / (d1 * d0), n = j % (d1 * d0);
-      Rec r = {};
-      r.z = fadd(fcmin.z, fmul(dr, (float)m));          // host code of the reference: no fused multiply-add
-      r.y = fadd(fcmin.y, fmul(dr, (float)(n / d0)));
-      r.x = fadd(fcmin.x, fmul(dr, (float)(n % d0)));
-      r.vol = fluid_vol;
-      r.kpar = 1; r.kfluid = 1;
-      r.iref = k;
-      store_rec(rec + k, r);
-      k++;
-    }
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarp) {
+    const uint32_t bits = __ldg(fpos + w);
+    if (!(bits >> lane & 1u)) continue;
+    const int32_t k = __ldg(wbase + w) + __popc(bits & ((1u << lane) - 1u));
+    const int64_t j = w * 32 + lane;
+    const int64_t m = j / (d1 * d0), n = j % (d1 * d0);
+    Rec r = {};
+    r.z = fadd(fcmin.z, fmul(dr, (float)m));          // host code of the reference: no fused multiply-add
+    r.y = fadd(fcmin.y, fmul(dr, (float)(n / d0)));
+    r.x = fadd(fcmin.x, fmul(dr, (float)(n % d0)));
+    r.vol = fluid_vol;
+    r.kpar = 1; r.kfluid = 1;
+    r.iref = k;
+    store_rec(rec + k, r);
   }
 }
 
