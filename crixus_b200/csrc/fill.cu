@@ -124,6 +124,9 @@ struct FillArgs {
   int resolved_all;             // every hard cell of the owned planes was resolved up front (no per-round resolve)
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
+  int64_t w_lo, w_hi;           // word range k_unpack / k_pack walk (slab calls: the owned planes, +-1 halo plane for k_unpack)
+  long long item_lo, item_hi;   // item range of the up-front resolve (slab calls: the tile layers of the owned planes)
+  int classify_inline;          // up-front resolve computes the hard mask itself (no k_classify pass over the lattice)
   const float4 *rec;            // per-segment invariants of checkCollision (k_seg_prep), 8 x float4 per segment
   float rrej;                   // plane distance beyond which a well-formed triangle cannot matter
   float drw2;                   // dr_wall*dr_wall
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(256) k_cell3_flags(cx_params p, const int32_t 
 __global__ void __launch_bounds__(256) k_unpack(FillArgs A, const uint32_t *__restrict__ fpos)
 {
   const int64_t rows = (int64_t)A.dimg[1] * A.dimg[2];
-  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t wi = A.w_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.w_hi; wi += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = wi / A.wr;
     const int wx = (int)(wi - row * A.wr);
     if (row >= rows) continue;
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(256) k_unpack(FillArgs A, const uint32_t *__re
 
 __global__ void __launch_bounds__(256) k_pack(FillArgs A, uint32_t *__restrict__ fpos)
 {
-  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t wi = A.w_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.w_hi; wi += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t v = A.F[wi];
     if (!v) continue;
     const int64_t row = wi / A.wr;
@@ -439,6 +442,33 @@ __global__ void __launch_bounds__(256) k_classify(FillArgs A)
   }
 }
 
+// the same hard mask for one 32-cell word, computed by a warp (lane = cell): used by the up-front resolve so that no
+// separate pass over the whole lattice is needed (at 1e10 cells k_classify alone is ~0.1 s, and it does not shard)
+__device__ __forceinline__ uint32_t classify_word_warp(const FillArgs &A, int wx, int j, int k, int lane)
+{
+  const cx_params &p = A.p;
+  const int nvalid = min(32, A.dimg[0] - wx * 32);
+  const uint32_t vmask = nvalid < 32 ? (1u << nvalid) - 1u : 0xffffffffu;
+  if (A.all_hard || *A.all_hard_d) return vmask;
+  int hard = 0;
+  if (lane < nvalid) {
+    const float sy = ffma((float)j, p.dr, p.fcmin[1]), sz = ffma((float)k, p.dr, p.fcmin[2]);
+    const int gy = cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]), gz = cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]);
+    const float sx = ffma((float)(wx * 32 + lane), p.dr, p.fcmin[0]);
+    const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
+    hard = A.nbflag[((int64_t)gx * p.gridn[1] + gy) * p.gridn[2] + gz];
+    for (int t = 0; t < A.nfs && !hard; t++) {
+      const FsDesc &f = A.fs[t];
+      if (sx >= f.lo[0] && sx <= f.hi[0] && sy >= f.lo[1] && sy <= f.hi[1] && sz >= f.lo[2] && sz <= f.hi[2]) hard = 1;
+      else if (f.quirk) {
+        const float a = f.n[0] * (sx - f.v0[0]) + f.n[1] * (sy - f.v0[1]) + f.n[2] * (sz - f.v0[2]);
+        if (fabsf(a) < 4.f * p.eps) hard = 1;
+      }
+    }
+  }
+  return __ballot_sync(0xffffffffu, hard) & vmask;
+}
+
 __global__ void k_seed(FillArgs A, int64_t seed)
 {
   if (seed < 0) return;
@@ -479,14 +509,24 @@ __global__ void __launch_bounds__(256, 3) k_resolve_tiles(FillArgs A)
     long long item = 0;
     if (lane == 0) item = ALL ? (long long)atomicAdd((unsigned long long *)A.count64, 1ull) : (long long)atomicAdd(&A.count[3], 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (ALL && A.res_nparts > 1) item = ((item >> 6) * A.res_nparts + A.res_part) * 64 + (item & 63);   // interleaved sharding
-    if (item >= (ALL ? A.ntiles : (long long)A.count[2]) * FT_THREADS) break;
+    if (ALL && A.res_nparts > 1) {   // interleaved sharding: every group of nparts 64-item chunks is dealt one chunk per rank, the
+      const long long g = item >> 6;   // order rotated by a hash of the group (plane-aligned walls would otherwise land on few ranks)
+      const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)A.res_nparts);
+      item = (g * A.res_nparts + (A.res_part + rot) % A.res_nparts) * 64 + (item & 63);
+    }
+    if (ALL) item += A.item_lo;
+    if (item >= (ALL ? A.item_hi : (long long)A.count[2] * FT_THREADS)) break;
     const int tile = ALL ? (int)(item / FT_THREADS) : A.rlist[item / FT_THREADS], wt = (int)(item % FT_THREADS);
     const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
     const int j = tyi * FT_Y + wt % FT_Y, k = tzi * FT_Z + wt / FT_Y;
     if (j >= A.dimg[1] || k >= A.dimg[2] || k < A.k_lo || k >= A.k_hi) continue;
     const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
-    uint32_t todo = A.H[wi] & ~A.F[wi];
+    uint32_t hw;
+    if (ALL && A.classify_inline) {
+      hw = classify_word_warp(A, wx, j, k, lane);
+      if (lane == 0) A.H[wi] = hw;
+    } else hw = A.H[wi];
+    uint32_t todo = hw & ~A.F[wi];
     if (!todo) continue;
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
     while (todo) {
@@ -608,7 +648,7 @@ struct FillState {
   const uint32_t *fpos_key = nullptr;
   int64_t dimg[3] = {0, 0, 0};
   int64_t nbe = 0, cnbe = 0;
-  uint32_t *F = nullptr, *H = nullptr, *B = nullptr;
+  uint32_t *F = nullptr, *B = nullptr;   // B: 6 blocked planes + the hard mask
   float4 *rec = nullptr;
   int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0;
   uint8_t *nbflag = nullptr, *act = nullptr, *tile_res = nullptr;
@@ -623,7 +663,7 @@ void cx_fill_state_free(cx_ctx *ctx)
 {
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
-  cudaFree(s->F); cudaFree(s->H); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
+  cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
   cudaFree(s->count); cudaFree(s->fs); cudaFree(s->tile_res); cudaFree(s->rlist); cudaFree(s->rec);
   delete s;
   ctx->fill_state = nullptr;
@@ -688,11 +728,12 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     }
     // buffers are kept between calls and only grow (cudaMalloc/cudaFree cost milliseconds and synchronise)
     if (nw > s->cap_nw) {
-      cudaFree(s->F); cudaFree(s->H); cudaFree(s->B);
-      s->F = s->H = s->B = nullptr; s->cap_nw = 0;
+      // the hard mask lives right behind the six blocked planes: one buffer of 7 planes, so that a multi-GPU caller merges
+      // mask and planes with a single all-reduce (cx_fill_resolve_part)
+      cudaFree(s->F); cudaFree(s->B);
+      s->F = s->B = nullptr; s->cap_nw = 0;
       CX_CUDA(ctx, cudaMalloc(&s->F, sizeof(uint32_t) * (size_t)nw));
-      CX_CUDA(ctx, cudaMalloc(&s->H, sizeof(uint32_t) * (size_t)nw));
-      CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 6));
+      CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 7));
       s->cap_nw = nw;
     }
     if (ntiles > s->cap_ntiles) {
@@ -719,7 +760,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
     for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
     CX_CUDA(ctx, cudaMemsetAsync(s->tile_res, 0, (size_t)ntiles, st));
-    CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
+    CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 7, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)ntiles * 2, st));
     // fshape descriptors are built on the device (k_fs_desc): no host round trip
     s->nfs = (cnbe > 0 && cnbe <= FS_MAX_DESC) ? (int)cnbe : 0;
@@ -732,7 +773,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   for (int k = 0; k < 3; k++) A->dimg[k] = (int)dimg[k];
   A->wr = wr; A->ty = ty; A->tz = tz; A->ntiles = ntiles; A->nw = nw;
   A->k_lo = 0; A->k_hi = (int)dimg[2];
-  A->F = s->F; A->H = s->H; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
+  A->w_lo = 0; A->w_hi = nw;
+  A->item_lo = 0; A->item_hi = (long long)ntiles * FT_THREADS;
+  A->classify_inline = getenv("CX_FILL_LAZY") ? 0 : 1;
+  A->F = s->F; A->H = s->B + 6 * nw; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
   A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
   A->tile_res = s->tile_res; A->rlist = s->rlist;
   A->count64 = (unsigned long long *)(s->count + 4);
@@ -752,8 +796,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     }
     k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
     CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
-    k_classify<<<cx_blocks(nw, 256, ctx->num_sms * 16), 256, 0, st>>>(*A);
-    CX_LAUNCH_CHECK(ctx, "k_classify");
+    if (!A->classify_inline) {   // lazy per-round resolution (CX_FILL_LAZY=1, kept for comparison) reads the mask tile by tile
+      k_classify<<<cx_blocks(nw, 256, ctx->num_sms * 16), 256, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_classify");
+    }
   }
   *out = s;
   return CX_OK;
@@ -813,17 +859,28 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   const bool dbg = getenv("CX_DEBUG_TIMING") != nullptr;
   double t0 = 0, t1 = 0, t2 = 0;
   if (dbg) { cudaStreamSynchronize(ctx->stream); t0 = dbg_now(); }
-  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, first_call, &A, &s);
+  // first_call: 1 = start of a fill (state is rebuilt), 2 = start of a fill whose directed tests were resolved by
+  // cx_fill_resolve_part (+ the caller's merge of the blocked planes): the state is kept, the seed is still to be set
+  const bool pre_resolved = first_call == 2;
+  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, first_call == 1, &A, &s);
   if (rc != CX_OK) return rc;
   if (dbg) { cudaStreamSynchronize(ctx->stream); t1 = dbg_now(); }
   if (k_begin < 0 || k_end > A.dimg[2] || k_begin >= k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
+  if (pre_resolved && !(s->resolved_lo <= k_begin && s->resolved_hi >= k_end))
+    return cx_fail(ctx, CX_WRONG_INPUT, "fill: first_call = 2 without cx_fill_resolve_part");
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
+  // only the owned planes (and one halo plane either side) are touched: a rank of an N-GPU run does not pay for the lattice
+  const int64_t wplane = (int64_t)A.wr * A.dimg[1];
+  A.w_lo = wplane * (k_begin > 0 ? k_begin - 1 : 0);
+  A.w_hi = wplane * (k_end < A.dimg[2] ? k_end + 1 : k_end);
+  A.item_lo = (long long)(k_begin / FT_Z) * A.ty * A.wr * FT_THREADS;
+  A.item_hi = (long long)((k_end + FT_Z - 1) / FT_Z) * A.ty * A.wr * FT_THREADS;
   cudaStream_t st = ctx->stream;
   CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
   // a previous call that stopped at the round limit left its pending tile activations in the first half of s->act
   if (first_call || !ctx->fill_unfinished) CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
-  A.merge = first_call ? 0 : 1;
-  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  A.merge = first_call == 1 ? 0 : 1;
+  k_unpack<<<cx_blocks(A.w_hi - A.w_lo, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_unpack");
   if (first_call) {
     k_seed<<<1, 1, 0, st>>>(A, seed);
@@ -834,8 +891,8 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   // CX_FILL_LAZY=1 restores the per-round resolution of newly reached tiles.
   static const bool lazy = getenv("CX_FILL_LAZY") != nullptr;
   if (!lazy) {
-    if (first_call) { s->resolved_lo = s->resolved_hi = 0; }
-    if (s->resolved_lo != A.k_lo || s->resolved_hi != A.k_hi) {
+    if (first_call == 1) { s->resolved_lo = s->resolved_hi = 0; }
+    if (!(s->resolved_lo <= A.k_lo && s->resolved_hi >= A.k_hi)) {
       CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
       k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
       CX_LAUNCH_CHECK(ctx, "k_resolve_all");
@@ -850,7 +907,8 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
     t2 = dbg_now();
     fprintf(stderr, "[cx fill] prepare %.3f ms, rounds %.3f ms (%d rounds)\n", 1e3 * (t1 - t0), 1e3 * (t2 - t1), rounds_host ? *rounds_host : -1);
   }
-  k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  A.w_lo = wplane * k_begin; A.w_hi = wplane * k_end;   // only owned planes are written back
+  k_pack<<<cx_blocks(A.w_hi - A.w_lo, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_pack");
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CX_CUDA(ctx, cudaStreamSynchronize(st));
@@ -897,7 +955,7 @@ extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *f
   }
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
   if (blocked_d) *blocked_d = s->B;
-  if (blocked_words) *blocked_words = 6 * A.nw;
+  if (blocked_words) *blocked_words = 7 * A.nw;
   return CX_OK;
 }
 
@@ -924,7 +982,7 @@ extern "C" int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *f
   CX_LAUNCH_CHECK(ctx, "k_resolve_all");
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];
   if (blocked_d) *blocked_d = s->B;
-  if (blocked_words) *blocked_words = 6 * A.nw;
+  if (blocked_words) *blocked_words = 7 * A.nw;
   return CX_OK;
 }
 

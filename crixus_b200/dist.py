@@ -184,7 +184,8 @@ class ShardedHotPath:
         self.parallelism = "1 GPU" if world == 1 else (
             "vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; fill: %s; cheap stages and device weld replicated"
             % (VV_CHUNK, world, ("directed tests dealt to %d ranks in interleaved chunks, blocked planes all-reduced, flood replicated" % world) if small else
-               ("%d z-slabs, halo exchange every %d rounds" % (world, FILL_ROUNDS_PER_EXCHANGE))))
+               ("directed tests dealt to %d ranks in interleaved chunks, blocked planes all-reduced, flood in %d z-slabs with a halo "
+                "exchange every %d rounds" % (world, world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
         # one untimed pass to learn trisize (vertex-range balancing) and the S27 statistic for the byte count
@@ -291,8 +292,14 @@ class ShardedHotPath:
             else:
                 import torch.distributed as dist
 
+                # The directed tests (the expensive, geometry-only part) are dealt to the ranks in interleaved chunks -- z-slabs
+                # balance badly: the floor and lid slabs hold whole walls -- and the blocked planes + hard mask are merged by one
+                # all-reduce (disjoint words, zero elsewhere: SUM == OR); only the cheap flood is sharded by z-slab.
+                B = ctx.fill_resolve_part(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.world, self.rank)
+                dist.all_reduce(B)
+
                 def slab(fpos, seed_, k0, k1, first):
-                    n = ctx.fill_geometry_slab(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed_, k0, k1, first)
+                    n = ctx.fill_geometry_slab(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed_, k0, k1, 2 if first else 0)
                     self._rounds += ctx.last_rounds
                     return n, ctx.fill_unfinished()
                 self._rounds = 0

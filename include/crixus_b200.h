@@ -123,7 +123,10 @@ int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const fl
 /* z-slab variant for multi-GPU runs: this rank owns lattice planes [k_begin, k_end); fpos_d is still the full packed
  * bitfield on every rank (<= 1.25 GB at 1e10 cells) but only owned planes are written.  One call = propagate inside
  * the slab until locally converged, given the current state of the two halo planes (k_begin-1, k_end) in fpos_d.
- * *changed_host = number of cells newly set in the slab.  The caller exchanges boundary planes between calls. */
+ * *changed_host = number of cells newly set in the slab.  The caller exchanges boundary planes between calls.
+ * first_call: 1 = start of a fill (directed tests of the slab are resolved here), 0 = continuation, 2 = start of a fill whose
+ * directed tests were resolved by cx_fill_resolve_part / _slab and merged by the caller (balanced; see below).  Only the
+ * owned planes and one halo plane either side are touched, so a rank's cost does not grow with the whole lattice. */
 int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                           const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                           int64_t k_begin, int64_t k_end, int first_call, int64_t *changed_host, int32_t *rounds_host);
@@ -134,10 +137,11 @@ int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, con
 int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds);
 int cx_fill_unfinished(cx_ctx *ctx);
 
-/* Multi-GPU variant for lattices whose bit planes are small: the directed tests (pure functions of the geometry) are
- * resolved for planes [k_begin, k_end) only; *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32,
- * zero outside the slab) which the caller merges across ranks (rows are disjoint: SUM == OR); cx_fill_propagate then
- * runs the flood on the whole lattice on every rank.  No halo exchange, no per-sweep collective. */
+/* Multi-GPU: the directed tests (pure functions of the geometry) are resolved for planes [k_begin, k_end) only;
+ * *blocked_d points to the 6 "blocked" bit planes followed by the hard mask (*blocked_words uint32 = 7 planes, zero
+ * outside this rank's share) which the caller merges across ranks (words are disjoint: SUM == OR).  Then either
+ * cx_fill_propagate runs the flood on the whole lattice on every rank (small lattices: no halo exchange, no per-sweep
+ * collective) or cx_fill_geometry_slab(first_call = 2) floods by z-slab (large lattices). */
 int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
                          int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words);

@@ -174,7 +174,45 @@ def _check_fill(hp, oracle, nsample=1500):
         got = ctxs[r].fill_propagate(p, fr[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed)
         assert torch.equal(fr[r], f0), "sharded-tests/replicated-flood result differs from the unsharded fill"
         assert got == int(bits.sum()) - before
+    # ---- large-lattice multi-GPU path: directed tests dealt to the ranks, planes merged, flood by z-slab (first_call = 2)
+    fz = [torch.zeros_like(f0) for _ in range(n)]
+    for r in range(n):
+        for x in w["fills"]:
+            if x[0] == "box":
+                ctxs[r].fill_box(hp.pf, fz[r], x[1], x[2])
+    views = [ctxs[r].fill_resolve_part(p, fz[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, n, r) for r in range(n)]
+    totz = views[0].clone()
+    for r in range(1, n):
+        totz += views[r]
+    assert torch.equal(totz, totp)
+    for r in range(n):
+        views[r].copy_(totz)
     for c in ctxs:
+        c.fill_set_max_rounds(3)
+    first, total2 = True, 0
+    for outer in range(100000):
+        changed, unfinished = 0, 0
+        for r in range(n):
+            changed += ctxs[r].fill_geometry_slab(p, fz[r], gn, ge, gp, fnbe, hp.cnbe, hp.cell_idx, seed, ks[r][0], ks[r][1], 2 if first else 0)
+            unfinished += ctxs[r].fill_unfinished()
+        first = False
+        total2 += changed
+        if changed == 0 and unfinished == 0:
+            break
+        for r in range(n - 1):
+            for src, dst, k in ((r, r + 1, ks[r][1] - 1), (r + 1, r, ks[r + 1][0])):
+                a, b = (k * P) // 32, ((k + 1) * P + 31) // 32
+                fz[dst][a:b] |= fz[src][a:b]
+    assert total2 == total, (total2, total)
+    merged2 = torch.zeros_like(f0)
+    for r in range(n):
+        pb = np.unpackbits(fz[r].cpu().numpy().view(np.uint8), bitorder="little")
+        keep = np.zeros_like(pb)
+        keep[ks[r][0] * P: ks[r][1] * P] = 1
+        merged2 |= torch.from_numpy(np.packbits(pb & keep, bitorder="little").view(np.int32).copy()).to(merged2.device)
+    assert torch.equal(merged2, f0), "dealt-tests / z-slab-flood result differs from the unsharded fill"
+    for c in ctxs:
+        c.fill_set_max_rounds(0)
         c.close()
     # ---- closure: unset cells next to set cells must be blocked by the reference's predicate (oracle on a sample)
     pos, norm, ep = (t.cpu().numpy() for t in (gp, gn, ge))
