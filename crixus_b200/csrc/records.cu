@@ -134,7 +134,7 @@ extern "C" int cx_assemble_records_device(cx_ctx *ctx, const cx_params *pfill, c
   if (!ctx || !pfill || !dimg || !fpos_d || !pos_d || !norm_d || !ep_d || !surf_d || !vol_d || !n_host || nvert < 0 || nbe < 0)
     return CX_WRONG_INPUT;
   const int64_t G = dimg[0] * dimg[1] * dimg[2], nwords = (G + 31) / 32;
-  if (nwords + nvert + nbe >= (int64_t)1 << 31) return CX_WRONG_INPUT;   // 32-bit particle indices (AbsoluteIndex is an int)
+  if (nwords + 1 >= (int64_t)1 << 31 || nvert + 1 >= (int64_t)1 << 31 || nbe + 1 >= (int64_t)1 << 31) return CX_WRONG_INPUT;
   cudaStream_t st = ctx->stream;
   int32_t *wbase = nullptr, *abase = nullptr, *slot = nullptr, *flag = nullptr;
   CX_CUDA(ctx, cudaMallocAsync(&wbase, 4 * (size_t)(nwords + 1), st));
@@ -155,8 +155,12 @@ extern "C" int cx_assemble_records_device(cx_ctx *ctx, const cx_params *pfill, c
     CX_CUDA(ctx, cudaMemcpyAsync(&kmax, ctx->d_mail, 4, cudaMemcpyDeviceToHost, st));
   }
   CX_CUDA(ctx, cudaStreamSynchronize(st));
-  const int64_t nfl = tot[0], nalive = tot[1], n = nfl + nalive + nbe;
+  const int64_t nfl = (uint32_t)tot[0], nalive = tot[1], n = nfl + nalive + nbe;
   *n_host = n;
+  if (n >= (int64_t)1 << 31 || nfluid_for_indices + nvert >= (int64_t)1 << 31) {   // 32-bit particle indices (AbsoluteIndex,
+    cudaFreeAsync(wbase, st); cudaFreeAsync(abase, st);                              // VertexParticle are ints in both formats)
+    return cx_fail(ctx, CX_WRONG_INPUT, "records: more than 2^31 particles");
+  }
   if (!records_d) { cudaFreeAsync(wbase, st); cudaFreeAsync(abase, st); return CX_OK; }   // sizing call
   if (capacity < n) { cudaFreeAsync(wbase, st); cudaFreeAsync(abase, st); return CX_WRONG_INPUT; }
   if (sbid_d && kmax > 0) {   // stable grouping by KENT: one flag-scan per id (ids are few: the number of special-boundary grids)

@@ -95,3 +95,29 @@ def test_subdivide_is_watertight_and_scales():
     e = np.sort(np.concatenate([t2[:, [0, 1]], t2[:, [1, 2]], t2[:, [2, 0]]]), axis=1)
     _, cnt = np.unique(e, axis=0, return_counts=True)
     assert (cnt == 2).all()
+
+
+def test_ctypes_binding_covers_the_header(cxlib):
+    """crixus_b200/api.py declares argument types for every entry point of include/crixus_b200.h, and the ctypes mirror of
+    cx_job has the library's size (api.lib() checks it on load)."""
+    hdr = open(os.path.join(ROOT, "include", "crixus_b200.h")).read()
+    declared = set(re.findall(r"\b(cx_[a-z_0-9]+)\s*\(", hdr))
+    missing = sorted(declared - set(cxlib._declared))
+    assert not missing, "no ctypes signature for %s" % missing
+    assert cxlib.cx_job_sizeof() == ctypes.sizeof(api.CxJob)
+
+
+def test_null_context_is_rejected_without_a_gpu(cxlib):
+    """The stage entry points added for the rows either side of the hot path validate their arguments before touching the
+    device: CX_WRONG_INPUT (-11), never a crash."""
+    z = ctypes.c_void_p()
+    n = ctypes.c_int64(0)
+    p = api.CxParams()
+    d = (ctypes.c_int64 * 3)(1, 1, 1)
+    assert cxlib.cx_identify_special_boundary(z, ctypes.byref(p), z, z, z, 0, 0, z, z, 0, z, 1) == -11
+    assert cxlib.cx_assemble_records_device(z, ctypes.byref(p), d, z, z, z, z, z, z, z, 0, 0, 0, z, 0, ctypes.byref(n)) == -11
+    assert cxlib.cx_write_vtu_records_device(z, z, 0, b"/tmp/x.vtu") == -11
+    assert cxlib.cx_write_h5sph_records_device(z, z, 0, b"/tmp/x.h5sph") == -11
+    assert cxlib.cx_write_split_records(z, 3, 0, 1, b"x", 1) == -11
+    assert cxlib.cx_write_split_records(z, 0, 0, 0, b"x", 1) == -11
+    assert cxlib.cx_fill_geometry_slab(z, ctypes.byref(p), z, z, z, z, 0, 0, z, 0, 0, 1, 2, ctypes.byref(n), None) == -11
