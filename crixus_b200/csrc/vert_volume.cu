@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #define VV_WARPS 4
+#define VV_EST_DEFAULT false   // estimate-and-verify search in the narrow-band kernel (CX_VV_EST=0/1 overrides)
 #define VV_GS 41      // gres*2+1 voxels per axis (crixus_d.cu:280)
 #define VV_LINES (VV_GS * VV_GS)
 #define VV_PLANE_F4 10
@@ -47,6 +48,7 @@ struct VVArgs {
   int *big_list;             // vertices deferred to the TCAP=50 launch
   int *big_count;
   float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
+  float igdr;                // 1/gdr: voxel index of a z coordinate, m = g*igdr + 20 (estimate only, see mono_search_est)
 };
 
 // per-warp shared-memory working set; TCAP = max fan size it can hold.  Almost every vertex has <= 16 triangles, so the
@@ -160,10 +162,29 @@ __device__ __forceinline__ int mono_search(const float *gzt, bool pa, Pred pred)
   return s;
 }
 
+// Estimate-and-verify form of the same search.  Every plane expression is (up to rounding) linear in gz, so the flip index
+// can be predicted by solving the linear equation in fast float arithmetic (est = real-valued voxel index of the threshold
+// crossing).  The prediction is only a hint: it is accepted iff the exact predicate -- the same arithmetic as above -- holds
+// pa at voxel s and !pa at voxel s+1, which by monotonicity identifies the flip uniquely; otherwise (the crossing lies
+// within rounding of a voxel, |est - integer| <~ 1e-3) the lane takes the six-step search.  2 exact evaluations instead of 6.
+template <class Pred>
+__device__ __forceinline__ int mono_search_est(const float *gzt, bool pa, bool need, float est, Pred pred)
+{
+  int s = __float2int_rd(est);                 // NaN -> 0, +-inf saturate: clamped below
+  s = min(max(s, 0), VV_GS - 2);
+  const bool ok = (pred(gzt[s]) == pa) && (pred(gzt[s + 1]) != pa);
+  if (__any_sync(VV_FULLWARP, need && !ok)) {
+    VV_STAT(9, 1);
+    const int t = mono_search(gzt, pa, pred);
+    if (!ok) s = t;
+  }
+  return s;
+}
+
 // mask of the voxels where pv(f(gz[m])) holds.  fa, fb = f at the two ends.  lo = last index that agrees with end A
-// (40 if the line is not cut by the predicate), pa = the predicate at end A.
-template <class F, class PV>
-__device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float fb, F f, PV pv, int &lo, bool &pa)
+// (40 if the line is not cut by the predicate), pa = the predicate at end A.  EST: est = predicted crossing (see above).
+template <bool EST = false, class F, class PV>
+__device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float fb, F f, PV pv, int &lo, bool &pa, float est = 0.f)
 {
   pa = pv(fa);
   const bool pb = pv(fb);
@@ -172,7 +193,8 @@ __device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float 
   if (cutm) {
     VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
     const bool pa_ = pa;
-    const int s = mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
+    const int s = EST ? mono_search_est(gzt, pa_, pa != pb, est, [&](float g) { return pv(f(g)); })
+                      : mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
     if (pa != pb) lo = s;
   }
   // lmt[1][b] = the b lowest voxels, lmt[0][b] = the others (gzt + 64 floats = two tables of 64 x uint64)
@@ -239,8 +261,11 @@ __device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool 
 // against a band of 2*eps: for dr below ~2e-3 (length units of the mesh) a cut line has two or more voxels within eps
 // of a plane as a rule, and those lanes also need the flip of {f > -eps}.  The non-WIDE kernel leaves that (then
 // rare) case to exact_tri; the extra gated search costs ~8 % when it is never needed, hence two kernels.
-template <bool WIDE, class F>
-__device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig)
+// EST: (T, ek, ed) describe the linear form of f for the estimate: f(g) ~ T + (g + D)*C, crossing of threshold th at voxel
+// index (th - T)*ek + ed with ek = igdr/C, ed = 20 - D*igdr.
+template <bool WIDE, bool EST = false, class F>
+__device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig,
+                                           float T = 0.f, float ek = 0.f, float ed = 0.f)
 {
   const float neps = -eps;
   const bool pa = fa > eps, pb = fb > eps, Aa = fa > neps, Ab = fb > neps;
@@ -252,7 +277,8 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   const unsigned cutm = __ballot_sync(VV_FULLWARP, cutK || cutA);
   if (cutm) {
     VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
-    const int s = mono_search(gzt, qa, [&](float g) { return f(g) > th; });
+    const int s = EST ? mono_search_est(gzt, qa, cutK || cutA, ffma(fsub(th, T), ek, ed), [&](float g) { return f(g) > th; })
+                      : mono_search(gzt, qa, [&](float g) { return f(g) > th; });
     if (cutK || cutA) lo = s;
   }
   const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
@@ -374,7 +400,7 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
 
 // Second pass: the weight of one surviving z-line (in units of 2^-31), every lane of the warp on a line of its own.
 // Lanes without a line (valid == false) run along with an empty line.
-template <bool OPEN, bool WIDE, class VVWarp>
+template <bool OPEN, bool WIDE, bool EST, class VVWarp>
 __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
                                                  float gp1, bool valid)
 {
@@ -406,13 +432,19 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
     const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill<WIDE>(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps))))
+      plane_kill<WIDE, EST>(gzt, sVa, sVb, fV, eps, K, HV, trig, tV, EST ? __fdividef(a.igdr, P4.z) : 0.f,
+                            EST ? ffma(fsub(P5.y, pi.z), a.igdr, 20.f) : 0.f);
     if (OPEN) {
       const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
-      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill<WIDE>(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
+      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps))))
+        plane_kill<WIDE, EST>(gzt, s2a, s2b, fV2, eps, K, HV2, trig, tV2, EST ? __fdividef(a.igdr, P6.x) : 0.f,
+                              EST ? ffma(fsub(P6.w, pi.z), a.igdr, 20.f) : 0.f);
     }
     const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill<WIDE>(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps))))
+      plane_kill<WIDE, EST>(gzt, sEa, sEb, fE, eps, K, HE, trig, tE, EST ? __fdividef(a.igdr, P9.w) : 0.f,
+                            EST ? ffma(P4.z, a.igdr, 20.f) : 0.f);
     trig = trig && live;
     VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
@@ -448,9 +480,11 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     auto ge = [&](float v) { return !(v < neps); };
     int lo0, lo1, lo2;
     bool pa0, pa1, pa2;
-    const uint64_t IN0 = mono_mask(gzt, w0a, w0b, fW0, ge, lo0, pa0);
-    const uint64_t IN1 = mono_mask(gzt, w1a, w1b, fW1, ge, lo1, pa1);
-    const uint64_t IN2 = mono_mask(gzt, w2a, w2b, fW2, ge, lo2, pa2);
+    // estimate of the crossing of w = -eps: voxel index (neps - tW)*igdr/C + 20
+    const float ek0 = EST ? __fdividef(a.igdr, P7.z) : 0.f, ek1 = EST ? __fdividef(a.igdr, P8.y) : 0.f, ek2 = EST ? __fdividef(a.igdr, P9.x) : 0.f;
+    const uint64_t IN0 = mono_mask<EST>(gzt, w0a, w0b, fW0, ge, lo0, pa0, ffma(fsub(neps, tW0), ek0, 20.f));
+    const uint64_t IN1 = mono_mask<EST>(gzt, w1a, w1b, fW1, ge, lo1, pa1, ffma(fsub(neps, tW1), ek1, 20.f));
+    const uint64_t IN2 = mono_mask<EST>(gzt, w2a, w2b, fW2, ge, lo2, pa2, ffma(fsub(neps, tW2), ek2, 20.f));
     const uint64_t inside = IN0 & IN1 & IN2;
     // LT = {w0 < eps}.  On a line cut by IN0 it is the complement of IN0 plus the n voxels of IN0 next to the flip that
     // lie in the wall plane (n = 0 or 1 in all but degenerate cases).
@@ -476,7 +510,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     if (__any_sync(VV_FULLWARP, needLT)) {
       int lo_;
       bool pa_;
-      const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
+      const uint64_t m = mono_mask<EST>(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_, ffma(fsub(eps, tW0), ek0, 20.f));
       if (needLT) LT = m;
     }
     K = inside & ~LT;
@@ -535,7 +569,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   return valid ? group_weight(hit & alive, h, a.cmax) : 0ll;
 }
 
-template <int TCAP, bool LIST, bool WIDE>
+template <int TCAP, bool LIST, bool WIDE, bool EST = false>
 __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volume(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<TCAP> VVWarp;
@@ -754,7 +788,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
         const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
         const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
         const float h0 = gzt[kk], h1 = gzt[ll];
-        acc += closed ? line_weight<false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have) : line_weight<true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
+        acc += closed ? line_weight<false, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have)
+                      : line_weight<true, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
         const int took = min(qn, 32);
         qh = (qh + took) & 63;
         qn -= took;
@@ -820,6 +855,7 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   const float dr = p->dr, eps = p->eps;
   const float gdr = (float)(dr / 2.0 / (float)CX_GRES);               // crixus_d.cu:281
   for (int m = 0; m < VV_GS; m++) a.gz[m] = ((float)m - (float)(VV_GS - 1) / 2) * gdr;  // :493-495
+  a.igdr = 1.0f / gdr;
   const double thr_d = dr / 2. + eps;                                  // :535 (double)
   float thr = (float)thr_d;
   if ((double)thr > thr_d) thr = nextafterf(thr, -INFINITY);
@@ -841,13 +877,19 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   // see plane_kill<WIDE>: below this dr several voxels of a cut line lie within eps of a plane as a rule
   static const char *force_wide = getenv("CX_VV_WIDE");
   const bool wide = force_wide ? (force_wide[0] == '1') : (dr < 3.0e-3f);
+  // estimate-and-verify threshold search (mono_search_est): narrow-band kernel only -- at fine dr the crossing estimate is
+  // within rounding of a voxel too often (coordinates ~1 against a voxel step of dr/40) and the fallback search would run
+  static const char *force_est = getenv("CX_VV_EST");
+  const bool est = !wide && (force_est ? (force_est[0] == '1') : VV_EST_DEFAULT);
   if (wide) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, true>, VV_WARPS * 32, 0));
+  else if (est) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false, true>, VV_WARPS * 32, 0));
   else CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false>, VV_WARPS * 32, 0));
   if (bps < 1) bps = 1;
   int64_t want = (a.nown + VV_WARPS - 1) / VV_WARPS;
   int64_t grid = (int64_t)ctx->num_sms * bps;
   if (grid > want) grid = want;
   if (wide) k_vert_volume<VV_TCAP_SMALL, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else if (est) k_vert_volume<VV_TCAP_SMALL, false, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
   else k_vert_volume<VV_TCAP_SMALL, false, false><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
   CX_LAUNCH_CHECK(ctx, "k_vert_volume");
   // second launch: the (rare) vertices with more than 16 triangles, work list built by the first launch
