@@ -29,6 +29,13 @@ struct CopyStream {   // second stream + event for the overlapped download; rele
   cudaEvent_t e = nullptr;
   ~CopyStream() { if (s) cudaStreamDestroy(s); if (e) cudaEventDestroy(e); }
 };
+struct DevTmp {       // stream-ordered temporary, released on every exit path
+  void *p = nullptr;
+  cudaStream_t st = nullptr;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes, s); }
+  void *release() { void *q = p; p = nullptr; return q; }
+  ~DevTmp() { if (p) cudaFreeAsync(p, st); }
+};
 #define RC(call) do { int rc__ = (call); if (rc__ != CX_OK) return rc__; } while (0)
 #define CU(call) do { if ((call) != cudaSuccess) return CX_CUDA_ERROR; } while (0)
 }  // namespace
@@ -53,14 +60,15 @@ extern "C" int64_t cx_job_sizeof(void) { return (int64_t)sizeof(cx_job); }
 static int weld_grid(cx_ctx *ctx, cudaStream_t st, const float *corners, int64_t n, float dr, float **pos4_d, int32_t **ep4_d,
                      int64_t *nvert)
 {
-  float *c_d = nullptr;
-  CU(cudaMallocAsync((void **)&c_d, 36 * (size_t)n, st));
-  CU(cudaMallocAsync((void **)pos4_d, 48 * (size_t)n, st));
-  CU(cudaMallocAsync((void **)ep4_d, 16 * (size_t)n, st));
+  DevTmp c, pos, ep;
+  CU(c.alloc(36 * (size_t)n, st));
+  CU(pos.alloc(48 * (size_t)n, st));
+  CU(ep.alloc(16 * (size_t)n, st));
+  float *c_d = (float *)c.p;
   CU(cudaMemcpyAsync(c_d, corners, 36 * (size_t)n, cudaMemcpyHostToDevice, st));
   float lo[3], hi[3];
   RC(cx_bbox_device(ctx, c_d, 3 * n, lo, hi));
-  int rc = cx_weld_device(ctx, c_d, 3 * n, dr, lo, hi, *pos4_d, *ep4_d, nvert);
+  int rc = cx_weld_device(ctx, c_d, 3 * n, dr, lo, hi, (float *)pos.p, (int32_t *)ep.p, nvert);
   if (rc == CX_WELD_CELL_TOO_FULL) {
     std::vector<float> verts((size_t)9 * n), hp;
     std::vector<int32_t> ids((size_t)3 * n), he((size_t)4 * n, 0);
@@ -68,12 +76,14 @@ static int weld_grid(cx_ctx *ctx, cudaStream_t st, const float *corners, int64_t
     hp.assign((size_t)4 * *nvert, 0.f);
     for (int64_t v = 0; v < *nvert; v++) for (int k = 0; k < 3; k++) hp[4 * v + k] = verts[3 * v + k];
     for (int64_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) he[4 * i + k] = ids[3 * i + k];
-    CU(cudaMemcpy(*pos4_d, hp.data(), 16 * (size_t)*nvert, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(*ep4_d, he.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(pos.p, hp.data(), 16 * (size_t)*nvert, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ep.p, he.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
     rc = CX_OK;
   }
-  CU(cudaFreeAsync(c_d, st));
-  return rc;
+  RC(rc);
+  *pos4_d = (float *)pos.release();   // handed to the caller, who frees them after the tagging kernel
+  *ep4_d = (int32_t *)ep.release();
+  return CX_OK;
 }
 
 extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
@@ -226,10 +236,10 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
       int32_t *se = nullptr;
       int64_t snv = 0;
       RC(weld_grid(ctx, st, job->sb_corners[k], job->sb_nbe[k], dr, &sp, &se, &snv));
+      DevTmp gsp, gse;
+      gsp.p = sp; gsp.st = st; gse.p = se; gse.st = st;
       RC(cx_identify_special_boundary(ctx, &p, pos.as<float>(), ep.as<int32_t>(), cell_idx.as<int32_t>(), nvert, nbe, sp, se,
                                       job->sb_nbe[k], sbid.as<int32_t>(), k + 1));
-      CU(cudaFreeAsync(sp, st));
-      CU(cudaFreeAsync(se, st));
     }
     job->sbid = (int32_t *)(hbase + o_sbid);
     CU(cudaEventRecord(cs.e, st));
