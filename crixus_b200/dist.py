@@ -34,6 +34,26 @@ def split_range(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+FT_Y, FT_Z, DEAL_CHUNK = 16, 16, 64   # fill tiles (csrc/fill.cu FT_Y / FT_Z) and the chunk of the interleaved dealing
+
+
+def dealt_chunk_owner(chunk, nparts):
+    """Rank that resolves 64-item chunk `chunk` of the up-front directed tests (csrc/fill.cu, k_resolve_tiles<ALL>): every
+    group of nparts consecutive chunks is dealt one chunk per rank, the order rotated by a multiplicative hash of the group
+    number.  (Plain round-robin correlates with the tile layout: a lattice plane is rows 0..15 of every tile, i.e. chunk 0 of
+    4, so a plane-aligned wall would land on nparts/4 of the ranks.)  Vectorised over numpy arrays."""
+    chunk = np.asarray(chunk, dtype=np.int64)
+    g, slot = chunk // nparts, chunk % nparts
+    rot = ((g.astype(np.uint64) & np.uint64(0xFFFFFFFF)) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)
+    return ((slot - (rot % np.uint64(nparts)).astype(np.int64)) % nparts).astype(np.int64)
+
+
+def resolve_item_of_word(wx, j, k, wr, ty):
+    """work item of the up-front resolve that handles the 32-cell word (wx, row j, plane k): tile-major, 256 items per tile"""
+    tile = ((k // FT_Z) * ty + j // FT_Y) * wr + wx
+    return tile * (FT_Y * FT_Z) + (k % FT_Z) * FT_Y + j % FT_Y
+
+
 def split_weighted(weights, world, rank):
     """contiguous range [lo, hi) with ~equal sum of weights (vertex ranges balanced by trisize)"""
     c = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
