@@ -319,3 +319,76 @@ def test_split_output(fmt, tmp_path, cxlib, capfd, monkeypatch):
             np.testing.assert_array_equal(surf, rec["surf"][want])
     assert cxlib.cx_write_split_records(rec.ctypes.data, n, nfl, 2, base.encode(), fmt) == -18   # a KENT >= num_kents: INTERNAL_ERROR
     assert cxlib.cx_write_split_records(rec.ctypes.data, n, n + 1, 5, base.encode(), fmt) == -11
+
+
+def test_ini_reader_fuzz_against_reference(tmp_path, cxlib, refshim):
+    """600 generated .ini files built from the characters and line shapes inih treats specially (section brackets, '=' and
+    ':' separators, ';' after whitespace, '#', continuation lines, over-long lines / names / sections, BOM, CR LF, empty
+    names and values, repeated keys, garbage): ParseError and every lookup -- Get, GetInteger, GetReal, GetBoolean, in
+    mixed case -- must equal the reference's own INIReader (vendored inih, linked into oracle/_ref/libcrixus_refshim.so)."""
+    R = refshim.R
+    R.refshim_ini_open.restype = C.c_void_p
+    R.refshim_ini_open.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    R.refshim_ini_close.argtypes = [C.c_void_p]
+    R.refshim_ini_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    R.refshim_ini_get_integer.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_long]
+    R.refshim_ini_get_integer.restype = C.c_long
+    R.refshim_ini_get_real.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]
+    R.refshim_ini_get_real.restype = C.c_double
+    R.refshim_ini_get_boolean.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    rng = np.random.default_rng(20140327)
+    secs = ["mesh", "Mesh", "fill_0", "fill_1", "a b", "", "s" * 60, "x]y", "output"]
+    names = ["dr", "DR", "stlfile", "x seed", "", "n" * 70, "k;v", "a=b", "use", "name"]
+    vals = ["1", "0x1F", "-3.5e-2", "true", "Yes", "OFF", "maybe", "", "a ; b", "a;b", "tank.stl ;c", "v" * 250, "  padded  ", "1e400", "010",
+            "+7", ".5", "nan", "0x", "2 3", "=", ":", "[x]"]
+
+    def line():
+        k = rng.integers(0, 12)
+        sec, name, val = secs[rng.integers(len(secs))], names[rng.integers(len(names))], vals[rng.integers(len(vals))]
+        sep = [" = ", "=", ":", " : ", "\\t=\\t"][rng.integers(5)].replace("\\t", "\t")
+        if k == 0:
+            return "[%s]" % sec
+        if k == 1:
+            return "  [%s]  ; c" % sec
+        if k == 2:
+            return "[%s" % sec
+        if k == 3:
+            return "; comment %s" % val
+        if k == 4:
+            return "# %s" % val
+        if k == 5:
+            return "   " + val               # continuation (or an error / a key, depending on what precedes it)
+        if k == 6:
+            return ""
+        if k == 7:
+            return name                      # no separator
+        if k == 8:
+            return name + sep + val + " ; trailing"
+        return name + sep + val
+
+    checked = 0
+    for idx in range(600):
+        nl = ["\n", "\r\n"][idx % 7 == 0]
+        text = ("﻿" if idx % 11 == 0 else "") + nl.join(line() for _ in range(int(rng.integers(0, 14)))) + (nl if idx % 3 else "")
+        path = _write(tmp_path, text, "f%d.ini" % idx).encode()
+        err = C.c_int(0)
+        r = R.refshim_ini_open(path, C.byref(err))
+        h = api.VP()
+        mine = cxlib.cx_ini_open(path, C.byref(h))
+        assert mine == err.value, (idx, mine, err.value, text)
+        for sec in secs + ["MESH", "nope"]:
+            for name in names + ["Use", "nope"]:
+                a, b = C.create_string_buffer(1024), C.create_string_buffer(1024)
+                la = R.refshim_ini_get(r, sec.encode(), name.encode(), b"DEF", a, 1024)
+                lb = cxlib.cx_ini_get(h, sec.encode(), name.encode(), b"DEF", b, 1024)
+                assert (la, a.value) == (lb, b.value), (idx, sec, name, a.value, b.value, text)
+                if a.value != b"DEF":
+                    checked += 1
+                    assert R.refshim_ini_get_integer(r, sec.encode(), name.encode(), -7) == cxlib.cx_ini_get_integer(h, sec.encode(), name.encode(), -7), (idx, sec, name, a.value)
+                    ra, rb = R.refshim_ini_get_real(r, sec.encode(), name.encode(), -7.5), cxlib.cx_ini_get_real(h, sec.encode(), name.encode(), -7.5)
+                    assert ra == rb or (ra != ra and rb != rb), (idx, sec, name, a.value, ra, rb)
+                    for d in (0, 1):
+                        assert R.refshim_ini_get_boolean(r, sec.encode(), name.encode(), d) == cxlib.cx_ini_get_boolean(h, sec.encode(), name.encode(), d)
+        R.refshim_ini_close(r)
+        cxlib.cx_ini_close(h)
+    assert checked > 1000
