@@ -142,3 +142,29 @@ def test_triangle_size_vs_reference_tool(oracle, tmp_path):
         assert failed == ref_failed, (dr, failed, ref_failed)
         assert abs(mind - ref_min) < 1e-6 and abs(maxd - ref_max) < 1e-6
     assert oracle.triangle_size(v[t], np.float32(0.06))[0] == 0 and oracle.triangle_size(v[t], np.float32(0.03))[0] > 0
+
+
+def test_weld_fuzz_vs_reference(oracle, refshim, cxlib):
+    """remove_duplicate_vertices (src/crixus.cpp:343-455, the reference's own host code through the shim) against the oracle's
+    restatement AND the product's host weld (cx_weld_host, the checker of the device weld) on generated corner clouds: exact
+    duplicates, near-duplicates inside a cell (merged), across a cell border (kept apart, App. B-1), negative coordinates
+    ((int)(x/dr) truncates towards zero), shuffled order."""
+    from crixus_b200 import api
+    rng = np.random.default_rng(11)
+    for rep in range(25):
+        dr = np.float32(rng.choice([0.05, 0.1, 0.37]))
+        n = int(rng.integers(30, 400))
+        base = rng.uniform(-3 * dr, 6 * dr, size=(n, 3)).astype(np.float32)
+        snap = (np.round(base / dr) * dr).astype(np.float32)                      # points on cell borders
+        pts = np.concatenate([base, base, base + np.float32(3e-7) * dr, base[: n // 3] + np.float32(2e-5) * dr, snap,
+                              snap + np.float32(1e-6) * dr, snap - np.float32(1e-6) * dr])
+        pts = pts[rng.permutation(pts.shape[0])]
+        pts = np.ascontiguousarray(pts[: pts.shape[0] // 3 * 3], dtype=np.float32)
+        rv, re_ = refshim.weld(pts, dr)
+        ov, oe = oracle.weld(pts, dr)
+        hv, he = api.weld_host(pts, dr)
+        np.testing.assert_array_equal(ov, rv)
+        np.testing.assert_array_equal(oe, re_)
+        np.testing.assert_array_equal(hv, rv)
+        np.testing.assert_array_equal(he, re_)
+        assert rv.shape[0] < pts.shape[0]
