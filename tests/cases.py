@@ -181,3 +181,34 @@ def special_stress(tris, seed, n=160, skip=()):
         if kind not in skip:
             out.append([v0, v0 + ba, v0 + ca])
     return np.ascontiguousarray(np.array(out), dtype=np.float32)
+
+
+def generated(seed):
+    """A generated parity case: jittered closed tank (box + geometry fill, free-surface lid at a random height for even seeds)
+    or, for seed % 3 == 2, an x/y-periodic channel; dr, dr_wall, jitter amplitude and the fill seed are drawn from the seed."""
+    rng = np.random.default_rng(500 + seed)
+    dr = float(rng.choice([0.07, 0.08, 0.1]))
+    if seed % 3 == 2:
+        v, t, n = mg.channel(n=int(rng.integers(10, 18)), dr=dr, height=8 * 1.25 * dr)
+        L = float(v[:, 0].max())
+        c = dict(swap_normals=True, periodic=(True, True, False), container=None, fshape=None,
+                 fills=[("geometry", (L * rng.uniform(0.2, 0.8), L * rng.uniform(0.2, 0.8), 4 * 1.25 * dr), dr * float(rng.choice([0.5, 1.0, 1.5])))])
+    else:
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+        interior = ((v > 1e-6) & (v < 1 - 1e-6)).sum(1) == 2
+        v = v.copy()
+        ids = np.nonzero(interior)[0]
+        ids = ids[np.lexsort((v[ids, 2], v[ids, 1], v[ids, 0]))]
+        v[ids] += rng.uniform(-1, 1, size=(ids.size, 3)).astype(np.float32) * np.float32(rng.choice([0.0, 0.002, 0.004]))
+        n = mg.geometric_normals(v, t)
+        n[(n * (v[t].mean(1) - 0.5)).sum(1) > 0] *= -1
+        zl = float(rng.uniform(0.3, 0.8))
+        fs_t = np.array([[[0, 0, zl], [1, 0, zl], [1, 1, zl]], [[0, 0, zl], [1, 1, zl], [0, 1, zl]]], dtype=np.float32)
+        fs_n = np.array([[0, 0, 1], [0, 0, 1]], dtype=np.float32)
+        c = dict(swap_normals=False, periodic=(False, False, False), container=None,
+                 fills=[("box", (0.3, 0.3, 0.1), (0.5, 0.6, 0.2)),
+                        ("geometry", tuple(float(x) for x in rng.uniform(0.15, 0.85, 2)) + (zl * 0.5,), dr * float(rng.choice([0.5, 1.0, 1.5])))],
+                 fshape=(fs_t, fs_n) if seed % 2 == 0 else None)
+    c.update(name="generated%d" % seed, tris=np.ascontiguousarray(v[t], dtype=np.float32), normals=np.ascontiguousarray(n, dtype=np.float32),
+             dr=np.float32(dr), zero_open=False, special=[])
+    return c

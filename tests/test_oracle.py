@@ -168,3 +168,16 @@ def test_weld_fuzz_vs_reference(oracle, refshim, cxlib):
         np.testing.assert_array_equal(hv, rv)
         np.testing.assert_array_equal(he, re_)
         assert rv.shape[0] < pts.shape[0]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fill_and_mesh_stages_fuzz_vs_reference_host_shim(seed, oracle, refshim):
+    """Generated variants (cases.generated: jitter amplitude, dr, dr_wall, fill seed, a free-surface lid at a random height,
+    optional x/y periodic channel) through the stages up to the fill, oracle against the reference's own kernels compiled for
+    the host: set_bound_elem, binning, links, trisize and the fluid bitfield must be identical."""
+    c = cases.generated(seed)
+    o, r = cases.run(oracle, c, stages=("fill",)), cases.run(refshim, c, stages=("fill",))
+    for k in ("verts", "epv", "pre_ep", "pre_surf", "pre_bary", "cell_idx", "ep", "pos", "norm", "surf", "trisize", "fpos", "dimg"):
+        np.testing.assert_array_equal(o[k], r[k], err_msg=k)
+    assert o["fill_counts"] == r["fill_counts"] and o["nfluid"] == r["nfluid"] > 0
+    assert o["missing_partners"] == r["missing_partners"] == 0
