@@ -42,6 +42,7 @@ def analyse(i, pos, norm, ep, dr, rim_index):
     zA, zB = g[0], g[-1]
     touchV, touchE, touchW = [], [], []
     in01, in012, killW = [], [], []          # per line: some voxel inside planes 0&1 / inside the tetrahedron / removed by it
+    forms = []                               # per triangle: linear forms (vector, constant) of sV, sE, w0, w1, w2
     G3 = g[None, None, :]
     dead = np.zeros((GS, GS), dtype=bool)
     cutV, cutE, cutW = [], [], []
@@ -77,6 +78,7 @@ def analyse(i, pos, norm, ep, dr, rim_index):
         w0 = c9[0] * GX[:, :, None] + c9[1] * GY[:, :, None] + c9[2] * G3
         w1 = c10[0] * GX[:, :, None] + c10[1] * GY[:, :, None] + c10[2] * G3
         w2 = c11[0] * GX[:, :, None] + c11[1] * GY[:, :, None] + c11[2] * G3
+        forms.append(((e1, -e1.dot(e1) / 2), (en, -en.dot(e1)), (c9, 0.0), (c10, 0.0), (c11, 0.0)))
         i01 = (w0 >= -eps) & (w1 >= -eps)
         in01.append(i01.any(2))
         in012.append((i01 & (w2 >= -eps)).any(2))
@@ -113,6 +115,22 @@ def analyse(i, pos, norm, ep, dr, rim_index):
             mc = np.concatenate([cut[f], np.zeros((T, 1), dtype=bool)], 1)[:, b]
             res["%s_search_%s" % (name, f)] = int(mc.any(2).sum())
         res[name + "_iters"] = nb * T
+        # per-batch interval gating: bounding box of the batch's (x, y) offsets x {zA, zB}; a family of triangle t is skipped
+        # iff the upper bound of its expression over the box is <= -eps (walls: of one of the three expressions)
+        xs, ys = GX.ravel()[surv], GY.ravel()[surv]
+        ent = {"V": 0, "E": 0, "W": 0}
+        missed = 0
+        for bi in range(nb):
+            idx = b[bi][b[bi] >= 0]
+            lo = np.array([xs[idx].min(), ys[idx].min(), zA]); hi = np.array([xs[idx].max(), ys[idx].max(), zB])
+            for t_ in range(T):
+                ub = [np.maximum(vec * lo, vec * hi).sum() + c0 for vec, c0 in forms[t_]]
+                eV, eE, eW = ub[0] > -eps, ub[1] > -eps, min(ub[2], ub[3], ub[4]) >= -eps
+                ent["V"] += eV; ent["E"] += eE; ent["W"] += eW
+                missed += (fam["V"][t_, idx].any() and not eV) + (fam["E"][t_, idx].any() and not eE) + (fam["W"][t_, idx].any() and not eW)
+        for f in "VEW":
+            res["%s_bbox_%s" % (name, f)] = int(ent[f])
+        res[name + "_bbox_missed"] = int(missed)
         mw = np.concatenate([fam["W"], np.zeros((T, 1), dtype=bool)], 1)[:, b].any(2)          # wall iterations entered
         for k2, arr in extra.items():
             mm = np.concatenate([arr & fam["W"], np.zeros((T, 1), dtype=bool)], 1)[:, b].any(2)
@@ -151,6 +169,9 @@ def main():
               % (label, m["lanes_touch_" + f], need, m["index_entered_" + f], m["sector_entered_" + f], m["index_search_" + f],
                  m["sector_search_" + f], m["lanes_cut_" + f]))
     report_walls(m)
+    print("per-batch interval gating (bounding box of the batch, one lane per triangle): entered V %.0f E %.0f W %.0f (exact per-lane "
+          "gating: %.0f %.0f %.0f); blocks it would wrongly skip: %g" % (m["index_bbox_V"], m["index_bbox_E"], m["index_bbox_W"],
+          m["index_entered_V"], m["index_entered_E"], m["index_entered_W"], m["index_bbox_missed"]))
 
 
 def report_walls(m):
