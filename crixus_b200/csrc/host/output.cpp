@@ -7,29 +7,52 @@
 #include <string>
 
 // ---------------------------------------------------------------------------------------------- STL
+// Bulk reader with the outcome of the reference's per-value iostream loop (crixus.cu:137-221), malformed files included
+// (restated call by call in oracle/stl_reader.cpp and compared on truncated files in tests/test_frontend.py):
+//   * the loop runs min(count, floor(payload / 50) + 1) times -- the iteration in which the end of the file is hit still
+//     appends a facet, made of the bytes that were still there and, for the rest, the PREVIOUS facet's values;
+//   * READ_ERROR only if that differs from the count in the header (crixus.cu:218-221), i.e. a file whose last facet is cut
+//     short is accepted by the reference, and so it is here.
 int cx_read_stl(const std::string &filename, std::vector<float> &corners, std::vector<float> &normals)
 {
-  std::ifstream f(filename.c_str(), std::ios::in | std::ios::binary);
-  if (!f.is_open()) return CX_FILE_NOT_OPEN;
-  char head[80];
-  f.read(head, 80);
-  if (f.gcount() >= 5 && memcmp(head, "solid", 5) == 0) return CX_STL_NOT_BINARY;  // crixus.cu:137-153
+  corners.clear();
+  normals.clear();
+  FILE *f = fopen(filename.c_str(), "rb");
+  if (!f) return CX_FILE_NOT_OPEN;
+  unsigned char head[84];
+  memset(head, 0, sizeof(head));
+  const size_t got = fread(head, 1, sizeof(head), f);
+  if (got >= 5 && memcmp(head, "solid", 5) == 0) { fclose(f); return CX_STL_NOT_BINARY; }  // crixus.cu:137-153
   uint32_t n = 0;
-  f.read((char *)&n, 4);
-  corners.resize((size_t)9 * n);
-  normals.resize((size_t)3 * n);
-  uint32_t through = 0;
-  while (through < n && !f.eof()) {  // crixus.cu:188-213
-    float rec[12];
-    uint16_t attr;
-    f.read((char *)rec, 48);
-    f.read((char *)&attr, 2);
-    if (f.gcount() != 2) break;
-    memcpy(&normals[3 * (size_t)through], rec, 12);
-    memcpy(&corners[9 * (size_t)through], rec + 3, 36);
-    through++;
+  memcpy(&n, head + 80, 4);                       // a short read leaves the missing bytes untouched (zero here)
+  uint64_t avail = 0;
+  if (got == sizeof(head)) {
+    const long at = ftell(f);
+    if (fseek(f, 0, SEEK_END) == 0) {
+      const long end = ftell(f);
+      if (end > at) avail = (uint64_t)(end - at);
+    }
+    fseek(f, at, SEEK_SET);
   }
-  if (through != n) return CX_READ_ERROR;  // crixus.cu:218-221
+  const uint64_t m = got == sizeof(head) ? std::min<uint64_t>(n, avail / 50 + 1) : 0;   // facets the reference's loop appends
+  corners.resize((size_t)9 * m);
+  normals.resize((size_t)3 * m);
+  const size_t CH = 1 << 16;                      // facets per fread
+  std::vector<unsigned char> buf(CH * 50);
+  unsigned char rec[48];
+  memset(rec, 0, sizeof(rec));                    // m_v_floats before the first facet (uninitialised in the reference)
+  for (uint64_t i0 = 0; i0 < m; i0 += CH) {
+    const size_t cnt = (size_t)std::min<uint64_t>(CH, m - i0);
+    const size_t have = fread(buf.data(), 1, cnt * 50, f);
+    for (size_t i = 0; i < cnt; i++) {
+      const size_t off = i * 50, left = have > off ? have - off : 0;
+      memcpy(rec, buf.data() + off, std::min<size_t>(48, left));
+      memcpy(&normals[3 * (size_t)(i0 + i)], rec, 12);
+      memcpy(&corners[9 * (size_t)(i0 + i)], rec + 12, 36);
+    }
+  }
+  fclose(f);
+  if (m != n) return CX_READ_ERROR;               // crixus.cu:218-221
   return CX_OK;
 }
 

@@ -5,4 +5,5 @@ set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 gcc -std=c11 -O2 -fopenmp -mfma -ffp-contract=off -fno-fast-math -fPIC -shared -Wall -Wno-unused-function \
     "$HERE/crixus_oracle.c" -o "$HERE/liboracle.so" -lm
-echo "built $HERE/liboracle.so"
+g++ -std=c++17 -O1 -fPIC -shared -Wall "$HERE/stl_reader.cpp" -o "$HERE/liboracle_stl.so"
+echo "built $HERE/liboracle.so $HERE/liboracle_stl.so"

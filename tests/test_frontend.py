@@ -195,9 +195,10 @@ def test_stl_reader_edge_cases(tmp_path, cxlib):
     asc = str(tmp_path / "ascii.stl")
     open(asc, "wb").write(b"solid x" + raw[7:])
     assert _stl_read(cxlib, asc)[0] == -1
-    # record count larger than the file content: crixus.cu:218-221 -> READ_ERROR
+    # record count larger than the file content: crixus.cu:218-221 -> READ_ERROR, but only when more than the last facet is
+    # missing (the reference's loop still appends the facet during which it hits the end; see the fuzz test below)
     trunc = str(tmp_path / "trunc.stl")
-    open(trunc, "wb").write(raw[:-30])
+    open(trunc, "wb").write(raw[:-130])
     assert _stl_read(cxlib, trunc)[0] == -5
     # missing file -> FILE_NOT_OPEN; empty mesh (0 facets) reads fine
     assert _stl_read(cxlib, str(tmp_path / "missing.stl"))[0] == -3
@@ -392,3 +393,59 @@ def test_ini_reader_fuzz_against_reference(tmp_path, cxlib, refshim):
         R.refshim_ini_close(r)
         cxlib.cx_ini_close(h)
     assert checked > 1000
+
+
+def test_stl_reader_on_truncated_files_equals_reference_loop(tmp_path, cxlib):
+    """cx_stl_read (one bulk read) against oracle/stl_reader.cpp -- the reference's ingest loop restated with the same
+    istream::read calls in the same order (crixus.cu:137-221) -- on a file cut at every length around the facet records, with
+    wrong facet counts, and on a few megabytes of facets (several read chunks): same return code, same facets, byte for
+    byte.  Notably a file whose LAST facet is cut short is accepted by the reference: the facet is completed with the previous
+    facet's values."""
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "liboracle_stl.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["bash", os.path.join(os.path.dirname(so), "build_oracle.sh")])
+    O = C.CDLL(so)
+    O.orc_stl_read.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_long, C.POINTER(C.c_long)]
+    rng = np.random.default_rng(3)
+
+    def both(path, cap):
+        oc, on = np.zeros(cap * 9 + 9, dtype=np.float32), np.zeros(cap * 3 + 3, dtype=np.float32)
+        nf = C.c_long(0)
+        orc_rc = O.orc_stl_read(path.encode(), oc.ctypes.data_as(C.POINTER(C.c_float)), on.ctypes.data_as(C.POINTER(C.c_float)), cap + 1, C.byref(nf))
+        rc, out = _stl_read(cxlib, path)
+        assert rc == orc_rc, (path, rc, orc_rc)
+        if rc == 0:
+            assert out[0].shape[0] == nf.value
+            assert out[0].tobytes() == oc[: 9 * nf.value].tobytes() and out[1].tobytes() == on[: 3 * nf.value].tobytes()
+        return rc, (out[0].shape[0] if rc == 0 else -1)
+
+    nfac = 7
+    tris = rng.standard_normal((nfac, 3, 3)).astype(np.float32)
+    nrm = rng.standard_normal((nfac, 3)).astype(np.float32)
+    good = str(tmp_path / "g.stl")
+    mg.write_stl(good, tris, nrm)
+    raw = open(good, "rb").read()
+    assert len(raw) == 84 + 50 * nfac
+    accepted_short = 0
+    for cut in list(range(84, len(raw) + 1)):           # every length from "count only" to the whole file
+        p = str(tmp_path / "t.stl")
+        open(p, "wb").write(raw[:cut])
+        rc, n = both(p, nfac)
+        if rc == 0 and cut < len(raw) - 2:
+            accepted_short += 1
+    assert accepted_short >= 48                         # the last facet may be cut anywhere (or be missing entirely)
+    for count in (0, 1, nfac - 1, nfac + 1, nfac + 2, 2 ** 31 + 5, 2 ** 32 - 1):   # header count disagrees with the content
+        p = str(tmp_path / "c.stl")
+        open(p, "wb").write(raw[:80] + struct.pack("<I", count) + raw[84:])
+        both(p, nfac + 2)
+    big_n = 70000                                       # > one 65536-facet read chunk
+    bt, bn = rng.standard_normal((big_n, 3, 3)).astype(np.float32), rng.standard_normal((big_n, 3)).astype(np.float32)
+    big = str(tmp_path / "big.stl")
+    mg.write_stl(big, bt, bn)
+    assert both(big, big_n) == (0, big_n)
+    rawb = open(big, "rb").read()
+    open(big, "wb").write(rawb[:-17])
+    assert both(big, big_n) == (0, big_n)
+    open(big, "wb").write(rawb[:-67])
+    assert both(big, big_n)[0] == -5
