@@ -204,6 +204,12 @@ int cx_run_ini(const char *ini_path)
     fills.push_back(f);
   }
   job.fills = fills.data(); job.nfills = (int32_t)fills.size();
+  // a free-surface file that exists but is shorter than its facet count is a READ_ERROR at the first geometry fill
+  // (crixus.cu:869-872); it is reported here, before any GPU work (an input error of an earlier box fill would have come
+  // first in the reference: fix one, see the other)
+  if (frc == CX_READ_ERROR)
+    for (const cx_fill_spec &f : fills)
+      if (f.option == 2) { printf("Reading facets of fluid geometry ... [FAILED]\n"); return CX_READ_ERROR; }
 
   cx_ctx *ctx = nullptr;
   const double t_c0 = wall_s();

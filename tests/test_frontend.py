@@ -213,6 +213,21 @@ def test_run_ini_without_config_or_gpu(cxlib, tmp_path, capfd):
     assert cxlib.cx_run_ini(str(tmp_path / "nope.ini").encode()) == -4  # CANT_READ_CONFIG, crixus.cu:67-71
     ini = _write(tmp_path, "[mesh]\nstlfile=%s\ndr=0.1\n" % (tmp_path / "missing.stl"))
     assert cxlib.cx_run_ini(ini.encode()) == -3                        # FILE_NOT_OPEN
+    # input errors that the reference reports from its file readers are returned before any GPU work:
+    v, t, n = mg.plate(3, 0.1)
+    stl, fs, sb = str(tmp_path / "m.stl"), str(tmp_path / "m_fs.stl"), str(tmp_path / "m_sb.stl")
+    mg.write_stl(stl, v[t], n)
+    mg.write_stl(fs, v[t], n)
+    raw = open(fs, "rb").read()
+    open(fs, "wb").write(raw[:-120])                                   # free-surface file two facets short: READ_ERROR (crixus.cu:869-872)
+    open(sb, "wb").write(raw[:-120])
+    base = "[mesh]\nstlfile=%s\ndr=0.08\nfshape=%s\n" % (stl, fs)
+    ini = _write(tmp_path, base + "[fill_0]\noption=geometry\nxseed=0.1\nyseed=0.1\nzseed=0.1\n", "g.ini")
+    assert cxlib.cx_run_ini(ini.encode()) == -5
+    ini = _write(tmp_path, "[mesh]\nstlfile=%s\ndr=0.08\n[special_boundary_grids]\nmesh1=%s\n" % (stl, sb), "s.ini")
+    assert cxlib.cx_run_ini(ini.encode()) == -5                        # special-boundary grid short of facets (crixus.cu:564-567)
+    open(stl, "wb").write(b"solid " + raw[6:])
+    assert cxlib.cx_run_ini(ini.encode()) == -1                        # STL_NOT_BINARY
     capfd.readouterr()
 
 
