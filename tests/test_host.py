@@ -121,3 +121,35 @@ def test_null_context_is_rejected_without_a_gpu(cxlib):
     assert cxlib.cx_write_split_records(z, 3, 0, 1, b"x", 1) == -11
     assert cxlib.cx_write_split_records(z, 0, 0, 0, b"x", 1) == -11
     assert cxlib.cx_fill_geometry_slab(z, ctypes.byref(p), z, z, z, z, 0, 0, z, 0, 0, 1, 2, ctypes.byref(n), None) == -11
+
+
+def test_host_glue_fuzz_against_oracle(oracle, cxlib):
+    """cx_params_domain / _fill_eps / _container / cx_fill_dims / cx_seed_index (csrc/ctx.cu) against the oracle's independent
+    restatement of crixus.cu:262-283,464-467,698-722,799-804 on 2000 random domains, spacings, containers and seeds:
+    identical bytes / integers (float-to-int truncation, (extent+eps)/gridn, round() of a double expression)."""
+    rng = np.random.default_rng(42)
+    for it in range(2000):
+        scale = 10 ** rng.uniform(-3, 2)
+        lo = (rng.uniform(-1, 1, 3) * scale).astype(np.float32)
+        ext = (10 ** rng.uniform(-1.5, 0.5, 3) * scale).astype(np.float32)
+        hi = (lo + ext).astype(np.float32)
+        dr = np.float32(float(ext.min()) * 10 ** rng.uniform(-1.8, 0.3))
+        p, q = api.params_domain(dr, lo, hi), oracle.params_domain(dr, lo, hi)
+        assert bytes(p) == bytes(q), (it, lo, hi, dr)
+        for j in range(3):
+            p.per[j] = q.per[j] = int(rng.integers(0, 2))
+        api.params_fill_eps(p)
+        oracle.params_fill_eps(q)
+        if it % 2:
+            cmin = (lo + rng.uniform(-0.2, 0.5, 3).astype(np.float32) * ext).astype(np.float32)
+            cmax = (cmin + rng.uniform(0.05, 1.2, 3).astype(np.float32) * ext).astype(np.float32)
+            api.params_container(p, True, cmin, cmax)
+            oracle.params_container(q, True, cmin, cmax)
+        else:
+            api.params_container(p, False)
+            oracle.params_container(q, False)
+        assert bytes(p) == bytes(q), (it, "container")
+        np.testing.assert_array_equal(api.fill_dims(p), oracle.fill_dims(q))
+        for _ in range(3):
+            s = (lo + rng.uniform(-0.3, 1.3, 3).astype(np.float32) * ext).astype(np.float32)
+            assert api.seed_index(p, s) == oracle.seed_index(q, s), (it, s)
