@@ -49,13 +49,16 @@ class CxJob(C.Structure):
                 ("params_fill", CxParams),
                 ("tri_failed", C.c_int64), ("tri_mind", C.c_float), ("tri_maxd", C.c_float),
                 ("t_weld_s", C.c_double), ("t_gpu_s", C.c_double), ("t_h2d_s", C.c_double), ("t_d2h_s", C.c_double),
-                ("stage_ms", C.c_float * 8)]
+                ("stage_ms", C.c_float * 8),
+                ("out_sharded", C.c_int32),
+                ("seg_lo", C.c_int64), ("seg_hi", C.c_int64), ("vert_lo", C.c_int64), ("vert_hi", C.c_int64),
+                ("fword_lo", C.c_int64), ("fword_hi", C.c_int64)]
 
 
 ERRORS = {0: "CX_OK", -1: "STL_NOT_BINARY", -2: "NO_FILE", -3: "FILE_NOT_OPEN", -4: "CANT_READ_CONFIG", -5: "READ_ERROR",
           -6: "FLUID_NDEF", -7: "WRITE_FAIL", -9: "NO_PER_VERT", -11: "WRONG_INPUT", -16: "NO_WRITE_FILE",
           -17: "FLUID_BBOX_TOO_SMALL", -18: "INTERNAL_ERROR", -101: "CUDA_ERROR", -102: "TRIMAX_EXCEEDED",
-          -103: "FAN_INCOMPLETE", -104: "SEED_OUTSIDE", -105: "NO_DEVICE", -106: "WELD_CELL_TOO_FULL"}
+          -103: "FAN_INCOMPLETE", -104: "SEED_OUTSIDE", -105: "NO_DEVICE", -106: "WELD_CELL_TOO_FULL", -107: "NO_NCCL"}
 
 
 class CxError(RuntimeError):
@@ -113,6 +116,18 @@ def lib():
         "cx_fill_resolve_part": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, C.c_int, C.c_int, C.POINTER(VP), C.POINTER(I64)]),
         "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
         "cx_preprocess_host": (C.c_int, [VP, C.POINTER(CxJob)]),
+        "cx_preprocess_dist": (C.c_int, [VP, C.POINTER(CxJob)]),
+        "cx_dist_unique_id": (C.c_int, [VP]),
+        "cx_dist_init": (C.c_int, [VP, VP, C.c_int, C.c_int]),
+        "cx_dist_attach": (C.c_int, [VP, VP, C.c_int, C.c_int]),
+        "cx_dist_init_local": (C.c_int, [C.POINTER(VP), C.c_int]),
+        "cx_dist_finalize": (C.c_int, [VP]),
+        "cx_dist_world": (C.c_int, [VP]),
+        "cx_dist_rank": (C.c_int, [VP]),
+        "cx_dist_calc_vert_volume": (C.c_int, [VP, P, VP, VP, VP, VP, VP, VP, I64, I64, C.c_int]),
+        "cx_dist_fill_geometry": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
+        "cx_hash_u32": (C.c_int, [VP, VP, I64, C.POINTER(C.c_uint64)]),
+        "cx_dist_set_fill_mode": (C.c_int, [VP, C.c_int]),
         "cx_job_free": (None, [C.POINTER(CxJob)]),
         "cx_job_sizeof": (I64, []),
         "cx_weld_host": (I64, [C.POINTER(C.c_float), I64, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
@@ -178,6 +193,23 @@ def fill_dims(p):
 
 def seed_index(p, spos):
     return int(lib().cx_seed_index(C.byref(p), f3(spos)))
+
+
+def dist_unique_id():
+    """128 bytes identifying a new NCCL communicator (ncclGetUniqueId); rank 0 calls it and ships the bytes to the other ranks"""
+    buf = (C.c_char * 128)()
+    rc = lib().cx_dist_unique_id(C.cast(buf, VP))
+    if rc != 0:
+        raise CxError(rc)
+    return bytes(buf.raw)
+
+
+def dist_init_local(contexts):
+    """the given contexts (same process; one host thread per context must then drive it) form a group without NCCL"""
+    arr = (VP * len(contexts))(*[c.h for c in contexts])
+    rc = lib().cx_dist_init_local(arr, len(contexts))
+    if rc != 0:
+        raise CxError(rc)
 
 
 def weld_host(corners, dr):
@@ -345,6 +377,44 @@ class Context:
 
     def preprocess_host(self, job):
         self._ck(self.L.cx_preprocess_host(self.h, C.byref(job)))
+
+    # ---- multi-GPU (include/crixus_b200.h "multi-GPU"): the communicator lives inside the library
+    def dist_init(self, id128, world, rank):
+        """joins the NCCL communicator identified by the 128 bytes of cx_dist_unique_id (created on rank 0, shipped by the caller)"""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id128))
+        self._ck(self.L.cx_dist_init(self.h, C.cast(buf, VP), int(world), int(rank)))
+
+    def dist_finalize(self):
+        self.L.cx_dist_finalize(self.h)
+
+    def dist_set_fill_mode(self, mode):
+        self._ck(self.L.cx_dist_set_fill_mode(self.h, int(mode)))
+
+    def dist_world(self):
+        return int(self.L.cx_dist_world(self.h))
+
+    def dist_rank(self):
+        return int(self.L.cx_dist_rank(self.h))
+
+    def preprocess_dist(self, job):
+        self._ck(self.L.cx_preprocess_dist(self.h, C.byref(job)))
+
+    def dist_calc_vert_volume(self, p, pos, norm, ep, vol, trisize, cell_idx, nvert, nbe, zero_open=False):
+        self._ck(self.L.cx_dist_calc_vert_volume(self.h, C.byref(p), self._p(pos), self._p(norm), self._p(ep), self._p(vol),
+                                                 self._p(trisize), self._p(cell_idx), nvert, nbe, int(zero_open)))
+
+    def dist_fill_geometry(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, seed):
+        n, r = I64(0), C.c_int32(0)
+        self._ck(self.L.cx_dist_fill_geometry(self.h, C.byref(p), self._p(fpos), self._p(norm), self._p(ep), self._p(pos), nbe, cnbe,
+                                              self._p(cell_idx), seed, C.byref(n), C.byref(r)))
+        self.last_rounds = int(r.value)
+        return int(n.value)
+
+    def hash_u32(self, t):
+        """(order-independent 64-bit checksum, popcount) of a 4-byte-element CUDA tensor, computed on the device"""
+        out = (C.c_uint64 * 2)()
+        self._ck(self.L.cx_hash_u32(self.h, self._p(t), t.numel() * t.element_size() // 4, out))
+        return int(out[0]), int(out[1])
 
     def assemble_records_device(self, job, nfluid_for_indices=None):
         """cx_assemble_records_device on the device arrays a cx_preprocess_host call left behind -> torch uint8 (n, 64)"""

@@ -33,6 +33,9 @@ struct cx_ctx {
   // pinned staging of the streamed file writers (records.cu)
   void *pin_stage = nullptr;
   size_t pin_stage_bytes = 0;
+  // multi-GPU: collective back-end of this rank (dist.h: NCCL communicator or in-process group); nullptr = single GPU
+  void *dist = nullptr;
+  int dist_fill_mode = 0;       // cx_dist_set_fill_mode: 0 = by lattice size, 1 = replicated flood, 2 = z-slab flood
 };
 
 int cx_fail(cx_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
@@ -40,6 +43,7 @@ int cx_fail(cx_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess
 void *cx_scratch(cx_ctx *ctx, size_t bytes);
 void *cx_scratch_pinned(cx_ctx *ctx, size_t bytes);  // grow-only pinned host staging; nullptr on failure
 void cx_fill_state_free(cx_ctx *ctx);  // fill.cu
+void cx_dist_release(cx_ctx *ctx);     // dist.cu
 
 #define CX_CUDA(ctx, call)                                              \
   do {                                                                  \

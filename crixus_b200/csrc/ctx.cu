@@ -81,6 +81,7 @@ void cx_destroy(cx_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cx_dist_release(ctx);
   cx_fill_state_free(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->dev_arena) cudaFree(ctx->dev_arena);
@@ -129,6 +130,22 @@ int cx_internal_expand3(cx_ctx *ctx, const float *src3_d, float *dst4_d, int64_t
   if (n <= 0) return CX_OK;
   k_expand3<<<cx_blocks(n, 256, ctx->num_sms * 16), 256, 0, ctx->stream>>>(src3_d, (float4 *)dst4_d, n);
   CX_LAUNCH_CHECK(ctx, "k_expand3");
+  return CX_OK;
+}
+
+__global__ void __launch_bounds__(256) k_offset_ep4(const int4 *__restrict__ s, int4 *__restrict__ d, int64_t n, int32_t off)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 e = s[i];
+    d[i] = make_int4(e.x + off, e.y + off, e.z + off, 0);
+  }
+}
+
+int cx_internal_offset_ep4(cx_ctx *ctx, const int32_t *src_ep4_d, int32_t *dst_ep4_d, int64_t n, int32_t offset)
+{
+  if (n <= 0) return CX_OK;
+  k_offset_ep4<<<cx_blocks(n, 256, ctx->num_sms * 16), 256, 0, ctx->stream>>>((const int4 *)src_ep4_d, (int4 *)dst_ep4_d, n, offset);
+  CX_LAUNCH_CHECK(ctx, "k_offset_ep4");
   return CX_OK;
 }
 

@@ -5,29 +5,33 @@
 // The fill result is the least fixed point of "s unset, a 6-neighbour e set, !checkCollision(s,e) => set s"
 // (SURVEY.md A.6), so any schedule reaches the same bits.  B200 mapping (DESIGN.md "fill"):
 //   * the packed reference bitfield is unpacked to a row-aligned layout (x-rows padded to 32-bit words);
-//   * a classification pass marks the cells whose test can be non-trivial ("hard": a non-empty 27-cell
-//     neighbourhood in the 3dr grid, or close to a free-surface triangle).  For every other cell
-//     checkCollision is provably false, so propagation is pure bit arithmetic on 32-cell words;
-//   * the lattice is cut into tiles of 1 word x 16 x 16 rows.  The first time the flood reaches a tile, ALL hard cells
-//     of the tile are resolved in one bulk, perfectly parallel pass (k_resolve_tiles): one warp per cell, lanes
-//     stride the cell-sorted segments of the 27 neighbour cells, the 6 directions of a cell share the distance
-//     computation; the results are 6 "blocked" bit planes.  The directed tests are pure functions of (s,e), so
-//     evaluating them before they are needed changes nothing but the schedule;
-//   * propagation is then bit arithmetic for every cell: tiles are iterated to local convergence in shared memory
-//     (k_fill_tiles); a tile that changed activates its 6 face neighbours for the next round; rounds continue
-//     until no tile is active.  Only reached tiles are touched: work ~ filled volume + wall area.
-// Bound: HBM, 0.25 B/cell + 8 B/filled cell -- in practice latency/round bound.
+//   * checkCollision(s, .) can only be true for a lattice cell s whose 3dr-cell has segments in its 27-neighbourhood, or that
+//     lies near a free-surface (fshape) triangle.  All of these directed tests are pure functions of the geometry and are
+//     resolved ONCE, up front, into six "blocked" bit planes B[d] (bit set = cell s must not be entered from direction d):
+//       - k_resolve_blocks: one warp per non-empty 3dr-cell neighbourhood.  The lattice cells of a 3dr-cell (3-4 per axis)
+//         share their 27-cell neighbourhood, so the candidate segment records are streamed once per 3dr-cell, rejected
+//         against the whole block of lattice cells by their plane distance, staged in shared memory, and then every lane
+//         tests ITS lattice cell against the staged records (broadcast reads) with exact, division-free pre-filters in front
+//         of the reference's arithmetic;
+//       - k_resolve_fs: the free-surface triangles against the lattice rows they can touch;
+//   * propagation is then pure bit arithmetic on 32-cell words: tiles of 1 word x 16 x 16 rows are iterated to local
+//     convergence in shared memory (k_fill_tiles); a tile that changed activates its 6 face neighbours; rounds continue until
+//     no tile is active.  Only reached tiles are touched: work ~ filled volume + wall area.
+//   * multi-GPU (cx_dist_fill_geometry): the directed tests are dealt to the ranks by 3dr-cell chunk, the blocked planes are
+//     reduced to the z-slab owners, each rank floods its slab and exchanges boundary planes with its z-neighbours.
+// Bound: HBM, 0.25 B/cell + 8 B/filled cell -- in practice the directed tests (ALU) and the round latency.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <vector>
 #include "common.cuh"
+#include "dist.h"
 
 #define FT_Y 16
 #define FT_Z 16
 #define FT_THREADS (FT_Y * FT_Z)
-#define FS_MAX_DESC 512
 
 // ================================================================================================ box fill
 // crixus_d.cu:686-717.  One thread per packed 32-bit word; nfi counts every in-box cell (even if already set).
@@ -86,11 +90,12 @@ extern "C" int cx_fill_box(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, co
 }
 
 // ================================================================================================ geometry fill
-// conservative description of a free-surface (fshape) triangle, used only to decide which cells are "hard"
+// conservative description of a free-surface (fshape) triangle: where checkTriangleCollision(s, ., triangle) can be true
 struct FsDesc {
-  float lo[3], hi[3];  // bounding box grown by the margin outside of which checkTriangleCollision cannot be true
+  float lo[3], hi[3];  // bounding box grown by the margin outside of which the segment test cannot hit the triangle
   float n[3], v0[3];   // plane, for the "ray in plane => collision" rule (crixus_d.cu:766-769)
-  int quirk;           // some axis direction can be parallel to the plane within eps
+  int quirk;           // some axis direction can be parallel to the plane within eps: cells within 4 eps of the plane matter too
+  int cull;            // 0: the triangle is ill-conditioned / its normal disagrees with its plane -> every cell is tested
 };
 
 struct FillArgs {
@@ -106,37 +111,34 @@ struct FillArgs {
   int64_t ntiles;    // wr * ty * tz
   int k_lo, k_hi;    // owned planes [k_lo, k_hi): only these are written (z-slab sharding)
   uint32_t *F;       // row-aligned filled bits, wr*dimg[1]*dimg[2] words
-  uint32_t *H;       // hard mask, same shape
   uint32_t *B;       // 6 blocked planes, same shape each (direction d at B + d*nw)
   int64_t nw;        // words per plane set
   const uint8_t *nbflag;  // per 3dr-cell: 27-neighbourhood contains a segment
-  const FsDesc *fs;       // fshape descriptors
-  int nfs, all_hard;
-  const int *all_hard_d;       // set by k_fs_desc when a free-surface triangle cannot be culled
+  const FsDesc *fs;       // fshape descriptors (cnbe of them)
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
-  int32_t *count;               // [0] = list length, [1] = cursor, [2] = resolve-list length, [3] = resolve cursor
-  unsigned long long *count64;  // work counter of the up-front resolve (one item per 32-cell word of the lattice)
-  uint8_t *tile_res;            // tile already resolved (blocked planes valid)
-  int32_t *rlist;               // tiles to resolve this round
+  int32_t *count;               // [0] = list length, [1] = cursor
+  unsigned long long *count64;  // work counter of the up-front resolve
   unsigned long long *changed;  // newly set cells
-  int res_nparts, res_part;     // up-front resolve of items part, part+nparts, ... in chunks of 64 (0/1: everything)
-  int resolved_all;             // every hard cell of the owned planes was resolved up front (no per-round resolve)
+  int res_nparts, res_part;     // up-front resolve: 3dr-cell chunks dealt to nparts ranks, this rank resolves its share (0/1: all)
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
   int64_t w_lo, w_hi;           // word range k_unpack / k_pack walk (slab calls: the owned planes, +-1 halo plane for k_unpack)
-  long long item_lo, item_hi;   // item range of the up-front resolve (slab calls: the tile layers of the owned planes)
-  int classify_inline;          // up-front resolve computes the hard mask itself (no k_classify pass over the lattice)
   const float4 *rec;            // per-segment invariants of checkCollision (k_seg_prep), 8 x float4 per segment
   float rrej;                   // plane distance beyond which a well-formed triangle cannot matter
   float drw2;                   // dr_wall*dr_wall
   double one_eps;               // 1.0 + eps (double, crixus_d.cu:774)
+  int dist_dead;                // eps >= dr_wall^2: the distance test `dist + eps < dr_wall^2` (crixus_d.cu:940) can never hold
+  int nofilter;                 // debugging: no pre-filters, every pair inside rrej runs the reference's arithmetic
+  float sph2;                   // (1.01 (1 + 3 eps))^2: hit points further than sqrt(sph2 * max(uu, vv)) from v0 miss the triangle
 };
 
-// ---- the reference's directed test, warp-cooperative -------------------------------------------------------------
+// ---- the reference's directed test -------------------------------------------------------------------------------
 // Everything in checkCollision that depends on the triangle alone is hoisted into a per-segment record (k_seg_prep):
 // the same operations in the same order, so the results are bit-identical to evaluating them per (cell, segment) pair.
 //   R0 = (n, wf)   R1 = (v0, uu)   R2 = (v1, uv)   R3 = (v2, vv)   R4 = (segpos, D)   R5..R7 = (nr[0..2], -)
+// wf: 0 = no assumption, 1 = well-formed normal (plane-distance reject is valid), 2 = and well-conditioned edges (the
+// bounding-sphere pre-filter of the segment test is valid too)
 #define FREC 8
 
 // checkTriangleCollision, crixus_d.cu:753-799 (u, v, uu, uv, vv, D from the record)
@@ -185,7 +187,7 @@ __device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0,
 }
 
 // one thread per segment: the triangle-only parts of crixus_d.cu:859-896 (segpos, edge normals nr) and :755-783 (uu, uv,
-// vv, D), plus the "well-formed" flag that licenses the plane-distance reject in warp_check_collision.
+// vv, D), plus the flags that license the pre-filters of the resolve kernels.
 __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict__ rec)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < A.nbe; i += (int64_t)gridDim.x * blockDim.x) {
@@ -213,13 +215,20 @@ __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict
     // every point within the influence radius, |n.(s - v0)| is the distance to the triangle's plane within a few
     // per cent, and no distance the reference can compute (plane, vertex or edge-line distance) is smaller.
     const double nn = (double)n.x * n.x + (double)n.y * n.y + (double)n.z * n.z;
-    const double lu = sqrt((double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z);
-    const double lv = sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z);
+    const double lu2 = (double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z;
+    const double lv2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;
+    const double lu = sqrt(lu2), lv = sqrt(lv2);
     const double nu = (double)n.x * u.x + (double)n.y * u.y + (double)n.z * u.z;
     const double nv = (double)n.x * v.x + (double)n.y * v.y + (double)n.z * v.z;
+    const double duv = (double)u.x * v.x + (double)u.y * v.y + (double)u.z * v.z;
     const bool wf = nn > 0.98 && nn < 1.02 && lu > 0 && lv > 0 && fabs(nu) <= 2e-3 * lu && fabs(nv) <= 2e-3 * lv;
+    // well-conditioned: sin^2 of the angle between the edges >= 1e-2 and the float D agrees with it: then the barycentric
+    // coordinates (t1, t2) the reference computes describe the hit point within ~1e-4, and |t1 u + t2 v| <= (1 + 3 eps) max(|u|, |v|)
+    // for every accepted (t1, t2)
+    const double Dd = lu2 * lv2 - duv * duv;
+    const bool wc = wf && Dd >= 1e-2 * lu2 * lv2 && isfinite(D) && fabs((double)(-D) - Dd) <= 1e-3 * Dd;
     float4 *r = rec + i * FREC;
-    r[0] = make_float4(n.x, n.y, n.z, wf ? 1.f : 0.f);
+    r[0] = make_float4(n.x, n.y, n.z, wc ? 2.f : (wf ? 1.f : 0.f));
     r[1] = make_float4(v0.x, v0.y, v0.z, uu);
     r[2] = make_float4(v1.x, v1.y, v1.z, uv);
     r[3] = make_float4(v2.x, v2.y, v2.z, vv);
@@ -230,119 +239,63 @@ __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict
   }
 }
 
-// checkCollision (crixus_d.cu:801-963) for cell s=(si,sj,sk) and every direction in dmask at once (bit d: 0:-x 1:+x
-// 2:-y 3:+y 4:-z 5:+z, the reference's neighbour order).  Called by a full warp; returns the directions that collide.
-//
-// Plane-distance reject (exact): for a well-formed triangle, a cell further than rrej = 1.2 max(dr_wall, dr) from the
-// triangle's plane can neither pass the distance test (every distance the reference computes is >= the plane
-// distance up to a few per cent) nor be hit by a lattice step of length dr, and the "ray in plane" rule needs
-// |n.(s-v0)| < eps.  Such pairs are skipped after two loads; everything else runs the reference's arithmetic.
-__device__ uint32_t warp_check_collision(const FillArgs &A, int si, int sj, int sk, uint32_t dmask, int lane)
+// lattice position along one axis, crixus_d.cu:805-807 (R5)
+__device__ __forceinline__ float lat_pos(const cx_params &p, int a, int idx) { return ffma((float)idx, p.dr, p.fcmin[a]); }
+__device__ __forceinline__ int lat_cell(const cx_params &p, int a, int idx)
+{
+  return cell_coord(lat_pos(p, a, idx), p.dmin[a], p.griddr[a], p.gridn[a]);
+}
+
+// the body of checkCollision's segment loop (crixus_d.cu:846-948) for ONE (lattice cell, segment record) pair and the
+// directions in `need` (bit d: 0:-x 1:+x 2:-y 3:+y 4:-z 5:+z, the reference's neighbour order): influence-radius test,
+// distance test, segment-triangle test.  Returns the directions that collide.  Called by diverged lanes (rare path).
+__device__ __noinline__ uint32_t pair_full(const FillArgs &A, int si, int sj, int sk, int64_t ri, uint32_t need)
 {
   const cx_params &p = A.p;
   const float dr = p.dr, eps = p.eps;
   const int sidx[3] = {si, sj, sk};
-  float sc[3], ec[6], dirc[6], infl[6], midc[6], mids[3];
+  float sc[3];
 #pragma unroll
-  for (int a = 0; a < 3; a++) {
-    sc[a] = ffma((float)sidx[a], dr, p.fcmin[a]);  // crixus_d.cu:805-807 (R5)
-    mids[a] = fadd(sc[a], sc[a]);
-  }
+  for (int a = 0; a < 3; a++) sc[a] = lat_pos(p, a, sidx[a]);
+  const f3 s = mk3(sc[0], sc[1], sc[2]);
+  const float4 *r = A.rec + ri * FREC;
+  const float4 R0 = __ldg(r), R1 = __ldg(r + 1), R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4);
+  const f3 n = mk3(R0), v0 = mk3(R1), v1 = mk3(R2), v2 = mk3(R3);
+  uint32_t pass = 0;
+  float dirc[6];
 #pragma unroll
   for (int d = 0; d < 6; d++) {
+    dirc[d] = 0.f;
+    if (!(need >> d & 1)) continue;
     const int a = d >> 1;
-    ec[d] = ffma((float)(sidx[a] + ((d & 1) ? 1 : -1)), dr, p.fcmin[a]);
-    dirc[d] = fsub(ec[d], sc[a]);
-    const float hd = fmul(fsub(sc[a], ec[d]), 0.5f);  // (s-e)/2.0f; the two other components are exactly +0
+    const float ec = lat_pos(p, a, sidx[a] + ((d & 1) ? 1 : -1));
+    dirc[d] = fsub(ec, sc[a]);
+    const float hd = fmul(fsub(sc[a], ec), 0.5f);  // (s-e)/2.0f; the two other components are exactly +0
     const f3 hv = mk3(a == 0 ? hd : 0.f, a == 1 ? hd : 0.f, a == 2 ? hd : 0.f);
-    float l = dot3_r3(hv, hv);
-    l = __fsqrt_rn(l);
-    float r = fadd(ffma(dr, 3.0f, l), p.dr_wall);  // crixus_d.cu:815 (R6)
-    infl[d] = fmul(r, r);
-    midc[d] = fadd(sc[a], ec[d]);
+    const float l = __fsqrt_rn(dot3_r3(hv, hv));
+    const float rr = fadd(ffma(dr, 3.0f, l), p.dr_wall);  // crixus_d.cu:815 (R6)
+    const float infl = fmul(rr, rr);
+    const float midc = fadd(sc[a], ec);
+    const f3 tt = mk3(ffma(a == 0 ? midc : fadd(sc[0], sc[0]), 0.5f, -v0.x), ffma(a == 1 ? midc : fadd(sc[1], sc[1]), 0.5f, -v0.y),
+                      ffma(a == 2 ? midc : fadd(sc[2], sc[2]), 0.5f, -v0.z));
+    if (!(dot3_r3(tt, tt) > infl)) pass |= 1u << d;  // crixus_d.cu:855-857
   }
-  const f3 s = mk3(sc[0], sc[1], sc[2]);
-  const int gx = cell_coord(sc[0], p.dmin[0], p.griddr[0], p.gridn[0]);
-  const int gy = cell_coord(sc[1], p.dmin[1], p.griddr[1], p.gridn[1]);
-  const int gz = cell_coord(sc[2], p.dmin[2], p.griddr[2], p.gridn[2]);
-  uint32_t coll = 0;
-  // the 27 cells as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run
-  // of segments (plus, at a periodic z border, the wrapped cell as a run of its own)
-  for (int c9 = 0; c9 < 9 && coll != dmask; c9++) {
-    const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
-    for (int part = 0; part < 3 && coll != dmask; part++) {
-      int b, e;
-      if (part == 0) {
-        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
-        const int64_t c0 = nb_cell(p, cx, cy, z0);
-        if (c0 < 0) break;   // column outside the grid (not periodic): nothing in the other parts either
-        b = __ldg(&A.cell_idx[c0]); e = __ldg(&A.cell_idx[c0 + (z1 - z0) + 1]);
-      } else {
-        const int zz = part == 1 ? gz - 1 : gz + 1;
-        if (zz >= 0 && zz < p.gridn[2]) continue;   // in range: part of the run above
-        const int64_t c0 = nb_cell(p, cx, cy, zz);  // wrapped (periodic z) or -1
-        if (c0 < 0) continue;
-        b = __ldg(&A.cell_idx[c0]); e = __ldg(&A.cell_idx[c0 + 1]);
-      }
-      for (int base = b; base < e && coll != dmask; base += 32) {
-        const int i = base + lane;
-        uint32_t mine = 0;
-        if (i < e) {
-          const float4 *r = A.rec + (int64_t)i * FREC;
-          const float4 R0 = __ldg(r), R1 = __ldg(r + 1);
-          const f3 n = mk3(R0), v0 = mk3(R1);
-          const float t = (s.x - v0.x) * n.x + (s.y - v0.y) * n.y + (s.z - v0.z) * n.z;
-          if (!(R0.w != 0.f && fabsf(t) > A.rrej)) {
-            uint32_t pass = 0;
-#pragma unroll
-            for (int d = 0; d < 6; d++) {
-              if (!((dmask & ~coll) >> d & 1)) continue;
-              const int a = d >> 1;
-              const f3 tt = mk3(ffma(a == 0 ? midc[d] : mids[0], 0.5f, -v0.x), ffma(a == 1 ? midc[d] : mids[1], 0.5f, -v0.y),
-                                ffma(a == 2 ? midc[d] : mids[2], 0.5f, -v0.z));
-              if (!(dot3_r3(tt, tt) > infl[d])) pass |= 1u << d;  // crixus_d.cu:855-857
-            }
-            if (pass) {
-              const float4 R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4), R5 = __ldg(r + 5), R6 = __ldg(r + 6), R7 = __ldg(r + 7);
-              const f3 v1 = mk3(R2), v2 = mk3(R3);
-              const float dist = tri_dist2(A, s, n, v0, v1, v2, mk3(R4), mk3(R5), mk3(R6), mk3(R7));
-              if (fadd(dist, eps) < A.drw2) mine = pass;  // crixus_d.cu:940
-              else {
-                const f3 u = sub3(v1, v0), v = sub3(v2, v0);
-#pragma unroll
-                for (int d = 0; d < 6; d++) {
-                  if (!(pass >> d & 1)) continue;
-                  const int a = d >> 1;
-                  const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
-                  if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) mine |= 1u << d;
-                }
-              }
-            }
-          }
-        }
-        coll |= __reduce_or_sync(0xffffffffu, mine);
-      }
-    }
+  if (!pass) return 0;
+  if (!A.dist_dead) {
+    const float4 R5 = __ldg(r + 5), R6 = __ldg(r + 6), R7 = __ldg(r + 7);
+    const float dist = tri_dist2(A, s, n, v0, v1, v2, mk3(R4), mk3(R5), mk3(R6), mk3(R7));
+    if (fadd(dist, eps) < A.drw2) return pass;  // crixus_d.cu:940
   }
-  // free-surface triangles: all of them, segment test only (crixus_d.cu:951-960)
-  for (int64_t base = A.nbe - A.cnbe; base < A.nbe && coll != dmask; base += 32) {
-    const int64_t i = base + lane;
-    uint32_t mine = 0;
-    if (i < A.nbe) {
-      const float4 *r = A.rec + i * FREC;
-      const float4 R0 = __ldg(r), R1 = __ldg(r + 1), R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4);
-      const f3 n = mk3(R0), v0 = mk3(R1), u = sub3(mk3(R2), v0), v = sub3(mk3(R3), v0);
+  uint32_t mine = 0;
+  const f3 u = sub3(v1, v0), v = sub3(v2, v0);
 #pragma unroll
-      for (int d = 0; d < 6; d++) {
-        if (!((dmask & ~coll) >> d & 1)) continue;
-        const int a = d >> 1;
-        const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
-        if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) mine |= 1u << d;
-      }
-    }
-    coll |= __reduce_or_sync(0xffffffffu, mine);
+  for (int d = 0; d < 6; d++) {
+    if (!(pass >> d & 1)) continue;
+    const int a = d >> 1;
+    const f3 dir = mk3(a == 0 ? dirc[d] : 0.f, a == 1 ? dirc[d] : 0.f, a == 2 ? dirc[d] : 0.f);
+    if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) mine |= 1u << d;
   }
-  return coll & dmask;
+  return mine;
 }
 
 // ---- preparation kernels ---------------------------------------------------------------------------------------
@@ -406,67 +359,23 @@ __global__ void __launch_bounds__(256) k_pack(FillArgs A, uint32_t *__restrict__
   }
 }
 
-// hard mask: cell needs the real test (otherwise checkCollision(s, .) is false for every direction)
-__global__ void __launch_bounds__(256) k_classify(FillArgs A)
+// a boundary plane received from a z-neighbour (row-aligned words of lattice plane k) is OR-ed into F; tiles that got new
+// bits are activated and *fresh is raised
+__global__ void __launch_bounds__(256) k_merge_plane(FillArgs A, const uint32_t *__restrict__ plane, int k, int *fresh)
 {
-  const cx_params &p = A.p;
-  const int64_t rows = (int64_t)A.dimg[1] * A.dimg[2];
-  for (int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wi < A.nw; wi += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = wi / A.wr;
-    const int wx = (int)(wi - row * A.wr);
-    if (row >= rows) continue;
-    const int j = (int)(row % A.dimg[1]), k = (int)(row / A.dimg[1]);
-    const int nvalid = min(32, A.dimg[0] - wx * 32);
-    uint32_t h = 0;
-    if (A.all_hard || *A.all_hard_d) h = 0xffffffffu;
-    else {
-      const float sy = ffma((float)j, p.dr, p.fcmin[1]), sz = ffma((float)k, p.dr, p.fcmin[2]);
-      const int gy = cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]), gz = cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]);
-      for (int b = 0; b < nvalid; b++) {
-        const float sx = ffma((float)(wx * 32 + b), p.dr, p.fcmin[0]);
-        const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
-        int hard = A.nbflag[((int64_t)gx * p.gridn[1] + gy) * p.gridn[2] + gz];
-        for (int t = 0; t < A.nfs && !hard; t++) {
-          const FsDesc &f = A.fs[t];
-          if (sx >= f.lo[0] && sx <= f.hi[0] && sy >= f.lo[1] && sy <= f.hi[1] && sz >= f.lo[2] && sz <= f.hi[2]) hard = 1;
-          else if (f.quirk) {
-            const float a = f.n[0] * (sx - f.v0[0]) + f.n[1] * (sy - f.v0[1]) + f.n[2] * (sz - f.v0[2]);
-            if (fabsf(a) < 4.f * p.eps) hard = 1;
-          }
-        }
-        h |= (uint32_t)hard << b;
-      }
-    }
-    if (nvalid < 32) h &= (1u << nvalid) - 1u;
-    A.H[wi] = h;
-  }
-}
-
-// the same hard mask for one 32-cell word, computed by a warp (lane = cell): used by the up-front resolve so that no
-// separate pass over the whole lattice is needed (at 1e10 cells k_classify alone is ~0.1 s, and it does not shard)
-__device__ __forceinline__ uint32_t classify_word_warp(const FillArgs &A, int wx, int j, int k, int lane)
-{
-  const cx_params &p = A.p;
-  const int nvalid = min(32, A.dimg[0] - wx * 32);
-  const uint32_t vmask = nvalid < 32 ? (1u << nvalid) - 1u : 0xffffffffu;
-  if (A.all_hard || *A.all_hard_d) return vmask;
-  int hard = 0;
-  if (lane < nvalid) {
-    const float sy = ffma((float)j, p.dr, p.fcmin[1]), sz = ffma((float)k, p.dr, p.fcmin[2]);
-    const int gy = cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]), gz = cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]);
-    const float sx = ffma((float)(wx * 32 + lane), p.dr, p.fcmin[0]);
-    const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
-    hard = A.nbflag[((int64_t)gx * p.gridn[1] + gy) * p.gridn[2] + gz];
-    for (int t = 0; t < A.nfs && !hard; t++) {
-      const FsDesc &f = A.fs[t];
-      if (sx >= f.lo[0] && sx <= f.hi[0] && sy >= f.lo[1] && sy <= f.hi[1] && sz >= f.lo[2] && sz <= f.hi[2]) hard = 1;
-      else if (f.quirk) {
-        const float a = f.n[0] * (sx - f.v0[0]) + f.n[1] * (sy - f.v0[1]) + f.n[2] * (sz - f.v0[2]);
-        if (fabsf(a) < 4.f * p.eps) hard = 1;
-      }
+  const int64_t wplane = (int64_t)A.wr * A.dimg[1];
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < wplane; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = plane[q];
+    if (!v) continue;
+    const int64_t wi = (int64_t)k * wplane + q;
+    const uint32_t old = A.F[wi];
+    if (v & ~old) {
+      A.F[wi] = old | v;
+      const int j = (int)(q / A.wr), wx = (int)(q - (int64_t)j * A.wr);
+      A.act_cur[((int64_t)(k / FT_Z) * A.ty + j / FT_Y) * A.wr + wx] = 1;
+      *fresh = 1;
     }
   }
-  return __ballot_sync(0xffffffffu, hard) & vmask;
 }
 
 __global__ void k_seed(FillArgs A, int64_t seed)
@@ -483,8 +392,335 @@ __global__ void k_seed(FillArgs A, int64_t seed)
   A.act_cur[((int64_t)(k / FT_Z) * A.ty + j / FT_Y) * A.wr + (i >> 5)] = 1;
 }
 
+// ---- up-front resolution of the directed tests ---------------------------------------------------------------------
+// smallest lattice index i in [0, dim] whose 3dr-cell coordinate along `axis` is >= g (dim if there is none).  The cell
+// coordinate is a monotone function of i (every operation of lat_cell is correctly rounded and monotone): binary search.
+__device__ int idx_lo(const cx_params &p, int axis, int g, int dim)
+{
+  if (g <= 0) return 0;
+  if (g >= p.gridn[axis]) return dim;
+  int lo = 0, hi = dim;   // invariant: cells < lo have coordinate < g, cells >= hi have coordinate >= g
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lat_cell(p, axis, mid) >= g) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// which rank resolves the 3dr-cells of chunk `chunk` (32 consecutive cells): every group of nparts chunks is dealt one chunk
+// per rank, the order rotated by a hash of the group (walls are planes of the cell grid: plain round-robin would be periodic
+// in them).  The same function on every rank, so the shares are disjoint and complete.
+__device__ __forceinline__ int chunk_owner(long long chunk, int nparts)
+{
+  const long long g = chunk / nparts;
+  const int slot = (int)(chunk - g * nparts);
+  const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)nparts);
+  return (slot + nparts - rot) % nparts;
+}
+
+#define RB_WARPS 8
+#define RB_CAP 96   // staged records per warp (phase 1 appends up to 32 per step and flushes above RB_CAP - 32)
+
+// one lattice cell against the staged records: exact pre-filters, then the reference's arithmetic (pair_full) for the few
+// pairs that survive them.  (si, sj, sk) = the lane's cell, dm = its in-lattice directions, coll = directions already blocked.
+__device__ __forceinline__ uint32_t cell_vs_staged(const FillArgs &A, const float4 *sR0, const float4 *sR1, const int *sIdx, int cnt,
+                                                   int si, int sj, int sk, uint32_t dm, uint32_t coll)
+{
+  const cx_params &p = A.p;
+  const float eps = p.eps;
+  const f3 s = mk3(lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk));
+  // direction vectors e - s, one non-zero component each
+  const float dxm = fsub(lat_pos(p, 0, si - 1), s.x), dxp = fsub(lat_pos(p, 0, si + 1), s.x);
+  const float dym = fsub(lat_pos(p, 1, sj - 1), s.y), dyp = fsub(lat_pos(p, 1, sj + 1), s.y);
+  const float dzm = fsub(lat_pos(p, 2, sk - 1), s.z), dzp = fsub(lat_pos(p, 2, sk + 1), s.z);
+  for (int q = 0; q < cnt; q++) {
+    uint32_t need = dm & ~coll;
+    if (!need) break;
+    const float4 R0 = sR0[q], R1 = sR1[q];
+    const f3 n = mk3(R0), v0 = mk3(R1);
+    const float wx = s.x - v0.x, wy = s.y - v0.y, wz = s.z - v0.z;
+    const float t = wx * n.x + wy * n.y + wz * n.z;
+    if (R0.w != 0.f && fabsf(t) > A.rrej) continue;   // plane-distance reject: neither test can hold
+    uint32_t cand = need;
+    // the distance test is alive unless eps >= dr_wall^2 or (well-formed triangle) the plane distance alone exceeds dr_wall:
+    // every distance the reference computes is >= |t| / 1.2
+    const bool dist_alive = !A.dist_dead && !(R0.w != 0.f && t * t >= 1.44f * A.drw2);
+    if (!dist_alive && !A.nofilter) {
+      // segment test only.  a, b exactly as checkTriangleCollision computes them; r = a / b must lie in [-eps, 1 + eps]
+      const float a = -dot3_r3(n, sub3(s, v0));
+      cand = 0;
+#pragma unroll
+      for (int d = 0; d < 6; d++) {
+        if (!(need >> d & 1)) continue;
+        const int ax = d >> 1;
+        const float dc = d == 0 ? dxm : d == 1 ? dxp : d == 2 ? dym : d == 3 ? dyp : d == 4 ? dzm : dzp;
+        const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
+        const float b = dot3_r3(n, dir);
+        const float ab = fabsf(b);
+        if (ab < eps) {
+          if (fabsf(a) < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
+          continue;
+        }
+        if (!(ab <= 3.0e38f)) { cand |= 1u << d; continue; }        // inf / NaN: no shortcut
+        const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
+        if (qn > ab * 1.0001f * (1.0f + eps) || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
+        if (R0.w == 2.f) {
+          // hit point P = s + r dir; an accepted (t1, t2) puts it within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned
+          // triangles only).  r from a fast division: the 1 % margin of sph2 covers its error many times over.
+          const float r = __fdividef(qn, ab);
+          const float px = ax == 0 ? wx + r * dc : wx, py = ax == 1 ? wy + r * dc : wy, pz = ax == 2 ? wz + r * dc : wz;
+          if (px * px + py * py + pz * pz > A.sph2 * __int_as_float(sIdx[RB_CAP + q])) continue;
+        }
+        cand |= 1u << d;
+      }
+      if (!cand) continue;
+    }
+    coll |= pair_full(A, si, sj, sk, sIdx[q], cand);
+  }
+  return coll;
+}
+
+__global__ void __launch_bounds__(RB_WARPS * 32, 2) k_resolve_blocks(const __grid_constant__ FillArgs A)
+{
+  __shared__ float4 sR0[RB_WARPS][RB_CAP], sR1[RB_WARPS][RB_CAP];
+  __shared__ int sIdx[RB_WARPS][2 * RB_CAP];   // record index, then (as float bits) max(uu, vv) of the record
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const cx_params &p = A.p;
+  const long long ncell = p.gridn[3];
+  const long long nchunk = (ncell + 31) / 32;
+  const int nparts = A.res_nparts > 1 ? A.res_nparts : 1;
+  float4 *mR0 = sR0[wp], *mR1 = sR1[wp];
+  int *mIdx = sIdx[wp];
+  for (;;) {
+    long long chunk = 0;
+    if (lane == 0) chunk = (long long)atomicAdd(A.count64, 1ull);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (nparts > 1) {   // my q-th chunk: group q, the slot that chunk_owner() gives to this rank
+      const long long g = chunk;
+      const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)nparts);
+      chunk = g * nparts + (A.res_part + rot) % nparts;
+    }
+    if (chunk >= nchunk) { if (nparts > 1 && chunk - (chunk % nparts) < nchunk) continue; break; }
+    const long long c0 = chunk * 32 + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, c0 < ncell && A.nbflag[c0]);
+    while (todo) {
+      const int bsel = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long c = chunk * 32 + bsel;
+      const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((long long)p.gridn[2] * p.gridn[1]));
+      // lattice index ranges of the cells that map to this 3dr-cell: lanes 0..5 search one bound each
+      int bound = 0;
+      if (lane < 6) {
+        const int ax = lane >> 1, g = (ax == 0 ? gx : ax == 1 ? gy : gz) + (lane & 1);
+        bound = idx_lo(p, ax, g, A.dimg[ax]);
+      }
+      const int bi0 = __shfl_sync(0xffffffffu, bound, 0), bi1 = __shfl_sync(0xffffffffu, bound, 1);
+      const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
+      const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
+      if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
+      // the neighbourhood as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run of
+      // records (plus, at a periodic z border, the wrapped cell as a run of its own): lane l < 27 holds run l (9 columns x 3 parts)
+      int rb = 0, re = 0;
+      if (lane < 27) {
+        const int c9 = lane / 3, part = lane % 3;
+        const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
+        if (part == 0) {
+          const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
+          const int64_t q0 = nb_cell(p, cx, cy, z0);
+          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
+        } else {
+          const int zz = part == 1 ? gz - 1 : gz + 1;
+          if (zz < 0 || zz >= p.gridn[2]) {   // out of range: wrapped (periodic z) or skipped
+            const int64_t q0 = nb_cell(p, cx, cy, zz);
+            if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
+          }
+        }
+      }
+      // sub-blocks of at most 4 x 4 x 4 lattice cells (a 3dr-cell holds 3-4 cells per axis; border cells of a container that is
+      // larger than the domain hold more), two cells per lane
+      for (int k0 = bk0; k0 < bk1; k0 += 4)
+        for (int j0 = bj0; j0 < bj1; j0 += 4)
+          for (int i0 = bi0; i0 < bi1; i0 += 4) {
+            const int nx = min(4, bi1 - i0), ny = min(4, bj1 - j0), nz = min(4, bk1 - k0);
+            const int ncl = nx * ny * nz;
+            int ci[2], cj[2], ck[2];
+            uint32_t dm[2], coll[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+              const int q = lane + 32 * sl;
+              const bool v = q < ncl;
+              ci[sl] = i0 + (v ? q % nx : 0); cj[sl] = j0 + (v ? (q / nx) % ny : 0); ck[sl] = k0 + (v ? q / (nx * ny) : 0);
+              dm[sl] = !v ? 0u : ((ci[sl] > 0 ? 1u : 0u) | (ci[sl] + 1 < A.dimg[0] ? 2u : 0u) | (cj[sl] > 0 ? 4u : 0u) |
+                                  (cj[sl] + 1 < A.dimg[1] ? 8u : 0u) | (ck[sl] > 0 ? 16u : 0u) | (ck[sl] + 1 < A.dimg[2] ? 32u : 0u));
+              coll[sl] = 0;
+            }
+            // centre and half extents of the sub-block, for the block-level plane-distance reject
+            const float xlo = lat_pos(p, 0, i0), xhi = lat_pos(p, 0, i0 + nx - 1), ylo = lat_pos(p, 1, j0), yhi = lat_pos(p, 1, j0 + ny - 1);
+            const float zlo = lat_pos(p, 2, k0), zhi = lat_pos(p, 2, k0 + nz - 1);
+            const float bcx = 0.5f * (xlo + xhi), bcy = 0.5f * (ylo + yhi), bcz = 0.5f * (zlo + zhi);
+            const float bhx = 0.5f * (xhi - xlo), bhy = 0.5f * (yhi - ylo), bhz = 0.5f * (zhi - zlo);
+            int cnt = 0;
+            for (int run = 0; run < 27; run++) {
+              const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
+              for (int base = b; base < e; base += 32) {
+                const int i = base + lane;
+                bool keep = false;
+                float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+                float muv = 0.f;
+                if (i < e) {
+                  const float4 *r = A.rec + (int64_t)i * FREC;
+                  R0 = __ldg(r); R1 = __ldg(r + 1);
+                  const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
+                  const float rad = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
+                  keep = !(R0.w != 0.f && fabsf(tc) - rad > A.rrej);
+                  if (keep && R0.w == 2.f) muv = fmaxf(R1.w, __ldg(r + 3).w);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (!bal) continue;
+                if (keep) {
+                  const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+                  mR0[at] = R0; mR1[at] = R1; mIdx[at] = i; mIdx[RB_CAP + at] = __float_as_int(muv);
+                }
+                cnt += __popc(bal);
+                __syncwarp();
+                if (cnt > RB_CAP - 32) {
+#pragma unroll
+                  for (int sl = 0; sl < 2; sl++)
+                    if (dm[sl] & ~coll[sl]) coll[sl] = cell_vs_staged(A, mR0, mR1, mIdx, cnt, ci[sl], cj[sl], ck[sl], dm[sl], coll[sl]);
+                  cnt = 0;
+                  __syncwarp();
+                }
+              }
+            }
+            if (cnt) {
+#pragma unroll
+              for (int sl = 0; sl < 2; sl++)
+                if (dm[sl] & ~coll[sl]) coll[sl] = cell_vs_staged(A, mR0, mR1, mIdx, cnt, ci[sl], cj[sl], ck[sl], dm[sl], coll[sl]);
+              __syncwarp();
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+              const uint32_t cl = coll[sl] & dm[sl];
+              if (!cl) continue;
+              const int64_t wi = ((int64_t)ck[sl] * A.dimg[1] + cj[sl]) * A.wr + (ci[sl] >> 5);
+              const uint32_t bit = 1u << (ci[sl] & 31);
+#pragma unroll
+              for (int d = 0; d < 6; d++)
+                if (cl >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
+            }
+          }
+    }
+  }
+}
+
+// free-surface triangles: all of them against every lattice cell, segment test only, no cell lookup (crixus_d.cu:951-960).
+// One thread per (triangle, lattice row); the cells of the row that can be hit are an index interval (FsDesc).
+__global__ void __launch_bounds__(128) k_resolve_fs(FillArgs A)
+{
+  const cx_params &p = A.p;
+  const int64_t rows = (int64_t)A.dimg[1] * (A.k_hi - A.k_lo);
+  const int64_t total = rows * A.cnbe;
+  const int nparts = A.res_nparts > 1 ? A.res_nparts : 1;
+  for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(it / rows);
+    const int64_t row = it - (int64_t)t * rows;
+    const int j = (int)(row % A.dimg[1]), k = A.k_lo + (int)(row / A.dimg[1]);
+    const FsDesc f = A.fs[t];
+    const float sy = lat_pos(p, 1, j), sz = lat_pos(p, 2, k);
+    int ia = 0, ib = A.dimg[0] - 1;
+    if (f.cull && !A.nofilter) {
+      ia = A.dimg[0]; ib = -1;
+      if (sy >= f.lo[1] && sy <= f.hi[1] && sz >= f.lo[2] && sz <= f.hi[2]) {   // the bounding box part
+        const double a = floor(((double)f.lo[0] - p.fcmin[0]) / p.dr) - 1.0, b = ceil(((double)f.hi[0] - p.fcmin[0]) / p.dr) + 1.0;
+        ia = (int)fmax(a, 0.0); ib = (int)fmin(b, (double)A.dimg[0] - 1.0);
+      }
+      if (f.quirk) {   // cells within 4 eps of the plane: |a0 + i c| < 4 eps
+        const double a0 = (double)f.n[0] * ((double)p.fcmin[0] - f.v0[0]) + (double)f.n[1] * ((double)sy - f.v0[1]) +
+                          (double)f.n[2] * ((double)sz - f.v0[2]);
+        const double c = (double)f.n[0] * p.dr, band = 4.0 * p.eps + 1e-5 * (fabs(a0) + fabs(c) * A.dimg[0]);
+        int qa, qb;
+        if (fabs(c) * A.dimg[0] < 0.25 * band) { qa = fabs(a0) < 2.0 * band ? 0 : A.dimg[0]; qb = fabs(a0) < 2.0 * band ? A.dimg[0] - 1 : -1; }
+        else {
+          const double i1 = (-a0 - band) / c, i2 = (-a0 + band) / c;
+          qa = (int)fmax(floor(fmin(i1, i2)) - 1.0, 0.0); qb = (int)fmin(ceil(fmax(i1, i2)) + 1.0, (double)A.dimg[0] - 1.0);
+        }
+        if (qa <= qb) { ia = min(ia, qa); ib = max(ib, qb); }
+      }
+    }
+    if (ia > ib) continue;
+    const int64_t ri = A.nbe - A.cnbe + t;
+    const float4 *r = A.rec + ri * FREC;
+    const float4 R0 = __ldg(r), R1 = __ldg(r + 1), R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4);
+    const f3 n = mk3(R0), v0 = mk3(R1), u = sub3(mk3(R2), v0), v = sub3(mk3(R3), v0);
+    const int gy = nparts > 1 ? cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]) : 0;
+    const int gz = nparts > 1 ? cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]) : 0;
+    for (int i = ia; i <= ib; i++) {
+      const float sx = lat_pos(p, 0, i);
+      if (nparts > 1) {   // the rank that resolves the cell's 3dr-cell owns the cell (disjoint bits: a SUM merge is an OR)
+        const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
+        const long long c = ((long long)gx * p.gridn[1] + gy) * p.gridn[2] + gz;
+        if (chunk_owner(c >> 5, nparts) != A.res_part) continue;
+      }
+      const f3 s = mk3(sx, sy, sz);
+      const int idx[3] = {i, j, k};
+      uint32_t cl = 0;
+#pragma unroll
+      for (int d = 0; d < 6; d++) {
+        const int ax = d >> 1, e = idx[ax] + ((d & 1) ? 1 : -1);
+        if (e < 0 || e >= A.dimg[ax]) continue;
+        const float dc = fsub(lat_pos(p, ax, e), ax == 0 ? sx : ax == 1 ? sy : sz);
+        const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
+        if (tri_collision(A, s, dir, n, v0, u, v, R1.w, R2.w, R3.w, R4.w)) cl |= 1u << d;
+      }
+      if (!cl) continue;
+      const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + (i >> 5);
+#pragma unroll
+      for (int d = 0; d < 6; d++)
+        if (cl >> d & 1) atomicOr(&A.B[d * A.nw + wi], 1u << (i & 31));
+    }
+  }
+}
+
+// conservative fshape descriptors, one thread per free-surface triangle (DESIGN.md "fill / free surface").
+// A triangle is "cullable" when its stored normal is consistent with its plane and it is well conditioned; then
+// checkTriangleCollision(s, dir, .) can only be true for s inside the triangle's bounding box grown by the margin below, or
+// (ray-in-plane rule, crixus_d.cu:766-769) within 4 eps of its plane when some axis direction is parallel to the plane within
+// eps.  eps is ABSOLUTE (1e-5 x the domain extent) but enters the segment test as a RELATIVE tolerance (r <= 1 + eps,
+// t1, t2 >= -eps in barycentric units), so every margin scales with it: the ray may start (1 + eps) dr away, and the accepted
+// barycentric region overhangs the triangle by eps (|u| + |v|).
+__global__ void k_fs_desc(FillArgs A, FsDesc *out)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.cnbe) return;
+  const int64_t i = A.nbe - A.cnbe + t;
+  const float4 n4 = A.norm[i];
+  const int4 E = A.ep[i];
+  const float4 a4 = A.pos[E.x], b4 = A.pos[E.y], c4 = A.pos[E.z];
+  const float n[3] = {n4.x, n4.y, n4.z}, a[3] = {a4.x, a4.y, a4.z}, b[3] = {b4.x, b4.y, b4.z}, c[3] = {c4.x, c4.y, c4.z};
+  double lu = 0, lv = 0, ln = 0, nu = 0, nv = 0, uv = 0;
+  for (int k = 0; k < 3; k++) {
+    const double u = (double)b[k] - a[k], v = (double)c[k] - a[k];
+    lu += u * u; lv += v * v; ln += (double)n[k] * n[k];
+    nu += (double)n[k] * u; nv += (double)n[k] * v; uv += u * v;
+  }
+  lu = sqrt(lu); lv = sqrt(lv); ln = sqrt(ln);
+  const double eps = A.p.eps;
+  FsDesc d;
+  d.cull = ln > 0 && lu > 0 && lv > 0 && fabs(nu) <= 1e-3 * ln * lu && fabs(nv) <= 1e-3 * ln * lv &&
+           (lu * lu * lv * lv - uv * uv) >= 1e-4 * lu * lu * lv * lv && eps < 0.25;
+  const double margin = (1.5 + eps) * A.p.dr + (0.01 + 2.0 * eps) * (lu + lv) + 10.0 * eps;
+  d.quirk = 0;
+  for (int k = 0; k < 3; k++) {
+    const float mn = fminf(a[k], fminf(b[k], c[k])), mx = fmaxf(a[k], fmaxf(b[k], c[k]));
+    d.lo[k] = (float)(mn - margin); d.hi[k] = (float)(mx + margin);
+    d.n[k] = n[k]; d.v0[k] = a[k];
+    if (fabs((double)n[k]) * A.p.dr * 0.5 < eps) d.quirk = 1;
+  }
+  out[t] = d;
+}
+
 // ---- one round -------------------------------------------------------------------------------------------------
-__global__ void k_round_prep(int32_t *count) { count[0] = 0; count[1] = 0; count[2] = 0; count[3] = 0; }
+__global__ void k_round_prep(int32_t *count) { count[0] = 0; count[1] = 0; }
 
 __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
 {
@@ -492,63 +728,7 @@ __global__ void __launch_bounds__(256) k_build_list(FillArgs A)
     if (A.act_cur[t]) {
       A.act_cur[t] = 0;
       A.list[atomicAdd(&A.count[0], 1)] = (int32_t)t;
-      if (!A.tile_res[t]) {   // first visit: its hard cells are resolved before k_fill_tiles runs
-        A.tile_res[t] = 1;
-        A.rlist[atomicAdd(&A.count[2], 1)] = (int32_t)t;
-      }
     }
-}
-
-// bulk resolution of the hard cells of newly reached tiles: one warp per 32-cell word, one warp-cooperative
-// checkCollision per hard cell for all of its in-lattice directions at once
-template <bool ALL>
-__global__ void __launch_bounds__(256, 3) k_resolve_tiles(FillArgs A)
-{
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    long long item = 0;
-    if (lane == 0) item = ALL ? (long long)atomicAdd((unsigned long long *)A.count64, 1ull) : (long long)atomicAdd(&A.count[3], 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (ALL && A.res_nparts > 1) {   // interleaved sharding: every group of nparts 64-item chunks is dealt one chunk per rank, the
-      const long long g = item >> 6;   // order rotated by a hash of the group (plane-aligned walls would otherwise land on few ranks)
-      const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)A.res_nparts);
-      item = (g * A.res_nparts + (A.res_part + rot) % A.res_nparts) * 64 + (item & 63);
-    }
-    if (ALL) item += A.item_lo;
-    if (item >= (ALL ? A.item_hi : (long long)A.count[2] * FT_THREADS)) break;
-    const int tile = ALL ? (int)(item / FT_THREADS) : A.rlist[item / FT_THREADS], wt = (int)(item % FT_THREADS);
-    const int wx = tile % A.wr, tyi = (tile / A.wr) % A.ty, tzi = tile / (A.wr * A.ty);
-    const int j = tyi * FT_Y + wt % FT_Y, k = tzi * FT_Z + wt / FT_Y;
-    if (j >= A.dimg[1] || k >= A.dimg[2] || k < A.k_lo || k >= A.k_hi) continue;
-    const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
-    uint32_t hw;
-    if (ALL && A.classify_inline) {
-      hw = classify_word_warp(A, wx, j, k, lane);
-      if (lane == 0) A.H[wi] = hw;
-    } else hw = A.H[wi];
-    uint32_t todo = hw & ~A.F[wi];
-    if (!todo) continue;
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
-    while (todo) {
-      const int b = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int i = wx * 32 + b;
-      const uint32_t dm = (i > 0 ? 1u : 0u) | (i + 1 < A.dimg[0] ? 2u : 0u) | (j > 0 ? 4u : 0u) | (j + 1 < A.dimg[1] ? 8u : 0u) |
-                          (k > 0 ? 16u : 0u) | (k + 1 < A.dimg[2] ? 32u : 0u);
-      const uint32_t coll = warp_check_collision(A, i, j, k, dm, lane);
-      const uint32_t bit = 1u << b;
-      if (coll & 1u) b0 |= bit;
-      if (coll & 2u) b1 |= bit;
-      if (coll & 4u) b2 |= bit;
-      if (coll & 8u) b3 |= bit;
-      if (coll & 16u) b4 |= bit;
-      if (coll & 32u) b5 |= bit;
-    }
-    if (lane == 0) {
-      A.B[0 * A.nw + wi] = b0; A.B[1 * A.nw + wi] = b1; A.B[2 * A.nw + wi] = b2;
-      A.B[3 * A.nw + wi] = b3; A.B[4 * A.nw + wi] = b4; A.B[5 * A.nw + wi] = b5;
-    }
-  }
 }
 
 struct TileSM {
@@ -556,7 +736,7 @@ struct TileSM {
   int changed, newbits;
 };
 
-// propagation inside active tiles: pure bit arithmetic (all directed tests of the tile are already in the B planes)
+// propagation inside active tiles: pure bit arithmetic (all directed tests are already in the B planes)
 __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
 {
   __shared__ TileSM S;
@@ -588,17 +768,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
     const bool inrow = j < A.dimg[1] && k < A.dimg[2];
     const bool owned = inrow && k >= A.k_lo && k < A.k_hi;
     const int64_t wi = ((int64_t)k * A.dimg[1] + j) * A.wr + wx;
-    uint32_t xl = 0, xr = 0, hmask = 0;
-    // per direction: cells that may be entered from that neighbour (easy cells always, hard cells unless blocked)
+    uint32_t xl = 0, xr = 0;
+    // per direction: cells that may be entered from that neighbour (every cell unless its directed test blocks it)
     uint32_t o0 = vmask, o1 = vmask, o2 = vmask, o3 = vmask, o4 = vmask, o5 = vmask;
-    if (inrow) {
+    if (owned) {
       if (wx > 0) xl = A.F[wi - 1] >> 31;
       if (wx + 1 < A.wr) xr = A.F[wi + 1] << 31;
-      hmask = A.H[wi];
-      if (hmask) {
-        o0 &= ~(hmask & A.B[0 * A.nw + wi]); o1 &= ~(hmask & A.B[1 * A.nw + wi]); o2 &= ~(hmask & A.B[2 * A.nw + wi]);
-        o3 &= ~(hmask & A.B[3 * A.nw + wi]); o4 &= ~(hmask & A.B[4 * A.nw + wi]); o5 &= ~(hmask & A.B[5 * A.nw + wi]);
-      }
+      o0 &= ~A.B[0 * A.nw + wi]; o1 &= ~A.B[1 * A.nw + wi]; o2 &= ~A.B[2 * A.nw + wi];
+      o3 &= ~A.B[3 * A.nw + wi]; o4 &= ~A.B[4 * A.nw + wi]; o5 &= ~A.B[5 * A.nw + wi];
     }
     __syncthreads();
     const uint32_t f_start = S.F[lz + 1][ly + 1];
@@ -648,15 +825,16 @@ struct FillState {
   const uint32_t *fpos_key = nullptr;
   int64_t dimg[3] = {0, 0, 0};
   int64_t nbe = 0, cnbe = 0;
-  uint32_t *F = nullptr, *B = nullptr;   // B: 6 blocked planes + the hard mask
+  uint32_t *F = nullptr, *B = nullptr;   // B: 6 blocked planes
+  uint32_t *halo = nullptr;              // two received boundary planes (multi-GPU)
   float4 *rec = nullptr;
-  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0;
-  uint8_t *nbflag = nullptr, *act = nullptr, *tile_res = nullptr;
-  int32_t *list = nullptr, *count = nullptr, *rlist = nullptr;
+  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
+  uint8_t *nbflag = nullptr, *act = nullptr;
+  int32_t *list = nullptr, *count = nullptr;
   FsDesc *fs = nullptr;
-  int nfs = 0, all_hard = 0;
   int64_t nw = 0, ntiles = 0;
-  int resolved_lo = 0, resolved_hi = 0;   // planes whose hard cells were resolved up front
+  int resolved_lo = 0, resolved_hi = 0;   // planes whose directed tests are in B
+  int act_swapped = 0;                    // which half of `act` is the current one (kept across slab calls)
 };
 
 void cx_fill_state_free(cx_ctx *ctx)
@@ -664,45 +842,9 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->tile_res); cudaFree(s->rlist); cudaFree(s->rec);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo);
   delete s;
   ctx->fill_state = nullptr;
-}
-
-// conservative fshape descriptors, one thread per free-surface triangle (DESIGN.md "fill / easy cells").
-// A triangle is "cullable" when its stored normal is consistent with its plane and it is well conditioned; then
-// checkTriangleCollision(s, dir, .) can only be true for s inside the triangle's bounding box grown by
-// 1.5 dr + 1 % of its edge lengths + 10 eps, or (ray-in-plane rule, crixus_d.cu:766-769) within 4 eps of its plane
-// when some axis direction is parallel to the plane within eps.  One non-cullable triangle makes every cell hard.
-__global__ void k_fs_desc(FillArgs A, FsDesc *out, int *all_hard)
-{
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= A.cnbe) return;
-  const int64_t i = A.nbe - A.cnbe + t;
-  const float4 n4 = A.norm[i];
-  const int4 E = A.ep[i];
-  const float4 a4 = A.pos[E.x], b4 = A.pos[E.y], c4 = A.pos[E.z];
-  const float n[3] = {n4.x, n4.y, n4.z}, a[3] = {a4.x, a4.y, a4.z}, b[3] = {b4.x, b4.y, b4.z}, c[3] = {c4.x, c4.y, c4.z};
-  double lu = 0, lv = 0, ln = 0, nu = 0, nv = 0, uv = 0;
-  for (int k = 0; k < 3; k++) {
-    const double u = (double)b[k] - a[k], v = (double)c[k] - a[k];
-    lu += u * u; lv += v * v; ln += (double)n[k] * n[k];
-    nu += (double)n[k] * u; nv += (double)n[k] * v; uv += u * v;
-  }
-  lu = sqrt(lu); lv = sqrt(lv); ln = sqrt(ln);
-  const bool cullable = ln > 0 && lu > 0 && lv > 0 && fabs(nu) <= 1e-3 * ln * lu && fabs(nv) <= 1e-3 * ln * lv &&
-                        (lu * lu * lv * lv - uv * uv) >= 1e-4 * lu * lu * lv * lv;
-  if (!cullable) atomicExch(all_hard, 1);
-  const double margin = 1.5 * A.p.dr + 0.01 * (lu + lv) + 10.0 * A.p.eps;
-  FsDesc d;
-  d.quirk = 0;
-  for (int k = 0; k < 3; k++) {
-    const float mn = fminf(a[k], fminf(b[k], c[k])), mx = fmaxf(a[k], fmaxf(b[k], c[k]));
-    d.lo[k] = (float)(mn - margin); d.hi[k] = (float)(mx + margin);
-    d.n[k] = n[k]; d.v0[k] = a[k];
-    if (fabs((double)n[k]) * A.p.dr * 0.5 < A.p.eps) d.quirk = 1;
-  }
-  out[t] = d;
 }
 
 static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
@@ -728,21 +870,17 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     }
     // buffers are kept between calls and only grow (cudaMalloc/cudaFree cost milliseconds and synchronise)
     if (nw > s->cap_nw) {
-      // the hard mask lives right behind the six blocked planes: one buffer of 7 planes, so that a multi-GPU caller merges
-      // mask and planes with a single all-reduce (cx_fill_resolve_part)
       cudaFree(s->F); cudaFree(s->B);
       s->F = s->B = nullptr; s->cap_nw = 0;
       CX_CUDA(ctx, cudaMalloc(&s->F, sizeof(uint32_t) * (size_t)nw));
-      CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 7));
+      CX_CUDA(ctx, cudaMalloc(&s->B, sizeof(uint32_t) * (size_t)nw * 6));
       s->cap_nw = nw;
     }
     if (ntiles > s->cap_ntiles) {
-      cudaFree(s->act); cudaFree(s->list); cudaFree(s->tile_res); cudaFree(s->rlist);
-      s->act = s->tile_res = nullptr; s->list = s->rlist = nullptr; s->cap_ntiles = 0;
+      cudaFree(s->act); cudaFree(s->list);
+      s->act = nullptr; s->list = nullptr; s->cap_ntiles = 0;
       CX_CUDA(ctx, cudaMalloc(&s->act, (size_t)ntiles * 2));
       CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
-      CX_CUDA(ctx, cudaMalloc(&s->tile_res, (size_t)ntiles));
-      CX_CUDA(ctx, cudaMalloc(&s->rlist, sizeof(int32_t) * (size_t)ntiles));
       s->cap_ntiles = ntiles;
     }
     if (p->gridn[3] > s->cap_ncell) {
@@ -755,16 +893,18 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       CX_CUDA(ctx, cudaMalloc(&s->rec, sizeof(float4) * FREC * (size_t)nbe));
       s->cap_rec = nbe;
     }
+    if (cnbe > s->cap_fs) {
+      cudaFree(s->fs); s->fs = nullptr; s->cap_fs = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * (size_t)cnbe));
+      s->cap_fs = cnbe;
+    }
     if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 8));
-    if (!s->fs) CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * FS_MAX_DESC + 16));
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
     for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
-    CX_CUDA(ctx, cudaMemsetAsync(s->tile_res, 0, (size_t)ntiles, st));
-    CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 7, st));
+    CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
     CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)ntiles * 2, st));
-    // fshape descriptors are built on the device (k_fs_desc): no host round trip
-    s->nfs = (cnbe > 0 && cnbe <= FS_MAX_DESC) ? (int)cnbe : 0;
-    s->all_hard = (cnbe > FS_MAX_DESC) ? 1 : 0;
+    s->resolved_lo = s->resolved_hi = 0;
+    s->act_swapped = 0;
   }
   memset(A, 0, sizeof(*A));
   A->p = *p;
@@ -774,70 +914,83 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->wr = wr; A->ty = ty; A->tz = tz; A->ntiles = ntiles; A->nw = nw;
   A->k_lo = 0; A->k_hi = (int)dimg[2];
   A->w_lo = 0; A->w_hi = nw;
-  A->item_lo = 0; A->item_hi = (long long)ntiles * FT_THREADS;
-  A->classify_inline = getenv("CX_FILL_LAZY") ? 0 : 1;
-  A->F = s->F; A->H = s->B + 6 * nw; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs; A->nfs = s->nfs; A->all_hard = s->all_hard;
-  A->act_cur = s->act; A->act_next = s->act + ntiles; A->list = s->list; A->count = s->count;
-  A->tile_res = s->tile_res; A->rlist = s->rlist;
+  A->F = s->F; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs;
+  A->act_cur = s->act + (s->act_swapped ? ntiles : 0); A->act_next = s->act + (s->act_swapped ? 0 : ntiles);
+  A->list = s->list; A->count = s->count;
   A->count64 = (unsigned long long *)(s->count + 4);
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
   A->rec = s->rec;
-  A->rrej = 1.2f * fmaxf(p->dr_wall, p->dr);
+  // plane-distance reject: a lattice step reaches (1 + eps) dr in barycentric units of the ray parameter, and the distance
+  // test reaches dr_wall; 20 % on top for everything the stored normal and the float arithmetic can add
+  A->rrej = (1.2f + 2.0f * p->eps) * fmaxf(p->dr_wall, p->dr);
   A->drw2 = p->dr_wall * p->dr_wall;
   A->one_eps = 1.0 + (double)p->eps;
-  A->all_hard_d = (const int *)((const char *)s->fs + sizeof(FsDesc) * FS_MAX_DESC);
+  A->dist_dead = (p->eps >= A->drw2) ? 1 : 0;
+  static const bool nofilter = getenv("CX_FILL_NOFILTER") != nullptr;
+  A->nofilter = nofilter ? 1 : 0;
+  {
+    const float f = 1.01f * (1.0f + 3.0f * p->eps);
+    A->sph2 = f * f;
+  }
   if (fresh) {
     k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec);
     CX_LAUNCH_CHECK(ctx, "k_seg_prep");
-    CX_CUDA(ctx, cudaMemsetAsync((void *)A->all_hard_d, 0, sizeof(int), st));
-    if (s->nfs > 0) {
-      k_fs_desc<<<cx_blocks(s->nfs, 128), 128, 0, st>>>(*A, s->fs, (int *)A->all_hard_d);
+    if (cnbe > 0) {
+      k_fs_desc<<<cx_blocks(cnbe, 128), 128, 0, st>>>(*A, s->fs);
       CX_LAUNCH_CHECK(ctx, "k_fs_desc");
     }
     k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
     CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
-    if (!A->classify_inline) {   // lazy per-round resolution (CX_FILL_LAZY=1, kept for comparison) reads the mask tile by tile
-      k_classify<<<cx_blocks(nw, 256, ctx->num_sms * 16), 256, 0, st>>>(*A);
-      CX_LAUNCH_CHECK(ctx, "k_classify");
-    }
   }
   *out = s;
   return CX_OK;
 }
 
-// runs rounds until no tile is active; returns the number of rounds
-static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int32_t *rounds_out)
+// directed tests of the planes [A->k_lo, A->k_hi), share (res_part of res_nparts), into the B planes
+static int fill_resolve(cx_ctx *ctx, FillArgs *A)
+{
+  cudaStream_t st = ctx->stream;
+  if (A->k_hi <= A->k_lo) return CX_OK;
+  CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+  k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
+  CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
+  if (A->cnbe > 0) {
+    const int64_t total = (int64_t)A->dimg[1] * (A->k_hi - A->k_lo) * A->cnbe;
+    k_resolve_fs<<<cx_blocks(total, 128, ctx->num_sms * 32), 128, 0, st>>>(*A);
+    CX_LAUNCH_CHECK(ctx, "k_resolve_fs");
+  }
+  return CX_OK;
+}
+
+// propagation rounds.  max_rounds == 0: until no tile is active (the active count is read back every 4 rounds);
+// max_rounds > 0: exactly that many rounds without any host synchronisation (empty rounds are cheap); the number of tiles
+// still active afterwards is left in count[0] on the device.
+static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int max_rounds, int32_t *rounds_out)
 {
   cudaStream_t st = ctx->stream;
   int rounds = 0;
   const int grid_tiles = ctx->num_sms * 4;
   int32_t *hcount = (int32_t *)(ctx->h_mail + 28);
   for (;;) {
-    // a batch of rounds without host synchronisation; empty rounds are cheap
-    const int batch = 4;
+    const int batch = max_rounds > 0 ? max_rounds : 4;
     for (int r = 0; r < batch; r++) {
       k_round_prep<<<1, 1, 0, st>>>(A->count);
       CX_LAUNCH_CHECK(ctx, "k_round_prep");
       k_build_list<<<cx_blocks(A->ntiles, 256, ctx->num_sms * 8), 256, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_build_list");
-      if (!A->resolved_all) {
-        k_resolve_tiles<false><<<ctx->num_sms * 4, 256, 0, st>>>(*A);
-        CX_LAUNCH_CHECK(ctx, "k_resolve_tiles");
-      }
       A->force_activate = (rounds == 0);
       k_fill_tiles<<<grid_tiles, FT_THREADS, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_fill_tiles");
       std::swap(A->act_cur, A->act_next);
+      s->act_swapped ^= 1;
       rounds++;
     }
+    if (max_rounds > 0) break;
     CX_CUDA(ctx, cudaMemcpyAsync(hcount, A->count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CX_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->fill_unfinished = 0;
     if (hcount[0] == 0) break;  // the last round of the batch found no active tile
-    if (ctx->fill_max_rounds > 0 && rounds >= ctx->fill_max_rounds) { ctx->fill_unfinished = 1; break; }   // caller exchanges halos first
     if (rounds > 4000000) return cx_fail(ctx, CX_INTERNAL_ERROR, "fill: round limit");
   }
-  (void)s;
   if (rounds_out) *rounds_out = rounds;
   return CX_OK;
 }
@@ -857,14 +1010,13 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   FillArgs A;
   FillState *s = nullptr;
   const bool dbg = getenv("CX_DEBUG_TIMING") != nullptr;
-  double t0 = 0, t1 = 0, t2 = 0;
+  double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
   if (dbg) { cudaStreamSynchronize(ctx->stream); t0 = dbg_now(); }
   // first_call: 1 = start of a fill (state is rebuilt), 2 = start of a fill whose directed tests were resolved by
   // cx_fill_resolve_part (+ the caller's merge of the blocked planes): the state is kept, the seed is still to be set
   const bool pre_resolved = first_call == 2;
   int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, first_call == 1, &A, &s);
   if (rc != CX_OK) return rc;
-  if (dbg) { cudaStreamSynchronize(ctx->stream); t1 = dbg_now(); }
   if (k_begin < 0 || k_end > A.dimg[2] || k_begin >= k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
   if (pre_resolved && !(s->resolved_lo <= k_begin && s->resolved_hi >= k_end))
     return cx_fail(ctx, CX_WRONG_INPUT, "fill: first_call = 2 without cx_fill_resolve_part");
@@ -873,12 +1025,13 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   const int64_t wplane = (int64_t)A.wr * A.dimg[1];
   A.w_lo = wplane * (k_begin > 0 ? k_begin - 1 : 0);
   A.w_hi = wplane * (k_end < A.dimg[2] ? k_end + 1 : k_end);
-  A.item_lo = (long long)(k_begin / FT_Z) * A.ty * A.wr * FT_THREADS;
-  A.item_hi = (long long)((k_end + FT_Z - 1) / FT_Z) * A.ty * A.wr * FT_THREADS;
   cudaStream_t st = ctx->stream;
   CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
-  // a previous call that stopped at the round limit left its pending tile activations in the first half of s->act
-  if (first_call || !ctx->fill_unfinished) CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  // a previous call that stopped at the round limit left its pending tile activations in the current half of s->act, and
+  // cx_fill_resolve_part (first_call = 2) left the activations of the tiles that already hold set cells
+  if (first_call == 1 || (first_call == 0 && !ctx->fill_unfinished)) {
+    CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  }
   A.merge = first_call == 1 ? 0 : 1;
   k_unpack<<<cx_blocks(A.w_hi - A.w_lo, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_unpack");
@@ -886,32 +1039,31 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
     k_seed<<<1, 1, 0, st>>>(A, seed);
     CX_LAUNCH_CHECK(ctx, "k_seed");
   }
-  // Resolve every hard cell of the owned planes up front, in one balanced launch: the directed tests are pure functions
-  // of the geometry, so nothing is gained by waiting for the flood to arrive (24 small launches with tails before).
-  // CX_FILL_LAZY=1 restores the per-round resolution of newly reached tiles.
-  static const bool lazy = getenv("CX_FILL_LAZY") != nullptr;
-  if (!lazy) {
-    if (first_call == 1) { s->resolved_lo = s->resolved_hi = 0; }
-    if (!(s->resolved_lo <= A.k_lo && s->resolved_hi >= A.k_hi)) {
-      CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
-      k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
-      CX_LAUNCH_CHECK(ctx, "k_resolve_all");
-      s->resolved_lo = A.k_lo; s->resolved_hi = A.k_hi;
-    }
-    A.resolved_all = 1;
+  if (dbg) { cudaStreamSynchronize(ctx->stream); t1 = dbg_now(); }
+  // Resolve every directed test of the owned planes up front, in one balanced launch: they are pure functions of the
+  // geometry, so nothing is gained by waiting for the flood to arrive.
+  if (!(s->resolved_lo <= A.k_lo && s->resolved_hi >= A.k_hi)) {
+    rc = fill_resolve(ctx, &A);
+    if (rc != CX_OK) return rc;
+    s->resolved_lo = A.k_lo; s->resolved_hi = A.k_hi;
   }
-  rc = fill_rounds(ctx, &A, s, rounds_host);
+  if (dbg) { cudaStreamSynchronize(ctx->stream); t2 = dbg_now(); }
+  int32_t rounds = 0;
+  rc = fill_rounds(ctx, &A, s, ctx->fill_max_rounds, &rounds);
   if (rc != CX_OK) return rc;
-  if (dbg) {
-    cudaStreamSynchronize(ctx->stream);
-    t2 = dbg_now();
-    fprintf(stderr, "[cx fill] prepare %.3f ms, rounds %.3f ms (%d rounds)\n", 1e3 * (t1 - t0), 1e3 * (t2 - t1), rounds_host ? *rounds_host : -1);
-  }
+  if (rounds_host) *rounds_host = rounds;
+  if (dbg) { cudaStreamSynchronize(ctx->stream); t3 = dbg_now(); }
   A.w_lo = wplane * k_begin; A.w_hi = wplane * k_end;   // only owned planes are written back
   k_pack<<<cx_blocks(A.w_hi - A.w_lo, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_pack");
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 28, A.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CX_CUDA(ctx, cudaStreamSynchronize(st));
+  // with a round limit: the last round still had active tiles -> what they activated is pending in the current half of s->act
+  ctx->fill_unfinished = (ctx->fill_max_rounds > 0 && *(int32_t *)(ctx->h_mail + 28) != 0) ? 1 : 0;
+  if (dbg)
+    fprintf(stderr, "[cx fill] prepare+unpack %.3f ms, resolve %.3f ms, %d rounds %.3f ms\n", 1e3 * (t1 - t0), 1e3 * (t2 - t1), rounds,
+            1e3 * (t3 - t2));
   if (changed_host) *changed_host = ctx->h_mail[24];
   return CX_OK;
 }
@@ -920,70 +1072,65 @@ extern "C" int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_
                                 const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed, int64_t *nfi_host,
                                 int32_t *rounds_host)
 {
-  if (!p) return CX_WRONG_INPUT;
+  if (!ctx || !p) return CX_WRONG_INPUT;
   int64_t dimg[3];
   cx_fill_dims(p, dimg);
   if (seed >= dimg[0] * dimg[1] * dimg[2]) return cx_fail(ctx, CX_SEED_OUTSIDE, "fill: seed outside the lattice");
-  return cx_fill_geometry_slab(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, seed, 0, dimg[2], 1, nfi_host, rounds_host);
+  const int keep = ctx->fill_max_rounds;
+  ctx->fill_max_rounds = 0;
+  const int rc = cx_fill_geometry_slab(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, seed, 0, dimg[2], 1, nfi_host, rounds_host);
+  ctx->fill_max_rounds = keep;
+  return rc;
 }
 
-// ---- multi-GPU helpers: resolve a slab, merge the blocked planes across ranks, propagate everywhere ---------------
-// The directed tests are pure functions of the geometry: each rank resolves the hard cells of its own planes
-// (the expensive part, shards perfectly), the six blocked bit planes are merged by the caller (disjoint rows: a SUM
-// all-reduce is an OR), and the cheap propagation then runs on the whole lattice on every rank -- no halo exchange and
-// no per-sweep collective.  Meant for lattices whose bit planes are small; large lattices use cx_fill_geometry_slab.
-extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
-                                    const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
-                                    int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words)
+// ---- multi-GPU building blocks (stage level; cx_dist_fill_geometry below strings them together) ---------------------
+// The directed tests are pure functions of the geometry: each rank resolves its share, the six blocked bit planes are merged
+// by the caller (every lattice cell is resolved by exactly one rank, so the shares are disjoint bit sets and a SUM
+// all-reduce is an OR), and the cheap propagation then runs on the whole lattice on every rank (cx_fill_propagate) or by
+// z-slab (cx_fill_geometry_slab(first_call = 2)).
+static int resolve_share(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d, const float *pos_d,
+                         int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin, int64_t k_end, int nparts, int part,
+                         uint32_t **blocked_d, int64_t *blocked_words)
 {
-  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
   FillArgs A;
   FillState *s = nullptr;
   int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 1, &A, &s);
   if (rc != CX_OK) return rc;
   if (k_begin < 0 || k_end > A.dimg[2] || k_begin > k_end) return cx_fail(ctx, CX_WRONG_INPUT, "fill: bad slab");
   cudaStream_t st = ctx->stream;
-  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
   A.merge = 0;
-  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);   // cells that are already set need no test
+  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
+  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);   // tiles that hold set cells are activated
   CX_LAUNCH_CHECK(ctx, "k_unpack");
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
-  if (k_end > k_begin) {
-    CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
-    k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
-    CX_LAUNCH_CHECK(ctx, "k_resolve_all");
-  }
+  A.res_nparts = nparts; A.res_part = part;
+  rc = fill_resolve(ctx, &A);
+  if (rc != CX_OK) return rc;
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
   if (blocked_d) *blocked_d = s->B;
-  if (blocked_words) *blocked_words = 7 * A.nw;
+  if (blocked_words) *blocked_words = 6 * A.nw;
   return CX_OK;
 }
 
-// interleaved variant: the 32-cell words of the lattice are dealt to the ranks in chunks of 64 (z-slabs balance badly:
-// the floor slab holds most of the hard cells); same contract otherwise
+extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                    const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
+                                    int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words)
+{
+  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
+  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k_begin, k_end, 1, 0, blocked_d, blocked_words);
+}
+
+// interleaved variant: the 3dr-cells are dealt to the ranks in chunks of 32 (z-slabs balance badly: the floor slab holds a
+// whole wall); same contract otherwise
 extern "C" int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                                     const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
                                     uint32_t **blocked_d, int64_t *blocked_words)
 {
   if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe || nparts < 1 || part < 0 || part >= nparts)
     return CX_WRONG_INPUT;
-  FillArgs A;
-  FillState *s = nullptr;
-  int rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 1, &A, &s);
-  if (rc != CX_OK) return rc;
-  cudaStream_t st = ctx->stream;
-  CX_CUDA(ctx, cudaMemsetAsync(s->act, 0, (size_t)A.ntiles * 2, st));
-  A.merge = 0;
-  k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
-  CX_LAUNCH_CHECK(ctx, "k_unpack");
-  A.res_nparts = nparts; A.res_part = part;
-  CX_CUDA(ctx, cudaMemsetAsync(A.count64, 0, sizeof(unsigned long long), st));
-  k_resolve_tiles<true><<<ctx->num_sms * 6, 256, 0, st>>>(A);
-  CX_LAUNCH_CHECK(ctx, "k_resolve_all");
-  s->resolved_lo = 0; s->resolved_hi = A.dimg[2];
-  if (blocked_d) *blocked_d = s->B;
-  if (blocked_words) *blocked_words = 7 * A.nw;
-  return CX_OK;
+  int64_t dimg[3];
+  cx_fill_dims(p, dimg);
+  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], nparts, part, blocked_d, blocked_words);
 }
 
 extern "C" int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
@@ -1004,8 +1151,7 @@ extern "C" int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos
   CX_LAUNCH_CHECK(ctx, "k_unpack");
   k_seed<<<1, 1, 0, st>>>(A, seed);
   CX_LAUNCH_CHECK(ctx, "k_seed");
-  A.resolved_all = 1;
-  rc = fill_rounds(ctx, &A, s, rounds_host);
+  rc = fill_rounds(ctx, &A, s, 0, rounds_host);
   if (rc != CX_OK) return rc;
   k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
   CX_LAUNCH_CHECK(ctx, "k_pack");
@@ -1024,3 +1170,131 @@ extern "C" int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds)
   return CX_OK;
 }
 extern "C" int cx_fill_unfinished(cx_ctx *ctx) { return ctx ? ctx->fill_unfinished : 0; }
+extern "C" int cx_dist_set_fill_mode(cx_ctx *ctx, int mode)
+{
+  if (!ctx || mode < 0 || mode > 2) return CX_WRONG_INPUT;
+  ctx->dist_fill_mode = mode;
+  return CX_OK;
+}
+
+// ================================================================================================ multi-GPU geometry fill
+// fill_fluid_complex to its fixed point over all ranks of the context's communicator (the loop of crixus.cu:934-947, sharded):
+//   1. every rank resolves its share of the directed tests (3dr-cell chunks dealt round-robin with a rotation: balanced,
+//      unlike z-slabs whose floor and lid hold whole walls);
+//   2. small lattices (blocked planes <= CX_DIST_SMALL_BYTES or fewer than 2 planes per rank): the planes are all-reduced and
+//      every rank floods the whole lattice -- no halo exchange, no per-sweep collective;
+//      large lattices: each blocked plane range is REDUCED to the rank that owns the z-slab (a reduce-scatter with unequal
+//      parts), every rank floods its slab for CX_DIST_FILL_ROUNDS rounds, boundary planes (row-aligned words) go to the
+//      z-neighbours, and one all-reduce of two counters decides termination; finally the owned planes are all-gathered
+//      (grouped broadcasts) and packed into the reference's bit order on every rank.
+// k_flags: [0] = this rank still has work (active tiles or fresh halo bits)
+__global__ void k_dist_flags(const int32_t *count, const int *fresh, const unsigned long long *changed, long long *out)
+{
+  out[0] = (count[0] != 0 || *fresh != 0) ? 1 : 0;
+  out[1] = (long long)*changed;
+}
+
+extern "C" int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                                     const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                                     int64_t *nfi_host, int32_t *rounds_host)
+{
+  if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
+  const int world = cx_world(ctx), rank = cx_rank(ctx);
+  if (world == 1) return cx_fill_geometry(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, seed, nfi_host, rounds_host);
+  CxColl *coll = cx_coll(ctx);
+  int64_t dimg[3];
+  cx_fill_dims(p, dimg);
+  if (seed >= dimg[0] * dimg[1] * dimg[2]) return cx_fail(ctx, CX_SEED_OUTSIDE, "fill: seed outside the lattice");
+  cudaStream_t st = ctx->stream;
+  uint32_t *B = nullptr;
+  int64_t bwords = 0;
+  int rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], world, rank, &B, &bwords);
+  if (rc != CX_OK) return rc;
+  FillArgs A;
+  FillState *s = nullptr;
+  rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, &A, &s);
+  if (rc != CX_OK) return rc;
+  CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
+  bool small = (size_t)bwords * sizeof(uint32_t) <= CX_DIST_SMALL_BYTES || dimg[2] < 2 * world;
+  if (ctx->dist_fill_mode == 2 && dimg[2] >= 2 * world) small = false;   // cx_dist_set_fill_mode (tests, tuning)
+  if (ctx->dist_fill_mode == 1) small = true;
+  int32_t rounds = 0;
+  if (small) {
+    rc = coll->allreduce_sum_u32(ctx, B, bwords);
+    if (rc != CX_OK) return rc;
+    k_seed<<<1, 1, 0, st>>>(A, seed);
+    CX_LAUNCH_CHECK(ctx, "k_seed");
+    rc = fill_rounds(ctx, &A, s, 0, &rounds);
+    if (rc != CX_OK) return rc;
+    k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+    CX_LAUNCH_CHECK(ctx, "k_pack");
+    CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 24, A.changed, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (nfi_host) *nfi_host = ctx->h_mail[24];
+    if (rounds_host) *rounds_host = rounds;
+    return CX_OK;
+  }
+  // ---- z-slabs
+  const int64_t wplane = (int64_t)A.wr * A.dimg[1];
+  std::vector<CxSeg> segs;
+  for (int r = 0; r < world; r++) {
+    int64_t a, b;
+    cx_split_range(dimg[2], world, r, &a, &b);
+    for (int d = 0; d < 6; d++) segs.push_back({d * A.nw + wplane * a, wplane * (b - a), r});
+  }
+  rc = coll->reduce_segments_u32(ctx, B, segs.data(), (int)segs.size());
+  if (rc != CX_OK) return rc;
+  int64_t k0, k1;
+  cx_split_range(dimg[2], world, rank, &k0, &k1);
+  A.k_lo = (int)k0; A.k_hi = (int)k1;
+  if (wplane > s->cap_halo) {
+    cudaFree(s->halo); s->halo = nullptr; s->cap_halo = 0;
+    CX_CUDA(ctx, cudaMalloc(&s->halo, sizeof(uint32_t) * (size_t)wplane * 2));
+    s->cap_halo = wplane;
+  }
+  k_seed<<<1, 1, 0, st>>>(A, seed);
+  CX_LAUNCH_CHECK(ctx, "k_seed");
+  int *fresh = (int *)(s->count + 6);
+  long long *flags = (long long *)(ctx->d_mail + 36);
+  for (int it = 0;; it++) {
+    int32_t r = 0;
+    rc = fill_rounds(ctx, &A, s, CX_DIST_FILL_ROUNDS, &r);   // force_activate in its first round: tiles holding fresh halo bits wake the slab
+    if (rc != CX_OK) return rc;
+    rounds += r;
+    // boundary planes to the z-neighbours: my top plane goes up, my bottom plane goes down
+    rc = coll->halo_exchange_u32(ctx, A.F + wplane * (k1 - 1), s->halo, A.F + wplane * k0, s->halo + wplane, wplane);
+    if (rc != CX_OK) return rc;
+    CX_CUDA(ctx, cudaMemsetAsync(fresh, 0, sizeof(int), st));
+    if (rank + 1 < world) {
+      k_merge_plane<<<cx_blocks(wplane, 256, ctx->num_sms * 8), 256, 0, st>>>(A, s->halo, (int)k1, fresh);
+      CX_LAUNCH_CHECK(ctx, "k_merge_plane");
+    }
+    if (rank > 0) {
+      k_merge_plane<<<cx_blocks(wplane, 256, ctx->num_sms * 8), 256, 0, st>>>(A, s->halo + wplane, (int)k0 - 1, fresh);
+      CX_LAUNCH_CHECK(ctx, "k_merge_plane");
+    }
+    k_dist_flags<<<1, 1, 0, st>>>(A.count, fresh, A.changed, flags);
+    CX_LAUNCH_CHECK(ctx, "k_dist_flags");
+    rc = coll->allreduce_sum_i64(ctx, (int64_t *)flags, 2);
+    if (rc != CX_OK) return rc;
+    CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 36, flags, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_mail[36] == 0) break;
+    if (it > 1000000) return cx_fail(ctx, CX_INTERNAL_ERROR, "fill: exchange limit");
+  }
+  if (nfi_host) *nfi_host = ctx->h_mail[37];
+  if (rounds_host) *rounds_host = rounds;
+  // ---- every rank gets every slab, then packs the whole lattice into the reference's bit order
+  segs.clear();
+  for (int r = 0; r < world; r++) {
+    int64_t a, b;
+    cx_split_range(dimg[2], world, r, &a, &b);
+    segs.push_back({wplane * a, wplane * (b - a), r});
+  }
+  rc = coll->bcast_segments_u32(ctx, A.F, segs.data(), (int)segs.size());
+  if (rc != CX_OK) return rc;
+  A.k_lo = 0; A.k_hi = A.dimg[2];
+  k_pack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);
+  CX_LAUNCH_CHECK(ctx, "k_pack");
+  return CX_OK;
+}

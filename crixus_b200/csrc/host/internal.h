@@ -9,4 +9,8 @@ void *cx_internal_dev_arena(cx_ctx *ctx, size_t bytes);
 void *cx_internal_host_arena(cx_ctx *ctx, size_t bytes);
 // dst[i] = (src[3i], src[3i+1], src[3i+2], 0) on the device, i < n
 int cx_internal_expand3(cx_ctx *ctx, const float *src3_d, float *dst4_d, int64_t n);
+// dst[i] = (src[i].x + offset, src[i].y + offset, src[i].z + offset, 0) on the device, i < n (segments appended behind a mesh)
+int cx_internal_offset_ep4(cx_ctx *ctx, const int32_t *src_ep4_d, int32_t *dst_ep4_d, int64_t n, int32_t offset);
+// in-place all-gather over the context's communicator: rank r owns bytes [r*bytes, (r+1)*bytes) of buf_d
+int cx_internal_allgather(cx_ctx *ctx, void *buf_d, int64_t bytes);
 }

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include "internal.h"
@@ -28,6 +29,10 @@ struct CopyStream {   // second stream + event for the overlapped download; rele
   cudaStream_t s = nullptr;
   cudaEvent_t e = nullptr;
   ~CopyStream() { if (s) cudaStreamDestroy(s); if (e) cudaEventDestroy(e); }
+};
+struct Events {
+  cudaEvent_t e[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  ~Events() { for (int k = 0; k < 8; k++) if (e[k]) cudaEventDestroy(e[k]); }
 };
 struct DevTmp {       // stream-ordered temporary, released on every exit path
   void *p = nullptr;
@@ -56,7 +61,7 @@ extern "C" void cx_job_free(cx_job *job)
 
 extern "C" int64_t cx_job_sizeof(void) { return (int64_t)sizeof(cx_job); }
 
-// bounding box + weld of a small auxiliary grid (special-boundary STL) on the device; host weld when a cell is over-full
+// bounding box + weld of an auxiliary grid (special-boundary or free-surface STL) on the device
 static int weld_grid(cx_ctx *ctx, cudaStream_t st, const float *corners, int64_t n, float dr, float **pos4_d, int32_t **ep4_d,
                      int64_t *nvert)
 {
@@ -68,27 +73,16 @@ static int weld_grid(cx_ctx *ctx, cudaStream_t st, const float *corners, int64_t
   CU(cudaMemcpyAsync(c_d, corners, 36 * (size_t)n, cudaMemcpyHostToDevice, st));
   float lo[3], hi[3];
   RC(cx_bbox_device(ctx, c_d, 3 * n, lo, hi));
-  int rc = cx_weld_device(ctx, c_d, 3 * n, dr, lo, hi, (float *)pos.p, (int32_t *)ep.p, nvert);
-  if (rc == CX_WELD_CELL_TOO_FULL) {
-    std::vector<float> verts((size_t)9 * n), hp;
-    std::vector<int32_t> ids((size_t)3 * n), he((size_t)4 * n, 0);
-    *nvert = cx_weld_host(corners, 3 * n, dr, verts.data(), ids.data());
-    hp.assign((size_t)4 * *nvert, 0.f);
-    for (int64_t v = 0; v < *nvert; v++) for (int k = 0; k < 3; k++) hp[4 * v + k] = verts[3 * v + k];
-    for (int64_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) he[4 * i + k] = ids[3 * i + k];
-    CU(cudaMemcpy(pos.p, hp.data(), 16 * (size_t)*nvert, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ep.p, he.data(), 16 * (size_t)n, cudaMemcpyHostToDevice));
-    rc = CX_OK;
-  }
-  RC(rc);
+  RC(cx_weld_device(ctx, c_d, 3 * n, dr, lo, hi, (float *)pos.p, (int32_t *)ep.p, nvert));
   *pos4_d = (float *)pos.release();   // handed to the caller, who frees them after the tagging kernel
   *ep4_d = (int32_t *)ep.release();
   return CX_OK;
 }
 
-extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
+static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
 {
   if (!ctx || !job || !job->normals || job->nbe <= 0 || !(job->dr > 0)) return CX_WRONG_INPUT;
+  const int world = dist ? cx_dist_world(ctx) : 1, rank = dist ? cx_dist_rank(ctx) : 0;
   if (!job->corners && !(job->welded_pos && job->welded_ep && job->welded_nvert > 0)) return CX_WRONG_INPUT;
   const int64_t nbe = job->nbe;
   const float dr = job->dr;
@@ -103,26 +97,19 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     for (int k = 0; k < 3; k++) { bbmin[k] = job->bbmin[k]; bbmax[k] = job->bbmax[k]; }
   } else {
     // raw corners -> device; bounding box (crixus.cu:185-208) and vertex weld (crixus.cu:214) run there
-    CU(cudaMallocAsync((void **)&w_corners, 36 * (size_t)nbe, st));
+    // with N ranks every rank uploads 1/N of the triangles and the pieces are all-gathered over NVLink (equal pieces of `per`
+    // triangles; the tail of the last piece is padding)
+    const int64_t per = (nbe + world - 1) / world;
+    const int64_t t_lo = std::min(nbe, per * rank), t_hi = std::min(nbe, per * (rank + 1));
+    CU(cudaMallocAsync((void **)&w_corners, 36 * (size_t)(per * world), st));
     CU(cudaMallocAsync((void **)&w_pos4, 48 * (size_t)nbe, st));
     CU(cudaMallocAsync((void **)&w_ep4, 16 * (size_t)nbe, st));
-    CU(cudaMemcpyAsync(w_corners, job->corners, 36 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+    if (t_hi > t_lo)
+      CU(cudaMemcpyAsync(w_corners + 9 * t_lo, job->corners + 9 * t_lo, 36 * (size_t)(t_hi - t_lo), cudaMemcpyHostToDevice, st));
+    if (world > 1) RC(cx_internal_allgather(ctx, w_corners, 36 * per));
     RC(cx_bbox_device(ctx, w_corners, 3 * nbe, bbmin, bbmax));
     RC(cx_check_triangle_size(ctx, w_corners, nbe, dr, &job->tri_failed, &job->tri_mind, &job->tri_maxd));
-    int wrc = cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert);
-    if (wrc == CX_WELD_CELL_TOO_FULL) {
-      // degenerate input (dr far larger than the mesh spacing): the host restatement of the weld, same outcome
-      std::vector<float> verts((size_t)9 * nbe), hp;
-      std::vector<int32_t> ids((size_t)3 * nbe), he((size_t)4 * nbe);
-      nvert = cx_weld_host(job->corners, 3 * nbe, dr, verts.data(), ids.data());
-      hp.resize((size_t)4 * nvert);
-      for (int64_t v = 0; v < nvert; v++) { hp[4 * v] = verts[3 * v]; hp[4 * v + 1] = verts[3 * v + 1]; hp[4 * v + 2] = verts[3 * v + 2]; hp[4 * v + 3] = 0.f; }
-      for (int64_t i = 0; i < nbe; i++) { for (int k = 0; k < 3; k++) he[4 * i + k] = ids[3 * i + k]; he[4 * i + 3] = 0; }
-      CU(cudaMemcpy(w_pos4, hp.data(), 16 * (size_t)nvert, cudaMemcpyHostToDevice));
-      CU(cudaMemcpy(w_ep4, he.data(), 16 * (size_t)nbe, cudaMemcpyHostToDevice));
-      wrc = CX_OK;
-    }
-    RC(wrc);
+    RC(cx_weld_device(ctx, w_corners, 3 * nbe, dr, bbmin, bbmax, w_pos4, w_ep4, &nvert));
     CU(cudaFreeAsync(w_corners, st));
   }
   job->nvert = nvert;
@@ -152,7 +139,8 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   pre_surf.off = db.take(4 * (size_t)nbe); surf.off = db.take(4 * (size_t)nbe);
   cell_idx.off = db.take(4 * (size_t)(ncell + 1)); trisize.off = db.take(4 * (size_t)nvert);
   vol.off = db.take(4 * (size_t)nvert); newlink.off = db.take(4 * (size_t)nvert);
-  norm3.off = db.take(12 * (size_t)nbe); fpos.off = db.take(4 * (size_t)nwords);
+  const int64_t per_n = (nbe + world - 1) / world;   // normals: uploaded in N pieces like the corners
+  norm3.off = db.take(12 * (size_t)(per_n * world)); fpos.off = db.take(4 * (size_t)nwords);
   if (fsn) {
     fnorm.off = db.take(16 * (size_t)(nbe + fsn)); fep.off = db.take(16 * (size_t)(nbe + fsn));
     fposv.off = db.take(16 * (size_t)(nvert + 3 * fsn));
@@ -165,7 +153,7 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     b->p = dbase + b->off;
   const size_t o_pos = hb.take(16 * (size_t)(nvert + nbe)), o_norm = hb.take(16 * (size_t)nbe), o_ep = hb.take(16 * (size_t)nbe),
                o_surf = hb.take(4 * (size_t)nbe), o_vol = hb.take(4 * (size_t)nvert), o_cell = hb.take(4 * (size_t)(ncell + 1)),
-               o_fpos = hb.take(4 * (size_t)nwords), o_fs = hb.take(fsn ? 16 * (size_t)(5 * fsn) : 0),
+               o_fpos = hb.take(4 * (size_t)nwords),
                o_sbid = hb.take(nsb ? 4 * (size_t)(nvert + nbe) : 0);
   char *hbase = (char *)cx_internal_host_arena(ctx, hb.off + 256);
   if (!hbase) return CX_CUDA_ERROR;
@@ -178,7 +166,12 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     CU(cudaFreeAsync(w_pos4, st));
     CU(cudaFreeAsync(w_ep4, st));
   }
-  CU(cudaMemcpyAsync(norm3.p, job->normals, 12 * (size_t)nbe, cudaMemcpyHostToDevice, st));
+  {
+    const int64_t n_lo = std::min(nbe, per_n * rank), n_hi = std::min(nbe, per_n * (rank + 1));
+    if (n_hi > n_lo)
+      CU(cudaMemcpyAsync(norm3.as<float>() + 3 * n_lo, job->normals + 3 * n_lo, 12 * (size_t)(n_hi - n_lo), cudaMemcpyHostToDevice, st));
+    if (world > 1) RC(cx_internal_allgather(ctx, norm3.p, 12 * per_n));
+  }
   RC(cx_internal_expand3(ctx, norm3.as<float>(), pre_norm.as<float>(), nbe));
   CU(cudaMemsetAsync(trisize.p, 0, 4 * (size_t)nvert, st));
   CU(cudaMemsetAsync(vol.p, 0, 4 * (size_t)nvert, st));
@@ -187,7 +180,8 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   job->t_h2d_s = now_s() - t0;
 
   t0 = now_s();
-  cudaEvent_t ev[8];
+  Events evs;   // released on every exit path
+  cudaEvent_t *ev = evs.e;
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&ev[k]));
   CU(cudaEventRecord(ev[0], st));
   if (job->swap_normals) RC(cx_swap_normals(ctx, pre_norm.as<float>(), nbe));  // crixus.cu:310-317
@@ -214,15 +208,35 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   CU(cudaEventRecord(cs.e, st));
   CU(cudaStreamWaitEvent(cs.s, cs.e, 0));
   cudaStream_t cst = cs.s;
-  CU(cudaMemcpyAsync(job->pos, pos.p, 16 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
-  CU(cudaMemcpyAsync(job->norm, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
-  CU(cudaMemcpyAsync(job->ep, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
-  CU(cudaMemcpyAsync(job->surf, surf.p, 4 * (size_t)nbe, cudaMemcpyDeviceToHost, cst));
-  CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, cst));
+  // which part of the results this rank brings to the host: everything (single GPU, or rank 0 of a gathered run), nothing
+  // (other ranks of a gathered run), or its 1/N share (out_sharded)
+  const bool sharded = world > 1 && job->out_sharded;
+  const bool all_here = world == 1 || (!sharded && rank == 0);
+  auto share = [&](int64_t n, int64_t *lo, int64_t *hi) {
+    if (sharded) { const int64_t per = (n + world - 1) / world; *lo = std::min(n, per * rank); *hi = std::min(n, per * (rank + 1)); }
+    else { *lo = 0; *hi = all_here ? n : 0; }
+  };
+  share(nbe, &job->seg_lo, &job->seg_hi);
+  share(nvert, &job->vert_lo, &job->vert_hi);
+  share(nwords, &job->fword_lo, &job->fword_hi);
+  const int64_t s_lo = job->seg_lo, s_n = job->seg_hi - job->seg_lo, v_lo = job->vert_lo, v_n = job->vert_hi - job->vert_lo;
+  if (v_n > 0) CU(cudaMemcpyAsync(job->pos + 4 * v_lo, pos.as<float>() + 4 * v_lo, 16 * (size_t)v_n, cudaMemcpyDeviceToHost, cst));
+  if (s_n > 0) {
+    CU(cudaMemcpyAsync(job->pos + 4 * (nvert + s_lo), pos.as<float>() + 4 * (nvert + s_lo), 16 * (size_t)s_n, cudaMemcpyDeviceToHost, cst));
+    CU(cudaMemcpyAsync(job->norm + 4 * s_lo, norm.as<float>() + 4 * s_lo, 16 * (size_t)s_n, cudaMemcpyDeviceToHost, cst));
+    CU(cudaMemcpyAsync(job->ep + 4 * s_lo, ep.as<int32_t>() + 4 * s_lo, 16 * (size_t)s_n, cudaMemcpyDeviceToHost, cst));
+    CU(cudaMemcpyAsync(job->surf + s_lo, surf.as<float>() + s_lo, 4 * (size_t)s_n, cudaMemcpyDeviceToHost, cst));
+  }
+  if (all_here || (sharded && rank == 0))
+    CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, cst));
   RC(cx_calc_trisize(ctx, ep.as<int32_t>(), trisize.as<int32_t>(), nbe));
   CU(cudaEventRecord(ev[4], st));
-  RC(cx_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
-                         cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
+  if (world > 1)
+    RC(cx_dist_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
+                                cell_idx.as<int32_t>(), nvert, nbe, job->zero_open));
+  else
+    RC(cx_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
+                           cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
 
   CU(cudaEventRecord(ev[5], st));
   cx_params_fill_eps(&p);   // crixus.cu:463-467
@@ -244,7 +258,8 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     job->sbid = (int32_t *)(hbase + o_sbid);
     CU(cudaEventRecord(cs.e, st));
     CU(cudaStreamWaitEvent(cst, cs.e, 0));
-    CU(cudaMemcpyAsync(job->sbid, sbid.p, 4 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
+    if (all_here || (sharded && rank == 0))
+      CU(cudaMemcpyAsync(job->sbid, sbid.p, 4 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
   }
   CU(cudaEventRecord(ev[6], st));
   // ---- fluid (crixus.cu:698-961)
@@ -259,22 +274,22 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
     if (fs.option == 2) {
       if (!have_fs && fsn > 0) {  // crixus.cu:809-930
         have_fs = true;
-        std::vector<float> fv((size_t)9 * fsn);
-        std::vector<int32_t> fid((size_t)3 * fsn);
-        const int64_t fsnvert = cx_weld_host(job->fs_corners, 3 * fsn, dr, fv.data(), fid.data());
-        float *hp = (float *)(hbase + o_fs), *hn = hp + 4 * (3 * fsn);
-        int32_t *he = (int32_t *)(hn + 4 * fsn);
-        for (int64_t v = 0; v < fsnvert; v++) { hp[4 * v] = fv[3 * v]; hp[4 * v + 1] = fv[3 * v + 1]; hp[4 * v + 2] = fv[3 * v + 2]; hp[4 * v + 3] = 0.f; }
-        for (int64_t i = 0; i < fsn; i++) {
-          for (int k = 0; k < 3; k++) { hn[4 * i + k] = job->fs_normals[3 * i + k]; he[4 * i + k] = fid[3 * i + k] + (int32_t)nvert; }
-          hn[4 * i + 3] = 0.f; he[4 * i + 3] = 0;
-        }
+        // the free-surface STL is welded like the main mesh (crixus.cu:861-905) -- on the device -- and appended behind the
+        // wall geometry: vertices behind the nvert wall vertices, segments behind the nbe wall segments
+        float *fsp = nullptr;
+        int32_t *fse = nullptr;
+        int64_t fsnvert = 0;
+        RC(weld_grid(ctx, st, job->fs_corners, fsn, dr, &fsp, &fse, &fsnvert));
+        DevTmp gfp, gfe, gfn;
+        gfp.p = fsp; gfp.st = st; gfe.p = fse; gfe.st = st;
+        CU(gfn.alloc(12 * (size_t)fsn, st));
+        CU(cudaMemcpyAsync(gfn.p, job->fs_normals, 12 * (size_t)fsn, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(fnorm.p, norm.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(fep.p, ep.p, 16 * (size_t)nbe, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(fposv.p, pos.p, 16 * (size_t)nvert, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(fnorm.as<float>() + 4 * nbe, hn, 16 * (size_t)fsn, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fep.as<int32_t>() + 4 * nbe, he, 16 * (size_t)fsn, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(fposv.as<float>() + 4 * nvert, hp, 16 * (size_t)fsnvert, cudaMemcpyHostToDevice, st));
+        RC(cx_internal_expand3(ctx, (const float *)gfn.p, fnorm.as<float>() + 4 * nbe, fsn));
+        CU(cudaMemcpyAsync(fposv.as<float>() + 4 * nvert, fsp, 16 * (size_t)fsnvert, cudaMemcpyDeviceToDevice, st));
+        RC(cx_internal_offset_ep4(ctx, fse, fep.as<int32_t>() + 4 * nbe, fsn, (int32_t)nvert));
         g_norm = fnorm.as<float>(); g_ep = fep.as<int32_t>(); g_pos = fposv.as<float>();
         fnbe = nbe + fsn; cnbe = fsn;
       }
@@ -283,7 +298,10 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
       if (seed < 0) return CX_SEED_OUTSIDE;
       int64_t nfi = 0;
       int32_t rounds = 0;
-      RC(cx_fill_geometry(ctx, &p, fpos.as<uint32_t>(), g_norm, g_ep, g_pos, fnbe, cnbe, cell_idx.as<int32_t>(), seed, &nfi, &rounds));
+      if (world > 1)
+        RC(cx_dist_fill_geometry(ctx, &p, fpos.as<uint32_t>(), g_norm, g_ep, g_pos, fnbe, cnbe, cell_idx.as<int32_t>(), seed, &nfi, &rounds));
+      else
+        RC(cx_fill_geometry(ctx, &p, fpos.as<uint32_t>(), g_norm, g_ep, g_pos, fnbe, cnbe, cell_idx.as<int32_t>(), seed, &nfi, &rounds));
       job->nfluid_counted += nfi;
     } else {
       const float *lo = fs.lo, *hi = fs.hi;  // crixus.cu:759-773
@@ -301,7 +319,6 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   for (int k = 0; k < 5; k++) { CU(cudaEventElapsedTime(&job->stage_ms[k], ev[k], ev[k + 1])); }
   CU(cudaEventElapsedTime(&job->stage_ms[5], ev[6], ev[7]));
   CU(cudaEventElapsedTime(&job->stage_ms[6], ev[5], ev[6]));
-  for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
   job->params_fill = p;
   job->d_pos = pos.as<float>(); job->d_norm = norm.as<float>(); job->d_ep = ep.as<int32_t>(); job->d_surf = surf.as<float>();
   job->d_vol = vol.as<float>(); job->d_fpos = fpos.as<uint32_t>(); job->d_sbid = nsb ? sbid.as<int32_t>() : nullptr;
@@ -310,13 +327,19 @@ extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job)
   t0 = now_s();
   job->vol = (float *)(hbase + o_vol);
   job->fpos = (uint32_t *)(hbase + o_fpos);
-  CU(cudaMemcpyAsync(job->vol, vol.p, 4 * (size_t)nvert, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(job->fpos, fpos.p, 4 * (size_t)nwords, cudaMemcpyDeviceToHost, st));
+  if (v_n > 0) CU(cudaMemcpyAsync(job->vol + v_lo, vol.as<float>() + v_lo, 4 * (size_t)v_n, cudaMemcpyDeviceToHost, st));
+  if (job->fword_hi > job->fword_lo)
+    CU(cudaMemcpyAsync(job->fpos + job->fword_lo, fpos.as<uint32_t>() + job->fword_lo, 4 * (size_t)(job->fword_hi - job->fword_lo),
+                       cudaMemcpyDeviceToHost, st));
+  uint64_t hp[2];
+  RC(cx_hash_u32(ctx, fpos.p, nwords, hp));   // popcount on the device (every rank holds the complete bitfield); synchronises st
+  job->nfluid = (int64_t)hp[1];
   CU(cudaStreamSynchronize(cst));
-  RC(cx_synchronize(ctx));
-  int64_t pop = 0;
-  for (int64_t w = 0; w < nwords; w++) pop += __builtin_popcount(job->fpos[w]);
-  job->nfluid = pop;
   job->t_d2h_s = now_s() - t0;
   return CX_OK;
 }
+
+extern "C" int cx_preprocess_host(cx_ctx *ctx, cx_job *job) { return preprocess_impl(ctx, job, false); }
+
+// every rank of the context's communicator calls this with the same job (include/crixus_b200.h)
+extern "C" int cx_preprocess_dist(cx_ctx *ctx, cx_job *job) { return preprocess_impl(ctx, job, true); }

@@ -230,7 +230,7 @@ static int radix_sort_pairs(cx_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ weld
-#define CX_WELD_MAX_RUN 20000
+#define CX_WELD_BIG_RUN 256   // corners per dr-cell above which the claim loop of a cell is run by a whole block
 
 struct WeldGrid {
   int32_t cmin[3];
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) k_weld_starts(const uint64_t *__restrict_
     if (i == 0 || keys[i] != keys[i - 1]) start[headscan[i]] = (int32_t)i;
 }
 
-// longest run (corners per cell): the claim loop is quadratic in it
+// longest run (corners per cell): runs above CX_WELD_BIG_RUN are claimed by a whole block (k_weld_cells_big)
 __global__ void __launch_bounds__(256) k_weld_maxrun(const int32_t *__restrict__ start, int64_t nruns, int64_t n, int32_t *__restrict__ mx)
 {
   int m = 0;
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(128) k_weld_cells(const float *__restrict__ c,
 {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nruns; r += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = start[r], e = (r + 1 < nruns) ? (int64_t)start[r + 1] : n;
+    if (e - s > CX_WELD_BIG_RUN) continue;   // k_weld_cells_big
     for (int64_t i = s; i < e; i++) { rep[i] = -1; isrep[i] = 0; }
     for (int64_t i = s; i < e; i++) {
       if (rep[i] >= 0) continue;   // found
@@ -295,6 +296,35 @@ __global__ void __launch_bounds__(128) k_weld_cells(const float *__restrict__ c,
         if ((double)dist < thr) rep[k] = (int32_t)i;
       }
     }
+  }
+}
+
+// the same claim loop for over-full cells (dr far larger than the mesh spacing: thousands of corners in one dr-cell), one BLOCK
+// per cell: the outer loop over unclaimed corners stays sequential (the claim order is the outcome), the inner loop over the
+// later corners of the cell is spread over the threads.  Same result as the one-thread loop for every run length.
+__global__ void __launch_bounds__(256) k_weld_cells_big(const float *__restrict__ c, const uint32_t *__restrict__ vals,
+                                                        const int32_t *__restrict__ start, int64_t nruns, int64_t n, double thr,
+                                                        volatile int32_t *rep, int32_t *__restrict__ isrep)
+{
+  for (int64_t r = blockIdx.x; r < nruns; r += gridDim.x) {
+    const int64_t s = start[r], e = (r + 1 < nruns) ? (int64_t)start[r + 1] : n;
+    if (e - s <= CX_WELD_BIG_RUN) continue;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) { rep[i] = -1; isrep[i] = 0; }
+    __syncthreads();
+    for (int64_t i = s; i < e; i++) {
+      if (rep[i] >= 0) continue;   // block-uniform: every write to rep[] is followed by a barrier before the next read
+      if (threadIdx.x == 0) { rep[i] = (int32_t)i; isrep[i] = 1; }
+      const float *pi = c + 3 * (int64_t)vals[i];
+      const float xi = pi[0], yi = pi[1], zi = pi[2];
+      for (int64_t k = i + 1 + threadIdx.x; k < e; k += blockDim.x) {
+        const float *pk = c + 3 * (int64_t)vals[k];
+        const float xij = __fsub_rn(pk[0], xi), yij = __fsub_rn(pk[1], yi), zij = __fsub_rn(pk[2], zi);
+        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(xij, xij), __fmul_rn(yij, yij)), __fmul_rn(zij, zij));   // crixus.cpp:320-323
+        if ((double)dist < thr) rep[k] = (int32_t)i;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
   }
 }
 
@@ -367,19 +397,23 @@ extern "C" int cx_weld_device(cx_ctx *ctx, const float *corners_d, int64_t ncorn
   CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 44, head + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CX_CUDA(ctx, cudaStreamSynchronize(st));
   const int64_t nruns = *(int32_t *)(ctx->h_mail + 44);
-  {  // a cell with tens of thousands of corners (dr far larger than the mesh spacing) would make one thread loop for minutes
+  int32_t maxrun = 0;
+  {
     int32_t *mx = (int32_t *)(ctx->d_mail + 45);
     CX_CUDA(ctx, cudaMemsetAsync(mx, 0, sizeof(int32_t), st));
     k_weld_maxrun<<<cx_blocks(nruns, 256, ctx->num_sms * 8), 256, 0, st>>>(start, nruns, n, mx);
     CX_LAUNCH_CHECK(ctx, "k_weld_maxrun");
     CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 45, mx, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CX_CUDA(ctx, cudaStreamSynchronize(st));
-    if (*(int32_t *)(ctx->h_mail + 45) > CX_WELD_MAX_RUN)
-      return cx_fail(ctx, CX_WELD_CELL_TOO_FULL, "weld: more than 20000 corners in one dr-cell (dr far larger than the mesh spacing?)");
+    maxrun = *(int32_t *)(ctx->h_mail + 45);
   }
   const double thr = 1e-10 * dr * dr;                   // crixus.cpp:324 (double)
   k_weld_cells<<<cx_blocks(nruns, 128, ctx->num_sms * 32), 128, 0, st>>>(corners_d, vs, start, nruns, n, thr, rep, isrep);
   CX_LAUNCH_CHECK(ctx, "k_weld_cells");
+  if (maxrun > CX_WELD_BIG_RUN) {   // over-full cells: one block each (no host fallback)
+    k_weld_cells_big<<<cx_blocks(nruns, 1, ctx->num_sms * 8), 256, 0, st>>>(corners_d, vs, start, nruns, n, thr, rep, isrep);
+    CX_LAUNCH_CHECK(ctx, "k_weld_cells_big");
+  }
   CX_CUDA(ctx, cudaMemsetAsync(isrep + n, 0, sizeof(int32_t), st));
   int32_t *vid = head;                                  // reuse: exclusive scan of the representative flags = vertex ids
   rc = cx_exclusive_scan_i32(ctx, isrep, vid, n + 1);

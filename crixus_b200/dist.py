@@ -1,18 +1,19 @@
-"""Multi-GPU orchestration of the hot path above the C-ABI: one process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU harness above the C-ABI: one process per GPU.
 
-What shards and what does not (DESIGN.md "multi-GPU"):
-  * swap_normals / set_bound_elem / cell binning / calc_trisize are HBM-bound passes of ~100-150 B per segment; an
-    all-gather of their outputs over NVLink would move more bytes than recomputing them, so every rank runs them on
-    the full (replicated) mesh -- identical results on every rank because the binning order is stable.
-  * calc_vert_volume (FP32-ALU bound, >99 % of the time) shards by contiguous vertex-index ranges; the volumes
-    (4 B/vertex) are all-gathered.
-  * the geometry fill shards the dr lattice into z-slabs.  Each rank propagates inside its slab to local convergence
-    (cx_fill_geometry_slab), then the two boundary planes are exchanged with the z-neighbours (the packed words covering
-    the plane are OR-ed in) and the global count of new cells is all-reduced; repeat until no rank changed anything.
-    Bit-exactness across rank counts follows from the fixed-point property of the fill.
+The sharded algorithms live INSIDE the library (include/crixus_b200.h "multi-GPU": cx_dist_init, cx_dist_calc_vert_volume,
+cx_dist_fill_geometry, cx_preprocess_dist -- NCCL collectives on the context's stream, csrc/dist.cu + csrc/fill.cu); this module
+only ships the 128-byte NCCL id between the ranks (through torch.distributed, which the launcher already set up) and holds the
+device-resident workload for bench.py.  What shards and what does not (DESIGN.md "multi-GPU"):
+  * swap_normals / set_bound_elem / cell binning / calc_trisize / device weld are HBM-bound passes of ~100-150 B per segment; an
+    all-gather of their outputs over NVLink would move more bytes than recomputing them, so every rank runs them on the full
+    (replicated) mesh -- identical results on every rank because the binning order is stable.
+  * calc_vert_volume (FP32-ALU bound, ~90 % of the time): interleaved 1024-vertex chunks, volumes all-reduced (4 B/vertex).
+  * geometry fill: directed tests dealt by 3dr-cell chunk, blocked planes reduced to the z-slab owners, slab floods with halo
+    exchange, owned planes all-gathered.  Bit-exact across rank counts by the fixed-point property of the fill.
 
-The partition helpers are pure functions (tested on CPU with gloo, world_size 2, with the CPU oracle as the compute
-backend in tests/test_dist.py)."""
+The pure partition helpers below restate the library's sharding rules; they are tested on CPU with gloo (world_size 2 and 3,
+the CPU oracle as the compute backend, tests/test_dist.py) -- the same rules the C++ code follows (csrc/dist.h cx_split_range,
+csrc/fill.cu chunk_owner)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -38,20 +39,19 @@ FT_Y, FT_Z, DEAL_CHUNK = 16, 16, 64   # fill tiles (csrc/fill.cu FT_Y / FT_Z) an
 
 
 def dealt_chunk_owner(chunk, nparts):
-    """Rank that resolves 64-item chunk `chunk` of the up-front directed tests (csrc/fill.cu, k_resolve_tiles<ALL>): every
-    group of nparts consecutive chunks is dealt one chunk per rank, the order rotated by a multiplicative hash of the group
-    number.  (Plain round-robin correlates with the tile layout: a lattice plane is rows 0..15 of every tile, i.e. chunk 0 of
-    4, so a plane-aligned wall would land on nparts/4 of the ranks.)  Vectorised over numpy arrays."""
+    """Rank that resolves the directed tests of 3dr-cell chunk `chunk` (32 consecutive 3dr-cells; csrc/fill.cu chunk_owner):
+    every group of nparts consecutive chunks is dealt one chunk per rank, the order rotated by a multiplicative hash of the
+    group number.  (Plain round-robin is periodic in the cell grid: a wall is a plane of 3dr-cells, i.e. every gridn_z/32-th
+    chunk, and could land on few ranks.)  Vectorised over numpy arrays."""
     chunk = np.asarray(chunk, dtype=np.int64)
     g, slot = chunk // nparts, chunk % nparts
     rot = ((g.astype(np.uint64) & np.uint64(0xFFFFFFFF)) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)
     return ((slot - (rot % np.uint64(nparts)).astype(np.int64)) % nparts).astype(np.int64)
 
 
-def resolve_item_of_word(wx, j, k, wr, ty):
-    """work item of the up-front resolve that handles the 32-cell word (wx, row j, plane k): tile-major, 256 items per tile"""
-    tile = ((k // FT_Z) * ty + j // FT_Y) * wr + wx
-    return tile * (FT_Y * FT_Z) + (k % FT_Z) * FT_Y + j % FT_Y
+def cell3_chunk(gx, gy, gz, gridn):
+    """chunk of the up-front resolve that holds 3dr-cell (gx, gy, gz): cells are numbered gx*ny*nz + gy*nz + gz, 32 per chunk"""
+    return ((np.asarray(gx, dtype=np.int64) * gridn[1] + gy) * gridn[2] + gz) // 32
 
 
 def split_weighted(weights, world, rank):
@@ -161,7 +161,8 @@ class ShardedHotPath:
         dev = ctx.device
         nv, nbe = w["nvert"], w["nbe"]
         self.nv, self.nbe = nv, nbe
-        f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+        # the welded mesh: numpy arrays (small workloads built on the host) or tensors already on the device (large ones, welded there)
+        f = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
         self.pos0, self.norm0, self.ep0 = f(w["pos"]), f(w["norm"]), f(w["ep"])
         self.p = api.params_domain(w["dr"], w["bbmin"], w["bbmax"])
         self.ncell3 = int(self.p.gridn[3])
@@ -200,12 +201,14 @@ class ShardedHotPath:
             self.fnorm, self.fep = z4(nbe + self.cnbe), z4(nbe + self.cnbe, torch.int32)
         self.v0, self.v1 = 0, nv
         self.k0, self.k1 = split_range(int(self.dimg[2]), world, rank)
-        small = 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES
+        wr = (int(self.dimg[0]) + 31) // 32
+        small = 6 * 4 * wr * int(self.dimg[1]) * int(self.dimg[2]) <= SMALL_LATTICE_BYTES or int(self.dimg[2]) < 2 * world
         self.parallelism = "1 GPU" if world == 1 else (
-            "vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; fill: %s; cheap stages and device weld replicated"
-            % (VV_CHUNK, world, ("directed tests dealt to %d ranks in interleaved chunks, blocked planes all-reduced, flood replicated" % world) if small else
-               ("directed tests dealt to %d ranks in interleaved chunks, blocked planes all-reduced, flood in %d z-slabs with a halo "
-                "exchange every %d rounds" % (world, world, FILL_ROUNDS_PER_EXCHANGE))))
+            "one process per GPU, NCCL inside the C-ABI (cx_dist_*); vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; "
+            "fill: %s; cheap stages and device weld replicated"
+            % (VV_CHUNK, world, ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes all-reduced, flood replicated" % world) if small else
+               ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes reduced to the slab owners, flood in %d z-slabs with a "
+                "halo exchange over NCCL send/recv every %d rounds, owned planes all-gathered" % (world, world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
         # one untimed pass to learn trisize (vertex-range balancing) and the S27 statistic for the byte count
@@ -223,7 +226,7 @@ class ShardedHotPath:
         pad = np.pad(cnt, 1)
         s27 = sum(pad[1 + a:pad.shape[0] - 1 + a, 1 + b:pad.shape[1] - 1 + b, 1 + c:pad.shape[2] - 1 + c]
                   for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1))
-        vpos = w["pos"][own, :3]
+        vpos = (w["pos"].cpu().numpy() if torch.is_tensor(w["pos"]) else w["pos"])[own, :3]
         g = [np.clip(((vpos[:, j] - np.float32(self.p.dmin[j])) / np.float32(self.p.griddr[j])).astype(np.int64), 0, self.p.gridn[j] - 1)
              for j in range(3)]
         S27 = s27[g[0], g[1], g[2]].astype(np.float64)
@@ -265,14 +268,8 @@ class ShardedHotPath:
         mark()
         if self.world == 1:
             ctx.calc_vert_volume(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"], 0, nv)
-        else:
-            # interleaved chunks: the cost per vertex varies along the mesh (walls, corners, curved parts), contiguous
-            # ranges balance badly.  Every rank fills its own chunks of a zeroed array; SUM all-reduce = gather.
-            import torch.distributed as dist
-            self.vol.zero_()
-            ctx.calc_vert_volume_part(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"],
-                                      VV_CHUNK, self.world, self.rank)
-            dist.all_reduce(self.vol)
+        else:   # interleaved chunks + all-reduce inside the library (cx_dist_calc_vert_volume)
+            ctx.dist_calc_vert_volume(pv, self.pos, self.norm, self.ep, self.vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"])
         mark()
         self._fill()
         mark()
@@ -301,36 +298,9 @@ class ShardedHotPath:
             seed = api.seed_index(p, f[1])
             if self.world == 1:
                 nfl += ctx.fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
-                rounds += ctx.last_rounds
-            elif 6 * 4 * self.fpos.numel() <= SMALL_LATTICE_BYTES:
-                # small lattice: shard the directed tests by z-slab, merge the blocked planes, flood everywhere
-                import torch.distributed as dist
-                B = ctx.fill_resolve_part(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.world, self.rank)
-                dist.all_reduce(B)                       # rows are disjoint and zero elsewhere: SUM == OR
-                nfl += ctx.fill_propagate(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
-                rounds += ctx.last_rounds
-            else:
-                import torch.distributed as dist
-
-                # The directed tests (the expensive, geometry-only part) are dealt to the ranks in interleaved chunks -- z-slabs
-                # balance badly: the floor and lid slabs hold whole walls -- and the blocked planes + hard mask are merged by one
-                # all-reduce (disjoint words, zero elsewhere: SUM == OR); only the cheap flood is sharded by z-slab.
-                B = ctx.fill_resolve_part(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, self.world, self.rank)
-                dist.all_reduce(B)
-
-                def slab(fpos, seed_, k0, k1, first):
-                    n = ctx.fill_geometry_slab(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed_, k0, k1, 2 if first else 0)
-                    self._rounds += ctx.last_rounds
-                    return n, ctx.fill_unfinished()
-                self._rounds = 0
-                # exchange boundary planes every FILL_ROUNDS_PER_EXCHANGE rounds: the flood front crosses the slabs while
-                # it is moving, instead of one slab converging after the other
-                ctx.fill_set_max_rounds(FILL_ROUNDS_PER_EXCHANGE)
-                n, its = distributed_fill(slab, self.fpos, self.dimg, seed, self.rank, self.world, dist)
-                ctx.fill_set_max_rounds(0)
-                gather_slabs(self.fpos, self.dimg, self.rank, self.world, dist)
-                nfl += n
-                rounds += self._rounds
+            else:   # dealt directed tests, reduce to slab owners, slab floods + halo exchange, all-gather: cx_dist_fill_geometry
+                nfl += ctx.dist_fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
+            rounds += ctx.last_rounds
         self.nfluid, self.fill_rounds = int(nfl), int(rounds)
 
     def collect_stage_ms(self):
@@ -348,95 +318,116 @@ class ShardedHotPath:
         self._stage_rank_local = rank0
         return t.cpu().numpy()
 
+    # ---- bitwise evidence
+    def check(self):
+        """popcount + order-independent 64-bit checksums (cx_hash_u32, computed on the device) of the fluid bitfield, the
+        vertex-volume bits and the sorted geometry -- what a wrong bit anywhere would change"""
+        hf, pop = self.ctx.hash_u32(self.fpos)
+        hv, _ = self.ctx.hash_u32(self.vol)
+        hg = sum(self.ctx.hash_u32(t)[0] for t in (self.pos, self.norm, self.ep, self.surf, self.cell_idx)) & 0xFFFFFFFFFFFFFFFF
+        return {"nfluid_popcount": pop, "fpos_hash": "%016x" % hf, "vol_hash": "%016x" % hv, "geometry_hash": "%016x" % hg}
+
+    def single_gpu_check(self):
+        """the same inputs through the single-GPU calls (cx_calc_vert_volume, cx_fill_geometry) on this rank alone: the
+        checksums a sharded run has to reproduce"""
+        torch, ctx, w, nv, nbe = self.torch, self.ctx, self.w, self.nv, self.nbe
+        from . import api
+        pv = self.p.copy()
+        for idim in range(3):
+            pv.per[idim] = int(w["periodic"][idim])
+        vol = torch.zeros_like(self.vol)
+        ctx.calc_vert_volume(pv, self.pos, self.norm, self.ep, vol, self.trisize, self.cell_idx, nv, nbe, w["zero_open"], 0, nv)
+        fpos = torch.zeros_like(self.fpos)
+        gn, ge, gp, fnbe = (self.fnorm, self.fep, self.fposv, nbe + self.cnbe) if self.cnbe else (self.norm, self.ep, self.pos, nbe)
+        for f in w["fills"]:
+            if f[0] == "box":
+                ctx.fill_box(self.pf, fpos, f[1], f[2])
+                continue
+            p = self.pf.copy()
+            p.dr_wall = np.float32(f[2] if f[2] is not None else w["dr"])
+            ctx.fill_geometry(p, fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, api.seed_index(p, f[1]))
+        hf, pop = ctx.hash_u32(fpos)
+        hv, _ = ctx.hash_u32(vol)
+        return {"nfluid_popcount": pop, "fpos_hash": "%016x" % hf, "vol_hash": "%016x" % hv}
+
     # ---- end to end with host buffers
-    def e2e(self, steps, barrier):
-        import time
-        torch, w = self.torch, self.w
-        nv, nbe = self.nv, self.nbe
-        if self.world == 1:
-            from . import api
-            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
-            # the raw STL content in pinned host memory: 9 corner floats + 3 normal floats per triangle.  The vertex weld
-            # and the bounding box run on the device inside the call.
-            hcorn, hnorm3 = pin(w["tris"].reshape(-1)), pin(np.ascontiguousarray(w["normals"], dtype=np.float32))
-            job = api.CxJob()
-            job.normals = C.cast(hnorm3.data_ptr(), C.POINTER(C.c_float))
-            job.nbe = nbe
-            job.corners = C.cast(hcorn.data_ptr(), C.POINTER(C.c_float))
+    def make_job(self, hcorn, hnorm3, keep):
+        """cx_job over the raw STL content (corners + facet normals) in pinned host memory"""
+        from . import api
+        w, nbe = self.w, self.nbe
+        job = api.CxJob()
+        job.normals = C.cast(hnorm3.data_ptr(), C.POINTER(C.c_float))
+        job.nbe = nbe
+        job.corners = C.cast(hcorn.data_ptr(), C.POINTER(C.c_float))
+        for j in range(3):
+            job.periodic[j] = int(w["periodic"][j])
+        job.dr = float(w["dr"])
+        job.swap_normals, job.zero_open = int(w["swap_normals"]), int(w["zero_open"])
+        if w["container"] is not None:
+            job.use_container = 1
             for j in range(3):
-                job.periodic[j] = int(w["periodic"][j])
-            job.dr = float(w["dr"])
-            job.swap_normals, job.zero_open = int(w["swap_normals"]), int(w["zero_open"])
-            if w["container"] is not None:
-                job.use_container = 1
+                job.cmin[j], job.cmax[j] = w["container"][0][j], w["container"][1][j]
+        if w["fshape"] is not None:
+            fc = np.ascontiguousarray(w["fshape"][0], dtype=np.float32).reshape(-1)
+            fn = np.ascontiguousarray(w["fshape"][1], dtype=np.float32).reshape(-1)
+            keep += [fc, fn]
+            job.fs_corners = fc.ctypes.data_as(C.POINTER(C.c_float))
+            job.fs_normals = fn.ctypes.data_as(C.POINTER(C.c_float))
+            job.fs_nbe = w["fshape"][0].shape[0]
+        specs = (api.CxFillSpec * len(w["fills"]))()
+        for i, f in enumerate(w["fills"]):
+            if f[0] == "box":
+                specs[i].option = 1
                 for j in range(3):
-                    job.cmin[j], job.cmax[j] = w["container"][0][j], w["container"][1][j]
-            keep = []
-            if w["fshape"] is not None:
-                fc = np.ascontiguousarray(w["fshape"][0], dtype=np.float32).reshape(-1)
-                fn = np.ascontiguousarray(w["fshape"][1], dtype=np.float32).reshape(-1)
-                keep += [fc, fn]
-                job.fs_corners = fc.ctypes.data_as(C.POINTER(C.c_float))
-                job.fs_normals = fn.ctypes.data_as(C.POINTER(C.c_float))
-                job.fs_nbe = w["fshape"][0].shape[0]
-            specs = (api.CxFillSpec * len(w["fills"]))()
-            for i, f in enumerate(w["fills"]):
-                if f[0] == "box":
-                    specs[i].option = 1
-                    for j in range(3):
-                        specs[i].lo[j], specs[i].hi[j] = f[1][j], f[2][j]
-                else:
-                    specs[i].option = 2
-                    for j in range(3):
-                        specs[i].seed[j] = f[1][j]
-                    specs[i].dr_wall = float(f[2]) if f[2] is not None else 0.0
-            job.fills, job.nfills = specs, len(w["fills"])
-            self.ctx.preprocess_host(job)           # warm-up
-            self.ctx.L.cx_job_free(C.byref(job))
-            barrier()
-            t0 = time.perf_counter()
-            br = {"weld_s": 0.0, "h2d_s": 0.0, "gpu_s": 0.0, "d2h_s": 0.0}
-            for _ in range(steps):
-                self.ctx.preprocess_host(job)
-                br["weld_s"] += job.t_weld_s; br["h2d_s"] += job.t_h2d_s; br["gpu_s"] += job.t_gpu_s; br["d2h_s"] += job.t_d2h_s
-                assert int(job.nvert) == nv
-                nfl = int(job.nfluid)
-                self.ctx.L.cx_job_free(C.byref(job))
-            barrier()
-            dt = time.perf_counter() - t0
-            G = int(np.prod(self.dimg))
-            h2d = 36 * nbe + 12 * nbe + (w["fshape"][0].shape[0] * 48 if w["fshape"] is not None else 0)
-            d2h = 16 * (nv + nbe) + 16 * nbe * 2 + 4 * nbe + 4 * nv + 4 * (self.ncell3 + 1) + 4 * ((G + 31) // 32)
-            return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * dt / steps, "api": "cx_preprocess_host (raw STL corners + normals in pinned host memory; weld on the device)",
-                    "breakdown_ms": {k: 1e3 * v / steps for k, v in br.items()}, "nfluid": nfl}
-        # N > 1: the sharded driver with the input upload and the result download inside the timed region.  Every rank
-        # uploads the raw STL content and welds it on its own device (replicated, like the other cheap stages).
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
-        hcorn, hnorm = pin(w["tris"].reshape(-1, 3)), pin(w["norm"])
-        dcorn = torch.empty_like(hcorn, device=self.ctx.device)
-        out = [torch.empty_like(t, device="cpu").pin_memory() for t in (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)]
+                    specs[i].lo[j], specs[i].hi[j] = f[1][j], f[2][j]
+            else:
+                specs[i].option = 2
+                for j in range(3):
+                    specs[i].seed[j] = f[1][j]
+                specs[i].dr_wall = float(f[2]) if f[2] is not None else 0.0
+        job.fills, job.nfills = specs, len(w["fills"])
+        keep.append(specs)
+        return job
+
+    def e2e(self, steps, barrier, hcorn, hnorm3):
+        """The whole pass through the reference-facing C-ABI call on HOST buffers: cx_preprocess_host (one GPU) or
+        cx_preprocess_dist (every rank uploads 1/N of the raw STL content, NCCL all-gather, sharded stages, every rank
+        downloads its 1/N share of the results).  hcorn / hnorm3: pinned host tensors with the raw corners / facet normals."""
+        import time
+        torch, nv, nbe = self.torch, self.nv, self.nbe
+        keep = []
+        job = self.make_job(hcorn, hnorm3, keep)
+        job.out_sharded = 1
+        call = self.ctx.preprocess_host if self.world == 1 else self.ctx.preprocess_dist
+        call(job)                                   # warm-up: grows the arenas
+        self.ctx.L.cx_job_free(C.byref(job))
         barrier()
         t0 = time.perf_counter()
+        br = {"weld_s": 0.0, "h2d_s": 0.0, "gpu_s": 0.0, "d2h_s": 0.0}
+        nfl = 0
         for _ in range(steps):
-            dcorn.copy_(hcorn, non_blocking=True)
-            self.norm0.copy_(hnorm, non_blocking=True)
-            pos4, ep4, _lo, _hi = self.ctx.weld_device(dcorn, w["dr"])
-            assert pos4.shape[0] == nv
-            self.pos0.copy_(pos4)
-            self.ep0.copy_(ep4)
-            self.step()
-            if self.rank == 0:      # every rank holds the complete result; the host needs it once
-                for o, t in zip(out, (self.pos, self.norm, self.ep, self.surf, self.vol, self.fpos)):
-                    o.copy_(t, non_blocking=True)
-            torch.cuda.synchronize()
+            call(job)
+            br["weld_s"] += job.t_weld_s; br["h2d_s"] += job.t_h2d_s; br["gpu_s"] += job.t_gpu_s; br["d2h_s"] += job.t_d2h_s
+            assert int(job.nvert) == nv, (int(job.nvert), nv)
+            nfl = int(job.nfluid)
+            d2h_local = 16 * (job.vert_hi - job.vert_lo) + (16 * 3 + 4) * (job.seg_hi - job.seg_lo) + 4 * (job.vert_hi - job.vert_lo) + \
+                4 * (job.fword_hi - job.fword_lo) + (4 * (self.ncell3 + 1) if self.rank == 0 else 0)
+            self.ctx.L.cx_job_free(C.byref(job))
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=self.ctx.device)
-        import torch.distributed as dist
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        h2d = sum(t.numel() * t.element_size() for t in (hcorn, hnorm))
-        d2h = sum(t.numel() * t.element_size() for t in out)
-        return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dt / steps, "api": "stage-level C-ABI on every rank (upload + device weld replicated, sharded hot path), results downloaded by rank 0, pinned host buffers"}
+        fs_bytes = self.w["fshape"][0].shape[0] * 48 if self.w["fshape"] is not None else 0
+        per = (nbe + self.world - 1) // self.world
+        h2d_local = 48 * max(0, min(nbe, per * (self.rank + 1)) - min(nbe, per * self.rank)) + fs_bytes
+        tt = torch.tensor([dt, float(h2d_local), float(d2h_local)], dtype=torch.float64, device=self.ctx.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            dt = float(tmax[0].item())
+        h2d, d2h = int(tt[1].item()), int(tt[2].item())
+        api_name = ("cx_preprocess_host (raw STL corners + normals in pinned host memory; bounding box + weld on the device)" if self.world == 1 else
+                    "cx_preprocess_dist on every rank (each uploads 1/N of the raw STL content, NCCL all-gather, device weld replicated, "
+                    "calc_vert_volume and the fill sharded, each rank downloads its 1/N share of every result array)")
+        return {"value": nbe * steps / dt, "unit": "triangles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * dt / steps, "api": api_name, "breakdown_ms_rank0": {k: 1e3 * v / steps for k, v in br.items()}, "nfluid": nfl}

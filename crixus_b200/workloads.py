@@ -84,3 +84,79 @@ def sphere_tank(side_cells=200, dr=0.005, sphere_levels=6):
              fills=[("geometry", (4 * dr, 4 * dr, 4 * dr), np.float32(dr))])
     w["name"] = "config4 family: sphere in tank, %d^3 cells" % side_cells
     return _finish(w)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs
+# bench.py --config N (1-based, N = index into BASELINE.json `configs` + 1).  Small workloads are welded on the host
+# (_finish); the large ones are only GENERATED here (raw STL content) and welded on the device by the harness.
+def _options(dr, fills, periodic=(False, False, False), container=None, fshape=None, swap_normals=True, zero_open=False):
+    return dict(dr=np.float32(dr), swap_normals=swap_normals, periodic=periodic, zero_open=zero_open, container=container, fshape=fshape,
+                fills=fills)
+
+
+def bench_config(n, size=None):
+    """-> (name, options dict, generator of (corners (nbe,3,3) float32, normals (nbe,3) float32)).  `size` overrides the
+    BASELINE size of the family (tests use smaller members)."""
+    if n == 1:
+        w = config1()
+        return w["name"], w, (lambda: (w["tris"], np.ascontiguousarray(w["normals"], dtype=np.float32)))
+    if n == 2:
+        lv = 3 if size is None else int(size)
+        w = spheric2_family(SPHERIC2_DR / 2 ** (lv - 1), 1.25, levels=lv, base_dr=SPHERIC2_DR)
+        name = "configs[1]: spheric2 subdivided x%d, dr=%.6g, fshape geometry fill" % (4 ** lv, float(w["dr"]))
+        opts = _options(w["dr"], w["fills"], container=w["container"], fshape=w["fshape"])
+        return name, opts, (lambda: (np.ascontiguousarray(w["tris"], dtype=np.float32), np.ascontiguousarray(w["normals"], dtype=np.float32)))
+    if n == 3:
+        nq = 1581 if size is None else int(size)
+        dr = 0.01
+        L, H = nq * 1.25 * dr, max(6, nq // 4) * 1.25 * dr
+
+        def gen():
+            v, t, nn = mg.channel(n=nq, dr=dr)
+            return np.ascontiguousarray(v[t], dtype=np.float32), np.ascontiguousarray(nn, dtype=np.float32)
+        return ("configs[2]: x/y-periodic channel, %d x %d quads per wall, dr=%g" % (nq, nq, dr),
+                _options(dr, [("geometry", (L / 2, L / 2, H / 2), np.float32(dr))], periodic=(True, True, False)), gen)
+    if n == 4:
+        side = 1000 if size is None else int(size)
+        dr = 1.0 / side
+
+        def gen():
+            v, t, nn = mg.sphere_in_tank(side_cells=side, dr=dr, hfac=0.5, sphere_levels=7 if side >= 400 else (5 if side >= 100 else 2))
+            return np.ascontiguousarray(v[t], dtype=np.float32), np.ascontiguousarray(nn, dtype=np.float32)
+        return ("configs[3]: sphere in tank, %d^3-cell lattice, h=dr/2" % (side + 1),
+                _options(dr, [("geometry", (4 * dr, 4 * dr, 4 * dr), np.float32(dr))]), gen)
+    if n == 5:
+        side = 2154 if size is None else int(size)
+        dr = 1.0 / side
+
+        def gen():
+            v, t, nn = mg.box_tank((0, 0, 0), (1, 1, 1), 0.53 * dr, inward=False)
+            return np.ascontiguousarray(v[t], dtype=np.float32), np.ascontiguousarray(nn, dtype=np.float32)
+        return ("configs[4]: subdivided tank, %d^3-cell lattice, h=0.53dr" % (side + 1),
+                _options(dr, [("geometry", (0.5, 0.5, 0.5), np.float32(dr))]), gen)
+    raise ValueError("config must be 1..5")
+
+
+def bench_config_name(n):
+    return {1: "configs[0]: resources/spheric2.ini", 2: "configs[1]: spheric2 subdivided x64 at dr/4, fshape geometry fill",
+            3: "configs[2]: x/y-periodic channel, ~1e7 triangles", 4: "configs[3]: sphere in tank, 4.8e7 triangles, 1001^3-cell lattice",
+            5: "configs[4]: subdivided tank, 2e8 triangles, 1e10-cell lattice"}[n]
+
+
+def cpu_sample(n, steps_total=25):
+    """The bounded sample of config n that BOTH CPU arms of bench.py time (the cpu_baseline leg of the GPU arm and
+    `--impl reference`): the same geometry family, options and mesh refinement relative to dr at a coarser dr, sized so that one
+    pass costs seconds on the host cores.  -> (name, options, corners, normals)"""
+    small = steps_total > 30
+    if n in (1, 2):
+        dr = 0.06 if small else 0.045
+        w = spheric2_family(dr, 0.625)
+        if n == 1:
+            w["fills"] = [("box", (0.2, 0.2, 0.2), (0.4, 0.4, 0.4))] + w["fills"]
+        name = "spheric2 tank + fshape fill at dr=%g, h=0.625dr" % dr
+        opts = _options(w["dr"], w["fills"], container=w["container"], fshape=w["fshape"])
+        return name, opts, np.ascontiguousarray(w["tris"], dtype=np.float32), np.ascontiguousarray(w["normals"], dtype=np.float32)
+    size = {3: 64 if small else 96, 4: 16 if small else 24, 5: 20 if small else 28}[n]
+    name, opts, gen = bench_config(n, size)
+    c, nn = gen()
+    return name, opts, c, nn

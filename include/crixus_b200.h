@@ -38,7 +38,8 @@ enum {
   CX_FAN_INCOMPLETE = -103,  /* a vertex' triangles were not all found in its 27 cells (mesh precondition violated) */
   CX_SEED_OUTSIDE = -104,    /* geometry-fill seed outside the fluid lattice (reference: out-of-bounds write) */
   CX_NO_DEVICE = -105,
-  CX_WELD_CELL_TOO_FULL = -106 /* cx_weld_device: > 20000 corners in one dr-cell; cx_preprocess_host falls back to cx_weld_host */
+  CX_WELD_CELL_TOO_FULL = -106, /* (no longer returned: the device weld handles cells of any size) */
+  CX_NO_NCCL = -107            /* a multi-GPU communicator was requested but libnccl.so.2 cannot be loaded */
 };
 
 /* the __constant__ symbols of src/crixus_d.cu:13-32 */
@@ -138,20 +139,57 @@ int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds);
 int cx_fill_unfinished(cx_ctx *ctx);
 
 /* Multi-GPU: the directed tests (pure functions of the geometry) are resolved for planes [k_begin, k_end) only;
- * *blocked_d points to the 6 "blocked" bit planes followed by the hard mask (*blocked_words uint32 = 7 planes, zero
- * outside this rank's share) which the caller merges across ranks (words are disjoint: SUM == OR).  Then either
+ * *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32, zero outside this rank's share) which the caller
+ * merges across ranks (every lattice cell is resolved by exactly one rank -- disjoint bits: SUM == OR).  Then either
  * cx_fill_propagate runs the flood on the whole lattice on every rank (small lattices: no halo exchange, no per-sweep
  * collective) or cx_fill_geometry_slab(first_call = 2) floods by z-slab (large lattices). */
 int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
                          int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words);
-/* same, but the lattice words are dealt to the ranks in interleaved chunks (balanced; z-slabs are not) */
+/* same, but the 3dr-cells (and with them their lattice cells) are dealt to the ranks in interleaved chunks of 32 (balanced;
+ * z-slabs are not: the floor slab holds a whole wall) */
 int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
                          uint32_t **blocked_d, int64_t *blocked_words);
 int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                       const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
                       int64_t *nfi_host, int32_t *rounds_host);
+
+/* ---- multi-GPU: one process (or host thread) per GPU.  The reference is single-GPU (src/crixus.cu:80-119 selects one device);
+ * this is where a device list enters.  A context joins a communicator once; the cx_dist_* stage calls and cx_preprocess_dist then
+ * run sharded over its ranks, all collectives on the context's stream:
+ *   calc_vert_volume  interleaved chunks of CX_DIST_VV_CHUNK vertices per rank + one all-reduce of the volumes
+ *   geometry fill     directed tests dealt to the ranks by 3dr-cell chunk, blocked planes reduced to the z-slab owners, slab
+ *                     floods with boundary planes exchanged between z-neighbours every CX_DIST_FILL_ROUNDS rounds (NCCL
+ *                     send/recv), termination by an all-reduce of two counters, owned planes all-gathered at the end
+ *   cheap stages      (set_bound_elem, binning, links, trisize, device weld) replicated: recomputing them costs less HBM
+ *                     traffic than gathering their outputs would cost NVLink traffic
+ * Results are bit-identical for every rank count (the fill is a least fixed point; the volumes are per-vertex). */
+#define CX_NCCL_ID_BYTES 128
+#define CX_DIST_VV_CHUNK 1024
+#define CX_DIST_FILL_ROUNDS 8
+#define CX_DIST_SMALL_BYTES (64u << 20) /* six blocked planes below this size: all-reduce them and flood replicated */
+int cx_dist_unique_id(void *id128);                                            /* ncclGetUniqueId; rank 0 calls it, the application ships the bytes */
+int cx_dist_init(cx_ctx *ctx, const void *id128, int world, int rank);         /* ncclCommInitRank on the context's device */
+int cx_dist_attach(cx_ctx *ctx, void *nccl_comm, int world, int rank);         /* use a ncclComm_t the caller owns */
+int cx_dist_init_local(cx_ctx *const *ctxs, int n);  /* n contexts of ONE process form a group (one host thread per context must
+                                                        then call the cx_dist_* functions concurrently); no NCCL involved */
+int cx_dist_finalize(cx_ctx *ctx);
+int cx_dist_world(cx_ctx *ctx);
+int cx_dist_rank(cx_ctx *ctx);
+/* same arguments as cx_calc_vert_volume / cx_fill_geometry, the (replicated) inputs resident on every rank; every rank ends with
+ * all volumes / the complete bitfield.  *nfi_host = newly set cells over all ranks. */
+int cx_dist_calc_vert_volume(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
+                             float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
+                             int zero_open);
+int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
+                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t seed,
+                          int64_t *nfi_host, int32_t *rounds_host);
+/* which form cx_dist_fill_geometry takes: 0 = by lattice size (CX_DIST_SMALL_BYTES), 1 = replicated flood, 2 = z-slab flood */
+int cx_dist_set_fill_mode(cx_ctx *ctx, int mode);
+/* order-independent checksum of n 32-bit words in device memory: out[0] = sum_i mix(i, word_i) mod 2^64, out[1] = popcount.
+ * Used to compare results between rank counts and against the single-GPU pass without moving them. */
+int cx_hash_u32(cx_ctx *ctx, const void *words_d, int64_t n, uint64_t out_host[2]);
 
 /* identifySpecialBoundarySegments, crixus_d.cu:1085-1112 (+ segInTri :1060-1083): segments whose barycentre lies in a
  * triangle of the special-boundary grid (sbpos float4[sbnvert], sbep int4[sbnbe], welded like the main mesh,
@@ -203,9 +241,19 @@ typedef struct cx_job {
   int64_t tri_failed; float tri_mind, tri_maxd; /* mesh precondition (cx_check_triangle_size), filled when raw corners are given */
   double t_weld_s, t_gpu_s, t_h2d_s, t_d2h_s; /* wall-clock breakdown */
   float stage_ms[8]; /* CUDA-event times: 0 swap+set_bound_elem, 1 binning, 2 periodic links, 3 trisize, 4 vert volume, 5 fills, 6 special-boundary tagging */
+  /* cx_preprocess_dist: in: out_sharded; out: the ranges this rank downloaded (whole arrays on rank 0 when out_sharded = 0) */
+  int32_t out_sharded;
+  int64_t seg_lo, seg_hi, vert_lo, vert_hi, fword_lo, fword_hi;
 } cx_job;
 
 int cx_preprocess_host(cx_ctx *ctx, cx_job *job);
+/* the same on every rank of the context's communicator (every rank passes the same job, i.e. can read the same input files):
+ * each rank uploads 1/N of the raw corners and normals and the pieces are all-gathered over NVLink; calc_vert_volume and the
+ * geometry fills run sharded (cx_dist_*).  job->out_sharded = 0: rank 0 downloads every result array (the other ranks none);
+ * 1: every rank downloads its share -- segments [seg_lo, seg_hi) of pos(barycentres)/norm/ep/surf, vertices [vert_lo, vert_hi) of
+ * pos/vol, bitfield words [fword_lo, fword_hi) -- into its own (full-size) host arrays, for a consumer that writes the particle
+ * file in parallel.  nvert / nfluid / dimg are valid on every rank. */
+int cx_preprocess_dist(cx_ctx *ctx, cx_job *job);
 void cx_job_free(cx_job *job);
 int64_t cx_job_sizeof(void); /* sizeof(cx_job) of the library, for bindings to check their mirror of the struct */
 

@@ -113,14 +113,12 @@ def test_partition_helpers():
 
 @pytest.mark.parametrize("nparts", [2, 3, 4, 8])
 def test_dealing_of_the_directed_tests_is_a_balanced_partition(nparts):
-    """The multi-GPU fill merges the blocked planes of the ranks with one SUM all-reduce, which equals OR only if every
-    lattice word is resolved by exactly one rank; and the walls of a tank -- whole lattice planes / rows / columns -- must
-    not all land on a few ranks (measured: plain round-robin gave 50 ms on four ranks and 28 ms on the others, the hashed
-    rotation 40.3 ms on all eight).  cd.dealt_chunk_owner mirrors the kernel's formula (csrc/fill.cu k_resolve_tiles)."""
-    dimg = (301, 301, 301)
-    wr, ty, tz = (dimg[0] + 31) // 32, (dimg[1] + 15) // 16, (dimg[2] + 15) // 16
-    nitems = wr * ty * tz * 256
-    nchunks = nitems // 64
+    """The multi-GPU fill merges the blocked planes of the ranks with SUM reductions, which equal OR only if every lattice cell
+    is resolved by exactly one rank; and the walls of a tank -- whole planes of the 3dr-cell grid -- must not all land on a few
+    ranks.  cd.dealt_chunk_owner mirrors the kernel's formula (csrc/fill.cu chunk_owner: chunks of 32 consecutive 3dr-cells)."""
+    gridn = (100, 100, 100)
+    ncell = gridn[0] * gridn[1] * gridn[2]
+    nchunks = (ncell + 31) // 32
     owner = cd.dealt_chunk_owner(np.arange(nchunks), nparts)
     # partition: within every complete group of nparts chunks each rank appears exactly once
     full = (nchunks // nparts) * nparts
@@ -132,23 +130,15 @@ def test_dealing_of_the_directed_tests_is_a_balanced_partition(nparts):
     for part in range(nparts):
         mine = g * nparts + (part + (rot % np.uint64(nparts)).astype(np.int64)) % nparts
         assert (owner[mine] == part).all()
-    # balance on the six walls of the tank (the hard cells): floor / lid planes, front / back rows, left / right words
-    J, K = np.meshgrid(np.arange(dimg[1]), np.arange(dimg[2]), indexing="ij")
+    # balance on the six walls of the tank (two layers of 3dr-cells each hold the lattice cells whose tests are expensive)
+    A, B = np.meshgrid(np.arange(gridn[0]), np.arange(gridn[1]), indexing="ij")
     walls = []
-    for k in (0, 1, dimg[2] - 2, dimg[2] - 1):
-        WX, JJ = np.meshgrid(np.arange(wr), np.arange(dimg[1]), indexing="ij")
-        walls.append(cd.resolve_item_of_word(WX.ravel(), JJ.ravel(), np.full(WX.size, k), wr, ty))
-    for j in (0, 1, dimg[1] - 2, dimg[1] - 1):
-        WX, KK = np.meshgrid(np.arange(wr), np.arange(dimg[2]), indexing="ij")
-        walls.append(cd.resolve_item_of_word(WX.ravel(), np.full(WX.size, j), KK.ravel(), wr, ty))
-    for wx in (0, wr - 1):
-        walls.append(cd.resolve_item_of_word(np.full(J.size, wx), J.ravel(), K.ravel(), wr, ty))
-    items = np.concatenate(walls)
-    load = np.bincount(cd.dealt_chunk_owner(items // 64, nparts), minlength=nparts)
+    for layer in (0, 1, gridn[2] - 2, gridn[2] - 1):
+        walls.append(cd.cell3_chunk(A.ravel(), B.ravel(), np.full(A.size, layer), gridn))
+        walls.append(cd.cell3_chunk(A.ravel(), np.full(A.size, layer), B.ravel(), gridn))
+        walls.append(cd.cell3_chunk(np.full(A.size, layer), A.ravel(), B.ravel(), gridn))
+    load = np.bincount(cd.dealt_chunk_owner(np.concatenate(walls), nparts), minlength=nparts)
     assert load.max() <= 1.15 * load.mean(), load
-    floor = walls[0]                                                     # one lattice plane: rows 0..15 of every tile = chunk 0 of 4
-    load = np.bincount(cd.dealt_chunk_owner(floor // 64, nparts), minlength=nparts)
-    assert load.max() <= 1.25 * load.mean(), load
-    naive = np.bincount((floor // 64) % nparts, minlength=nparts)       # what plain round-robin would have done
-    if nparts in (4, 8):
-        assert (naive == 0).sum() >= nparts // 2, naive                  # ... the plane lands on at most half of the ranks
+    for one in walls[:3]:                                                 # every single wall layer by itself
+        load = np.bincount(cd.dealt_chunk_owner(one, nparts), minlength=nparts)
+        assert load.max() <= 1.3 * load.mean(), load

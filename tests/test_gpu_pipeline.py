@@ -291,16 +291,18 @@ def test_device_weld_equals_host_weld(name, cuda_backend):
     assert not ep4[:, 3].any() and not pos4[:, 3].any()
 
 
-def test_device_weld_refuses_overfull_cells(cuda_backend):
-    """dr far larger than the mesh spacing puts every corner into one cell; the per-cell claim loop is quadratic, so the
-    device weld refuses (CX_WELD_CELL_TOO_FULL) and cx_preprocess_host takes the host weld instead."""
+def test_device_weld_overfull_cells(cuda_backend):
+    """dr far larger than the mesh spacing puts every corner into one dr-cell (> 20 000 corners): the claim loop of such a cell
+    is run by a whole block (k_weld_cells_big) -- no host fallback -- with the host weld's outcome."""
     import torch
     v, t, n = mg.plate(60, 0.01)
     corners = np.ascontiguousarray(v[t], dtype=np.float32).reshape(-1, 3)
     assert corners.shape[0] > 20000
-    with pytest.raises(api.CxError) as e:
-        cuda_backend.ctx.weld_device(torch.from_numpy(corners).to(cuda_backend.ctx.device), np.float32(5.0))
-    assert e.value.code == -106
+    hv, hid = api.weld_host(corners, np.float32(5.0))
+    pos4, ep4, lo, hi = cuda_backend.ctx.weld_device(torch.from_numpy(corners).to(cuda_backend.ctx.device), np.float32(5.0))
+    assert pos4.shape[0] == hv.shape[0] == v.shape[0]
+    np.testing.assert_array_equal(pos4.cpu().numpy()[:, :3], hv)
+    np.testing.assert_array_equal(ep4.cpu().numpy()[:, :3], hid)
 
 
 def test_cli_equals_reference_binary_on_config1(tmp_path):

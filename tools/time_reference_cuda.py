@@ -72,38 +72,49 @@ def compare_outputs(d, c, ini):
             "reference_count_shift": int(shift)}
 
 
+def compare_level(d, level, parity=True, timing=True, limit=300):
+    """one SPHERIC-2 level in directory d: both programs on the same .ini + STL files -> dict (wall clocks, parity)"""
+    lv = level
+    c = case_for(lv)
+    c["name"] = "m"
+    stl, fsp, ini = os.path.join(d, "m.stl"), os.path.join(d, "m_fs.stl"), os.path.join(d, "m.ini")
+    mg.write_stl(stl, c["tris"], c["normals"])
+    mg.write_stl(fsp, c["fshape"][0], c["fshape"][1])
+    write_ini(ini, c, stl, fsp)
+    row = {"level": lv, "triangles": int(c["tris"].shape[0]), "dr": float(c["dr"])}
+    ok = True
+    for name, exe in (("ours", os.path.join(ROOT, "crixus_b200", "bin", "crixus")), ("reference_cuda", os.path.join(ROOT, "oracle", "_ref", "Crixus_ref"))):
+        if not os.path.exists(exe):
+            row[name] = "missing"
+            ok = False
+            continue
+        if not timing:
+            continue
+        run([exe, ini], d, limit) if name == "ours" else None      # warm-up of our side only (driver/context start-up is in both)
+        t, rc, tail = run([exe, ini], d, limit)
+        row[name + "_wall_s"] = t
+        row[name + "_rc"] = rc
+        ok = ok and rc == 0
+        for line in tail.splitlines():
+            if "Timing:" in line or "fluid particles completed" in line:
+                row.setdefault(name + "_log", []).append(line.strip())
+    # ---- full-size parity: our .vtu against the reference's, particle by particle
+    if parity and ok:
+        try:
+            row["parity"] = compare_outputs(d, c, ini)
+        except AssertionError as e:
+            row["parity"] = "MISMATCH: " + str(e)[:300]
+    return row
+
+
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "ref_timing.json")
     levels = [int(x) for x in sys.argv[2:]] or [0, 1, 2]
     limit = int(os.environ.get("CX_REF_TIMEOUT", "300"))
     res = []
     for lv in levels:
-        c = case_for(lv)
-        c["name"] = "m"
         with tempfile.TemporaryDirectory() as d:
-            stl, fsp, ini = os.path.join(d, "m.stl"), os.path.join(d, "m_fs.stl"), os.path.join(d, "m.ini")
-            mg.write_stl(stl, c["tris"], c["normals"])
-            mg.write_stl(fsp, c["fshape"][0], c["fshape"][1])
-            write_ini(ini, c, stl, fsp)
-            row = {"level": lv, "triangles": int(c["tris"].shape[0]), "dr": float(c["dr"])}
-            for name, exe in (("ours", os.path.join(ROOT, "crixus_b200", "bin", "crixus")), ("reference_cuda", os.path.join(ROOT, "oracle", "_ref", "Crixus_ref"))):
-                if not os.path.exists(exe):
-                    row[name] = "missing"
-                    continue
-                run([exe, ini], d, limit) if name == "ours" else None      # warm-up of our side only (driver/context start-up is in both)
-                t, rc, tail = run([exe, ini], d, limit)
-                row[name + "_wall_s"] = t
-                row[name + "_rc"] = rc
-                for line in tail.splitlines():
-                    if "Timing:" in line or "fluid particles completed" in line:
-                        row.setdefault(name + "_log", []).append(line.strip())
-            # ---- full-size parity: our .vtu against the reference's, particle by particle
-            ours_vtu, ref_vtu = os.path.join(d, c["name"] + ".vtu"), None
-            if row.get("reference_cuda_rc") == 0 and row.get("ours_rc") == 0:
-                try:
-                    row["parity"] = compare_outputs(d, c, ini)
-                except AssertionError as e:
-                    row["parity"] = "MISMATCH: " + str(e)[:300]
+            row = compare_level(d, lv, limit=limit)
             res.append(row)
             print(json.dumps(row), flush=True)
     json.dump(res, open(out, "w"), indent=1)
