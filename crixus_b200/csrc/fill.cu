@@ -423,6 +423,13 @@ __device__ __forceinline__ int chunk_owner(long long chunk, int nparts)
 
 // one lattice cell against the staged records: exact pre-filters, then the reference's arithmetic (pair_full) for the few
 // pairs that survive them.  (si, sj, sk) = the lane's cell, dm = its in-lattice directions, coll = directions already blocked.
+//
+// With a = -n.(s - v0) and b = n.dir exactly as checkTriangleCollision computes them (crixus_d.cu:757-765), a direction along
+// axis x can only collide if |b| < eps and |a| < eps (ray in the plane), or r = a / b lies in [-eps, 1 + eps], which needs
+// |a| <= |n_x| |dir| (1 + eps) up to rounding.  L[x] = max |dir| (1 + eps) 1.0002 per axis is a property of the cell, so the
+// test for BOTH directions of an axis is one multiply and one compare per record; the (rare) survivors get the sign test and
+// a bounding-sphere test of the hit point before the reference's arithmetic runs.  Only for well-formed triangles (R0.w != 0:
+// finite, unit normal perpendicular to the edges); everything else takes the reference's arithmetic unfiltered.
 __device__ __forceinline__ uint32_t cell_vs_staged(const FillArgs &A, const float4 *sR0, const float4 *sR1, const int *sIdx, int cnt,
                                                    int si, int sj, int sk, uint32_t dm, uint32_t coll)
 {
@@ -433,42 +440,49 @@ __device__ __forceinline__ uint32_t cell_vs_staged(const FillArgs &A, const floa
   const float dxm = fsub(lat_pos(p, 0, si - 1), s.x), dxp = fsub(lat_pos(p, 0, si + 1), s.x);
   const float dym = fsub(lat_pos(p, 1, sj - 1), s.y), dyp = fsub(lat_pos(p, 1, sj + 1), s.y);
   const float dzm = fsub(lat_pos(p, 2, sk - 1), s.z), dzp = fsub(lat_pos(p, 2, sk + 1), s.z);
+  const float grow = 1.0002f * (1.0f + eps);
+  const float Lx = fmaxf(fabsf(dxm), fabsf(dxp)) * grow, Ly = fmaxf(fabsf(dym), fabsf(dyp)) * grow, Lz = fmaxf(fabsf(dzm), fabsf(dzp)) * grow;
+  const float lim_alive = 1.44f * A.drw2;
   for (int q = 0; q < cnt; q++) {
-    uint32_t need = dm & ~coll;
+    const uint32_t need = dm & ~coll;
     if (!need) break;
     const float4 R0 = sR0[q], R1 = sR1[q];
     const f3 n = mk3(R0), v0 = mk3(R1);
-    const float wx = s.x - v0.x, wy = s.y - v0.y, wz = s.z - v0.z;
-    const float t = wx * n.x + wy * n.y + wz * n.z;
-    if (R0.w != 0.f && fabsf(t) > A.rrej) continue;   // plane-distance reject: neither test can hold
-    uint32_t cand = need;
+    const f3 w0 = sub3(s, v0);
+    const float a = -dot3_r3(n, w0);
+    const float aa = fabsf(a);
+    const bool wf = R0.w != 0.f;
+    if (wf && aa > A.rrej) continue;   // plane-distance reject: neither test can hold
     // the distance test is alive unless eps >= dr_wall^2 or (well-formed triangle) the plane distance alone exceeds dr_wall:
-    // every distance the reference computes is >= |t| / 1.2
-    const bool dist_alive = !A.dist_dead && !(R0.w != 0.f && t * t >= 1.44f * A.drw2);
-    if (!dist_alive && !A.nofilter) {
-      // segment test only.  a, b exactly as checkTriangleCollision computes them; r = a / b must lie in [-eps, 1 + eps]
-      const float a = -dot3_r3(n, sub3(s, v0));
+    // every distance the reference computes is >= |a| / 1.2
+    uint32_t cand = need;
+    if (wf && (A.dist_dead || a * a >= lim_alive) && !A.nofilter) {
+      uint32_t m = 0;
+      if (aa <= fabsf(n.x) * Lx || aa < eps) m |= 3u;
+      if (aa <= fabsf(n.y) * Ly || aa < eps) m |= 12u;
+      if (aa <= fabsf(n.z) * Lz || aa < eps) m |= 48u;
+      m &= need;
+      if (!m) continue;
       cand = 0;
-#pragma unroll
-      for (int d = 0; d < 6; d++) {
-        if (!(need >> d & 1)) continue;
+      while (m) {
+        const int d = __ffs(m) - 1;
+        m &= m - 1;
         const int ax = d >> 1;
         const float dc = d == 0 ? dxm : d == 1 ? dxp : d == 2 ? dym : d == 3 ? dyp : d == 4 ? dzm : dzp;
         const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
         const float b = dot3_r3(n, dir);
         const float ab = fabsf(b);
         if (ab < eps) {
-          if (fabsf(a) < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
+          if (aa < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
           continue;
         }
-        if (!(ab <= 3.0e38f)) { cand |= 1u << d; continue; }        // inf / NaN: no shortcut
         const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
         if (qn > ab * 1.0001f * (1.0f + eps) || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
         if (R0.w == 2.f) {
           // hit point P = s + r dir; an accepted (t1, t2) puts it within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned
           // triangles only).  r from a fast division: the 1 % margin of sph2 covers its error many times over.
           const float r = __fdividef(qn, ab);
-          const float px = ax == 0 ? wx + r * dc : wx, py = ax == 1 ? wy + r * dc : wy, pz = ax == 2 ? wz + r * dc : wz;
+          const float px = ax == 0 ? w0.x + r * dc : w0.x, py = ax == 1 ? w0.y + r * dc : w0.y, pz = ax == 2 ? w0.z + r * dc : w0.z;
           if (px * px + py * py + pz * pz > A.sph2 * __int_as_float(sIdx[RB_CAP + q])) continue;
         }
         cand |= 1u << d;

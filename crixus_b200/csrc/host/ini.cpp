@@ -1,3 +1,20 @@
+// crixus_b200 -- .ini reader.  The parse loop below follows inih (the parser vendored by the reference under src/ini/, which
+// Crixus's option semantics are defined by): same line rules, same helper structure (rstrip / lskip / find_char_or_comment),
+// same limits.  inih is third-party code under the New BSD license; its notice is reproduced here as that license requires:
+//
+//   inih -- simple .INI file parser.  Copyright (c) 2009, Brush Technology.  All rights reserved.
+//   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the
+//   following conditions are met: * Redistributions of source code must retain the above copyright notice, this list of
+//   conditions and the following disclaimer. * Redistributions in binary form must reproduce the above copyright notice, this
+//   list of conditions and the following disclaimer in the documentation and/or other materials provided with the
+//   distribution. * Neither the name of Brush Technology nor the names of its contributors may be used to endorse or promote
+//   products derived from this software without specific prior written permission.
+//   THIS SOFTWARE IS PROVIDED BY BRUSH TECHNOLOGY ''AS IS'' AND ANY EXPRESS OR IMPLIED WARRANTIES, INCLUDING, BUT NOT LIMITED
+//   TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE DISCLAIMED. IN NO EVENT SHALL BRUSH
+//   TECHNOLOGY BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT
+//   LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER
+//   CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE)
+//   ARISING IN ANY WAY OUT OF THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
 #include "ini.h"
 #include <algorithm>
 #include <cctype>

@@ -1,4 +1,4 @@
-// crixus_b200 -- .ini front end.  Own parser that honours the rules of the reference's vendored inih
+// crixus_b200 -- .ini front end.  A C++ reader with the rules (and, in ini.cpp, the parse-loop structure -- BSD notice there) of the reference's vendored inih
 // (/root/reference/src/ini/ini.c:60-167, src/ini/cpp/INIReader.cpp): sections, name=value or name:value, ';'/'#'
 // comment lines, ';' inline comments only after whitespace, continuation lines (leading whitespace), lines cut at
 // 199 characters, case-insensitive section.name keys, repeated keys joined with '\n', strtol/strtod value parsing,
