@@ -127,6 +127,14 @@ def case(name):
         n = mg.geometric_normals(v, t)
         sb = special_stress(v[t], 7, n=240)
         c.update(dr=0.08, special=[sb[:120], sb[120:]], **_PLATE_FILL)
+    elif name == "tank_mm":        # a mesh in MILLIMETRES: eps = 1e-5 x extent = 0.2 is absolute, but enters the segment-triangle
+        dr = 500.0                 # test as a relative tolerance (r <= 1 + eps; t1, t2 >= -eps in barycentric units): the free
+        v, t, n = mg.box_tank((0, 0, 0), (20000, 15000, 10000), dr, inward=True)   # surface blocks cells up to eps |u| = 7 dr
+        fs_t = np.array([[[0, 0, 5000], [9750, 0, 5000], [9750, 15000, 5000]],      # beyond its edge; it spans half the tank
+                         [[0, 0, 5000], [9750, 15000, 5000], [0, 15000, 5000]],
+                         [[12000, 2000, 2000], [16000, 2000, 2600], [14000, 9000, 2300]]], dtype=np.float32)   # + a slanted one
+        fs_n = mg.geometric_normals(fs_t.reshape(-1, 3), np.arange(9, dtype=np.int32).reshape(3, 3))
+        c.update(dr=dr, fills=[("geometry", (2250.0, 2250.0, 2250.0), dr)], fshape=(fs_t, fs_n))
     else:
         raise KeyError(name)
     c.update(name=name, tris=np.ascontiguousarray(v[t], dtype=np.float32), normals=np.ascontiguousarray(n, dtype=np.float32),
@@ -135,6 +143,10 @@ def case(name):
 
 
 ALL = ["plate", "plate_jitter", "plate_zero_open", "fan20", "cube", "cube_jitter", "cube_h05", "cube_tiny", "spheric2_mini", "channel", "channel_yz", "cube_fs_bad", "sphere_tank", "cube_sb", "sphere_sb", "plate_sb_stress"]
+
+
+# cases without a golden fixture of the reference CUDA binary (pinned against the reference's host build instead)
+EXTRA = ["tank_mm"]
 
 
 def run(B, c, stages=("volume", "fill")):

@@ -50,7 +50,7 @@ def _cmp_pipeline(o, g, c):
         np.testing.assert_array_equal(g["fpos"], o["fpos"])
 
 
-@pytest.mark.parametrize("name", cases.ALL)
+@pytest.mark.parametrize("name", cases.ALL + cases.EXTRA)
 def test_case_vs_oracle(name, oracle, cuda_backend):
     c = cases.case(name)
     o = cases.run(oracle, c)

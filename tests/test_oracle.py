@@ -46,7 +46,7 @@ def test_oracle_vs_reference_cuda_golden(name, oracle):
     assert nbad == 0
 
 
-@pytest.mark.parametrize("name", ["plate_jitter", "cube_jitter", "spheric2_mini", "channel", "sphere_tank", "cube_sb", "sphere_sb"])
+@pytest.mark.parametrize("name", ["plate_jitter", "cube_jitter", "spheric2_mini", "channel", "sphere_tank", "cube_sb", "sphere_sb", "tank_mm"])
 def test_oracle_vs_reference_host_shim(name, oracle, refshim):
     """Stage by stage against the reference's own src/crixus_d.cu compiled for the host (g++ contraction)."""
     c = cases.case(name)
