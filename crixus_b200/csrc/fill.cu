@@ -121,6 +121,8 @@ struct FillArgs {
   unsigned long long *count64;  // work counter of the up-front resolve
   unsigned long long *changed;  // newly set cells
   int res_nparts, res_part;     // up-front resolve: 3dr-cell chunks dealt to nparts ranks, this rank resolves its share (0/1: all)
+  const int32_t *blist;         // work list of the up-front resolve (3dr-cells of this rank's share), nblist entries
+  long long nblist;
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
   int64_t w_lo, w_hi;           // word range k_unpack / k_pack walk (slab calls: the owned planes, +-1 halo plane for k_unpack)
@@ -419,211 +421,283 @@ __device__ __forceinline__ int chunk_owner(long long chunk, int nparts)
 }
 
 #define RB_WARPS 8
-#define RB_CAP 96   // staged records per warp (phase 1 appends up to 32 per step and flushes above RB_CAP - 32)
+#define RB_CAP 96    // staged records per warp (phase 1 appends up to 32 per step and flushes above RB_CAP - 32)
+#define RB_QUEUE 64  // ring of candidate (cell, record) pairs per warp
 
-// one lattice cell against the staged records: exact pre-filters, then the reference's arithmetic (pair_full) for the few
-// pairs that survive them.  (si, sj, sk) = the lane's cell, dm = its in-lattice directions, coll = directions already blocked.
-//
-// With a = -n.(s - v0) and b = n.dir exactly as checkTriangleCollision computes them (crixus_d.cu:757-765), a direction along
-// axis x can only collide if |b| < eps and |a| < eps (ray in the plane), or r = a / b lies in [-eps, 1 + eps], which needs
-// |a| <= |n_x| |dir| (1 + eps) up to rounding.  L[x] = max |dir| (1 + eps) 1.0002 per axis is a property of the cell, so the
-// test for BOTH directions of an axis is one multiply and one compare per record; the (rare) survivors get the sign test and
-// a bounding-sphere test of the hit point before the reference's arithmetic runs.  Only for well-formed triangles (R0.w != 0:
-// finite, unit normal perpendicular to the edges); everything else takes the reference's arithmetic unfiltered.
-__device__ __forceinline__ uint32_t cell_vs_staged(const FillArgs &A, const float4 *sR0, const float4 *sR1, const int *sIdx, int cnt,
-                                                   int si, int sj, int sk, uint32_t dm, uint32_t coll)
+// per-warp working set of k_resolve_blocks
+struct RBWarp {
+  float4 R0[RB_CAP], R1[RB_CAP];   // (n, flags) and (v0, uu) of the staged records
+  int idx[RB_CAP];                 // record index
+  float rad[RB_CAP];               // bounding radius of the accepted barycentric region around v0 (well-conditioned records)
+  unsigned short queue[RB_QUEUE];  // candidate pairs: (cell << 8) | staged slot
+  uint32_t coll[64];               // blocked directions per lattice cell of the sub-block
+};
+
+// geometry of a sub-block of lattice cells: cell q = (i0 + q % nx, j0 + (q / nx) % ny, k0 + q / (nx ny)), q < nx ny nz <= 64
+struct RBSub {
+  int i0, j0, k0, nx, ny, nz;
+};
+
+__device__ __forceinline__ uint32_t cell_dirs(const FillArgs &A, int si, int sj, int sk)
+{
+  return (si > 0 ? 1u : 0u) | (si + 1 < A.dimg[0] ? 2u : 0u) | (sj > 0 ? 4u : 0u) | (sj + 1 < A.dimg[1] ? 8u : 0u) | (sk > 0 ? 16u : 0u) |
+         (sk + 1 < A.dimg[2] ? 32u : 0u);
+}
+
+// One candidate (lattice cell, staged record) pair, exactly: the directions that can collide are narrowed with exact, division-
+// free tests, the reference's arithmetic (pair_full) decides the rest.
+//   With a = -n.(s - v0) and b = n.dir exactly as checkTriangleCollision computes them (crixus_d.cu:757-765), a direction along
+//   axis x can only collide if |b| < eps and |a| < eps (ray in the plane), or r = a / b lies in [-eps, 1 + eps], which needs
+//   |a| <= |n_x| |dir| (1 + eps) up to rounding; the hit point s + r dir of an accepted (t1, t2) lies within rad of v0.
+// Only for well-formed triangles (R0.w != 0: finite, unit normal perpendicular to the edges) whose distance test is provably
+// false; everything else takes the reference's arithmetic unfiltered.
+__device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &W, int q, int si, int sj, int sk, uint32_t need)
 {
   const cx_params &p = A.p;
   const float eps = p.eps;
   const f3 s = mk3(lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk));
-  // direction vectors e - s, one non-zero component each
-  const float dxm = fsub(lat_pos(p, 0, si - 1), s.x), dxp = fsub(lat_pos(p, 0, si + 1), s.x);
-  const float dym = fsub(lat_pos(p, 1, sj - 1), s.y), dyp = fsub(lat_pos(p, 1, sj + 1), s.y);
-  const float dzm = fsub(lat_pos(p, 2, sk - 1), s.z), dzp = fsub(lat_pos(p, 2, sk + 1), s.z);
-  const float grow = 1.0002f * (1.0f + eps);
-  const float Lx = fmaxf(fabsf(dxm), fabsf(dxp)) * grow, Ly = fmaxf(fabsf(dym), fabsf(dyp)) * grow, Lz = fmaxf(fabsf(dzm), fabsf(dzp)) * grow;
-  const float lim_alive = 1.44f * A.drw2;
-  for (int q = 0; q < cnt; q++) {
-    const uint32_t need = dm & ~coll;
-    if (!need) break;
-    const float4 R0 = sR0[q], R1 = sR1[q];
-    const f3 n = mk3(R0), v0 = mk3(R1);
-    const f3 w0 = sub3(s, v0);
-    const float a = -dot3_r3(n, w0);
-    const float aa = fabsf(a);
-    const bool wf = R0.w != 0.f;
-    if (wf && aa > A.rrej) continue;   // plane-distance reject: neither test can hold
-    // the distance test is alive unless eps >= dr_wall^2 or (well-formed triangle) the plane distance alone exceeds dr_wall:
-    // every distance the reference computes is >= |a| / 1.2
-    uint32_t cand = need;
-    if (wf && (A.dist_dead || a * a >= lim_alive) && !A.nofilter) {
-      uint32_t m = 0;
-      if (aa <= fabsf(n.x) * Lx || aa < eps) m |= 3u;
-      if (aa <= fabsf(n.y) * Ly || aa < eps) m |= 12u;
-      if (aa <= fabsf(n.z) * Lz || aa < eps) m |= 48u;
-      m &= need;
-      if (!m) continue;
-      cand = 0;
-      while (m) {
-        const int d = __ffs(m) - 1;
-        m &= m - 1;
-        const int ax = d >> 1;
-        const float dc = d == 0 ? dxm : d == 1 ? dxp : d == 2 ? dym : d == 3 ? dyp : d == 4 ? dzm : dzp;
-        const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
-        const float b = dot3_r3(n, dir);
-        const float ab = fabsf(b);
-        if (ab < eps) {
-          if (aa < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
-          continue;
-        }
-        const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
-        if (qn > ab * 1.0001f * (1.0f + eps) || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
-        if (R0.w == 2.f) {
-          // hit point P = s + r dir; an accepted (t1, t2) puts it within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned
-          // triangles only).  r from a fast division: the 1 % margin of sph2 covers its error many times over.
-          const float r = __fdividef(qn, ab);
-          const float px = ax == 0 ? w0.x + r * dc : w0.x, py = ax == 1 ? w0.y + r * dc : w0.y, pz = ax == 2 ? w0.z + r * dc : w0.z;
-          if (px * px + py * py + pz * pz > A.sph2 * __int_as_float(sIdx[RB_CAP + q])) continue;
-        }
-        cand |= 1u << d;
+  const float4 R0 = W.R0[q], R1 = W.R1[q];
+  const f3 n = mk3(R0), v0 = mk3(R1);
+  const f3 w0 = sub3(s, v0);
+  const float a = -dot3_r3(n, w0);
+  const float aa = fabsf(a);
+  const bool wf = R0.w != 0.f;
+  if (wf && aa > A.rrej) return 0;   // plane-distance reject: neither test can hold
+  uint32_t cand = need;
+  // the distance test is alive unless eps >= dr_wall^2 or (well-formed triangle) the plane distance alone exceeds dr_wall:
+  // every distance the reference computes is >= |a| / 1.2
+  if (wf && (A.dist_dead || a * a >= 1.44f * A.drw2) && !A.nofilter) {
+    cand = 0;
+    uint32_t m = need;
+    const float grow = 1.0001f * (1.0f + eps);
+    const float rad = W.rad[q];
+    while (m) {
+      const int d = __ffs(m) - 1;
+      m &= m - 1;
+      const int ax = d >> 1;
+      const int sidx = ax == 0 ? si : ax == 1 ? sj : sk;
+      const float sc = ax == 0 ? s.x : ax == 1 ? s.y : s.z;
+      const float dc = fsub(lat_pos(p, ax, sidx + ((d & 1) ? 1 : -1)), sc);
+      const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
+      const float b = dot3_r3(n, dir);
+      const float ab = fabsf(b);
+      if (ab < eps) {
+        if (aa < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
+        continue;
       }
-      if (!cand) continue;
+      const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
+      if (qn > ab * grow || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
+      if (R0.w == 2.f) {
+        // hit point P = s + r dir (r from a fast division: the 1 % margin of rad covers its error many times over)
+        const float r = __fdividef(qn, ab);
+        const float px = ax == 0 ? w0.x + r * dc : w0.x, py = ax == 1 ? w0.y + r * dc : w0.y, pz = ax == 2 ? w0.z + r * dc : w0.z;
+        if (px * px + py * py + pz * pz > rad * rad) continue;
+      }
+      cand |= 1u << d;
     }
-    coll |= pair_full(A, si, sj, sk, sIdx[q], cand);
+    if (!cand) return 0;
   }
-  return coll;
+  return pair_full(A, si, sj, sk, W.idx[q], cand);
+}
+
+// the lattice cells of one sub-block against the staged records.
+//   filter: every lane holds a cell (two passes for sub-blocks of more than 32 cells) and walks the staged records with a
+//           cheap, CONSERVATIVE, warp-uniform test (approximate plane distance; for well-conditioned triangles a sphere that
+//           contains every hit point a lattice step from this cell can produce; cells in the plane keep every record while an
+//           in-plane direction is open: the "ray in plane" rule ignores the triangle's extent).  Survivors are appended to a
+//           ring of (cell, record) pairs -- ballot + popc compaction;
+//   pairs : as soon as 32 pairs wait, every lane takes one and runs the exact test (pair_exact) -- full lanes for the
+//           expensive part instead of a warp that diverges on every record.
+__device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, const RBSub &S, int cnt, int lane)
+{
+  const cx_params &p = A.p;
+  const int ncl = S.nx * S.ny * S.nz;
+  int qh = 0, qn = 0;   // ring head / fill (warp-uniform)
+  auto drain = [&](int take) {
+    const bool have = lane < take;
+    if (have) {
+      const unsigned e = W.queue[(qh + lane) & (RB_QUEUE - 1)];
+      const int cell = (int)(e >> 8), q = (int)(e & 255u);
+      const int si = S.i0 + cell % S.nx, sj = S.j0 + (cell / S.nx) % S.ny, sk = S.k0 + cell / (S.nx * S.ny);
+      const uint32_t need = cell_dirs(A, si, sj, sk) & ~W.coll[cell];
+      if (need) {
+        const uint32_t got = pair_exact(A, W, q, si, sj, sk, need);
+        if (got) atomicOr(&W.coll[cell], got);
+      }
+    }
+    qh = (qh + take) & (RB_QUEUE - 1);
+    qn -= take;
+    __syncwarp();
+  };
+  for (int sl = 0; sl * 32 < ncl; sl++) {
+    const int cell = lane + 32 * sl;
+    const bool valid = cell < ncl;
+    const int si = S.i0 + (valid ? cell % S.nx : 0), sj = S.j0 + (valid ? (cell / S.nx) % S.ny : 0), sk = S.k0 + (valid ? cell / (S.nx * S.ny) : 0);
+    const uint32_t dm = valid ? cell_dirs(A, si, sj, sk) : 0u;
+    const float sx = lat_pos(p, 0, si), sy = lat_pos(p, 1, sj), sz = lat_pos(p, 2, sk);
+    // reach of a lattice step from this cell, with the tolerances of the ray parameter: (1 + eps) |dir|, 2 % on top
+    const float L = 1.02f * (1.0f + p.eps) * fmaxf(fmaxf(fabsf(lat_pos(p, 0, si + 1) - sx), fabsf(lat_pos(p, 0, si - 1) - sx)),
+                                                  fmaxf(fmaxf(fabsf(lat_pos(p, 1, sj + 1) - sy), fabsf(lat_pos(p, 1, sj - 1) - sy)),
+                                                        fmaxf(fabsf(lat_pos(p, 2, sk + 1) - sz), fabsf(lat_pos(p, 2, sk - 1) - sz))));
+    const float eps2 = 2.0f * p.eps;
+    for (int q = 0; q < cnt; q++) {
+      bool c = false;
+      const uint32_t need = valid ? (dm & ~W.coll[cell]) : 0u;
+      if (need) {
+        const float4 R0 = W.R0[q], R1 = W.R1[q];
+        const float wx = sx - R1.x, wy = sy - R1.y, wz = sz - R1.z;
+        const float aa = fabsf(wx * R0.x + wy * R0.y + wz * R0.z);   // approximate: every threshold below has slack for its rounding
+        if (R0.w == 0.f || A.nofilter) c = true;                     // no assumption about this triangle: exact path
+        else if (aa <= A.rrej * 1.001f) {
+          if (!(A.dist_dead || aa * aa >= 1.45f * A.drw2)) c = true; // the distance test may hold: exact path
+          else if (aa < eps2) {
+            // in the plane: while a direction parallel to the plane is open every record counts; afterwards only hit points
+            const uint32_t inpl = (fabsf(R0.x) * L < eps2 ? 3u : 0u) | (fabsf(R0.y) * L < eps2 ? 12u : 0u) | (fabsf(R0.z) * L < eps2 ? 48u : 0u);
+            c = (need & inpl) != 0u;
+            if (!c) { const float rr = W.rad[q] + L; c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr; }
+          } else if (aa <= L) {
+            const float rr = W.rad[q] + L;
+            c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, c);
+      if (bal) {
+        if (c) W.queue[(qh + qn + __popc(bal & ((1u << lane) - 1u))) & (RB_QUEUE - 1)] = (unsigned short)((cell << 8) | q);
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) drain(32);
+      }
+    }
+    if (qn > 0) drain(qn);
+  }
 }
 
 __global__ void __launch_bounds__(RB_WARPS * 32, 2) k_resolve_blocks(const __grid_constant__ FillArgs A)
 {
-  __shared__ float4 sR0[RB_WARPS][RB_CAP], sR1[RB_WARPS][RB_CAP];
-  __shared__ int sIdx[RB_WARPS][2 * RB_CAP];   // record index, then (as float bits) max(uu, vv) of the record
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  __shared__ RBWarp sW[RB_WARPS];
+  const int lane = threadIdx.x & 31;
   const cx_params &p = A.p;
-  const long long ncell = p.gridn[3];
-  const long long nchunk = (ncell + 31) / 32;
-  const int nparts = A.res_nparts > 1 ? A.res_nparts : 1;
-  float4 *mR0 = sR0[wp], *mR1 = sR1[wp];
-  int *mIdx = sIdx[wp];
+  RBWarp &W = sW[threadIdx.x >> 5];
+  const float radf = 1.01f * (1.0f + 3.0f * p.eps);
   for (;;) {
-    long long chunk = 0;
-    if (lane == 0) chunk = (long long)atomicAdd(A.count64, 1ull);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (nparts > 1) {   // my q-th chunk: group q, the slot that chunk_owner() gives to this rank
-      const long long g = chunk;
-      const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)nparts);
-      chunk = g * nparts + (A.res_part + rot) % nparts;
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(A.count64, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= A.nblist) break;
+    const long long c = A.blist[item];
+    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((long long)p.gridn[2] * p.gridn[1]));
+    // lattice index ranges of the cells that map to this 3dr-cell: lanes 0..5 search one bound each
+    int bound = 0;
+    if (lane < 6) {
+      const int ax = lane >> 1, g = (ax == 0 ? gx : ax == 1 ? gy : gz) + (lane & 1);
+      bound = idx_lo(p, ax, g, A.dimg[ax]);
     }
-    if (chunk >= nchunk) { if (nparts > 1 && chunk - (chunk % nparts) < nchunk) continue; break; }
-    const long long c0 = chunk * 32 + lane;
-    unsigned todo = __ballot_sync(0xffffffffu, c0 < ncell && A.nbflag[c0]);
-    while (todo) {
-      const int bsel = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const long long c = chunk * 32 + bsel;
-      const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((long long)p.gridn[2] * p.gridn[1]));
-      // lattice index ranges of the cells that map to this 3dr-cell: lanes 0..5 search one bound each
-      int bound = 0;
-      if (lane < 6) {
-        const int ax = lane >> 1, g = (ax == 0 ? gx : ax == 1 ? gy : gz) + (lane & 1);
-        bound = idx_lo(p, ax, g, A.dimg[ax]);
-      }
-      const int bi0 = __shfl_sync(0xffffffffu, bound, 0), bi1 = __shfl_sync(0xffffffffu, bound, 1);
-      const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
-      const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
-      if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
-      // the neighbourhood as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run of
-      // records (plus, at a periodic z border, the wrapped cell as a run of its own): lane l < 27 holds run l (9 columns x 3 parts)
-      int rb = 0, re = 0;
-      if (lane < 27) {
-        const int c9 = lane / 3, part = lane % 3;
-        const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
-        if (part == 0) {
-          const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
-          const int64_t q0 = nb_cell(p, cx, cy, z0);
-          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
-        } else {
-          const int zz = part == 1 ? gz - 1 : gz + 1;
-          if (zz < 0 || zz >= p.gridn[2]) {   // out of range: wrapped (periodic z) or skipped
-            const int64_t q0 = nb_cell(p, cx, cy, zz);
-            if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
-          }
+    const int bi0 = __shfl_sync(0xffffffffu, bound, 0), bi1 = __shfl_sync(0xffffffffu, bound, 1);
+    const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
+    const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
+    if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
+    // the neighbourhood as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run of
+    // records (plus, at a periodic z border, the wrapped cell as a run of its own): lane l < 27 holds run l (9 columns x 3 parts)
+    int rb = 0, re = 0;
+    if (lane < 27) {
+      const int c9 = lane / 3, part = lane % 3;
+      const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
+      if (part == 0) {
+        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
+        const int64_t q0 = nb_cell(p, cx, cy, z0);
+        if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
+      } else {
+        const int zz = part == 1 ? gz - 1 : gz + 1;
+        if (zz < 0 || zz >= p.gridn[2]) {   // out of range: wrapped (periodic z) or skipped
+          const int64_t q0 = nb_cell(p, cx, cy, zz);
+          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
         }
       }
-      // sub-blocks of at most 4 x 4 x 4 lattice cells (a 3dr-cell holds 3-4 cells per axis; border cells of a container that is
-      // larger than the domain hold more), two cells per lane
-      for (int k0 = bk0; k0 < bk1; k0 += 4)
-        for (int j0 = bj0; j0 < bj1; j0 += 4)
-          for (int i0 = bi0; i0 < bi1; i0 += 4) {
-            const int nx = min(4, bi1 - i0), ny = min(4, bj1 - j0), nz = min(4, bk1 - k0);
-            const int ncl = nx * ny * nz;
-            int ci[2], cj[2], ck[2];
-            uint32_t dm[2], coll[2];
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-              const int q = lane + 32 * sl;
-              const bool v = q < ncl;
-              ci[sl] = i0 + (v ? q % nx : 0); cj[sl] = j0 + (v ? (q / nx) % ny : 0); ck[sl] = k0 + (v ? q / (nx * ny) : 0);
-              dm[sl] = !v ? 0u : ((ci[sl] > 0 ? 1u : 0u) | (ci[sl] + 1 < A.dimg[0] ? 2u : 0u) | (cj[sl] > 0 ? 4u : 0u) |
-                                  (cj[sl] + 1 < A.dimg[1] ? 8u : 0u) | (ck[sl] > 0 ? 16u : 0u) | (ck[sl] + 1 < A.dimg[2] ? 32u : 0u));
-              coll[sl] = 0;
-            }
-            // centre and half extents of the sub-block, for the block-level plane-distance reject
-            const float xlo = lat_pos(p, 0, i0), xhi = lat_pos(p, 0, i0 + nx - 1), ylo = lat_pos(p, 1, j0), yhi = lat_pos(p, 1, j0 + ny - 1);
-            const float zlo = lat_pos(p, 2, k0), zhi = lat_pos(p, 2, k0 + nz - 1);
-            const float bcx = 0.5f * (xlo + xhi), bcy = 0.5f * (ylo + yhi), bcz = 0.5f * (zlo + zhi);
-            const float bhx = 0.5f * (xhi - xlo), bhy = 0.5f * (yhi - ylo), bhz = 0.5f * (zhi - zlo);
-            int cnt = 0;
-            for (int run = 0; run < 27; run++) {
-              const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
-              for (int base = b; base < e; base += 32) {
-                const int i = base + lane;
-                bool keep = false;
-                float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
-                float muv = 0.f;
-                if (i < e) {
-                  const float4 *r = A.rec + (int64_t)i * FREC;
-                  R0 = __ldg(r); R1 = __ldg(r + 1);
-                  const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
-                  const float rad = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
-                  keep = !(R0.w != 0.f && fabsf(tc) - rad > A.rrej);
-                  if (keep && R0.w == 2.f) muv = fmaxf(R1.w, __ldg(r + 3).w);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (!bal) continue;
-                if (keep) {
-                  const int at = cnt + __popc(bal & ((1u << lane) - 1u));
-                  mR0[at] = R0; mR1[at] = R1; mIdx[at] = i; mIdx[RB_CAP + at] = __float_as_int(muv);
-                }
-                cnt += __popc(bal);
+    }
+    // sub-blocks of at most 4 x 4 x 4 lattice cells (a 3dr-cell holds 3-4 cells per axis; border cells of a container that is
+    // larger than the domain hold more)
+    for (int k0 = bk0; k0 < bk1; k0 += 4)
+      for (int j0 = bj0; j0 < bj1; j0 += 4)
+        for (int i0 = bi0; i0 < bi1; i0 += 4) {
+          RBSub S;
+          S.i0 = i0; S.j0 = j0; S.k0 = k0;
+          S.nx = min(4, bi1 - i0); S.ny = min(4, bj1 - j0); S.nz = min(4, bk1 - k0);
+          const int ncl = S.nx * S.ny * S.nz;
+          W.coll[lane] = 0u; W.coll[lane + 32] = 0u;
+          __syncwarp();
+          // centre and half extents of the sub-block, for the block-level plane-distance reject
+          const float xlo = lat_pos(p, 0, i0), xhi = lat_pos(p, 0, i0 + S.nx - 1), ylo = lat_pos(p, 1, j0), yhi = lat_pos(p, 1, j0 + S.ny - 1);
+          const float zlo = lat_pos(p, 2, k0), zhi = lat_pos(p, 2, k0 + S.nz - 1);
+          const float bcx = 0.5f * (xlo + xhi), bcy = 0.5f * (ylo + yhi), bcz = 0.5f * (zlo + zhi);
+          const float bhx = 0.5f * (xhi - xlo), bhy = 0.5f * (yhi - ylo), bhz = 0.5f * (zhi - zlo);
+          int cnt = 0;
+          for (int run = 0; run < 27; run++) {
+            const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
+            for (int base = b; base < e; base += 32) {
+              const int i = base + lane;
+              bool keep = false;
+              float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+              float rad = 0.f;
+              if (i < e) {
+                const float4 *r = A.rec + (int64_t)i * FREC;
+                R0 = __ldg(r); R1 = __ldg(r + 1);
+                const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
+                const float hr = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
+                keep = !(R0.w != 0.f && fabsf(tc) - hr > A.rrej * 1.001f);
+                // an accepted (t1, t2) puts the hit point within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned triangles), 1 % on top
+                if (keep && R0.w == 2.f) rad = radf * sqrtf(fmaxf(R1.w, __ldg(r + 3).w));
+              }
+              const unsigned bal = __ballot_sync(0xffffffffu, keep);
+              if (!bal) continue;
+              if (keep) {
+                const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+                W.R0[at] = R0; W.R1[at] = R1; W.idx[at] = i; W.rad[at] = rad;
+              }
+              cnt += __popc(bal);
+              __syncwarp();
+              if (cnt > RB_CAP - 32) {
+                sub_vs_staged(A, W, S, cnt, lane);
+                cnt = 0;
                 __syncwarp();
-                if (cnt > RB_CAP - 32) {
-#pragma unroll
-                  for (int sl = 0; sl < 2; sl++)
-                    if (dm[sl] & ~coll[sl]) coll[sl] = cell_vs_staged(A, mR0, mR1, mIdx, cnt, ci[sl], cj[sl], ck[sl], dm[sl], coll[sl]);
-                  cnt = 0;
-                  __syncwarp();
-                }
               }
             }
-            if (cnt) {
-#pragma unroll
-              for (int sl = 0; sl < 2; sl++)
-                if (dm[sl] & ~coll[sl]) coll[sl] = cell_vs_staged(A, mR0, mR1, mIdx, cnt, ci[sl], cj[sl], ck[sl], dm[sl], coll[sl]);
-              __syncwarp();
-            }
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-              const uint32_t cl = coll[sl] & dm[sl];
-              if (!cl) continue;
-              const int64_t wi = ((int64_t)ck[sl] * A.dimg[1] + cj[sl]) * A.wr + (ci[sl] >> 5);
-              const uint32_t bit = 1u << (ci[sl] & 31);
-#pragma unroll
-              for (int d = 0; d < 6; d++)
-                if (cl >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
-            }
           }
-    }
+          if (cnt) {
+            sub_vs_staged(A, W, S, cnt, lane);
+            __syncwarp();
+          }
+          for (int cell = lane; cell < ncl; cell += 32) {
+            const int si = i0 + cell % S.nx, sj = j0 + (cell / S.nx) % S.ny, sk = k0 + cell / (S.nx * S.ny);
+            const uint32_t cl = W.coll[cell] & cell_dirs(A, si, sj, sk);
+            if (!cl) continue;
+            const int64_t wi = ((int64_t)sk * A.dimg[1] + sj) * A.wr + (si >> 5);
+            const uint32_t bit = 1u << (si & 31);
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+              if (cl >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
+          }
+          __syncwarp();
+        }
+  }
+}
+
+// work list of k_resolve_blocks: the 3dr-cells whose neighbourhood holds segments and that this rank resolves.  One list entry
+// per cell (a warp takes one at a time): with coarser items a warp that drew a chunk of 32 wall cells ran for milliseconds
+// after all others had finished.
+__global__ void __launch_bounds__(256) k_block_list(cx_params p, const uint8_t *__restrict__ nbflag, int nparts, int part, int32_t *list,
+                                                    unsigned long long *count)
+{
+  const long long n = p.gridn[3];
+  for (long long c0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31ll; c0 < n; c0 += (long long)gridDim.x * blockDim.x) {
+    const long long c = c0 + (threadIdx.x & 31);
+    const bool mine = c < n && nbflag[c] && (nparts <= 1 || chunk_owner(c >> 5, nparts) == part);
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine && list) list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (int32_t)c;
   }
 }
 
@@ -841,6 +915,8 @@ struct FillState {
   int64_t nbe = 0, cnbe = 0;
   uint32_t *F = nullptr, *B = nullptr;   // B: 6 blocked planes
   uint32_t *halo = nullptr;              // two received boundary planes (multi-GPU)
+  int32_t *blist = nullptr;              // work list of the up-front resolve
+  int64_t cap_blist = 0;
   float4 *rec = nullptr;
   int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
   uint8_t *nbflag = nullptr, *act = nullptr;
@@ -856,7 +932,7 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -961,13 +1037,36 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
 }
 
 // directed tests of the planes [A->k_lo, A->k_hi), share (res_part of res_nparts), into the B planes
-static int fill_resolve(cx_ctx *ctx, FillArgs *A)
+static int fill_resolve(cx_ctx *ctx, FillArgs *A, FillState *s)
 {
   cudaStream_t st = ctx->stream;
   if (A->k_hi <= A->k_lo) return CX_OK;
-  CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
-  k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
-  CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
+  // work list: count, (grow the buffer,) fill -- the order of the entries is irrelevant (results are OR-ed bits)
+  const int64_t ncell = A->p.gridn[3];
+  const int lgrid = cx_blocks(ncell, 256, ctx->num_sms * 16);
+  for (int pass = 0; pass < 2; pass++) {
+    CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+    k_block_list<<<lgrid, 256, 0, st>>>(A->p, A->nbflag, A->res_nparts, A->res_part, pass ? s->blist : nullptr, A->count64);
+    CX_LAUNCH_CHECK(ctx, "k_block_list");
+    if (pass == 0) {
+      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CX_CUDA(ctx, cudaStreamSynchronize(st));
+      A->nblist = ctx->h_mail[30];
+      if (A->nblist > s->cap_blist) {
+        cudaFree(s->blist); s->blist = nullptr; s->cap_blist = 0;
+        const int64_t want = A->nblist + A->nblist / 8 + 1024;
+        CX_CUDA(ctx, cudaMalloc(&s->blist, sizeof(int32_t) * (size_t)want));
+        s->cap_blist = want;
+      }
+      A->blist = s->blist;
+      if (A->nblist == 0) break;
+    }
+  }
+  if (A->nblist > 0) {
+    CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+    k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
+    CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
+  }
   if (A->cnbe > 0) {
     const int64_t total = (int64_t)A->dimg[1] * (A->k_hi - A->k_lo) * A->cnbe;
     k_resolve_fs<<<cx_blocks(total, 128, ctx->num_sms * 32), 128, 0, st>>>(*A);
@@ -1057,7 +1156,7 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   // Resolve every directed test of the owned planes up front, in one balanced launch: they are pure functions of the
   // geometry, so nothing is gained by waiting for the flood to arrive.
   if (!(s->resolved_lo <= A.k_lo && s->resolved_hi >= A.k_hi)) {
-    rc = fill_resolve(ctx, &A);
+    rc = fill_resolve(ctx, &A, s);
     if (rc != CX_OK) return rc;
     s->resolved_lo = A.k_lo; s->resolved_hi = A.k_hi;
   }
@@ -1118,7 +1217,7 @@ static int resolve_share(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, cons
   CX_LAUNCH_CHECK(ctx, "k_unpack");
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
   A.res_nparts = nparts; A.res_part = part;
-  rc = fill_resolve(ctx, &A);
+  rc = fill_resolve(ctx, &A, s);
   if (rc != CX_OK) return rc;
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
   if (blocked_d) *blocked_d = s->B;

@@ -217,10 +217,18 @@ int cx_run_ini(const char *ini_path)
   if (rc != CX_OK) { printf("No usable CUDA device (crixus_b200 has no CPU path)\n"); return rc; }
   const double t_create = wall_s() - t_c0;
   rc = cx_preprocess_host(ctx, &job);
-  if (rc != CX_OK) { printf("Preprocessing failed: %d %s\n", rc, cx_last_error(ctx)); cx_destroy(ctx); return rc; }
-  if (job.tri_failed > 0)   // the reference leaves this check to its stand-alone tool resources/test-triangle-size.c
+  // the reference leaves this check to its stand-alone tool resources/test-triangle-size.c; here it runs before the first stage, so
+  // the diagnosis is available on the failure path too (oversized triangles are what makes calc_vert_volume return
+  // CX_FAN_INCOMPLETE, where the reference reads uninitialised memory and carries on)
+  if (job.tri_failed > 0)
     printf("WARNING: %lld vertex-barycentre distances exceed dr - 1e-4*dr (max %g): triangles too large for dr, results are unreliable\n",
            (long long)job.tri_failed, job.tri_maxd);
+  if (rc != CX_OK) {
+    printf("Preprocessing failed: %d %s\n", rc, cx_last_error(ctx));
+    if (rc == CX_NO_PER_VERT) printf("(the reference skips such vertices silently, src/crixus_d.cu:229-232; see INTEGRATION.md section 4b)\n");
+    cx_destroy(ctx);
+    return rc;
+  }
   printf("\n\tInformation:\n\tNumber of vertices:         \t%lld\n\tNumber of boundary elements:\t%lld\n\n", (long long)job.nvert, (long long)job.nbe);
   printf("\tNormals information:\n\tPositive (n.(0,0,1)) minimum z: %g (%g)\n\tNegative (n.(0,0,1)) minimum z: %g (%g)\n\n", job.zstat[0],
          job.zstat[2], job.zstat[1], job.zstat[3]);

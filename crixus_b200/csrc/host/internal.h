@@ -2,7 +2,16 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../../include/crixus_b200.h"
+
+// NVTX range of the running stage (header-only NVTX 3: a no-op unless a profiler is attached); closed on every exit path
+struct CxStage {
+  bool open = false;
+  void next(const char *name) { end(); nvtxRangePushA(name); open = true; }
+  void end() { if (open) { nvtxRangePop(); open = false; } }
+  ~CxStage() { end(); }
+};
 extern "C" {
 // grow-only arenas owned by the context: >= bytes of device memory / pinned host memory, contents undefined
 void *cx_internal_dev_arena(cx_ctx *ctx, size_t bytes);

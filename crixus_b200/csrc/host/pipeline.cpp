@@ -181,15 +181,19 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
 
   t0 = now_s();
   Events evs;   // released on every exit path
+  CxStage stage;   // NVTX range of the running stage, closed on every exit path
   cudaEvent_t *ev = evs.e;
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&ev[k]));
   CU(cudaEventRecord(ev[0], st));
+  stage.next("cx: swap_normals + set_bound_elem");
   if (job->swap_normals) RC(cx_swap_normals(ctx, pre_norm.as<float>(), nbe));  // crixus.cu:310-317
   RC(cx_set_bound_elem(ctx, pre_pos.as<float>(), pre_norm.as<float>(), pre_surf.as<float>(), pre_ep.as<int32_t>(), nbe, nvert, job->zstat));
   CU(cudaEventRecord(ev[1], st));
+  stage.next("cx: cell binning");
   RC(cx_bin_segments(ctx, &p, pre_pos.as<float>(), pos.as<float>(), pre_norm.as<float>(), norm.as<float>(), pre_ep.as<int32_t>(),
                      ep.as<int32_t>(), pre_surf.as<float>(), surf.as<float>(), cell_idx.as<int32_t>(), nbe, nvert));
   CU(cudaEventRecord(ev[2], st));
+  stage.next("cx: periodic links");
   for (int idim = 0; idim < 3; idim++) {  // crixus.cu:391-412
     if (!job->periodic[idim]) continue;
     CU(cudaMemsetAsync(newlink.p, 0xff, 4 * (size_t)nvert, st));
@@ -198,6 +202,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
   }
   for (int k = 0; k < 3; k++) p.per[k] = job->periodic[k] ? 1 : 0;  // crixus.cu:428
   CU(cudaEventRecord(ev[3], st));
+  stage.end();
   // pos / norm / ep / surf / cell_idx are final from here on (crixus.cu:363-365, 413): download them on a second stream
   // while calc_vert_volume and the fills run
   job->pos = (float *)(hbase + o_pos); job->norm = (float *)(hbase + o_norm); job->ep = (int32_t *)(hbase + o_ep);
@@ -231,6 +236,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
     CU(cudaMemcpyAsync(job->cell_idx, cell_idx.p, 4 * (size_t)(ncell + 1), cudaMemcpyDeviceToHost, cst));
   RC(cx_calc_trisize(ctx, ep.as<int32_t>(), trisize.as<int32_t>(), nbe));
   CU(cudaEventRecord(ev[4], st));
+  stage.next("cx: calc_vert_volume");
   if (world > 1)
     RC(cx_dist_calc_vert_volume(ctx, &p, pos.as<float>(), norm.as<float>(), ep.as<int32_t>(), vol.as<float>(), trisize.as<int32_t>(),
                                 cell_idx.as<int32_t>(), nvert, nbe, job->zero_open));
@@ -239,6 +245,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
                            cell_idx.as<int32_t>(), nvert, nbe, job->zero_open, 0, nvert));
 
   CU(cudaEventRecord(ev[5], st));
+  stage.next("cx: special boundaries");
   cx_params_fill_eps(&p);   // crixus.cu:463-467
   // ---- special-boundary grids #1..nsb (crixus.cu:469-617); a later grid overwrites the ids of an earlier one
   job->sbid = nullptr;
@@ -262,6 +269,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
       CU(cudaMemcpyAsync(job->sbid, sbid.p, 4 * (size_t)(nvert + nbe), cudaMemcpyDeviceToHost, cst));
   }
   CU(cudaEventRecord(ev[6], st));
+  stage.next("cx: fills");
   // ---- fluid (crixus.cu:698-961)
   cx_params_container(&p, job->use_container, job->cmin, job->cmax);
   job->nfluid_counted = 0;
@@ -314,6 +322,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
     }
   }
   CU(cudaEventRecord(ev[7], st));
+  stage.end();
   RC(cx_synchronize(ctx));
   job->t_gpu_s = now_s() - t0;
   for (int k = 0; k < 5; k++) { CU(cudaEventElapsedTime(&job->stage_ms[k], ev[k], ev[k + 1])); }

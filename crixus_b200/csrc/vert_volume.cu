@@ -211,11 +211,15 @@ struct TriCtx {
 // halving events.  Used for the lanes where the threshold shortcut cannot prove its result (two voxels within eps of a
 // plane on a line that is cut by it, or an expression exactly equal to a threshold).  One function per plane family,
 // because pass 2 visits the families in two separate triangle loops.
-__device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
+// Results go to a per-warp shared-memory scratch (res[lane] = kill mask, res[32 k + lane] = voxels with at least k halvings,
+// k = 1..3): no address of a caller's register variable escapes into this out-of-line function, so the
+// per-voxel state of the hot loop (alive, h[5]) stays in registers (with reference parameters it lived in local memory:
+// 2.5 % of the executed instructions were LDL/STL).
+__device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool mine, unsigned long long *res, int lane)
 {
   if (!mine) return;   // called by the whole warp (keeps it converged); only the flagged lanes do the work
   const float eps = c.eps;
-  uint64_t k = 0ull;
+  uint64_t k = 0ull, c1 = 0ull, c2 = 0ull, c3 = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
     const float q2 = fadd(g, c.piz);
@@ -231,24 +235,26 @@ __device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool
     kill |= sE > eps;
     nh += fabsf(sE) < eps;
     if (kill) k |= 1ull << m;
-    for (int r = 0; r < nh; r++) half_inc(h, 1ull << m);
+    if (nh >= 1) c1 |= 1ull << m;
+    if (nh >= 2) c2 |= 1ull << m;
+    if (nh >= 3) c3 |= 1ull << m;
   }
-  K = k;
+  res[lane] = k; res[32 + lane] = c1; res[64 + lane] = c2; res[96 + lane] = c3;
 }
-__device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool mine, uint64_t &K, uint64_t (&h)[5])
+__device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool mine, unsigned long long *res, int lane)
 {
   if (!mine) return;
   const float eps = c.eps, neps = -c.eps;
-  uint64_t k = 0ull;
+  uint64_t k = 0ull, n0 = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
     const float w0 = ffma(g, c.P7.z, c.tW0), w1 = ffma(g, c.P8.y, c.tW1), w2 = ffma(g, c.P9.x, c.tW2);
     const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
     const bool hw = fabsf(w0) < eps;
     if (inside && !hw) k |= 1ull << m;
-    if (inside && hw) half_inc(h, 1ull << m);
+    if (inside && hw) n0 |= 1ull << m;
   }
-  K = k;
+  res[lane] = k; res[32 + lane] = n0;
 }
 
 // kill mask {f > eps} and halving mask {|f| < eps} of a voronoi / edge plane on one line.  trig is raised when the
@@ -402,7 +408,7 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
 // Lanes without a line (valid == false) run along with an empty line.
 template <bool OPEN, bool WIDE, bool EST, class VVWarp>
 __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
-                                                 float gp1, bool valid)
+                                                 float gp1, bool valid, unsigned long long *xres, int lane)
 {
   const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
   const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
@@ -452,8 +458,13 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       TriCtx c;
       c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P4; c.P8 = P4; c.P9 = P9;
       c.tV = tV; c.tV2 = tV2; c.tW0 = 0.f; c.tW1 = 0.f; c.tW2 = 0.f; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
-      exact_tri_ve(a, c, trig, K, h);
-      if (trig) { HV = 0ull; HV2 = 0ull; HE = 0ull; }
+      exact_tri_ve(a, c, trig, xres, lane);
+      __syncwarp();
+      if (trig) {   // voxels with >= 1, >= 2, >= 3 halvings: one increment each (the third only with a second voronoi plane)
+        K = xres[lane];
+        HV = xres[32 + lane]; HE = xres[64 + lane]; HV2 = xres[96 + lane];
+      }
+      __syncwarp();
     }
     if (__any_sync(VV_FULLWARP, (HV | HE) != 0ull)) { VV_STAT(8, 1); half_inc_warp(h, HV); half_inc_warp(h, HE); }
     if (OPEN) if (__any_sync(VV_FULLWARP, HV2 != 0ull)) half_inc_warp(h, HV2);
@@ -520,8 +531,10 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       TriCtx c;
       c.P4 = P7; c.P5 = P7; c.P6 = P7; c.P7 = P7; c.P8 = P8; c.P9 = P9;
       c.tV = 0.f; c.tV2 = 0.f; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = 0.f; c.piz = pi.z; c.eps = eps; c.open = 0;
-      exact_tri_w(a, c, trig, K, h);
-      if (trig) HW = 0ull;
+      exact_tri_w(a, c, trig, xres, lane);
+      __syncwarp();
+      if (trig) { K = xres[lane]; HW = xres[32 + lane]; }
+      __syncwarp();
     }
     if (__any_sync(VV_FULLWARP, HW != 0ull)) { VV_STAT(7, 1); half_inc_warp(h, HW); }
     alive &= ~K;
@@ -578,10 +591,12 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
                                                   // 64-entry uint64 mask tables used by mono_mask
   __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
   __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = z-line (k, l) is dead
+  __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
   unsigned short *wq = wqs[threadIdx.x >> 5];
   unsigned long long *rd = rds[threadIdx.x >> 5];
+  unsigned long long *xres = xress[threadIdx.x >> 5];
   if (threadIdx.x < 64) {
     gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
     uint64_t *lmt = reinterpret_cast<uint64_t *>(gzt + 64);
@@ -788,8 +803,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
         const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
         const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
         const float h0 = gzt[kk], h1 = gzt[ll];
-        acc += closed ? line_weight<false, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have)
-                      : line_weight<true, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have);
+        acc += closed ? line_weight<false, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
+                      : line_weight<true, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
         const int took = min(qn, 32);
         qh = (qh + took) & 63;
         qn -= took;
