@@ -149,6 +149,7 @@ def lib():
         "cx_assemble_records_device": (C.c_int, [VP, P, C.POINTER(I64), VP, VP, VP, VP, VP, VP, VP, I64, I64, I64, VP, I64, C.POINTER(I64)]),
         "cx_write_vtu_records_device": (C.c_int, [VP, VP, I64, C.c_char_p]),
         "cx_write_h5sph_records_device": (C.c_int, [VP, VP, I64, C.c_char_p]),
+        "cx_stream_h5sph_device": (C.c_int, [VP, P, C.POINTER(I64), VP, VP, VP, VP, VP, VP, I64, I64, I64, C.c_char_p, I64, C.POINTER(I64)]),
         "cx_run_ini": (C.c_int, [C.c_char_p]),
     }
     for name, (res, args) in sig.items():
@@ -428,6 +429,15 @@ class Context:
                                                    cap, C.byref(n)))
         self.synchronize()
         return rec[: int(n.value)]
+
+    def stream_h5sph_device(self, job, filename, chunk_items=0, nfluid_for_indices=None):
+        """cx_stream_h5sph_device on the device arrays a cx_preprocess_host call left behind -> records written"""
+        n = I64(0)
+        self._ck(self.L.cx_stream_h5sph_device(self.h, C.byref(job.params_fill), job.dimg, VP(job.d_fpos), VP(job.d_pos), VP(job.d_norm),
+                                               VP(job.d_ep), VP(job.d_surf), VP(job.d_vol), int(job.nvert), int(job.nbe),
+                                               int(job.nfluid if nfluid_for_indices is None else nfluid_for_indices),
+                                               str(filename).encode(), int(chunk_items), C.byref(n)))
+        return int(n.value)
 
     def write_records_device(self, rec, filename, fmt="vtu"):
         fn = self.L.cx_write_h5sph_records_device if fmt == "h5sph" else self.L.cx_write_vtu_records_device

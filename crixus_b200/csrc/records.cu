@@ -107,6 +107,52 @@ __global__ void __launch_bounds__(256) k_rec_segment(const float4 *__restrict__ 
   }
 }
 
+// chunked variants for the streamed writer (cx_stream_h5sph_device): records are written relative to the chunk's first record
+__global__ void __launch_bounds__(256) k_rec_fluid_chunk(const uint32_t *__restrict__ fpos, const int32_t *__restrict__ wbase, int64_t w0, int64_t w1,
+                                                         int64_t d0, int64_t d1, float3 fcmin, float dr, float fluid_vol, int32_t rec0,
+                                                         Rec *__restrict__ rec)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = w0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); w < w1; w += nwarp) {
+    const uint32_t bits = __ldg(fpos + w);
+    if (!(bits >> lane & 1u)) continue;
+    const int32_t k = __ldg(wbase + w) + __popc(bits & ((1u << lane) - 1u));
+    const int64_t j = w * 32 + lane;
+    const int64_t m = j / (d1 * d0), n = j % (d1 * d0);
+    Rec r = {};
+    r.z = fadd(fcmin.z, fmul(dr, (float)m));
+    r.y = fadd(fcmin.y, fmul(dr, (float)(n / d0)));
+    r.x = fadd(fcmin.x, fmul(dr, (float)(n % d0)));
+    r.vol = fluid_vol;
+    r.kpar = 1; r.kfluid = 1;
+    r.iref = k;
+    store_rec(rec + (k - rec0), r);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rec_segment_chunk(const float4 *__restrict__ pos, const float4 *__restrict__ norm,
+                                                           const int4 *__restrict__ ep, const float *__restrict__ surf,
+                                                           const int32_t *__restrict__ abase, int64_t nvert, int64_t s0, int64_t s1, int32_t ncur,
+                                                           int32_t nfluid_idx, Rec *__restrict__ rec)
+{
+  for (int64_t i = s0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < s1; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = pos[nvert + i], n = norm[i];
+    const int4 e = ep[i];
+    Rec r = {};
+    r.x = p.x; r.y = p.y; r.z = p.z;
+    r.nx = n.x; r.ny = n.y; r.nz = n.z;
+    r.surf = surf[i];
+    r.kpar = 3; r.kfluid = 1;
+    r.iref = ncur + (int32_t)i;
+    const int ax = abase[e.x], ay = abase[e.y], az = abase[e.z];
+    r.ep1 = nfluid_idx + (abase[e.x + 1] != ax ? ax : e.x);
+    r.ep2 = nfluid_idx + (abase[e.y + 1] != ay ? ay : e.y);
+    r.ep3 = nfluid_idx + (abase[e.z + 1] != az ? az : e.z);
+    store_rec(rec + (i - s0), r);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_kent_max(const int32_t *__restrict__ kent, int64_t n, int32_t *__restrict__ out)
 {
   int m = 0;
@@ -305,4 +351,105 @@ extern "C" int cx_write_h5sph_records_device(cx_ctx *ctx, const void *records_d,
   if (n > 0) rc = stream_to_file(ctx, f, records_d, 64 * (size_t)n);
   fclose(f);
   return rc != CX_OK ? rc : (ok ? CX_OK : CX_WRITE_FAIL);
+}
+
+
+// ------------------------------------------------------------------------------------------------ streamed .h5sph (large runs)
+// cx_assemble_records_device needs all n records resident (64 B each: 64 GB at BASELINE configs[3]).  The .h5sph body is just the
+// records in order -- fluid particles in bit order, vertices, segments -- so it can be produced and written in CHUNKS: the prefix
+// sums over the bitfield popcounts / alive flags give every chunk its first record index, a chunk of bitfield words (or of
+// vertices / segments) is assembled into a bounded device buffer and leaves through the pinned staging while the next one is
+// being assembled.  Same bytes as cx_assemble_records_device + cx_write_h5sph_records_device (tests/test_gpu_pipeline.py).
+// Not available with special boundaries (the stable grouping by KENT permutes the segment records): CX_WRONG_INPUT.
+__global__ void __launch_bounds__(256) k_gather_stride(const int32_t *__restrict__ src, int64_t stride, int64_t n, int64_t limit,
+                                                       int32_t *__restrict__ dst)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i * stride;
+    dst[i] = src[j < limit ? j : limit];
+  }
+}
+
+extern "C" int cx_stream_h5sph_device(cx_ctx *ctx, const cx_params *pfill, const int64_t dimg[3], const uint32_t *fpos_d,
+                                      const float *pos_d, const float *norm_d, const int32_t *ep_d, const float *surf_d,
+                                      const float *vol_d, int64_t nvert, int64_t nbe, int64_t nfluid_for_indices, const char *filename,
+                                      int64_t chunk_items, int64_t *n_host)
+{
+  if (!ctx || !pfill || !dimg || !fpos_d || !pos_d || !norm_d || !ep_d || !surf_d || !vol_d || !filename || nvert < 0 || nbe < 0)
+    return CX_WRONG_INPUT;
+  const int64_t G = dimg[0] * dimg[1] * dimg[2], nwords = (G + 31) / 32;
+  if (nwords + 1 >= (int64_t)1 << 31 || nvert + 1 >= (int64_t)1 << 31 || nbe + 1 >= (int64_t)1 << 31) return CX_WRONG_INPUT;
+  if (chunk_items <= 0) chunk_items = (int64_t)1 << 20;       // bitfield words / vertices / segments per chunk
+  cudaStream_t st = ctx->stream;
+  const int grid = ctx->num_sms * 8;
+  int32_t *wbase = nullptr, *abase = nullptr, *cstart = nullptr;
+  Rec *buf = nullptr;
+  const int64_t nch_w = (nwords + chunk_items - 1) / chunk_items;
+  CX_CUDA(ctx, cudaMallocAsync(&wbase, 4 * (size_t)(nwords + 1), st));
+  CX_CUDA(ctx, cudaMallocAsync(&abase, 4 * (size_t)(nvert + 1), st));
+  CX_CUDA(ctx, cudaMallocAsync(&cstart, 4 * (size_t)(nch_w + 2), st));
+  CX_CUDA(ctx, cudaMallocAsync(&buf, sizeof(Rec) * (size_t)(32 * chunk_items), st));   // a chunk of words holds <= 32 records per word
+  struct Cleanup {
+    cudaStream_t st; void *a, *b, *c, *d; FILE *f = nullptr;
+    ~Cleanup() { cudaFreeAsync(a, st); cudaFreeAsync(b, st); cudaFreeAsync(c, st); cudaFreeAsync(d, st); if (f) fclose(f); }
+  } cl{st, wbase, abase, cstart, buf};
+  k_rec_flags<<<grid, 256, 0, st>>>(fpos_d, nwords, wbase, (const float4 *)pos_d, nvert, abase);
+  CX_LAUNCH_CHECK(ctx, "k_rec_flags");
+  int rc = cx_exclusive_scan_i32(ctx, wbase, wbase, nwords + 1);
+  if (rc == CX_OK) rc = cx_exclusive_scan_i32(ctx, abase, abase, nvert + 1);
+  if (rc != CX_OK) return rc;
+  k_gather_stride<<<cx_blocks(nch_w + 1, 256), 256, 0, st>>>(wbase, chunk_items, nch_w + 1, nwords, cstart);   // first record of every chunk
+  CX_LAUNCH_CHECK(ctx, "k_gather_stride");
+  std::vector<int32_t> hstart((size_t)nch_w + 1);
+  int32_t nalive32 = 0;
+  CX_CUDA(ctx, cudaMemcpyAsync(hstart.data(), cstart, 4 * (size_t)(nch_w + 1), cudaMemcpyDeviceToHost, st));
+  CX_CUDA(ctx, cudaMemcpyAsync(&nalive32, abase + nvert, 4, cudaMemcpyDeviceToHost, st));
+  CX_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t nfl = (uint32_t)hstart[(size_t)nch_w], nalive = nalive32, n = nfl + nalive + nbe;
+  if (n_host) *n_host = n;
+  if (n >= (int64_t)1 << 31 || nfluid_for_indices + nvert >= (int64_t)1 << 31)
+    return cx_fail(ctx, CX_WRONG_INPUT, "records: more than 2^31 particles (the file formats index particles with 32-bit integers)");
+  std::vector<uint8_t> head;
+  rc = cx_h5sph_header((uint64_t)n, head);
+  if (rc != CX_OK) return rc;
+  cl.f = fopen(filename, "wb");
+  if (!cl.f) return CX_NO_WRITE_FILE;
+  setvbuf(cl.f, nullptr, _IOFBF, 8 << 20);
+  if (fwrite(head.data(), 1, head.size(), cl.f) != head.size()) return CX_WRITE_FAIL;
+  const float dr = pfill->dr;
+  const float fluid_vol = (float)pow(dr, 3);   // crixus.cu:986
+  // ---- fluid particles, a chunk of bitfield words at a time (records rebased to the chunk's first record)
+  for (int64_t c = 0; c < nch_w; c++) {
+    const int64_t w0 = c * chunk_items, w1 = std::min(nwords, w0 + chunk_items);
+    const int64_t r0 = (uint32_t)hstart[(size_t)c], r1 = (uint32_t)hstart[(size_t)c + 1];
+    if (r1 == r0) continue;
+    k_rec_fluid_chunk<<<grid, 256, 0, st>>>(fpos_d, wbase, w0, w1, dimg[0], dimg[1], make_float3(pfill->fcmin[0], pfill->fcmin[1], pfill->fcmin[2]),
+                                            dr, fluid_vol, (int32_t)r0, buf);
+    CX_LAUNCH_CHECK(ctx, "k_rec_fluid_chunk");
+    rc = stream_to_file(ctx, cl.f, buf, sizeof(Rec) * (size_t)(r1 - r0));
+    if (rc != CX_OK) return rc;
+  }
+  // ---- vertex particles: chunks of vertex indices (alive vertices of a chunk are consecutive records)
+  std::vector<int32_t> two(2);
+  for (int64_t v0 = 0; v0 < nvert; v0 += 32 * chunk_items) {
+    const int64_t v1 = std::min(nvert, v0 + 32 * chunk_items);
+    CX_CUDA(ctx, cudaMemcpyAsync(&two[0], abase + v0, 4, cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaMemcpyAsync(&two[1], abase + v1, 4, cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (two[1] == two[0]) continue;
+    k_rec_vertex<<<grid, 256, 0, st>>>((const float4 *)pos_d + v0, vol_d + v0, nullptr, abase + v0, v1 - v0, (int32_t)nfl, buf - (nfl + two[0]));
+    CX_LAUNCH_CHECK(ctx, "k_rec_vertex");
+    rc = stream_to_file(ctx, cl.f, buf, sizeof(Rec) * (size_t)(two[1] - two[0]));
+    if (rc != CX_OK) return rc;
+  }
+  // ---- boundary segments: chunks of segment indices
+  for (int64_t s0 = 0; s0 < nbe; s0 += 32 * chunk_items) {
+    const int64_t s1 = std::min(nbe, s0 + 32 * chunk_items);
+    k_rec_segment_chunk<<<grid, 256, 0, st>>>((const float4 *)pos_d, (const float4 *)norm_d, (const int4 *)ep_d, surf_d, abase, nvert, s0, s1,
+                                              (int32_t)(nfl + nalive), (int32_t)nfluid_for_indices, buf);
+    CX_LAUNCH_CHECK(ctx, "k_rec_segment_chunk");
+    rc = stream_to_file(ctx, cl.f, buf, sizeof(Rec) * (size_t)(s1 - s0));
+    if (rc != CX_OK) return rc;
+  }
+  return CX_OK;
 }

@@ -314,6 +314,14 @@ int cx_assemble_records_device(cx_ctx *ctx, const cx_params *pfill, const int64_
 int cx_write_vtu_records_device(cx_ctx *ctx, const void *records_d, int64_t n, const char *filename);
 int cx_write_h5sph_records_device(cx_ctx *ctx, const void *records_d, int64_t n, const char *filename);
 
+/* The .h5sph file of a LARGE run without holding the records: cx_assemble_records_device needs all n 64-byte records resident (64 GB at
+ * BASELINE configs[3]); here chunks of chunk_items bitfield words (32 chunk_items vertices / segments) are assembled into a bounded device
+ * buffer and streamed to the file one after the other (src/crixus.cu:973-1097 + src/crixus.cpp:12-60, same bytes as the resident path).
+ * chunk_items <= 0: 2^20.  Not with special boundaries (the KENT grouping permutes the segment records).  *n_host = records written. */
+int cx_stream_h5sph_device(cx_ctx *ctx, const cx_params *pfill, const int64_t dimg[3], const uint32_t *fpos_d, const float *pos_d,
+                           const float *norm_d, const int32_t *ep_d, const float *surf_d, const float *vol_d, int64_t nvert, int64_t nbe,
+                           int64_t nfluid_for_indices, const char *filename, int64_t chunk_items, int64_t *n_host);
+
 /* what `Crixus file.ini` does (crixus_main, src/crixus.cu:31-1237, hot path only): ini -> STL -> GPU -> output file */
 int cx_run_ini(const char *ini_path);
 
