@@ -431,11 +431,17 @@ __device__ __forceinline__ bool nb_axis(const cx_params &p, int ax, int gs, int 
 // every radius used here) and to [cut_lo, cut_hi)
 __device__ __forceinline__ void axis_range(const cx_params &p, int ax, float c, float R, int gc, int cut_lo, int cut_hi, int dim, int *lo, int *hi)
 {
-  const double a = floor(((double)c - (double)R - (double)p.fcmin[ax]) / (double)p.dr) - 1.0;
-  const double b = ceil(((double)c + (double)R - (double)p.fcmin[ax]) / (double)p.dr) + 1.0;
-  int l = (int)fmax(a, 0.0), h = (int)fmin(b, (double)dim - 1.0);   // NaN -> the whole axis; the neighbourhood cut below bounds it
-  l = max(l, max(idx_lo(p, ax, gc - 1, dim), cut_lo));
-  h = min(h, min(idx_lo(p, ax, gc + 2, dim), cut_hi) - 1);
+  // 1e-3 of a lattice step covers the rounding of lat_pos against this double computation (and R carries a 1 % margin)
+  const double a = ceil(((double)c - (double)R - (double)p.fcmin[ax]) / (double)p.dr - 1e-3);
+  const double b = floor(((double)c + (double)R - (double)p.fcmin[ax]) / (double)p.dr + 1e-3);
+  int l, h;
+  if (a >= -1e9 && b <= 1e9) {   // the usual case: a handful of cells (the neighbourhood rule is applied per cell, nb_axis)
+    l = max((int)fmax(a, 0.0), cut_lo);
+    h = min((int)fmin(b, (double)dim - 1.0), cut_hi - 1);
+  } else {                       // non-finite geometry: whatever the reference's arithmetic makes of it, inside the neighbourhood
+    l = max(idx_lo(p, ax, gc - 1, dim), cut_lo);
+    h = min(idx_lo(p, ax, gc + 2, dim), cut_hi) - 1;
+  }
   *lo = l; *hi = h;
 }
 
@@ -510,103 +516,206 @@ __device__ __forceinline__ void block_dirs(const FillArgs &A, int si, int sj, in
     if (got >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
 }
 
-__global__ void __launch_bounds__(128) k_resolve_records(const __grid_constant__ FillArgs A)
+// load the part of a record the filters need
+__device__ __forceinline__ RecView load_rec(const FillArgs &A, int64_t i)
+{
+  const float4 *r = A.rec + i * FREC;
+  const float4 R0 = __ldg(r), R1 = __ldg(r + 1);
+  RecView T;
+  T.n = mk3(R0); T.v0 = mk3(R1); T.flag = R0.w; T.idx = i;
+  T.rad = R0.w == 2.f ? 1.01f * (1.0f + 3.0f * A.p.eps) * sqrtf(fmaxf(R1.w, __ldg(r + 3).w)) : 0.f;
+  const int c = __float_as_int(__ldg(r + 5).w);
+  T.g[2] = c % A.p.gridn[2]; T.g[1] = (c / A.p.gridn[2]) % A.p.gridn[1]; T.g[0] = c / (A.p.gridn[2] * A.p.gridn[1]);
+  return T;
+}
+
+// the "ray in plane" rule for one (cell, segment) pair and the directions in cand, exactly (crixus_d.cu:855-857 + :757-769): the
+// influence-radius test of the direction, then |b| < eps and |a| < eps
+__device__ __forceinline__ uint32_t inplane_exact(const FillArgs &A, const RecView &T, int si, int sj, int sk, uint32_t cand)
 {
   const cx_params &p = A.p;
+  const float eps = p.eps, dr = p.dr;
+  const int sidx[3] = {si, sj, sk};
+  const float sc[3] = {lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk)};
+  const f3 s = mk3(sc[0], sc[1], sc[2]);
+  const float a = -dot3_r3(T.n, sub3(s, T.v0));
+  if (!(fabsf(a) < eps)) return 0;
+  uint32_t got = 0;
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    if (!(cand >> d & 1)) continue;
+    const int ax = d >> 1;
+    const float ec = lat_pos(p, ax, sidx[ax] + ((d & 1) ? 1 : -1));
+    const float dc = fsub(ec, sc[ax]);
+    const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
+    if (!(fabsf(dot3_r3(T.n, dir)) < eps)) continue;
+    const float hd = fmul(fsub(sc[ax], ec), 0.5f);
+    const f3 hv = mk3(ax == 0 ? hd : 0.f, ax == 1 ? hd : 0.f, ax == 2 ? hd : 0.f);
+    const float l = __fsqrt_rn(dot3_r3(hv, hv));
+    const float rr = fadd(ffma(dr, 3.0f, l), p.dr_wall);
+    const float midc = fadd(sc[ax], ec);
+    const f3 tt = mk3(ffma(ax == 0 ? midc : fadd(sc[0], sc[0]), 0.5f, -T.v0.x), ffma(ax == 1 ? midc : fadd(sc[1], sc[1]), 0.5f, -T.v0.y),
+                      ffma(ax == 2 ? midc : fadd(sc[2], sc[2]), 0.5f, -T.v0.z));
+    if (!(dot3_r3(tt, tt) > fmul(rr, rr))) got |= 1u << d;
+  }
+  return got;
+}
+
+#define RQ_WARPS 4
+#define RQ_CAP 64    // ring of candidate (segment, cell) pairs per warp
+
+// Every lane holds one segment.  The loops over its candidate cells run in lock step across the warp (trip counts = the widest
+// lane), the cheap conservative filters are evaluated by all lanes together, and the pairs that survive are appended to a
+// per-warp ring (ballot + popc).  As soon as 32 pairs wait, every lane takes one and runs the exact test: the expensive code is
+// entered by full warps at one place instead of by single lanes at 32 different loop iterations (a first, thread-per-segment
+// version with the exact test inside the loops was 8 x slower than this for that reason alone).
+__global__ void __launch_bounds__(RQ_WARPS * 32) k_resolve_records(const __grid_constant__ FillArgs A)
+{
+  __shared__ int4 sQ[RQ_WARPS][RQ_CAP];       // (segment, i, j | in-plane flag << 30, k) ; directions are recomputed
+  __shared__ unsigned char sD[RQ_WARPS][RQ_CAP];   // candidate directions of the pair
+  const cx_params &p = A.p;
+  const int lane = threadIdx.x & 31;
+  int4 *Q = sQ[threadIdx.x >> 5];
+  unsigned char *QD = sD[threadIdx.x >> 5];
   const int64_t nwall = A.nbe - A.cnbe;
   const float eps2 = 2.0f * p.eps;
-  const float radf = 1.01f * (1.0f + 3.0f * p.eps);
   const float r_infl = 1.01f * (4.0f * p.dr + p.dr_wall);   // |s - v0| of every pair that passes the influence-radius test
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nwall; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 *r = A.rec + i * FREC;
-    const float4 R0 = __ldg(r), R1 = __ldg(r + 1);
+  const float zlo = lat_pos(p, 2, A.k_lo) - r_infl - p.dr, zhi = lat_pos(p, 2, A.k_hi - 1) + r_infl + p.dr;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int qh = 0, qn = 0;   // ring head / fill (warp-uniform)
+  auto drain = [&](int take) {
+    if (lane < take) {
+      const int slot = (qh + lane) & (RQ_CAP - 1);
+      const int4 e = Q[slot];
+      const uint32_t cand = QD[slot];
+      const RecView T = load_rec(A, e.x);
+      const int sj = e.z & 0x3fffffff;
+      const uint32_t got = (e.z >> 30) ? inplane_exact(A, T, e.y, sj, e.w, cand) : pair_exact(A, T, e.y, sj, e.w, cand);
+      if (got) block_dirs(A, e.y, sj, e.w, got);
+    }
+    qh = (qh + take) & (RQ_CAP - 1);
+    qn -= take;
+    __syncwarp();
+  };
+  auto push = [&](bool c, int64_t idx, int si, int sj, int sk, uint32_t cand, int inpl) {
+    const unsigned bal = __ballot_sync(0xffffffffu, c);
+    if (!bal) return;
+    if (c) {
+      const int slot = (qh + qn + __popc(bal & ((1u << lane) - 1u))) & (RQ_CAP - 1);
+      Q[slot] = make_int4((int)idx, si, sj | (inpl << 30), sk);
+      QD[slot] = (unsigned char)cand;
+    }
+    qn += __popc(bal);
+    __syncwarp();
+    if (qn >= 32) drain(32);
+  };
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nwall; base += nwarp * 32) {
+    const int64_t i = base + lane;
+    bool valid = i < nwall;
     RecView T;
-    T.n = mk3(R0); T.v0 = mk3(R1); T.flag = R0.w; T.idx = i; T.rad = 0.f;
-    // quick exit for segments far from this rank's planes (z-slab ownership): nothing beyond r_infl of v0 is touched
-    {
-      const float zlo = lat_pos(p, 2, A.k_lo) - r_infl - p.dr, zhi = lat_pos(p, 2, A.k_hi - 1) + r_infl + p.dr;
-      if (T.v0.z < zlo || T.v0.z > zhi) continue;   // (NaN falls through)
+    T.n = mk3(0.f, 0.f, 1.f); T.v0 = mk3(0.f, 0.f, 0.f); T.flag = 0.f; T.rad = 0.f; T.idx = 0; T.g[0] = T.g[1] = T.g[2] = 0;
+    if (valid) {
+      T = load_rec(A, i);
+      if (T.v0.z < zlo || T.v0.z > zhi) valid = false;   // far from this rank's planes (NaN falls through)
     }
-    {
-      const int c = __float_as_int(__ldg(r + 5).w);
-      T.g[2] = c % p.gridn[2]; T.g[1] = (c / p.gridn[2]) % p.gridn[1]; T.g[0] = c / (p.gridn[2] * p.gridn[1]);
-    }
+    if (!__any_sync(0xffffffffu, valid)) continue;
     const bool wf = T.flag != 0.f;
     const bool tight = T.flag == 2.f && A.dist_dead && !A.nofilter;   // only the segment test, and it needs a hit inside the sphere
-    if (T.flag == 2.f) T.rad = radf * sqrtf(fmaxf(R1.w, __ldg(r + 3).w));
     // ---- main pass: cells within reach of a hit (tight) or within the influence radius
     const float rm = tight ? T.rad + A.lstep : r_infl;
-    int lo[3], hi[3];
-    axis_range(p, 0, T.v0.x, rm, T.g[0], 0, A.dimg[0], A.dimg[0], &lo[0], &hi[0]);
-    axis_range(p, 1, T.v0.y, rm, T.g[1], 0, A.dimg[1], A.dimg[1], &lo[1], &hi[1]);
-    axis_range(p, 2, T.v0.z, rm, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &lo[2], &hi[2]);
-    for (int sk = lo[2]; sk <= hi[2]; sk++) {
-      const float sz = lat_pos(p, 2, sk), wz = sz - T.v0.z;
-      if (!nb_axis(p, 2, lat_cell(p, 2, sk), T.g[2])) continue;
-      for (int sj = lo[1]; sj <= hi[1]; sj++) {
-        const float sy = lat_pos(p, 1, sj), wy = sy - T.v0.y;
-        if (!nb_axis(p, 1, lat_cell(p, 1, sj), T.g[1])) continue;
-        const float wyz2 = wy * wy + wz * wz, ayz = wy * T.n.y + wz * T.n.z;
-        if (tight && wyz2 > rm * rm) continue;
-        for (int si = lo[0]; si <= hi[0]; si++) {
-          const float sx = lat_pos(p, 0, si), wx = sx - T.v0.x;
-          const float aa = fabsf(wx * T.n.x + ayz);   // approximate plane distance: every threshold below has slack for its rounding
-          if (wf && aa > A.rrej * 1.001f) continue;
-          if (tight && (wx * wx + wyz2 > rm * rm || (aa > A.lstep && aa >= eps2))) continue;
-          if (!nb_axis(p, 0, lat_cell(p, 0, si), T.g[0])) continue;
-          const uint32_t got = pair_exact(A, T, si, sj, sk, cell_dirs(A, si, sj, sk));
-          if (got) block_dirs(A, si, sj, sk, got);
+    int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
+    if (valid) {
+      axis_range(p, 0, T.v0.x, rm, T.g[0], 0, A.dimg[0], A.dimg[0], &lo[0], &hi[0]);
+      axis_range(p, 1, T.v0.y, rm, T.g[1], 0, A.dimg[1], A.dimg[1], &lo[1], &hi[1]);
+      axis_range(p, 2, T.v0.z, rm, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &lo[2], &hi[2]);
+    }
+    const int n0 = __reduce_max_sync(0xffffffffu, hi[0] - lo[0] + 1), n1 = __reduce_max_sync(0xffffffffu, hi[1] - lo[1] + 1),
+              n2 = __reduce_max_sync(0xffffffffu, hi[2] - lo[2] + 1);
+    if (n0 > 0 && n1 > 0 && n2 > 0)
+      for (int tk = 0; tk < n2; tk++) {
+        const int sk = lo[2] + tk;
+        const float wz = lat_pos(p, 2, sk) - T.v0.z;
+        const bool okk = sk <= hi[2] && nb_axis(p, 2, lat_cell(p, 2, sk), T.g[2]);
+        for (int tj = 0; tj < n1; tj++) {
+          const int sj = lo[1] + tj;
+          const float wy = lat_pos(p, 1, sj) - T.v0.y;
+          const float wyz2 = wy * wy + wz * wz, ayz = wy * T.n.y + wz * T.n.z;
+          const bool okj = okk && sj <= hi[1] && !(tight && wyz2 > rm * rm) && nb_axis(p, 1, lat_cell(p, 1, sj), T.g[1]);
+          if (!__any_sync(0xffffffffu, okj)) continue;
+          for (int ti = 0; ti < n0; ti++) {
+            const int si = lo[0] + ti;
+            bool c = okj && si <= hi[0];
+            if (c) {
+              const float wx = lat_pos(p, 0, si) - T.v0.x;
+              const float aa = fabsf(wx * T.n.x + ayz);   // approximate plane distance: every threshold below has slack for its rounding
+              c = !(wf && aa > A.rrej * 1.001f) && !(tight && (wx * wx + wyz2 > rm * rm || (aa > A.lstep && aa >= eps2))) &&
+                  nb_axis(p, 0, lat_cell(p, 0, si), T.g[0]);
+            }
+            push(c, i, si, sj, sk, c ? cell_dirs(A, si, sj, sk) : 0u, 0);
+          }
         }
       }
-    }
     // ---- in-plane pass (tight records only; otherwise the main pass already covered the influence ball): cells within 2 eps of
     // the triangle's plane collide along every axis that is parallel to the plane within eps, whatever the triangle's extent
     // (crixus_d.cu:766-769) -- as far as the influence radius reaches.  For every pair of indices along the two axes with the
     // smaller normal components, the index along the third follows from the plane equation.
-    if (!tight) continue;
-    const uint32_t capable = (fabsf(T.n.x) * A.lstep < eps2 ? 3u : 0u) | (fabsf(T.n.y) * A.lstep < eps2 ? 12u : 0u) |
-                             (fabsf(T.n.z) * A.lstep < eps2 ? 48u : 0u);
-    if (!capable) continue;
+    const uint32_t capable = !(valid && tight) ? 0u : ((fabsf(T.n.x) * A.lstep < eps2 ? 3u : 0u) | (fabsf(T.n.y) * A.lstep < eps2 ? 12u : 0u) |
+                                                       (fabsf(T.n.z) * A.lstep < eps2 ? 48u : 0u));
+    if (!__any_sync(0xffffffffu, capable != 0u)) continue;
     const int m = (fabsf(T.n.x) >= fabsf(T.n.y) && fabsf(T.n.x) >= fabsf(T.n.z)) ? 0 : (fabsf(T.n.y) >= fabsf(T.n.z) ? 1 : 2);
     const int u = (m + 1) % 3, v = (m + 2) % 3;
     const float nm = comp(T.n, m), nu = comp(T.n, u), nv = comp(T.n, v);
     const float v0m = comp(T.v0, m), v0u = comp(T.v0, u), v0v = comp(T.v0, v);
-    int plo[3], phi[3];
-    axis_range(p, 0, T.v0.x, r_infl, T.g[0], 0, A.dimg[0], A.dimg[0], &plo[0], &phi[0]);
-    axis_range(p, 1, T.v0.y, r_infl, T.g[1], 0, A.dimg[1], A.dimg[1], &plo[1], &phi[1]);
-    axis_range(p, 2, T.v0.z, r_infl, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &plo[2], &phi[2]);
-    for (int iu = plo[u]; iu <= phi[u]; iu++) {
+    int plo[3] = {0, 0, 0}, phi[3] = {-1, -1, -1};
+    if (capable) {
+      axis_range(p, 0, T.v0.x, r_infl, T.g[0], 0, A.dimg[0], A.dimg[0], &plo[0], &phi[0]);
+      axis_range(p, 1, T.v0.y, r_infl, T.g[1], 0, A.dimg[1], A.dimg[1], &plo[1], &phi[1]);
+      axis_range(p, 2, T.v0.z, r_infl, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &plo[2], &phi[2]);
+    }
+    const int ulo = plo[u], uhi = phi[u], vlo = plo[v], vhi = phi[v], mlo = plo[m], mhi = phi[m];
+    const int nu_ = __reduce_max_sync(0xffffffffu, uhi - ulo + 1), nv_ = __reduce_max_sync(0xffffffffu, vhi - vlo + 1);
+    if (nu_ <= 0 || nv_ <= 0) continue;
+    for (int tu = 0; tu < nu_; tu++) {
+      const int iu = ulo + tu;
       const float wu = lat_pos(p, u, iu) - v0u;
-      if (!nb_axis(p, u, lat_cell(p, u, iu), T.g[u])) continue;
-      for (int iv = plo[v]; iv <= phi[v]; iv++) {
+      const bool oku = capable && iu <= uhi && mhi >= mlo && nb_axis(p, u, lat_cell(p, u, iu), T.g[u]);
+      if (!__any_sync(0xffffffffu, oku)) continue;
+      for (int tv = 0; tv < nv_; tv++) {
+        const int iv = vlo + tv;
         const float wv = lat_pos(p, v, iv) - v0v;
-        if (wu * wu + wv * wv > r_infl * r_infl) continue;
+        const bool okv = oku && iv <= vhi && !(wu * wu + wv * wv > r_infl * r_infl);
         // n.(s - v0) = 0  ->  coordinate along m, and the two lattice indices around it
         const float tm = (v0m - (nu * wu + nv * wv) / nm - p.fcmin[m]) / p.dr;
-        if (!(tm > -2.0f && tm < (float)A.dimg[m] + 1.0f)) continue;
-        const int im0 = (int)floorf(tm);
-        for (int im = max(im0, plo[m]); im <= min(im0 + 1, phi[m]); im++) {
-          const float wm = lat_pos(p, m, im) - v0m;
-          if (fabsf(nm * wm + nu * wu + nv * wv) >= eps2) continue;
-          const float w2 = wm * wm + wu * wu + wv * wv;
-          if (w2 > r_infl * r_infl || w2 <= rm * rm) continue;     // beyond the influence radius / already done by the main pass
-          if (!nb_axis(p, m, lat_cell(p, m, im), T.g[m])) continue;
-          int idx[3];
-          idx[m] = im; idx[u] = iu; idx[v] = iv;
-          uint32_t cand = capable & cell_dirs(A, idx[0], idx[1], idx[2]);
-          // directions that an earlier segment already blocked need no test (a stale read only costs a repeated test)
-          const int64_t wi = ((int64_t)idx[2] * A.dimg[1] + idx[1]) * A.wr + (idx[0] >> 5);
-          const uint32_t bit = 1u << (idx[0] & 31);
+        const int im0 = (okv && tm > -2.0f && tm < (float)A.dimg[m] + 1.0f) ? (int)floorf(tm) : -0x40000000;
 #pragma unroll
-          for (int d = 0; d < 6; d++)
-            if ((cand >> d & 1) && (__ldcg(&A.B[d * A.nw + wi]) & bit)) cand &= ~(1u << d);
-          if (!cand) continue;
-          const uint32_t got = pair_full(A, idx[0], idx[1], idx[2], T.idx, cand);
-          if (got) block_dirs(A, idx[0], idx[1], idx[2], got);
+        for (int q = 0; q < 2; q++) {
+          const int im = im0 + q;
+          bool c = okv && im >= mlo && im <= mhi;
+          uint32_t cand = 0;
+          int idx[3] = {0, 0, 0};
+          if (c) {
+            const float wm = lat_pos(p, m, im) - v0m;
+            const float w2 = wm * wm + wu * wu + wv * wv;
+            c = fabsf(nm * wm + nu * wu + nv * wv) < eps2 && !(w2 > r_infl * r_infl) && !(w2 <= rm * rm) &&   // main pass did the inner ball
+                nb_axis(p, m, lat_cell(p, m, im), T.g[m]);
+            if (c) {
+              idx[m] = im; idx[u] = iu; idx[v] = iv;
+              cand = capable & cell_dirs(A, idx[0], idx[1], idx[2]);
+              // directions that an earlier segment already blocked need no test (a stale read only costs a repeated test)
+              const int64_t wi = ((int64_t)idx[2] * A.dimg[1] + idx[1]) * A.wr + (idx[0] >> 5);
+              const uint32_t bit = 1u << (idx[0] & 31);
+#pragma unroll
+              for (int d = 0; d < 6; d++)
+                if ((cand >> d & 1) && (__ldcg(&A.B[d * A.nw + wi]) & bit)) cand &= ~(1u << d);
+              c = cand != 0u;
+            }
+          }
+          push(c, i, idx[0], idx[1], idx[2], cand, 1);
         }
       }
     }
   }
+  if (qn > 0) drain(qn);
 }
 
 // free-surface triangles: all of them against every lattice cell, segment test only, no cell lookup (crixus_d.cu:951-960).
@@ -932,7 +1041,7 @@ static int fill_resolve(cx_ctx *ctx, FillArgs *A)
   if (A->k_hi <= A->k_lo) return CX_OK;
   const int64_t nwall = A->nbe - A->cnbe;
   if (nwall > 0) {
-    k_resolve_records<<<cx_blocks(nwall, 128, ctx->num_sms * 64), 128, 0, st>>>(*A);
+    k_resolve_records<<<cx_blocks(nwall, RQ_WARPS * 32, ctx->num_sms * 16), RQ_WARPS * 32, 0, st>>>(*A);
     CX_LAUNCH_CHECK(ctx, "k_resolve_records");
   }
   if (A->cnbe > 0) {

@@ -147,6 +147,90 @@ def test_h5sph_writer_against_independent_parser(n, tmp_path, cxlib):
     assert info["data_address"] % 8 == 0
 
 
+def test_h5sph_bytes_field_by_field_against_the_format_specification(tmp_path, cxlib):
+    """A second, parser-free check of the hand-written HDF5 writer: every metadata field of a 2-record file at its byte offset,
+    with the value the HDF5 File Format Specification (version 2.0, superblock version 0) prescribes -- section numbers below.
+    (No libhdf5 / h5py in this image; tests/h5mini.py is the structural reader, this is the hex-level one.)"""
+    import struct
+    rec = _records(2, seed=5)
+    path = str(tmp_path / "0.two.h5sph")
+    assert cxlib.cx_write_h5sph_records(rec.ctypes.data, 2, path.encode()) == 0
+    b = open(path, "rb").read()
+    u8 = lambda o: b[o]                                     # noqa: E731
+    u16 = lambda o: struct.unpack_from("<H", b, o)[0]       # noqa: E731
+    u32 = lambda o: struct.unpack_from("<I", b, o)[0]       # noqa: E731
+    u64 = lambda o: struct.unpack_from("<Q", b, o)[0]       # noqa: E731
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    # II.A superblock, version 0
+    assert b[0:8] == bytes([0x89]) + b"HDF\r\n\x1a\n"                          # format signature
+    assert [u8(8), u8(9), u8(10), u8(11), u8(12)] == [0, 0, 0, 0, 0]           # versions: superblock, free space, root group, reserved, shared header
+    assert (u8(13), u8(14), u8(15)) == (8, 8, 0)                                # size of offsets, size of lengths, reserved
+    assert (u16(16), u16(18)) == (4, 16)                                        # group leaf node K, group internal node K
+    assert u32(20) == 0                                                         # file consistency flags
+    assert u64(24) == 0 and u64(32) == UNDEF and u64(48) == UNDEF               # base address, free-space info, driver info
+    assert u64(40) == len(b)                                                    # end-of-file address
+    # root group symbol table entry (III.C): link name offset, object header address, cache type 1, scratch = B-tree + heap addresses
+    root_hdr, btree, heap = u64(64), u64(80), u64(88)
+    assert u64(56) == 0 and u32(72) == 1 and u32(76) == 0
+    # IV.A.1.a root object header, version 1: one message of type 0x0011 (symbol table) carrying the same two addresses
+    assert (u8(root_hdr), u16(root_hdr + 2), u32(root_hdr + 4)) == (1, 1, 1)
+    assert u16(root_hdr + 16) == 0x0011 and u16(root_hdr + 18) == 16
+    assert (u64(root_hdr + 24), u64(root_hdr + 32)) == (btree, heap)
+    # III.D local heap: signature, version, data segment size, free-list head, data address; the name lives at offset 8
+    assert b[heap:heap + 4] == b"HEAP" and u8(heap + 4) == 0
+    heap_data = u64(heap + 24)
+    assert b[heap_data + 8:heap_data + 17] == b"Compound\0"                     # dataset name (src/crixus.h:21)
+    free = u64(heap + 16)
+    assert u64(heap_data + free) == 1 and u64(heap_data + free + 8) == u64(heap + 8) - free   # one free block: next = 1 (none), size = the rest
+    # III.A.1 version-1 B-tree node: group node (type 0), leaf (level 0), one entry, no siblings, key 1 = heap offset of the largest name
+    assert b[btree:btree + 4] == b"TREE" and (u8(btree + 4), u8(btree + 5), u16(btree + 6)) == (0, 0, 1)
+    assert u64(btree + 8) == UNDEF and u64(btree + 16) == UNDEF
+    snod = u64(btree + 32)
+    assert u64(btree + 24) == 0 and u64(btree + 40) == 8
+    # III.B symbol table node: version 1, one symbol; its entry: name offset 8, object header address, cache type 0
+    assert b[snod:snod + 4] == b"SNOD" and (u8(snod + 4), u16(snod + 6)) == (1, 1)
+    dset = u64(snod + 16)
+    assert u64(snod + 8) == 8 and u32(snod + 24) == 0
+    # dataset object header, version 1, four messages: dataspace 0x0001, datatype 0x0003, fill value 0x0005, layout 0x0008
+    assert (u8(dset), u16(dset + 2), u32(dset + 4)) == (1, 4, 1)
+    o, seen = dset + 16, {}
+    for _ in range(4):
+        t, sz = u16(o), u16(o + 2)
+        seen[t] = o + 8
+        o += 8 + sz
+        assert sz % 8 == 0                                                      # version-1 messages are 8-byte aligned
+    assert o - (dset + 16) == u32(dset + 8)                                     # object header size
+    assert sorted(seen) == [0x0001, 0x0003, 0x0005, 0x0008]
+    sp = seen[0x0001]                                                           # IV.A.2.b dataspace v1: rank 1, no max dims, dim = 2
+    assert (u8(sp), u8(sp + 1), u8(sp + 2)) == (1, 1, 0) and u64(sp + 8) == 2
+    ty = seen[0x0003]                                                           # IV.A.2.d datatype: class 6 (compound) version 1, 16 members, 64 bytes
+    assert u8(ty) == 0x16 and (u8(ty + 1) | u8(ty + 2) << 8) == 16 and u32(ty + 4) == 64
+    m = ty + 8
+    for i, name in enumerate(H5_NAMES):
+        n = len(name) + 1
+        assert b[m:m + n] == name.encode() + b"\0"
+        m += (n + 7) & ~7                                                       # name padded to a multiple of 8
+        assert u32(m) == 4 * i                                                  # byte offset of the member
+        assert u8(m + 4) == 0                                                   # dimensionality
+        m += 4 + 4 + 4 + 4 + 16                                                 # offset, dim/reserved, permutation, reserved, 4 dimension sizes
+        cls, bits0, size = u8(m) & 0x0F, u8(m + 1), u32(m + 4)
+        assert size == 4
+        if i < 8:    # class 1 floating point, little endian, IEEE: bit offset 0, precision 32, exponent at 23 (8 bits), mantissa at 0 (23 bits), bias 127
+            assert cls == 1 and bits0 & 1 == 0
+            assert (u16(m + 8), u16(m + 10), u8(m + 12), u8(m + 13), u8(m + 14), u8(m + 15), u32(m + 16)) == (0, 32, 23, 8, 0, 23, 127)
+            assert (u8(m + 1) >> 4) & 3 == 2 and u8(m + 2) == 31             # mantissa normalisation: implied leading 1; sign bit at 31
+            m += 8 + 12
+        else:        # class 0 fixed point, little endian, two's complement (signed): bit offset 0, precision 32
+            assert cls == 0 and bits0 & 1 == 0 and bits0 & 8 == 8
+            assert (u16(m + 8), u16(m + 10)) == (0, 32)
+            m += 8 + 4
+    la = seen[0x0008]                                                           # IV.A.2.i data layout v3, class 1 (contiguous): address, size
+    assert (u8(la), u8(la + 1)) == (3, 1)
+    data, size = u64(la + 2), u64(la + 10)
+    assert size == 2 * 64 and data + size == len(b) and data % 8 == 0
+    assert b[data:] == rec.tobytes()                                            # the records, verbatim (src/crixus.cpp:40-57)
+
+
 def test_h5mini_rejects_corruption(tmp_path, cxlib):
     import h5mini
     rec = _records(3)

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Per-kernel SASS instruction mix of crixus_b200/libcrixus_b200.so (cuobjdump -sass), written to profiles/:
+
+    python tools/sass_summary.py > profiles/r02_sass_summary.txt
+
+States which Blackwell-specific data-movement / tensor instructions occur (UTMALDG/UTMASTG/UBLKCP = TMA, SYNCS = mbarrier,
+UTCMMA/UTCBAR = tcgen05, LDGSTS = cp.async) -- none: every kernel on this path is an irregular integer / fp32 SIMT kernel
+(gather by index, bit arithmetic, threshold searches); there is no dense tile to stage and no contraction to hand to tensor cores."""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "crixus_b200", "libcrixus_b200.so")
+SPECIAL = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "UTCMMA", "UTCBAR", "LDGSTS", "HMMA", "IMMA", "REDUX", "MATCH", "VOTE", "SHFL", "ATOMG", "ATOMS", "REDG", "RED", "ATOM")
+
+
+def main():
+    txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    kernels, cur = collections.OrderedDict(), None
+    for line in txt.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = collections.Counter()
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            kernels[cur][m.group(1)] += 1
+    dem = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
+    print("# SASS instruction mix per kernel, sm_100a, %s" % os.path.relpath(LIB, ROOT))
+    print("# columns: total instructions | FP32 (FFMA FMUL FADD FSETP FMNMX MUFU) | FP64 (D*) | integer/logic | LDG/STG | LDS/STS | LDL/STL | control (BRA BSSY BSYNC ...)")
+    tot_special = collections.Counter()
+    for (k, c), name in zip(kernels.items(), dem):
+        n = sum(c.values())
+        fp32 = sum(v for o, v in c.items() if o in ("FFMA", "FMUL", "FADD", "FSETP", "FMNMX", "MUFU", "FSEL", "FCHK"))
+        fp64 = sum(v for o, v in c.items() if o.startswith("D") and o not in ("DEPBAR",))
+        integer = sum(v for o, v in c.items() if o in ("IMAD", "IADD3", "VIADD", "LOP3", "SHF", "ISETP", "LEA", "SEL", "PRMT", "POPC", "FLO", "IABS", "VIMNMX", "PLOP3", "I2F", "F2I", "I2FP", "F2F", "MOV", "UMOV", "UIADD3", "ULOP3", "USHF", "UISETP", "UIMAD", "ULEA", "CS2R", "S2R", "S2UR", "R2UR", "IMNMX"))
+        ldg = sum(v for o, v in c.items() if o in ("LDG", "STG", "LD", "ST"))
+        lds = sum(v for o, v in c.items() if o in ("LDS", "STS", "LDSM"))
+        ldl = sum(v for o, v in c.items() if o in ("LDL", "STL"))
+        ctl = sum(v for o, v in c.items() if o in ("BRA", "BSSY", "BSYNC", "EXIT", "RET", "CALL", "BAR", "WARPSYNC", "BREAK", "NOP", "YIELD"))
+        sp = {o: v for o, v in c.items() if o in SPECIAL}
+        tot_special.update(sp)
+        short = re.sub(r"\(.*", "", name)
+        print("%-58s %6d | %5d | %4d | %5d | %4d | %4d | %4d | %4d | %s" % (short[:58], n, fp32, fp64, integer, ldg, lds, ldl, ctl,
+                                                                           " ".join("%s=%d" % kv for kv in sorted(sp.items()))))
+    print()
+    print("# Blackwell / Hopper specific instructions over the whole library:")
+    for o in ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "UTCMMA", "UTCBAR", "LDGSTS", "HMMA", "IMMA"):
+        print("#   %-8s %d" % (o, tot_special.get(o, 0)))
+    print("# warp-collective instructions used instead: " + ", ".join("%s=%d" % (o, tot_special.get(o, 0)) for o in ("VOTE", "SHFL", "MATCH", "REDUX", "ATOMG", "ATOMS", "REDG")))
+    print("# No TMA, no mbarrier, no tcgen05, no cp.async on purpose: none of the kernels moves dense tiles.  The HBM-bound passes\n"
+          "# (set_bound_elem, binning, records, weld) are one-touch gathers/scatters of 16-byte AoS elements (LDG.128/STG.128, coalesced\n"
+          "# where the index allows); calc_vert_volume keeps its per-vertex working set (<= 8 KB: 160 B per fan triangle + mask tables)\n"
+          "# in shared memory written by the warp that computed it -- there is nothing in global memory to bulk-copy; the fill's\n"
+          "# record-driven resolve keeps ONE 80-byte record in registers per thread and touches ~100 lattice cells; the flood works on\n"
+          "# 1 x 16 x 16-word tiles (1 KB + halo) whose loads are single coalesced 4-byte words per thread.  BASELINE.json's north_star\n"
+          "# waives tensor cores for this path; its 'shared-memory/TMA-staged segment tiles' were evaluated for the fill (round-2 first\n"
+          "# version: 27-cell neighbourhoods staged per 3dr-cell in shared memory) and lost 9 x against the record-driven form, which\n"
+          "# needs no staging at all (DESIGN.md section 3.2).")
+
+
+if __name__ == "__main__":
+    main()
