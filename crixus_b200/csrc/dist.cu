@@ -21,6 +21,7 @@ struct NcclApi {
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclSend) Send = nullptr;
@@ -38,7 +39,7 @@ struct NcclApi {
       if (names[i]) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
     if (!h) { err = std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "?"); return false; }
 #define CX_SYM(n) n = (decltype(n))dlsym(h, "nccl" #n); if (!n) { err = "NCCL symbol missing: nccl" #n; h = nullptr; return false; }
-    CX_SYM(GetUniqueId) CX_SYM(CommInitRank) CX_SYM(CommDestroy) CX_SYM(AllReduce) CX_SYM(Broadcast)
+    CX_SYM(GetUniqueId) CX_SYM(CommInitRank) CX_SYM(CommDestroy) CX_SYM(AllReduce) CX_SYM(Reduce) CX_SYM(Broadcast)
     CX_SYM(AllGather) CX_SYM(Send) CX_SYM(Recv) CX_SYM(GroupStart) CX_SYM(GroupEnd) CX_SYM(GetErrorString)
 #undef CX_SYM
     return true;
@@ -66,6 +67,16 @@ struct NcclColl : CxColl {
   int allreduce_sum_u32(cx_ctx *ctx, uint32_t *buf, int64_t count) override { return allreduce(ctx, buf, count, ncclUint32); }
   int allreduce_sum_f32(cx_ctx *ctx, float *buf, int64_t count) override { return allreduce(ctx, buf, count, ncclFloat32); }
   int allreduce_sum_i64(cx_ctx *ctx, int64_t *buf, int64_t count) override { return allreduce(ctx, buf, count, ncclInt64); }
+  int reduce_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) override
+  {
+    CX_NCCL(ctx, g_nccl.GroupStart());
+    for (int i = 0; i < nseg; i++)
+      if (segs[i].count > 0)
+        CX_NCCL(ctx, g_nccl.Reduce(base + segs[i].offset, base + segs[i].offset, (size_t)segs[i].count, ncclUint32, ncclSum, segs[i].root,
+                                   comm, ctx->stream));
+    CX_NCCL(ctx, g_nccl.GroupEnd());
+    return CX_OK;
+  }
   int bcast_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) override
   {
     CX_NCCL(ctx, g_nccl.GroupStart());
@@ -164,6 +175,19 @@ struct LocalColl : CxColl {
   int allreduce_sum_u32(cx_ctx *ctx, uint32_t *buf, int64_t count) override { return allreduce(ctx, buf, count); }
   int allreduce_sum_f32(cx_ctx *ctx, float *buf, int64_t count) override { return allreduce(ctx, buf, count); }
   int allreduce_sum_i64(cx_ctx *ctx, int64_t *buf, int64_t count) override { return allreduce(ctx, (long long *)buf, count); }
+  int reduce_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) override
+  {
+    CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    g->slot[rank][0] = base;
+    g->barrier();
+    for (int i = 0; i < nseg; i++)   // the root's own segment is read and written element by element by the same thread
+      if (segs[i].root == rank && segs[i].count > 0)
+        k_local_sum<uint32_t><<<cx_blocks(segs[i].count, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(gather(base), base + segs[i].offset,
+                                                                                                         segs[i].offset, segs[i].count);
+    CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    g->barrier();
+    return CX_OK;
+  }
   int bcast_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) override
   {
     CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

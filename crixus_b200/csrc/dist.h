@@ -1,5 +1,5 @@
 // crixus_b200 -- collective layer of the multi-GPU path (library-internal).
-// One rank = one cx_ctx = one GPU.  Two back-ends behind the same operations:
+// One rank = one cx_ctx = one GPU.  Two back-ends behind the same five operations:
 //   * NCCL (one process per GPU, NVLink / NVSwitch): resolved with dlopen("libnccl.so.2") when a communicator is created, so
 //     the library has no link-time NCCL dependency;
 //   * local: N contexts inside ONE process, one host thread per rank, buffers exchanged by peer pointers (same device or
@@ -21,6 +21,8 @@ struct CxColl {
   virtual int allreduce_sum_u32(cx_ctx *ctx, uint32_t *buf, int64_t count) = 0;
   virtual int allreduce_sum_f32(cx_ctx *ctx, float *buf, int64_t count) = 0;
   virtual int allreduce_sum_i64(cx_ctx *ctx, int64_t *buf, int64_t count) = 0;
+  // for every segment: base[offset .. offset+count) of rank `root` = sum over ranks of the same range (other ranks keep theirs)
+  virtual int reduce_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) = 0;
   // for every segment: base[offset .. offset+count) of every rank = the same range of rank `root` (an all-gather with unequal parts)
   virtual int bcast_segments_u32(cx_ctx *ctx, uint32_t *base, const CxSeg *segs, int nseg) = 0;
   // z-neighbour exchange: send `up_send` to rank+1 and `dn_send` to rank-1, receive their counterparts (count words each way;

@@ -113,11 +113,16 @@ struct FillArgs {
   uint32_t *F;       // row-aligned filled bits, wr*dimg[1]*dimg[2] words
   uint32_t *B;       // 6 blocked planes, same shape each (direction d at B + d*nw)
   int64_t nw;        // words per plane set
+  const uint8_t *nbflag;  // per 3dr-cell: 27-neighbourhood contains a segment
   const FsDesc *fs;       // fshape descriptors (cnbe of them)
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
   int32_t *count;               // [0] = list length, [1] = cursor
+  unsigned long long *count64;  // work counter of the up-front resolve
   unsigned long long *changed;  // newly set cells
+  int res_nparts, res_part;     // up-front resolve: 3dr-cell chunks dealt to nparts ranks, this rank resolves its share (0/1: all)
+  const int32_t *blist;         // work list of the up-front resolve (3dr-cells of this rank's share), nblist entries
+  long long nblist;
   int force_activate;           // first round of a call: processed tiles wake their neighbours unconditionally
   int merge;                    // k_unpack: OR into the existing row-aligned state (later slab calls)
   int64_t w_lo, w_hi;           // word range k_unpack / k_pack walk (slab calls: the owned planes, +-1 halo plane for k_unpack)
@@ -127,7 +132,7 @@ struct FillArgs {
   double one_eps;               // 1.0 + eps (double, crixus_d.cu:774)
   int dist_dead;                // eps >= dr_wall^2: the distance test `dist + eps < dr_wall^2` (crixus_d.cu:940) can never hold
   int nofilter;                 // debugging: no pre-filters, every pair inside rrej runs the reference's arithmetic
-  float lstep;                  // reach of one lattice step with the ray parameter's tolerance: 1.03 (1 + eps) dr
+  float sph2;                   // (1.01 (1 + 3 eps))^2: hit points further than sqrt(sph2 * max(uu, vv)) from v0 miss the triangle
 };
 
 // ---- the reference's directed test -------------------------------------------------------------------------------
@@ -296,6 +301,20 @@ __device__ __noinline__ uint32_t pair_full(const FillArgs &A, int si, int sj, in
 }
 
 // ---- preparation kernels ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell3_flags(cx_params p, const int32_t *__restrict__ cell_idx, uint8_t *__restrict__ flag)
+{
+  const int64_t n = p.gridn[3];
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((int64_t)p.gridn[2] * p.gridn[1]));
+    int any = 0;
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int64_t q = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
+      if (q >= 0 && cell_idx[q + 1] > cell_idx[q]) { any = 1; break; }
+    }
+    flag[c] = (uint8_t)any;
+  }
+}
+
 // packed (reference) layout -> row-aligned words; marks tiles that contain set bits as active
 __global__ void __launch_bounds__(256) k_unpack(FillArgs A, const uint32_t *__restrict__ fpos)
 {
@@ -376,15 +395,6 @@ __global__ void k_seed(FillArgs A, int64_t seed)
 }
 
 // ---- up-front resolution of the directed tests ---------------------------------------------------------------------
-// RECORD-DRIVEN: one thread per wall segment.  A segment can only influence lattice cells near it -- every test of
-// checkCollision's segment loop sits behind the influence-radius test |(s + e)/2 - v0| <= 3.5 dr + dr_wall (crixus_d.cu:855),
-// so |s - v0| <= 4 dr + dr_wall -- and for a well-conditioned triangle whose distance test is provably false the segment test
-// only reaches cells within (1 + eps) dr of its bounding sphere.  The thread keeps the record in registers, enumerates those few
-// lattice cells, applies the reference's neighbourhood rule (the segment's 3dr-cell must be one of the 27 around the cell's) and
-// exact, division-free pre-filters, and runs the reference's arithmetic (pair_full) on what is left.  Compared with a cell-driven
-// search (every lattice cell against the ~650 records of its 27 cells) this evaluates ~100 pairs per segment instead of ~650 per
-// cell: 15 x fewer pair tests at BASELINE configs[3], and no staging.
-
 // smallest lattice index i in [0, dim] whose 3dr-cell coordinate along `axis` is >= g (dim if there is none).  The cell
 // coordinate is a monotone function of i (every operation of lat_cell is correctly rounded and monotone): binary search.
 __device__ int idx_lo(const cx_params &p, int axis, int g, int dim)
@@ -399,16 +409,34 @@ __device__ int idx_lo(const cx_params &p, int axis, int g, int dim)
   return lo;
 }
 
-// the 3dr-cell of every segment (the cell the BINNING put it in: cell_idx is the authority, not a recomputed barycentre),
-// stored in the unused .w of record slot 5: one thread per 3dr-cell walks its run of segments
-__global__ void __launch_bounds__(256) k_seg_cells(cx_params p, const int32_t *__restrict__ cell_idx, int64_t nwall, float4 *__restrict__ rec)
+// which rank resolves the 3dr-cells of chunk `chunk` (32 consecutive cells): every group of nparts chunks is dealt one chunk
+// per rank, the order rotated by a hash of the group (walls are planes of the cell grid: plain round-robin would be periodic
+// in them).  The same function on every rank, so the shares are disjoint and complete.
+__device__ __forceinline__ int chunk_owner(long long chunk, int nparts)
 {
-  const int64_t n = p.gridn[3];
-  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
-    const int b = cell_idx[c], e = cell_idx[c + 1];
-    for (int64_t i = b; i < e && i < nwall; i++) rec[i * FREC + 5].w = __int_as_float((int)c);
-  }
+  const long long g = chunk / nparts;
+  const int slot = (int)(chunk - g * nparts);
+  const int rot = (int)((((unsigned)g * 2654435761u) >> 16) % (unsigned)nparts);
+  return (slot + nparts - rot) % nparts;
 }
+
+#define RB_WARPS 8
+#define RB_CAP 96    // staged records per warp (phase 1 appends up to 32 per step and flushes above RB_CAP - 32)
+#define RB_QUEUE 64  // ring of candidate (cell, record) pairs per warp
+
+// per-warp working set of k_resolve_blocks
+struct RBWarp {
+  float4 R0[RB_CAP], R1[RB_CAP];   // (n, flags) and (v0, uu) of the staged records
+  int idx[RB_CAP];                 // record index
+  float rad[RB_CAP];               // bounding radius of the accepted barycentric region around v0 (well-conditioned records)
+  unsigned short queue[RB_QUEUE];  // candidate pairs: (cell << 8) | staged slot
+  uint32_t coll[64];               // blocked directions per lattice cell of the sub-block
+};
+
+// geometry of a sub-block of lattice cells: cell q = (i0 + q % nx, j0 + (q / nx) % ny, k0 + q / (nx ny)), q < nx ny nz <= 64
+struct RBSub {
+  int i0, j0, k0, nx, ny, nz;
+};
 
 __device__ __forceinline__ uint32_t cell_dirs(const FillArgs &A, int si, int sj, int sk)
 {
@@ -416,58 +444,24 @@ __device__ __forceinline__ uint32_t cell_dirs(const FillArgs &A, int si, int sj,
          (sk + 1 < A.dimg[2] ? 32u : 0u);
 }
 
-// the reference looks a segment up only from lattice cells whose 3dr-cell has the segment's cell among its 27 neighbours
-// (crixus_d.cu:822-846, periodic wrap per axis, no wrap otherwise): per axis the cell coordinates differ by at most one, or
-// sit at the two ends of a periodic axis
-__device__ __forceinline__ bool nb_axis(const cx_params &p, int ax, int gs, int gc)
-{
-  const int d = gc - gs;
-  if (d >= -1 && d <= 1) return true;
-  return p.per[ax] && ((gs == 0 && gc == p.gridn[ax] - 1) || (gs == p.gridn[ax] - 1 && gc == 0));
-}
-
-// lattice index range [lo, hi] (inclusive) of the cells whose coordinate along ax can lie in [c - R, c + R], cut to the cells
-// whose 3dr-cell coordinate is within one of gc (the wrapped neighbours of a periodic axis are a domain length away: beyond
-// every radius used here) and to [cut_lo, cut_hi)
-__device__ __forceinline__ void axis_range(const cx_params &p, int ax, float c, float R, int gc, int cut_lo, int cut_hi, int dim, int *lo, int *hi)
-{
-  // 1e-3 of a lattice step covers the rounding of lat_pos against this double computation (and R carries a 1 % margin)
-  const double a = ceil(((double)c - (double)R - (double)p.fcmin[ax]) / (double)p.dr - 1e-3);
-  const double b = floor(((double)c + (double)R - (double)p.fcmin[ax]) / (double)p.dr + 1e-3);
-  int l, h;
-  if (a >= -1e9 && b <= 1e9) {   // the usual case: a handful of cells (the neighbourhood rule is applied per cell, nb_axis)
-    l = max((int)fmax(a, 0.0), cut_lo);
-    h = min((int)fmin(b, (double)dim - 1.0), cut_hi - 1);
-  } else {                       // non-finite geometry: whatever the reference's arithmetic makes of it, inside the neighbourhood
-    l = max(idx_lo(p, ax, gc - 1, dim), cut_lo);
-    h = min(idx_lo(p, ax, gc + 2, dim), cut_hi) - 1;
-  }
-  *lo = l; *hi = h;
-}
-
-struct RecView {       // one segment record in registers
-  f3 n, v0;
-  float flag, rad;     // flag: 0 / 1 well-formed / 2 and well-conditioned; rad: bounding radius of the accepted barycentric region
-  int64_t idx;
-  int g[3];            // its 3dr-cell
-};
-
-// One (lattice cell, segment) pair, exactly: the directions that can collide are narrowed with exact, division-free tests, the
-// reference's arithmetic (pair_full) decides the rest.
+// One candidate (lattice cell, staged record) pair, exactly: the directions that can collide are narrowed with exact, division-
+// free tests, the reference's arithmetic (pair_full) decides the rest.
 //   With a = -n.(s - v0) and b = n.dir exactly as checkTriangleCollision computes them (crixus_d.cu:757-765), a direction along
 //   axis x can only collide if |b| < eps and |a| < eps (ray in the plane), or r = a / b lies in [-eps, 1 + eps], which needs
 //   |a| <= |n_x| |dir| (1 + eps) up to rounding; the hit point s + r dir of an accepted (t1, t2) lies within rad of v0.
-// Only for well-formed triangles (flag != 0: finite, unit normal perpendicular to the edges) whose distance test is provably
+// Only for well-formed triangles (R0.w != 0: finite, unit normal perpendicular to the edges) whose distance test is provably
 // false; everything else takes the reference's arithmetic unfiltered.
-__device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RecView &T, int si, int sj, int sk, uint32_t need)
+__device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &W, int q, int si, int sj, int sk, uint32_t need)
 {
   const cx_params &p = A.p;
   const float eps = p.eps;
   const f3 s = mk3(lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk));
-  const f3 w0 = sub3(s, T.v0);
-  const float a = -dot3_r3(T.n, w0);
+  const float4 R0 = W.R0[q], R1 = W.R1[q];
+  const f3 n = mk3(R0), v0 = mk3(R1);
+  const f3 w0 = sub3(s, v0);
+  const float a = -dot3_r3(n, w0);
   const float aa = fabsf(a);
-  const bool wf = T.flag != 0.f;
+  const bool wf = R0.w != 0.f;
   if (wf && aa > A.rrej) return 0;   // plane-distance reject: neither test can hold
   uint32_t cand = need;
   // the distance test is alive unless eps >= dr_wall^2 or (well-formed triangle) the plane distance alone exceeds dr_wall:
@@ -476,17 +470,16 @@ __device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RecView 
     cand = 0;
     uint32_t m = need;
     const float grow = 1.0001f * (1.0f + eps);
+    const float rad = W.rad[q];
     while (m) {
       const int d = __ffs(m) - 1;
       m &= m - 1;
       const int ax = d >> 1;
-      const float nax = ax == 0 ? T.n.x : ax == 1 ? T.n.y : T.n.z;
-      if (!(aa <= fabsf(nax) * A.lstep || aa < eps)) { m &= ~(3u << (2 * ax)); continue; }   // neither direction of this axis
       const int sidx = ax == 0 ? si : ax == 1 ? sj : sk;
       const float sc = ax == 0 ? s.x : ax == 1 ? s.y : s.z;
       const float dc = fsub(lat_pos(p, ax, sidx + ((d & 1) ? 1 : -1)), sc);
       const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
-      const float b = dot3_r3(T.n, dir);
+      const float b = dot3_r3(n, dir);
       const float ab = fabsf(b);
       if (ab < eps) {
         if (aa < eps) cand |= 1u << d;   // ray in the plane: collision whatever the triangle's extent (crixus_d.cu:766-769)
@@ -494,228 +487,218 @@ __device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RecView 
       }
       const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
       if (qn > ab * grow || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
-      if (T.flag == 2.f) {
+      if (R0.w == 2.f) {
         // hit point P = s + r dir (r from a fast division: the 1 % margin of rad covers its error many times over)
         const float r = __fdividef(qn, ab);
         const float px = ax == 0 ? w0.x + r * dc : w0.x, py = ax == 1 ? w0.y + r * dc : w0.y, pz = ax == 2 ? w0.z + r * dc : w0.z;
-        if (px * px + py * py + pz * pz > T.rad * T.rad) continue;
+        if (px * px + py * py + pz * pz > rad * rad) continue;
       }
       cand |= 1u << d;
     }
     if (!cand) return 0;
   }
-  return pair_full(A, si, sj, sk, T.idx, cand);
+  return pair_full(A, si, sj, sk, W.idx[q], cand);
 }
 
-__device__ __forceinline__ void block_dirs(const FillArgs &A, int si, int sj, int sk, uint32_t got)
-{
-  const int64_t wi = ((int64_t)sk * A.dimg[1] + sj) * A.wr + (si >> 5);
-  const uint32_t bit = 1u << (si & 31);
-#pragma unroll
-  for (int d = 0; d < 6; d++)
-    if (got >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
-}
-
-// load the part of a record the filters need
-__device__ __forceinline__ RecView load_rec(const FillArgs &A, int64_t i)
-{
-  const float4 *r = A.rec + i * FREC;
-  const float4 R0 = __ldg(r), R1 = __ldg(r + 1);
-  RecView T;
-  T.n = mk3(R0); T.v0 = mk3(R1); T.flag = R0.w; T.idx = i;
-  T.rad = R0.w == 2.f ? 1.01f * (1.0f + 3.0f * A.p.eps) * sqrtf(fmaxf(R1.w, __ldg(r + 3).w)) : 0.f;
-  const int c = __float_as_int(__ldg(r + 5).w);
-  T.g[2] = c % A.p.gridn[2]; T.g[1] = (c / A.p.gridn[2]) % A.p.gridn[1]; T.g[0] = c / (A.p.gridn[2] * A.p.gridn[1]);
-  return T;
-}
-
-// the "ray in plane" rule for one (cell, segment) pair and the directions in cand, exactly (crixus_d.cu:855-857 + :757-769): the
-// influence-radius test of the direction, then |b| < eps and |a| < eps
-__device__ __forceinline__ uint32_t inplane_exact(const FillArgs &A, const RecView &T, int si, int sj, int sk, uint32_t cand)
+// the lattice cells of one sub-block against the staged records.
+//   filter: every lane holds a cell (two passes for sub-blocks of more than 32 cells) and walks the staged records with a
+//           cheap, CONSERVATIVE, warp-uniform test (approximate plane distance; for well-conditioned triangles a sphere that
+//           contains every hit point a lattice step from this cell can produce; cells in the plane keep every record while an
+//           in-plane direction is open: the "ray in plane" rule ignores the triangle's extent).  Survivors are appended to a
+//           ring of (cell, record) pairs -- ballot + popc compaction;
+//   pairs : as soon as 32 pairs wait, every lane takes one and runs the exact test (pair_exact) -- full lanes for the
+//           expensive part instead of a warp that diverges on every record.
+__device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, const RBSub &S, int cnt, int lane)
 {
   const cx_params &p = A.p;
-  const float eps = p.eps, dr = p.dr;
-  const int sidx[3] = {si, sj, sk};
-  const float sc[3] = {lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk)};
-  const f3 s = mk3(sc[0], sc[1], sc[2]);
-  const float a = -dot3_r3(T.n, sub3(s, T.v0));
-  if (!(fabsf(a) < eps)) return 0;
-  uint32_t got = 0;
-#pragma unroll
-  for (int d = 0; d < 6; d++) {
-    if (!(cand >> d & 1)) continue;
-    const int ax = d >> 1;
-    const float ec = lat_pos(p, ax, sidx[ax] + ((d & 1) ? 1 : -1));
-    const float dc = fsub(ec, sc[ax]);
-    const f3 dir = mk3(ax == 0 ? dc : 0.f, ax == 1 ? dc : 0.f, ax == 2 ? dc : 0.f);
-    if (!(fabsf(dot3_r3(T.n, dir)) < eps)) continue;
-    const float hd = fmul(fsub(sc[ax], ec), 0.5f);
-    const f3 hv = mk3(ax == 0 ? hd : 0.f, ax == 1 ? hd : 0.f, ax == 2 ? hd : 0.f);
-    const float l = __fsqrt_rn(dot3_r3(hv, hv));
-    const float rr = fadd(ffma(dr, 3.0f, l), p.dr_wall);
-    const float midc = fadd(sc[ax], ec);
-    const f3 tt = mk3(ffma(ax == 0 ? midc : fadd(sc[0], sc[0]), 0.5f, -T.v0.x), ffma(ax == 1 ? midc : fadd(sc[1], sc[1]), 0.5f, -T.v0.y),
-                      ffma(ax == 2 ? midc : fadd(sc[2], sc[2]), 0.5f, -T.v0.z));
-    if (!(dot3_r3(tt, tt) > fmul(rr, rr))) got |= 1u << d;
-  }
-  return got;
-}
-
-#define RQ_WARPS 4
-#define RQ_CAP 64    // ring of candidate (segment, cell) pairs per warp
-
-// Every lane holds one segment.  The loops over its candidate cells run in lock step across the warp (trip counts = the widest
-// lane), the cheap conservative filters are evaluated by all lanes together, and the pairs that survive are appended to a
-// per-warp ring (ballot + popc).  As soon as 32 pairs wait, every lane takes one and runs the exact test: the expensive code is
-// entered by full warps at one place instead of by single lanes at 32 different loop iterations (a first, thread-per-segment
-// version with the exact test inside the loops was 8 x slower than this for that reason alone).
-__global__ void __launch_bounds__(RQ_WARPS * 32) k_resolve_records(const __grid_constant__ FillArgs A)
-{
-  __shared__ int4 sQ[RQ_WARPS][RQ_CAP];       // (segment, i, j | in-plane flag << 30, k) ; directions are recomputed
-  __shared__ unsigned char sD[RQ_WARPS][RQ_CAP];   // candidate directions of the pair
-  const cx_params &p = A.p;
-  const int lane = threadIdx.x & 31;
-  int4 *Q = sQ[threadIdx.x >> 5];
-  unsigned char *QD = sD[threadIdx.x >> 5];
-  const int64_t nwall = A.nbe - A.cnbe;
-  const float eps2 = 2.0f * p.eps;
-  const float r_infl = 1.01f * (4.0f * p.dr + p.dr_wall);   // |s - v0| of every pair that passes the influence-radius test
-  const float zlo = lat_pos(p, 2, A.k_lo) - r_infl - p.dr, zhi = lat_pos(p, 2, A.k_hi - 1) + r_infl + p.dr;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int ncl = S.nx * S.ny * S.nz;
   int qh = 0, qn = 0;   // ring head / fill (warp-uniform)
   auto drain = [&](int take) {
-    if (lane < take) {
-      const int slot = (qh + lane) & (RQ_CAP - 1);
-      const int4 e = Q[slot];
-      const uint32_t cand = QD[slot];
-      const RecView T = load_rec(A, e.x);
-      const int sj = e.z & 0x3fffffff;
-      const uint32_t got = (e.z >> 30) ? inplane_exact(A, T, e.y, sj, e.w, cand) : pair_exact(A, T, e.y, sj, e.w, cand);
-      if (got) block_dirs(A, e.y, sj, e.w, got);
+    const bool have = lane < take;
+    if (have) {
+      const unsigned e = W.queue[(qh + lane) & (RB_QUEUE - 1)];
+      const int cell = (int)(e >> 8), q = (int)(e & 255u);
+      const int si = S.i0 + cell % S.nx, sj = S.j0 + (cell / S.nx) % S.ny, sk = S.k0 + cell / (S.nx * S.ny);
+      const uint32_t need = cell_dirs(A, si, sj, sk) & ~W.coll[cell];
+      if (need) {
+        const uint32_t got = pair_exact(A, W, q, si, sj, sk, need);
+        if (got) atomicOr(&W.coll[cell], got);
+      }
     }
-    qh = (qh + take) & (RQ_CAP - 1);
+    qh = (qh + take) & (RB_QUEUE - 1);
     qn -= take;
     __syncwarp();
   };
-  auto push = [&](bool c, int64_t idx, int si, int sj, int sk, uint32_t cand, int inpl) {
-    const unsigned bal = __ballot_sync(0xffffffffu, c);
-    if (!bal) return;
-    if (c) {
-      const int slot = (qh + qn + __popc(bal & ((1u << lane) - 1u))) & (RQ_CAP - 1);
-      Q[slot] = make_int4((int)idx, si, sj | (inpl << 30), sk);
-      QD[slot] = (unsigned char)cand;
-    }
-    qn += __popc(bal);
-    __syncwarp();
-    if (qn >= 32) drain(32);
-  };
-  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nwall; base += nwarp * 32) {
-    const int64_t i = base + lane;
-    bool valid = i < nwall;
-    RecView T;
-    T.n = mk3(0.f, 0.f, 1.f); T.v0 = mk3(0.f, 0.f, 0.f); T.flag = 0.f; T.rad = 0.f; T.idx = 0; T.g[0] = T.g[1] = T.g[2] = 0;
-    if (valid) {
-      T = load_rec(A, i);
-      if (T.v0.z < zlo || T.v0.z > zhi) valid = false;   // far from this rank's planes (NaN falls through)
-    }
-    if (!__any_sync(0xffffffffu, valid)) continue;
-    const bool wf = T.flag != 0.f;
-    const bool tight = T.flag == 2.f && A.dist_dead && !A.nofilter;   // only the segment test, and it needs a hit inside the sphere
-    // ---- main pass: cells within reach of a hit (tight) or within the influence radius
-    const float rm = tight ? T.rad + A.lstep : r_infl;
-    int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
-    if (valid) {
-      axis_range(p, 0, T.v0.x, rm, T.g[0], 0, A.dimg[0], A.dimg[0], &lo[0], &hi[0]);
-      axis_range(p, 1, T.v0.y, rm, T.g[1], 0, A.dimg[1], A.dimg[1], &lo[1], &hi[1]);
-      axis_range(p, 2, T.v0.z, rm, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &lo[2], &hi[2]);
-    }
-    const int n0 = __reduce_max_sync(0xffffffffu, hi[0] - lo[0] + 1), n1 = __reduce_max_sync(0xffffffffu, hi[1] - lo[1] + 1),
-              n2 = __reduce_max_sync(0xffffffffu, hi[2] - lo[2] + 1);
-    if (n0 > 0 && n1 > 0 && n2 > 0)
-      for (int tk = 0; tk < n2; tk++) {
-        const int sk = lo[2] + tk;
-        const float wz = lat_pos(p, 2, sk) - T.v0.z;
-        const bool okk = sk <= hi[2] && nb_axis(p, 2, lat_cell(p, 2, sk), T.g[2]);
-        for (int tj = 0; tj < n1; tj++) {
-          const int sj = lo[1] + tj;
-          const float wy = lat_pos(p, 1, sj) - T.v0.y;
-          const float wyz2 = wy * wy + wz * wz, ayz = wy * T.n.y + wz * T.n.z;
-          const bool okj = okk && sj <= hi[1] && !(tight && wyz2 > rm * rm) && nb_axis(p, 1, lat_cell(p, 1, sj), T.g[1]);
-          if (!__any_sync(0xffffffffu, okj)) continue;
-          for (int ti = 0; ti < n0; ti++) {
-            const int si = lo[0] + ti;
-            bool c = okj && si <= hi[0];
-            if (c) {
-              const float wx = lat_pos(p, 0, si) - T.v0.x;
-              const float aa = fabsf(wx * T.n.x + ayz);   // approximate plane distance: every threshold below has slack for its rounding
-              c = !(wf && aa > A.rrej * 1.001f) && !(tight && (wx * wx + wyz2 > rm * rm || (aa > A.lstep && aa >= eps2))) &&
-                  nb_axis(p, 0, lat_cell(p, 0, si), T.g[0]);
-            }
-            push(c, i, si, sj, sk, c ? cell_dirs(A, si, sj, sk) : 0u, 0);
+  for (int sl = 0; sl * 32 < ncl; sl++) {
+    const int cell = lane + 32 * sl;
+    const bool valid = cell < ncl;
+    const int si = S.i0 + (valid ? cell % S.nx : 0), sj = S.j0 + (valid ? (cell / S.nx) % S.ny : 0), sk = S.k0 + (valid ? cell / (S.nx * S.ny) : 0);
+    const uint32_t dm = valid ? cell_dirs(A, si, sj, sk) : 0u;
+    const float sx = lat_pos(p, 0, si), sy = lat_pos(p, 1, sj), sz = lat_pos(p, 2, sk);
+    // reach of a lattice step from this cell, with the tolerances of the ray parameter: (1 + eps) |dir|, 2 % on top
+    const float L = 1.02f * (1.0f + p.eps) * fmaxf(fmaxf(fabsf(lat_pos(p, 0, si + 1) - sx), fabsf(lat_pos(p, 0, si - 1) - sx)),
+                                                  fmaxf(fmaxf(fabsf(lat_pos(p, 1, sj + 1) - sy), fabsf(lat_pos(p, 1, sj - 1) - sy)),
+                                                        fmaxf(fabsf(lat_pos(p, 2, sk + 1) - sz), fabsf(lat_pos(p, 2, sk - 1) - sz))));
+    const float eps2 = 2.0f * p.eps;
+    for (int q = 0; q < cnt; q++) {
+      bool c = false;
+      const uint32_t need = valid ? (dm & ~W.coll[cell]) : 0u;
+      if (need) {
+        const float4 R0 = W.R0[q], R1 = W.R1[q];
+        const float wx = sx - R1.x, wy = sy - R1.y, wz = sz - R1.z;
+        const float aa = fabsf(wx * R0.x + wy * R0.y + wz * R0.z);   // approximate: every threshold below has slack for its rounding
+        if (R0.w == 0.f || A.nofilter) c = true;                     // no assumption about this triangle: exact path
+        else if (aa <= A.rrej * 1.001f) {
+          if (!(A.dist_dead || aa * aa >= 1.45f * A.drw2)) c = true; // the distance test may hold: exact path
+          else if (aa < eps2) {
+            // in the plane: while a direction parallel to the plane is open every record counts; afterwards only hit points
+            const uint32_t inpl = (fabsf(R0.x) * L < eps2 ? 3u : 0u) | (fabsf(R0.y) * L < eps2 ? 12u : 0u) | (fabsf(R0.z) * L < eps2 ? 48u : 0u);
+            c = (need & inpl) != 0u;
+            if (!c) { const float rr = W.rad[q] + L; c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr; }
+          } else if (aa <= L) {
+            const float rr = W.rad[q] + L;
+            c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;
           }
         }
       }
-    // ---- in-plane pass (tight records only; otherwise the main pass already covered the influence ball): cells within 2 eps of
-    // the triangle's plane collide along every axis that is parallel to the plane within eps, whatever the triangle's extent
-    // (crixus_d.cu:766-769) -- as far as the influence radius reaches.  For every pair of indices along the two axes with the
-    // smaller normal components, the index along the third follows from the plane equation.
-    const uint32_t capable = !(valid && tight) ? 0u : ((fabsf(T.n.x) * A.lstep < eps2 ? 3u : 0u) | (fabsf(T.n.y) * A.lstep < eps2 ? 12u : 0u) |
-                                                       (fabsf(T.n.z) * A.lstep < eps2 ? 48u : 0u));
-    if (!__any_sync(0xffffffffu, capable != 0u)) continue;
-    const int m = (fabsf(T.n.x) >= fabsf(T.n.y) && fabsf(T.n.x) >= fabsf(T.n.z)) ? 0 : (fabsf(T.n.y) >= fabsf(T.n.z) ? 1 : 2);
-    const int u = (m + 1) % 3, v = (m + 2) % 3;
-    const float nm = comp(T.n, m), nu = comp(T.n, u), nv = comp(T.n, v);
-    const float v0m = comp(T.v0, m), v0u = comp(T.v0, u), v0v = comp(T.v0, v);
-    int plo[3] = {0, 0, 0}, phi[3] = {-1, -1, -1};
-    if (capable) {
-      axis_range(p, 0, T.v0.x, r_infl, T.g[0], 0, A.dimg[0], A.dimg[0], &plo[0], &phi[0]);
-      axis_range(p, 1, T.v0.y, r_infl, T.g[1], 0, A.dimg[1], A.dimg[1], &plo[1], &phi[1]);
-      axis_range(p, 2, T.v0.z, r_infl, T.g[2], A.k_lo, A.k_hi, A.dimg[2], &plo[2], &phi[2]);
-    }
-    const int ulo = plo[u], uhi = phi[u], vlo = plo[v], vhi = phi[v], mlo = plo[m], mhi = phi[m];
-    const int nu_ = __reduce_max_sync(0xffffffffu, uhi - ulo + 1), nv_ = __reduce_max_sync(0xffffffffu, vhi - vlo + 1);
-    if (nu_ <= 0 || nv_ <= 0) continue;
-    for (int tu = 0; tu < nu_; tu++) {
-      const int iu = ulo + tu;
-      const float wu = lat_pos(p, u, iu) - v0u;
-      const bool oku = capable && iu <= uhi && mhi >= mlo && nb_axis(p, u, lat_cell(p, u, iu), T.g[u]);
-      if (!__any_sync(0xffffffffu, oku)) continue;
-      for (int tv = 0; tv < nv_; tv++) {
-        const int iv = vlo + tv;
-        const float wv = lat_pos(p, v, iv) - v0v;
-        const bool okv = oku && iv <= vhi && !(wu * wu + wv * wv > r_infl * r_infl);
-        // n.(s - v0) = 0  ->  coordinate along m, and the two lattice indices around it
-        const float tm = (v0m - (nu * wu + nv * wv) / nm - p.fcmin[m]) / p.dr;
-        const int im0 = (okv && tm > -2.0f && tm < (float)A.dimg[m] + 1.0f) ? (int)floorf(tm) : -0x40000000;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int im = im0 + q;
-          bool c = okv && im >= mlo && im <= mhi;
-          uint32_t cand = 0;
-          int idx[3] = {0, 0, 0};
-          if (c) {
-            const float wm = lat_pos(p, m, im) - v0m;
-            const float w2 = wm * wm + wu * wu + wv * wv;
-            c = fabsf(nm * wm + nu * wu + nv * wv) < eps2 && !(w2 > r_infl * r_infl) && !(w2 <= rm * rm) &&   // main pass did the inner ball
-                nb_axis(p, m, lat_cell(p, m, im), T.g[m]);
-            if (c) {
-              idx[m] = im; idx[u] = iu; idx[v] = iv;
-              cand = capable & cell_dirs(A, idx[0], idx[1], idx[2]);
-              // directions that an earlier segment already blocked need no test (a stale read only costs a repeated test)
-              const int64_t wi = ((int64_t)idx[2] * A.dimg[1] + idx[1]) * A.wr + (idx[0] >> 5);
-              const uint32_t bit = 1u << (idx[0] & 31);
-#pragma unroll
-              for (int d = 0; d < 6; d++)
-                if ((cand >> d & 1) && (__ldcg(&A.B[d * A.nw + wi]) & bit)) cand &= ~(1u << d);
-              c = cand != 0u;
-            }
-          }
-          push(c, i, idx[0], idx[1], idx[2], cand, 1);
-        }
+      const unsigned bal = __ballot_sync(0xffffffffu, c);
+      if (bal) {
+        if (c) W.queue[(qh + qn + __popc(bal & ((1u << lane) - 1u))) & (RB_QUEUE - 1)] = (unsigned short)((cell << 8) | q);
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) drain(32);
       }
     }
+    if (qn > 0) drain(qn);
   }
-  if (qn > 0) drain(qn);
+}
+
+__global__ void __launch_bounds__(RB_WARPS * 32, 2) k_resolve_blocks(const __grid_constant__ FillArgs A)
+{
+  __shared__ RBWarp sW[RB_WARPS];
+  const int lane = threadIdx.x & 31;
+  const cx_params &p = A.p;
+  RBWarp &W = sW[threadIdx.x >> 5];
+  const float radf = 1.01f * (1.0f + 3.0f * p.eps);
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(A.count64, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= A.nblist) break;
+    const long long c = A.blist[item];
+    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((long long)p.gridn[2] * p.gridn[1]));
+    // lattice index ranges of the cells that map to this 3dr-cell: lanes 0..5 search one bound each
+    int bound = 0;
+    if (lane < 6) {
+      const int ax = lane >> 1, g = (ax == 0 ? gx : ax == 1 ? gy : gz) + (lane & 1);
+      bound = idx_lo(p, ax, g, A.dimg[ax]);
+    }
+    const int bi0 = __shfl_sync(0xffffffffu, bound, 0), bi1 = __shfl_sync(0xffffffffu, bound, 1);
+    const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
+    const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
+    if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
+    // the neighbourhood as 9 (x,y) columns; the z-neighbours of a column are adjacent in memory, so one column is one run of
+    // records (plus, at a periodic z border, the wrapped cell as a run of its own): lane l < 27 holds run l (9 columns x 3 parts)
+    int rb = 0, re = 0;
+    if (lane < 27) {
+      const int c9 = lane / 3, part = lane % 3;
+      const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
+      if (part == 0) {
+        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
+        const int64_t q0 = nb_cell(p, cx, cy, z0);
+        if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
+      } else {
+        const int zz = part == 1 ? gz - 1 : gz + 1;
+        if (zz < 0 || zz >= p.gridn[2]) {   // out of range: wrapped (periodic z) or skipped
+          const int64_t q0 = nb_cell(p, cx, cy, zz);
+          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
+        }
+      }
+    }
+    // sub-blocks of at most 4 x 4 x 4 lattice cells (a 3dr-cell holds 3-4 cells per axis; border cells of a container that is
+    // larger than the domain hold more)
+    for (int k0 = bk0; k0 < bk1; k0 += 4)
+      for (int j0 = bj0; j0 < bj1; j0 += 4)
+        for (int i0 = bi0; i0 < bi1; i0 += 4) {
+          RBSub S;
+          S.i0 = i0; S.j0 = j0; S.k0 = k0;
+          S.nx = min(4, bi1 - i0); S.ny = min(4, bj1 - j0); S.nz = min(4, bk1 - k0);
+          const int ncl = S.nx * S.ny * S.nz;
+          W.coll[lane] = 0u; W.coll[lane + 32] = 0u;
+          __syncwarp();
+          // centre and half extents of the sub-block, for the block-level plane-distance reject
+          const float xlo = lat_pos(p, 0, i0), xhi = lat_pos(p, 0, i0 + S.nx - 1), ylo = lat_pos(p, 1, j0), yhi = lat_pos(p, 1, j0 + S.ny - 1);
+          const float zlo = lat_pos(p, 2, k0), zhi = lat_pos(p, 2, k0 + S.nz - 1);
+          const float bcx = 0.5f * (xlo + xhi), bcy = 0.5f * (ylo + yhi), bcz = 0.5f * (zlo + zhi);
+          const float bhx = 0.5f * (xhi - xlo), bhy = 0.5f * (yhi - ylo), bhz = 0.5f * (zhi - zlo);
+          int cnt = 0;
+          for (int run = 0; run < 27; run++) {
+            const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
+            for (int base = b; base < e; base += 32) {
+              const int i = base + lane;
+              bool keep = false;
+              float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+              float rad = 0.f;
+              if (i < e) {
+                const float4 *r = A.rec + (int64_t)i * FREC;
+                R0 = __ldg(r); R1 = __ldg(r + 1);
+                const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
+                const float hr = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
+                keep = !(R0.w != 0.f && fabsf(tc) - hr > A.rrej * 1.001f);
+                // an accepted (t1, t2) puts the hit point within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned triangles), 1 % on top
+                if (keep && R0.w == 2.f) rad = radf * sqrtf(fmaxf(R1.w, __ldg(r + 3).w));
+              }
+              const unsigned bal = __ballot_sync(0xffffffffu, keep);
+              if (!bal) continue;
+              if (keep) {
+                const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+                W.R0[at] = R0; W.R1[at] = R1; W.idx[at] = i; W.rad[at] = rad;
+              }
+              cnt += __popc(bal);
+              __syncwarp();
+              if (cnt > RB_CAP - 32) {
+                sub_vs_staged(A, W, S, cnt, lane);
+                cnt = 0;
+                __syncwarp();
+              }
+            }
+          }
+          if (cnt) {
+            sub_vs_staged(A, W, S, cnt, lane);
+            __syncwarp();
+          }
+          for (int cell = lane; cell < ncl; cell += 32) {
+            const int si = i0 + cell % S.nx, sj = j0 + (cell / S.nx) % S.ny, sk = k0 + cell / (S.nx * S.ny);
+            const uint32_t cl = W.coll[cell] & cell_dirs(A, si, sj, sk);
+            if (!cl) continue;
+            const int64_t wi = ((int64_t)sk * A.dimg[1] + sj) * A.wr + (si >> 5);
+            const uint32_t bit = 1u << (si & 31);
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+              if (cl >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
+          }
+          __syncwarp();
+        }
+  }
+}
+
+// work list of k_resolve_blocks: the 3dr-cells whose neighbourhood holds segments and that this rank resolves.  One list entry
+// per cell (a warp takes one at a time): with coarser items a warp that drew a chunk of 32 wall cells ran for milliseconds
+// after all others had finished.
+__global__ void __launch_bounds__(256) k_block_list(cx_params p, const uint8_t *__restrict__ nbflag, int nparts, int part, int32_t *list,
+                                                    unsigned long long *count)
+{
+  const long long n = p.gridn[3];
+  for (long long c0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31ll; c0 < n; c0 += (long long)gridDim.x * blockDim.x) {
+    const long long c = c0 + (threadIdx.x & 31);
+    const bool mine = c < n && nbflag[c] && (nparts <= 1 || chunk_owner(c >> 5, nparts) == part);
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine && list) list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (int32_t)c;
+  }
 }
 
 // free-surface triangles: all of them against every lattice cell, segment test only, no cell lookup (crixus_d.cu:951-960).
@@ -725,6 +708,7 @@ __global__ void __launch_bounds__(128) k_resolve_fs(FillArgs A)
   const cx_params &p = A.p;
   const int64_t rows = (int64_t)A.dimg[1] * (A.k_hi - A.k_lo);
   const int64_t total = rows * A.cnbe;
+  const int nparts = A.res_nparts > 1 ? A.res_nparts : 1;
   for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(it / rows);
     const int64_t row = it - (int64_t)t * rows;
@@ -756,8 +740,15 @@ __global__ void __launch_bounds__(128) k_resolve_fs(FillArgs A)
     const float4 *r = A.rec + ri * FREC;
     const float4 R0 = __ldg(r), R1 = __ldg(r + 1), R2 = __ldg(r + 2), R3 = __ldg(r + 3), R4 = __ldg(r + 4);
     const f3 n = mk3(R0), v0 = mk3(R1), u = sub3(mk3(R2), v0), v = sub3(mk3(R3), v0);
+    const int gy = nparts > 1 ? cell_coord(sy, p.dmin[1], p.griddr[1], p.gridn[1]) : 0;
+    const int gz = nparts > 1 ? cell_coord(sz, p.dmin[2], p.griddr[2], p.gridn[2]) : 0;
     for (int i = ia; i <= ib; i++) {
       const float sx = lat_pos(p, 0, i);
+      if (nparts > 1) {   // the rank that resolves the cell's 3dr-cell owns the cell (disjoint bits: a SUM merge is an OR)
+        const int gx = cell_coord(sx, p.dmin[0], p.griddr[0], p.gridn[0]);
+        const long long c = ((long long)gx * p.gridn[1] + gy) * p.gridn[2] + gz;
+        if (chunk_owner(c >> 5, nparts) != A.res_part) continue;
+      }
       const f3 s = mk3(sx, sy, sz);
       const int idx[3] = {i, j, k};
       uint32_t cl = 0;
@@ -924,9 +915,11 @@ struct FillState {
   int64_t nbe = 0, cnbe = 0;
   uint32_t *F = nullptr, *B = nullptr;   // B: 6 blocked planes
   uint32_t *halo = nullptr;              // two received boundary planes (multi-GPU)
+  int32_t *blist = nullptr;              // work list of the up-front resolve
+  int64_t cap_blist = 0;
   float4 *rec = nullptr;
-  int64_t cap_nw = 0, cap_ntiles = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
-  uint8_t *act = nullptr;
+  int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
+  uint8_t *nbflag = nullptr, *act = nullptr;
   int32_t *list = nullptr, *count = nullptr;
   FsDesc *fs = nullptr;
   int64_t nw = 0, ntiles = 0;
@@ -938,8 +931,8 @@ void cx_fill_state_free(cx_ctx *ctx)
 {
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
-  cudaFree(s->F); cudaFree(s->B); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo);
+  cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -980,6 +973,11 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       CX_CUDA(ctx, cudaMalloc(&s->list, sizeof(int32_t) * (size_t)ntiles));
       s->cap_ntiles = ntiles;
     }
+    if (p->gridn[3] > s->cap_ncell) {
+      cudaFree(s->nbflag); s->nbflag = nullptr; s->cap_ncell = 0;
+      CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
+      s->cap_ncell = p->gridn[3];
+    }
     if (nbe > s->cap_rec) {
       cudaFree(s->rec); s->rec = nullptr; s->cap_rec = 0;
       CX_CUDA(ctx, cudaMalloc(&s->rec, sizeof(float4) * FREC * (size_t)nbe));
@@ -1006,9 +1004,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->wr = wr; A->ty = ty; A->tz = tz; A->ntiles = ntiles; A->nw = nw;
   A->k_lo = 0; A->k_hi = (int)dimg[2];
   A->w_lo = 0; A->w_hi = nw;
-  A->F = s->F; A->B = s->B; A->fs = s->fs;
+  A->F = s->F; A->B = s->B; A->nbflag = s->nbflag; A->fs = s->fs;
   A->act_cur = s->act + (s->act_swapped ? ntiles : 0); A->act_next = s->act + (s->act_swapped ? 0 : ntiles);
   A->list = s->list; A->count = s->count;
+  A->count64 = (unsigned long long *)(s->count + 4);
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
   A->rec = s->rec;
   // plane-distance reject: a lattice step reaches (1 + eps) dr in barycentric units of the ray parameter, and the distance
@@ -1019,7 +1018,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->dist_dead = (p->eps >= A->drw2) ? 1 : 0;
   static const bool nofilter = getenv("CX_FILL_NOFILTER") != nullptr;
   A->nofilter = nofilter ? 1 : 0;
-  A->lstep = 1.03f * (1.0f + p->eps) * p->dr;
+  {
+    const float f = 1.01f * (1.0f + 3.0f * p->eps);
+    A->sph2 = f * f;
+  }
   if (fresh) {
     k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec);
     CX_LAUNCH_CHECK(ctx, "k_seg_prep");
@@ -1027,22 +1029,43 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       k_fs_desc<<<cx_blocks(cnbe, 128), 128, 0, st>>>(*A, s->fs);
       CX_LAUNCH_CHECK(ctx, "k_fs_desc");
     }
-    k_seg_cells<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, nbe - cnbe, s->rec);
-    CX_LAUNCH_CHECK(ctx, "k_seg_cells");
+    k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
+    CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
   }
   *out = s;
   return CX_OK;
 }
 
-// directed tests of the planes [A->k_lo, A->k_hi) into the B planes
-static int fill_resolve(cx_ctx *ctx, FillArgs *A)
+// directed tests of the planes [A->k_lo, A->k_hi), share (res_part of res_nparts), into the B planes
+static int fill_resolve(cx_ctx *ctx, FillArgs *A, FillState *s)
 {
   cudaStream_t st = ctx->stream;
   if (A->k_hi <= A->k_lo) return CX_OK;
-  const int64_t nwall = A->nbe - A->cnbe;
-  if (nwall > 0) {
-    k_resolve_records<<<cx_blocks(nwall, RQ_WARPS * 32, ctx->num_sms * 16), RQ_WARPS * 32, 0, st>>>(*A);
-    CX_LAUNCH_CHECK(ctx, "k_resolve_records");
+  // work list: count, (grow the buffer,) fill -- the order of the entries is irrelevant (results are OR-ed bits)
+  const int64_t ncell = A->p.gridn[3];
+  const int lgrid = cx_blocks(ncell, 256, ctx->num_sms * 16);
+  for (int pass = 0; pass < 2; pass++) {
+    CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+    k_block_list<<<lgrid, 256, 0, st>>>(A->p, A->nbflag, A->res_nparts, A->res_part, pass ? s->blist : nullptr, A->count64);
+    CX_LAUNCH_CHECK(ctx, "k_block_list");
+    if (pass == 0) {
+      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CX_CUDA(ctx, cudaStreamSynchronize(st));
+      A->nblist = ctx->h_mail[30];
+      if (A->nblist > s->cap_blist) {
+        cudaFree(s->blist); s->blist = nullptr; s->cap_blist = 0;
+        const int64_t want = A->nblist + A->nblist / 8 + 1024;
+        CX_CUDA(ctx, cudaMalloc(&s->blist, sizeof(int32_t) * (size_t)want));
+        s->cap_blist = want;
+      }
+      A->blist = s->blist;
+      if (A->nblist == 0) break;
+    }
+  }
+  if (A->nblist > 0) {
+    CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+    k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
+    CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
   }
   if (A->cnbe > 0) {
     const int64_t total = (int64_t)A->dimg[1] * (A->k_hi - A->k_lo) * A->cnbe;
@@ -1133,7 +1156,7 @@ extern "C" int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *
   // Resolve every directed test of the owned planes up front, in one balanced launch: they are pure functions of the
   // geometry, so nothing is gained by waiting for the flood to arrive.
   if (!(s->resolved_lo <= A.k_lo && s->resolved_hi >= A.k_hi)) {
-    rc = fill_resolve(ctx, &A);
+    rc = fill_resolve(ctx, &A, s);
     if (rc != CX_OK) return rc;
     s->resolved_lo = A.k_lo; s->resolved_hi = A.k_hi;
   }
@@ -1174,12 +1197,12 @@ extern "C" int cx_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_
 }
 
 // ---- multi-GPU building blocks (stage level; cx_dist_fill_geometry below strings them together) ---------------------
-// The directed tests are pure functions of the geometry: each rank resolves the lattice planes of its z-slab (the blocked bits
-// of a cell live with the cell, so a slab needs nothing from its neighbours).  For the replicated flood (cx_fill_propagate) the
-// six blocked bit planes are merged by the caller -- disjoint planes, zero elsewhere: a SUM all-reduce is an OR; the z-slab
-// flood (cx_fill_geometry_slab(first_call = 2)) needs no merge at all.
+// The directed tests are pure functions of the geometry: each rank resolves its share, the six blocked bit planes are merged
+// by the caller (every lattice cell is resolved by exactly one rank, so the shares are disjoint bit sets and a SUM
+// all-reduce is an OR), and the cheap propagation then runs on the whole lattice on every rank (cx_fill_propagate) or by
+// z-slab (cx_fill_geometry_slab(first_call = 2)).
 static int resolve_share(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d, const float *pos_d,
-                         int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin, int64_t k_end,
+                         int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin, int64_t k_end, int nparts, int part,
                          uint32_t **blocked_d, int64_t *blocked_words)
 {
   FillArgs A;
@@ -1193,7 +1216,8 @@ static int resolve_share(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, cons
   k_unpack<<<cx_blocks(A.nw, 256, ctx->num_sms * 16), 256, 0, st>>>(A, fpos_d);   // tiles that hold set cells are activated
   CX_LAUNCH_CHECK(ctx, "k_unpack");
   A.k_lo = (int)k_begin; A.k_hi = (int)k_end;
-  rc = fill_resolve(ctx, &A);
+  A.res_nparts = nparts; A.res_part = part;
+  rc = fill_resolve(ctx, &A, s);
   if (rc != CX_OK) return rc;
   s->resolved_lo = 0; s->resolved_hi = A.dimg[2];   // after the caller's merge every plane is resolved
   if (blocked_d) *blocked_d = s->B;
@@ -1206,20 +1230,20 @@ extern "C" int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *f
                                     int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words)
 {
   if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe) return CX_WRONG_INPUT;
-  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k_begin, k_end, blocked_d, blocked_words);
+  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k_begin, k_end, 1, 0, blocked_d, blocked_words);
 }
 
-// the same for part `part` of nparts: its planes are the z-slab cx_dist_* gives that rank (sizes differ by at most one plane)
+// interleaved variant: the 3dr-cells are dealt to the ranks in chunks of 32 (z-slabs balance badly: the floor slab holds a
+// whole wall); same contract otherwise
 extern "C" int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                                     const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
                                     uint32_t **blocked_d, int64_t *blocked_words)
 {
   if (!ctx || !p || !fpos_d || !norm_d || !ep_d || !pos_d || !cell_idx_d || cnbe < 0 || cnbe > nbe || nparts < 1 || part < 0 || part >= nparts)
     return CX_WRONG_INPUT;
-  int64_t dimg[3], k0, k1;
+  int64_t dimg[3];
   cx_fill_dims(p, dimg);
-  cx_split_range(dimg[2], nparts, part, &k0, &k1);
-  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k0, k1, blocked_d, blocked_words);
+  return resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], nparts, part, blocked_d, blocked_words);
 }
 
 extern "C" int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
@@ -1297,9 +1321,7 @@ extern "C" int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *
   cudaStream_t st = ctx->stream;
   uint32_t *B = nullptr;
   int64_t bwords = 0;
-  int64_t k0, k1;
-  cx_split_range(dimg[2], world, rank, &k0, &k1);
-  int rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k0, k1, &B, &bwords);   // the planes of my slab
+  int rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], world, rank, &B, &bwords);
   if (rc != CX_OK) return rc;
   FillArgs A;
   FillState *s = nullptr;
@@ -1325,9 +1347,18 @@ extern "C" int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *
     if (rounds_host) *rounds_host = rounds;
     return CX_OK;
   }
-  // ---- z-slabs: every rank resolved exactly the planes it floods -- nothing to merge
+  // ---- z-slabs
   const int64_t wplane = (int64_t)A.wr * A.dimg[1];
   std::vector<CxSeg> segs;
+  for (int r = 0; r < world; r++) {
+    int64_t a, b;
+    cx_split_range(dimg[2], world, r, &a, &b);
+    for (int d = 0; d < 6; d++) segs.push_back({d * A.nw + wplane * a, wplane * (b - a), r});
+  }
+  rc = coll->reduce_segments_u32(ctx, B, segs.data(), (int)segs.size());
+  if (rc != CX_OK) return rc;
+  int64_t k0, k1;
+  cx_split_range(dimg[2], world, rank, &k0, &k1);
   A.k_lo = (int)k0; A.k_hi = (int)k1;
   if (wplane > s->cap_halo) {
     cudaFree(s->halo); s->halo = nullptr; s->cap_halo = 0;

@@ -202,44 +202,6 @@ __device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float 
   return lmt[(pa ? 64 : 0) + lo + 1];
 }
 
-// Three planes searched in ONE six-step loop (the three wall planes of a fan triangle are always searched together): the same
-// evaluations as three mono_mask calls, but one warp vote, one loop counter and one branch per step instead of three, and three
-// independent dependency chains per step for the scheduler to interleave.
-template <class F0, class F1, class F2, class PV>
-__device__ __forceinline__ void mono_mask3(const float *gzt, float a0, float b0, F0 f0, float a1, float b1, F1 f1, float a2, float b2, F2 f2,
-                                           PV pv, uint64_t &M0, uint64_t &M1, uint64_t &M2, int &lo0, bool &pa0)
-{
-  const bool p0 = pv(a0), p1 = pv(a1), p2 = pv(a2);
-  const bool c0 = p0 != pv(b0), c1 = p1 != pv(b1), c2 = p2 != pv(b2);
-  int l0 = VV_GS - 1, l1 = VV_GS - 1, l2 = VV_GS - 1;
-  const unsigned cutm = __ballot_sync(VV_FULLWARP, c0 || c1 || c2);
-  if (cutm) {
-    VV_STAT(2, 3); VV_STAT(3, __popc(cutm));
-    const float g32 = gzt[32];
-    int s0 = (pv(f0(g32)) == p0) ? 32 : 0, s1 = (pv(f1(g32)) == p1) ? 32 : 0, s2 = (pv(f2(g32)) == p2) ? 32 : 0;
-    {
-      const int i0 = min(s0 + 16, VV_GS - 1), i1 = min(s1 + 16, VV_GS - 1), i2 = min(s2 + 16, VV_GS - 1);
-      if (pv(f0(gzt[i0])) == p0) s0 = i0;
-      if (pv(f1(gzt[i1])) == p1) s1 = i1;
-      if (pv(f2(gzt[i2])) == p2) s2 = i2;
-    }
-#pragma unroll 1
-    for (int st = 8; st >= 1; st >>= 1) {   // never beyond 39 for a lane that is really cut; the table has 64 entries
-      if (pv(f0(gzt[s0 + st])) == p0) s0 += st;
-      if (pv(f1(gzt[s1 + st])) == p1) s1 += st;
-      if (pv(f2(gzt[s2 + st])) == p2) s2 += st;
-    }
-    if (c0) l0 = s0;
-    if (c1) l1 = s1;
-    if (c2) l2 = s2;
-  }
-  const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
-  M0 = lmt[(p0 ? 64 : 0) + l0 + 1];
-  M1 = lmt[(p1 ? 64 : 0) + l1 + 1];
-  M2 = lmt[(p2 ? 64 : 0) + l2 + 1];
-  lo0 = l0; pa0 = p0;
-}
-
 struct TriCtx {
   float4 P4, P5, P6, P7, P8, P9;
   float tV, tV2, tW0, tW1, tW2, tE, piz, eps;
@@ -531,14 +493,9 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     bool pa0, pa1, pa2;
     // estimate of the crossing of w = -eps: voxel index (neps - tW)*igdr/C + 20
     const float ek0 = EST ? __fdividef(a.igdr, P7.z) : 0.f, ek1 = EST ? __fdividef(a.igdr, P8.y) : 0.f, ek2 = EST ? __fdividef(a.igdr, P9.x) : 0.f;
-    uint64_t IN0, IN1, IN2;
-    if (EST) {
-      IN0 = mono_mask<EST>(gzt, w0a, w0b, fW0, ge, lo0, pa0, ffma(fsub(neps, tW0), ek0, 20.f));
-      IN1 = mono_mask<EST>(gzt, w1a, w1b, fW1, ge, lo1, pa1, ffma(fsub(neps, tW1), ek1, 20.f));
-      IN2 = mono_mask<EST>(gzt, w2a, w2b, fW2, ge, lo2, pa2, ffma(fsub(neps, tW2), ek2, 20.f));
-    } else {
-      mono_mask3(gzt, w0a, w0b, fW0, w1a, w1b, fW1, w2a, w2b, fW2, ge, IN0, IN1, IN2, lo0, pa0);
-    }
+    const uint64_t IN0 = mono_mask<EST>(gzt, w0a, w0b, fW0, ge, lo0, pa0, ffma(fsub(neps, tW0), ek0, 20.f));
+    const uint64_t IN1 = mono_mask<EST>(gzt, w1a, w1b, fW1, ge, lo1, pa1, ffma(fsub(neps, tW1), ek1, 20.f));
+    const uint64_t IN2 = mono_mask<EST>(gzt, w2a, w2b, fW2, ge, lo2, pa2, ffma(fsub(neps, tW2), ek2, 20.f));
     const uint64_t inside = IN0 & IN1 & IN2;
     // LT = {w0 < eps}.  On a line cut by IN0 it is the complement of IN0 plus the n voxels of IN0 next to the flip that
     // lie in the wall plane (n = 0 or 1 in all but degenerate cases).

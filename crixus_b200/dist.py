@@ -8,12 +8,12 @@ device-resident workload for bench.py.  What shards and what does not (DESIGN.md
     all-gather of their outputs over NVLink would move more bytes than recomputing them, so every rank runs them on the full
     (replicated) mesh -- identical results on every rank because the binning order is stable.
   * calc_vert_volume (FP32-ALU bound, ~90 % of the time): interleaved 1024-vertex chunks, volumes all-reduced (4 B/vertex).
-  * geometry fill: z-slabs of the dr lattice.  Every rank resolves the directed tests of its own planes (record-driven: it walks
-    the segments near its slab), floods its slab and exchanges boundary planes with its z-neighbours; owned planes are
-    all-gathered at the end.  Bit-exact across rank counts by the fixed-point property of the fill.
+  * geometry fill: directed tests dealt by 3dr-cell chunk, blocked planes reduced to the z-slab owners, slab floods with halo
+    exchange, owned planes all-gathered.  Bit-exact across rank counts by the fixed-point property of the fill.
 
 The pure partition helpers below restate the library's sharding rules; they are tested on CPU with gloo (world_size 2 and 3,
-the CPU oracle as the compute backend, tests/test_dist.py) -- the same rules the C++ code follows (csrc/dist.h cx_split_range)."""
+the CPU oracle as the compute backend, tests/test_dist.py) -- the same rules the C++ code follows (csrc/dist.h cx_split_range,
+csrc/fill.cu chunk_owner)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -33,6 +33,25 @@ def split_range(n, world, rank):
     base, rem = divmod(int(n), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+FT_Y, FT_Z, DEAL_CHUNK = 16, 16, 64   # fill tiles (csrc/fill.cu FT_Y / FT_Z) and the chunk of the interleaved dealing
+
+
+def dealt_chunk_owner(chunk, nparts):
+    """Rank that resolves the directed tests of 3dr-cell chunk `chunk` (32 consecutive 3dr-cells; csrc/fill.cu chunk_owner):
+    every group of nparts consecutive chunks is dealt one chunk per rank, the order rotated by a multiplicative hash of the
+    group number.  (Plain round-robin is periodic in the cell grid: a wall is a plane of 3dr-cells, i.e. every gridn_z/32-th
+    chunk, and could land on few ranks.)  Vectorised over numpy arrays."""
+    chunk = np.asarray(chunk, dtype=np.int64)
+    g, slot = chunk // nparts, chunk % nparts
+    rot = ((g.astype(np.uint64) & np.uint64(0xFFFFFFFF)) * np.uint64(2654435761) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)
+    return ((slot - (rot % np.uint64(nparts)).astype(np.int64)) % nparts).astype(np.int64)
+
+
+def cell3_chunk(gx, gy, gz, gridn):
+    """chunk of the up-front resolve that holds 3dr-cell (gx, gy, gz): cells are numbered gx*ny*nz + gy*nz + gz, 32 per chunk"""
+    return ((np.asarray(gx, dtype=np.int64) * gridn[1] + gy) * gridn[2] + gz) // 32
 
 
 def split_weighted(weights, world, rank):
@@ -187,9 +206,9 @@ class ShardedHotPath:
         self.parallelism = "1 GPU" if world == 1 else (
             "one process per GPU, NCCL inside the C-ABI (cx_dist_*); vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; "
             "fill: %s; cheap stages and device weld replicated"
-            % (VV_CHUNK, world, ("directed tests by z-slab (%d ranks), blocked planes all-reduced, flood replicated" % world) if small else
-               ("%d z-slabs: each rank resolves the directed tests of its planes and floods them, halo exchange over NCCL send/recv "
-                "every %d rounds, owned planes all-gathered" % (world, FILL_ROUNDS_PER_EXCHANGE))))
+            % (VV_CHUNK, world, ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes all-reduced, flood replicated" % world) if small else
+               ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes reduced to the slab owners, flood in %d z-slabs with a "
+                "halo exchange over NCCL send/recv every %d rounds, owned planes all-gathered" % (world, world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
         # one untimed pass to learn trisize (vertex-range balancing) and the S27 statistic for the byte count

@@ -138,16 +138,16 @@ int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, con
 int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds);
 int cx_fill_unfinished(cx_ctx *ctx);
 
-/* Multi-GPU building blocks (cx_dist_fill_geometry strings them together; exported for callers with their own collectives):
- * the directed tests (pure functions of the geometry) are resolved for planes [k_begin, k_end) only;
+/* Multi-GPU: the directed tests (pure functions of the geometry) are resolved for planes [k_begin, k_end) only;
  * *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32, zero outside this rank's share) which the caller
- * merges across ranks (every lattice plane is resolved by exactly one rank -- disjoint bits: SUM == OR).  Then either
+ * merges across ranks (every lattice cell is resolved by exactly one rank -- disjoint bits: SUM == OR).  Then either
  * cx_fill_propagate runs the flood on the whole lattice on every rank (small lattices: no halo exchange, no per-sweep
  * collective) or cx_fill_geometry_slab(first_call = 2) floods by z-slab (large lattices). */
 int cx_fill_resolve_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int64_t k_begin,
                          int64_t k_end, uint32_t **blocked_d, int64_t *blocked_words);
-/* same for part `part` of nparts: its planes are the z-slab of that rank (sizes differ by at most one plane) */
+/* same, but the 3dr-cells (and with them their lattice cells) are dealt to the ranks in interleaved chunks of 32 (balanced;
+ * z-slabs are not: the floor slab holds a whole wall) */
 int cx_fill_resolve_part(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const float *norm_d, const int32_t *ep_d,
                          const float *pos_d, int64_t nbe, int64_t cnbe, const int32_t *cell_idx_d, int nparts, int part,
                          uint32_t **blocked_d, int64_t *blocked_words);
@@ -159,10 +159,9 @@ int cx_fill_propagate(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, const f
  * this is where a device list enters.  A context joins a communicator once; the cx_dist_* stage calls and cx_preprocess_dist then
  * run sharded over its ranks, all collectives on the context's stream:
  *   calc_vert_volume  interleaved chunks of CX_DIST_VV_CHUNK vertices per rank + one all-reduce of the volumes
- *   geometry fill     z-slabs of the lattice: every rank resolves the directed tests of its planes and floods them, boundary
- *                     planes exchanged between z-neighbours every CX_DIST_FILL_ROUNDS rounds (NCCL send/recv), termination
- *                     by an all-reduce of two counters, owned planes all-gathered at the end (small lattices: blocked planes
- *                     all-reduced, flood replicated)
+ *   geometry fill     directed tests dealt to the ranks by 3dr-cell chunk, blocked planes reduced to the z-slab owners, slab
+ *                     floods with boundary planes exchanged between z-neighbours every CX_DIST_FILL_ROUNDS rounds (NCCL
+ *                     send/recv), termination by an all-reduce of two counters, owned planes all-gathered at the end
  *   cheap stages      (set_bound_elem, binning, links, trisize, device weld) replicated: recomputing them costs less HBM
  *                     traffic than gathering their outputs would cost NVLink traffic
  * Results are bit-identical for every rank count (the fill is a least fixed point; the volumes are per-vertex). */

@@ -109,3 +109,36 @@ def test_partition_helpers():
         assert np.array_equal(bits[:G], want[:G])
         acc += part
     assert np.array_equal(np.unpackbits(acc.numpy().view(np.uint8), bitorder="little")[:G], np.ones(G, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+def test_dealing_of_the_directed_tests_is_a_balanced_partition(nparts):
+    """The multi-GPU fill merges the blocked planes of the ranks with SUM reductions, which equal OR only if every lattice cell
+    is resolved by exactly one rank; and the walls of a tank -- whole planes of the 3dr-cell grid -- must not all land on a few
+    ranks.  cd.dealt_chunk_owner mirrors the kernel's formula (csrc/fill.cu chunk_owner: chunks of 32 consecutive 3dr-cells)."""
+    gridn = (100, 100, 100)
+    ncell = gridn[0] * gridn[1] * gridn[2]
+    nchunks = (ncell + 31) // 32
+    owner = cd.dealt_chunk_owner(np.arange(nchunks), nparts)
+    # partition: within every complete group of nparts chunks each rank appears exactly once
+    full = (nchunks // nparts) * nparts
+    grp = owner[:full].reshape(-1, nparts)
+    assert (np.sort(grp, axis=1) == np.arange(nparts)).all()
+    # the kernel's enumeration (rank `part` takes slot (part + rot(g)) % nparts of group g) hits exactly the chunks it owns
+    g = np.arange(nchunks // nparts)
+    rot = ((g.astype(np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)
+    for part in range(nparts):
+        mine = g * nparts + (part + (rot % np.uint64(nparts)).astype(np.int64)) % nparts
+        assert (owner[mine] == part).all()
+    # balance on the six walls of the tank (two layers of 3dr-cells each hold the lattice cells whose tests are expensive)
+    A, B = np.meshgrid(np.arange(gridn[0]), np.arange(gridn[1]), indexing="ij")
+    walls = []
+    for layer in (0, 1, gridn[2] - 2, gridn[2] - 1):
+        walls.append(cd.cell3_chunk(A.ravel(), B.ravel(), np.full(A.size, layer), gridn))
+        walls.append(cd.cell3_chunk(A.ravel(), np.full(A.size, layer), B.ravel(), gridn))
+        walls.append(cd.cell3_chunk(np.full(A.size, layer), A.ravel(), B.ravel(), gridn))
+    load = np.bincount(cd.dealt_chunk_owner(np.concatenate(walls), nparts), minlength=nparts)
+    assert load.max() <= 1.15 * load.mean(), load
+    for one in walls[:3]:                                                 # every single wall layer by itself
+        load = np.bincount(cd.dealt_chunk_owner(one, nparts), minlength=nparts)
+        assert load.max() <= 1.3 * load.mean(), load
