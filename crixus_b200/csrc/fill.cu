@@ -431,6 +431,7 @@ struct RBWarp {
   float rad[RB_CAP];               // bounding radius of the accepted barycentric region around v0 (well-conditioned records)
   unsigned short queue[RB_QUEUE];  // candidate pairs: (cell << 8) | staged slot
   uint32_t coll[64];               // blocked directions per lattice cell of the sub-block
+  unsigned char cxyz[64];          // local coordinates of the cells: x | y << 2 | z << 4
 };
 
 // geometry of a sub-block of lattice cells: cell q = (i0 + q % nx, j0 + (q / nx) % ny, k0 + q / (nx ny)), q < nx ny nz <= 64
@@ -518,7 +519,8 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
     if (have) {
       const unsigned e = W.queue[(qh + lane) & (RB_QUEUE - 1)];
       const int cell = (int)(e >> 8), q = (int)(e & 255u);
-      const int si = S.i0 + cell % S.nx, sj = S.j0 + (cell / S.nx) % S.ny, sk = S.k0 + cell / (S.nx * S.ny);
+      const unsigned xyz = W.cxyz[cell];
+      const int si = S.i0 + (int)(xyz & 3u), sj = S.j0 + (int)((xyz >> 2) & 3u), sk = S.k0 + (int)(xyz >> 4);
       const uint32_t need = cell_dirs(A, si, sj, sk) & ~W.coll[cell];
       if (need) {
         const uint32_t got = pair_exact(A, W, q, si, sj, sk, need);
@@ -532,7 +534,8 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
   for (int sl = 0; sl * 32 < ncl; sl++) {
     const int cell = lane + 32 * sl;
     const bool valid = cell < ncl;
-    const int si = S.i0 + (valid ? cell % S.nx : 0), sj = S.j0 + (valid ? (cell / S.nx) % S.ny : 0), sk = S.k0 + (valid ? cell / (S.nx * S.ny) : 0);
+    const unsigned xyz = valid ? W.cxyz[cell] : 0u;
+    const int si = S.i0 + (int)(xyz & 3u), sj = S.j0 + (int)((xyz >> 2) & 3u), sk = S.k0 + (int)(xyz >> 4);
     const uint32_t dm = valid ? cell_dirs(A, si, sj, sk) : 0u;
     const float sx = lat_pos(p, 0, si), sy = lat_pos(p, 1, sj), sz = lat_pos(p, 2, sk);
     // reach of a lattice step from this cell, with the tolerances of the ray parameter: (1 + eps) |dir|, 2 % on top
@@ -540,24 +543,23 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
                                                   fmaxf(fmaxf(fabsf(lat_pos(p, 1, sj + 1) - sy), fabsf(lat_pos(p, 1, sj - 1) - sy)),
                                                         fmaxf(fabsf(lat_pos(p, 2, sk + 1) - sz), fabsf(lat_pos(p, 2, sk - 1) - sz))));
     const float eps2 = 2.0f * p.eps;
+    const float lim_rej = A.rrej * 1.001f, lim_alive = A.dist_dead ? 0.f : 1.45f * A.drw2;
+    uint32_t need = valid ? (dm & ~W.coll[cell]) : 0u;   // refreshed after every drain (the only place coll changes)
     for (int q = 0; q < cnt; q++) {
+      if (!__any_sync(0xffffffffu, need != 0u)) break;   // every cell of this pass has all its directions blocked
       bool c = false;
-      const uint32_t need = valid ? (dm & ~W.coll[cell]) : 0u;
       if (need) {
         const float4 R0 = W.R0[q], R1 = W.R1[q];
         const float wx = sx - R1.x, wy = sy - R1.y, wz = sz - R1.z;
         const float aa = fabsf(wx * R0.x + wy * R0.y + wz * R0.z);   // approximate: every threshold below has slack for its rounding
         if (R0.w == 0.f || A.nofilter) c = true;                     // no assumption about this triangle: exact path
-        else if (aa <= A.rrej * 1.001f) {
-          if (!(A.dist_dead || aa * aa >= 1.45f * A.drw2)) c = true; // the distance test may hold: exact path
-          else if (aa < eps2) {
-            // in the plane: while a direction parallel to the plane is open every record counts; afterwards only hit points
-            const uint32_t inpl = (fabsf(R0.x) * L < eps2 ? 3u : 0u) | (fabsf(R0.y) * L < eps2 ? 12u : 0u) | (fabsf(R0.z) * L < eps2 ? 48u : 0u);
-            c = (need & inpl) != 0u;
-            if (!c) { const float rr = W.rad[q] + L; c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr; }
-          } else if (aa <= L) {
+        else if (aa <= lim_rej) {
+          if (aa * aa < lim_alive) c = true;                         // the distance test may hold: exact path
+          else if (aa <= L || aa < eps2) {
             const float rr = W.rad[q] + L;
-            c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;
+            c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;   // a lattice step from here can hit inside the triangle's sphere
+            if (!c && aa < eps2)   // in the plane: while a direction parallel to the plane is open every record counts
+              c = (need & ((fabsf(R0.x) * L < eps2 ? 3u : 0u) | (fabsf(R0.y) * L < eps2 ? 12u : 0u) | (fabsf(R0.z) * L < eps2 ? 48u : 0u))) != 0u;
           }
         }
       }
@@ -566,7 +568,10 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
         if (c) W.queue[(qh + qn + __popc(bal & ((1u << lane) - 1u))) & (RB_QUEUE - 1)] = (unsigned short)((cell << 8) | q);
         qn += __popc(bal);
         __syncwarp();
-        if (qn >= 32) drain(32);
+        if (qn >= 32) {
+          drain(32);
+          need = valid ? (dm & ~W.coll[cell]) : 0u;
+        }
       }
     }
     if (qn > 0) drain(qn);
@@ -625,6 +630,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 2) k_resolve_blocks(const __gri
           S.nx = min(4, bi1 - i0); S.ny = min(4, bj1 - j0); S.nz = min(4, bk1 - k0);
           const int ncl = S.nx * S.ny * S.nz;
           W.coll[lane] = 0u; W.coll[lane + 32] = 0u;
+          for (int q = lane; q < ncl; q += 32) W.cxyz[q] = (unsigned char)((q % S.nx) | (((q / S.nx) % S.ny) << 2) | ((q / (S.nx * S.ny)) << 4));
           __syncwarp();
           // centre and half extents of the sub-block, for the block-level plane-distance reject
           const float xlo = lat_pos(p, 0, i0), xhi = lat_pos(p, 0, i0 + S.nx - 1), ylo = lat_pos(p, 1, j0), yhi = lat_pos(p, 1, j0 + S.ny - 1);
