@@ -54,13 +54,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int32_t *__r
   if (threadIdx.x == 0) sums[blockIdx.x] = tot;
 }
 
+// vec: in and out are 16-byte aligned (int4 loads / stores); the scalar path serves caller-owned pointers that are not (the
+// C-ABI passes e.g. cell_idx_d straight through)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int32_t *__restrict__ in, int32_t *__restrict__ out,
-                                                             const int32_t *__restrict__ offs, int64_t n)
+                                                             const int32_t *__restrict__ offs, int64_t n, int vec)
 {
   const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
-  if (base + SCAN_ITEMS <= n) {
+  const bool whole = vec && base + SCAN_ITEMS <= n;
+  if (whole) {
     const int4 *p = reinterpret_cast<const int4 *>(in + base);  // base is a multiple of 16 ints
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS / 4; k++) {
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int32_t *__re
   for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
   int tot;
   int ex = block_excl_scan(s, &tot) + (offs ? offs[blockIdx.x] : 0);
-  if (base + SCAN_ITEMS <= n) {
+  if (whole) {
     int4 *p = reinterpret_cast<int4 *>(out + base);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS / 4; k++) {
@@ -97,8 +100,9 @@ int cx_exclusive_scan_i32(cx_ctx *ctx, const int32_t *in_d, int32_t *out_d, int6
 {
   if (n <= 0) return CX_OK;
   const int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  const int vec = (((uintptr_t)in_d | (uintptr_t)out_d) & 15u) == 0 ? 1 : 0;
   if (nb == 1) {
-    k_scan_apply<<<1, SCAN_THREADS, 0, ctx->stream>>>(in_d, out_d, nullptr, n);
+    k_scan_apply<<<1, SCAN_THREADS, 0, ctx->stream>>>(in_d, out_d, nullptr, n, vec);
     CX_LAUNCH_CHECK(ctx, "k_scan_apply");
     return CX_OK;
   }
@@ -108,7 +112,7 @@ int cx_exclusive_scan_i32(cx_ctx *ctx, const int32_t *in_d, int32_t *out_d, int6
   CX_LAUNCH_CHECK(ctx, "k_scan_reduce");
   int rc = cx_exclusive_scan_i32(ctx, sums, sums, nb);  // in-place is safe: each block reads its chunk before writing
   if (rc != CX_OK) return rc;
-  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in_d, out_d, sums, n);
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in_d, out_d, sums, n, vec);
   CX_LAUNCH_CHECK(ctx, "k_scan_apply");
   CX_CUDA(ctx, cudaFreeAsync(sums, ctx->stream));
   return CX_OK;

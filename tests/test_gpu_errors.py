@@ -111,3 +111,30 @@ def test_empty_special_boundary_grid(cuda_backend):
     got = _arr(job.sbid, (nv + nbe,), np.int32)
     np.testing.assert_array_equal(got, np.where(full > 0, full + 1, 0))
     cuda_backend.ctx.L.cx_job_free(C.byref(job))
+
+
+def test_unaligned_cell_idx_pointer(cuda_backend, oracle):
+    """The C-ABI takes caller-owned device pointers as they are: cell_idx_d that is only 4-byte aligned (the scan inside
+    cx_bin_segments vectorises its loads when it can) gives the same prefix sums."""
+    import torch
+    import cases
+    c = cases.case("sphere_tank")
+    o = cases.run(oracle, c, stages=())
+    ctx, dev = cuda_backend.ctx, cuda_backend.ctx.device
+    nv, nbe = o["nvert"], o["nbe"]
+    p = o["params_domain"]
+    from crixus_b200 import api
+    pp = api.CxParams.from_buffer_copy(bytes(p))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    pre_pos = np.zeros((nv + nbe, 4), dtype=np.float32)
+    pre_pos[:nv, :3] = o["verts"]
+    pre_pos[nv:] = o["pre_bary"]
+    pre_norm = np.zeros((nbe, 4), dtype=np.float32)
+    pre_norm[:, :3] = c["normals"]
+    ins = [d(pre_pos), d(pre_norm), d(o["pre_ep"]), d(o["pre_surf"])]
+    outs = [torch.zeros_like(x) for x in ins]
+    buf = torch.zeros(pp.gridn[3] + 2, dtype=torch.int32, device=dev)
+    cell_idx = buf[1:]
+    assert cell_idx.data_ptr() % 16 == 4
+    ctx.bin_segments(pp, ins[0], outs[0], ins[1], outs[1], ins[2], outs[2], ins[3], outs[3], cell_idx, nbe, nv)
+    np.testing.assert_array_equal(cell_idx.cpu().numpy(), o["cell_idx"])
