@@ -6,18 +6,22 @@
 //   * phase A (warp-cooperative, once per vertex): fan gather over the 27 neighbouring 3dr-cells with lanes striding
 //     the cell-sorted segments (ballot/scan compaction keeps the reference's discovery order), chain ordering,
 //     edge-normal pairing, and the 12 plane vectors per fan triangle -> 160 B per triangle in shared memory;
-//   * phase B: the 41x41 z-lines of the voxel cube are dealt to the lanes.  Along a line only gp.z changes, and in
-//     the reference's left-to-right dot product gp.z enters LAST (R1: fma(gz,cz, fma(gy,cy, fma(gx,cx,0)))), so the
-//     (x,y) partial is shared by the 41 voxels of the line bit-exactly: 1 FFMA per plane per voxel instead of 3.
-//     Per-voxel state lives in bit masks (hit / alive / bit-sliced halving counters); the z loop is fully
-//     unrolled so gp.z comes straight from the kernel-parameter constant bank.
+//   * phase B: the voxel cube is cut into 41x41 LINES of 41 voxels and the lines are dealt to the lanes.  Every plane
+//     expression of the reference, sp = fma(gz,cz, fma(gy,cy, fma(gx,cx,0))) (R1), is a chain of correctly rounded, hence
+//     monotone, operations of each of its three grid coordinates: along a line a threshold predicate flips once, and the flip
+//     is found by a six-step search that evaluates the SAME arithmetic (exact).  Per-voxel state lives in 41-bit masks
+//     (hit / alive / bit-sliced halving counters).
+//   * the direction of the lines is chosen PER VERTEX (template parameter AX of the kernel, one launch per direction over a
+//     work list built by a classification pass): along the dominant axis of the vertex normal.  The voronoi, edge and wedge-side
+//     planes of a fan all contain (nearly) the normal direction, so lines parallel to it are removed whole by the row pass or lie
+//     inside ONE wall wedge, instead of crossing every sector of the fan: on an axis-aligned wall 2-3x fewer plane searches.
+//     Any direction gives the same bits; the choice only changes the amount of work.
 //   * the result is summed in integers (weights are 2^-k) so it is independent of the order of summation.
 // Bound: FP32 ALU (non-tensor).  Algorithmic flops F = 68921 * T * 56 per vertex.
 #include <stdlib.h>
 #include "common.cuh"
 
 #define VV_WARPS 4
-#define VV_EST_DEFAULT false   // estimate-and-verify search in the narrow-band kernel (CX_VV_EST=0/1 overrides)
 #define VV_GS 41      // gres*2+1 voxels per axis (crixus_d.cu:280)
 #define VV_LINES (VV_GS * VV_GS)
 #define VV_PLANE_F4 10
@@ -25,6 +29,15 @@
 #define VVE_TRIMAX 1
 #define VVE_FAN 2
 #define VVE_NONMANIFOLD 4
+
+// device-side control block of one call: work counters, list lengths (slot 0..2 = line direction x, y, z; slot 3 = fans with
+// more than 16 triangles), error bits
+struct VVCtl {
+  unsigned long long work[4];
+  int count[4];
+  int err;
+  int pad[3];
+};
 
 struct VVArgs {
   cx_params p;
@@ -43,12 +56,9 @@ struct VVArgs {
   float two_dr;    // 2*dr (crixus_d.cu:513)
   double gd3;      // pow(dr/2.0/(float)gres, 3) (crixus_d.cu:674)
   int cmax;        // largest k with 2^-k >= eps (vgrid < eps -> voxel dropped, crixus_d.cu:551,662)
-  unsigned long long *work;  // work counter
-  int *err;                  // error bits
-  int *big_list;             // vertices deferred to the TCAP=50 launch
-  int *big_count;
+  VVCtl *ctl;
+  int *list;                 // 4 work lists of nown entries each (slot s at list + s*nown)
   float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
-  float igdr;                // 1/gdr: voxel index of a z coordinate, m = g*igdr + 20 (estimate only, see mono_search_est)
 };
 
 // per-warp shared-memory working set; TCAP = max fan size it can hold.  Almost every vertex has <= 16 triangles, so the
@@ -162,29 +172,10 @@ __device__ __forceinline__ int mono_search(const float *gzt, bool pa, Pred pred)
   return s;
 }
 
-// Estimate-and-verify form of the same search.  Every plane expression is (up to rounding) linear in gz, so the flip index
-// can be predicted by solving the linear equation in fast float arithmetic (est = real-valued voxel index of the threshold
-// crossing).  The prediction is only a hint: it is accepted iff the exact predicate -- the same arithmetic as above -- holds
-// pa at voxel s and !pa at voxel s+1, which by monotonicity identifies the flip uniquely; otherwise (the crossing lies
-// within rounding of a voxel, |est - integer| <~ 1e-3) the lane takes the six-step search.  2 exact evaluations instead of 6.
-template <class Pred>
-__device__ __forceinline__ int mono_search_est(const float *gzt, bool pa, bool need, float est, Pred pred)
-{
-  int s = __float2int_rd(est);                 // NaN -> 0, +-inf saturate: clamped below
-  s = min(max(s, 0), VV_GS - 2);
-  const bool ok = (pred(gzt[s]) == pa) && (pred(gzt[s + 1]) != pa);
-  if (__any_sync(VV_FULLWARP, need && !ok)) {
-    VV_STAT(9, 1);
-    const int t = mono_search(gzt, pa, pred);
-    if (!ok) s = t;
-  }
-  return s;
-}
-
-// mask of the voxels where pv(f(gz[m])) holds.  fa, fb = f at the two ends.  lo = last index that agrees with end A
-// (40 if the line is not cut by the predicate), pa = the predicate at end A.  EST: est = predicted crossing (see above).
-template <bool EST = false, class F, class PV>
-__device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float fb, F f, PV pv, int &lo, bool &pa, float est = 0.f)
+// mask of the voxels where pv(f(g[m])) holds.  fa, fb = f at the two ends.  lo = last index that agrees with end A
+// (40 if the line is not cut by the predicate), pa = the predicate at end A.
+template <class F, class PV>
+__device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float fb, F f, PV pv, int &lo, bool &pa)
 {
   pa = pv(fa);
   const bool pb = pv(fb);
@@ -193,8 +184,7 @@ __device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float 
   if (cutm) {
     VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
     const bool pa_ = pa;
-    const int s = EST ? mono_search_est(gzt, pa_, pa != pb, est, [&](float g) { return pv(f(g)); })
-                      : mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
+    const int s = mono_search(gzt, pa_, [&](float g) { return pv(f(g)); });
     if (pa != pb) lo = s;
   }
   // lmt[1][b] = the b lowest voxels, lmt[0][b] = the others (gzt + 64 floats = two tables of 64 x uint64)
@@ -202,11 +192,77 @@ __device__ __forceinline__ uint64_t mono_mask(const float *gzt, float fa, float 
   return lmt[(pa ? 64 : 0) + lo + 1];
 }
 
-struct TriCtx {
-  float4 P4, P5, P6, P7, P8, P9;
-  float tV, tV2, tW0, tW1, tW2, tE, piz, eps;
-  int open;
+// ---------------------------------------------------------------------------------------------------------------
+// One plane expression of the reference as a function of ONE grid coordinate (axis VAR), the two others fixed.
+// The reference evaluates sp = fma(tz,cz, fma(ty,cy, fma(tx,cx, 0))) (R1) where the term inputs are
+//   KIND 0 (voronoi planes, crixus_d.cu:604-611):  t = (g + pi) - off      g = grid offset, pi = vertex, off = point of the plane
+//   KIND 1 (edge plane, :629-633):                 t = g - off
+//   KIND 2 (wall planes :640-648, cubes :531-540):  t = g
+// Whatever sits outside the varying term is hoisted (same operations, same order -> same bits):
+//   VAR 2: pre = fma(ty,cy, fma(tx,cx,0));             f(g) = fma(t(g), cz, pre)
+//   VAR 1: pre = fma(tx,cx,0), a2 = tz;                f(g) = fma(a2, cz, fma(t(g), cy, pre))
+//   VAR 0: a1 = ty, a2 = tz;                           f(g) = fma(a2, cz, fma(a1, cy, fma(t(g), cx, 0)))
+// Every step is a correctly rounded operation that is monotone in its varying argument, so f is a monotone function of g
+// (rising or falling with the sign of the coefficient of axis VAR) for every VAR -- the premise of mono_search.
+template <int D> __device__ __forceinline__ float cget(const f3 &v) { return D == 0 ? v.x : (D == 1 ? v.y : v.z); }
+
+template <int VAR, int KIND>
+struct PlaneF {
+  float cv, add, off, pre, a1, k1, a2, k2;
+  __device__ __forceinline__ float operator()(float g) const
+  {
+    const float t = KIND == 0 ? fsub(fadd(g, add), off) : (KIND == 1 ? fsub(g, off) : g);
+    if (VAR == 2) return ffma(t, cv, pre);
+    if (VAR == 1) return ffma(a2, k2, ffma(t, cv, pre));
+    return ffma(a2, k2, ffma(a1, k1, ffma(t, cv, 0.f)));
+  }
 };
+// c = plane vector, off = point of the plane (KIND 0, 1), pi = vertex (KIND 0), gp = grid offsets (component VAR is ignored)
+template <int VAR, int KIND>
+__device__ __forceinline__ PlaneF<VAR, KIND> make_plane(const f3 &c, const f3 &off, const f3 &pi, const f3 &gp)
+{
+  PlaneF<VAR, KIND> F;
+  const float tx = KIND == 0 ? fsub(fadd(gp.x, pi.x), off.x) : (KIND == 1 ? fsub(gp.x, off.x) : gp.x);
+  const float ty = KIND == 0 ? fsub(fadd(gp.y, pi.y), off.y) : (KIND == 1 ? fsub(gp.y, off.y) : gp.y);
+  const float tz = KIND == 0 ? fsub(fadd(gp.z, pi.z), off.z) : (KIND == 1 ? fsub(gp.z, off.z) : gp.z);
+  F.cv = cget<VAR>(c); F.add = cget<VAR>(pi); F.off = cget<VAR>(off);
+  F.pre = 0.f; F.a1 = 0.f; F.k1 = 0.f; F.a2 = 0.f; F.k2 = 0.f;
+  if (VAR == 2) F.pre = ffma(ty, c.y, ffma(tx, c.x, 0.f));
+  if (VAR == 1) { F.pre = ffma(tx, c.x, 0.f); F.a2 = tz; F.k2 = c.z; }
+  if (VAR == 0) { F.a1 = ty; F.k1 = c.y; F.a2 = tz; F.k2 = c.z; }
+  return F;
+}
+// voxel-cube coordinates of a line: a along the line axis AX, (u, v) on the two other axes in ascending order
+// (AX 2: u = x, v = y;  AX 1: u = x, v = z;  AX 0: u = y, v = z).  The lines of one u form a "row".
+template <int AX> __device__ __forceinline__ f3 place3(float a, float u, float v)
+{
+  return AX == 2 ? mk3(u, v, a) : (AX == 1 ? mk3(u, a, v) : mk3(a, u, v));
+}
+
+// the plane vectors of one fan triangle as the kernel keeps them in shared memory (phase A)
+struct TriPlanes {
+  f3 c0, c1, n, c3, c4;     // axes of the two sampling cubes (crixus_d.cu:507-529)
+  f3 e1, c6, e2, c8;        // voronoi planes: vector and midpoint (:552-561)
+  f3 c9, c10, c11, en;      // wall wedge (:562-579) and edge normal (:581-596)
+};
+#define VV_LOAD_VE(P, t)                                                                                      \
+  {                                                                                                           \
+    const float4 P4 = (P)[4], P5 = (P)[5], P6 = (P)[6], P9 = (P)[9];                                          \
+    t.e1 = mk3(P4.x, P4.y, P4.z); t.c6 = mk3(P4.w, P5.x, P5.y); t.e2 = mk3(P5.z, P5.w, P6.x);                 \
+    t.c8 = mk3(P6.y, P6.z, P6.w); t.en = mk3(P9.y, P9.z, P9.w);                                               \
+  }
+#define VV_LOAD_W(P, t)                                                                                       \
+  {                                                                                                           \
+    const float4 P7 = (P)[7], P8 = (P)[8], P9 = (P)[9];                                                       \
+    t.c9 = mk3(P7.x, P7.y, P7.z); t.c10 = mk3(P7.w, P8.x, P8.y); t.c11 = mk3(P8.z, P8.w, P9.x);               \
+  }
+#define VV_LOAD_CUBES(P, t)                                                                                   \
+  {                                                                                                           \
+    const float4 P0 = (P)[0], P1 = (P)[1], P2 = (P)[2], P3 = (P)[3];                                          \
+    t.c0 = mk3(P0.x, P0.y, P0.z); t.c1 = mk3(P0.w, P1.x, P1.y); t.n = mk3(P1.z, P1.w, P2.x);                  \
+    t.c3 = mk3(P2.y, P2.z, P2.w); t.c4 = mk3(P3.x, P3.y, P3.z);                                               \
+  }
+
 // Exact per-voxel evaluation of triangle j on one line (the reference's loop body, crixus_d.cu:598-662): kill mask and
 // halving events.  Used for the lanes where the threshold shortcut cannot prove its result (two voxels within eps of a
 // plane on a line that is cut by it, or an expression exactly equal to a threshold).  One function per plane family,
@@ -215,23 +271,33 @@ struct TriCtx {
 // k = 1..3): no address of a caller's register variable escapes into this out-of-line function, so the
 // per-voxel state of the hot loop (alive, h[5]) stays in registers (with reference parameters it lived in local memory:
 // 2.5 % of the executed instructions were LDL/STL).
-__device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool mine, unsigned long long *res, int lane)
+template <int AX> struct TriCtxVE {
+  PlaneF<AX, 0> V, V2;
+  PlaneF<AX, 1> E;
+  float eps;
+  int open;
+};
+template <int AX> struct TriCtxW {
+  PlaneF<AX, 2> W0, W1, W2;
+  float eps;
+};
+template <int AX>
+__device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtxVE<AX> &c, bool mine, unsigned long long *res, int lane)
 {
   if (!mine) return;   // called by the whole warp (keeps it converged); only the flagged lanes do the work
   const float eps = c.eps;
   uint64_t k = 0ull, c1 = 0ull, c2 = 0ull, c3 = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
-    const float q2 = fadd(g, c.piz);
-    const float sV = ffma(fsub(q2, c.P5.y), c.P4.z, c.tV);
+    const float sV = c.V(g);
     bool kill = sV > eps;
     int nh = fabsf(sV) < eps;
     if (c.open) {
-      const float sV2 = ffma(fsub(q2, c.P6.w), c.P6.x, c.tV2);
+      const float sV2 = c.V2(g);
       kill |= sV2 > eps;
       nh += fabsf(sV2) < eps;
     }
-    const float sE = ffma(fsub(g, c.P4.z), c.P9.w, c.tE);
+    const float sE = c.E(g);
     kill |= sE > eps;
     nh += fabsf(sE) < eps;
     if (kill) k |= 1ull << m;
@@ -241,14 +307,15 @@ __device__ __noinline__ void exact_tri_ve(const VVArgs &a, const TriCtx &c, bool
   }
   res[lane] = k; res[32 + lane] = c1; res[64 + lane] = c2; res[96 + lane] = c3;
 }
-__device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool mine, unsigned long long *res, int lane)
+template <int AX>
+__device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtxW<AX> &c, bool mine, unsigned long long *res, int lane)
 {
   if (!mine) return;
   const float eps = c.eps, neps = -c.eps;
   uint64_t k = 0ull, n0 = 0ull;
   for (int m = 0; m < VV_GS; m++) {
     const float g = a.gz[m];
-    const float w0 = ffma(g, c.P7.z, c.tW0), w1 = ffma(g, c.P8.y, c.tW1), w2 = ffma(g, c.P9.x, c.tW2);
+    const float w0 = c.W0(g), w1 = c.W1(g), w2 = c.W2(g);
     const bool inside = !(w0 < neps) && !(w1 < neps) && !(w2 < neps);
     const bool hw = fabsf(w0) < eps;
     if (inside && !hw) k |= 1ull << m;
@@ -267,11 +334,8 @@ __device__ __noinline__ void exact_tri_w(const VVArgs &a, const TriCtx &c, bool 
 // against a band of 2*eps: for dr below ~2e-3 (length units of the mesh) a cut line has two or more voxels within eps
 // of a plane as a rule, and those lanes also need the flip of {f > -eps}.  The non-WIDE kernel leaves that (then
 // rare) case to exact_tri; the extra gated search costs ~8 % when it is never needed, hence two kernels.
-// EST: (T, ek, ed) describe the linear form of f for the estimate: f(g) ~ T + (g + D)*C, crossing of threshold th at voxel
-// index (th - T)*ek + ed with ek = igdr/C, ed = 20 - D*igdr.
-template <bool WIDE, bool EST = false, class F>
-__device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig,
-                                           float T = 0.f, float ek = 0.f, float ed = 0.f)
+template <bool WIDE, class F>
+__device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb, F f, float eps, uint64_t &K, uint64_t &H, bool &trig)
 {
   const float neps = -eps;
   const bool pa = fa > eps, pb = fb > eps, Aa = fa > neps, Ab = fb > neps;
@@ -283,8 +347,7 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   const unsigned cutm = __ballot_sync(VV_FULLWARP, cutK || cutA);
   if (cutm) {
     VV_STAT(2, 1); VV_STAT(3, __popc(cutm));
-    const int s = EST ? mono_search_est(gzt, qa, cutK || cutA, ffma(fsub(th, T), ek, ed), [&](float g) { return f(g) > th; })
-                      : mono_search(gzt, qa, [&](float g) { return f(g) > th; });
+    const int s = mono_search(gzt, qa, [&](float g) { return f(g) > th; });
     if (cutK || cutA) lo = s;
   }
   const uint64_t *lmt = reinterpret_cast<const uint64_t *>(gzt + 64);
@@ -321,51 +384,49 @@ __device__ __forceinline__ void plane_kill(const float *gzt, float fa, float fb,
   }
 }
 
-// First pass, a whole x-row of 41 z-lines at a time: which lines are removed entirely by a single triangle?
+// First pass, a whole row of 41 lines at a time: which lines are removed entirely by a single triangle?
 // A line dies if both of its ends lie beyond a voronoi/edge plane or strictly inside a wall sector (exact, by
-// monotonicity along z).  Along z each plane expression takes its smaller value at a FIXED end (A if its z coefficient
-// is >= 0, else B), so "both ends pass" is one predicate of the y index l -- again a monotone step function, found by
-// the same six-evaluation search over gz[l].  One lane per (row, triangle): ~6 searches instead of 41 line tests.
-template <bool OPEN, class VVWarp>
+// monotonicity along the line).  Along the line each plane expression takes its smaller value at a FIXED end (A if its
+// coefficient of the line axis is >= 0, else B), so "both ends pass" is one predicate of the in-row index l -- again a monotone
+// step function, found by the same six-evaluation search over g[l].  One lane per (row, triangle): ~6 searches instead of
+// 41 line tests.
+template <int AX, bool OPEN, class VVWarp>
 __device__ __forceinline__ void rows_dead(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, int lane,
                                           unsigned long long *rd)
 {
+  constexpr int VX = (AX == 2) ? 1 : 2;     // the in-row axis (place3)
   const float eps = a.eps, neps = -a.eps;
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
-  const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
   const int nitems = VV_GS * tris;
   for (int base = 0; base < nitems; base += 32) {   // warp-uniform trip count
     const int item = base + lane;
     const bool act = item < nitems;
     const int j = act ? item / VV_GS : 0, k = act ? item - j * VV_GS : 0;   // consecutive lanes: same triangle (broadcast loads)
-    const float gp0 = gzt[k];
-    const float q0 = fadd(gp0, pi.x);
-    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P7 = w.plane[j][7], P8 = w.plane[j][8],
-                 P9 = w.plane[j][9];
+    const float gu = gzt[k];
+    TriPlanes t;
+    VV_LOAD_VE(w.plane[j], t);
+    VV_LOAD_W(w.plane[j], t);
+    // grid offsets of the row with the line axis at the end where the expression is smallest
+    auto low_end = [&](const f3 &c) { return place3<AX>(cget<AX>(c) >= 0.f ? gA : gB, gu, 0.f); };
     int lo;
     bool pa;
     uint64_t dead;
-    {  // voronoi plane: s = ffma(fsub(q2, P5.y), P4.z, ffma(fsub(fadd(gy, pi.y), P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0)))
-      const float X = ffma(fsub(q0, P4.w), P4.x, 0.f), c = fsub(P4.z >= 0.f ? q2A : q2B, P5.y);
-      auto f = [&](float g) { return ffma(c, P4.z, ffma(fsub(fadd(g, pi.y), P5.x), P4.y, X)); };
+    {  // voronoi plane
+      const PlaneF<VX, 0> f = make_plane<VX, 0>(t.e1, t.c6, pi, low_end(t.e1));
       dead = mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
     }
     if (OPEN) {
-      const float X = ffma(fsub(q0, P6.y), P5.z, 0.f), c = fsub(P6.x >= 0.f ? q2A : q2B, P6.w);
-      auto f = [&](float g) { return ffma(c, P6.x, ffma(fsub(fadd(g, pi.y), P6.z), P5.w, X)); };
+      const PlaneF<VX, 0> f = make_plane<VX, 0>(t.e2, t.c8, pi, low_end(t.e2));
       dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
     }
     {  // edge plane
-      const float X = ffma(fsub(gp0, P4.x), P9.y, 0.f), c = fsub(P9.w >= 0.f ? gA : gB, P4.z);
-      auto f = [&](float g) { return ffma(c, P9.w, ffma(fsub(g, P4.y), P9.z, X)); };
+      const PlaneF<VX, 1> f = make_plane<VX, 1>(t.en, t.e1, pi, low_end(t.en));
       dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
     }
     {  // wall sector: w0 >= eps, w1 >= -eps, w2 >= -eps at both ends
-      const float X0 = ffma(gp0, P7.x, 0.f), X1 = ffma(gp0, P7.w, 0.f), X2 = ffma(gp0, P8.z, 0.f);
-      const float e0 = P7.z >= 0.f ? gA : gB, e1 = P8.y >= 0.f ? gA : gB, e2 = P9.x >= 0.f ? gA : gB;
-      auto f0 = [&](float g) { return ffma(e0, P7.z, ffma(g, P7.y, X0)); };
-      auto f1 = [&](float g) { return ffma(e1, P8.y, ffma(g, P8.x, X1)); };
-      auto f2 = [&](float g) { return ffma(e2, P9.x, ffma(g, P8.w, X2)); };
+      const PlaneF<VX, 2> f0 = make_plane<VX, 2>(t.c9, t.c9, pi, low_end(t.c9));
+      const PlaneF<VX, 2> f1 = make_plane<VX, 2>(t.c10, t.c10, pi, low_end(t.c10));
+      const PlaneF<VX, 2> f2 = make_plane<VX, 2>(t.c11, t.c11, pi, low_end(t.c11));
       uint64_t m = mono_mask(gzt, f0(gA), f0(gB), f0, [&](float v) { return v >= eps; }, lo, pa);
       m &= mono_mask(gzt, f1(gA), f1(gB), f1, [&](float v) { return v >= neps; }, lo, pa);
       m &= mono_mask(gzt, f2(gA), f2(gB), f2, [&](float v) { return v >= neps; }, lo, pa);
@@ -404,61 +465,50 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
   return s;
 }
 
-// Second pass: the weight of one surviving z-line (in units of 2^-31), every lane of the warp on a line of its own.
-// Lanes without a line (valid == false) run along with an empty line.
-template <bool OPEN, bool WIDE, bool EST, class VVWarp>
-__device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gp0,
-                                                 float gp1, bool valid, unsigned long long *xres, int lane)
+// Second pass: the weight of one surviving line (in units of 2^-31), every lane of the warp on a line of its own.
+// Lanes without a line (valid == false) run along with an empty line.  gu, gv: grid offsets of the line on the two axes other
+// than AX (place3).
+template <int AX, bool OPEN, bool WIDE, class VVWarp>
+__device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gu,
+                                                 float gv, bool valid, unsigned long long *xres, int lane)
 {
   const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
-  const float q0 = fadd(gp0, pi.x), q1 = fadd(gp1, pi.y);
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
-  const float q2A = fadd(gA, pi.z), q2B = fadd(gB, pi.z);
+  const f3 gp = place3<AX>(0.f, gu, gv);
   uint64_t alive = valid ? VV_ALL : 0ull;
   uint64_t h[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
   // ---------------- planes (crixus_d.cu:598-662) in two triangle loops -- voronoi (+ second voronoi) and edge planes first,
   // wall tetrahedra second.  The per-voxel result is a product over triangles and families, so the order is free; two
   // small loop bodies instead of one large one keep the hot code inside the instruction cache (ncu: instruction-fetch
   // stalls were a quarter of the issue interval), and lines that the voronoi planes remove never reach the wall tests.
-  // c5 = (P4.x,P4.y,P4.z) c6 = (P4.w,P5.x,P5.y) c7 = (P5.z,P5.w,P6.x) c8 = (P6.y,P6.z,P6.w)
-  // c9 = (P7.x,P7.y,P7.z) c10 = (P7.w,P8.x,P8.y) c11 = (P8.z,P8.w,P9.x) en = (P9.y,P9.z,P9.w)
   for (int j = 0; j < tris; j++) {
     if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
-    const float4 P4 = w.plane[j][4], P5 = w.plane[j][5], P6 = w.plane[j][6], P9 = w.plane[j][9];
-    const float tV = ffma(fsub(q1, P5.x), P4.y, ffma(fsub(q0, P4.w), P4.x, 0.f));
-    float tV2 = 0.f;
-    if (OPEN) tV2 = ffma(fsub(q1, P6.z), P5.w, ffma(fsub(q0, P6.y), P5.z, 0.f));
-    const float tE = ffma(fsub(gp1, P4.y), P9.z, ffma(fsub(gp0, P4.x), P9.y, 0.f));
-    auto fV = [&](float g) { return ffma(fsub(fadd(g, pi.z), P5.y), P4.z, tV); };
-    auto fV2 = [&](float g) { return ffma(fsub(fadd(g, pi.z), P6.w), P6.x, tV2); };
-    auto fE = [&](float g) { return ffma(fsub(g, P4.z), P9.w, tE); };
+    TriPlanes t;
+    VV_LOAD_VE(w.plane[j], t);
+    const PlaneF<AX, 0> fV = make_plane<AX, 0>(t.e1, t.c6, pi, gp);
+    const PlaneF<AX, 1> fE = make_plane<AX, 1>(t.en, t.e1, pi, gp);
+    PlaneF<AX, 0> fV2 = fV;
+    if (OPEN) fV2 = make_plane<AX, 0>(t.e2, t.c8, pi, gp);
     uint64_t K = 0ull, HV = 0ull, HV2 = 0ull, HE = 0ull;
     bool trig = false;
     const bool live = alive != 0ull;
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
-    const float sVa = ffma(fsub(q2A, P5.y), P4.z, tV), sVb = ffma(fsub(q2B, P5.y), P4.z, tV);
-    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps))))
-      plane_kill<WIDE, EST>(gzt, sVa, sVb, fV, eps, K, HV, trig, tV, EST ? __fdividef(a.igdr, P4.z) : 0.f,
-                            EST ? ffma(fsub(P5.y, pi.z), a.igdr, 20.f) : 0.f);
+    const float sVa = fV(gA), sVb = fV(gB);
+    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill<WIDE>(gzt, sVa, sVb, fV, eps, K, HV, trig);
     if (OPEN) {
-      const float s2a = ffma(fsub(q2A, P6.w), P6.x, tV2), s2b = ffma(fsub(q2B, P6.w), P6.x, tV2);
-      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps))))
-        plane_kill<WIDE, EST>(gzt, s2a, s2b, fV2, eps, K, HV2, trig, tV2, EST ? __fdividef(a.igdr, P6.x) : 0.f,
-                              EST ? ffma(fsub(P6.w, pi.z), a.igdr, 20.f) : 0.f);
+      const float s2a = fV2(gA), s2b = fV2(gB);
+      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill<WIDE>(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
     }
-    const float sEa = ffma(fsub(gA, P4.z), P9.w, tE), sEb = ffma(fsub(gB, P4.z), P9.w, tE);
-    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps))))
-      plane_kill<WIDE, EST>(gzt, sEa, sEb, fE, eps, K, HE, trig, tE, EST ? __fdividef(a.igdr, P9.w) : 0.f,
-                            EST ? ffma(P4.z, a.igdr, 20.f) : 0.f);
+    const float sEa = fE(gA), sEb = fE(gB);
+    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill<WIDE>(gzt, sEa, sEb, fE, eps, K, HE, trig);
     trig = trig && live;
     VV_STAT(1, 1);
     if (__any_sync(VV_FULLWARP, trig)) {
       VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
-      TriCtx c;
-      c.P4 = P4; c.P5 = P5; c.P6 = P6; c.P7 = P4; c.P8 = P4; c.P9 = P9;
-      c.tV = tV; c.tV2 = tV2; c.tW0 = 0.f; c.tW1 = 0.f; c.tW2 = 0.f; c.tE = tE; c.piz = pi.z; c.eps = eps; c.open = OPEN ? 1 : 0;
-      exact_tri_ve(a, c, trig, xres, lane);
+      TriCtxVE<AX> c;
+      c.V = fV; c.V2 = fV2; c.E = fE; c.eps = eps; c.open = OPEN ? 1 : 0;
+      exact_tri_ve<AX>(a, c, trig, xres, lane);
       __syncwarp();
       if (trig) {   // voxels with >= 1, >= 2, >= 3 halvings: one increment each (the third only with a second voronoi plane)
         K = xres[lane];
@@ -472,18 +522,16 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   }
   for (int j = 0; j < tris; j++) {
     if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
-    const float4 P7 = w.plane[j][7], P8 = w.plane[j][8], P9 = w.plane[j][9];
-    const float tW0 = ffma(gp1, P7.y, ffma(gp0, P7.x, 0.f));
-    const float tW1 = ffma(gp1, P8.x, ffma(gp0, P7.w, 0.f));
-    const float tW2 = ffma(gp1, P8.w, ffma(gp0, P8.z, 0.f));
-    auto fW0 = [&](float g) { return ffma(g, P7.z, tW0); };
-    auto fW1 = [&](float g) { return ffma(g, P8.y, tW1); };
-    auto fW2 = [&](float g) { return ffma(g, P9.x, tW2); };
+    TriPlanes t;
+    VV_LOAD_W(w.plane[j], t);
+    const PlaneF<AX, 2> fW0 = make_plane<AX, 2>(t.c9, t.c9, pi, gp);
+    const PlaneF<AX, 2> fW1 = make_plane<AX, 2>(t.c10, t.c10, pi, gp);
+    const PlaneF<AX, 2> fW2 = make_plane<AX, 2>(t.c11, t.c11, pi, gp);
     const bool live = alive != 0ull;
     // ---- wall tetrahedron: inside = all three w >= -eps; inside and |w0| < eps -> halved, inside otherwise -> removed
-    const float w0a = ffma(gA, P7.z, tW0), w0b = ffma(gB, P7.z, tW0);
-    const float w1a = ffma(gA, P8.y, tW1), w1b = ffma(gB, P8.y, tW1);
-    const float w2a = ffma(gA, P9.x, tW2), w2b = ffma(gB, P9.x, tW2);
+    const float w0a = fW0(gA), w0b = fW0(gB);
+    const float w1a = fW1(gA), w1b = fW1(gB);
+    const float w2a = fW2(gA), w2b = fW2(gB);
     const bool noneW = ((w0a < neps) && (w0b < neps)) || ((w1a < neps) && (w1b < neps)) || ((w2a < neps) && (w2b < neps));
     if (!__any_sync(VV_FULLWARP, live && !noneW)) continue;
     uint64_t K, HW;
@@ -491,11 +539,9 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     auto ge = [&](float v) { return !(v < neps); };
     int lo0, lo1, lo2;
     bool pa0, pa1, pa2;
-    // estimate of the crossing of w = -eps: voxel index (neps - tW)*igdr/C + 20
-    const float ek0 = EST ? __fdividef(a.igdr, P7.z) : 0.f, ek1 = EST ? __fdividef(a.igdr, P8.y) : 0.f, ek2 = EST ? __fdividef(a.igdr, P9.x) : 0.f;
-    const uint64_t IN0 = mono_mask<EST>(gzt, w0a, w0b, fW0, ge, lo0, pa0, ffma(fsub(neps, tW0), ek0, 20.f));
-    const uint64_t IN1 = mono_mask<EST>(gzt, w1a, w1b, fW1, ge, lo1, pa1, ffma(fsub(neps, tW1), ek1, 20.f));
-    const uint64_t IN2 = mono_mask<EST>(gzt, w2a, w2b, fW2, ge, lo2, pa2, ffma(fsub(neps, tW2), ek2, 20.f));
+    const uint64_t IN0 = mono_mask(gzt, w0a, w0b, fW0, ge, lo0, pa0);
+    const uint64_t IN1 = mono_mask(gzt, w1a, w1b, fW1, ge, lo1, pa1);
+    const uint64_t IN2 = mono_mask(gzt, w2a, w2b, fW2, ge, lo2, pa2);
     const uint64_t inside = IN0 & IN1 & IN2;
     // LT = {w0 < eps}.  On a line cut by IN0 it is the complement of IN0 plus the n voxels of IN0 next to the flip that
     // lie in the wall plane (n = 0 or 1 in all but degenerate cases).
@@ -521,17 +567,16 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     if (__any_sync(VV_FULLWARP, needLT)) {
       int lo_;
       bool pa_;
-      const uint64_t m = mono_mask<EST>(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_, ffma(fsub(eps, tW0), ek0, 20.f));
+      const uint64_t m = mono_mask(gzt, w0a, w0b, fW0, [&](float v) { return v < eps; }, lo_, pa_);
       if (needLT) LT = m;
     }
     K = inside & ~LT;
     HW = inside & LT;
     trig = trig && live;
     if (__any_sync(VV_FULLWARP, trig)) {
-      TriCtx c;
-      c.P4 = P7; c.P5 = P7; c.P6 = P7; c.P7 = P7; c.P8 = P8; c.P9 = P9;
-      c.tV = 0.f; c.tV2 = 0.f; c.tW0 = tW0; c.tW1 = tW1; c.tW2 = tW2; c.tE = 0.f; c.piz = pi.z; c.eps = eps; c.open = 0;
-      exact_tri_w(a, c, trig, xres, lane);
+      TriCtxW<AX> c;
+      c.W0 = fW0; c.W1 = fW1; c.W2 = fW2; c.eps = eps;
+      exact_tri_w<AX>(a, c, trig, xres, lane);
       __syncwarp();
       if (trig) { K = xres[lane]; HW = xres[32 + lane]; }
       __syncwarp();
@@ -543,17 +588,16 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   uint64_t hit = 0ull;
   for (int j = 0; j < tris; j++) {
     if (!__any_sync(VV_FULLWARP, (alive & ~hit) != 0ull)) break;
-    const float4 P0 = w.plane[j][0], P1 = w.plane[j][1], P2 = w.plane[j][2], P3 = w.plane[j][3];
-    const float t0 = ffma(gp1, P0.y, ffma(gp0, P0.x, 0.f));  // c0
-    const float t1 = ffma(gp1, P1.x, ffma(gp0, P0.w, 0.f));  // c1
-    const float t2 = ffma(gp1, P1.w, ffma(gp0, P1.z, 0.f));  // c2
-    const float t3 = ffma(gp1, P2.z, ffma(gp0, P2.y, 0.f));  // c3
-    const float t4 = ffma(gp1, P3.y, ffma(gp0, P3.x, 0.f));  // c4
-    const float a0 = ffma(gA, P0.z, t0), b0 = ffma(gB, P0.z, t0);
-    const float a1 = ffma(gA, P1.y, t1), b1 = ffma(gB, P1.y, t1);
-    const float a2 = ffma(gA, P2.x, t2), b2 = ffma(gB, P2.x, t2);
-    const float a3 = ffma(gA, P2.w, t3), b3 = ffma(gB, P2.w, t3);
-    const float a4 = ffma(gA, P3.z, t4), b4 = ffma(gB, P3.z, t4);
+    TriPlanes t;
+    VV_LOAD_CUBES(w.plane[j], t);
+    const PlaneF<AX, 2> f0 = make_plane<AX, 2>(t.c0, t.c0, pi, gp), f1 = make_plane<AX, 2>(t.c1, t.c1, pi, gp),
+                        f2 = make_plane<AX, 2>(t.n, t.n, pi, gp), f3_ = make_plane<AX, 2>(t.c3, t.c3, pi, gp),
+                        f4 = make_plane<AX, 2>(t.c4, t.c4, pi, gp);
+    const float a0 = f0(gA), b0 = f0(gB);
+    const float a1 = f1(gA), b1 = f1(gB);
+    const float a2 = f2(gA), b2 = f2(gB);
+    const float a3 = f3_(gA), b3 = f3_(gB);
+    const float a4 = f4(gA), b4 = f4(gB);
     // both ends inside a cube => the whole line is inside it
     const bool i0 = fmaxf(fabsf(a0), fabsf(b0)) <= thr, i1 = fmaxf(fabsf(a1), fabsf(b1)) <= thr, i2 = fmaxf(fabsf(a2), fabsf(b2)) <= thr,
                i3 = fmaxf(fabsf(a3), fabsf(b3)) <= thr, i4 = fmaxf(fabsf(a4), fabsf(b4)) <= thr;
@@ -567,14 +611,12 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
       auto ge = [&](float v) { return v >= nthr; };
       int lo_;
       bool pa_;
-#define VV_SLAB(fa, fb, C, T)                                                                       \
-  (mono_mask(gzt, fa, fb, [&](float g) { return ffma(g, C, T); }, le, lo_, pa_) &                    \
-   mono_mask(gzt, fa, fb, [&](float g) { return ffma(g, C, T); }, ge, lo_, pa_))
-      const uint64_t s0 = VV_SLAB(a0, b0, P0.z, t0);
-      const uint64_t s1 = VV_SLAB(a1, b1, P1.y, t1);
-      const uint64_t s2 = VV_SLAB(a2, b2, P2.x, t2);
-      const uint64_t s3 = VV_SLAB(a3, b3, P2.w, t3);
-      const uint64_t s4 = VV_SLAB(a4, b4, P3.z, t4);
+#define VV_SLAB(fa, fb, F) (mono_mask(gzt, fa, fb, F, le, lo_, pa_) & mono_mask(gzt, fa, fb, F, ge, lo_, pa_))
+      const uint64_t s0 = VV_SLAB(a0, b0, f0);
+      const uint64_t s1 = VV_SLAB(a1, b1, f1);
+      const uint64_t s2 = VV_SLAB(a2, b2, f2);
+      const uint64_t s3 = VV_SLAB(a3, b3, f3_);
+      const uint64_t s4 = VV_SLAB(a4, b4, f4);
 #undef VV_SLAB
       hit |= (s0 & s1 & s2) | (s2 & s3 & s4);
     }
@@ -582,15 +624,70 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   return valid ? group_weight(hit & alive, h, a.cmax) : 0ll;
 }
 
-template <int TCAP, bool LIST, bool WIDE, bool EST = false>
-__global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volume(const __grid_constant__ VVArgs a)
+// ---------------------------------------------------------------------------------------------------------------
+// Line direction per vertex.  k_vv_normal_sums adds the (quantised) normals of the segments onto their three vertices with one
+// packed 64-bit atomic each -- integer sums, so the outcome does not depend on the order -- and k_vv_classify deals the owned
+// vertices to the three work lists by the dominant axis of that sum.  The sum only approximates the kernel's own avnorm; a
+// different choice changes the amount of work, never the result.
+__global__ void __launch_bounds__(256) k_vv_normal_sums(const float4 *__restrict__ norm, const int4 *__restrict__ ep, int64_t nbe,
+                                                        int64_t nvert, unsigned long long *__restrict__ acc)
+{
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nbe; s += (int64_t)gridDim.x * blockDim.x) {
+    const float4 n = __ldg(&norm[s]);
+    const int4 E = __ldg(&ep[s]);
+    auto q = [](float x) { return (unsigned long long)(__float2int_rn(fminf(fmaxf(x, -1.f), 1.f) * 100.f) + 128); };   // NaN -> 128 - 100
+    const unsigned long long v = q(n.x) | (q(n.y) << 16) | (q(n.z) << 32) | (1ull << 48);
+    if ((uint64_t)E.x < (uint64_t)nvert) atomicAdd(&acc[E.x], v);
+    if ((uint64_t)E.y < (uint64_t)nvert) atomicAdd(&acc[E.y], v);
+    if ((uint64_t)E.z < (uint64_t)nvert) atomicAdd(&acc[E.z], v);
+  }
+}
+
+__device__ __forceinline__ int64_t vv_owned_vertex(const VVArgs &a, int64_t idx)
+{
+  const int64_t q = idx / a.chunk;
+  return a.v_begin + (q * a.nparts + a.part) * a.chunk + (idx - q * a.chunk);
+}
+
+__global__ void __launch_bounds__(256) k_vv_classify(const __grid_constant__ VVArgs a, const unsigned long long *__restrict__ acc, int force)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t n32 = (a.nown + 31) & ~(int64_t)31;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n32; idx += (int64_t)gridDim.x * blockDim.x) {   // whole warps
+    int cls = -1;
+    int64_t i = 0;
+    if (idx < a.nown) {
+      i = vv_owned_vertex(a, idx);
+      const unsigned long long s = acc[i];
+      const int c = (int)(s >> 48);
+      const int sx = abs((int)(s & 0xffffu) - 128 * c), sy = abs((int)((s >> 16) & 0xffffu) - 128 * c),
+                sz = abs((int)((s >> 32) & 0xffffu) - 128 * c);
+      cls = (sz >= sx && sz >= sy) ? 2 : (sy >= sx ? 1 : 0);      // ties: z, then y (the cheaper evaluations)
+      if (force >= 0) cls = force;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+      if (m) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&a.ctl->count[k], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (cls == k) a.list[(int64_t)k * a.nown + base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+      }
+    }
+  }
+}
+
+// SLOT: work list of this launch (0..2: vertices whose lines run along x, y, z; 3: the fans with more than 16 triangles)
+template <int TCAP, int SLOT, bool WIDE, int AX>
+__global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? (AX == 2 ? 6 : 5) : 4) k_vert_volume(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
-  __shared__ __align__(16) float gzt[64 + 256];   // gz[0..40] for lane-dependent lookups (padded to 64), then the two
+  __shared__ __align__(16) float gzt[64 + 256];   // g[0..40] for lane-dependent lookups (padded to 64), then the two
                                                   // 64-entry uint64 mask tables used by mono_mask
   __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
-  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = z-line (k, l) is dead
+  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = line (k, l) is dead
   __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
@@ -606,20 +703,15 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
   }
   __syncthreads();
   const cx_params &p = a.p;
+  const int *list = a.list + (int64_t)SLOT * a.nown;
+  const int64_t nlist = a.ctl->count[SLOT];     // complete: filled by an earlier launch
 
   for (;;) {
     unsigned long long widx = 0;
-    if (lane == 0) widx = atomicAdd(a.work, 1ull);
+    if (lane == 0) widx = atomicAdd(&a.ctl->work[SLOT], 1ull);
     widx = __shfl_sync(0xffffffffu, widx, 0);
-    int64_t i;
-    if (LIST) {
-      if ((int64_t)widx >= (int64_t)*a.big_count) break;
-      i = a.big_list[widx];
-    } else {
-      if ((int64_t)widx >= a.nown) break;
-      const int64_t q = (int64_t)widx / a.chunk;
-      i = a.v_begin + (q * a.nparts + a.part) * a.chunk + ((int64_t)widx - q * a.chunk);
-    }
+    if ((int64_t)widx >= nlist) break;
+    const int64_t i = list[widx];
     __syncwarp();
 
     const float4 pi4 = __ldg(&a.pos[i]);
@@ -627,12 +719,12 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     const f3 pi = mk3(pi4);
     const int tris = __ldg(&a.trisize[i]);
     if (tris > CX_TRIMAX) {  // crixus_d.cu:306: the reference thread gives up; here: flag + zero
-      if (lane == 0) { atomicOr(a.err, VVE_TRIMAX); a.vol[i] = 0.f; }
+      if (lane == 0) { atomicOr(&a.ctl->err, VVE_TRIMAX); a.vol[i] = 0.f; }
       continue;
     }
     if (tris <= 0) { if (lane == 0) a.vol[i] = 0.f; continue; }
     if (tris > TCAP) {  // fan too large for this launch's shared-memory slot: defer
-      if (lane == 0) a.big_list[atomicAdd(a.big_count, 1)] = (int)i;
+      if (lane == 0) a.list[3 * a.nown + atomicAdd(&a.ctl->count[3], 1)] = (int)i;
       continue;
     }
 
@@ -666,7 +758,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       }
     }
     if (itris != tris) {  // triangles outside the 27-cell neighbourhood: the reference reads garbage here
-      if (lane == 0) { atomicOr(a.err, VVE_FAN); a.vol[i] = 0.f; }
+      if (lane == 0) { atomicOr(&a.ctl->err, VVE_FAN); a.vol[i] = 0.f; }
       continue;
     }
     __syncwarp();
@@ -722,7 +814,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
           if (vf == 2) {
             const int slot = atomicAdd(&w.ecount[k], 1);
             if (slot < 2) w.eseg[k][slot] = j;
-            else atomicOr(a.err, VVE_NONMANIFOLD);
+            else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
           }
         }
       }
@@ -776,13 +868,14 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     }
     __syncwarp();
 
-    // ---------------- the voxel cube: lanes take z-lines (k = x index, l = y index), crixus_d.cu:488-670
-    // pass 1 (rows_dead) drops the lines that a single triangle removes entirely (about half of them); the survivors
-    // are compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
+
+    // ---------------- the voxel cube: lanes take lines (k, l) = indices on the two axes other than AX (place3),
+    // crixus_d.cu:488-670.  Pass 1 (rows_dead) drops the lines that a single triangle removes entirely (about half of them);
+    // the survivors are compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
     for (int r = lane; r < 48; r += 32) rd[r] = 0ull;
     __syncwarp();
-    if (closed) rows_dead<false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
-    else rows_dead<true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+    if (closed) rows_dead<AX, false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+    else rows_dead<AX, true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
     __syncwarp();
     long long acc = 0;
     int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
@@ -790,7 +883,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
       const int line = it * 32 + lane;
       const bool valid = line < VV_LINES;
       const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
-      // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so the z table serves all three
+      // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so one table serves all three
       const bool dead = !valid || ((rd[k] >> l) & 1ull);
       const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
       if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
@@ -803,8 +896,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
         const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
         const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
         const float h0 = gzt[kk], h1 = gzt[ll];
-        acc += closed ? line_weight<false, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
-                      : line_weight<true, WIDE, EST, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
+        acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
+                      : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
         const int took = min(qn, 32);
         qh = (qh + took) & 63;
         qn -= took;
@@ -819,8 +912,6 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? 6 : 4) k_vert_volu
     }
   }
 }
-
-__global__ void k_vv_init(unsigned long long *work, int *err, int *big_count) { *work = 0ull; *err = 0; if (big_count) *big_count = 0; }
 
 static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
                             float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
@@ -845,14 +936,28 @@ extern "C" int cx_calc_vert_volume_part(cx_ctx *ctx, const cx_params *p, const f
   return vert_volume_impl(ctx, p, pos_d, norm_d, ep_d, vol_d, trisize_d, cell_idx_d, nvert, nbe, zero_open, 0, nvert, chunk, nparts, part);
 }
 
+template <int AX, bool WIDE>
+static cudaError_t vv_launch_axis(cx_ctx *ctx, const VVArgs &a)
+{
+  int bps = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, AX, WIDE, AX>, VV_WARPS * 32, 0);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) bps = 1;
+  int64_t grid = (int64_t)ctx->num_sms * bps;
+  const int64_t want = (a.nown + VV_WARPS - 1) / VV_WARPS;
+  if (grid > want) grid = want;
+  k_vert_volume<VV_TCAP_SMALL, AX, WIDE, AX><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
 static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
                             float *vol_d, const int32_t *trisize_d, const int32_t *cell_idx_d, int64_t nvert, int64_t nbe,
                             int zero_open, int64_t v_begin, int64_t v_end, int64_t chunk, int nparts, int part)
 {
   if (!ctx || !p || !pos_d || !norm_d || !ep_d || !vol_d || !trisize_d || !cell_idx_d) return CX_WRONG_INPUT;
-  if (v_begin < 0 || v_end > nvert || v_begin > v_end) return CX_WRONG_INPUT;
+  if (v_begin < 0 || v_end > nvert || v_begin > v_end || nbe < 0) return CX_WRONG_INPUT;
   if (v_begin == v_end) return CX_OK;
-  (void)nbe;
   VVArgs a;
   a.p = *p;
   a.pos = (const float4 *)pos_d; a.norm = (const float4 *)norm_d; a.ep = (const int4 *)ep_d;
@@ -870,7 +975,6 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   const float dr = p->dr, eps = p->eps;
   const float gdr = (float)(dr / 2.0 / (float)CX_GRES);               // crixus_d.cu:281
   for (int m = 0; m < VV_GS; m++) a.gz[m] = ((float)m - (float)(VV_GS - 1) / 2) * gdr;  // :493-495
-  a.igdr = 1.0f / gdr;
   const double thr_d = dr / 2. + eps;                                  // :535 (double)
   float thr = (float)thr_d;
   if ((double)thr > thr_d) thr = nextafterf(thr, -INFINITY);
@@ -882,39 +986,47 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   int cmax = 0;
   while (cmax < 31 && !(ldexpf(1.0f, -(cmax + 1)) < eps)) cmax++;
   a.cmax = cmax;
-  a.work = (unsigned long long *)(ctx->d_mail + 16);
-  a.err = (int *)(ctx->d_mail + 17);
-  a.big_count = (int *)(ctx->d_mail + 18);
-  CX_CUDA(ctx, cudaMallocAsync(&a.big_list, sizeof(int) * (size_t)a.nown, ctx->stream));
-  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, a.err, a.big_count);
-  CX_LAUNCH_CHECK(ctx, "k_vv_init");
-  int bps = 0;
+  // temporaries: control block | normal sums (8 B per vertex) | 4 work lists of nown entries
+  const size_t ctl_bytes = 256, acc_bytes = (sizeof(unsigned long long) * (size_t)nvert + 255) & ~(size_t)255;
+  char *tmp = nullptr;
+  CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + acc_bytes + sizeof(int) * 4 * (size_t)a.nown, ctx->stream));
+  a.ctl = (VVCtl *)tmp;
+  unsigned long long *acc = (unsigned long long *)(tmp + ctl_bytes);
+  a.list = (int *)(tmp + ctl_bytes + acc_bytes);
+  auto fail = [&](const char *what, cudaError_t e) { cudaFreeAsync(tmp, ctx->stream); return cx_fail(ctx, CX_CUDA_ERROR, what, e); };
+  cudaError_t e = cudaMemsetAsync(tmp, 0, ctl_bytes + acc_bytes, ctx->stream);
+  if (e != cudaSuccess) return fail("calc_vert_volume: memset", e);
+  // CX_VV_AXIS=0/1/2 forces one line direction for every vertex (testing: every direction gives the same bits)
+  static const char *force_axis = getenv("CX_VV_AXIS");
+  const int force = (force_axis && force_axis[0] >= '0' && force_axis[0] <= '2') ? force_axis[0] - '0' : -1;
+  if (force < 0 && nbe > 0) {
+    k_vv_normal_sums<<<cx_blocks(nbe, 256, (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(a.norm, a.ep, nbe, nvert, acc);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_normal_sums", e);
+  }
+  k_vv_classify<<<cx_blocks(a.nown, 256, (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(a, acc, force);
+  ctx->launches++;
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_classify", e);
   // see plane_kill<WIDE>: below this dr several voxels of a cut line lie within eps of a plane as a rule
   static const char *force_wide = getenv("CX_VV_WIDE");
   const bool wide = force_wide ? (force_wide[0] == '1') : (dr < 3.0e-3f);
-  // estimate-and-verify threshold search (mono_search_est): narrow-band kernel only -- at fine dr the crossing estimate is
-  // within rounding of a voxel too often (coordinates ~1 against a voxel step of dr/40) and the fallback search would run
-  static const char *force_est = getenv("CX_VV_EST");
-  const bool est = !wide && (force_est ? (force_est[0] == '1') : VV_EST_DEFAULT);
-  if (wide) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, true>, VV_WARPS * 32, 0));
-  else if (est) CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false, true>, VV_WARPS * 32, 0));
-  else CX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, false, false>, VV_WARPS * 32, 0));
-  if (bps < 1) bps = 1;
-  int64_t want = (a.nown + VV_WARPS - 1) / VV_WARPS;
-  int64_t grid = (int64_t)ctx->num_sms * bps;
-  if (grid > want) grid = want;
-  if (wide) k_vert_volume<VV_TCAP_SMALL, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  else if (est) k_vert_volume<VV_TCAP_SMALL, false, false, true><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  else k_vert_volume<VV_TCAP_SMALL, false, false><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  CX_LAUNCH_CHECK(ctx, "k_vert_volume");
-  // second launch: the (rare) vertices with more than 16 triangles, work list built by the first launch
-  k_vv_init<<<1, 1, 0, ctx->stream>>>(a.work, (int *)(ctx->d_mail + 19), nullptr);
-  CX_LAUNCH_CHECK(ctx, "k_vv_init");
-  if (wide) k_vert_volume<CX_TRIMAX, true, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  else k_vert_volume<CX_TRIMAX, true, false><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  CX_LAUNCH_CHECK(ctx, "k_vert_volume_big");
-  CX_CUDA(ctx, cudaFreeAsync(a.big_list, ctx->stream));
-  CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 17, ctx->d_mail + 17, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (wide) {
+    if ((e = vv_launch_axis<2, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<z>", e);
+    if ((e = vv_launch_axis<1, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<y>", e);
+    if ((e = vv_launch_axis<0, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<x>", e);
+  } else {
+    if ((e = vv_launch_axis<2, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<z>", e);
+    if ((e = vv_launch_axis<1, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<y>", e);
+    if ((e = vv_launch_axis<0, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<x>", e);
+  }
+  // last launch: the (rare) vertices with more than 16 triangles, work list built by the launches above
+  if (wide) k_vert_volume<CX_TRIMAX, 3, true, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else k_vert_volume<CX_TRIMAX, 3, false, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vert_volume_big", e);
+  e = cudaMemcpyAsync(ctx->h_mail + 17, &a.ctl->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return fail("calc_vert_volume: read-back", e);
+  CX_CUDA(ctx, cudaFreeAsync(tmp, ctx->stream));
   CX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 #ifdef VV_STATS
   {
