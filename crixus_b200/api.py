@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcrixus_b200.so")
+LIB_PATH = os.environ.get("CX_LIB_PATH") or os.path.join(HERE, "libcrixus_b200.so")   # CX_LIB_PATH: kernel experiments (tools/)
 
 
 class CxParams(C.Structure):

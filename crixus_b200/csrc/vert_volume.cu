@@ -30,13 +30,15 @@
 #define VVE_FAN 2
 #define VVE_NONMANIFOLD 4
 
-// device-side control block of one call: work counters, list lengths (slot 0..2 = line direction x, y, z; slot 3 = fans with
-// more than 16 triangles), error bits
+// device-side control block of one call: work counters (0: k_vv_fans, 1..3: k_vv_rows<x,y,z>, 4..6: k_vv_lines<x,y,z>, 7: the
+// monolithic kernel), list lengths (0..2 = line direction x, y, z; 3 = fans for the monolithic kernel), bump pointer of the plane
+// store, error bits.  Everything except count[3] and err is reset for every chunk of vertices.
 struct VVCtl {
-  unsigned long long work[4];
+  unsigned long long work[8];
   int count[4];
+  int bump;
   int err;
-  int pad[3];
+  int pad[2];
 };
 
 struct VVArgs {
@@ -57,7 +59,13 @@ struct VVArgs {
   double gd3;      // pow(dr/2.0/(float)gres, 3) (crixus_d.cu:674)
   int cmax;        // largest k with 2^-k >= eps (vgrid < eps -> voxel dropped, crixus_d.cu:551,662)
   VVCtl *ctl;
-  int *list;                 // 4 work lists of nown entries each (slot s at list + s*nown)
+  int *list;                 // 4 work lists of nown entries each (slot s at list + s*nown): 0..2 hold chunk slots, 3 vertices
+  int64_t c_begin, c_end;    // the chunk of owned vertices (indices into the owned set) the split kernels work on
+  int4 *heads;               // per chunk slot: plane offset, fan size, closed, vertex
+  float4 *planes;            // plane store of the chunk: 10 float4 per fan triangle
+  int plane_cap;             // its capacity in fan triangles
+  unsigned long long *rdead; // per chunk slot: 41 words, bit l of word k = line (k, l) is dead
+  int force_axis;            // CX_VV_AXIS: one line direction for every vertex (-1: by the fan normal)
   float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
 };
 
@@ -158,18 +166,36 @@ __device__ unsigned long long vv_stats[16];
 // evaluations of the very same arithmetic (exact, no approximation): the largest s in [0,39] with pred(gz[s]) == pa,
 // given pred(gz[0]) == pa and pred(gz[40]) != pa.  Lanes whose ends agree run along (the warp stays converged) and
 // ignore the result.
+#ifndef VV_EXP
+#define VV_EXP 0
+#endif
+#define VV_UNLIKELY(x) ((VV_EXP & 1) ? __builtin_expect(!!(x), 0) : (x))
 template <class Pred>
 __device__ __forceinline__ int mono_search(const float *gzt, bool pa, Pred pred)
 {
+#if (VV_EXP & 8)
+  int s = 0;
+#pragma unroll 1
+  for (int st = 32; st >= 1; st >>= 1) {
+    const int i = min(s + st, VV_GS - 1);
+    if (pred(gzt[i]) == pa) s = i;
+  }
+  return min(s, VV_GS - 2);
+#else
   int s = (pred(gzt[32]) == pa) ? 32 : 0;
   {
     const int i = min(s + 16, VV_GS - 1);
     if (pred(gzt[i]) == pa) s = i;
   }
+#if (VV_EXP & 4)
+#pragma unroll
+#else
 #pragma unroll 1   // rolled on purpose: ~40 inlined instances; the hot loops sit at the edge of the instruction cache (2 % faster)
+#endif
   for (int st = 8; st >= 1; st >>= 1)
     if (pred(gzt[s + st]) == pa) s += st;   // never beyond 39 for a lane that is really cut; the table has 64 entries
   return s;
+#endif
 }
 
 // mask of the voxels where pv(f(g[m])) holds.  fa, fb = f at the two ends.  lo = last index that agrees with end A
@@ -495,16 +521,16 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     // A family is entered only if it can touch a live line of the warp: both ends <= -eps means every voxel of the
     // line is (by monotonicity) on the near side of the plane and further than eps from it.
     const float sVa = fV(gA), sVb = fV(gB);
-    if (__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps)))) plane_kill<WIDE>(gzt, sVa, sVb, fV, eps, K, HV, trig);
+    if (VV_UNLIKELY(__any_sync(VV_FULLWARP, live && !((sVa <= neps) && (sVb <= neps))))) plane_kill<WIDE>(gzt, sVa, sVb, fV, eps, K, HV, trig);
     if (OPEN) {
       const float s2a = fV2(gA), s2b = fV2(gB);
-      if (__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps)))) plane_kill<WIDE>(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
+      if (VV_UNLIKELY(__any_sync(VV_FULLWARP, live && !((s2a <= neps) && (s2b <= neps))))) plane_kill<WIDE>(gzt, s2a, s2b, fV2, eps, K, HV2, trig);
     }
     const float sEa = fE(gA), sEb = fE(gB);
-    if (__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps)))) plane_kill<WIDE>(gzt, sEa, sEb, fE, eps, K, HE, trig);
+    if (VV_UNLIKELY(__any_sync(VV_FULLWARP, live && !((sEa <= neps) && (sEb <= neps))))) plane_kill<WIDE>(gzt, sEa, sEb, fE, eps, K, HE, trig);
     trig = trig && live;
     VV_STAT(1, 1);
-    if (__any_sync(VV_FULLWARP, trig)) {
+    if (VV_UNLIKELY(__any_sync(VV_FULLWARP, trig))) {
       VV_STAT(4, 1); VV_STAT(5, __popc(__ballot_sync(VV_FULLWARP, trig)));
       TriCtxVE<AX> c;
       c.V = fV; c.V2 = fV2; c.E = fE; c.eps = eps; c.open = OPEN ? 1 : 0;
@@ -573,7 +599,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
     K = inside & ~LT;
     HW = inside & LT;
     trig = trig && live;
-    if (__any_sync(VV_FULLWARP, trig)) {
+    if (VV_UNLIKELY(__any_sync(VV_FULLWARP, trig))) {
       TriCtxW<AX> c;
       c.W0 = fW0; c.W1 = fW1; c.W2 = fW2; c.eps = eps;
       exact_tri_w<AX>(a, c, trig, xres, lane);
@@ -625,75 +651,214 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Line direction per vertex.  k_vv_normal_sums adds the (quantised) normals of the segments onto their three vertices with one
-// packed 64-bit atomic each -- integer sums, so the outcome does not depend on the order -- and k_vv_classify deals the owned
-// vertices to the three work lists by the dominant axis of that sum.  The sum only approximates the kernel's own avnorm; a
-// different choice changes the amount of work, never the result.
-__global__ void __launch_bounds__(256) k_vv_normal_sums(const float4 *__restrict__ norm, const int4 *__restrict__ ep, int64_t nbe,
-                                                        int64_t nvert, unsigned long long *__restrict__ acc)
+// Phase A of one vertex (warp-cooperative): fan gather, chain ordering, edge-normal pairing, plane vectors -> w.
+// Returns false when the vertex is finished here (error flagged or volume zero written).  av = the reference's avnorm.
+template <int TCAP, class VVWarp>
+__device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t i, const f3 pi, const int tris, const int lane,
+                                       int &closed_out, f3 &av_out)
 {
-  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nbe; s += (int64_t)gridDim.x * blockDim.x) {
-    const float4 n = __ldg(&norm[s]);
-    const int4 E = __ldg(&ep[s]);
-    auto q = [](float x) { return (unsigned long long)(__float2int_rn(fminf(fmaxf(x, -1.f), 1.f) * 100.f) + 128); };   // NaN -> 128 - 100
-    const unsigned long long v = q(n.x) | (q(n.y) << 16) | (q(n.z) << 32) | (1ull << 48);
-    if ((uint64_t)E.x < (uint64_t)nvert) atomicAdd(&acc[E.x], v);
-    if ((uint64_t)E.y < (uint64_t)nvert) atomicAdd(&acc[E.y], v);
-    if ((uint64_t)E.z < (uint64_t)nvert) atomicAdd(&acc[E.z], v);
+  const cx_params &p = a.p;
+  const int gx = cell_coord(pi.x, p.dmin[0], p.griddr[0], p.gridn[0]);
+  const int gy = cell_coord(pi.y, p.dmin[1], p.griddr[1], p.gridn[1]);
+  const int gz = cell_coord(pi.z, p.dmin[2], p.griddr[2], p.gridn[2]);
+
+  // the 27 neighbouring 3dr-cells (crixus_d.cu:327-347): lane c holds the segment range of cell c (empty if skipped)
+  int cb = 0, ce = 0;
+  if (lane < 27) {
+    const int64_t c = nb_cell(p, gx + lane / 9 - 1, gy + (lane / 3) % 3 - 1, gz + lane % 3 - 1);
+    if (c >= 0) { cb = __ldg(&a.cell_idx[c]); ce = __ldg(&a.cell_idx[c + 1]); }
   }
-}
-
-__device__ __forceinline__ int64_t vv_owned_vertex(const VVArgs &a, int64_t idx)
-{
-  const int64_t q = idx / a.chunk;
-  return a.v_begin + (q * a.nparts + a.part) * a.chunk + (idx - q * a.chunk);
-}
-
-__global__ void __launch_bounds__(256) k_vv_classify(const __grid_constant__ VVArgs a, const unsigned long long *__restrict__ acc, int force)
-{
-  const int lane = threadIdx.x & 31;
-  const int64_t n32 = (a.nown + 31) & ~(int64_t)31;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n32; idx += (int64_t)gridDim.x * blockDim.x) {   // whole warps
-    int cls = -1;
-    int64_t i = 0;
-    if (idx < a.nown) {
-      i = vv_owned_vertex(a, idx);
-      const unsigned long long s = acc[i];
-      const int c = (int)(s >> 48);
-      const int sx = abs((int)(s & 0xffffu) - 128 * c), sy = abs((int)((s >> 16) & 0xffffu) - 128 * c),
-                sz = abs((int)((s >> 32) & 0xffffu) - 128 * c);
-      cls = (sz >= sx && sz >= sy) ? 2 : (sy >= sx ? 1 : 0);      // ties: z, then y (the cheaper evaluations)
-      if (force >= 0) cls = force;
+  // ---------------- fan gather (crixus_d.cu:316-369): discovery order = cell order, segment order, corner order
+  int itris = 0;
+  for (int c27 = 0; c27 < 27; c27++) {
+    const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
+    for (int base = b; base < e; base += 32) {
+      const int j = base + lane;
+      int4 E = make_int4(-1, -1, -1, -1);
+      if (j < e) E = __ldg(&a.ep[j]);
+      const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
+      const int cnt = m0 + m1 + m2;
+      if (!__any_sync(0xffffffffu, cnt != 0)) continue;
+      const int incl = warp_incl_scan_i(cnt, lane);
+      int off = itris + incl - cnt;
+      if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
+      if (m1 && off < TCAP) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
+      if (m2 && off < TCAP) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
+      itris += __shfl_sync(0xffffffffu, incl, 31);
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const unsigned m = __ballot_sync(0xffffffffu, cls == k);
-      if (m) {
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&a.ctl->count[k], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (cls == k) a.list[(int64_t)k * a.nown + base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  }
+  if (itris != tris) {  // triangles outside the 27-cell neighbourhood: the reference reads garbage here
+    if (lane == 0) { atomicOr(&a.ctl->err, VVE_FAN); a.vol[i] = 0.f; }
+    return false;
+  }
+  __syncwarp();
+
+  // ---------------- chain ordering + closedness (crixus_d.cu:371-399), serial on lane 0 (T <= 50)
+  if (lane == 0) {
+    int closed = 1;
+    for (int j = 0; j < tris; j++) {
+      for (int k = j + 1; k < tris; k++) {
+        if (w.tri[j][1] == w.tri[k][0]) {
+          if (k != j + 1)
+            for (int l = 0; l < 3; l++) { int t = w.tri[j + 1][l]; w.tri[j + 1][l] = w.tri[k][l]; w.tri[k][l] = t; }
+          break;
+        }
+        if (w.tri[j][1] == w.tri[k][1]) {
+          const int d0 = w.tri[k][1], d1 = w.tri[k][0], d2 = w.tri[k][2];
+          for (int l = 0; l < 3; l++) w.tri[k][l] = w.tri[j + 1][l];
+          w.tri[j + 1][0] = d0; w.tri[j + 1][1] = d1; w.tri[j + 1][2] = d2;
+          break;
+        }
+        if (k == tris - 1) closed = 0;
+      }
+    }
+    if (w.tri[0][0] != w.tri[tris - 1][1]) closed = 0;
+    w.closed = closed;
+  }
+  for (int k = lane; k < tris; k += 32) w.ecount[k] = 0;
+  __syncwarp();
+  const int closed = w.closed;
+  if (a.zero_open && !closed) {  // crixus_d.cu:403-407
+    if (lane == 0) a.vol[i] = 0.f;
+    return false;
+  }
+
+  // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k.
+  // A 64-bit filter of the rim vertices (id mod 64) rejects almost every segment batch without entering the k loop.
+  uint64_t rim = 0ull;
+  for (int k = 0; k < tris; k++) rim |= (1ull << (w.tri[k][0] & 63)) | (1ull << (w.tri[k][1] & 63));
+  for (int c27 = 0; c27 < 27; c27++) {
+    const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
+    for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
+      const int j = base + lane;
+      int4 E = make_int4(-1, -1, -1, -1);
+      bool cand = false;
+      if (j < e) {
+        E = __ldg(&a.ep[j]);
+        cand = (int)((rim >> (E.x & 63)) & 1ull) + (int)((rim >> (E.y & 63)) & 1ull) + (int)((rim >> (E.z & 63)) & 1ull) >= 2;
+      }
+      if (!__any_sync(0xffffffffu, cand)) continue;
+      for (int k = 0; k < tris; k++) {
+        const int t0 = w.tri[k][0], t1 = w.tri[k][1];
+        const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
+        if (vf == 2) {
+          const int slot = atomicAdd(&w.ecount[k], 1);
+          if (slot < 2) w.eseg[k][slot] = j;
+          else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
+        }
       }
     }
   }
+  __syncwarp();
+
+  // ---------------- avnorm (crixus_d.cu:524): float sum in fan order, every lane computes the same value
+  f3 av = mk3(0.f, 0.f, 0.f);
+  for (int j = 0; j < tris; j++) {
+    const float4 n = __ldg(&a.norm[w.tri[j][2]]);
+    av = mk3(fsub(av.x, n.x), fsub(av.y, n.y), fsub(av.z, n.z));
+  }
+
+  // ---------------- per-triangle plane vectors (crixus_d.cu:507-529 and :552-596), one lane per fan triangle
+  for (int jb = 0; jb < tris; jb += 32) {
+    const int j = jb + lane;
+    if (j >= tris) continue;
+    const f3 n = mk3(__ldg(&a.norm[w.tri[j][2]]));
+    const f3 va = mk3(__ldg(&a.pos[w.tri[j][0]])), vb = mk3(__ldg(&a.pos[w.tri[j][1]]));
+    const f3 e1 = unwrap3(p, sub3(va, pi), a.two_dr);  // cvec[5] (and cvec[0] before normalisation)
+    const f3 e2 = unwrap3(p, sub3(vb, pi), a.two_dr);  // tvec[1] / cvec[7] (and cvec[3] before normalisation)
+    const f3 c0 = normalise_ref(e1), c3 = normalise_ref(e2);
+    const f3 c1 = cross_r2(c0, n), c4 = cross_r2(c3, n);
+    const f3 c6 = mk3(halfway(pi.x, e1.x), halfway(pi.y, e1.y), halfway(pi.z, e1.z));
+    const f3 c8 = mk3(halfway(pi.x, e2.x), halfway(pi.y, e2.y), halfway(pi.z, e2.z));
+    f3 c9 = cross_r2(e1, e2), c10 = cross_r2(e2, av), c11 = cross_r2(av, e1);  // crixus_d.cu:570
+    if (dot3_r1(n, c9) > 0.f) { c9 = neg3(c9); c10 = neg3(c10); c11 = neg3(c11); }
+    // edge normal: sum of the (<=2) adjacent segment normals x edge (crixus_d.cu:447-473)
+    f3 en = mk3(0.f, 0.f, 0.f);
+    const int cnt = min(w.ecount[j], 2);
+    if (cnt >= 1) {
+      const f3 na = mk3(__ldg(&a.norm[w.eseg[j][0]]));
+      en = add3(en, na);
+      if (cnt == 2) en = add3(en, mk3(__ldg(&a.norm[w.eseg[j][1]])));
+      f3 edge = sub3(va, vb);
+      if (cnt == 2) edge = unwrap3(p, edge, a.two_dr);  // single-segment edges are not unwrapped (:465-473)
+      en = cross_r2(en, edge);
+    }
+    if (dot3_r1(en, e1) < 0.f) en = neg3(en);  // crixus_d.cu:581-585
+    float4 *P = w.plane[j];
+    P[0] = make_float4(c0.x, c0.y, c0.z, c1.x);
+    P[1] = make_float4(c1.y, c1.z, n.x, n.y);
+    P[2] = make_float4(n.z, c3.x, c3.y, c3.z);
+    P[3] = make_float4(c4.x, c4.y, c4.z, 0.f);
+    P[4] = make_float4(e1.x, e1.y, e1.z, c6.x);
+    P[5] = make_float4(c6.y, c6.z, e2.x, e2.y);
+    P[6] = make_float4(e2.z, c8.x, c8.y, c8.z);
+    P[7] = make_float4(c9.x, c9.y, c9.z, c10.x);
+    P[8] = make_float4(c10.y, c10.z, c11.x, c11.y);
+    P[9] = make_float4(c11.z, en.x, en.y, en.z);
+  }
+  __syncwarp();
+  closed_out = closed;
+  av_out = av;
+  return true;
 }
 
-// SLOT: work list of this launch (0..2: vertices whose lines run along x, y, z; 3: the fans with more than 16 triangles)
-template <int TCAP, int SLOT, bool WIDE, int AX>
-__global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? (AX == 2 ? 6 : 5) : 4) k_vert_volume(const __grid_constant__ VVArgs a)
+// Pass 1 of one vertex: rd[k] bit l = line (k, l) is removed whole by one triangle (48 words per warp, 41 used)
+template <int AX, class VVWarp>
+__device__ __forceinline__ void vv_rows(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
+                                        unsigned long long *rd)
 {
-  typedef VVWarpT<TCAP> VVWarp;
-  __shared__ VVWarp sm[VV_WARPS];
-  __shared__ __align__(16) float gzt[64 + 256];   // g[0..40] for lane-dependent lookups (padded to 64), then the two
-                                                  // 64-entry uint64 mask tables used by mono_mask
-  __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
-  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = line (k, l) is dead
-  __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
-  const int lane = threadIdx.x & 31;
-  VVWarp &w = sm[threadIdx.x >> 5];
-  unsigned short *wq = wqs[threadIdx.x >> 5];
-  unsigned long long *rd = rds[threadIdx.x >> 5];
-  unsigned long long *xres = xress[threadIdx.x >> 5];
+  for (int r = lane; r < 48; r += 32) rd[r] = 0ull;
+  __syncwarp();
+  if (closed) rows_dead<AX, false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+  else rows_dead<AX, true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+  __syncwarp();
+}
+
+// Pass 2 of one vertex: the surviving lines are compacted through a small per-warp ring so that line_weight always runs with
+// 32 live lines; the weights are summed in integers and converted once.
+template <int AX, bool WIDE, class VVWarp>
+__device__ __forceinline__ void vv_lines(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
+                                         const unsigned long long *rd, unsigned short *wq, unsigned long long *xres, int64_t i)
+{
+  long long acc = 0;
+  int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
+  for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
+    const int line = it * 32 + lane;
+    const bool valid = line < VV_LINES;
+    const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
+    // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so one table serves all three
+    const bool dead = !valid || ((rd[k] >> l) & 1ull);
+    const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
+    if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
+    qn += __popc(live);
+    __syncwarp();
+    const bool last = it == (VV_LINES + 31) / 32 - 1;
+    while (qn >= 32 || (last && qn > 0)) {
+      const bool have = lane < qn;
+      VV_STAT(6, min(qn, 32)); VV_STAT(12, 1);
+      const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
+      const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
+      const float h0 = gzt[kk], h1 = gzt[ll];
+      acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
+                    : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
+      const int took = min(qn, 32);
+      qh = (qh + took) & 63;
+      qn -= took;
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float volf = (float)((double)acc * (1.0 / 2147483648.0));  // exact sum of 2^-k weights, rounded once
+    a.vol[i] = (float)((double)volf * a.gd3);                          // crixus_d.cu:674
+  }
+}
+
+// shared-memory tables of phase B: g[0..40] for lane-dependent lookups (padded to 64), then the two 64-entry uint64 mask tables
+// used by mono_mask
+__device__ __forceinline__ void vv_init_tables(const VVArgs &a, float *gzt)
+{
   if (threadIdx.x < 64) {
     gzt[threadIdx.x] = threadIdx.x < VV_GS ? a.gz[threadIdx.x] : 0.f;
     uint64_t *lmt = reinterpret_cast<uint64_t *>(gzt + 64);
@@ -702,18 +867,39 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? (AX == 2 ? 6 : 5) 
     lmt[64 + threadIdx.x] = lm;
   }
   __syncthreads();
-  const cx_params &p = a.p;
-  const int *list = a.list + (int64_t)SLOT * a.nown;
-  const int64_t nlist = a.ctl->count[SLOT];     // complete: filled by an earlier launch
+}
 
+__device__ __forceinline__ int64_t vv_owned_vertex(const VVArgs &a, int64_t idx)
+{
+  const int64_t q = idx / a.chunk;
+  return a.v_begin + (q * a.nparts + a.part) * a.chunk + (idx - q * a.chunk);
+}
+
+// The three phases run as three kernels over one chunk of the owned vertices (the instruction cache decides: the monolithic
+// kernel's per-vertex path is ~60 KB of SASS against a 32 KB L1.5 instruction cache, and a third of its warp stall samples were
+// "no instruction"), handing the fan's plane vectors (160 B per fan triangle) and the dead-line masks (41 words per vertex)
+// through HBM scratch -- ~1.4 KB per vertex, noise against the arithmetic.
+//   k_vv_fans         phase A; picks the line direction from the fan's own avnorm and appends the vertex to that work list
+//   k_vv_rows<AX>     pass 1 (rows_dead)
+//   k_vv_lines<AX>    pass 2 (ring compaction + line_weight)
+// Fans with more than 16 triangles, and fans that find the chunk's plane store full, go to the monolithic k_vert_volume (list 3).
+struct VVHead { int off, tris, closed, vertex; };
+
+__global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_fans(const __grid_constant__ VVArgs a)
+{
+  typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
+  __shared__ VVWarp sm[VV_WARPS];
+  const int lane = threadIdx.x & 31;
+  VVWarp &w = sm[threadIdx.x >> 5];
+  const int force = a.force_axis;
   for (;;) {
     unsigned long long widx = 0;
-    if (lane == 0) widx = atomicAdd(&a.ctl->work[SLOT], 1ull);
+    if (lane == 0) widx = atomicAdd(&a.ctl->work[0], 1ull);
     widx = __shfl_sync(0xffffffffu, widx, 0);
-    if ((int64_t)widx >= nlist) break;
-    const int64_t i = list[widx];
+    if ((int64_t)widx >= a.c_end - a.c_begin) break;
+    const int64_t idx = a.c_begin + (int64_t)widx;
+    const int64_t i = vv_owned_vertex(a, idx);
     __syncwarp();
-
     const float4 pi4 = __ldg(&a.pos[i]);
     if (pi4.x < -1e9f) continue;  // vertex deleted by the periodic pairing (crixus_d.cu:297)
     const f3 pi = mk3(pi4);
@@ -723,193 +909,147 @@ __global__ void __launch_bounds__(VV_WARPS * 32, TCAP <= 16 ? (AX == 2 ? 6 : 5) 
       continue;
     }
     if (tris <= 0) { if (lane == 0) a.vol[i] = 0.f; continue; }
-    if (tris > TCAP) {  // fan too large for this launch's shared-memory slot: defer
+    if (tris > VV_TCAP_SMALL) {  // fan too large for the shared-memory slot of the split kernels
       if (lane == 0) a.list[3 * a.nown + atomicAdd(&a.ctl->count[3], 1)] = (int)i;
       continue;
     }
-
-    const int gx = cell_coord(pi.x, p.dmin[0], p.griddr[0], p.gridn[0]);
-    const int gy = cell_coord(pi.y, p.dmin[1], p.griddr[1], p.gridn[1]);
-    const int gz = cell_coord(pi.z, p.dmin[2], p.griddr[2], p.gridn[2]);
-
-    // the 27 neighbouring 3dr-cells (crixus_d.cu:327-347): lane c holds the segment range of cell c (empty if skipped)
-    int cb = 0, ce = 0;
-    if (lane < 27) {
-      const int64_t c = nb_cell(p, gx + lane / 9 - 1, gy + (lane / 3) % 3 - 1, gz + lane % 3 - 1);
-      if (c >= 0) { cb = __ldg(&a.cell_idx[c]); ce = __ldg(&a.cell_idx[c + 1]); }
-    }
-    // ---------------- fan gather (crixus_d.cu:316-369): discovery order = cell order, segment order, corner order
-    int itris = 0;
-    for (int c27 = 0; c27 < 27; c27++) {
-      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
-      for (int base = b; base < e; base += 32) {
-        const int j = base + lane;
-        int4 E = make_int4(-1, -1, -1, -1);
-        if (j < e) E = __ldg(&a.ep[j]);
-        const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
-        const int cnt = m0 + m1 + m2;
-        if (!__any_sync(0xffffffffu, cnt != 0)) continue;
-        const int incl = warp_incl_scan_i(cnt, lane);
-        int off = itris + incl - cnt;
-        if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
-        if (m1 && off < TCAP) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
-        if (m2 && off < TCAP) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
-        itris += __shfl_sync(0xffffffffu, incl, 31);
-      }
-    }
-    if (itris != tris) {  // triangles outside the 27-cell neighbourhood: the reference reads garbage here
-      if (lane == 0) { atomicOr(&a.ctl->err, VVE_FAN); a.vol[i] = 0.f; }
+    int closed;
+    f3 av;
+    if (!vv_fan<VV_TCAP_SMALL>(a, w, i, pi, tris, lane, closed, av)) continue;
+    int off = 0;
+    if (lane == 0) off = atomicAdd(&a.ctl->bump, tris);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + tris > a.plane_cap) {   // plane store of this chunk is full: the monolithic kernel takes the vertex
+      if (lane == 0) a.list[3 * a.nown + atomicAdd(&a.ctl->count[3], 1)] = (int)i;
       continue;
     }
     __syncwarp();
-
-    // ---------------- chain ordering + closedness (crixus_d.cu:371-399), serial on lane 0 (T <= 50)
+    const float4 *src = &w.plane[0][0];
+    float4 *dst = a.planes + (int64_t)off * VV_PLANE_F4;
+    for (int q = lane; q < tris * VV_PLANE_F4; q += 32) dst[q] = src[q];
     if (lane == 0) {
-      int closed = 1;
-      for (int j = 0; j < tris; j++) {
-        for (int k = j + 1; k < tris; k++) {
-          if (w.tri[j][1] == w.tri[k][0]) {
-            if (k != j + 1)
-              for (int l = 0; l < 3; l++) { int t = w.tri[j + 1][l]; w.tri[j + 1][l] = w.tri[k][l]; w.tri[k][l] = t; }
-            break;
-          }
-          if (w.tri[j][1] == w.tri[k][1]) {
-            const int d0 = w.tri[k][1], d1 = w.tri[k][0], d2 = w.tri[k][2];
-            for (int l = 0; l < 3; l++) w.tri[k][l] = w.tri[j + 1][l];
-            w.tri[j + 1][0] = d0; w.tri[j + 1][1] = d1; w.tri[j + 1][2] = d2;
-            break;
-          }
-          if (k == tris - 1) closed = 0;
-        }
-      }
-      if (w.tri[0][0] != w.tri[tris - 1][1]) closed = 0;
-      w.closed = closed;
+      // line direction = dominant axis of the fan normal; ties: z, then y (the cheaper evaluations)
+      const float ax = fabsf(av.x), ay = fabsf(av.y), az = fabsf(av.z);
+      int cls = (az >= ax && az >= ay) ? 2 : (ay >= ax ? 1 : 0);
+      if (force >= 0) cls = force;
+      VVHead h;
+      h.off = off; h.tris = tris; h.closed = closed; h.vertex = (int)i;
+      const int slot = (int)(idx - a.c_begin);
+      a.heads[slot] = make_int4(h.off, h.tris, h.closed, h.vertex);
+      a.list[(int64_t)cls * a.nown + atomicAdd(&a.ctl->count[cls], 1)] = slot;
     }
-    for (int k = lane; k < tris; k += 32) w.ecount[k] = 0;
-    __syncwarp();
-    const int closed = w.closed;
-    if (a.zero_open && !closed) {  // crixus_d.cu:403-407
-      if (lane == 0) a.vol[i] = 0.f;
-      continue;
-    }
+  }
+}
 
-    // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k.
-    // A 64-bit filter of the rim vertices (id mod 64) rejects almost every segment batch without entering the k loop.
-    uint64_t rim = 0ull;
-    for (int k = 0; k < tris; k++) rim |= (1ull << (w.tri[k][0] & 63)) | (1ull << (w.tri[k][1] & 63));
-    for (int c27 = 0; c27 < 27; c27++) {
-      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
-      for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
-        const int j = base + lane;
-        int4 E = make_int4(-1, -1, -1, -1);
-        bool cand = false;
-        if (j < e) {
-          E = __ldg(&a.ep[j]);
-          cand = (int)((rim >> (E.x & 63)) & 1ull) + (int)((rim >> (E.y & 63)) & 1ull) + (int)((rim >> (E.z & 63)) & 1ull) >= 2;
-        }
-        if (!__any_sync(0xffffffffu, cand)) continue;
-        for (int k = 0; k < tris; k++) {
-          const int t0 = w.tri[k][0], t1 = w.tri[k][1];
-          const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
-          if (vf == 2) {
-            const int slot = atomicAdd(&w.ecount[k], 1);
-            if (slot < 2) w.eseg[k][slot] = j;
-            else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
-          }
-        }
-      }
-    }
-    __syncwarp();
+// fetch of one work item of the split kernels: header + plane vectors into shared memory
+template <class VVWarp>
+__device__ __forceinline__ VVHead vv_fetch(const VVArgs &a, VVWarp &w, int slot, int lane)
+{
+  const int4 hv = __ldg(a.heads + slot);
+  VVHead h;
+  h.off = hv.x; h.tris = hv.y; h.closed = hv.z; h.vertex = hv.w;
+  const float4 *src = a.planes + (int64_t)h.off * VV_PLANE_F4;
+  float4 *dst = &w.plane[0][0];
+  for (int q = lane; q < h.tris * VV_PLANE_F4; q += 32) dst[q] = src[q];
+  __syncwarp();
+  return h;
+}
 
-    // ---------------- avnorm (crixus_d.cu:524): float sum in fan order, every lane computes the same value
-    f3 av = mk3(0.f, 0.f, 0.f);
-    for (int j = 0; j < tris; j++) {
-      const float4 n = __ldg(&a.norm[w.tri[j][2]]);
-      av = mk3(fsub(av.x, n.x), fsub(av.y, n.y), fsub(av.z, n.z));
-    }
-
-    // ---------------- per-triangle plane vectors (crixus_d.cu:507-529 and :552-596), one lane per fan triangle
-    for (int jb = 0; jb < tris; jb += 32) {
-      const int j = jb + lane;
-      if (j >= tris) continue;
-      const f3 n = mk3(__ldg(&a.norm[w.tri[j][2]]));
-      const f3 va = mk3(__ldg(&a.pos[w.tri[j][0]])), vb = mk3(__ldg(&a.pos[w.tri[j][1]]));
-      const f3 e1 = unwrap3(p, sub3(va, pi), a.two_dr);  // cvec[5] (and cvec[0] before normalisation)
-      const f3 e2 = unwrap3(p, sub3(vb, pi), a.two_dr);  // tvec[1] / cvec[7] (and cvec[3] before normalisation)
-      const f3 c0 = normalise_ref(e1), c3 = normalise_ref(e2);
-      const f3 c1 = cross_r2(c0, n), c4 = cross_r2(c3, n);
-      const f3 c6 = mk3(halfway(pi.x, e1.x), halfway(pi.y, e1.y), halfway(pi.z, e1.z));
-      const f3 c8 = mk3(halfway(pi.x, e2.x), halfway(pi.y, e2.y), halfway(pi.z, e2.z));
-      f3 c9 = cross_r2(e1, e2), c10 = cross_r2(e2, av), c11 = cross_r2(av, e1);  // crixus_d.cu:570
-      if (dot3_r1(n, c9) > 0.f) { c9 = neg3(c9); c10 = neg3(c10); c11 = neg3(c11); }
-      // edge normal: sum of the (<=2) adjacent segment normals x edge (crixus_d.cu:447-473)
-      f3 en = mk3(0.f, 0.f, 0.f);
-      const int cnt = min(w.ecount[j], 2);
-      if (cnt >= 1) {
-        const f3 na = mk3(__ldg(&a.norm[w.eseg[j][0]]));
-        en = add3(en, na);
-        if (cnt == 2) en = add3(en, mk3(__ldg(&a.norm[w.eseg[j][1]])));
-        f3 edge = sub3(va, vb);
-        if (cnt == 2) edge = unwrap3(p, edge, a.two_dr);  // single-segment edges are not unwrapped (:465-473)
-        en = cross_r2(en, edge);
-      }
-      if (dot3_r1(en, e1) < 0.f) en = neg3(en);  // crixus_d.cu:581-585
-      float4 *P = w.plane[j];
-      P[0] = make_float4(c0.x, c0.y, c0.z, c1.x);
-      P[1] = make_float4(c1.y, c1.z, n.x, n.y);
-      P[2] = make_float4(n.z, c3.x, c3.y, c3.z);
-      P[3] = make_float4(c4.x, c4.y, c4.z, 0.f);
-      P[4] = make_float4(e1.x, e1.y, e1.z, c6.x);
-      P[5] = make_float4(c6.y, c6.z, e2.x, e2.y);
-      P[6] = make_float4(e2.z, c8.x, c8.y, c8.z);
-      P[7] = make_float4(c9.x, c9.y, c9.z, c10.x);
-      P[8] = make_float4(c10.y, c10.z, c11.x, c11.y);
-      P[9] = make_float4(c11.z, en.x, en.y, en.z);
-    }
+template <int AX>
+__global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_rows(const __grid_constant__ VVArgs a)
+{
+  typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
+  __shared__ VVWarp sm[VV_WARPS];
+  __shared__ __align__(16) float gzt[64 + 256];
+  __shared__ unsigned long long rds[VV_WARPS][48];
+  const int lane = threadIdx.x & 31;
+  VVWarp &w = sm[threadIdx.x >> 5];
+  unsigned long long *rd = rds[threadIdx.x >> 5];
+  vv_init_tables(a, gzt);
+  const int *list = a.list + (int64_t)AX * a.nown;
+  const int64_t nlist = a.ctl->count[AX];
+  for (;;) {
+    unsigned long long widx = 0;
+    if (lane == 0) widx = atomicAdd(&a.ctl->work[1 + AX], 1ull);
+    widx = __shfl_sync(0xffffffffu, widx, 0);
+    if ((int64_t)widx >= nlist) break;
+    const int slot = list[widx];
     __syncwarp();
-
-
-    // ---------------- the voxel cube: lanes take lines (k, l) = indices on the two axes other than AX (place3),
-    // crixus_d.cu:488-670.  Pass 1 (rows_dead) drops the lines that a single triangle removes entirely (about half of them);
-    // the survivors are compacted through a small per-warp ring so that pass 2 always runs with 32 live lines.
-    for (int r = lane; r < 48; r += 32) rd[r] = 0ull;
+    const VVHead h = vv_fetch(a, w, slot, lane);
+    const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
+    vv_rows<AX>(a, w, gzt, h.tris, h.closed, pi, lane, rd);
+    unsigned long long *out = a.rdead + (int64_t)slot * VV_GS;
+    for (int r = lane; r < VV_GS; r += 32) out[r] = rd[r];
     __syncwarp();
-    if (closed) rows_dead<AX, false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
-    else rows_dead<AX, true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
+  }
+}
+
+template <int AX, bool WIDE>
+__global__ void __launch_bounds__(VV_WARPS * 32, AX == 2 ? 6 : 5) k_vv_lines(const __grid_constant__ VVArgs a)
+{
+  typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
+  __shared__ VVWarp sm[VV_WARPS];
+  __shared__ __align__(16) float gzt[64 + 256];
+  __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
+  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = line (k, l) is dead
+  __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
+  const int lane = threadIdx.x & 31;
+  VVWarp &w = sm[threadIdx.x >> 5];
+  unsigned short *wq = wqs[threadIdx.x >> 5];
+  unsigned long long *rd = rds[threadIdx.x >> 5];
+  unsigned long long *xres = xress[threadIdx.x >> 5];
+  vv_init_tables(a, gzt);
+  const int *list = a.list + (int64_t)AX * a.nown;
+  const int64_t nlist = a.ctl->count[AX];
+  for (;;) {
+    unsigned long long widx = 0;
+    if (lane == 0) widx = atomicAdd(&a.ctl->work[4 + AX], 1ull);
+    widx = __shfl_sync(0xffffffffu, widx, 0);
+    if ((int64_t)widx >= nlist) break;
+    const int slot = list[widx];
     __syncwarp();
-    long long acc = 0;
-    int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
-    for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
-      const int line = it * 32 + lane;
-      const bool valid = line < VV_LINES;
-      const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
-      // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so one table serves all three
-      const bool dead = !valid || ((rd[k] >> l) & 1ull);
-      const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
-      if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
-      qn += __popc(live);
-      __syncwarp();
-      const bool last = it == (VV_LINES + 31) / 32 - 1;
-      while (qn >= 32 || (last && qn > 0)) {
-        const bool have = lane < qn;
-        VV_STAT(6, min(qn, 32)); VV_STAT(12, 1);
-        const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
-        const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
-        const float h0 = gzt[kk], h1 = gzt[ll];
-        acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
-                      : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
-        const int took = min(qn, 32);
-        qh = (qh + took) & 63;
-        qn -= took;
-        __syncwarp();
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const float volf = (float)((double)acc * (1.0 / 2147483648.0));  // exact sum of 2^-k weights, rounded once
-      a.vol[i] = (float)((double)volf * a.gd3);                          // crixus_d.cu:674
-    }
+    const unsigned long long *in = a.rdead + (int64_t)slot * VV_GS;
+    for (int r = lane; r < VV_GS; r += 32) rd[r] = in[r];
+    const VVHead h = vv_fetch(a, w, slot, lane);
+    const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
+    vv_lines<AX, WIDE>(a, w, gzt, h.tris, h.closed, pi, lane, rd, wq, xres, h.vertex);
+    __syncwarp();
+  }
+}
+
+// The monolithic form: all phases of a vertex in one kernel, fans of up to TCAP = trimax triangles; serves work list 3
+template <int TCAP, bool WIDE, int AX>
+__global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_constant__ VVArgs a)
+{
+  typedef VVWarpT<TCAP> VVWarp;
+  __shared__ VVWarp sm[VV_WARPS];
+  __shared__ __align__(16) float gzt[64 + 256];
+  __shared__ unsigned short wqs[VV_WARPS][64];
+  __shared__ unsigned long long rds[VV_WARPS][48];
+  __shared__ unsigned long long xress[VV_WARPS][128];
+  const int lane = threadIdx.x & 31;
+  VVWarp &w = sm[threadIdx.x >> 5];
+  unsigned short *wq = wqs[threadIdx.x >> 5];
+  unsigned long long *rd = rds[threadIdx.x >> 5];
+  unsigned long long *xres = xress[threadIdx.x >> 5];
+  vv_init_tables(a, gzt);
+  const int *list = a.list + 3 * a.nown;
+  const int64_t nlist = a.ctl->count[3];     // complete: filled by the earlier launches
+  for (;;) {
+    unsigned long long widx = 0;
+    if (lane == 0) widx = atomicAdd(&a.ctl->work[7], 1ull);
+    widx = __shfl_sync(0xffffffffu, widx, 0);
+    if ((int64_t)widx >= nlist) break;
+    const int64_t i = list[widx];
+    __syncwarp();
+    const f3 pi = mk3(__ldg(&a.pos[i]));
+    const int tris = __ldg(&a.trisize[i]);    // 1 .. trimax (k_vv_fans)
+    int closed;
+    f3 av;
+    if (!vv_fan<TCAP>(a, w, i, pi, tris, lane, closed, av)) continue;
+    vv_rows<AX>(a, w, gzt, tris, closed, pi, lane, rd);
+    vv_lines<AX, WIDE>(a, w, gzt, tris, closed, pi, lane, rd, wq, xres, i);
+    __syncwarp();
   }
 }
 
@@ -936,19 +1076,28 @@ extern "C" int cx_calc_vert_volume_part(cx_ctx *ctx, const cx_params *p, const f
   return vert_volume_impl(ctx, p, pos_d, norm_d, ep_d, vol_d, trisize_d, cell_idx_d, nvert, nbe, zero_open, 0, nvert, chunk, nparts, part);
 }
 
-template <int AX, bool WIDE>
-static cudaError_t vv_launch_axis(cx_ctx *ctx, const VVArgs &a)
+template <class K>
+static cudaError_t vv_launch(cx_ctx *ctx, K kernel, const VVArgs &a, int64_t items)
 {
   int bps = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_vert_volume<VV_TCAP_SMALL, AX, WIDE, AX>, VV_WARPS * 32, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, VV_WARPS * 32, 0);
   if (e != cudaSuccess) return e;
   if (bps < 1) bps = 1;
   int64_t grid = (int64_t)ctx->num_sms * bps;
-  const int64_t want = (a.nown + VV_WARPS - 1) / VV_WARPS;
+  const int64_t want = (items + VV_WARPS - 1) / VV_WARPS;
   if (grid > want) grid = want;
-  k_vert_volume<VV_TCAP_SMALL, AX, WIDE, AX><<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  if (grid < 1) grid = 1;
+  kernel<<<(unsigned)grid, VV_WARPS * 32, 0, ctx->stream>>>(a);
   ctx->launches++;
   return cudaGetLastError();
+}
+
+template <int AX>
+static cudaError_t vv_launch_axis(cx_ctx *ctx, const VVArgs &a, bool wide, int64_t items)
+{
+  cudaError_t e = vv_launch(ctx, k_vv_rows<AX>, a, items);
+  if (e != cudaSuccess) return e;
+  return wide ? vv_launch(ctx, k_vv_lines<AX, true>, a, items) : vv_launch(ctx, k_vv_lines<AX, false>, a, items);
 }
 
 static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d, const float *norm_d, const int32_t *ep_d,
@@ -986,44 +1135,55 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   int cmax = 0;
   while (cmax < 31 && !(ldexpf(1.0f, -(cmax + 1)) < eps)) cmax++;
   a.cmax = cmax;
-  // temporaries: control block | normal sums (8 B per vertex) | 4 work lists of nown entries
-  const size_t ctl_bytes = 256, acc_bytes = (sizeof(unsigned long long) * (size_t)nvert + 255) & ~(size_t)255;
-  char *tmp = nullptr;
-  CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + acc_bytes + sizeof(int) * 4 * (size_t)a.nown, ctx->stream));
-  a.ctl = (VVCtl *)tmp;
-  unsigned long long *acc = (unsigned long long *)(tmp + ctl_bytes);
-  a.list = (int *)(tmp + ctl_bytes + acc_bytes);
-  auto fail = [&](const char *what, cudaError_t e) { cudaFreeAsync(tmp, ctx->stream); return cx_fail(ctx, CX_CUDA_ERROR, what, e); };
-  cudaError_t e = cudaMemsetAsync(tmp, 0, ctl_bytes + acc_bytes, ctx->stream);
-  if (e != cudaSuccess) return fail("calc_vert_volume: memset", e);
   // CX_VV_AXIS=0/1/2 forces one line direction for every vertex (testing: every direction gives the same bits)
-  static const char *force_axis = getenv("CX_VV_AXIS");
-  const int force = (force_axis && force_axis[0] >= '0' && force_axis[0] <= '2') ? force_axis[0] - '0' : -1;
-  if (force < 0 && nbe > 0) {
-    k_vv_normal_sums<<<cx_blocks(nbe, 256, (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(a.norm, a.ep, nbe, nvert, acc);
-    ctx->launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_normal_sums", e);
-  }
-  k_vv_classify<<<cx_blocks(a.nown, 256, (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(a, acc, force);
-  ctx->launches++;
-  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_classify", e);
+  const char *force_axis = getenv("CX_VV_AXIS");
+  a.force_axis = (force_axis && force_axis[0] >= '0' && force_axis[0] <= '2') ? force_axis[0] - '0' : -1;
   // see plane_kill<WIDE>: below this dr several voxels of a cut line lie within eps of a plane as a rule
-  static const char *force_wide = getenv("CX_VV_WIDE");
+  const char *force_wide = getenv("CX_VV_WIDE");
   const bool wide = force_wide ? (force_wide[0] == '1') : (dr < 3.0e-3f);
-  if (wide) {
-    if ((e = vv_launch_axis<2, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<z>", e);
-    if ((e = vv_launch_axis<1, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<y>", e);
-    if ((e = vv_launch_axis<0, true>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<x>", e);
-  } else {
-    if ((e = vv_launch_axis<2, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<z>", e);
-    if ((e = vv_launch_axis<1, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<y>", e);
-    if ((e = vv_launch_axis<0, false>(ctx, a)) != cudaSuccess) return fail("k_vert_volume<x>", e);
+  // The owned vertices are processed in chunks whose scratch (heads, dead-line masks, plane store) stays within ~2 GB.  The plane
+  // store holds 1.5 x the mean fan size per vertex (mean = 3 nbe / nvert: every segment sits in three fans); a chunk whose fans
+  // are larger than that overflows into the monolithic kernel's list.
+  const double mean_fan = nvert > 0 && nbe > 0 ? 3.0 * (double)nbe / (double)nvert : 6.0;
+  const double tri_per_vertex = fmin(fmax(1.5 * mean_fan, 4.0), (double)VV_TCAP_SMALL);
+  const double bytes_per_vertex = sizeof(int4) + VV_GS * sizeof(unsigned long long) + tri_per_vertex * VV_PLANE_F4 * sizeof(float4);
+  static const char *chunk_env = getenv("CX_VV_CHUNK");      // vertices per chunk (testing)
+  int64_t cmax_v = chunk_env ? atoll(chunk_env) : (int64_t)(2.0e9 / bytes_per_vertex);
+  if (cmax_v < 1) cmax_v = 1;
+  const int64_t cv = a.nown < cmax_v ? a.nown : cmax_v;
+  a.plane_cap = (int)fmin(tri_per_vertex * (double)cv + 64.0, 2.0e9);
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned long long) * VV_GS * (size_t)cv),
+               plane_bytes = up(sizeof(float4) * VV_PLANE_F4 * (size_t)a.plane_cap), list_bytes = sizeof(int) * 4 * (size_t)a.nown;
+  char *tmp = nullptr;
+  CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + head_bytes + rd_bytes + plane_bytes + list_bytes, ctx->stream));
+  a.ctl = (VVCtl *)tmp;
+  a.heads = (int4 *)(tmp + ctl_bytes);
+  a.rdead = (unsigned long long *)(tmp + ctl_bytes + head_bytes);
+  a.planes = (float4 *)(tmp + ctl_bytes + head_bytes + rd_bytes);
+  a.list = (int *)(tmp + ctl_bytes + head_bytes + rd_bytes + plane_bytes);
+  auto fail = [&](const char *what, cudaError_t e) { cudaFreeAsync(tmp, ctx->stream); return cx_fail(ctx, CX_CUDA_ERROR, what, e); };
+  cudaError_t e = cudaMemsetAsync(tmp, 0, ctl_bytes, ctx->stream);
+  if (e != cudaSuccess) return fail("calc_vert_volume: memset", e);
+  for (int64_t c0 = 0; c0 < a.nown; c0 += cv) {
+    a.c_begin = c0;
+    a.c_end = c0 + cv < a.nown ? c0 + cv : a.nown;
+    if (c0 > 0) {   // new chunk: everything but the monolithic kernel's list length and the error bits starts over
+      if ((e = cudaMemsetAsync(a.ctl->work, 0, sizeof(a.ctl->work), ctx->stream)) != cudaSuccess) return fail("calc_vert_volume: memset", e);
+      if ((e = cudaMemsetAsync(a.ctl->count, 0, 3 * sizeof(int), ctx->stream)) != cudaSuccess) return fail("calc_vert_volume: memset", e);
+      if ((e = cudaMemsetAsync(&a.ctl->bump, 0, sizeof(int), ctx->stream)) != cudaSuccess) return fail("calc_vert_volume: memset", e);
+    }
+    const int64_t items = a.c_end - a.c_begin;
+    if ((e = vv_launch(ctx, k_vv_fans, a, items)) != cudaSuccess) return fail("k_vv_fans", e);
+    if ((e = vv_launch_axis<2>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<z>", e);
+    if ((e = vv_launch_axis<1>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<y>", e);
+    if ((e = vv_launch_axis<0>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<x>", e);
   }
-  // last launch: the (rare) vertices with more than 16 triangles, work list built by the launches above
-  if (wide) k_vert_volume<CX_TRIMAX, 3, true, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  else k_vert_volume<CX_TRIMAX, 3, false, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  // last launch: the (rare) vertices with more than 16 triangles, work list built by k_vv_fans
+  if (wide) k_vert_volume<CX_TRIMAX, true, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else k_vert_volume<CX_TRIMAX, false, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
   ctx->launches++;
-  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vert_volume_big", e);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vert_volume", e);
   e = cudaMemcpyAsync(ctx->h_mail + 17, &a.ctl->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (e != cudaSuccess) return fail("calc_vert_volume: read-back", e);
   CX_CUDA(ctx, cudaFreeAsync(tmp, ctx->stream));

@@ -1,6 +1,7 @@
 set -x
 python tools/run_case.py > gpurun_out/ax_auto.log 2>&1; echo rc=$? >> gpurun_out/ax_auto.log
+CX_VV_CHUNK=777 python tools/run_case.py > gpurun_out/ax_chunk.log 2>&1; echo rc=$? >> gpurun_out/ax_chunk.log
 for ax in 0 1 2; do CX_VV_AXIS=$ax python tools/run_case.py > gpurun_out/ax_$ax.log 2>&1; echo rc=$? >> gpurun_out/ax_$ax.log; done
-python tools/exp_vv_axis.py > gpurun_out/exp_axis2.log 2>&1
-python bench.py --config 2 --steps 5 --warmup 3 > gpurun_out/b2_ax.log 2> gpurun_out/b2_ax.err
-tail -2 gpurun_out/ax_*.log; cat gpurun_out/exp_axis2.log
+python tools/time_vv.py 2
+python tools/time_vv.py 4 300
+python tools/exp_vv_axis.py
