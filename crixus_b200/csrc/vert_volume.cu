@@ -66,6 +66,8 @@ struct VVArgs {
   int plane_cap;             // its capacity in fan triangles
   unsigned long long *rdead; // per chunk slot: 41 words, bit l of word k = line (k, l) is dead
   int force_axis;            // CX_VV_AXIS: one line direction for every vertex (-1: by the fan normal)
+  const int *adj_start;      // vertex -> (segment, corner) adjacency (k_vv_adj_*): entries adj[adj_start[v] .. adj_start[v+1])
+  const int *adj;            // entry = segment * 4 + corner
   float gz[VV_GS];           // ((float)m - 20.f) * gdr   (crixus_d.cu:493-495)
 };
 
@@ -168,6 +170,13 @@ __device__ unsigned long long vv_stats[16];
 // ignore the result.
 #ifndef VV_EXP
 #define VV_EXP 0
+#endif
+// resident blocks per SM the kernels are compiled for (register budget = 65536 / (128 * blocks))
+#ifndef VV_LB_LINES
+#define VV_LB_LINES 7
+#endif
+#ifndef VV_LB_FANS
+#define VV_LB_FANS 10
 #endif
 #define VV_UNLIKELY(x) ((VV_EXP & 1) ? __builtin_expect(!!(x), 0) : (x))
 template <class Pred>
@@ -653,7 +662,10 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
 // ---------------------------------------------------------------------------------------------------------------
 // Phase A of one vertex (warp-cooperative): fan gather, chain ordering, edge-normal pairing, plane vectors -> w.
 // Returns false when the vertex is finished here (error flagged or volume zero written).  av = the reference's avnorm.
-template <int TCAP, class VVWarp>
+// CSR: the fan and the edge neighbours come from the vertex -> (segment, corner) adjacency built once per call (k_vv_adj_*)
+// instead of two scans over every segment of the 27 cells (~1700 segments per vertex on configs[1]); the 27 cell ranges only
+// serve to put the fan into the reference's discovery order and to reproduce what the reference's scan cannot see.
+template <int TCAP, bool CSR, class VVWarp>
 __device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t i, const f3 pi, const int tris, const int lane,
                                        int &closed_out, f3 &av_out)
 {
@@ -670,21 +682,61 @@ __device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t
   }
   // ---------------- fan gather (crixus_d.cu:316-369): discovery order = cell order, segment order, corner order
   int itris = 0;
-  for (int c27 = 0; c27 < 27; c27++) {
-    const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
-    for (int base = b; base < e; base += 32) {
-      const int j = base + lane;
-      int4 E = make_int4(-1, -1, -1, -1);
-      if (j < e) E = __ldg(&a.ep[j]);
-      const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
-      const int cnt = m0 + m1 + m2;
-      if (!__any_sync(0xffffffffu, cnt != 0)) continue;
-      const int incl = warp_incl_scan_i(cnt, lane);
-      int off = itris + incl - cnt;
-      if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
-      if (m1 && off < TCAP) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
-      if (m2 && off < TCAP) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
-      itris += __shfl_sync(0xffffffffu, incl, 31);
+  if (CSR) {
+    // entry = segment * 4 + corner.  Its place in the discovery order: (position of its cell among the 27, segment, corner);
+    // the cell is the one whose range holds the segment (a ballot over the lanes' ranges).  A segment outside the neighbourhood
+    // is not found by the reference's scan, one whose cell the neighbourhood holds twice (periodic grid of < 3 cells) is found
+    // twice: both end in the itris != tris error below.
+    const int base = __ldg(&a.adj_start[i]), ni = __ldg(&a.adj_start[i + 1]) - base;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(&w.plane[0][0]);   // scratch: the planes come later
+    const int nstore = min(ni, TCAP);
+    for (int eb = 0; eb < ni; eb += 32) {
+      const int e = eb + lane;
+      int ent = 0, rank = 0;
+      if (e < ni) ent = __ldg(&a.adj[base + e]);
+      const int nb = min(32, ni - eb);
+      for (int t = 0; t < nb; t++) {
+        const int st = __shfl_sync(0xffffffffu, ent, t) >> 2;
+        const unsigned m = __ballot_sync(0xffffffffu, lane < 27 && st >= cb && st < ce);
+        itris += __popc(m);
+        if (lane == t) rank = m ? __ffs(m) - 1 : 27;
+      }
+      if (e < nstore) keys[e] = ((unsigned long long)(unsigned)rank << 32) | (unsigned)ent;
+    }
+    if (ni != tris) itris = -1;
+    __syncwarp();
+    if (itris == tris) {
+      for (int eb = 0; eb < nstore; eb += 32) {
+        const int e = eb + lane;
+        if (e < nstore) {
+          const unsigned long long key = keys[e];
+          int off = 0;
+          for (int t = 0; t < nstore; t++) off += keys[t] < key;
+          const int ent = (int)(unsigned)key, j = ent >> 2, c = ent & 3;
+          const int4 E = __ldg(&a.ep[j]);
+          w.tri[off][0] = c == 0 ? E.y : (c == 1 ? E.z : E.x);
+          w.tri[off][1] = c == 0 ? E.z : (c == 1 ? E.x : E.y);
+          w.tri[off][2] = j;
+        }
+      }
+    }
+  } else {
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
+      for (int base = b; base < e; base += 32) {
+        const int j = base + lane;
+        int4 E = make_int4(-1, -1, -1, -1);
+        if (j < e) E = __ldg(&a.ep[j]);
+        const int m0 = (E.x == (int)i), m1 = (E.y == (int)i), m2 = (E.z == (int)i);
+        const int cnt = m0 + m1 + m2;
+        if (!__any_sync(0xffffffffu, cnt != 0)) continue;
+        const int incl = warp_incl_scan_i(cnt, lane);
+        int off = itris + incl - cnt;
+        if (m0 && off < TCAP) { w.tri[off][0] = E.y; w.tri[off][1] = E.z; w.tri[off][2] = j; off++; }
+        if (m1 && off < TCAP) { w.tri[off][0] = E.z; w.tri[off][1] = E.x; w.tri[off][2] = j; off++; }
+        if (m2 && off < TCAP) { w.tri[off][0] = E.x; w.tri[off][1] = E.y; w.tri[off][2] = j; off++; }
+        itris += __shfl_sync(0xffffffffu, incl, 31);
+      }
     }
   }
   if (itris != tris) {  // triangles outside the 27-cell neighbourhood: the reference reads garbage here
@@ -724,30 +776,75 @@ __device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t
   }
 
   // ---------------- edge-normal pairing (crixus_d.cu:409-464): the <=2 segments that contain both ends of fan edge k.
-  // A 64-bit filter of the rim vertices (id mod 64) rejects almost every segment batch without entering the k loop.
-  uint64_t rim = 0ull;
-  for (int k = 0; k < tris; k++) rim |= (1ull << (w.tri[k][0] & 63)) | (1ull << (w.tri[k][1] & 63));
-  for (int c27 = 0; c27 < 27; c27++) {
-    const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
-    for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
-      const int j = base + lane;
-      int4 E = make_int4(-1, -1, -1, -1);
-      bool cand = false;
-      if (j < e) {
-        E = __ldg(&a.ep[j]);
-        cand = (int)((rim >> (E.x & 63)) & 1ull) + (int)((rim >> (E.y & 63)) & 1ull) + (int)((rim >> (E.z & 63)) & 1ull) >= 2;
+  if (CSR) {
+    // A segment with two corners in {t0, t1} contains t0, or (degenerate) t1 twice: the adjacency lists of t0 and t1 hold them
+    // all.  Each segment is taken once (at its first corner equal to the list's vertex) and counted as often as the scan of the
+    // 27 cells meets it (0: outside the neighbourhood).  The order of the two slots is irrelevant (their normals are added).
+    __syncwarp();
+    for (int k = 0; k < tris; k++) {
+      const int t0 = w.tri[k][0], t1 = w.tri[k][1];
+      int cnt = 0;   // warp-uniform
+      for (int pass = 0; pass < (t0 == t1 ? 1 : 2); pass++) {
+        const int v = pass == 0 ? t0 : t1;
+        const int vb = __ldg(&a.adj_start[v]), vn = __ldg(&a.adj_start[v + 1]) - vb;
+        for (int eb = 0; eb < vn; eb += 32) {
+          const int e = eb + lane;
+          bool hit = false;
+          int sj = 0;
+          if (e < vn) {
+            const int ent = __ldg(&a.adj[vb + e]), c = ent & 3;
+            sj = ent >> 2;
+            const int4 E = __ldg(&a.ep[sj]);
+            const bool first = (c == 0) || (c == 1 && E.x != v) || (c == 2 && E.x != v && E.y != v);
+            const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
+            const bool has0 = E.x == t0 || E.y == t0 || E.z == t0;
+            hit = first && vf == 2 && (pass == 0 || !has0);
+          }
+          unsigned hm = __ballot_sync(0xffffffffu, hit);
+          while (hm) {
+            const int src = __ffs(hm) - 1;
+            hm &= hm - 1u;
+            const int sh = __shfl_sync(0xffffffffu, sj, src);
+            const int mult = __popc(__ballot_sync(0xffffffffu, lane < 27 && sh >= cb && sh < ce));
+            for (int r = 0; r < mult; r++) {
+              if (lane == 0) {
+                if (cnt < 2) w.eseg[k][cnt] = sh;
+                else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
+              }
+              cnt++;
+            }
+          }
+        }
       }
-      if (!__any_sync(0xffffffffu, cand)) continue;
-      for (int k = 0; k < tris; k++) {
-        const int t0 = w.tri[k][0], t1 = w.tri[k][1];
-        const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
-        if (vf == 2) {
-          const int slot = atomicAdd(&w.ecount[k], 1);
-          if (slot < 2) w.eseg[k][slot] = j;
-          else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
+      if (lane == 0) w.ecount[k] = cnt;
+    }
+  } else {
+    // A 64-bit filter of the rim vertices (id mod 64) rejects almost every segment batch without entering the k loop.
+    uint64_t rim = 0ull;
+    for (int k = 0; k < tris; k++) rim |= (1ull << (w.tri[k][0] & 63)) | (1ull << (w.tri[k][1] & 63));
+    for (int c27 = 0; c27 < 27; c27++) {
+      const int b = __shfl_sync(0xffffffffu, cb, c27), e = __shfl_sync(0xffffffffu, ce, c27);
+      for (int base = b; base < e; base += 32) {   // warp-uniform trip count: the warp must stay converged
+        const int j = base + lane;
+        int4 E = make_int4(-1, -1, -1, -1);
+        bool cand = false;
+        if (j < e) {
+          E = __ldg(&a.ep[j]);
+          cand = (int)((rim >> (E.x & 63)) & 1ull) + (int)((rim >> (E.y & 63)) & 1ull) + (int)((rim >> (E.z & 63)) & 1ull) >= 2;
+        }
+        if (!__any_sync(0xffffffffu, cand)) continue;
+        for (int k = 0; k < tris; k++) {
+          const int t0 = w.tri[k][0], t1 = w.tri[k][1];
+          const int vf = (E.x == t0 || E.x == t1) + (E.y == t0 || E.y == t1) + (E.z == t0 || E.z == t1);
+          if (vf == 2) {
+            const int slot = atomicAdd(&w.ecount[k], 1);
+            if (slot < 2) w.eseg[k][slot] = j;
+            else atomicOr(&a.ctl->err, VVE_NONMANIFOLD);
+          }
         }
       }
     }
+    __syncwarp();
   }
   __syncwarp();
 
@@ -885,7 +982,31 @@ __device__ __forceinline__ int64_t vv_owned_vertex(const VVArgs &a, int64_t idx)
 // Fans with more than 16 triangles, and fans that find the chunk's plane store full, go to the monolithic k_vert_volume (list 3).
 struct VVHead { int off, tris, closed, vertex; };
 
-__global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_fans(const __grid_constant__ VVArgs a)
+// vertex -> (segment, corner) adjacency: count, exclusive scan (cx_exclusive_scan_i32), fill.  The order inside a vertex's list
+// is whatever the atomics give; vv_fan sorts the (<= trimax) entries it uses.
+__global__ void __launch_bounds__(256) k_vv_adj_count(const int4 *__restrict__ ep, int64_t nbe, int64_t nvert, int *__restrict__ cnt)
+{
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nbe; s += (int64_t)gridDim.x * blockDim.x) {
+    const int4 E = __ldg(&ep[s]);
+    if ((uint64_t)E.x < (uint64_t)nvert) atomicAdd(&cnt[E.x], 1);
+    if ((uint64_t)E.y < (uint64_t)nvert) atomicAdd(&cnt[E.y], 1);
+    if ((uint64_t)E.z < (uint64_t)nvert) atomicAdd(&cnt[E.z], 1);
+  }
+}
+__global__ void __launch_bounds__(256) k_vv_adj_fill(const int4 *__restrict__ ep, int64_t nbe, int64_t nvert, const int *__restrict__ start,
+                                                     int *__restrict__ cursor, int *__restrict__ adj)
+{
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nbe; s += (int64_t)gridDim.x * blockDim.x) {
+    const int4 E = __ldg(&ep[s]);
+    const int e4 = (int)s * 4;
+    if ((uint64_t)E.x < (uint64_t)nvert) adj[start[E.x] + atomicAdd(&cursor[E.x], 1)] = e4;
+    if ((uint64_t)E.y < (uint64_t)nvert) adj[start[E.y] + atomicAdd(&cursor[E.y], 1)] = e4 + 1;
+    if ((uint64_t)E.z < (uint64_t)nvert) adj[start[E.z] + atomicAdd(&cursor[E.z], 1)] = e4 + 2;
+  }
+}
+
+template <bool CSR>
+__global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_FANS) k_vv_fans(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
@@ -915,7 +1036,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_fans(const __grid_const
     }
     int closed;
     f3 av;
-    if (!vv_fan<VV_TCAP_SMALL>(a, w, i, pi, tris, lane, closed, av)) continue;
+    if (!vv_fan<VV_TCAP_SMALL, CSR>(a, w, i, pi, tris, lane, closed, av)) continue;
     int off = 0;
     if (lane == 0) off = atomicAdd(&a.ctl->bump, tris);
     off = __shfl_sync(0xffffffffu, off, 0);
@@ -985,7 +1106,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_rows(const __grid_const
 }
 
 template <int AX, bool WIDE>
-__global__ void __launch_bounds__(VV_WARPS * 32, AX == 2 ? 6 : 5) k_vv_lines(const __grid_constant__ VVArgs a)
+__global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_LINES) k_vv_lines(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
@@ -1018,7 +1139,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, AX == 2 ? 6 : 5) k_vv_lines(con
 }
 
 // The monolithic form: all phases of a vertex in one kernel, fans of up to TCAP = trimax triangles; serves work list 3
-template <int TCAP, bool WIDE, int AX>
+template <int TCAP, bool WIDE, int AX, bool CSR>
 __global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_constant__ VVArgs a)
 {
   typedef VVWarpT<TCAP> VVWarp;
@@ -1046,7 +1167,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_c
     const int tris = __ldg(&a.trisize[i]);    // 1 .. trimax (k_vv_fans)
     int closed;
     f3 av;
-    if (!vv_fan<TCAP>(a, w, i, pi, tris, lane, closed, av)) continue;
+    if (!vv_fan<TCAP, CSR>(a, w, i, pi, tris, lane, closed, av)) continue;
     vv_rows<AX>(a, w, gzt, tris, closed, pi, lane, rd);
     vv_lines<AX, WIDE>(a, w, gzt, tris, closed, pi, lane, rd, wq, xres, i);
     __syncwarp();
@@ -1154,9 +1275,13 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   a.plane_cap = (int)fmin(tri_per_vertex * (double)cv + 64.0, 2.0e9);
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned long long) * VV_GS * (size_t)cv),
-               plane_bytes = up(sizeof(float4) * VV_PLANE_F4 * (size_t)a.plane_cap), list_bytes = sizeof(int) * 4 * (size_t)a.nown;
+               plane_bytes = up(sizeof(float4) * VV_PLANE_F4 * (size_t)a.plane_cap), list_bytes = up(sizeof(int) * 4 * (size_t)a.nown);
+  // CX_VV_SCAN=1: fans by scanning the 27 cells (the form without the adjacency; also taken when segment * 4 + corner overflows)
+  const char *scan_env = getenv("CX_VV_SCAN");
+  const bool csr = !(scan_env && scan_env[0] == '1') && nbe > 0 && nbe < ((int64_t)1 << 29);
+  const size_t start_bytes = csr ? up(sizeof(int) * ((size_t)nvert + 1)) : 0, adj_bytes = csr ? up(sizeof(int) * 3 * (size_t)nbe) : 0;
   char *tmp = nullptr;
-  CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + head_bytes + rd_bytes + plane_bytes + list_bytes, ctx->stream));
+  CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + head_bytes + rd_bytes + plane_bytes + list_bytes + 2 * start_bytes + adj_bytes, ctx->stream));
   a.ctl = (VVCtl *)tmp;
   a.heads = (int4 *)(tmp + ctl_bytes);
   a.rdead = (unsigned long long *)(tmp + ctl_bytes + head_bytes);
@@ -1165,6 +1290,24 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   auto fail = [&](const char *what, cudaError_t e) { cudaFreeAsync(tmp, ctx->stream); return cx_fail(ctx, CX_CUDA_ERROR, what, e); };
   cudaError_t e = cudaMemsetAsync(tmp, 0, ctl_bytes, ctx->stream);
   if (e != cudaSuccess) return fail("calc_vert_volume: memset", e);
+  a.adj_start = nullptr;
+  a.adj = nullptr;
+  if (csr) {
+    int *start = (int *)(tmp + ctl_bytes + head_bytes + rd_bytes + plane_bytes + list_bytes);
+    int *cursor = (int *)((char *)start + start_bytes), *adj = (int *)((char *)start + 2 * start_bytes);
+    if ((e = cudaMemsetAsync(start, 0, 2 * start_bytes, ctx->stream)) != cudaSuccess) return fail("calc_vert_volume: memset", e);
+    const int gb = cx_blocks(nbe, 256, (int64_t)ctx->num_sms * 16);
+    k_vv_adj_count<<<gb, 256, 0, ctx->stream>>>(a.ep, nbe, nvert, start);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_adj_count", e);
+    const int rc = cx_exclusive_scan_i32(ctx, start, start, nvert + 1);   // in place; start[nvert] = number of entries
+    if (rc != CX_OK) { cudaFreeAsync(tmp, ctx->stream); return rc; }
+    k_vv_adj_fill<<<gb, 256, 0, ctx->stream>>>(a.ep, nbe, nvert, start, cursor, adj);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vv_adj_fill", e);
+    a.adj_start = start;
+    a.adj = adj;
+  }
   for (int64_t c0 = 0; c0 < a.nown; c0 += cv) {
     a.c_begin = c0;
     a.c_end = c0 + cv < a.nown ? c0 + cv : a.nown;
@@ -1174,14 +1317,16 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
       if ((e = cudaMemsetAsync(&a.ctl->bump, 0, sizeof(int), ctx->stream)) != cudaSuccess) return fail("calc_vert_volume: memset", e);
     }
     const int64_t items = a.c_end - a.c_begin;
-    if ((e = vv_launch(ctx, k_vv_fans, a, items)) != cudaSuccess) return fail("k_vv_fans", e);
+    if ((e = csr ? vv_launch(ctx, k_vv_fans<true>, a, items) : vv_launch(ctx, k_vv_fans<false>, a, items)) != cudaSuccess) return fail("k_vv_fans", e);
     if ((e = vv_launch_axis<2>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<z>", e);
     if ((e = vv_launch_axis<1>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<y>", e);
     if ((e = vv_launch_axis<0>(ctx, a, wide, items)) != cudaSuccess) return fail("k_vv_rows/lines<x>", e);
   }
   // last launch: the (rare) vertices with more than 16 triangles, work list built by k_vv_fans
-  if (wide) k_vert_volume<CX_TRIMAX, true, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
-  else k_vert_volume<CX_TRIMAX, false, 2><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  if (wide && csr) k_vert_volume<CX_TRIMAX, true, 2, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else if (wide) k_vert_volume<CX_TRIMAX, true, 2, false><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else if (csr) k_vert_volume<CX_TRIMAX, false, 2, true><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
+  else k_vert_volume<CX_TRIMAX, false, 2, false><<<ctx->num_sms, VV_WARPS * 32, 0, ctx->stream>>>(a);
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_vert_volume", e);
   e = cudaMemcpyAsync(ctx->h_mail + 17, &a.ctl->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
