@@ -34,8 +34,11 @@ def main():
     torch.cuda.synchronize()
     ms = hp.collect_stage_ms() / reps
     vv = float(ms[hp.STAGES.index("vert_volume")])
-    print("%s | lib %s | nvert %d | vert_volume %.3f ms  %.2f Mverts/s | vol_hash %s" % (
-        name, os.path.basename(os.environ.get("CX_LIB_PATH", "default")), w["nvert"], vv, w["nvert"] / vv / 1e3, hp.check()["vol_hash"]), flush=True)
+    fill = float(ms[hp.STAGES.index("fill")])
+    chk = hp.check()
+    print("%s | lib %s | nvert %d | vert_volume %.3f ms  %.2f Mverts/s | vol_hash %s | fill %.3f ms fpos_hash %s" % (
+        name, os.path.basename(os.environ.get("CX_LIB_PATH", "default")), w["nvert"], vv, w["nvert"] / vv / 1e3, chk["vol_hash"], fill,
+        chk["fpos_hash"]), flush=True)
 
 
 if __name__ == "__main__":
