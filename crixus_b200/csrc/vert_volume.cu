@@ -64,7 +64,7 @@ struct VVArgs {
   int4 *heads;               // per chunk slot: plane offset, fan size, closed, vertex
   float4 *planes;            // plane store of the chunk: 10 float4 per fan triangle
   int plane_cap;             // its capacity in fan triangles
-  unsigned long long *rdead; // per chunk slot: 41 words, bit l of word k = line (k, l) is dead
+  unsigned long long *rdead; // per chunk slot: 2 x 41 words, bit l of word k = line (k, l) is dead / touched by a voronoi or edge plane
   int force_axis;            // CX_VV_AXIS: one line direction for every vertex (-1: by the fan normal)
   const int *adj_start;      // vertex -> (segment, corner) adjacency (k_vv_adj_*): entries adj[adj_start[v] .. adj_start[v+1])
   const int *adj;            // entry = segment * 4 + corner
@@ -446,18 +446,29 @@ __device__ __forceinline__ void rows_dead(const VVArgs &a, const VVWarp &w, cons
     int lo;
     bool pa;
     uint64_t dead;
+    // the lines of the row a voronoi / edge plane TOUCHES (removes or halves a voxel of): its expression exceeds -eps
+    // somewhere on the line, i.e. at the end where it is largest -- the same kind of predicate of l
+    auto high_end = [&](const f3 &c) { return place3<AX>(cget<AX>(c) >= 0.f ? gB : gA, gu, 0.f); };
+    uint64_t touch;
     {  // voronoi plane
       const PlaneF<VX, 0> f = make_plane<VX, 0>(t.e1, t.c6, pi, low_end(t.e1));
       dead = mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
+      const PlaneF<VX, 0> fh = make_plane<VX, 0>(t.e1, t.c6, pi, high_end(t.e1));
+      touch = mono_mask(gzt, fh(gA), fh(gB), fh, [&](float v) { return v > neps; }, lo, pa);
     }
     if (OPEN) {
       const PlaneF<VX, 0> f = make_plane<VX, 0>(t.e2, t.c8, pi, low_end(t.e2));
       dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
+      const PlaneF<VX, 0> fh = make_plane<VX, 0>(t.e2, t.c8, pi, high_end(t.e2));
+      touch |= mono_mask(gzt, fh(gA), fh(gB), fh, [&](float v) { return v > neps; }, lo, pa);
     }
     {  // edge plane
       const PlaneF<VX, 1> f = make_plane<VX, 1>(t.en, t.e1, pi, low_end(t.en));
       dead |= mono_mask(gzt, f(gA), f(gB), f, [&](float v) { return v > eps; }, lo, pa);
+      const PlaneF<VX, 1> fh = make_plane<VX, 1>(t.en, t.e1, pi, high_end(t.en));
+      touch |= mono_mask(gzt, fh(gA), fh(gB), fh, [&](float v) { return v > neps; }, lo, pa);
     }
+    if (act && touch) atomicOr(&rd[48 + k], (unsigned long long)touch);
     {  // wall sector: w0 >= eps, w1 >= -eps, w2 >= -eps at both ends
       const PlaneF<VX, 2> f0 = make_plane<VX, 2>(t.c9, t.c9, pi, low_end(t.c9));
       const PlaneF<VX, 2> f1 = make_plane<VX, 2>(t.c10, t.c10, pi, low_end(t.c10));
@@ -505,7 +516,7 @@ __device__ __forceinline__ long long group_weight(uint64_t va, const uint64_t (&
 // than AX (place3).
 template <int AX, bool OPEN, bool WIDE, class VVWarp>
 __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, f3 pi, float gu,
-                                                 float gv, bool valid, unsigned long long *xres, int lane)
+                                                 float gv, bool valid, bool ve, unsigned long long *xres, int lane)
 {
   const float thr = a.thr_cube, eps = a.eps, neps = -a.eps;
   const float gA = a.gz[0], gB = a.gz[VV_GS - 1];
@@ -516,7 +527,7 @@ __device__ __forceinline__ long long line_weight(const VVArgs &a, const VVWarp &
   // wall tetrahedra second.  The per-voxel result is a product over triangles and families, so the order is free; two
   // small loop bodies instead of one large one keep the hot code inside the instruction cache (ncu: instruction-fetch
   // stalls were a quarter of the issue interval), and lines that the voronoi planes remove never reach the wall tests.
-  for (int j = 0; j < tris; j++) {
+  for (int j = 0; j < (ve ? tris : 0); j++) {    // ve: warp-uniform (vv_lines: the ring of the lines those planes touch)
     if (!__any_sync(VV_FULLWARP, alive != 0ull)) break;
     TriPlanes t;
     VV_LOAD_VE(w.plane[j], t);
@@ -899,12 +910,13 @@ __device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t
   return true;
 }
 
-// Pass 1 of one vertex: rd[k] bit l = line (k, l) is removed whole by one triangle (48 words per warp, 41 used)
+// Pass 1 of one vertex: rd[k] bit l = line (k, l) is removed whole by one triangle; rd[48 + k] bit l = some voronoi / edge plane
+// touches line (k, l) (96 words per warp, 2 x 41 used)
 template <int AX, class VVWarp>
 __device__ __forceinline__ void vv_rows(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
                                         unsigned long long *rd)
 {
-  for (int r = lane; r < 48; r += 32) rd[r] = 0ull;
+  for (int r = lane; r < 96; r += 32) rd[r] = 0ull;
   __syncwarp();
   if (closed) rows_dead<AX, false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
   else rows_dead<AX, true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
@@ -917,30 +929,40 @@ template <int AX, bool WIDE, class VVWarp>
 __device__ __forceinline__ void vv_lines(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
                                          const unsigned long long *rd, unsigned short *wq, unsigned long long *xres, int64_t i)
 {
+  // Two rings: lines that no voronoi / edge plane touches (pass 1 knows) run line_weight without its first triangle loop.
+  // On a wall-like fan with the lines along the normal those planes are parallel to the lines: they remove whole lines (pass 1)
+  // and touch the few that lie within eps of them, nothing else.
   long long acc = 0;
-  int qn = 0, qh = 0;   // ring fill / head (warp-uniform)
+  int qn0 = 0, qh0 = 0, qn1 = 0, qh1 = 0;   // ring fill / head (warp-uniform); ring 0: untouched lines, ring 1: touched
   for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
     const int line = it * 32 + lane;
     const bool valid = line < VV_LINES;
     const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
     // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so one table serves all three
     const bool dead = !valid || ((rd[k] >> l) & 1ull);
-    const unsigned live = __ballot_sync(VV_FULLWARP, !dead);
-    if (!dead) wq[(qh + qn + __popc(live & ((1u << lane) - 1u))) & 63] = (unsigned short)line;
-    qn += __popc(live);
+    const bool tch = ((rd[48 + k] >> l) & 1ull) != 0ull;
+    const unsigned live0 = __ballot_sync(VV_FULLWARP, !dead && !tch), live1 = __ballot_sync(VV_FULLWARP, !dead && tch);
+    const unsigned below = (1u << lane) - 1u;
+    if (!dead && !tch) wq[(qh0 + qn0 + __popc(live0 & below)) & 63] = (unsigned short)line;
+    if (!dead && tch) wq[64 + ((qh1 + qn1 + __popc(live1 & below)) & 63)] = (unsigned short)line;
+    qn0 += __popc(live0);
+    qn1 += __popc(live1);
     __syncwarp();
     const bool last = it == (VV_LINES + 31) / 32 - 1;
-    while (qn >= 32 || (last && qn > 0)) {
-      const bool have = lane < qn;
-      VV_STAT(6, min(qn, 32)); VV_STAT(12, 1);
-      const int ln = have ? (int)wq[(qh + lane) & 63] : 0;
+    for (;;) {   // one call site of line_weight for both rings (it is the bulk of the kernel's code)
+      const int lim = last ? 1 : 32;
+      const int rg = qn1 >= lim ? 1 : (qn0 >= lim ? 0 : -1);
+      if (rg < 0) break;
+      const int take = min(rg ? qn1 : qn0, 32), qh = rg ? qh1 : qh0;
+      const bool have = lane < take;
+      VV_STAT(6, take); VV_STAT(12, 1);
+      const int ln = have ? (int)wq[rg * 64 + ((qh + lane) & 63)] : 0;
       const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
       const float h0 = gzt[kk], h1 = gzt[ll];
-      acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane)
-                    : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, xres, lane);
-      const int took = min(qn, 32);
-      qh = (qh + took) & 63;
-      qn -= took;
+      acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, rg != 0, xres, lane)
+                    : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, rg != 0, xres, lane);
+      if (rg) { qh1 = (qh1 + take) & 63; qn1 -= take; }
+      else { qh0 = (qh0 + take) & 63; qn0 -= take; }
       __syncwarp();
     }
   }
@@ -1082,7 +1104,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_rows(const __grid_const
   typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   __shared__ __align__(16) float gzt[64 + 256];
-  __shared__ unsigned long long rds[VV_WARPS][48];
+  __shared__ unsigned long long rds[VV_WARPS][96];
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
   unsigned long long *rd = rds[threadIdx.x >> 5];
@@ -1099,8 +1121,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_rows(const __grid_const
     const VVHead h = vv_fetch(a, w, slot, lane);
     const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
     vv_rows<AX>(a, w, gzt, h.tris, h.closed, pi, lane, rd);
-    unsigned long long *out = a.rdead + (int64_t)slot * VV_GS;
-    for (int r = lane; r < VV_GS; r += 32) out[r] = rd[r];
+    unsigned long long *out = a.rdead + (int64_t)slot * (2 * VV_GS);
+    for (int r = lane; r < 2 * VV_GS; r += 32) out[r] = rd[r < VV_GS ? r : r - VV_GS + 48];
     __syncwarp();
   }
 }
@@ -1111,8 +1133,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_LINES) k_vv_lines(const _
   typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   __shared__ __align__(16) float gzt[64 + 256];
-  __shared__ unsigned short wqs[VV_WARPS][64];    // per-warp ring of surviving lines
-  __shared__ unsigned long long rds[VV_WARPS][48]; // per-warp: bit l of rds[.][k] = line (k, l) is dead
+  __shared__ unsigned short wqs[VV_WARPS][128];   // per-warp rings of surviving lines (2 x 64)
+  __shared__ unsigned long long rds[VV_WARPS][96]; // per-warp: bit l of rds[.][k] = line (k, l) is dead, of rds[.][48 + k]: touched
   __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
@@ -1129,8 +1151,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_LINES) k_vv_lines(const _
     if ((int64_t)widx >= nlist) break;
     const int slot = list[widx];
     __syncwarp();
-    const unsigned long long *in = a.rdead + (int64_t)slot * VV_GS;
-    for (int r = lane; r < VV_GS; r += 32) rd[r] = in[r];
+    const unsigned long long *in = a.rdead + (int64_t)slot * (2 * VV_GS);
+    for (int r = lane; r < 2 * VV_GS; r += 32) rd[r < VV_GS ? r : r - VV_GS + 48] = in[r];
     const VVHead h = vv_fetch(a, w, slot, lane);
     const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
     vv_lines<AX, WIDE>(a, w, gzt, h.tris, h.closed, pi, lane, rd, wq, xres, h.vertex);
@@ -1145,8 +1167,8 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_c
   typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   __shared__ __align__(16) float gzt[64 + 256];
-  __shared__ unsigned short wqs[VV_WARPS][64];
-  __shared__ unsigned long long rds[VV_WARPS][48];
+  __shared__ unsigned short wqs[VV_WARPS][128];
+  __shared__ unsigned long long rds[VV_WARPS][96];
   __shared__ unsigned long long xress[VV_WARPS][128];
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
@@ -1267,14 +1289,14 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   // are larger than that overflows into the monolithic kernel's list.
   const double mean_fan = nvert > 0 && nbe > 0 ? 3.0 * (double)nbe / (double)nvert : 6.0;
   const double tri_per_vertex = fmin(fmax(1.5 * mean_fan, 4.0), (double)VV_TCAP_SMALL);
-  const double bytes_per_vertex = sizeof(int4) + VV_GS * sizeof(unsigned long long) + tri_per_vertex * VV_PLANE_F4 * sizeof(float4);
+  const double bytes_per_vertex = sizeof(int4) + 2 * VV_GS * sizeof(unsigned long long) + tri_per_vertex * VV_PLANE_F4 * sizeof(float4);
   static const char *chunk_env = getenv("CX_VV_CHUNK");      // vertices per chunk (testing)
   int64_t cmax_v = chunk_env ? atoll(chunk_env) : (int64_t)(2.0e9 / bytes_per_vertex);
   if (cmax_v < 1) cmax_v = 1;
   const int64_t cv = a.nown < cmax_v ? a.nown : cmax_v;
   a.plane_cap = (int)fmin(tri_per_vertex * (double)cv + 64.0, 2.0e9);
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned long long) * VV_GS * (size_t)cv),
+  const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned long long) * 2 * VV_GS * (size_t)cv),
                plane_bytes = up(sizeof(float4) * VV_PLANE_F4 * (size_t)a.plane_cap), list_bytes = up(sizeof(int) * 4 * (size_t)a.nown);
   // CX_VV_SCAN=1: fans by scanning the 27 cells (the form without the adjacency; also taken when segment * 4 + corner overflows)
   const char *scan_env = getenv("CX_VV_SCAN");
