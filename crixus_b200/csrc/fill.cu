@@ -578,7 +578,10 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
   }
 }
 
-__global__ void __launch_bounds__(RB_WARPS * 32, 2) k_resolve_blocks(const __grid_constant__ FillArgs A)
+#ifndef FILL_LB
+#define FILL_LB 2
+#endif
+__global__ void __launch_bounds__(RB_WARPS * 32, FILL_LB) k_resolve_blocks(const __grid_constant__ FillArgs A)
 {
   __shared__ RBWarp sW[RB_WARPS];
   const int lane = threadIdx.x & 31;
