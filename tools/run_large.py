@@ -68,6 +68,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {"config": kind, "size": size, "n_gpus": world}
     ctx = api.Context(local)
+    if world > 1:   # the library's own NCCL communicator (as bench.py): rank 0 creates the id, torch.distributed ships the 128 bytes
+        box = [api.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.dist_init(box[0], world, rank)
     dev = ctx.device
     if rank == 0:      # rank 0 generates and welds the mesh; the other ranks receive the welded arrays over NCCL
         t0 = time.time()
@@ -133,6 +137,7 @@ def main():
         print(json.dumps(out), flush=True)
     if rank != 0:       # the checks below run on rank 0 (every rank holds the gathered volumes and the merged bitfield)
         dist.barrier()
+        ctx.dist_finalize()
         dist.destroy_process_group()
         return
     # ---- properties
@@ -197,6 +202,7 @@ def main():
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "large_%s_%d%s.json" % (kind, size, "" if world == 1 else "_n%d" % world)), "w"), indent=1)
     if world > 1:
         dist.barrier()
+        ctx.dist_finalize()
         dist.destroy_process_group()
 
 
