@@ -324,13 +324,15 @@ def main():
                        "vert_volume_verts_per_s": nalive / (vv_ms * 1e-3), "fill_cells_per_s": G / (fill_ms * 1e-3),
                        "ms": {k: float(v) for k, v in zip(hp.STAGES, stage_ms)}, "fill_rounds": hp.fill_rounds},
             "check": check,
-            "roofline": {"kernel": "k_vert_volume", "bound": "fp32_alu", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": "calc_vert_volume = k_vv_fans + k_vv_rows<AX> + k_vv_lines<AX> per chunk of vertices (one C-ABI call)",
+                         "bound": "fp32_alu", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": nv_ncu.get("dram_bytes"),
                          "issue_slot_frac": nv_ncu.get("issue_slot_frac"), "instr_per_vertex": nv_ncu.get("warp_instr_per_vertex"),
                          "executed_fma_frac": nv_ncu.get("fma_pipe_frac"),
-                         "frac_note": "ALGORITHMIC flops of the reference's brute-force 41^3 quadrature over the measured FFMA peak; the kernel "
-                                      "removes > 90 % of them by exact culling (monotone threshold search), hence frac > 1.  The machine view is "
-                                      "issue_slot_frac / instr_per_vertex / executed_fma_frac (ncu, profiles/)",
+                         "frac_note": "ALGORITHMIC flops of the reference's brute-force 41^3 quadrature over the measured FFMA peak; the kernels "
+                                      "remove > 95 % of them by exact culling (monotone threshold search), hence frac > 1.  The machine view is "
+                                      "issue_slot_frac / instr_per_vertex (warp instructions) / executed_fma_frac from the whole-pass ncu capture of "
+                                      "this workload (profiles/ncu_summary.json): the honest bound is instruction issue",
                          "peak_source": "FFMA micro-kernel measured in this run (cx_measure_fp32_peak); nominal 148*128*2*1.965 GHz = 74.4",
                          "flops_per_vertex": VOXELS * T * FLOP_PER_VOXEL_TRI, "mean_trisize": T,
                          "hbm_frac": (hp.vv_bytes / (hp.vv_kernel_ms * 1e-3) / 1e9) / hbm_peak if hp.vv_bytes else None},
