@@ -26,7 +26,7 @@ def main():
             cur = m.group(1)
             kernels[cur] = collections.Counter()
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
         if m and cur:
             kernels[cur][m.group(1)] += 1
     dem = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
@@ -54,13 +54,14 @@ def main():
     print("# warp-collective instructions used instead: " + ", ".join("%s=%d" % (o, tot_special.get(o, 0)) for o in ("VOTE", "SHFL", "MATCH", "REDUX", "ATOMG", "ATOMS", "REDG")))
     print("# No TMA, no mbarrier, no tcgen05, no cp.async on purpose: none of the kernels moves dense tiles.  The HBM-bound passes\n"
           "# (set_bound_elem, binning, records, weld) are one-touch gathers/scatters of 16-byte AoS elements (LDG.128/STG.128, coalesced\n"
-          "# where the index allows); calc_vert_volume keeps its per-vertex working set (<= 8 KB: 160 B per fan triangle + mask tables)\n"
-          "# in shared memory written by the warp that computed it -- there is nothing in global memory to bulk-copy; the fill's\n"
-          "# record-driven resolve keeps ONE 80-byte record in registers per thread and touches ~100 lattice cells; the flood works on\n"
-          "# 1 x 16 x 16-word tiles (1 KB + halo) whose loads are single coalesced 4-byte words per thread.  BASELINE.json's north_star\n"
-          "# waives tensor cores for this path; its 'shared-memory/TMA-staged segment tiles' were evaluated for the fill (round-2 first\n"
-          "# version: 27-cell neighbourhoods staged per 3dr-cell in shared memory) and lost 9 x against the record-driven form, which\n"
-          "# needs no staging at all (DESIGN.md section 3.2).")
+          "# where the index allows).  calc_vert_volume's per-vertex working set is <= 3 KB (160 B per fan triangle + two 41-word masks):\n"
+          "# the phase kernels hand it through HBM scratch and each warp copies ITS vertex's 1 KB into shared memory with plain 16-byte\n"
+          "# loads -- a bulk copy per warp of 4 warps per CTA would need an mbarrier per warp for a kilobyte; the kernels are bound by\n"
+          "# instruction issue (80 % of the slots), not by that copy (2 % of the call at the measured HBM bandwidth).  The fill's\n"
+          "# k_resolve_blocks is the kernel that stages segment tiles in shared memory (27-cell neighbourhoods per 3dr-cell, ballot +\n"
+          "# popc compaction of the records that survive a plane-distance test -- a data-dependent gather, not a box copy); the flood\n"
+          "# works on 1 x 16 x 16-word tiles (1 KB + halo) whose loads are single coalesced 4-byte words per thread.  BASELINE.json's\n"
+          "# north_star waives tensor cores for this path (DESIGN.md sections 3.1, 3.2).")
 
 
 if __name__ == "__main__":
