@@ -25,6 +25,7 @@
 #define VV_GS 41      // gres*2+1 voxels per axis (crixus_d.cu:280)
 #define VV_LINES (VV_GS * VV_GS)
 #define VV_PLANE_F4 10
+#define VV_LSTRIDE 1688  // entries of the per-vertex line list (>= 41 * 41, 16-byte multiple)
 
 #define VVE_TRIMAX 1
 #define VVE_FAN 2
@@ -64,7 +65,8 @@ struct VVArgs {
   int4 *heads;               // per chunk slot: plane offset, fan size, closed, vertex
   float4 *planes;            // plane store of the chunk: 10 float4 per fan triangle
   int plane_cap;             // its capacity in fan triangles
-  unsigned long long *rdead; // per chunk slot: 2 x 41 words, bit l of word k = line (k, l) is dead / touched by a voronoi or edge plane
+  unsigned short *lines;     // per chunk slot: VV_LSTRIDE entries, the two lists of surviving lines (vv_rows)
+  unsigned short *lines_big; // the same per warp of the monolithic kernel's grid
   int force_axis;            // CX_VV_AXIS: one line direction for every vertex (-1: by the fan normal)
   const int *adj_start;      // vertex -> (segment, corner) adjacency (k_vv_adj_*): entries adj[adj_start[v] .. adj_start[v+1])
   const int *adj;            // entry = segment * 4 + corner
@@ -911,60 +913,74 @@ __device__ __forceinline__ bool vv_fan(const VVArgs &a, VVWarp &w, const int64_t
 }
 
 // Pass 1 of one vertex: rd[k] bit l = line (k, l) is removed whole by one triangle; rd[48 + k] bit l = some voronoi / edge plane
-// touches line (k, l) (96 words per warp, 2 x 41 used)
+// touches line (k, l) (96 words of shared memory per warp, 2 x 41 used); result: the two line lists in `lines` (global memory)
 template <int AX, class VVWarp>
 __device__ __forceinline__ void vv_rows(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
-                                        unsigned long long *rd)
+                                        unsigned long long *rd, unsigned short *lines, int &n0_out, int &n1_out)
 {
   for (int r = lane; r < 96; r += 32) rd[r] = 0ull;
   __syncwarp();
   if (closed) rows_dead<AX, false, VVWarp>(a, w, gzt, tris, pi, lane, rd);
   else rows_dead<AX, true, VVWarp>(a, w, gzt, tris, pi, lane, rd);
   __syncwarp();
+  // The surviving lines as two lists in ONE array of VV_LSTRIDE entries (line = row * 41 + l): the lines no voronoi / edge plane
+  // touches ascending from the front, the touched ones descending from the back.  Lane r expands rows r and r + 32: popcounts ->
+  // warp prefix -> one store per set bit (~3x fewer instructions than 53 ballot steps over the 1681 lines, which were a quarter
+  // of pass 2's instructions).
+  const int rb = lane + 32;
+  const uint64_t da = rd[lane], ta = rd[48 + lane];
+  const uint64_t db = rb < VV_GS ? rd[rb] : VV_ALL, tb = rb < VV_GS ? rd[48 + rb] : 0ull;
+  uint64_t u0a = ~da & ~ta & VV_ALL, u1a = ~da & ta & VV_ALL, u0b = ~db & ~tb & VV_ALL, u1b = ~db & tb & VV_ALL;
+  const int c0a = __popcll(u0a), c1a = __popcll(u1a), c0b = __popcll(u0b), c1b = __popcll(u1b);
+  // one scan for both lists and both row sets: four 11-bit counts cannot overflow 16-bit fields (<= 1681 in total)
+  const unsigned long long packed = (unsigned long long)c0a | ((unsigned long long)c0b << 16) | ((unsigned long long)c1a << 32) |
+                                    ((unsigned long long)c1b << 48);
+  unsigned long long incl = packed;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31), excl = incl - packed;
+  const int t0a = (int)(tot & 0xffffu), t0b = (int)((tot >> 16) & 0xffffu), t1a = (int)((tot >> 32) & 0xffffu), t1b = (int)(tot >> 48);
+  int o0a = (int)(excl & 0xffffu), o0b = t0a + (int)((excl >> 16) & 0xffffu);
+  int o1a = (int)((excl >> 32) & 0xffffu), o1b = t1a + (int)(excl >> 48);
+  auto expand = [&](uint64_t m, int row, int at, int step) {
+    unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int base = row * VV_GS;
+    while (lo) { lines[at] = (unsigned short)(base + __ffs(lo) - 1); at += step; lo &= lo - 1u; }
+    while (hi) { lines[at] = (unsigned short)(base + 31 + __ffs(hi)); at += step; hi &= hi - 1u; }
+  };
+  expand(u0a, lane, o0a, 1);
+  expand(u0b, rb, o0b, 1);
+  expand(u1a, lane, VV_LSTRIDE - 1 - o1a, -1);
+  expand(u1b, rb, VV_LSTRIDE - 1 - o1b, -1);
+  n0_out = t0a + t0b;
+  n1_out = t1a + t1b;
+  __syncwarp();
 }
 
-// Pass 2 of one vertex: the surviving lines are compacted through a small per-warp ring so that line_weight always runs with
-// 32 live lines; the weights are summed in integers and converted once.
+// Pass 2 of one vertex: the surviving lines come as two lists (vv_rows), 32 per step, one per lane; the weights are summed in
+// integers and converted once.  Lines that no voronoi / edge plane touches run line_weight without its first triangle loop: on a
+// wall-like fan with the lines along the normal those planes are parallel to the lines, remove whole lines (pass 1) and touch
+// the few that lie within eps of them, nothing else.
 template <int AX, bool WIDE, class VVWarp>
 __device__ __forceinline__ void vv_lines(const VVArgs &a, const VVWarp &w, const float *gzt, int tris, int closed, f3 pi, int lane,
-                                         const unsigned long long *rd, unsigned short *wq, unsigned long long *xres, int64_t i)
+                                         const unsigned short *lines, int n0, int n1, unsigned long long *xres, int64_t i)
 {
-  // Two rings: lines that no voronoi / edge plane touches (pass 1 knows) run line_weight without its first triangle loop.
-  // On a wall-like fan with the lines along the normal those planes are parallel to the lines: they remove whole lines (pass 1)
-  // and touch the few that lie within eps of them, nothing else.
   long long acc = 0;
-  int qn0 = 0, qh0 = 0, qn1 = 0, qh1 = 0;   // ring fill / head (warp-uniform); ring 0: untouched lines, ring 1: touched
-  for (int it = 0; it < (VV_LINES + 31) / 32; it++) {
-    const int line = it * 32 + lane;
-    const bool valid = line < VV_LINES;
-    const int k = valid ? line / VV_GS : 0, l = valid ? line - k * VV_GS : 0;
+  const int nb0 = (n0 + 31) >> 5, nb1 = (n1 + 31) >> 5;
+  for (int b = 0; b < nb0 + nb1; b++) {   // one call site of line_weight for both lists (it is the bulk of the kernel's code)
+    const bool ve = b >= nb0;
+    const int at = (ve ? b - nb0 : b) * 32 + lane;
+    const bool have = at < (ve ? n1 : n0);
+    VV_STAT(12, 1);
+    const int ln = have ? (int)lines[ve ? VV_LSTRIDE - 1 - at : at] : 0;
+    const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
     // gp = ((float)idx - 20.f) * gdr: identical expression for x, y and z, so one table serves all three
-    const bool dead = !valid || ((rd[k] >> l) & 1ull);
-    const bool tch = ((rd[48 + k] >> l) & 1ull) != 0ull;
-    const unsigned live0 = __ballot_sync(VV_FULLWARP, !dead && !tch), live1 = __ballot_sync(VV_FULLWARP, !dead && tch);
-    const unsigned below = (1u << lane) - 1u;
-    if (!dead && !tch) wq[(qh0 + qn0 + __popc(live0 & below)) & 63] = (unsigned short)line;
-    if (!dead && tch) wq[64 + ((qh1 + qn1 + __popc(live1 & below)) & 63)] = (unsigned short)line;
-    qn0 += __popc(live0);
-    qn1 += __popc(live1);
-    __syncwarp();
-    const bool last = it == (VV_LINES + 31) / 32 - 1;
-    for (;;) {   // one call site of line_weight for both rings (it is the bulk of the kernel's code)
-      const int lim = last ? 1 : 32;
-      const int rg = qn1 >= lim ? 1 : (qn0 >= lim ? 0 : -1);
-      if (rg < 0) break;
-      const int take = min(rg ? qn1 : qn0, 32), qh = rg ? qh1 : qh0;
-      const bool have = lane < take;
-      VV_STAT(6, take); VV_STAT(12, 1);
-      const int ln = have ? (int)wq[rg * 64 + ((qh + lane) & 63)] : 0;
-      const int kk = ln / VV_GS, ll = ln - kk * VV_GS;
-      const float h0 = gzt[kk], h1 = gzt[ll];
-      acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, rg != 0, xres, lane)
-                    : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, rg != 0, xres, lane);
-      if (rg) { qh1 = (qh1 + take) & 63; qn1 -= take; }
-      else { qh0 = (qh0 + take) & 63; qn0 -= take; }
-      __syncwarp();
-    }
+    const float h0 = gzt[kk], h1 = gzt[ll];
+    acc += closed ? line_weight<AX, false, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, ve, xres, lane)
+                  : line_weight<AX, true, WIDE, VVWarp>(a, w, gzt, tris, pi, h0, h1, have, ve, xres, lane);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1002,7 +1018,7 @@ __device__ __forceinline__ int64_t vv_owned_vertex(const VVArgs &a, int64_t idx)
 //   k_vv_rows<AX>     pass 1 (rows_dead)
 //   k_vv_lines<AX>    pass 2 (ring compaction + line_weight)
 // Fans with more than 16 triangles, and fans that find the chunk's plane store full, go to the monolithic k_vert_volume (list 3).
-struct VVHead { int off, tris, closed, vertex; };
+struct VVHead { int off, tris, closed, vertex, n0, n1; };
 
 // vertex -> (segment, corner) adjacency: count, exclusive scan (cx_exclusive_scan_i32), fill.  The order inside a vertex's list
 // is whatever the atomics give; vv_fan sorts the (<= trimax) entries it uses.
@@ -1076,7 +1092,7 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_FANS) k_vv_fans(const __g
       int cls = (az >= ax && az >= ay) ? 2 : (ay >= ax ? 1 : 0);
       if (force >= 0) cls = force;
       VVHead h;
-      h.off = off; h.tris = tris; h.closed = closed; h.vertex = (int)i;
+      h.off = off; h.tris = tris; h.closed = closed; h.vertex = (int)i; h.n0 = 0; h.n1 = 0;
       const int slot = (int)(idx - a.c_begin);
       a.heads[slot] = make_int4(h.off, h.tris, h.closed, h.vertex);
       a.list[(int64_t)cls * a.nown + atomicAdd(&a.ctl->count[cls], 1)] = slot;
@@ -1088,9 +1104,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_FANS) k_vv_fans(const __g
 template <class VVWarp>
 __device__ __forceinline__ VVHead vv_fetch(const VVArgs &a, VVWarp &w, int slot, int lane)
 {
-  const int4 hv = __ldg(a.heads + slot);
+  const int4 hv = a.heads[slot];
   VVHead h;
-  h.off = hv.x; h.tris = hv.y; h.closed = hv.z; h.vertex = hv.w;
+  h.off = hv.x; h.tris = hv.y; h.closed = hv.z & 1; h.vertex = hv.w; h.n0 = (hv.z >> 1) & 0x7ff; h.n1 = (hv.z >> 12) & 0x7ff;
   const float4 *src = a.planes + (int64_t)h.off * VV_PLANE_F4;
   float4 *dst = &w.plane[0][0];
   for (int q = lane; q < h.tris * VV_PLANE_F4; q += 32) dst[q] = src[q];
@@ -1120,9 +1136,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 6) k_vv_rows(const __grid_const
     __syncwarp();
     const VVHead h = vv_fetch(a, w, slot, lane);
     const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
-    vv_rows<AX>(a, w, gzt, h.tris, h.closed, pi, lane, rd);
-    unsigned long long *out = a.rdead + (int64_t)slot * (2 * VV_GS);
-    for (int r = lane; r < 2 * VV_GS; r += 32) out[r] = rd[r < VV_GS ? r : r - VV_GS + 48];
+    int n0, n1;
+    vv_rows<AX>(a, w, gzt, h.tris, h.closed, pi, lane, rd, a.lines + (int64_t)slot * VV_LSTRIDE, n0, n1);
+    if (lane == 0) a.heads[slot].z = h.closed | (n0 << 1) | (n1 << 12);     // counts <= 1681: 11 bits each
     __syncwarp();
   }
 }
@@ -1133,13 +1149,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_LINES) k_vv_lines(const _
   typedef VVWarpT<VV_TCAP_SMALL> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   __shared__ __align__(16) float gzt[64 + 256];
-  __shared__ unsigned short wqs[VV_WARPS][128];   // per-warp rings of surviving lines (2 x 64)
-  __shared__ unsigned long long rds[VV_WARPS][96]; // per-warp: bit l of rds[.][k] = line (k, l) is dead, of rds[.][48 + k]: touched
   __shared__ unsigned long long xress[VV_WARPS][128]; // per-warp: results of the out-of-line exact path (exact_tri_*)
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
-  unsigned short *wq = wqs[threadIdx.x >> 5];
-  unsigned long long *rd = rds[threadIdx.x >> 5];
   unsigned long long *xres = xress[threadIdx.x >> 5];
   vv_init_tables(a, gzt);
   const int *list = a.list + (int64_t)AX * a.nown;
@@ -1151,11 +1163,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, VV_LB_LINES) k_vv_lines(const _
     if ((int64_t)widx >= nlist) break;
     const int slot = list[widx];
     __syncwarp();
-    const unsigned long long *in = a.rdead + (int64_t)slot * (2 * VV_GS);
-    for (int r = lane; r < 2 * VV_GS; r += 32) rd[r < VV_GS ? r : r - VV_GS + 48] = in[r];
     const VVHead h = vv_fetch(a, w, slot, lane);
     const f3 pi = mk3(__ldg(&a.pos[h.vertex]));
-    vv_lines<AX, WIDE>(a, w, gzt, h.tris, h.closed, pi, lane, rd, wq, xres, h.vertex);
+    vv_lines<AX, WIDE>(a, w, gzt, h.tris, h.closed, pi, lane, a.lines + (int64_t)slot * VV_LSTRIDE, h.n0, h.n1, xres, h.vertex);
     __syncwarp();
   }
 }
@@ -1167,14 +1177,13 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_c
   typedef VVWarpT<TCAP> VVWarp;
   __shared__ VVWarp sm[VV_WARPS];
   __shared__ __align__(16) float gzt[64 + 256];
-  __shared__ unsigned short wqs[VV_WARPS][128];
   __shared__ unsigned long long rds[VV_WARPS][96];
   __shared__ unsigned long long xress[VV_WARPS][128];
   const int lane = threadIdx.x & 31;
   VVWarp &w = sm[threadIdx.x >> 5];
-  unsigned short *wq = wqs[threadIdx.x >> 5];
   unsigned long long *rd = rds[threadIdx.x >> 5];
   unsigned long long *xres = xress[threadIdx.x >> 5];
+  unsigned short *lines = a.lines_big + (int64_t)(blockIdx.x * VV_WARPS + (threadIdx.x >> 5)) * VV_LSTRIDE;   // this warp's line lists
   vv_init_tables(a, gzt);
   const int *list = a.list + 3 * a.nown;
   const int64_t nlist = a.ctl->count[3];     // complete: filled by the earlier launches
@@ -1190,8 +1199,9 @@ __global__ void __launch_bounds__(VV_WARPS * 32, 4) k_vert_volume(const __grid_c
     int closed;
     f3 av;
     if (!vv_fan<TCAP, CSR>(a, w, i, pi, tris, lane, closed, av)) continue;
-    vv_rows<AX>(a, w, gzt, tris, closed, pi, lane, rd);
-    vv_lines<AX, WIDE>(a, w, gzt, tris, closed, pi, lane, rd, wq, xres, i);
+    int n0, n1;
+    vv_rows<AX>(a, w, gzt, tris, closed, pi, lane, rd, lines, n0, n1);     // (global scratch of this warp; __syncwarp orders it)
+    vv_lines<AX, WIDE>(a, w, gzt, tris, closed, pi, lane, lines, n0, n1, xres, i);
     __syncwarp();
   }
 }
@@ -1284,19 +1294,20 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   // see plane_kill<WIDE>: below this dr several voxels of a cut line lie within eps of a plane as a rule
   const char *force_wide = getenv("CX_VV_WIDE");
   const bool wide = force_wide ? (force_wide[0] == '1') : (dr < 3.0e-3f);
-  // The owned vertices are processed in chunks whose scratch (heads, dead-line masks, plane store) stays within ~2 GB.  The plane
+  // The owned vertices are processed in chunks whose scratch (heads, line lists, plane store) stays within ~4 GB.  The plane
   // store holds 1.5 x the mean fan size per vertex (mean = 3 nbe / nvert: every segment sits in three fans); a chunk whose fans
   // are larger than that overflows into the monolithic kernel's list.
   const double mean_fan = nvert > 0 && nbe > 0 ? 3.0 * (double)nbe / (double)nvert : 6.0;
   const double tri_per_vertex = fmin(fmax(1.5 * mean_fan, 4.0), (double)VV_TCAP_SMALL);
-  const double bytes_per_vertex = sizeof(int4) + 2 * VV_GS * sizeof(unsigned long long) + tri_per_vertex * VV_PLANE_F4 * sizeof(float4);
+  const double bytes_per_vertex = sizeof(int4) + VV_LSTRIDE * sizeof(unsigned short) + tri_per_vertex * VV_PLANE_F4 * sizeof(float4);
   static const char *chunk_env = getenv("CX_VV_CHUNK");      // vertices per chunk (testing)
-  int64_t cmax_v = chunk_env ? atoll(chunk_env) : (int64_t)(2.0e9 / bytes_per_vertex);
+  int64_t cmax_v = chunk_env ? atoll(chunk_env) : (int64_t)(4.0e9 / bytes_per_vertex);
   if (cmax_v < 1) cmax_v = 1;
   const int64_t cv = a.nown < cmax_v ? a.nown : cmax_v;
   a.plane_cap = (int)fmin(tri_per_vertex * (double)cv + 64.0, 2.0e9);
+  if (const char *cap_env = getenv("CX_VV_PLANE_CAP")) a.plane_cap = atoi(cap_env) > 0 ? atoi(cap_env) : a.plane_cap;   // testing: overflow path
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned long long) * 2 * VV_GS * (size_t)cv),
+  const size_t ctl_bytes = 256, head_bytes = up(sizeof(int4) * (size_t)cv), rd_bytes = up(sizeof(unsigned short) * VV_LSTRIDE * ((size_t)cv + VV_WARPS * (size_t)ctx->num_sms)),
                plane_bytes = up(sizeof(float4) * VV_PLANE_F4 * (size_t)a.plane_cap), list_bytes = up(sizeof(int) * 4 * (size_t)a.nown);
   // CX_VV_SCAN=1: fans by scanning the 27 cells (the form without the adjacency; also taken when segment * 4 + corner overflows)
   const char *scan_env = getenv("CX_VV_SCAN");
@@ -1306,7 +1317,8 @@ static int vert_volume_impl(cx_ctx *ctx, const cx_params *p, const float *pos_d,
   CX_CUDA(ctx, cudaMallocAsync(&tmp, ctl_bytes + head_bytes + rd_bytes + plane_bytes + list_bytes + 2 * start_bytes + adj_bytes, ctx->stream));
   a.ctl = (VVCtl *)tmp;
   a.heads = (int4 *)(tmp + ctl_bytes);
-  a.rdead = (unsigned long long *)(tmp + ctl_bytes + head_bytes);
+  a.lines = (unsigned short *)(tmp + ctl_bytes + head_bytes);
+  a.lines_big = a.lines + (size_t)cv * VV_LSTRIDE;
   a.planes = (float4 *)(tmp + ctl_bytes + head_bytes + rd_bytes);
   a.list = (int *)(tmp + ctl_bytes + head_bytes + rd_bytes + plane_bytes);
   auto fail = [&](const char *what, cudaError_t e) { cudaFreeAsync(tmp, ctx->stream); return cx_fail(ctx, CX_CUDA_ERROR, what, e); };

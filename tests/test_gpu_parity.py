@@ -86,14 +86,14 @@ def test_special_boundary_stress_vs_oracle(name, oracle, cuda_backend):
         assert 0 < (o["sbid"] > 0).sum() < o["sbid"].size
 
 
-@pytest.mark.parametrize("axis", ["", "0", "1", "2", "chunk", "scan"])
+@pytest.mark.parametrize("axis", ["", "0", "1", "2", "chunk", "scan", "overflow"])
 @pytest.mark.parametrize("wide", ["0", "1"])
 def test_both_vert_volume_kernels(wide, axis):
     """calc_vert_volume has two line kernels (plane_kill<WIDE>, chosen from dr), each in three forms (voxel lines along x, y or
     z, chosen per vertex from its normal; CX_VV_AXIS forces one for all vertices): every one must be bit-exact on every kind of
     mesh: the fine-dr case (several voxels within eps of a plane), the commensurate case and an ordinary one.  "chunk": the
     owned vertices in chunks of 777 (the scratch of the split kernels is re-used from chunk to chunk); "scan": the fan
-    gather without the adjacency lists."""
+    gather without the adjacency lists; "overflow": a plane store so small that most fans take the monolithic kernel."""
     import os
     import subprocess
     import sys
@@ -101,6 +101,8 @@ def test_both_vert_volume_kernels(wide, axis):
     env = dict(os.environ, CX_VV_WIDE=wide)
     if axis == "chunk":
         env["CX_VV_CHUNK"] = "777"
+    elif axis == "overflow":
+        env["CX_VV_PLANE_CAP"] = "100"   # plane store of 100 fan triangles per chunk: most fans overflow into the monolithic kernel
     elif axis == "scan":
         env["CX_VV_SCAN"] = "1"       # fans by scanning the 27 cells instead of the vertex -> segment adjacency
     elif axis:
