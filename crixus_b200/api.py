@@ -112,6 +112,7 @@ def lib():
                                             C.POINTER(C.c_int32)]),
         "cx_fill_set_max_rounds": (C.c_int, [VP, C.c_int]),
         "cx_fill_unfinished": (C.c_int, [VP]),
+        "cx_fill_set_resolve_mode": (C.c_int, [VP, C.c_int]),
         "cx_fill_resolve_slab": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, I64, C.POINTER(VP), C.POINTER(I64)]),
         "cx_fill_resolve_part": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, C.c_int, C.c_int, C.POINTER(VP), C.POINTER(I64)]),
         "cx_fill_propagate": (C.c_int, [VP, P, VP, VP, VP, VP, I64, I64, VP, I64, C.POINTER(I64), C.POINTER(C.c_int32)]),
@@ -329,6 +330,10 @@ class Context:
 
     def fill_unfinished(self):
         return int(self.L.cx_fill_unfinished(self.h))
+
+    def fill_set_resolve_mode(self, mode):
+        """0 = record-driven directed tests at fine dr (default), 1 = the cell-driven kernel always"""
+        self._ck(self.L.cx_fill_set_resolve_mode(self.h, int(mode)))
 
     def fill_resolve_slab(self, p, fpos, norm, ep, pos, nbe, cnbe, cell_idx, k_begin, k_end):
         """-> torch int32 view (zero-copy) of the 6 blocked bit planes owned by the context"""

@@ -26,6 +26,7 @@ struct cx_ctx {
   void *fill_state = nullptr;
   int fill_max_rounds = 0;     // 0: cx_fill_geometry_slab runs until its slab is converged; n: at most ~n rounds per call
   int fill_unfinished = 0;     // the last slab call stopped with active tiles left
+  int fill_resolve_mode = 0;   // cx_fill_set_resolve_mode: 0 = by dr (record-driven kernels at fine dr), 1 = cell-driven kernel always
   // grow-only arenas of cx_preprocess_host: device working set and pinned host result buffers (cudaMalloc and
   // page-locking cost milliseconds per call; the arenas make repeated calls allocation-free)
   void *dev_arena = nullptr, *host_arena = nullptr;

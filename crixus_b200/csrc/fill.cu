@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "fill_enum.h"
 #include "dist.h"
 
 #define FT_Y 16
@@ -133,6 +134,9 @@ struct FillArgs {
   int dist_dead;                // eps >= dr_wall^2: the distance test `dist + eps < dr_wall^2` (crixus_d.cu:940) can never hold
   int nofilter;                 // debugging: no pre-filters, every pair inside rrej runs the reference's arithmetic
   float sph2;                   // (1.01 (1 + 3 eps))^2: hit points further than sqrt(sph2 * max(uu, vv)) from v0 miss the triangle
+  float lstep;                  // reach of one lattice step with the ray parameter's tolerance (fe_lstep)
+  int skip3;                    // k_resolve_blocks: records of flag 3 are resolved by k_resolve_cross / k_resolve_inplane
+  int32_t *nrest;               // k_seg_cells: number of wall records whose flag is not 3
 };
 
 // ---- the reference's directed test -------------------------------------------------------------------------------
@@ -140,7 +144,8 @@ struct FillArgs {
 // the same operations in the same order, so the results are bit-identical to evaluating them per (cell, segment) pair.
 //   R0 = (n, wf)   R1 = (v0, uu)   R2 = (v1, uv)   R3 = (v2, vv)   R4 = (segpos, D)   R5..R7 = (nr[0..2], -)
 // wf: 0 = no assumption, 1 = well-formed normal (plane-distance reject is valid), 2 = and well-conditioned edges (the
-// bounding-sphere pre-filter of the segment test is valid too)
+// bounding-sphere pre-filter of the segment test is valid too), 3 = and every lattice cell the segment can block is a
+// 27-neighbour of its 3dr-cell (set by k_seg_cells; the record-driven kernels take these).  R5.w = the segment's 3dr-cell.
 #define FREC 8
 
 // checkTriangleCollision, crixus_d.cu:753-799 (u, v, uu, uv, vv, D from the record)
@@ -213,24 +218,11 @@ __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict
     const f3 u = sub3(v1, v0), v = sub3(v2, v0);
     const float uu = dot3_r3(u, u), uv = dot3_r3(u, v), vv = dot3_r3(v, v);
     const float D = det_r2(uv, uv, uu, vv);
-    // well-formed: |n| = 1 within 1 %, n perpendicular to both edges within 2e-3 rad (evaluated in double).  Then for
-    // every point within the influence radius, |n.(s - v0)| is the distance to the triangle's plane within a few
-    // per cent, and no distance the reference can compute (plane, vertex or edge-line distance) is smaller.
-    const double nn = (double)n.x * n.x + (double)n.y * n.y + (double)n.z * n.z;
-    const double lu2 = (double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z;
-    const double lv2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;
-    const double lu = sqrt(lu2), lv = sqrt(lv2);
-    const double nu = (double)n.x * u.x + (double)n.y * u.y + (double)n.z * u.z;
-    const double nv = (double)n.x * v.x + (double)n.y * v.y + (double)n.z * v.z;
-    const double duv = (double)u.x * v.x + (double)u.y * v.y + (double)u.z * v.z;
-    const bool wf = nn > 0.98 && nn < 1.02 && lu > 0 && lv > 0 && fabs(nu) <= 2e-3 * lu && fabs(nv) <= 2e-3 * lv;
-    // well-conditioned: sin^2 of the angle between the edges >= 1e-2 and the float D agrees with it: then the barycentric
-    // coordinates (t1, t2) the reference computes describe the hit point within ~1e-4, and |t1 u + t2 v| <= (1 + 3 eps) max(|u|, |v|)
-    // for every accepted (t1, t2)
-    const double Dd = lu2 * lv2 - duv * duv;
-    const bool wc = wf && Dd >= 1e-2 * lu2 * lv2 && isfinite(D) && fabs((double)(-D) - Dd) <= 1e-3 * Dd;
+    // well-formed / well-conditioned: fe_classify (fill_enum.h, shared with the CPU check of the culling rules)
+    const float na[3] = {n.x, n.y, n.z}, ua[3] = {u.x, u.y, u.z}, va[3] = {v.x, v.y, v.z};
+    const int cls = fe_classify(na, ua, va, D);
     float4 *r = rec + i * FREC;
-    r[0] = make_float4(n.x, n.y, n.z, wc ? 2.f : (wf ? 1.f : 0.f));
+    r[0] = make_float4(n.x, n.y, n.z, (float)cls);
     r[1] = make_float4(v0.x, v0.y, v0.z, uu);
     r[2] = make_float4(v1.x, v1.y, v1.z, uv);
     r[3] = make_float4(v2.x, v2.y, v2.z, vv);
@@ -239,6 +231,52 @@ __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict
     r[6] = make_float4(nr[1].x, nr[1].y, nr[1].z, 0.f);
     r[7] = make_float4(nr[2].x, nr[2].y, nr[2].z, 0.f);
   }
+}
+
+// the 3dr-cell of every wall segment (the cell the BINNING put it in: cell_idx is the authority, not a recomputed barycentre)
+// into R5.w, and flag 2 -> 3 for the records the record-driven kernels may take (fe_rec_setup: safe).  A warp takes 32
+// consecutive 3dr-cells and strides their records together; *nrest counts the wall records that stay with the cell-driven
+// kernel.
+__global__ void __launch_bounds__(256) k_seg_cells(cx_params p, float lstep, const int32_t *__restrict__ cell_idx, int64_t nwall,
+                                                   float4 *__restrict__ rec, int32_t *nrest)
+{
+  const int64_t n = p.gridn[3];
+  const int lane = threadIdx.x & 31;
+  int rest = 0;
+  for (int64_t c0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; c0 < n; c0 += (int64_t)gridDim.x * blockDim.x) {
+    // the runs of 32 consecutive cells are one contiguous range of records: lane l holds the end of cell c0 + l's run, a
+    // record finds its cell by a 5-step search over the lanes
+    const int64_t cl = min(c0 + lane, n - 1);
+    const int me = __ldg(&cell_idx[cl + 1]);
+    const int64_t B = __ldg(&cell_idx[c0]), E = min((int64_t)__shfl_sync(0xffffffffu, me, 31), nwall);
+    for (int64_t i0 = B; i0 < E; i0 += 32) {
+      const int64_t i = i0 + lane;
+      int k = 0;   // number of lanes whose run ends at or before i = the lane of i's cell
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int e = __shfl_sync(0xffffffffu, me, k + step - 1);
+        if (e <= i) k += step;
+      }
+      if (i >= E) continue;
+      const int c = (int)min(c0 + k, n - 1);
+      int g[3];
+      fe_cell_coords(&p, c, g);
+      float4 *r = rec + i * FREC;
+      const float4 R0 = r[0];
+      r[5].w = __int_as_float(c);
+      bool take = false;
+      if (R0.w == 2.f) {
+        const float4 R1 = r[1], R2 = r[2], R3 = r[3];
+        const float na[3] = {R0.x, R0.y, R0.z}, a0[3] = {R1.x, R1.y, R1.z}, a1[3] = {R2.x, R2.y, R2.z}, a2[3] = {R3.x, R3.y, R3.z};
+        FeRec T;
+        fe_rec_setup(&p, lstep, na, a0, a1, a2, R1.w, R3.w, g, &T);
+        take = T.safe != 0;
+      }
+      if (take) r[0].w = 3.f;
+      else rest++;
+    }
+  }
+  if (rest) atomicAdd(nrest, rest);
 }
 
 // lattice position along one axis, crixus_d.cu:805-807 (R5)
@@ -452,12 +490,12 @@ __device__ __forceinline__ uint32_t cell_dirs(const FillArgs &A, int si, int sj,
 //   |a| <= |n_x| |dir| (1 + eps) up to rounding; the hit point s + r dir of an accepted (t1, t2) lies within rad of v0.
 // Only for well-formed triangles (R0.w != 0: finite, unit normal perpendicular to the edges) whose distance test is provably
 // false; everything else takes the reference's arithmetic unfiltered.
-__device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &W, int q, int si, int sj, int sk, uint32_t need)
+__device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, float4 R0, float4 R1, float rad, int64_t ridx, int si, int sj, int sk,
+                                               uint32_t need)
 {
   const cx_params &p = A.p;
   const float eps = p.eps;
   const f3 s = mk3(lat_pos(p, 0, si), lat_pos(p, 1, sj), lat_pos(p, 2, sk));
-  const float4 R0 = W.R0[q], R1 = W.R1[q];
   const f3 n = mk3(R0), v0 = mk3(R1);
   const f3 w0 = sub3(s, v0);
   const float a = -dot3_r3(n, w0);
@@ -471,7 +509,6 @@ __device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &
     cand = 0;
     uint32_t m = need;
     const float grow = 1.0001f * (1.0f + eps);
-    const float rad = W.rad[q];
     while (m) {
       const int d = __ffs(m) - 1;
       m &= m - 1;
@@ -488,7 +525,7 @@ __device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &
       }
       const float qn = b > 0.f ? a : -a;                            // r = qn / |b|
       if (qn > ab * grow || qn < -ab * eps * 1.0001f - 1e-37f) continue;   // r outside [-eps, 1+eps] for sure
-      if (R0.w == 2.f) {
+      if (R0.w >= 2.f) {
         // hit point P = s + r dir (r from a fast division: the 1 % margin of rad covers its error many times over)
         const float r = __fdividef(qn, ab);
         const float px = ax == 0 ? w0.x + r * dc : w0.x, py = ax == 1 ? w0.y + r * dc : w0.y, pz = ax == 2 ? w0.z + r * dc : w0.z;
@@ -498,7 +535,7 @@ __device__ __forceinline__ uint32_t pair_exact(const FillArgs &A, const RBWarp &
     }
     if (!cand) return 0;
   }
-  return pair_full(A, si, sj, sk, W.idx[q], cand);
+  return pair_full(A, si, sj, sk, ridx, cand);
 }
 
 // the lattice cells of one sub-block against the staged records.
@@ -523,7 +560,7 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
       const int si = S.i0 + (int)(xyz & 3u), sj = S.j0 + (int)((xyz >> 2) & 3u), sk = S.k0 + (int)(xyz >> 4);
       const uint32_t need = cell_dirs(A, si, sj, sk) & ~W.coll[cell];
       if (need) {
-        const uint32_t got = pair_exact(A, W, q, si, sj, sk, need);
+        const uint32_t got = pair_exact(A, W.R0[q], W.R1[q], W.rad[q], W.idx[q], si, sj, sk, need);
         if (got) atomicOr(&W.coll[cell], got);
       }
     }
@@ -557,7 +594,7 @@ __device__ __forceinline__ void sub_vs_staged(const FillArgs &A, RBWarp &W, cons
           if (aa * aa < lim_alive) c = true;                         // the distance test may hold: exact path
           else if (aa <= L || aa < eps2) {
             const float rr = W.rad[q] + L;
-            c = R0.w != 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;   // a lattice step from here can hit inside the triangle's sphere
+            c = R0.w < 2.f || wx * wx + wy * wy + wz * wz <= rr * rr;   // a lattice step from here can hit inside the triangle's sphere
             if (!c && aa < eps2)   // in the plane: while a direction parallel to the plane is open every record counts
               c = (need & ((fabsf(R0.x) * L < eps2 ? 3u : 0u) | (fabsf(R0.y) * L < eps2 ? 12u : 0u) | (fabsf(R0.z) * L < eps2 ? 48u : 0u))) != 0u;
           }
@@ -653,9 +690,9 @@ __global__ void __launch_bounds__(RB_WARPS * 32, FILL_LB) k_resolve_blocks(const
                 R0 = __ldg(r); R1 = __ldg(r + 1);
                 const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
                 const float hr = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
-                keep = !(R0.w != 0.f && fabsf(tc) - hr > A.rrej * 1.001f);
+                keep = !(R0.w != 0.f && fabsf(tc) - hr > A.rrej * 1.001f) && !(A.skip3 && R0.w == 3.f);
                 // an accepted (t1, t2) puts the hit point within (1 + 3 eps) max(|u|, |v|) of v0 (well-conditioned triangles), 1 % on top
-                if (keep && R0.w == 2.f) rad = radf * sqrtf(fmaxf(R1.w, __ldg(r + 3).w));
+                if (keep && R0.w >= 2.f) rad = radf * sqrtf(fmaxf(R1.w, __ldg(r + 3).w));
               }
               const unsigned bal = __ballot_sync(0xffffffffu, keep);
               if (!bal) continue;
@@ -707,6 +744,253 @@ __global__ void __launch_bounds__(256) k_block_list(cx_params p, const uint8_t *
     if ((threadIdx.x & 31) == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (mine && list) list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (int32_t)c;
+  }
+}
+
+// ---- record-driven resolution (fine dr: dead distance test; records of flag 3) ----------------------------------------------
+// With the distance test dead (eps >= dr_wall^2, crixus_d.cu:940 can never hold) a wall segment blocks a lattice cell in two ways
+// only (fill_enum.h): a lattice step CROSSES the triangle -- then the cell lies in the triangle's bounding box across the step and
+// within one step of it along the step: a handful of cells per segment, enumerated by the segment (k_resolve_cross) -- or the cell
+// lies IN THE PLANE of a triangle that is parallel to the step, whatever the triangle's extent, as far as the influence radius
+// reaches -- found per 3dr-cell from the segments of its 27 neighbours (k_resolve_inplane).  Both only produce candidates; the
+// reference's arithmetic (pair_exact / pair_full) decides.  tests/test_resolve_enum.py checks the enumeration against the oracle
+// on the CPU, tests/test_gpu_parity.py the blocked planes against the cell-driven kernel.
+__device__ __forceinline__ void block_dirs(const FillArgs &A, int si, int sj, int sk, uint32_t got)
+{
+  const int64_t wi = ((int64_t)sk * A.dimg[1] + sj) * A.wr + (si >> 5);
+  const uint32_t bit = 1u << (si & 31);
+#pragma unroll
+  for (int d = 0; d < 6; d++)
+    if (got >> d & 1) atomicOr(&A.B[d * A.nw + wi], bit);
+}
+
+#ifndef RX_LB
+#define RX_LB 4
+#endif
+// one lane per wall segment; the lanes of a warp walk their candidate boxes in lock-step (neighbouring segments of a wall have
+// congruent boxes)
+__global__ void __launch_bounds__(128, RX_LB) k_resolve_cross(const __grid_constant__ FillArgs A)
+{
+  const cx_params &p = A.p;
+  const int64_t nwall = A.nbe - A.cnbe;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // z-slab ownership: only cells of the planes [k_lo, k_hi) are written
+  const float zlo = lat_pos(p, 2, A.k_lo) - A.lstep, zhi = lat_pos(p, 2, A.k_hi - 1) + A.lstep;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nwall; base += nwarps * 32) {
+    const int64_t i = base + lane;
+    bool live = false;
+    FeRec T;
+    float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+    if (i < nwall) {
+      const float4 *r = A.rec + i * FREC;
+      R0 = __ldg(r);
+      if (R0.w == 3.f) {
+        R1 = __ldg(r + 1);
+        const float4 R2 = __ldg(r + 2), R3 = __ldg(r + 3);
+        int g[3];
+        fe_cell_coords(&p, __float_as_int(__ldg(r + 5).w), g);
+        const float na[3] = {R0.x, R0.y, R0.z}, a0[3] = {R1.x, R1.y, R1.z}, a1[3] = {R2.x, R2.y, R2.z}, a2[3] = {R3.x, R3.y, R3.z};
+        fe_rec_setup(&p, A.lstep, na, a0, a1, a2, R1.w, R3.w, g, &T);
+        live = !(T.bhi[2] < zlo || T.blo[2] > zhi);
+      }
+    }
+    if (!__any_sync(0xffffffffu, live)) continue;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      int lo0 = 0, hi0 = -1, lo1 = 0, hi1 = -1, lo2 = 0, hi2 = -1;
+      unsigned cnt = 0;
+      if (live && fe_axis_crossing(&p, A.lstep, &T, ax)) {
+        fe_axis_range(&p, &T, 0, ax == 0 ? A.lstep : 0.f, 0, A.dimg[0], &lo0, &hi0);
+        fe_axis_range(&p, &T, 1, ax == 1 ? A.lstep : 0.f, 0, A.dimg[1], &lo1, &hi1);
+        fe_axis_range(&p, &T, 2, ax == 2 ? A.lstep : 0.f, A.k_lo, A.k_hi, &lo2, &hi2);
+        if (lo0 <= hi0 && lo1 <= hi1 && lo2 <= hi2) {
+          const unsigned long long v = (unsigned long long)(hi0 - lo0 + 1) * (unsigned long long)(hi1 - lo1 + 1) * (unsigned long long)(hi2 - lo2 + 1);
+          cnt = v > 0x7fffffffull ? 0x7fffffffu : (unsigned)v;   // (flag 3: the box lies within the 27 neighbour cells)
+        }
+      }
+      const unsigned mx = __reduce_max_sync(0xffffffffu, cnt);
+      int ci = lo0, cj = lo1, ck = lo2;
+#pragma unroll 1
+      for (unsigned t = 0; t < mx; t++) {
+        if (t < cnt) {
+          bool cand = fe_cross_candidate(&p, A.lstep, &T, ax, ci, cj, ck) != 0;
+          if (cand && A.res_nparts > 1) {   // directed tests dealt to the ranks by 3dr-cell chunk (k_block_list)
+            const long long c3 = ((long long)lat_cell(p, 0, ci) * p.gridn[1] + lat_cell(p, 1, cj)) * p.gridn[2] + lat_cell(p, 2, ck);
+            cand = chunk_owner(c3 >> 5, A.res_nparts) == A.res_part;
+          }
+          if (cand) {
+            const uint32_t need = cell_dirs(A, ci, cj, ck) & (3u << (2 * ax));
+            if (need) {
+              const uint32_t got = pair_exact(A, R0, R1, T.rad, i, ci, cj, ck, need);
+              if (got) block_dirs(A, ci, cj, ck, got);
+            }
+          }
+          if (++ci > hi0) {
+            ci = lo0;
+            if (++cj > hi1) { cj = lo1; ++ck; }
+          }
+        }
+      }
+    }
+  }
+}
+
+// One warp per 3dr-cell of the work list (as k_resolve_blocks), sub-blocks of at most 4 x 4 x 4 lattice cells with the fixed
+// numbering q = x | y << 2 | z << 4.  Lanes = segments of the 27 neighbour cells, 32 at a time: a lane whose segment has an axis
+// parallel to its plane ("capable", fe_capable) and whose plane passes through the sub-block marks the cells within 2 eps of the
+// plane in a 64-bit mask; cells that still have an open direction along a capable axis are tested with the reference's
+// arithmetic (pair_full) -- one lane per distinct cell and round, each lane its own segment.  At a wall in a lattice plane the
+// first 32 segments block every in-plane cell and the rest of the neighbourhood costs the mask only.
+__global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_constant__ FillArgs A)
+{
+  __shared__ uint32_t sColl[RB_WARPS][64];
+  const int lane = threadIdx.x & 31;
+  const cx_params &p = A.p;
+  uint32_t *coll = sColl[threadIdx.x >> 5];
+  const float eps2 = 2.0f * p.eps;
+  const float reach2 = fe_infl_reach(&p, A.lstep) * fe_infl_reach(&p, A.lstep);   // beyond it the influence-radius test fails
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(A.count64, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= A.nblist) break;
+    const long long c = A.blist[item];
+    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((long long)p.gridn[2] * p.gridn[1]));
+    int bound = 0;
+    if (lane < 6) {
+      const int ax = lane >> 1, g = (ax == 0 ? gx : ax == 1 ? gy : gz) + (lane & 1);
+      bound = idx_lo(p, ax, g, A.dimg[ax]);
+    }
+    const int bi0 = __shfl_sync(0xffffffffu, bound, 0), bi1 = __shfl_sync(0xffffffffu, bound, 1);
+    const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
+    const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
+    if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
+    // the 27 neighbour cells as runs of records (see k_resolve_blocks)
+    int rb = 0, re = 0;
+    if (lane < 27) {
+      const int c9 = lane / 3, part = lane % 3;
+      const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
+      if (part == 0) {
+        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
+        const int64_t q0 = nb_cell(p, cx, cy, z0);
+        if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
+      } else {
+        const int zz = part == 1 ? gz - 1 : gz + 1;
+        if (zz < 0 || zz >= p.gridn[2]) {
+          const int64_t q0 = nb_cell(p, cx, cy, zz);
+          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
+        }
+      }
+    }
+    for (int k0 = bk0; k0 < bk1; k0 += 4)
+      for (int j0 = bj0; j0 < bj1; j0 += 4)
+        for (int i0 = bi0; i0 < bi1; i0 += 4) {
+          const int nx = min(4, bi1 - i0), ny = min(4, bj1 - j0), nz = min(4, bk1 - k0);
+          coll[lane] = 0u; coll[lane + 32] = 0u;
+          __syncwarp();
+          // this lane's two cells (q = lane, lane + 32) and the directions that exist for them
+          const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+          const uint32_t dmA = (lx < nx && ly < ny && lz < nz) ? cell_dirs(A, i0 + lx, j0 + ly, k0 + lz) : 0u;
+          const uint32_t dmB = (lx < nx && ly < ny && lz + 2 < nz) ? cell_dirs(A, i0 + lx, j0 + ly, k0 + lz + 2) : 0u;
+          unsigned long long openx, openy, openz;   // cells with an open direction along x / y / z
+          auto refresh = [&]() {
+            const uint32_t na = dmA & ~coll[lane], nb = dmB & ~coll[lane + 32];
+            openx = (unsigned long long)__ballot_sync(0xffffffffu, (na & 3u) != 0u) | ((unsigned long long)__ballot_sync(0xffffffffu, (nb & 3u) != 0u) << 32);
+            openy = (unsigned long long)__ballot_sync(0xffffffffu, (na & 12u) != 0u) | ((unsigned long long)__ballot_sync(0xffffffffu, (nb & 12u) != 0u) << 32);
+            openz = (unsigned long long)__ballot_sync(0xffffffffu, (na & 48u) != 0u) | ((unsigned long long)__ballot_sync(0xffffffffu, (nb & 48u) != 0u) << 32);
+          };
+          refresh();
+          // lattice positions of the sub-block, its centre and half extents (plane-through-the-block test)
+          float px[4], py[4], pz[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            px[t] = lat_pos(p, 0, i0 + min(t, nx - 1));
+            py[t] = lat_pos(p, 1, j0 + min(t, ny - 1));
+            pz[t] = lat_pos(p, 2, k0 + min(t, nz - 1));
+          }
+          const float bcx = 0.5f * (px[0] + px[3]), bcy = 0.5f * (py[0] + py[3]), bcz = 0.5f * (pz[0] + pz[3]);
+          const float bhx = 0.5f * (px[3] - px[0]), bhy = 0.5f * (py[3] - py[0]), bhz = 0.5f * (pz[3] - pz[0]);
+          for (int rr = 0; rr < 27; rr++) {
+            const int run = rr < 15 ? rr + 12 : rr - 15;   // the 3dr-cell's own column first: its segments are the nearest
+            const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
+            for (int base = b; base < e; base += 32) {
+              if (!(openx | openy | openz)) break;   // every direction of every cell is blocked
+              const int i = base + lane;
+              bool live = false;
+              uint32_t cap = 0u;
+              float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+              if (i < e) {
+                const float4 *r = A.rec + (int64_t)i * FREC;
+                R0 = __ldg(r);
+                if (R0.w == 3.f) {
+                  const float na[3] = {R0.x, R0.y, R0.z};
+                  cap = fe_capable(&p, A.lstep, na);
+                  if (cap) {
+                    R1 = __ldg(r + 1);
+                    const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
+                    const float hr = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
+                    live = fabsf(tc) - hr < eps2 * 1.01f;
+                  }
+                }
+              }
+              if (!__any_sync(0xffffffffu, live)) continue;
+              unsigned long long cm = 0ull;   // cells of the sub-block within 2 eps of this lane's plane
+              if (live) {
+#pragma unroll
+                for (int z = 0; z < 4; z++) {
+                  if (z < nz) {
+                    const float wz = pz[z] - R1.z;
+                    const float tz = wz * R0.z, dz2 = wz * wz;
+#pragma unroll
+                    for (int y = 0; y < 4; y++) {
+                      if (y < ny) {
+                        const float wy = py[y] - R1.y;
+                        const float tyz = fmaf(wy, R0.y, tz), dyz2 = fmaf(wy, wy, dz2);
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                          const float wx = px[x] - R1.x;
+                          if (x < nx && fabsf(fmaf(wx, R0.x, tyz)) < eps2 && fmaf(wx, wx, dyz2) <= reach2) cm |= 1ull << (x | (y << 2) | (z << 4));
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+              for (;;) {
+                const unsigned long long cand =
+                    live ? (cm & (((cap & 3u) ? openx : 0ull) | ((cap & 12u) ? openy : 0ull) | ((cap & 48u) ? openz : 0ull))) : 0ull;
+                if (!__any_sync(0xffffffffu, cand != 0ull)) break;
+                int q = 64 + lane;
+                if (cand) {   // spread the lanes over the set bits, so that a round tests as many distinct cells as possible
+                  unsigned long long tmp = cand;
+                  for (int k = (lane * __popcll(cand)) >> 5; k > 0; k--) tmp &= tmp - 1ull;
+                  q = __ffsll((long long)tmp) - 1;
+                }
+                const unsigned grp = __match_any_sync(0xffffffffu, q);
+                if (cand && (__ffs(grp) - 1) == lane) {   // one lane per cell
+                  cm &= ~(1ull << q);
+                  const int si = i0 + (q & 3), sj = j0 + ((q >> 2) & 3), sk = k0 + (q >> 4);
+                  const uint32_t need = cell_dirs(A, si, sj, sk) & ~coll[q] & cap;
+                  if (need) {
+                    const uint32_t got = pair_full(A, si, sj, sk, i, need);
+                    if (got) atomicOr(&coll[q], got);
+                  }
+                }
+                __syncwarp();
+                refresh();
+              }
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int q = lane + 32 * h;
+            const uint32_t cl = coll[q] & (h ? dmB : dmA);
+            if (cl) block_dirs(A, i0 + (q & 3), j0 + ((q >> 2) & 3), k0 + (q >> 4), cl);
+          }
+          __syncwarp();
+        }
   }
 }
 
@@ -1031,9 +1315,14 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     const float f = 1.01f * (1.0f + 3.0f * p->eps);
     A->sph2 = f * f;
   }
+  A->lstep = fe_lstep(p, A->dimg);
+  A->nrest = s->count + 6;
   if (fresh) {
     k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec);
     CX_LAUNCH_CHECK(ctx, "k_seg_prep");
+    CX_CUDA(ctx, cudaMemsetAsync(A->nrest, 0, sizeof(int32_t) * 2, st));
+    k_seg_cells<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, A->lstep, cell_idx_d, nbe - cnbe, s->rec, A->nrest);
+    CX_LAUNCH_CHECK(ctx, "k_seg_cells");
     if (cnbe > 0) {
       k_fs_desc<<<cx_blocks(cnbe, 128), 128, 0, st>>>(*A, s->fs);
       CX_LAUNCH_CHECK(ctx, "k_fs_desc");
@@ -1053,14 +1342,16 @@ static int fill_resolve(cx_ctx *ctx, FillArgs *A, FillState *s)
   // work list: count, (grow the buffer,) fill -- the order of the entries is irrelevant (results are OR-ed bits)
   const int64_t ncell = A->p.gridn[3];
   const int lgrid = cx_blocks(ncell, 256, ctx->num_sms * 16);
+  int64_t nrest = 0;   // wall records the record-driven kernels do not take
   for (int pass = 0; pass < 2; pass++) {
     CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
     k_block_list<<<lgrid, 256, 0, st>>>(A->p, A->nbflag, A->res_nparts, A->res_part, pass ? s->blist : nullptr, A->count64);
     CX_LAUNCH_CHECK(ctx, "k_block_list");
     if (pass == 0) {
-      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));   // + *nrest
       CX_CUDA(ctx, cudaStreamSynchronize(st));
       A->nblist = ctx->h_mail[30];
+      nrest = (int64_t)(ctx->h_mail[31] & 0xffffffffll);
       if (A->nblist > s->cap_blist) {
         cudaFree(s->blist); s->blist = nullptr; s->cap_blist = 0;
         const int64_t want = A->nblist + A->nblist / 8 + 1024;
@@ -1071,7 +1362,34 @@ static int fill_resolve(cx_ctx *ctx, FillArgs *A, FillState *s)
       if (A->nblist == 0) break;
     }
   }
-  if (A->nblist > 0) {
+  // fine dr (dead distance test): the segments enumerate the few cells they can block, the in-plane rule is resolved per 3dr-cell
+  // from plane masks; what they do not take (records that are not well-conditioned, or large against the 3dr-cells) stays with
+  // the cell-driven kernel.  cx_fill_set_resolve_mode(ctx, 1) / CX_FILL_RESOLVE=blocks: the cell-driven kernel for everything.
+  static const bool env_blocks = getenv("CX_FILL_RESOLVE") != nullptr && !strcmp(getenv("CX_FILL_RESOLVE"), "blocks");
+  const int64_t nwall = A->nbe - A->cnbe;
+  const bool rec_driven = A->dist_dead && !A->nofilter && !env_blocks && ctx->fill_resolve_mode != 1 && nwall > 0;
+  if (rec_driven) {
+    static int cross_bpm = 0, inplane_bpm = 0;
+    if (!cross_bpm) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cross_bpm, k_resolve_cross, 128, 0) != cudaSuccess || cross_bpm < 1) cross_bpm = 4;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inplane_bpm, k_resolve_inplane, RB_WARPS * 32, 0) != cudaSuccess || inplane_bpm < 1)
+        inplane_bpm = 2;
+    }
+    k_resolve_cross<<<cx_blocks(nwall, 128, (int64_t)ctx->num_sms * cross_bpm * 4), 128, 0, st>>>(*A);
+    CX_LAUNCH_CHECK(ctx, "k_resolve_cross");
+    if (A->nblist > 0) {
+      CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+      k_resolve_inplane<<<ctx->num_sms * inplane_bpm, RB_WARPS * 32, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_resolve_inplane");
+    }
+    if (A->nblist > 0 && nrest > 0) {
+      A->skip3 = 1;
+      CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
+      k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
+      CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
+      A->skip3 = 0;
+    }
+  } else if (A->nblist > 0) {
     CX_CUDA(ctx, cudaMemsetAsync(A->count64, 0, sizeof(unsigned long long), st));
     k_resolve_blocks<<<ctx->num_sms * 2, RB_WARPS * 32, 0, st>>>(*A);
     CX_LAUNCH_CHECK(ctx, "k_resolve_blocks");
@@ -1292,6 +1610,12 @@ extern "C" int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds)
   return CX_OK;
 }
 extern "C" int cx_fill_unfinished(cx_ctx *ctx) { return ctx ? ctx->fill_unfinished : 0; }
+extern "C" int cx_fill_set_resolve_mode(cx_ctx *ctx, int mode)
+{
+  if (!ctx || mode < 0 || mode > 1) return CX_WRONG_INPUT;
+  ctx->fill_resolve_mode = mode;
+  return CX_OK;
+}
 extern "C" int cx_dist_set_fill_mode(cx_ctx *ctx, int mode)
 {
   if (!ctx || mode < 0 || mode > 2) return CX_WRONG_INPUT;

@@ -137,6 +137,10 @@ int cx_fill_geometry_slab(cx_ctx *ctx, const cx_params *p, uint32_t *fpos_d, con
  * whether the last call stopped at the bound with active tiles left (the caller must then call again). */
 int cx_fill_set_max_rounds(cx_ctx *ctx, int max_rounds);
 int cx_fill_unfinished(cx_ctx *ctx);
+/* how the directed tests of the geometry fill (checkCollision, crixus_d.cu:801-963) are resolved: 0 (default) = by dr -- at fine
+ * dr, where eps >= dr_wall^2 kills the distance test (crixus_d.cu:940), the segments enumerate the cells they can block
+ * (record-driven kernels); 1 = always the cell-driven kernel.  Same bits either way (tests/test_gpu_parity.py). */
+int cx_fill_set_resolve_mode(cx_ctx *ctx, int mode);
 
 /* Multi-GPU: the directed tests (pure functions of the geometry) are resolved for planes [k_begin, k_end) only;
  * *blocked_d points to the 6 "blocked" bit planes (*blocked_words uint32, zero outside this rank's share) which the caller

@@ -1,0 +1,117 @@
+"""CPU check of the culling rules of the record-driven fill resolve (crixus_b200/csrc/fill_enum.h -- the header fill.cu compiles
+for the device) against the oracle's restatement of checkCollision (/root/reference/src/crixus_d.cu:753-857): on seeded scenes
+with a dead distance test (eps >= dr_wall^2, the regime the record-driven kernels run in) every (lattice cell, direction,
+segment) triple the reference's arithmetic blocks must be among the enumerated candidates.  tests/resolve_enum_check.c does the
+record-by-record comparison; the GPU tests compare the blocked planes the kernels produce with the cell-driven kernel and the
+oracle (tests/test_gpu_parity.py::test_resolve_paths_agree)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from crixus_b200 import meshgen as mg
+from oracle import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out = os.path.join(HERE, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libresolve_enum.so")
+    srcs = [os.path.join(HERE, "resolve_enum_check.c"), os.path.join(HERE, "..", "crixus_b200", "csrc", "fill_enum.h"),
+            os.path.join(HERE, "..", "oracle", "crixus_oracle.c")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["gcc", "-std=c11", "-O2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall",
+                               "-Wno-unused-function", srcs[0], "-o", so, "-lm"])
+    L = C.CDLL(so)
+    L.rec_enum_check.restype = C.c_int64
+    L.rec_enum_check.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def _rot(ax, ang):
+    c, s = np.cos(ang), np.sin(ang)
+    m = np.eye(3)
+    a, b = [(1, 2), (2, 0), (0, 1)][ax]
+    m[a, a] = c; m[a, b] = -s; m[b, a] = s; m[b, b] = c
+    return m
+
+
+def _scene(name):
+    """-> case dict with a geometry fill whose dr_wall makes the distance test dead"""
+    if name == "cube":               # walls in lattice planes: the "ray in plane" rule on every wall cell
+        c = cases.case("cube_h05")
+    elif name == "cube_jitter":      # generic planes
+        c = cases.case("cube_jitter")
+    elif name == "sphere_tank":      # curved, oblique facets
+        c = cases.case("sphere_tank")
+    elif name == "channel":          # periodic grid (wrapped neighbour cells)
+        c = cases.case("channel")
+    elif name == "cube_rot":         # a box rotated out of every lattice direction, its walls a hair off the axes for one of them
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.08, inward=True)
+        R = _rot(2, 0.31) @ _rot(0, 2e-6) @ _rot(1, 0.17)
+        v = (v.astype(np.float64) @ R.T).astype(np.float32)
+        n = mg.geometric_normals(v, t)
+        n[(n * (v[t].mean(1) - v.mean(0))).sum(1) > 0] *= -1
+        c = dict(cases.case("cube"), tris=np.ascontiguousarray(v[t]), normals=np.ascontiguousarray(n), dr=np.float32(0.07))
+        c["fills"] = [("geometry", tuple(float(x) for x in v.mean(0)), 0.07)]
+    elif name == "cube_tilt":        # walls within eps of the lattice planes but not in them (|b| around eps)
+        v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+        R = _rot(0, 1.5e-4) @ _rot(1, -0.9e-4)
+        v = (v.astype(np.float64) @ R.T).astype(np.float32)
+        n = mg.geometric_normals(v, t)
+        n[(n * (v[t].mean(1) - v.mean(0))).sum(1) > 0] *= -1
+        c = dict(cases.case("cube"), tris=np.ascontiguousarray(v[t]), normals=np.ascontiguousarray(n), dr=np.float32(0.08))
+    elif name == "slivers":          # triangles near the well-conditioned threshold, large against dr, random orientations
+        rng = np.random.default_rng(11)
+        tr = []
+        for _ in range(400):
+            o = rng.uniform(0.2, 0.8, 3)
+            a = rng.normal(size=3); a /= np.linalg.norm(a)
+            b = np.cross(a, rng.normal(size=3)); b /= np.linalg.norm(b)
+            la, lb = rng.uniform(0.02, 0.25, 2)
+            ang = rng.choice([0.11, 0.2, 0.7, 1.4, 2.9])    # sin^2 = 0.012 ... 1
+            tr.append([o, o + la * a, o + lb * (np.cos(ang) * a + np.sin(ang) * b)])
+        tr = np.array(tr, dtype=np.float32)
+        box_v, box_t, box_n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+        n = mg.geometric_normals(tr.reshape(-1, 3), np.arange(3 * len(tr), dtype=np.int32).reshape(-1, 3))
+        c = dict(cases.case("cube"), tris=np.ascontiguousarray(np.concatenate([box_v[box_t], tr])),
+                 normals=np.ascontiguousarray(np.concatenate([box_n, n])), dr=np.float32(0.05))
+    elif name == "tank_mm":          # eps = 0.2 as a relative tolerance of the segment test
+        c = cases.case("tank_mm")
+        c["fshape"] = None
+    else:
+        raise KeyError(name)
+    c = dict(c)
+    ext = float((c["tris"].reshape(-1, 3).max(0) - c["tris"].reshape(-1, 3).min(0)).max())
+    drw = 0.9 * np.sqrt(1e-5 * ext)
+    fills = []
+    for f in c["fills"]:
+        fills.append(("geometry", f[1], float(drw)) if f[0] == "geometry" else f)
+    c["fills"] = fills
+    return c
+
+
+@pytest.mark.parametrize("name", ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "tank_mm"])
+def test_candidates_cover_reference(lib, name):
+    c = _scene(name)
+    B = orc.Oracle()
+    o = cases.run(B, c, stages=("fill",))
+    p = o["params_fill"]
+    assert p.eps >= p.dr_wall * p.dr_wall
+    nwall = int(o["fnbe"] - o["cnbe"])
+    out = np.zeros(8, dtype=np.int64)
+    pos, norm, ep, ci = (np.ascontiguousarray(o[k]) for k in ("fposa", "fnorm", "fep", "cell_idx"))
+    rc = lib.rec_enum_check(C.byref(p), pos.ctypes.data, norm.ctypes.data, ep.ctypes.data, nwall, ci.ctypes.data, out.ctypes.data, 1)
+    assert rc == 0
+    blocked, missed, ncross, ninpl, nelig, nrec, nunsafe, looked = (int(x) for x in out)
+    print("%s: %d records (%d eligible, %d not safe), reference blocks %d triples of %d looked at; candidates: %d crossing, %d in-plane"
+          % (name, nrec, nelig, nunsafe, blocked, looked, ncross, ninpl))
+    assert nrec == nwall
+    assert blocked > 0 and nelig > 0
+    assert missed == 0
