@@ -136,7 +136,9 @@ struct FillArgs {
   float sph2;                   // (1.01 (1 + 3 eps))^2: hit points further than sqrt(sph2 * max(uu, vv)) from v0 miss the triangle
   float lstep;                  // reach of one lattice step with the ray parameter's tolerance (fe_lstep)
   int skip3;                    // k_resolve_blocks: records of flag 3 are resolved by k_resolve_cross / k_resolve_inplane
-  int32_t *nrest;               // k_seg_cells: number of wall records whose flag is not 3
+  int32_t *nrest;               // k_seg_prep: number of wall records whose flag is not 3
+  const float4 *plane;          // per wall segment (n, n.(v0 - fcmin)) if it can take part in the in-plane rule, (0, 0, 0, inf) otherwise
+  const int32_t *cellid;        // per wall segment: its 3dr-cell (k_seg_cells)
 };
 
 // ---- the reference's directed test -------------------------------------------------------------------------------
@@ -195,8 +197,10 @@ __device__ __forceinline__ float tri_dist2(const FillArgs &A, f3 s, f3 n, f3 v0,
 
 // one thread per segment: the triangle-only parts of crixus_d.cu:859-896 (segpos, edge normals nr) and :755-783 (uu, uv,
 // vv, D), plus the flags that license the pre-filters of the resolve kernels.
-__global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict__ rec)
+__global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict__ rec, float4 *__restrict__ plane)
 {
+  const int64_t nwall = A.nbe - A.cnbe;
+  int rest = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < A.nbe; i += (int64_t)gridDim.x * blockDim.x) {
     const f3 n = mk3(__ldg(&A.norm[i]));
     const int4 E = __ldg(&A.ep[i]);
@@ -220,32 +224,48 @@ __global__ void __launch_bounds__(256) k_seg_prep(FillArgs A, float4 *__restrict
     const float D = det_r2(uv, uv, uu, vv);
     // well-formed / well-conditioned: fe_classify (fill_enum.h, shared with the CPU check of the culling rules)
     const float na[3] = {n.x, n.y, n.z}, ua[3] = {u.x, u.y, u.z}, va[3] = {v.x, v.y, v.z};
-    const int cls = fe_classify(na, ua, va, D);
+    int cls = fe_classify(na, ua, va, D);
+    // wall segments: flag 3 if every lattice cell the segment can block is a 27-neighbour of its 3dr-cell (fe_rec_setup: safe) --
+    // the record-driven kernels take these; the plane (n, n.v0) of those that have an axis parallel to it (in-plane rule)
+    int cell = 0;
+    if (i < nwall) {
+      cell = __ldg(&A.cellid[i]);
+      float4 pl = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+      if (cls == 2) {
+        int g[3];
+        fe_cell_coords(&A.p, cell, g);
+        const float a0[3] = {v0.x, v0.y, v0.z}, a1[3] = {v1.x, v1.y, v1.z}, a2[3] = {v2.x, v2.y, v2.z};
+        FeRec T;
+        fe_rec_setup(&A.p, A.lstep, na, a0, a1, a2, uu, vv, g, &T);
+        if (T.safe) {
+          cls = 3;
+          if (fe_capable(&A.p, A.lstep, na)) pl = make_float4(n.x, n.y, n.z, fe_plane_offset(&A.p, na, a0));
+        }
+      }
+      plane[i] = pl;
+      if (cls != 3) rest++;
+    }
     float4 *r = rec + i * FREC;
     r[0] = make_float4(n.x, n.y, n.z, (float)cls);
     r[1] = make_float4(v0.x, v0.y, v0.z, uu);
     r[2] = make_float4(v1.x, v1.y, v1.z, uv);
     r[3] = make_float4(v2.x, v2.y, v2.z, vv);
     r[4] = make_float4(segpos.x, segpos.y, segpos.z, D);
-    r[5] = make_float4(nr[0].x, nr[0].y, nr[0].z, 0.f);
+    r[5] = make_float4(nr[0].x, nr[0].y, nr[0].z, __int_as_float(cell));
     r[6] = make_float4(nr[1].x, nr[1].y, nr[1].z, 0.f);
     r[7] = make_float4(nr[2].x, nr[2].y, nr[2].z, 0.f);
   }
+  rest = __reduce_add_sync(0xffffffffu, rest);
+  if ((threadIdx.x & 31) == 0 && rest) atomicAdd(A.nrest, rest);
 }
 
-// the 3dr-cell of every wall segment (the cell the BINNING put it in: cell_idx is the authority, not a recomputed barycentre)
-// into R5.w, and flag 2 -> 3 for the records the record-driven kernels may take (fe_rec_setup: safe).  A warp takes 32
-// consecutive 3dr-cells and strides their records together; *nrest counts the wall records that stay with the cell-driven
-// kernel.
-__global__ void __launch_bounds__(256) k_seg_cells(cx_params p, float lstep, const int32_t *__restrict__ cell_idx, int64_t nwall,
-                                                   float4 *__restrict__ rec, int32_t *nrest)
+// the 3dr-cell of every wall segment (the cell the BINNING put it in: cell_idx is the authority, not a recomputed barycentre).
+// A warp takes 32 consecutive 3dr-cells: their runs are one contiguous range of records, lane l holds the end of cell c0 + l's
+// run and a record finds its cell by a 5-step search over the lanes.
+__global__ void __launch_bounds__(256) k_seg_cells(int64_t n, const int32_t *__restrict__ cell_idx, int64_t nwall, int32_t *__restrict__ cellid)
 {
-  const int64_t n = p.gridn[3];
   const int lane = threadIdx.x & 31;
-  int rest = 0;
   for (int64_t c0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; c0 < n; c0 += (int64_t)gridDim.x * blockDim.x) {
-    // the runs of 32 consecutive cells are one contiguous range of records: lane l holds the end of cell c0 + l's run, a
-    // record finds its cell by a 5-step search over the lanes
     const int64_t cl = min(c0 + lane, n - 1);
     const int me = __ldg(&cell_idx[cl + 1]);
     const int64_t B = __ldg(&cell_idx[c0]), E = min((int64_t)__shfl_sync(0xffffffffu, me, 31), nwall);
@@ -257,26 +277,9 @@ __global__ void __launch_bounds__(256) k_seg_cells(cx_params p, float lstep, con
         const int e = __shfl_sync(0xffffffffu, me, k + step - 1);
         if (e <= i) k += step;
       }
-      if (i >= E) continue;
-      const int c = (int)min(c0 + k, n - 1);
-      int g[3];
-      fe_cell_coords(&p, c, g);
-      float4 *r = rec + i * FREC;
-      const float4 R0 = r[0];
-      r[5].w = __int_as_float(c);
-      bool take = false;
-      if (R0.w == 2.f) {
-        const float4 R1 = r[1], R2 = r[2], R3 = r[3];
-        const float na[3] = {R0.x, R0.y, R0.z}, a0[3] = {R1.x, R1.y, R1.z}, a1[3] = {R2.x, R2.y, R2.z}, a2[3] = {R3.x, R3.y, R3.z};
-        FeRec T;
-        fe_rec_setup(&p, lstep, na, a0, a1, a2, R1.w, R3.w, g, &T);
-        take = T.safe != 0;
-      }
-      if (take) r[0].w = 3.f;
-      else rest++;
+      if (i < E) cellid[i] = (int)min(c0 + k, n - 1);
     }
   }
-  if (rest) atomicAdd(nrest, rest);
 }
 
 // lattice position along one axis, crixus_d.cu:805-807 (R5)
@@ -788,8 +791,7 @@ __global__ void __launch_bounds__(128, RX_LB) k_resolve_cross(const __grid_const
       if (R0.w == 3.f) {
         R1 = __ldg(r + 1);
         const float4 R2 = __ldg(r + 2), R3 = __ldg(r + 3);
-        int g[3];
-        fe_cell_coords(&p, __float_as_int(__ldg(r + 5).w), g);
+        const int g[3] = {1, 1, 1};   // flag 3 = "safe" was established by k_seg_prep: the cell is not needed again
         const float na[3] = {R0.x, R0.y, R0.z}, a0[3] = {R1.x, R1.y, R1.z}, a1[3] = {R2.x, R2.y, R2.z}, a2[3] = {R3.x, R3.y, R3.z};
         fe_rec_setup(&p, A.lstep, na, a0, a1, a2, R1.w, R3.w, g, &T);
         live = !(T.bhi[2] < zlo || T.blo[2] > zhi);
@@ -901,16 +903,19 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_
             openz = (unsigned long long)__ballot_sync(0xffffffffu, (na & 48u) != 0u) | ((unsigned long long)__ballot_sync(0xffffffffu, (nb & 48u) != 0u) << 32);
           };
           refresh();
-          // lattice positions of the sub-block, its centre and half extents (plane-through-the-block test)
+          // lattice positions of the sub-block relative to the lattice origin (fe_plane_offset), its centre and half extents
+          // (plane-through-the-block test)
           float px[4], py[4], pz[4];
 #pragma unroll
           for (int t = 0; t < 4; t++) {
-            px[t] = lat_pos(p, 0, i0 + min(t, nx - 1));
-            py[t] = lat_pos(p, 1, j0 + min(t, ny - 1));
-            pz[t] = lat_pos(p, 2, k0 + min(t, nz - 1));
+            px[t] = lat_pos(p, 0, i0 + min(t, nx - 1)) - p.fcmin[0];
+            py[t] = lat_pos(p, 1, j0 + min(t, ny - 1)) - p.fcmin[1];
+            pz[t] = lat_pos(p, 2, k0 + min(t, nz - 1)) - p.fcmin[2];
           }
           const float bcx = 0.5f * (px[0] + px[3]), bcy = 0.5f * (py[0] + py[3]), bcz = 0.5f * (pz[0] + pz[3]);
           const float bhx = 0.5f * (px[3] - px[0]), bhy = 0.5f * (py[3] - py[0]), bhz = 0.5f * (pz[3] - pz[0]);
+          float cnx = 0.f, cny = 0.f, cnz = 0.f, cd = 0.f;   // the remembered plane (warp-uniform)
+          bool cvalid = false;
           for (int rr = 0; rr < 27; rr++) {
             const int run = rr < 15 ? rr + 12 : rr - 15;   // the 3dr-cell's own column first: its segments are the nearest
             const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
@@ -919,38 +924,41 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_
               const int i = base + lane;
               bool live = false;
               uint32_t cap = 0u;
-              float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0;
+              float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
               if (i < e) {
-                const float4 *r = A.rec + (int64_t)i * FREC;
-                R0 = __ldg(r);
-                if (R0.w == 3.f) {
-                  const float na[3] = {R0.x, R0.y, R0.z};
+                P = __ldg(&A.plane[i]);
+                if (P.w < 3.0e38f && P.w > -3.0e38f) {   // (n, d) of a segment that takes part in the in-plane rule
+                  const float na[3] = {P.x, P.y, P.z};
                   cap = fe_capable(&p, A.lstep, na);
-                  if (cap) {
-                    R1 = __ldg(r + 1);
-                    const float tc = (bcx - R1.x) * R0.x + (bcy - R1.y) * R0.y + (bcz - R1.z) * R0.z;
-                    const float hr = fabsf(R0.x) * bhx + fabsf(R0.y) * bhy + fabsf(R0.z) * bhz;
-                    live = fabsf(tc) - hr < eps2 * 1.01f;
-                  }
+                  const float tc = fmaf(bcx, P.x, fmaf(bcy, P.y, bcz * P.z)) - P.w;
+                  const float hr = fabsf(P.x) * bhx + fabsf(P.y) * bhy + fabsf(P.z) * bhz;
+                  // a plane that is (within eps / 2) one whose in-plane cells are all blocked along its capable axes has none left
+                  const bool known = cvalid && P.x == cnx && P.y == cny && P.z == cnz && fabsf(P.w - cd) < 0.5f * p.eps;
+                  live = cap != 0u && !known && fabsf(tc) - hr < eps2 * 1.01f;
                 }
               }
               if (!__any_sync(0xffffffffu, live)) continue;
-              unsigned long long cm = 0ull;   // cells of the sub-block within 2 eps of this lane's plane
+              unsigned long long cm = 0ull, cmp = 0ull;   // cells within 2 eps of this lane's plane: cmp; and within the influence radius: cm
               if (live) {
+                float4 R1 = __ldg(A.rec + (int64_t)i * FREC + 1);   // v0, for the influence radius
+                R1.x -= p.fcmin[0]; R1.y -= p.fcmin[1]; R1.z -= p.fcmin[2];
 #pragma unroll
                 for (int z = 0; z < 4; z++) {
                   if (z < nz) {
                     const float wz = pz[z] - R1.z;
-                    const float tz = wz * R0.z, dz2 = wz * wz;
+                    const float tz = fmaf(pz[z], P.z, -P.w), dz2 = wz * wz;
 #pragma unroll
                     for (int y = 0; y < 4; y++) {
                       if (y < ny) {
                         const float wy = py[y] - R1.y;
-                        const float tyz = fmaf(wy, R0.y, tz), dyz2 = fmaf(wy, wy, dz2);
+                        const float tyz = fmaf(py[y], P.y, tz), dyz2 = fmaf(wy, wy, dz2);
 #pragma unroll
                         for (int x = 0; x < 4; x++) {
                           const float wx = px[x] - R1.x;
-                          if (x < nx && fabsf(fmaf(wx, R0.x, tyz)) < eps2 && fmaf(wx, wx, dyz2) <= reach2) cm |= 1ull << (x | (y << 2) | (z << 4));
+                          if (x < nx && fabsf(fmaf(px[x], P.x, tyz)) < eps2) {
+                            cmp |= 1ull << (x | (y << 2) | (z << 4));
+                            if (fmaf(wx, wx, dyz2) <= reach2) cm |= 1ull << (x | (y << 2) | (z << 4));
+                          }
                         }
                       }
                     }
@@ -979,6 +987,15 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_
                 }
                 __syncwarp();
                 refresh();
+              }
+              // remember one plane whose in-plane cells (all of them, also those beyond this segment's influence radius) are done
+              const bool done = live && (cmp & (((cap & 3u) ? openx : 0ull) | ((cap & 12u) ? openy : 0ull) | ((cap & 48u) ? openz : 0ull))) == 0ull;
+              const unsigned dn = __ballot_sync(0xffffffffu, done);
+              if (dn) {
+                const int src = __ffs(dn) - 1;
+                cnx = __shfl_sync(0xffffffffu, P.x, src); cny = __shfl_sync(0xffffffffu, P.y, src);
+                cnz = __shfl_sync(0xffffffffu, P.z, src); cd = __shfl_sync(0xffffffffu, P.w, src);
+                cvalid = true;
               }
             }
           }
@@ -1210,7 +1227,8 @@ struct FillState {
   uint32_t *halo = nullptr;              // two received boundary planes (multi-GPU)
   int32_t *blist = nullptr;              // work list of the up-front resolve
   int64_t cap_blist = 0;
-  float4 *rec = nullptr;
+  float4 *rec = nullptr, *plane = nullptr;
+  int32_t *cellid = nullptr;
   int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
   uint8_t *nbflag = nullptr, *act = nullptr;
   int32_t *list = nullptr, *count = nullptr;
@@ -1225,7 +1243,7 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist); cudaFree(s->plane); cudaFree(s->cellid);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -1272,8 +1290,11 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       s->cap_ncell = p->gridn[3];
     }
     if (nbe > s->cap_rec) {
-      cudaFree(s->rec); s->rec = nullptr; s->cap_rec = 0;
+      cudaFree(s->rec); cudaFree(s->plane); cudaFree(s->cellid);
+      s->rec = s->plane = nullptr; s->cellid = nullptr; s->cap_rec = 0;
       CX_CUDA(ctx, cudaMalloc(&s->rec, sizeof(float4) * FREC * (size_t)nbe));
+      CX_CUDA(ctx, cudaMalloc(&s->plane, sizeof(float4) * (size_t)nbe));
+      CX_CUDA(ctx, cudaMalloc(&s->cellid, sizeof(int32_t) * (size_t)nbe));
       s->cap_rec = nbe;
     }
     if (cnbe > s->cap_fs) {
@@ -1302,7 +1323,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->list = s->list; A->count = s->count;
   A->count64 = (unsigned long long *)(s->count + 4);
   A->changed = (unsigned long long *)(ctx->d_mail + 24);
-  A->rec = s->rec;
+  A->rec = s->rec; A->plane = s->plane; A->cellid = s->cellid;
   // plane-distance reject: a lattice step reaches (1 + eps) dr in barycentric units of the ray parameter, and the distance
   // test reaches dr_wall; 20 % on top for everything the stored normal and the float arithmetic can add
   A->rrej = (1.2f + 2.0f * p->eps) * fmaxf(p->dr_wall, p->dr);
@@ -1318,11 +1339,13 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
   A->lstep = fe_lstep(p, A->dimg);
   A->nrest = s->count + 6;
   if (fresh) {
-    k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec);
-    CX_LAUNCH_CHECK(ctx, "k_seg_prep");
+    if (nbe - cnbe > 0) {
+      k_seg_cells<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(p->gridn[3], cell_idx_d, nbe - cnbe, s->cellid);
+      CX_LAUNCH_CHECK(ctx, "k_seg_cells");
+    }
     CX_CUDA(ctx, cudaMemsetAsync(A->nrest, 0, sizeof(int32_t) * 2, st));
-    k_seg_cells<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, A->lstep, cell_idx_d, nbe - cnbe, s->rec, A->nrest);
-    CX_LAUNCH_CHECK(ctx, "k_seg_cells");
+    k_seg_prep<<<cx_blocks(nbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->rec, s->plane);
+    CX_LAUNCH_CHECK(ctx, "k_seg_prep");
     if (cnbe > 0) {
       k_fs_desc<<<cx_blocks(cnbe, 128), 128, 0, st>>>(*A, s->fs);
       CX_LAUNCH_CHECK(ctx, "k_fs_desc");

@@ -200,9 +200,18 @@ FE_FN int fe_cross_candidate(const cx_params *p, float lstep, const FeRec *T, in
  * step within 3 dr + |step| / 2 + dr_wall of v0), 2 % on top */
 FE_FN float fe_infl_reach(const cx_params *p, float lstep) { return 4.0f * lstep + 1.01f * p->dr_wall; }
 
-/* in-plane rule: can the cell lie in the triangle's plane, within the influence radius?  w = s - v0 (any rounding), conservative */
-FE_FN int fe_inplane_candidate(const cx_params *p, const float n[3], float wx, float wy, float wz, float infl_reach)
+/* in-plane rule.  Planes are kept relative to the lattice origin, (n, d = n.(v0 - fcmin)), and tested at q = lat_pos - fcmin
+ * (the rounded lattice position the reference uses, minus the origin): every term is then of the size of the domain, so that the
+ * rounding of n.q - d is ~1e-7 x extent = 0.01 eps whatever the offset of the geometry from the coordinate origin. */
+FE_FN float fe_plane_offset(const cx_params *p, const float n[3], const float v0[3])
 {
-  return fabsf(wx * n[0] + wy * n[1] + wz * n[2]) < 2.0f * p->eps && wx * wx + wy * wy + wz * wz <= infl_reach * infl_reach;
+  return n[0] * (v0[0] - p->fcmin[0]) + n[1] * (v0[1] - p->fcmin[1]) + n[2] * (v0[2] - p->fcmin[2]);
+}
+/* can the cell at q lie in the plane (n, d), within the influence radius of v0?  conservative */
+FE_FN int fe_inplane_candidate(const cx_params *p, const float n[3], float d, const float q[3], const float v0[3], float infl_reach)
+{
+  if (!(fabsf(q[0] * n[0] + q[1] * n[1] + q[2] * n[2] - d) < 2.0f * p->eps)) return 0;
+  const float wx = q[0] - (v0[0] - p->fcmin[0]), wy = q[1] - (v0[1] - p->fcmin[1]), wz = q[2] - (v0[2] - p->fcmin[2]);
+  return wx * wx + wy * wy + wz * wz <= infl_reach * infl_reach;
 }
 #endif

@@ -63,16 +63,18 @@ int64_t rec_enum_check(const orc_params *op, const float *pos, const float *norm
               }
       }
       const uint32_t cap = fe_capable(p, lstep, T.n);
-      if (cap)
+      if (cap) {
+        const float d = fe_plane_offset(p, T.n, v0);
         for (int sk = blo[2]; sk <= bhi[2]; sk++)
           for (int sj = blo[1]; sj <= bhi[1]; sj++)
             for (int si = blo[0]; si <= bhi[0]; si++) {
-              const float wx = fe_lat_pos(p, 0, si) - v0[0], wy = fe_lat_pos(p, 1, sj) - v0[1], wz = fe_lat_pos(p, 2, sk) - v0[2];
-              if (fe_inplane_candidate(p, T.n, wx, wy, wz, fe_infl_reach(p, lstep))) {
+              const float q[3] = {fe_lat_pos(p, 0, si) - p->fcmin[0], fe_lat_pos(p, 1, sj) - p->fcmin[1], fe_lat_pos(p, 2, sk) - p->fcmin[2]};
+              if (fe_inplane_candidate(p, T.n, d, q, v0, fe_infl_reach(p, lstep))) {
                 out[3]++;
                 mark[((int64_t)sk * dim[1] + sj) * dim[0] + si] |= (uint8_t)cap;
               }
             }
+      }
       /* ---- the reference's arithmetic for this record alone (crixus_d.cu:846-857 influence radius, :942 segment test) */
       for (int sk = blo[2]; sk <= bhi[2]; sk++)
         for (int sj = blo[1]; sj <= bhi[1]; sj++)

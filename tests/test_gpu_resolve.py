@@ -16,7 +16,7 @@ from test_resolve_enum import _scene
 
 pytestmark = pytest.mark.gpu
 
-SCENES = ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "tank_mm"]
+SCENES = ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "cube_far", "tank_mm"]
 
 
 def _inputs(B, o):

@@ -82,6 +82,10 @@ def _scene(name):
         n = mg.geometric_normals(tr.reshape(-1, 3), np.arange(3 * len(tr), dtype=np.int32).reshape(-1, 3))
         c = dict(cases.case("cube"), tris=np.ascontiguousarray(np.concatenate([box_v[box_t], tr])),
                  normals=np.ascontiguousarray(np.concatenate([box_n, n])), dr=np.float32(0.05))
+    elif name == "cube_far":         # far from the coordinate origin: one ulp of a coordinate is 25 x eps
+        c = cases.case("cube_h05")   # (walls "in" lattice planes that the rounded lattice positions straddle)
+        c["tris"] = np.ascontiguousarray(c["tris"] + np.array([3000.0, -2000.0, 1000.0], dtype=np.float32))
+        c["fills"] = [("geometry", (3000.5, -1999.5, 1000.5), 0.1)]
     elif name == "tank_mm":          # eps = 0.2 as a relative tolerance of the segment test
         c = cases.case("tank_mm")
         c["fshape"] = None
@@ -97,7 +101,7 @@ def _scene(name):
     return c
 
 
-@pytest.mark.parametrize("name", ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "tank_mm"])
+@pytest.mark.parametrize("name", ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "cube_far", "tank_mm"])
 def test_candidates_cover_reference(lib, name):
     c = _scene(name)
     B = orc.Oracle()
