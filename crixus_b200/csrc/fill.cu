@@ -768,7 +768,7 @@ __device__ __forceinline__ void block_dirs(const FillArgs &A, int si, int sj, in
 }
 
 #ifndef RX_LB
-#define RX_LB 4
+#define RX_LB 6
 #endif
 // one lane per wall segment; the lanes of a warp walk their candidate boxes in lock-step (neighbouring segments of a wall have
 // congruent boxes)
