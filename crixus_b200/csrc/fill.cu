@@ -282,6 +282,22 @@ __global__ void __launch_bounds__(256) k_seg_cells(int64_t n, const int32_t *__r
   }
 }
 
+// 3dr-cells whose segments do not all share one plane for the in-plane rule: bit 1 of nbflag.  A cell without the bit either
+// holds no segment that takes part (the plane of its first segment is not finite) or only segments with the normal of the first
+// one, bit for bit, and plane offsets within eps / 4 of its offset -- k_resolve_inplane then decides about the whole cell from
+// its first segment.
+__global__ void __launch_bounds__(256) k_cell_planes(FillArgs A, uint8_t *__restrict__ nbflag)
+{
+  const int64_t nwall = A.nbe - A.cnbe;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nwall; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 P = __ldg(&A.plane[i]);
+    if (!(P.w < 3.0e38f && P.w > -3.0e38f)) continue;
+    const int c = __ldg(&A.cellid[i]);
+    const float4 P0 = __ldg(&A.plane[__ldg(&A.cell_idx[c])]);
+    if (!(P0.x == P.x && P0.y == P.y && P0.z == P.z && fabsf(P0.w - P.w) < 0.25f * A.p.eps)) nbflag[c] = (uint8_t)(nbflag[c] | 2u);
+  }
+}
+
 // lattice position along one axis, crixus_d.cu:805-807 (R5)
 __device__ __forceinline__ float lat_pos(const cx_params &p, int a, int idx) { return ffma((float)idx, p.dr, p.fcmin[a]); }
 __device__ __forceinline__ int lat_cell(const cx_params &p, int a, int idx)
@@ -740,7 +756,7 @@ __global__ void __launch_bounds__(256) k_block_list(cx_params p, const uint8_t *
   const long long n = p.gridn[3];
   for (long long c0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31ll; c0 < n; c0 += (long long)gridDim.x * blockDim.x) {
     const long long c = c0 + (threadIdx.x & 31);
-    const bool mine = c < n && nbflag[c] && (nparts <= 1 || chunk_owner(c >> 5, nparts) == part);
+    const bool mine = c < n && (nbflag[c] & 1) && (nparts <= 1 || chunk_owner(c >> 5, nparts) == part);
     const unsigned bal = __ballot_sync(0xffffffffu, mine);
     if (!bal) continue;
     unsigned long long base = 0;
@@ -868,22 +884,25 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_
     const int bj0 = __shfl_sync(0xffffffffu, bound, 2), bj1 = __shfl_sync(0xffffffffu, bound, 3);
     const int bk0 = max(__shfl_sync(0xffffffffu, bound, 4), A.k_lo), bk1 = min(__shfl_sync(0xffffffffu, bound, 5), A.k_hi);
     if (bi1 <= bi0 || bj1 <= bj0 || bk1 <= bk0) continue;
-    // the 27 neighbour cells as runs of records (see k_resolve_blocks)
-    int rb = 0, re = 0;
+    // lane l < 27 holds neighbour cell l (periodic wrap as in the reference's lookup): its run of records, whether its segments
+    // share one plane (k_cell_planes) and the plane of its first segment
+    int rb = 0, re = 0, mixed = 0;
+    float4 P0 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
     if (lane < 27) {
-      const int c9 = lane / 3, part = lane % 3;
-      const int cx = gx + c9 / 3 - 1, cy = gy + c9 % 3 - 1;
-      if (part == 0) {
-        const int z0 = max(gz - 1, 0), z1 = min(gz + 1, p.gridn[2] - 1);
-        const int64_t q0 = nb_cell(p, cx, cy, z0);
-        if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + (z1 - z0) + 1]); }
-      } else {
-        const int zz = part == 1 ? gz - 1 : gz + 1;
-        if (zz < 0 || zz >= p.gridn[2]) {
-          const int64_t q0 = nb_cell(p, cx, cy, zz);
-          if (q0 >= 0) { rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]); }
+      const int64_t q0 = nb_cell(p, gx + lane / 9 - 1, gy + (lane / 3) % 3 - 1, gz + lane % 3 - 1);
+      if (q0 >= 0) {
+        rb = __ldg(&A.cell_idx[q0]); re = __ldg(&A.cell_idx[q0 + 1]);
+        if (re > rb) {
+          mixed = (__ldg(&A.nbflag[q0]) & 2) ? 1 : 0;
+          P0 = __ldg(&A.plane[rb]);
         }
       }
+    }
+    const bool p0fin = P0.w < 3.0e38f && P0.w > -3.0e38f;
+    uint32_t cap0 = 0u;
+    if (p0fin) {
+      const float na[3] = {P0.x, P0.y, P0.z};
+      cap0 = fe_capable(&p, A.lstep, na);
     }
     for (int k0 = bk0; k0 < bk1; k0 += 4)
       for (int j0 = bj0; j0 < bj1; j0 += 4)
@@ -916,10 +935,24 @@ __global__ void __launch_bounds__(RB_WARPS * 32) k_resolve_inplane(const __grid_
           const float bhx = 0.5f * (px[3] - px[0]), bhy = 0.5f * (py[3] - py[0]), bhz = 0.5f * (pz[3] - pz[0]);
           float cnx = 0.f, cny = 0.f, cnz = 0.f, cd = 0.f;   // the remembered plane (warp-uniform)
           bool cvalid = false;
-          for (int rr = 0; rr < 27; rr++) {
-            const int run = rr < 15 ? rr + 12 : rr - 15;   // the 3dr-cell's own column first: its segments are the nearest
-            const int b = __shfl_sync(0xffffffffu, rb, run), e = __shfl_sync(0xffffffffu, re, run);
+          // cells to look at: mixed ones, and single-plane cells whose plane passes through the sub-block
+          bool look = re > rb && mixed;
+          if (re > rb && !mixed && cap0) {
+            const float tc = fmaf(bcx, P0.x, fmaf(bcy, P0.y, bcz * P0.z)) - P0.w;
+            const float hr = fabsf(P0.x) * bhx + fabsf(P0.y) * bhy + fabsf(P0.z) * bhz;
+            look = fabsf(tc) - hr < eps2 * 1.01f;
+          }
+          unsigned todo = __ballot_sync(0xffffffffu, look);
+          while (todo) {
+            const int src = (todo >> 13 & 1u) ? 13 : __ffs(todo) - 1;   // the 3dr-cell itself first: its segments are the nearest
+            todo &= ~(1u << src);
+            const int b = __shfl_sync(0xffffffffu, rb, src), e = __shfl_sync(0xffffffffu, re, src);
+            const int single = !__shfl_sync(0xffffffffu, mixed, src);
+            const float snx = __shfl_sync(0xffffffffu, P0.x, src), sny = __shfl_sync(0xffffffffu, P0.y, src);
+            const float snz = __shfl_sync(0xffffffffu, P0.z, src), sd = __shfl_sync(0xffffffffu, P0.w, src);
             for (int base = b; base < e; base += 32) {
+              // a single-plane cell whose plane is (within eps / 2) the remembered finished one has nothing left to give
+              if (single && cvalid && snx == cnx && sny == cny && snz == cnz && fabsf(sd - cd) < 0.5f * p.eps) break;
               if (!(openx | openy | openz)) break;   // every direction of every cell is blocked
               const int i = base + lane;
               bool live = false;
@@ -1352,6 +1385,10 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     }
     k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
     CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
+    if (nbe - cnbe > 0) {
+      k_cell_planes<<<cx_blocks(nbe - cnbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->nbflag);
+      CX_LAUNCH_CHECK(ctx, "k_cell_planes");
+    }
   }
   *out = s;
   return CX_OK;
