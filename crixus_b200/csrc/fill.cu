@@ -358,17 +358,29 @@ __device__ __noinline__ uint32_t pair_full(const FillArgs &A, int si, int sj, in
 }
 
 // ---- preparation kernels ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cell3_flags(cx_params p, const int32_t *__restrict__ cell_idx, uint8_t *__restrict__ flag)
+// nbflag bit 0: the 27 neighbour cells of a 3dr-cell (periodic wrap / skip per axis as in the reference's lookup,
+// crixus_d.cu:327-347) hold a segment.  The neighbourhood is a product of three per-axis neighbourhoods: three passes, each an
+// OR over the cell and its two neighbours along one axis (axis 2 = z reads the runs themselves).
+__global__ void __launch_bounds__(256) k_cell3_flags(cx_params p, int axis, const int32_t *__restrict__ cell_idx, const uint8_t *__restrict__ in,
+                                                     uint8_t *__restrict__ out)
 {
   const int64_t n = p.gridn[3];
+  const int64_t stride = axis == 2 ? 1 : (axis == 1 ? p.gridn[2] : (int64_t)p.gridn[2] * p.gridn[1]);
+  const int gn = p.gridn[axis];
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
-    const int gz = (int)(c % p.gridn[2]), gy = (int)((c / p.gridn[2]) % p.gridn[1]), gx = (int)(c / ((int64_t)p.gridn[2] * p.gridn[1]));
+    const int g = (int)((c / stride) % gn);
     int any = 0;
-    for (int c27 = 0; c27 < 27; c27++) {
-      const int64_t q = nb_cell(p, gx + c27 / 9 - 1, gy + (c27 / 3) % 3 - 1, gz + c27 % 3 - 1);
-      if (q >= 0 && cell_idx[q + 1] > cell_idx[q]) { any = 1; break; }
+#pragma unroll
+    for (int d = -1; d <= 1; d++) {
+      int gg = g + d;
+      if (gg == -1 || gg == gn) {
+        if (!p.per[axis]) continue;
+        gg = gg == -1 ? gn - 1 : 0;
+      }
+      const int64_t q = c + (int64_t)(gg - g) * stride;
+      any |= axis == 2 ? (__ldg(&cell_idx[q + 1]) > __ldg(&cell_idx[q]) ? 1 : 0) : (in[q] & 1);
     }
-    flag[c] = (uint8_t)any;
+    out[c] = (uint8_t)any;
   }
 }
 
@@ -1263,7 +1275,7 @@ struct FillState {
   float4 *rec = nullptr, *plane = nullptr;
   int32_t *cellid = nullptr;
   int64_t cap_nw = 0, cap_ntiles = 0, cap_ncell = 0, cap_rec = 0, cap_fs = 0, cap_halo = 0;
-  uint8_t *nbflag = nullptr, *act = nullptr;
+  uint8_t *nbflag = nullptr, *nbtmp = nullptr, *act = nullptr;
   int32_t *list = nullptr, *count = nullptr;
   FsDesc *fs = nullptr;
   int64_t nw = 0, ntiles = 0;
@@ -1276,7 +1288,7 @@ void cx_fill_state_free(cx_ctx *ctx)
   FillState *s = (FillState *)ctx->fill_state;
   if (!s) return;
   cudaFree(s->F); cudaFree(s->B); cudaFree(s->nbflag); cudaFree(s->act); cudaFree(s->list);
-  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist); cudaFree(s->plane); cudaFree(s->cellid);
+  cudaFree(s->count); cudaFree(s->fs); cudaFree(s->rec); cudaFree(s->halo); cudaFree(s->blist); cudaFree(s->plane); cudaFree(s->cellid); cudaFree(s->nbtmp);
   delete s;
   ctx->fill_state = nullptr;
 }
@@ -1318,8 +1330,9 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       s->cap_ntiles = ntiles;
     }
     if (p->gridn[3] > s->cap_ncell) {
-      cudaFree(s->nbflag); s->nbflag = nullptr; s->cap_ncell = 0;
+      cudaFree(s->nbflag); cudaFree(s->nbtmp); s->nbflag = s->nbtmp = nullptr; s->cap_ncell = 0;
       CX_CUDA(ctx, cudaMalloc(&s->nbflag, (size_t)p->gridn[3]));
+      CX_CUDA(ctx, cudaMalloc(&s->nbtmp, (size_t)p->gridn[3]));
       s->cap_ncell = p->gridn[3];
     }
     if (nbe > s->cap_rec) {
@@ -1335,7 +1348,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       CX_CUDA(ctx, cudaMalloc(&s->fs, sizeof(FsDesc) * (size_t)cnbe));
       s->cap_fs = cnbe;
     }
-    if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 8));
+    if (!s->count) CX_CUDA(ctx, cudaMalloc(&s->count, sizeof(int32_t) * 16));   // [0..1] tile list, [4..5] work counter, [6] halo flag, [8] nrest
     s->fpos_key = fpos_d; s->nbe = nbe; s->cnbe = cnbe; s->nw = nw; s->ntiles = ntiles;
     for (int k = 0; k < 3; k++) s->dimg[k] = dimg[k];
     CX_CUDA(ctx, cudaMemsetAsync(s->B, 0, sizeof(uint32_t) * (size_t)nw * 6, st));
@@ -1370,7 +1383,7 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
     A->sph2 = f * f;
   }
   A->lstep = fe_lstep(p, A->dimg);
-  A->nrest = s->count + 6;
+  A->nrest = s->count + 8;
   if (fresh) {
     if (nbe - cnbe > 0) {
       k_seg_cells<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(p->gridn[3], cell_idx_d, nbe - cnbe, s->cellid);
@@ -1383,7 +1396,11 @@ static int fill_prepare(cx_ctx *ctx, const cx_params *p, const uint32_t *fpos_d,
       k_fs_desc<<<cx_blocks(cnbe, 128), 128, 0, st>>>(*A, s->fs);
       CX_LAUNCH_CHECK(ctx, "k_fs_desc");
     }
-    k_cell3_flags<<<cx_blocks(p->gridn[3], 256, ctx->num_sms * 16), 256, 0, st>>>(*p, cell_idx_d, s->nbflag);
+    const int fgrid = cx_blocks(p->gridn[3], 256, ctx->num_sms * 16);
+    k_cell3_flags<<<fgrid, 256, 0, st>>>(*p, 2, cell_idx_d, nullptr, s->nbflag);
+    k_cell3_flags<<<fgrid, 256, 0, st>>>(*p, 1, cell_idx_d, s->nbflag, s->nbtmp);
+    k_cell3_flags<<<fgrid, 256, 0, st>>>(*p, 0, cell_idx_d, s->nbtmp, s->nbflag);
+    ctx->launches += 2;
     CX_LAUNCH_CHECK(ctx, "k_cell3_flags");
     if (nbe - cnbe > 0) {
       k_cell_planes<<<cx_blocks(nbe - cnbe, 256, ctx->num_sms * 16), 256, 0, st>>>(*A, s->nbflag);
@@ -1408,7 +1425,8 @@ static int fill_resolve(cx_ctx *ctx, FillArgs *A, FillState *s)
     k_block_list<<<lgrid, 256, 0, st>>>(A->p, A->nbflag, A->res_nparts, A->res_part, pass ? s->blist : nullptr, A->count64);
     CX_LAUNCH_CHECK(ctx, "k_block_list");
     if (pass == 0) {
-      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));   // + *nrest
+      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 30, A->count64, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CX_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 31, A->nrest, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
       CX_CUDA(ctx, cudaStreamSynchronize(st));
       A->nblist = ctx->h_mail[30];
       nrest = (int64_t)(ctx->h_mail[31] & 0xffffffffll);
