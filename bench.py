@@ -311,7 +311,7 @@ def main():
         fill_bytes = 0.25 * G + 8.0 * hp.nfluid + 48.0 * nbe + 16.0 * nvert + 4.0 * hp.ncell3
         key = "config%d" % args.config
         nv_ncu = NCU.get(key, {}).get("k_vert_volume", {}) if world == 1 and args.size is None else {}
-        nf_ncu = NCU.get(key, {}).get("k_resolve_blocks", {}) if world == 1 and args.size is None else {}
+        nf_ncu = NCU.get(key, {}).get("fill_resolve", {}) if world == 1 and args.size is None else {}
         sorted_gb = (16.0 * (nvert + nbe) + 36.0 * nbe) / 1e9
         line = {
             "metric": "end-to-end preprocess triangles/s (hot path)", "value": value, "unit": "triangles/s", "n_gpus": world,
@@ -336,12 +336,14 @@ def main():
                          "peak_source": "FFMA micro-kernel measured in this run (cx_measure_fp32_peak); nominal 148*128*2*1.965 GHz = 74.4",
                          "flops_per_vertex": VOXELS * T * FLOP_PER_VOXEL_TRI, "mean_trisize": T,
                          "hbm_frac": (hp.vv_bytes / (hp.vv_kernel_ms * 1e-3) / 1e9) / hbm_peak if hp.vv_bytes else None},
-            "roofline_fill": {"kernel": "whole geometry fill (k_resolve_blocks + k_fill_tiles rounds)", "bound": "hbm",
+            "roofline_fill": {"kernel": "whole geometry fill (k_seg_prep, k_resolve_cross + k_resolve_inplane, k_fill_tiles rounds)", "bound": "hbm",
                               "achieved": fill_bytes / (fill_ms * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s", "frac": fill_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak,
                               "traffic": nf_ncu.get("dram_bytes"), "peak_source": hbm_src, "bytes": fill_bytes,
-                              "frac_note": "SURVEY.md §8d bytes (0.25 B/cell + 8 B/filled cell + one pass over the geometry); the fill is bound by "
-                                           "the directed tests near walls (ALU) and the latency of the propagation rounds, not by HBM"},
+                              "issue_slot_frac": nf_ncu.get("issue_slot_frac"), "resolve_ms_under_ncu": nf_ncu.get("duration_ms_under_ncu"),
+                              "frac_note": "SURVEY.md §8d bytes (0.25 B/cell + 8 B/filled cell + one pass over the geometry); traffic = DRAM bytes of "
+                                           "the directed tests and their preparation (ncu).  The fill is bound by the latency of the propagation "
+                                           "rounds and the directed tests near walls (instruction issue), not by HBM"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu and world == 1:

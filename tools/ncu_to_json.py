@@ -7,7 +7,8 @@ quotes beside the live timings (`roofline.traffic`, `issue_slot_frac`, `instr_pe
 PASSES = passes of the hot path in the report (tools/profile_pass.py runs two: set-up + one step); figures are per pass.
 
 Kernels are grouped by the C-ABI call they belong to: "k_vert_volume" = everything cx_calc_vert_volume launches (k_vv_adj_*,
-k_vv_fans, k_vv_rows<AX>, k_vv_lines<AX>, k_vert_volume), "k_resolve_blocks" = the directed tests of the geometry fill.  Issue-slot
+k_vv_fans, k_vv_rows<AX>, k_vv_lines<AX>, k_vert_volume), "fill_resolve" = the directed tests of the geometry fill with their
+preparation (k_seg_*, k_cell*, k_block_list, k_resolve_*), "fill_flood" = the propagation rounds.  Issue-slot
 and pipe fractions are duration-weighted means over the group's launches."""
 import csv
 import io
@@ -16,7 +17,9 @@ import os
 import subprocess
 import sys
 
-GROUPS = {"k_vert_volume": ("k_vv_", "k_vert_volume"), "k_resolve_blocks": ("k_resolve_blocks",)}
+GROUPS = {"k_vert_volume": ("k_vv_", "k_vert_volume"),
+          "fill_resolve": ("k_resolve_", "k_seg_prep", "k_seg_cells", "k_cell3_flags", "k_cell_planes", "k_block_list"),
+          "fill_flood": ("k_fill_tiles", "k_build_list")}
 
 
 def num(x):
