@@ -119,6 +119,7 @@ struct FillArgs {
   uint8_t *act_cur, *act_next;  // tile activation flags
   int32_t *list;                // active tile list
   int32_t *count;               // [0] = list length, [1] = cursor
+  int32_t *count_next;          // the pair of the next propagation round (zeroed by k_fill_tiles of this round)
   unsigned long long *count64;  // work counter of the up-front resolve
   unsigned long long *changed;  // newly set cells
   int res_nparts, res_part;     // up-front resolve: 3dr-cell chunks dealt to nparts ranks, this rank resolves its share (0/1: all)
@@ -1184,14 +1185,17 @@ __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
 {
   __shared__ TileSM S;
   __shared__ int s_t;
+  __shared__ int s_face[6];   // new cells on the face towards -x, +x, -y, +y, -z, +z: only those neighbours see a change
   const int tid = threadIdx.x;
   const int ly = tid % FT_Y, lz = tid / FT_Y;
+  if (blockIdx.x == 0 && tid < 2) A.count_next[tid] = 0;   // list length and cursor of the NEXT round (the two pairs alternate)
   for (;;) {
     if (tid == 0) {
       const int q = atomicAdd(&A.count[1], 1);
       s_t = q < A.count[0] ? A.list[q] : -1;
       S.newbits = 0;
     }
+    if (tid < 6) s_face[tid] = 0;
     __syncthreads();
     const int tile = s_t;
     if (tile < 0) break;
@@ -1246,18 +1250,27 @@ __global__ void __launch_bounds__(FT_THREADS) k_fill_tiles(FillArgs A)
     // ---- write back + activate neighbours
     const uint32_t f_end = S.F[lz + 1][ly + 1];
     if (owned && f_end != f_start) {
+      const uint32_t nb = f_end & ~f_start;
       A.F[wi] = f_end;
-      atomicAdd(&S.newbits, __popc(f_end & ~f_start));
+      atomicAdd(&S.newbits, __popc(nb));
+      // a neighbouring tile reads this tile's face only (6-connectivity): bit 0 / bit 31 of the word, first / last row in y and z
+      if (nb & 1u) s_face[0] = 1;
+      if (nb >> 31) s_face[1] = 1;
+      if (ly == 0) s_face[2] = 1;
+      if (ly == FT_Y - 1) s_face[3] = 1;
+      if (lz == 0) s_face[4] = 1;
+      if (lz == FT_Z - 1) s_face[5] = 1;
     }
     __syncthreads();
     if (tid == 0 && S.newbits) atomicAdd(A.changed, (unsigned long long)S.newbits);
     if (tid == 0 && (S.newbits || A.force_activate)) {
-      if (wx > 0) A.act_next[tile - 1] = 1;
-      if (wx + 1 < A.wr) A.act_next[tile + 1] = 1;
-      if (tyi > 0) A.act_next[tile - A.wr] = 1;
-      if (tyi + 1 < A.ty) A.act_next[tile + A.wr] = 1;
-      if (tzi > 0) A.act_next[tile - A.wr * A.ty] = 1;
-      if (tzi + 1 < A.tz) A.act_next[tile + A.wr * A.ty] = 1;
+      const bool all = A.force_activate != 0;
+      if (wx > 0 && (all || s_face[0])) A.act_next[tile - 1] = 1;
+      if (wx + 1 < A.wr && (all || s_face[1])) A.act_next[tile + 1] = 1;
+      if (tyi > 0 && (all || s_face[2])) A.act_next[tile - A.wr] = 1;
+      if (tyi + 1 < A.ty && (all || s_face[3])) A.act_next[tile + A.wr] = 1;
+      if (tzi > 0 && (all || s_face[4])) A.act_next[tile - A.wr * A.ty] = 1;
+      if (tzi + 1 < A.tz && (all || s_face[5])) A.act_next[tile + A.wr * A.ty] = 1;
     }
     __syncthreads();
   }
@@ -1492,8 +1505,11 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int max_rounds, i
   for (;;) {
     const int batch = max_rounds > 0 ? max_rounds : 4;
     for (int r = 0; r < batch; r++) {
-      k_round_prep<<<1, 1, 0, st>>>(A->count);
-      CX_LAUNCH_CHECK(ctx, "k_round_prep");
+      if (rounds == 0) {   // later rounds find their pair zeroed by the k_fill_tiles before them
+        A->count = s->count; A->count_next = s->count + 2;
+        k_round_prep<<<1, 1, 0, st>>>(A->count);
+        CX_LAUNCH_CHECK(ctx, "k_round_prep");
+      }
       k_build_list<<<cx_blocks(A->ntiles, 256, ctx->num_sms * 8), 256, 0, st>>>(*A);
       CX_LAUNCH_CHECK(ctx, "k_build_list");
       A->force_activate = (rounds == 0);
@@ -1502,13 +1518,15 @@ static int fill_rounds(cx_ctx *ctx, FillArgs *A, FillState *s, int max_rounds, i
       std::swap(A->act_cur, A->act_next);
       s->act_swapped ^= 1;
       rounds++;
+      std::swap(A->count, A->count_next);   // the pair of the round just launched is now A->count_next
     }
     if (max_rounds > 0) break;
-    CX_CUDA(ctx, cudaMemcpyAsync(hcount, A->count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CX_CUDA(ctx, cudaMemcpyAsync(hcount, A->count_next, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CX_CUDA(ctx, cudaStreamSynchronize(st));
     if (hcount[0] == 0) break;  // the last round of the batch found no active tile
     if (rounds > 4000000) return cx_fail(ctx, CX_INTERNAL_ERROR, "fill: round limit");
   }
+  std::swap(A->count, A->count_next);   // callers read the number of tiles the last round found active from A->count[0]
   if (rounds_out) *rounds_out = rounds;
   return CX_OK;
 }
