@@ -1721,14 +1721,14 @@ extern "C" int cx_dist_set_fill_mode(cx_ctx *ctx, int mode)
 
 // ================================================================================================ multi-GPU geometry fill
 // fill_fluid_complex to its fixed point over all ranks of the context's communicator (the loop of crixus.cu:934-947, sharded):
-//   1. every rank resolves its share of the directed tests (3dr-cell chunks dealt round-robin with a rotation: balanced,
-//      unlike z-slabs whose floor and lid hold whole walls);
-//   2. small lattices (blocked planes <= CX_DIST_SMALL_BYTES or fewer than 2 planes per rank): the planes are all-reduced and
-//      every rank floods the whole lattice -- no halo exchange, no per-sweep collective;
-//      large lattices: each blocked plane range is REDUCED to the rank that owns the z-slab (a reduce-scatter with unequal
-//      parts), every rank floods its slab for CX_DIST_FILL_ROUNDS rounds, boundary planes (row-aligned words) go to the
-//      z-neighbours, and one all-reduce of two counters decides termination; finally the owned planes are all-gathered
-//      (grouped broadcasts) and packed into the reference's bit order on every rank.
+//   small lattices (blocked planes <= CX_DIST_SMALL_BYTES or fewer than 2 planes per rank): every rank resolves its share of
+//      the directed tests (3dr-cell chunks dealt round-robin with a rotation), the planes are all-reduced and every rank floods
+//      the whole lattice -- no halo exchange, no per-sweep collective;
+//   large lattices: every rank resolves the directed tests of the z-slab it floods (the blocked bits of a cell live with the
+//      cell: no merge.  The floor and lid slabs hold whole walls, but with the record-driven kernels the whole stage costs
+//      milliseconds, and dealing would make every rank enumerate every segment), floods its slab for CX_DIST_FILL_ROUNDS rounds,
+//      boundary planes (row-aligned words) go to the z-neighbours, and one all-reduce of two counters decides termination;
+//      finally the owned planes are all-gathered (grouped broadcasts) and packed into the reference's bit order on every rank.
 // k_flags: [0] = this rank still has work (active tiles or fresh halo bits)
 __global__ void k_dist_flags(const int32_t *count, const int *fresh, const unsigned long long *changed, long long *out)
 {
@@ -1749,17 +1749,24 @@ extern "C" int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *
   if (seed >= dimg[0] * dimg[1] * dimg[2]) return cx_fail(ctx, CX_SEED_OUTSIDE, "fill: seed outside the lattice");
   cudaStream_t st = ctx->stream;
   uint32_t *B = nullptr;
-  int64_t bwords = 0;
-  int rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], world, rank, &B, &bwords);
+  int64_t bwords = 6 * (int64_t)((dimg[0] + 31) / 32) * dimg[1] * dimg[2];
+  bool small = (size_t)bwords * sizeof(uint32_t) <= CX_DIST_SMALL_BYTES || dimg[2] < 2 * world;
+  if (ctx->dist_fill_mode == 2 && dimg[2] >= 2 * world) small = false;   // cx_dist_set_fill_mode (tests, tuning)
+  if (ctx->dist_fill_mode == 1) small = true;
+  int64_t k0 = 0, k1 = dimg[2];
+  int rc;
+  if (small) rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, dimg[2], world, rank, &B, &bwords);
+  else {
+    // the blocked bits of a cell live with the cell: a rank that resolves the planes it floods needs nothing from the others
+    cx_split_range(dimg[2], world, rank, &k0, &k1);
+    rc = resolve_share(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, k0, k1, 1, 0, &B, &bwords);
+  }
   if (rc != CX_OK) return rc;
   FillArgs A;
   FillState *s = nullptr;
   rc = fill_prepare(ctx, p, fpos_d, norm_d, ep_d, pos_d, nbe, cnbe, cell_idx_d, 0, &A, &s);
   if (rc != CX_OK) return rc;
   CX_CUDA(ctx, cudaMemsetAsync(A.changed, 0, sizeof(int64_t), st));
-  bool small = (size_t)bwords * sizeof(uint32_t) <= CX_DIST_SMALL_BYTES || dimg[2] < 2 * world;
-  if (ctx->dist_fill_mode == 2 && dimg[2] >= 2 * world) small = false;   // cx_dist_set_fill_mode (tests, tuning)
-  if (ctx->dist_fill_mode == 1) small = true;
   int32_t rounds = 0;
   if (small) {
     rc = coll->allreduce_sum_u32(ctx, B, bwords);
@@ -1779,15 +1786,6 @@ extern "C" int cx_dist_fill_geometry(cx_ctx *ctx, const cx_params *p, uint32_t *
   // ---- z-slabs
   const int64_t wplane = (int64_t)A.wr * A.dimg[1];
   std::vector<CxSeg> segs;
-  for (int r = 0; r < world; r++) {
-    int64_t a, b;
-    cx_split_range(dimg[2], world, r, &a, &b);
-    for (int d = 0; d < 6; d++) segs.push_back({d * A.nw + wplane * a, wplane * (b - a), r});
-  }
-  rc = coll->reduce_segments_u32(ctx, B, segs.data(), (int)segs.size());
-  if (rc != CX_OK) return rc;
-  int64_t k0, k1;
-  cx_split_range(dimg[2], world, rank, &k0, &k1);
   A.k_lo = (int)k0; A.k_hi = (int)k1;
   if (wplane > s->cap_halo) {
     cudaFree(s->halo); s->halo = nullptr; s->cap_halo = 0;

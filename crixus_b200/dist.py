@@ -8,8 +8,9 @@ device-resident workload for bench.py.  What shards and what does not (DESIGN.md
     all-gather of their outputs over NVLink would move more bytes than recomputing them, so every rank runs them on the full
     (replicated) mesh -- identical results on every rank because the binning order is stable.
   * calc_vert_volume (FP32-ALU bound, ~90 % of the time): interleaved 1024-vertex chunks, volumes all-reduced (4 B/vertex).
-  * geometry fill: directed tests dealt by 3dr-cell chunk, blocked planes reduced to the z-slab owners, slab floods with halo
-    exchange, owned planes all-gathered.  Bit-exact across rank counts by the fixed-point property of the fill.
+  * geometry fill: large lattices -- every rank resolves the directed tests of the z-slab it floods (no merge), slab floods
+    with halo exchange, owned planes all-gathered; small lattices -- directed tests dealt by 3dr-cell chunk, blocked planes
+    all-reduced, flood replicated.  Bit-exact across rank counts by the fixed-point property of the fill.
 
 The pure partition helpers below restate the library's sharding rules; they are tested on CPU with gloo (world_size 2 and 3,
 the CPU oracle as the compute backend, tests/test_dist.py) -- the same rules the C++ code follows (csrc/dist.h cx_split_range,
@@ -207,7 +208,7 @@ class ShardedHotPath:
             "one process per GPU, NCCL inside the C-ABI (cx_dist_*); vert-volume: interleaved %d-vertex chunks over %d ranks + all-reduce; "
             "fill: %s; cheap stages and device weld replicated"
             % (VV_CHUNK, world, ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes all-reduced, flood replicated" % world) if small else
-               ("directed tests dealt to %d ranks by 3dr-cell chunk, blocked planes reduced to the slab owners, flood in %d z-slabs with a "
+               ("z-slabs: each of the %d ranks resolves the directed tests of the planes it floods (no merge), flood in %d z-slabs with a "
                 "halo exchange over NCCL send/recv every %d rounds, owned planes all-gathered" % (world, world, FILL_ROUNDS_PER_EXCHANGE))))
         self.events, self.nfluid, self.fill_rounds = [], 0, 0
         self._sizes = None
@@ -298,7 +299,7 @@ class ShardedHotPath:
             seed = api.seed_index(p, f[1])
             if self.world == 1:
                 nfl += ctx.fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
-            else:   # dealt directed tests, reduce to slab owners, slab floods + halo exchange, all-gather: cx_dist_fill_geometry
+            else:   # slab-owned directed tests, slab floods + halo exchange, all-gather: cx_dist_fill_geometry
                 nfl += ctx.dist_fill_geometry(p, self.fpos, gn, ge, gp, fnbe, self.cnbe, self.cell_idx, seed)
             rounds += ctx.last_rounds
         self.nfluid, self.fill_rounds = int(nfl), int(rounds)
