@@ -57,9 +57,10 @@ def main():
           "# where the index allows).  calc_vert_volume's per-vertex working set is <= 3 KB (160 B per fan triangle + two 41-word masks):\n"
           "# the phase kernels hand it through HBM scratch and each warp copies ITS vertex's 1 KB into shared memory with plain 16-byte\n"
           "# loads -- a bulk copy per warp of 4 warps per CTA would need an mbarrier per warp for a kilobyte; the kernels are bound by\n"
-          "# instruction issue (80 % of the slots), not by that copy (2 % of the call at the measured HBM bandwidth).  The fill's\n"
-          "# k_resolve_blocks is the kernel that stages segment tiles in shared memory (27-cell neighbourhoods per 3dr-cell, ballot +\n"
-          "# popc compaction of the records that survive a plane-distance test -- a data-dependent gather, not a box copy); the flood\n"
+          "# instruction issue (76-80 % of the slots), not by that copy (2 % of the call at the measured HBM bandwidth).  The fill's\n"
+          "# k_resolve_blocks (coarse dr) stages segment tiles in shared memory (27-cell neighbourhoods per 3dr-cell, ballot + popc\n"
+          "# compaction of the records that survive a plane-distance test -- a data-dependent gather, not a box copy); at fine dr\n"
+          "# k_resolve_cross / k_resolve_inplane read one 64-byte / 16-byte element per lane and keep everything else in registers; the flood\n"
           "# works on 1 x 16 x 16-word tiles (1 KB + halo) whose loads are single coalesced 4-byte words per thread.  BASELINE.json's\n"
           "# north_star waives tensor cores for this path (DESIGN.md sections 3.1, 3.2).")
 
