@@ -163,6 +163,8 @@ FE_FN void fe_axis_range(const cx_params *p, const FeRec *T, int c, float grow, 
   if (!(a > (float)cut_lo)) a = (float)cut_lo;             /* also takes NaN to the whole range */
   if (!(b < (float)(cut_hi - 1))) b = (float)(cut_hi - 1);
   int ia = (int)a, ib = (int)b;
+  ia = ia > cut_lo ? ia : cut_lo;             /* (float)(cut_hi - 1) may have rounded up on lattices of more than 2^24 planes */
+  ib = ib < cut_hi - 1 ? ib : cut_hi - 1;
   while (ia <= ib && fe_lat_pos(p, c, ia) < lob) ia++;
   while (ib >= ia && fe_lat_pos(p, c, ib) > hib) ib--;
   *lo = ia;

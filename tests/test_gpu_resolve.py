@@ -12,7 +12,7 @@ import cases
 from backends import CudaBackend
 from crixus_b200 import api
 from oracle import orc
-from test_resolve_enum import _scene
+from test_resolve_enum import _fuzz_scene, _scene
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +59,19 @@ def test_resolve_paths_agree(name):
     g = cases.run(B, c, stages=("fill",))
     assert g["nfluid"] == o["nfluid"] and g["fill_counts"] == o["fill_counts"]
     assert np.array_equal(g["fpos"], o["fpos"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_resolve_paths_agree_fuzz(seed):
+    """generated boxes (random size, orientation incl. a few eps off the lattice directions, offset from the origin, mesh width)
+    with stray triangles: both paths give the same blocked planes, the fill equals the oracle's"""
+    c = _fuzz_scene(seed)
+    o = cases.run(orc.Oracle(), c, stages=("fill",))
+    B = CudaBackend()
+    rec, blk = _planes(B, o, 0), _planes(B, o, 1)
+    assert torch.equal(rec, blk), "%d blocked words differ" % int((rec != blk).sum())
+    g = cases.run(B, c, stages=("fill",))
+    assert g["nfluid"] == o["nfluid"] and np.array_equal(g["fpos"], o["fpos"])
 
 
 def test_resolve_with_free_surface():

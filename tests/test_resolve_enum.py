@@ -101,6 +101,56 @@ def _scene(name):
     return c
 
 
+def _fuzz_scene(seed):
+    """a box of random size, orientation (every third one within a few eps of the lattice directions), position and mesh width,
+    plus a few free-floating triangles; dr and dr_wall drawn so that the distance test is dead"""
+    rng = np.random.default_rng(9000 + seed)
+    dr = float(rng.choice([0.05, 0.07, 0.1]))
+    h = dr * float(rng.choice([0.5, 0.8, 1.25]))
+    size = np.array([rng.integers(6, 12) * h for _ in range(3)])
+    v, t, n = mg.box_tank((0, 0, 0), tuple(size), h, inward=True)
+    if seed % 3 == 0:
+        ang = rng.uniform(-3e-4, 3e-4, 3)
+    elif seed % 3 == 1:
+        ang = rng.uniform(-0.6, 0.6, 3)
+    else:
+        ang = np.array([0.0, 0.0, rng.uniform(-0.5, 0.5)])     # z stays a lattice direction: capable walls off the lattice planes
+    R = _rot(0, ang[0]) @ _rot(1, ang[1]) @ _rot(2, ang[2])
+    shift = rng.uniform(-1, 1, 3) * float(rng.choice([0.0, 3.0, 400.0]))
+    v = (v.astype(np.float64) @ R.T + shift).astype(np.float32)
+    nrm = mg.geometric_normals(v, t)
+    nrm[(nrm * (v[t].mean(1) - v.mean(0))).sum(1) > 0] *= -1
+    tr = [v[t]]
+    nn = [nrm]
+    k = int(rng.integers(0, 12))
+    if k:
+        o = v.mean(0) + rng.uniform(-0.2, 0.2, (k, 3)) * size
+        a = rng.normal(size=(k, 3)); b = rng.normal(size=(k, 3))
+        extra = np.stack([o, o + a * h * rng.uniform(0.3, 1.5, (k, 1)), o + b * h * rng.uniform(0.3, 1.5, (k, 1))], 1).astype(np.float32)
+        tr.append(extra)
+        nn.append(mg.geometric_normals(extra.reshape(-1, 3), np.arange(3 * k, dtype=np.int32).reshape(-1, 3)))
+    tris = np.ascontiguousarray(np.concatenate(tr), dtype=np.float32)
+    ext = float((tris.reshape(-1, 3).max(0) - tris.reshape(-1, 3).min(0)).max())
+    c = dict(cases.case("cube"), tris=tris, normals=np.ascontiguousarray(np.concatenate(nn), dtype=np.float32), dr=np.float32(dr))
+    c["fills"] = [("geometry", tuple(float(x) for x in v.mean(0)), float(0.9 * np.sqrt(1e-5 * ext)))]
+    return c
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_candidates_cover_reference_fuzz(lib, seed):
+    c = _fuzz_scene(seed)
+    o = cases.run(orc.Oracle(), c, stages=("fill",))
+    p = o["params_fill"]
+    assert p.eps >= p.dr_wall * p.dr_wall
+    nwall = int(o["fnbe"] - o["cnbe"])
+    out = np.zeros(8, dtype=np.int64)
+    pos, norm, ep, ci = (np.ascontiguousarray(o[k]) for k in ("fposa", "fnorm", "fep", "cell_idx"))
+    assert lib.rec_enum_check(C.byref(p), pos.ctypes.data, norm.ctypes.data, ep.ctypes.data, nwall, ci.ctypes.data, out.ctypes.data, 1) == 0
+    print("fuzz %d: %d records (%d eligible), reference blocks %d triples; candidates: %d crossing, %d in-plane" % (seed, out[5], out[4], out[0], out[2], out[3]))
+    assert out[5] == nwall and out[4] > 0
+    assert out[1] == 0
+
+
 @pytest.mark.parametrize("name", ["cube", "cube_jitter", "sphere_tank", "channel", "cube_rot", "cube_tilt", "slivers", "cube_far", "tank_mm"])
 def test_candidates_cover_reference(lib, name):
     c = _scene(name)
