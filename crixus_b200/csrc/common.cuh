@@ -34,6 +34,9 @@ struct cx_ctx {
   // pinned staging of the streamed file writers (records.cu)
   void *pin_stage = nullptr;
   size_t pin_stage_bytes = 0;
+  // device staging of the raw STL normals of cx_preprocess_host (grow-only; they travel on the copy stream while the weld runs)
+  void *norm_stage = nullptr;
+  size_t norm_stage_bytes = 0;
   // multi-GPU: collective back-end of this rank (dist.h: NCCL communicator or in-process group); nullptr = single GPU
   void *dist = nullptr;
   int dist_fill_mode = 0;       // cx_dist_set_fill_mode: 0 = by lattice size, 1 = replicated flood, 2 = z-slab flood

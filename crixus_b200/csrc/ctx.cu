@@ -89,8 +89,21 @@ void cx_destroy(cx_ctx *ctx)
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   if (ctx->d_mail) cudaFree(ctx->d_mail);
   if (ctx->pin_stage) cudaFreeHost(ctx->pin_stage);
+  if (ctx->norm_stage) cudaFree(ctx->norm_stage);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+void *cx_internal_norm_stage(cx_ctx *ctx, size_t bytes)
+{
+  if (bytes > ctx->norm_stage_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->norm_stage) cudaFree(ctx->norm_stage);
+    ctx->norm_stage = nullptr; ctx->norm_stage_bytes = 0;
+    if (cudaMalloc(&ctx->norm_stage, bytes + bytes / 8) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->norm_stage_bytes = bytes + bytes / 8;
+  }
+  return ctx->norm_stage;
 }
 
 void *cx_internal_dev_arena(cx_ctx *ctx, size_t bytes)

@@ -30,6 +30,10 @@ struct CopyStream {   // second stream + event for the overlapped download; rele
   cudaEvent_t e = nullptr;
   ~CopyStream() { if (s) cudaStreamDestroy(s); if (e) cudaEventDestroy(e); }
 };
+struct NormEvent {    // "the normals are on the device"; released on every exit path
+  cudaEvent_t e = nullptr;
+  ~NormEvent() { if (e) cudaEventDestroy(e); }
+};
 struct Events {
   cudaEvent_t e[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ~Events() { for (int k = 0; k < 8; k++) if (e[k]) cudaEventDestroy(e[k]); }
@@ -92,6 +96,15 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
   int64_t nvert;
   float *w_corners = nullptr, *w_pos4 = nullptr;   // device temporaries of the weld (stream-ordered pool)
   int32_t *w_ep4 = nullptr;
+  // second stream: the normals follow the corners over PCIe while the bounding box and the weld run (into a staging buffer of
+  // the context -- the working set is laid out only once the weld has counted the vertices), and the geometry arrays go back
+  // while calc_vert_volume and the fills run
+  CopyStream cs;
+  CU(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&cs.e, cudaEventDisableTiming));
+  NormEvent ev_norm;
+  float *w_norm3 = nullptr;
+  const int64_t per_n = (nbe + world - 1) / world;   // normals: uploaded in N pieces like the corners
   if (job->welded_pos) {  // the mesh as crixus_main holds it right before the upload (crixus.cu:225-245)
     nvert = job->welded_nvert;
     for (int k = 0; k < 3; k++) { bbmin[k] = job->bbmin[k]; bbmax[k] = job->bbmax[k]; }
@@ -104,8 +117,19 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
     CU(cudaMallocAsync((void **)&w_corners, 36 * (size_t)(per * world), st));
     CU(cudaMallocAsync((void **)&w_pos4, 48 * (size_t)nbe, st));
     CU(cudaMallocAsync((void **)&w_ep4, 16 * (size_t)nbe, st));
+    w_norm3 = (float *)cx_internal_norm_stage(ctx, 12 * (size_t)(per_n * world));
+    if (!w_norm3) return CX_CUDA_ERROR;
     if (t_hi > t_lo)
       CU(cudaMemcpyAsync(w_corners + 9 * t_lo, job->corners + 9 * t_lo, 36 * (size_t)(t_hi - t_lo), cudaMemcpyHostToDevice, st));
+    {
+      CU(cudaEventRecord(cs.e, st));              // behind the corners, and behind whatever read the staging buffer last
+      CU(cudaStreamWaitEvent(cs.s, cs.e, 0));
+      const int64_t n_lo = std::min(nbe, per_n * rank), n_hi = std::min(nbe, per_n * (rank + 1));
+      if (n_hi > n_lo)
+        CU(cudaMemcpyAsync(w_norm3 + 3 * n_lo, job->normals + 3 * n_lo, 12 * (size_t)(n_hi - n_lo), cudaMemcpyHostToDevice, cs.s));
+      CU(cudaEventCreateWithFlags(&ev_norm.e, cudaEventDisableTiming));
+      CU(cudaEventRecord(ev_norm.e, cs.s));
+    }
     if (world > 1) RC(cx_internal_allgather(ctx, w_corners, 36 * per));
     RC(cx_bbox_device(ctx, w_corners, 3 * nbe, bbmin, bbmax));
     RC(cx_check_triangle_size(ctx, w_corners, nbe, dr, &job->tri_failed, &job->tri_mind, &job->tri_maxd));
@@ -139,8 +163,7 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
   pre_surf.off = db.take(4 * (size_t)nbe); surf.off = db.take(4 * (size_t)nbe);
   cell_idx.off = db.take(4 * (size_t)(ncell + 1)); trisize.off = db.take(4 * (size_t)nvert);
   vol.off = db.take(4 * (size_t)nvert); newlink.off = db.take(4 * (size_t)nvert);
-  const int64_t per_n = (nbe + world - 1) / world;   // normals: uploaded in N pieces like the corners
-  norm3.off = db.take(12 * (size_t)(per_n * world)); fpos.off = db.take(4 * (size_t)nwords);
+  norm3.off = db.take(w_norm3 ? 0 : 12 * (size_t)(per_n * world)); fpos.off = db.take(4 * (size_t)nwords);
   if (fsn) {
     fnorm.off = db.take(16 * (size_t)(nbe + fsn)); fep.off = db.take(16 * (size_t)(nbe + fsn));
     fposv.off = db.take(16 * (size_t)(nvert + 3 * fsn));
@@ -166,13 +189,17 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
     CU(cudaFreeAsync(w_pos4, st));
     CU(cudaFreeAsync(w_ep4, st));
   }
-  {
+  if (w_norm3) {   // uploaded behind the corners (above)
+    CU(cudaStreamWaitEvent(st, ev_norm.e, 0));
+    if (world > 1) RC(cx_internal_allgather(ctx, w_norm3, 12 * per_n));
+    RC(cx_internal_expand3(ctx, w_norm3, pre_norm.as<float>(), nbe));
+  } else {
     const int64_t n_lo = std::min(nbe, per_n * rank), n_hi = std::min(nbe, per_n * (rank + 1));
     if (n_hi > n_lo)
       CU(cudaMemcpyAsync(norm3.as<float>() + 3 * n_lo, job->normals + 3 * n_lo, 12 * (size_t)(n_hi - n_lo), cudaMemcpyHostToDevice, st));
     if (world > 1) RC(cx_internal_allgather(ctx, norm3.p, 12 * per_n));
+    RC(cx_internal_expand3(ctx, norm3.as<float>(), pre_norm.as<float>(), nbe));
   }
-  RC(cx_internal_expand3(ctx, norm3.as<float>(), pre_norm.as<float>(), nbe));
   CU(cudaMemsetAsync(trisize.p, 0, 4 * (size_t)nvert, st));
   CU(cudaMemsetAsync(vol.p, 0, 4 * (size_t)nvert, st));
   CU(cudaMemsetAsync(fpos.p, 0, 4 * (size_t)nwords, st));
@@ -207,9 +234,6 @@ static int preprocess_impl(cx_ctx *ctx, cx_job *job, bool dist)
   // while calc_vert_volume and the fills run
   job->pos = (float *)(hbase + o_pos); job->norm = (float *)(hbase + o_norm); job->ep = (int32_t *)(hbase + o_ep);
   job->surf = (float *)(hbase + o_surf); job->cell_idx = (int32_t *)(hbase + o_cell);
-  CopyStream cs;
-  CU(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&cs.e, cudaEventDisableTiming));
   CU(cudaEventRecord(cs.e, st));
   CU(cudaStreamWaitEvent(cs.s, cs.e, 0));
   cudaStream_t cst = cs.s;

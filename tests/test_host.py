@@ -121,6 +121,7 @@ def test_null_context_is_rejected_without_a_gpu(cxlib):
     assert cxlib.cx_write_split_records(z, 3, 0, 1, b"x", 1) == -11
     assert cxlib.cx_write_split_records(z, 0, 0, 0, b"x", 1) == -11
     assert cxlib.cx_fill_geometry_slab(z, ctypes.byref(p), z, z, z, z, 0, 0, z, 0, 0, 1, 2, ctypes.byref(n), None) == -11
+    assert cxlib.cx_fill_set_resolve_mode(z, 0) == -11
 
 
 def test_host_glue_fuzz_against_oracle(oracle, cxlib):
