@@ -120,3 +120,77 @@ int64_t rec_enum_check(const orc_params *op, const float *pos, const float *norm
   free(mark);
   return 0;
 }
+
+/* The "remembered plane" of k_resolve_inplane: a segment j is skipped when a plane with the same normal bits and an offset within
+ * `tol` x eps of its own (tol = 0.5 per lane; 0.75 through the per-cell summaries) has all the cells of ITS 2-eps mask blocked.
+ * That is sound if every cell the reference puts in the plane of j (|a| < eps with the reference's arithmetic, crixus_d.cu:757,766)
+ * is in the 2-eps mask of that other plane i, computed the way the kernel computes it (fe_plane_offset, lattice positions relative
+ * to the lattice origin).  Checked here for every pair (i, j) of eligible capable segments of the same or neighbouring 3dr-cells.
+ * out: [0] pairs within the tolerance  [1] in-plane cells of j looked at  [2] of those outside i's mask (must be 0) */
+int64_t plane_cache_check(const orc_params *op, const float *pos, const float *norm, const int32_t *ep, int64_t nwall,
+                          const int32_t *cell_idx, double tol, int64_t *out)
+{
+  const cx_params *p = (const cx_params *)op;
+  if (!(op->eps >= op->dr_wall * op->dr_wall)) return -1;
+  int64_t dimg[3];
+  orc_fill_dims(op, dimg);
+  const int dim[3] = {(int)dimg[0], (int)dimg[1], (int)dimg[2]};
+  const float lstep = fe_lstep(p, dim);
+  out[0] = out[1] = out[2] = 0;
+  /* eligible capable segments with their planes */
+  int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nwall + 1));
+  float *dd = (float *)malloc(sizeof(float) * (size_t)(nwall + 1));
+  int *cellof = (int *)malloc(sizeof(int) * (size_t)(nwall + 1));
+  int64_t m = 0;
+  for (int64_t c = 0; c < op->gridn[3]; c++) {
+    int g3[3];
+    fe_cell_coords(p, (int)c, g3);
+    for (int64_t i = cell_idx[c]; i < cell_idx[c + 1] && i < nwall; i++) {
+      const float *n = norm + 4 * i;
+      const float *v0 = pos + 4 * (int64_t)ep[4 * i], *v1 = pos + 4 * (int64_t)ep[4 * i + 1], *v2 = pos + 4 * (int64_t)ep[4 * i + 2];
+      float u[3], v[3];
+      for (int j = 0; j < 3; j++) { u[j] = v1[j] - v0[j]; v[j] = v2[j] - v0[j]; }
+      const float uu = dot_r3(u, u), uv = dot_r3(u, v), vv = dot_r3(v, v);
+      if (fe_classify(n, u, v, det_r2(uv, uv, uu, vv)) != 2) continue;
+      FeRec T;
+      fe_rec_setup(p, lstep, n, v0, v1, v2, uu, vv, g3, &T);
+      if (!T.safe || !fe_capable(p, lstep, n)) continue;
+      idx[m] = i; dd[m] = fe_plane_offset(p, n, v0); cellof[m] = (int)c; m++;
+    }
+  }
+  const int reach = 6 + (int)ceilf(op->dr_wall / op->dr);
+  for (int64_t a = 0; a < m; a++)
+    for (int64_t b = 0; b < m; b++) {
+      const float *ni = norm + 4 * idx[a], *nj = norm + 4 * idx[b];
+      if (!(ni[0] == nj[0] && ni[1] == nj[1] && ni[2] == nj[2])) continue;
+      if (!(fabs((double)dd[a] - (double)dd[b]) < tol * op->eps)) continue;
+      int ga[3], gb[3], near = 1;
+      fe_cell_coords(p, cellof[a], ga); fe_cell_coords(p, cellof[b], gb);
+      for (int k = 0; k < 3; k++) if (abs(ga[k] - gb[k]) > 2) near = 0;
+      if (!near) continue;
+      out[0]++;
+      const float *v0 = pos + 4 * (int64_t)ep[4 * idx[b]];
+      for (int sk = 0; sk < dim[2]; sk++) {
+        const int ck = (int)floor(((double)v0[2] - op->fcmin[2]) / op->dr);
+        if (abs(sk - ck) > reach) continue;
+        for (int sj = 0; sj < dim[1]; sj++) {
+          const int cj = (int)floor(((double)v0[1] - op->fcmin[1]) / op->dr);
+          if (abs(sj - cj) > reach) continue;
+          for (int si = 0; si < dim[0]; si++) {
+            const int ci = (int)floor(((double)v0[0] - op->fcmin[0]) / op->dr);
+            if (abs(si - ci) > reach) continue;
+            const float s[3] = {fe_lat_pos(p, 0, si), fe_lat_pos(p, 1, sj), fe_lat_pos(p, 2, sk)};
+            float w0[3];
+            for (int k = 0; k < 3; k++) w0[k] = s[k] - v0[k];
+            const float aj = -dot_r3(nj, w0);                  /* the reference's a for segment j */
+            if (!(fabsf(aj) < op->eps)) continue;
+            out[1]++;
+            const float q[3] = {s[0] - p->fcmin[0], s[1] - p->fcmin[1], s[2] - p->fcmin[2]};
+            if (!(fabsf(q[0] * ni[0] + q[1] * ni[1] + q[2] * ni[2] - dd[a]) < 2.0f * op->eps)) out[2]++;   /* i's mask, as the kernel */
+          }
+        }
+      }
+    }
+  free(idx); free(dd); free(cellof);
+  return 0;
+}

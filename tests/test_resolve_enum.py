@@ -31,6 +31,8 @@ def lib():
     L = C.CDLL(so)
     L.rec_enum_check.restype = C.c_int64
     L.rec_enum_check.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    L.plane_cache_check.restype = C.c_int64
+    L.plane_cache_check.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p]
     return L
 
 
@@ -169,3 +171,49 @@ def test_candidates_cover_reference(lib, name):
     assert nrec == nwall
     assert blocked > 0 and nelig > 0
     assert missed == 0
+
+
+def _layered_scene(offset, far):
+    """a z-wall in a lattice plane and copies of it moved along the normal by fractions of eps (eps = 1e-5 x extent): planes with
+    the same normal bits whose offsets differ by less than the tolerance of the remembered plane -- and by more"""
+    v, t, n = mg.box_tank((0, 0, 0), (1, 1, 1), 0.1, inward=True)
+    tris, nrm = v[t], n
+    floor = np.abs(tris[:, :, 2]).max(1) < 1e-6
+    eps = 1e-5 * 1.0
+    layers = [tris]
+    norms = [nrm]
+    for f in offset:
+        lay = tris[floor].copy()
+        lay[:, :, 2] += np.float32(f * eps)
+        layers.append(lay)
+        norms.append(nrm[floor])
+    tris = np.concatenate(layers).astype(np.float32)
+    if far:
+        tris = tris + np.array([300.0, -200.0, 100.0], dtype=np.float32)
+    c = dict(cases.case("cube"), tris=np.ascontiguousarray(tris), normals=np.ascontiguousarray(np.concatenate(norms), dtype=np.float32),
+             dr=np.float32(0.1))
+    ctr = tris.reshape(-1, 3).mean(0)
+    c["fills"] = [("geometry", tuple(float(x) for x in ctr), float(0.9 * np.sqrt(1e-5)))]
+    return c
+
+
+@pytest.mark.parametrize("far", [False, True])
+def test_remembered_plane_is_sound(lib, far):
+    """k_resolve_inplane skips a segment whose plane is within eps / 2 (3 eps / 4 through the per-cell summaries) of a finished plane
+    with the same normal bits: every cell the reference puts in the skipped segment's plane must be in the finished plane's
+    2-eps mask -- also far from the coordinate origin, where one ulp of a coordinate is a third of eps"""
+    c = _layered_scene([0.2, 0.45, 0.7, 1.1, 2.3, -0.3, -0.74], far)
+    o = cases.run(orc.Oracle(), c, stages=("fill",))
+    p = o["params_fill"]
+    nwall = int(o["fnbe"] - o["cnbe"])
+    pos, norm, ep, ci = (np.ascontiguousarray(o[k]) for k in ("fposa", "fnorm", "fep", "cell_idx"))
+    for tol in (0.5, 0.75):
+        out = np.zeros(3, dtype=np.int64)
+        assert lib.plane_cache_check(C.byref(p), pos.ctypes.data, norm.ctypes.data, ep.ctypes.data, nwall, ci.ctypes.data, tol, out.ctypes.data) == 0
+        print("far=%s tol=%.2f: %d plane pairs, %d in-plane cells, %d outside the other mask" % (far, tol, out[0], out[1], out[2]))
+        assert out[0] > 0 and out[1] > 0
+        assert out[2] == 0
+    # the check has teeth: with a tolerance of 3 eps the layer at 2.3 eps would vouch for the one at 0.2 eps, and the inclusion fails
+    out = np.zeros(3, dtype=np.int64)
+    lib.plane_cache_check(C.byref(p), pos.ctypes.data, norm.ctypes.data, ep.ctypes.data, nwall, ci.ctypes.data, 3.0, out.ctypes.data)
+    assert out[2] > 0
